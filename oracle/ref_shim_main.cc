@@ -1,0 +1,236 @@
+// TEST INFRASTRUCTURE ONLY (oracle/): C-ABI shim that sets the reference up
+// exactly the way its own `main` does and exposes per-task objects so that
+// tests / the CPU-baseline leg can (1) harvest the raw inputs the DP kernels
+// consume (sequence codes, SGPT2 splice-signal table, frozen parameters) and
+// (2) run the reference's own kernels on them.
+//
+// The reference's start-up code (option parser, defaults, SetUpPwd) is a set
+// of file-static functions in src/spaln.cc, so this TU includes that file by
+// path (never copied) with `main` renamed.  See oracle/Makefile.
+
+// system headers first: the reference overloads fclose() for gzFile, which
+// breaks glibc attribute checks if <wchar.h> is first seen afterwards
+#include <string>
+#include <vector>
+#include <cwchar>
+
+#define main spaln_reference_main_unused
+#include "spaln.cc"
+#undef main
+
+extern "C" {
+int shim_s1_kernel(const Seq** seqs, const PwdB* pwd, int lw, int up,
+	int kind, int n_imd, int mode, int* score, int* skl_out, int cap,
+	int* cpos_out, double* seconds);
+int shim_s1_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up,
+	int* score, int* skl_out, int cap, double* seconds);
+int shim_s1_nelem();
+}
+
+namespace {
+PwdB*	g_pwd = 0;
+std::vector<std::string> g_args;
+
+struct RefTask {
+	Seq*	sqs[4];
+};
+}
+
+extern "C" {
+
+// optstr: the spaln command-line options, blank separated, e.g.
+// "-Q0 -A2 -S1 -yX0 -TDictyost".  genome_fa / query_fa: any DNA FASTA pair,
+// only used for molecule-type inference exactly as main() does
+// (src/spaln.cc:1496-1501,1588-1603).
+int ref_setup(const char* optstr, const char* genome_fa, const char* query_fa)
+{
+	if (g_pwd) return 1;
+	g_args.clear();
+	g_args.push_back("spaln");
+	std::string s(optstr? optstr: "");
+	size_t p = 0;
+	while (p < s.size()) {
+	    while (p < s.size() && isspace(s[p])) ++p;
+	    size_t q = p;
+	    while (q < s.size() && !isspace(s[q])) ++q;
+	    if (q > p) g_args.push_back(s.substr(p, q - p));
+	    p = q;
+	}
+	g_args.push_back(genome_fa);
+	g_args.push_back(query_fa);
+	std::vector<const char*> argv;
+	for (auto& a : g_args) argv.push_back(a.c_str());
+	int argc = (int) argv.size();
+
+	setdefparam();
+	optimize(GLOBAL, MAXIMUM);
+	int n = getoption(argc, argv.data());
+	spb_fact();
+	(void) n;
+	thread_num = 0;
+	if (!algmode.mlt) OutPrm.MaxOut = 1;
+	if (OutPrm.MaxOut > OutPrm.MaxOut2) OutPrm.MaxOut2 = OutPrm.MaxOut;
+	Seq*	seqs[3];
+	initseq(seqs, 3);
+	if (!seqs[1]->getseq(genome_fa)) return -1;
+	if (!seqs[0]->getseq(query_fa)) return -2;
+	g_pwd = SetUpPwd(seqs);
+	b_intr = seqs[1]->inex.intr;
+	if (seqs[0]->inex.intr || seqs[1]->inex.intr) makeStdSig53();
+	clearseq(seqs, 3);
+	return 0;
+}
+
+int ref_nelem() { return shim_s1_nelem(); }
+
+// frozen parameter block (all int32).  Layout documented in
+// tests/ref_harness.py::PARAM_FIELDS.
+int ref_get_params(int* out, int cap, int* simmtx_out, int simmtx_cap)
+{
+	if (!g_pwd) return -1;
+	int k = 0;
+	const PwdB* p = g_pwd;
+	int vals[] = {
+	    p->DvsP, p->Noll, (int) p->Vab, (int) p->Vthr,
+	    (int) p->BasicGOP, (int) p->BasicGEP, (int) p->LongGOP, (int) p->LongGEP,
+	    p->codonk1,
+	    p->IntPen? (int) p->IntPen->Penalty(): 0,
+	    IntronPrm.llmt, IntronPrm.mu, IntronPrm.rlmt, IntronPrm.minl,
+	    IntronPrm.maxl, IntronPrm.mode, IntronPrm.nquant,
+	    (int) algmode.alg, (int) algmode.lcl, (int) algmode.lsg,
+	    (int) algmode.any, (int) algmode.qck,
+	    (int) alprm.sh, (int) alprm.ubh, (int) alprm.scale,
+	    (int) p->simmtx->AvTrc(), p->simmtx->dim, MaxVmfSpace,
+	    (int) p->GapPenalty(1), ref_nelem()
+	};
+	int nv = sizeof(vals) / sizeof(int);
+	for (int i = 0; i < nv && k < cap; ++i) out[k++] = vals[i];
+	// quantile table (len, pen) x nquant
+	for (int j = 0; j < IntronPrm.nquant && p->IntPen && p->IntPen->qm; ++j) {
+	    if (k + 2 > cap) break;
+	    out[k++] = p->IntPen->qm[j].len;
+	    out[k++] = p->IntPen->qm[j].pen;
+	}
+	int d = p->simmtx->dim;
+	if (simmtx_out && simmtx_cap >= d * d)
+	    for (int i = 0; i < d; ++i)
+		for (int j = 0; j < d; ++j)
+		    simmtx_out[i * d + j] = p->simmtx->mtx[i][j];
+	return k;
+}
+
+// build the (query, genome) pair the way match_2 does for cDNA x genome
+// (src/spaln.cc:734-765): Exinon on b, end-gap flags from algmode.lcl.
+void* ref_task_new(const char* genome_fa, const char* query_fa, int comrev_query)
+{
+	if (!g_pwd) return 0;
+	RefTask* t = new RefTask;
+	initseq(t->sqs, 4);
+	Seq*& a = t->sqs[0];
+	Seq*& b = t->sqs[1];
+	if (!b->getseq(genome_fa) || !a->getseq(query_fa)) {
+	    clearseq(t->sqs, 4);
+	    delete t;
+	    return 0;
+	}
+	a->inex.intr = 0;
+	b->inex.intr = b_intr;
+	if (comrev_query) a->comrev();
+	if (!b->exin) b->exin = new Exinon(b, g_pwd, false);
+	if (algmode.lcl & 16) {
+	    a->exg_seq(1, 1);
+	    b->exg_seq(1, 1);
+	} else {
+	    a->exg_seq(algmode.lcl & 4, algmode.lcl & 8);
+	    b->exg_seq(algmode.lcl & 1, algmode.lcl & 2);
+	}
+	return t;
+}
+
+void ref_task_free(void* h)
+{
+	RefTask* t = (RefTask*) h;
+	if (!t) return;
+	clearseq(t->sqs, 4);
+	delete t;
+}
+
+// info[0..9] = a.len, b.len, a.left, a.right, b.left, b.right,
+//              a.exgl, a.exgr, b.exgl, b.exgr
+void ref_task_info(void* h, int* info)
+{
+	RefTask* t = (RefTask*) h;
+	const Seq* a = t->sqs[0];
+	const Seq* b = t->sqs[1];
+	info[0] = a->len; info[1] = b->len;
+	info[2] = a->left; info[3] = a->right;
+	info[4] = b->left; info[5] = b->right;
+	info[6] = a->inex.exgl; info[7] = a->inex.exgr;
+	info[8] = b->inex.exgl; info[9] = b->inex.exgr;
+}
+
+void ref_task_set(void* h, const int* info)
+{
+	RefTask* t = (RefTask*) h;
+	const Seq* a = t->sqs[0];
+	const Seq* b = t->sqs[1];
+	a->left = info[2]; a->right = info[3];
+	b->left = info[4]; b->right = info[5];
+	a->inex.exgl = info[6]; a->inex.exgr = info[7];
+	b->inex.exgl = info[8]; b->inex.exgr = info[9];
+}
+
+// a_codes[a.len + 2], b_codes[b.len + 2]: residue codes at(-1 .. len)
+// sig5/sig3[b.len + 2]: SGPT2 table entries for columns n = 0 .. b.len + 1
+void ref_task_export(void* h, unsigned char* a_codes, unsigned char* b_codes,
+	short* sig5, short* sig3)
+{
+	RefTask* t = (RefTask*) h;
+	const Seq* a = t->sqs[0];
+	const Seq* b = t->sqs[1];
+	for (int i = -1; i <= a->len; ++i) a_codes[i + 1] = *a->at(i);
+	for (int i = -1; i <= b->len; ++i) b_codes[i + 1] = *b->at(i);
+	for (int n = 0; n <= b->len + 1; ++n) {
+	    const SGPT2* g = b->exin->score_n(n);
+	    sig5[n] = g->sig5;
+	    sig3[n] = g->sig3;
+	}
+}
+
+// overwrite the splice-signal table (synthetic workloads)
+void ref_task_inject(void* h, const short* sig5, const short* sig3)
+{
+	RefTask* t = (RefTask*) h;
+	const Seq* b = t->sqs[1];
+	for (int n = 0; n <= b->len + 1; ++n) {
+	    SGPT2* g = b->exin->score_n(n);
+	    g->sig5 = sig5[n];
+	    g->sig3 = sig3[n];
+	}
+}
+
+void ref_task_stripe(void* h, int sh, int* lwup)
+{
+	RefTask* t = (RefTask*) h;
+	WINDOW w;
+	stripe((const Seq**) t->sqs, &w, sh);
+	lwup[0] = w.lw; lwup[1] = w.up; lwup[2] = w.width;
+}
+
+int ref_task_kernel(void* h, int lw, int up, int kind, int n_imd, int mode,
+	int* score, int* skl_out, int cap, int* cpos_out, double* seconds)
+{
+	RefTask* t = (RefTask*) h;
+	return shim_s1_kernel((const Seq**) t->sqs, g_pwd, lw, up, kind, n_imd,
+	    mode, score, skl_out, cap, cpos_out, seconds);
+}
+
+int ref_task_lsp(void* h, int lw, int up, int* score, int* skl_out, int cap,
+	double* seconds)
+{
+	RefTask* t = (RefTask*) h;
+	return shim_s1_lsp((const Seq**) t->sqs, g_pwd, lw, up, score, skl_out,
+	    cap, seconds);
+}
+
+}	// extern "C"

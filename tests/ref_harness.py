@@ -1,0 +1,184 @@
+"""ctypes front-end to oracle/_ref/libspaln_ref.so (the UNMODIFIED reference
+compiled by oracle/Makefile).  TEST INFRASTRUCTURE ONLY: used by tests/, by
+scripts that generate tests/golden/*, and by bench.py's cpu_baseline /
+--impl reference legs.  Never imported by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+REF_DIR = ROOT / "oracle" / "_ref"
+REF_SO = REF_DIR / "libspaln_ref.so"
+
+PARAM_FIELDS = [
+    "DvsP", "Noll", "Vab", "Vthr", "BasicGOP", "BasicGEP", "LongGOP", "LongGEP",
+    "codonk1", "GapWI", "llmt", "mu", "rlmt", "minl", "maxl", "ild_mode", "nquant",
+    "alg", "lcl", "lsg", "any", "qck", "sh", "ubh", "scale", "avmch", "simdim",
+    "MaxVmfSpace", "GapPenalty1", "nelem",
+]
+
+
+def available() -> bool:
+    return REF_SO.exists() and (REF_DIR / "table" / "gnm2tab").exists()
+
+
+def write_fasta(path, name, seq):
+    with open(path, "w") as f:
+        f.write(f">{name}\n")
+        for i in range(0, len(seq), 60):
+            f.write(seq[i:i + 60] + "\n")
+
+
+_COMP = str.maketrans("ACGTacgtNn", "TGCAtgcaNn")
+
+
+def revcomp(s: str) -> str:
+    return s.translate(_COMP)[::-1]
+
+
+class Reference:
+    """One process-wide reference set-up (the reference keeps its parameters
+    in globals, so a process can hold exactly one option string)."""
+
+    _instance = None
+
+    def __init__(self, opts: str = "-Q0 -A2 -S1 -yX0 -TDictyost"):
+        if Reference._instance is not None:
+            raise RuntimeError("reference already set up in this process")
+        if not available():
+            raise RuntimeError("oracle/_ref not built (run make -C oracle ref)")
+        os.environ["ALN_TAB"] = str(REF_DIR / "table")
+        os.environ.setdefault("ALN_DBS", str(REF_DIR / "seqdb"))
+        self.lib = C.CDLL(str(REF_SO))
+        L = self.lib
+        L.ref_setup.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+        L.ref_task_new.restype = C.c_void_p
+        L.ref_task_new.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        L.ref_task_free.argtypes = [C.c_void_p]
+        L.ref_task_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_task_set.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_task_export.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.ref_task_inject.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_task_stripe.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_task_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_void_p, C.c_void_p]
+        L.ref_task_lsp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_get_params.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        self.tmp = tempfile.TemporaryDirectory(prefix="spaln_ref_")
+        g = os.path.join(self.tmp.name, "g0.fa")
+        q = os.path.join(self.tmp.name, "q0.fa")
+        write_fasta(g, "g0", "ACGTTGCAAGTCCGATGCATGCAAGTCGATCGATGCTAGCTAGCATCGATCGACTAGCTAGCAT" * 4)
+        write_fasta(q, "q0", "ACGTTGCAAGTCCGATGCATGCAAGTCGATCGATGCTAGC")
+        rc = L.ref_setup(opts.encode(), g.encode(), q.encode())
+        if rc < 0:
+            raise RuntimeError(f"ref_setup failed: {rc}")
+        self.opts = opts
+        self._n = 0
+        Reference._instance = self
+
+    # ------------------------------------------------------------------
+    def params(self) -> dict:
+        buf = np.zeros(128, np.int32)
+        sim = np.zeros(64 * 64, np.int32)
+        k = self.lib.ref_get_params(buf.ctypes.data, 128, sim.ctypes.data, sim.size)
+        nf = len(PARAM_FIELDS)
+        p = {name: int(buf[i]) for i, name in enumerate(PARAM_FIELDS)}
+        q = buf[nf:k].reshape(-1, 2)
+        p["quant_len"] = q[:, 0].astype(np.int32).copy()
+        p["quant_pen"] = q[:, 1].astype(np.int32).copy()
+        d = p["simdim"]
+        p["simmtx"] = sim[: d * d].reshape(d, d).copy()
+        return p
+
+    def task(self, genome: str, query: str, comrev_query: bool = False) -> "RefTask":
+        self._n += 1
+        g = os.path.join(self.tmp.name, f"g{self._n}.fa")
+        q = os.path.join(self.tmp.name, f"q{self._n}.fa")
+        write_fasta(g, f"g{self._n}", genome)
+        write_fasta(q, f"q{self._n}", query)
+        h = self.lib.ref_task_new(g.encode(), q.encode(), int(comrev_query))
+        os.unlink(g)
+        os.unlink(q)
+        if not h:
+            raise RuntimeError("ref_task_new failed")
+        return RefTask(self, h)
+
+
+class RefTask:
+    def __init__(self, ref: Reference, h):
+        self.ref, self.h = ref, h
+        self.lib = ref.lib
+
+    def close(self):
+        if self.h:
+            self.lib.ref_task_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        b = np.zeros(10, np.int32)
+        self.lib.ref_task_info(self.h, b.ctypes.data)
+        keys = ["alen", "blen", "a_left", "a_right", "b_left", "b_right",
+                "a_exgl", "a_exgr", "b_exgl", "b_exgr"]
+        return {k: int(v) for k, v in zip(keys, b)}
+
+    def set(self, **kw):
+        d = self.info()
+        d.update(kw)
+        keys = ["alen", "blen", "a_left", "a_right", "b_left", "b_right",
+                "a_exgl", "a_exgr", "b_exgl", "b_exgr"]
+        b = np.array([d[k] for k in keys], np.int32)
+        self.lib.ref_task_set(self.h, b.ctypes.data)
+
+    def export(self) -> dict:
+        i = self.info()
+        a = np.zeros(i["alen"] + 2, np.uint8)
+        b = np.zeros(i["blen"] + 2, np.uint8)
+        s5 = np.zeros(i["blen"] + 2, np.int16)
+        s3 = np.zeros(i["blen"] + 2, np.int16)
+        self.lib.ref_task_export(self.h, a.ctypes.data, b.ctypes.data,
+                                 s5.ctypes.data, s3.ctypes.data)
+        i.update(a=a, b=b, sig5=s5, sig3=s3)
+        return i
+
+    def inject(self, sig5, sig3):
+        s5 = np.ascontiguousarray(sig5, np.int16)
+        s3 = np.ascontiguousarray(sig3, np.int16)
+        self.lib.ref_task_inject(self.h, s5.ctypes.data, s3.ctypes.data)
+
+    def stripe(self, sh: int):
+        b = np.zeros(3, np.int32)
+        self.lib.ref_task_stripe(self.h, sh, b.ctypes.data)
+        return int(b[0]), int(b[1])
+
+    def kernel(self, lw, up, kind=0, n_imd=0, mode=2, cap=1 << 16):
+        score = C.c_int(0)
+        secs = C.c_double(0)
+        skl = np.zeros((cap, 2), np.int32)
+        cpos = np.zeros((n_imd + 1, 10), np.int32)
+        n = self.lib.ref_task_kernel(self.h, lw, up, kind, n_imd, mode,
+                                     C.byref(score), skl.ctypes.data, cap,
+                                     cpos.ctypes.data, C.byref(secs))
+        return {"score": score.value, "skl": skl[:n].copy(), "cpos": cpos,
+                "seconds": secs.value}
+
+    def lsp(self, lw, up, cap=1 << 16):
+        score = C.c_int(0)
+        secs = C.c_double(0)
+        skl = np.zeros((cap, 2), np.int32)
+        n = self.lib.ref_task_lsp(self.h, lw, up, C.byref(score), skl.ctypes.data,
+                                  cap, C.byref(secs))
+        return {"score": score.value, "skl": skl[:n].copy(), "seconds": secs.value}
