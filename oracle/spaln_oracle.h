@@ -1,0 +1,70 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement (plain C) of the reference's
+ * DNA spliced-alignment DP kernels with quantised intron-length penalty
+ * ("_wip" family, `spaln -A2/-A3`), at the canonical vector width of the
+ * AVX2 build (nelem = 16 int16 lanes).
+ *
+ * Pinned against the unmodified reference compiled into oracle/_ref/ (see
+ * tests/test_oracle_vs_reference.py and tests/golden/).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline leg may use this.
+ *
+ * Reference files restated (paths relative to /root/reference):
+ *   src/fwd2s1_wip_simd.h:42-231   scoreonlyS1_wip
+ *   src/fwd2s1_wip_simd.h:233-474  forwardS1_wip
+ *   src/fwd2s1_simd.cc:163-262     fhinitS1 / fhlastS1
+ *   src/fwd2s1_simd.h:179-182,191-333  checkpoint(), buffer layout
+ *   src/rhomb_coord.h:65-235       Anti_rhomb_coord<CHAR> trace store + walk
+ *   src/simd_functions.h:1010-1074 (AVX2 int16 ops), 61-151 (Vec* helpers)
+ */
+#ifndef SPALN_ORACLE_H
+#define SPALN_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SO_MAXQUANT 8
+
+typedef struct {
+    int32_t gop;        /* PwdB::BasicGOP (<0)            src/aln2.cc:106 */
+    int32_t gep;        /* PwdB::BasicGEP (<0)            src/aln2.cc:107 */
+    int32_t lgop;       /* PwdB::LongGOP                  src/aln2.cc:110 */
+    int32_t lgep;       /* PwdB::LongGEP                  src/aln2.cc:108 */
+    int32_t noll;       /* PwdB::Noll: 2 affine, 3 double affine */
+    int32_t ipen;       /* IntronPenalty::Penalty() = GapWI  src/codepot.h:241 */
+    int32_t llmt;       /* IntronPrm.llmt */
+    int32_t nquant;     /* IntronPrm.nquant (1 under -A3) */
+    int32_t quant_len[SO_MAXQUANT];   /* IntronPenalty::qm[j].len */
+    int32_t quant_pen[SO_MAXQUANT];   /* IntronPenalty::qm[j].pen */
+    int32_t avmch;      /* int(Simmtx::AvTrc())           src/fwd2s1_simd.h:198 */
+    int32_t local;      /* algmode.lcl & 16 */
+    int32_t spj;        /* b->inex.intr */
+    int32_t simdim;     /* Simmtx::dim */
+    const int32_t* simmtx;  /* dim x dim, row = query code, col = genome code */
+    int32_t gappen1;    /* PwdB::GapPenalty(1) */
+} so_params;
+
+typedef struct {
+    const uint8_t* a;       /* query residue codes, a[i] == *a->at(i), i in [0, alen) */
+    const uint8_t* b;       /* genome residue codes */
+    const int16_t* sig5;    /* SGPT2::sig5 indexed by column n, n in [0, blen + 1] */
+    const int16_t* sig3;    /* SGPT2::sig3 */
+    int32_t a_left, a_right, b_left, b_right;   /* Seq::left / right */
+    int32_t a_exgl, a_exgr, b_exgl, b_exgr;     /* INEX end-gap flags */
+    int32_t lw, up;         /* WINDOW (width = up - lw + 3) */
+} so_task;
+
+/* forwardS1_wip: returns number of SKL corners written to skl[2*i], skl[2*i+1]
+ * (m, n) in the order Anti_rhomb_coord::traceback emits them (end -> start),
+ * or -1 on allocation failure.  *n_cells receives the inner-loop lane count. */
+int so_forward_wip(const so_params* p, const so_task* t, int32_t* score,
+                   int32_t* skl, int cap, int64_t* n_cells);
+
+/* scoreonlyS1_wip */
+int so_scoreonly_wip(const so_params* p, const so_task* t, int32_t* score);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,115 @@
+"""ctypes front-end to oracle/libspaln_oracle.so (our plain-C restatement of
+the reference algorithm).  TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_SO = ROOT / "oracle" / "libspaln_oracle.so"
+MAXQ = 8
+
+
+class SoParams(C.Structure):
+    _fields_ = [
+        ("gop", C.c_int32), ("gep", C.c_int32), ("lgop", C.c_int32), ("lgep", C.c_int32),
+        ("noll", C.c_int32), ("ipen", C.c_int32), ("llmt", C.c_int32), ("nquant", C.c_int32),
+        ("quant_len", C.c_int32 * MAXQ), ("quant_pen", C.c_int32 * MAXQ),
+        ("avmch", C.c_int32), ("local", C.c_int32), ("spj", C.c_int32),
+        ("simdim", C.c_int32), ("simmtx", C.c_void_p), ("gappen1", C.c_int32),
+    ]
+
+
+class SoTask(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("b", C.c_void_p), ("sig5", C.c_void_p), ("sig3", C.c_void_p),
+        ("a_left", C.c_int32), ("a_right", C.c_int32), ("b_left", C.c_int32), ("b_right", C.c_int32),
+        ("a_exgl", C.c_int32), ("a_exgr", C.c_int32), ("b_exgl", C.c_int32), ("b_exgr", C.c_int32),
+        ("lw", C.c_int32), ("up", C.c_int32),
+    ]
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", str(ROOT / "oracle"), "oracle"], check=True)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not ORACLE_SO.exists():
+            build()
+        _lib = C.CDLL(str(ORACLE_SO))
+        _lib.so_forward_wip.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_void_p]
+        _lib.so_scoreonly_wip.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    return _lib
+
+
+def make_params(p: dict):
+    """p: dict in the layout of tests/ref_harness.py::Reference.params() /
+    tests/golden params (see spaln_b200.params)."""
+    sp = SoParams()
+    sp.gop, sp.gep = p["BasicGOP"], p["BasicGEP"]
+    sp.lgop, sp.lgep = p["LongGOP"], p["LongGEP"]
+    sp.noll = p["Noll"]
+    sp.ipen = p["GapWI"]
+    sp.llmt = p["llmt"]
+    sp.nquant = p["nquant"]
+    for j in range(p["nquant"]):
+        sp.quant_len[j] = int(p["quant_len"][j])
+        sp.quant_pen[j] = int(p["quant_pen"][j])
+    sp.avmch = p["avmch"]
+    sp.local = 1 if (p["lcl"] & 16) else 0
+    sp.spj = p.get("spj", 1)
+    sp.simdim = p["simdim"]
+    sim = np.ascontiguousarray(p["simmtx"], np.int32)
+    sp.simmtx = sim.ctypes.data
+    sp.gappen1 = p["GapPenalty1"]
+    sp._keep = sim
+    return sp
+
+
+def make_task(t: dict):
+    """t: dict with a, b (uint8 arrays holding codes for at(-1..len)),
+    sig5, sig3 (int16, by column), ranges, flags, lw, up."""
+    st = SoTask()
+    a = np.ascontiguousarray(t["a"], np.uint8)
+    b = np.ascontiguousarray(t["b"], np.uint8)
+    s5 = np.ascontiguousarray(t["sig5"], np.int16)
+    s3 = np.ascontiguousarray(t["sig3"], np.int16)
+    st.a = a.ctypes.data + 1      # exported arrays start at at(-1)
+    st.b = b.ctypes.data + 1
+    st.sig5 = s5.ctypes.data
+    st.sig3 = s3.ctypes.data
+    for k in ("a_left", "a_right", "b_left", "b_right", "a_exgl", "a_exgr",
+              "b_exgl", "b_exgr", "lw", "up"):
+        setattr(st, k, int(t[k]))
+    st._keep = (a, b, s5, s3)
+    return st
+
+
+def forward_wip(p: dict, t: dict, cap: int = 1 << 16):
+    sp, st = make_params(p), make_task(t)
+    score = C.c_int32(0)
+    cells = C.c_int64(0)
+    skl = np.zeros((cap, 2), np.int32)
+    n = lib().so_forward_wip(C.byref(sp), C.byref(st), C.byref(score), skl.ctypes.data,
+                             cap, C.byref(cells))
+    if n < 0:
+        raise RuntimeError(f"so_forward_wip failed: {n}")
+    return {"score": score.value, "skl": skl[:n].copy(), "cells": cells.value}
+
+
+def scoreonly_wip(p: dict, t: dict):
+    sp, st = make_params(p), make_task(t)
+    score = C.c_int32(0)
+    rc = lib().so_scoreonly_wip(C.byref(sp), C.byref(st), C.byref(score))
+    if rc < 0:
+        raise RuntimeError("so_scoreonly_wip failed")
+    return {"score": score.value}
