@@ -1,0 +1,151 @@
+/* gspaln.h -- C-ABI of the B200-native spliced-alignment DP engine.
+ *
+ * Drop-in boundary for the DP hot path of ogotoh/spaln ("the reference").
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, returns
+ * 0 on success or a negative GSPALN_E* code; nothing throws, no globals are
+ * read after gspaln_create().  All paths are relative to /root/reference.
+ *
+ * What each entry point replaces in the reference:
+ *
+ *   gspaln_create            the process-global parameter set the kernels read
+ *                            (PwdB src/aln.h:235-308 built at src/aln2.cc:99-137,
+ *                            IntronPrm src/codepot.cc:38-46 + IntronPenalty::qm
+ *                            src/codepot.h:218-257, Simmtx::mtx src/simmtx.h:37-66,
+ *                            algmode.lcl src/clib.h:38-56), frozen into one POD.
+ *   gspaln_submit            kind GSPALN_FORWARD_WIP  = SimdAln2s1 ctor +
+ *                            SimdAln2s1::forwardS1_wip(Mfile*)
+ *                            (src/fwd2s1_simd.h:191-333, src/fwd2s1_wip_simd.h:233-474)
+ *                            as called from Aln2s1::trcbkalignS_ng
+ *                            (src/fwd2s1.cc:1676-1689, mode == 1);
+ *                            kind GSPALN_SCOREONLY_WIP = SimdAln2s1::scoreonlyS1_wip()
+ *                            (src/fwd2s1_wip_simd.h:42-231) as called from
+ *                            HomScoreS_ng (src/fwd2s1.cc:2696-2716).
+ *                            One gspaln_task == one such call; a batch of tasks
+ *                            is what the reference's pthread workers
+ *                            (src/spaln.cc:1363-1468) issue one at a time.
+ *   gspaln_result.skl        the (m, n) corner records the reference appends to
+ *                            the caller's Mfile through
+ *                            Anti_rhomb_coord::traceback (src/rhomb_coord.h:222-235),
+ *                            same order (alignment end first).
+ *
+ * Arithmetic is the reference's int16 saturating lane arithmetic at the
+ * canonical AVX2 width (strips of 16 query rows); results are bit-identical.
+ */
+#ifndef GSPALN_H
+#define GSPALN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSPALN_MAXQUANT 8
+#define GSPALN_MAXDIM   32      /* Simmtx::dim upper bound handled (DNA: 17) */
+
+enum {
+    GSPALN_OK = 0,
+    GSPALN_EINVAL = -1,         /* bad argument / unsupported parameter */
+    GSPALN_ENOMEM = -2,         /* device or host allocation failed */
+    GSPALN_ECUDA = -3,          /* CUDA runtime error (see gspaln_last_error) */
+    GSPALN_ENODEV = -4          /* no usable CUDA device: there is NO CPU fallback */
+};
+
+enum {                          /* gspaln_task.kind */
+    GSPALN_FORWARD_WIP = 0,     /* score + trace-back corners */
+    GSPALN_SCOREONLY_WIP = 1    /* score only */
+};
+
+enum {                          /* gspaln_result.status */
+    GSPALN_ST_OK = 0,
+    GSPALN_ST_SKL_OVERFLOW = 1, /* more corners than skl_cap: n_skl is the needed count */
+    GSPALN_ST_BAD_TRACE = 2     /* reference would have called fatal("Unexpected dir") */
+};
+
+/* frozen scoring parameters (reference globals -> one POD) */
+typedef struct gspaln_params {
+    int32_t gop;                /* PwdB::BasicGOP  (< 0) */
+    int32_t gep;                /* PwdB::BasicGEP  (< 0) */
+    int32_t lgop;               /* PwdB::LongGOP */
+    int32_t lgep;               /* PwdB::LongGEP */
+    int32_t noll;               /* PwdB::Noll: 2 = affine (3 = double affine: not yet on device) */
+    int32_t ipen;               /* IntronPenalty::Penalty() == GapWI */
+    int32_t llmt;               /* IntronPrm.llmt */
+    int32_t nquant;             /* IntronPrm.nquant (1 for -A3) */
+    int32_t quant_len[GSPALN_MAXQUANT];     /* IntronPenalty::qm[j].len */
+    int32_t quant_pen[GSPALN_MAXQUANT];     /* IntronPenalty::qm[j].pen */
+    int32_t avmch;              /* int(Simmtx::AvTrc()) */
+    int32_t local;              /* algmode.lcl & 16 */
+    int32_t spj;                /* Seq::inex.intr of the genomic sequence */
+    int32_t simdim;             /* Simmtx::dim */
+    int32_t gappen1;            /* PwdB::GapPenalty(1) */
+    int32_t simmtx[GSPALN_MAXDIM * GSPALN_MAXDIM];  /* mtx[q][g] at [q * simdim + g] */
+} gspaln_params;
+
+/* one DP problem == one SimdAln2s1 construction + kernel call */
+typedef struct gspaln_task {
+    int32_t kind;
+    const uint8_t* a;           /* query codes; a[i] == *Seq::at(i), i in [a_left, a_right) */
+    const uint8_t* b;           /* genome codes; b[i] == *Seq::at(i), i in [b_left, b_right) */
+    const int16_t* sig5;        /* Exinon::data_n[n].sig5 by column n, n in [b_left, b_right] */
+    const int16_t* sig3;        /* Exinon::data_n[n].sig3 */
+    int32_t a_left, a_right;    /* Seq::left / Seq::right of the query */
+    int32_t b_left, b_right;    /* ... of the genomic segment */
+    int32_t a_exgl, a_exgr;     /* INEX::exgl / exgr (src/seq.h:148-172) */
+    int32_t b_exgl, b_exgr;
+    int32_t lw, up;             /* WINDOW (src/cmn.h:133); width = up - lw + 3 */
+    int32_t skl_cap;            /* capacity of result.skl in corners */
+} gspaln_task;
+
+typedef struct gspaln_result {
+    int32_t score;              /* VTYPE return value of the kernel */
+    int32_t status;
+    int32_t n_skl;              /* corners written (or needed on overflow) */
+    int32_t reserved;
+    int64_t cells;              /* query rows x band columns evaluated (throughput accounting) */
+    int32_t* skl;               /* caller buffer: skl[2*i] = m, skl[2*i+1] = n */
+} gspaln_result;
+
+typedef struct gspaln_ctx gspaln_ctx;
+
+/* timing of the last submit, CUDA events on the engine's own stream */
+typedef struct gspaln_timing {
+    float h2d_ms;               /* host->device copies */
+    float kernel_ms;            /* DP kernel(s), start to end */
+    float d2h_ms;               /* device->host copies */
+    int32_t launches;           /* kernels launched by this call */
+    int64_t h2d_bytes, d2h_bytes;
+    int64_t trace_bytes;        /* trace-code bytes the DP kernel wrote */
+    int64_t cells;
+} gspaln_timing;
+
+int  gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device);
+void gspaln_destroy(gspaln_ctx* ctx);
+
+/* blocking: pack + H2D + kernels + D2H.  results[i].skl must point to
+ * tasks[i].skl_cap * 2 int32 (may be NULL for score-only tasks). */
+int  gspaln_submit(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
+                   gspaln_result* results);
+
+/* split form: inputs resident in HBM before the timed region starts.
+ * gspaln_upload packs and copies the batch; gspaln_run launches the kernels
+ * (may be called repeatedly on the same resident batch); gspaln_download
+ * fetches scores and corners. */
+int  gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n);
+int  gspaln_run(gspaln_ctx* ctx);
+int  gspaln_download(gspaln_ctx* ctx, gspaln_result* results);
+
+int  gspaln_get_timing(const gspaln_ctx* ctx, gspaln_timing* out);
+const char* gspaln_last_error(const gspaln_ctx* ctx);
+int  gspaln_device_count(void);
+const char* gspaln_version(void);
+
+/* band cells of a task exactly as the scalar reference counts them
+ * (inner-loop trip count of Aln2s1::forwardS_ng, src/fwd2s1.cc:252-276) */
+int64_t gspaln_task_cells(const gspaln_task* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSPALN_H */

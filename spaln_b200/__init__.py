@@ -1,0 +1,12 @@
+"""spaln_b200 -- B200-native spliced-alignment DP engine (gspaln).
+
+Only what the DP hot path needs lives here:
+  csrc/       hand-written sm_100a CUDA kernels + the C-ABI (include/gspaln.h)
+  capi.py     ctypes binding of that C-ABI
+  engine.py   host-side mirror of the reference's SimdAln2s1 call surface
+  workload.py seeded synthetic problems of the BASELINE.json shapes
+"""
+from .capi import FORWARD_WIP, SCOREONLY_WIP  # noqa: F401
+from .engine import Engine, EngineError, Problem, Result, Timing  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,120 @@
+"""ctypes binding of the C-ABI in include/gspaln.h (libgspaln.so).
+
+This is plumbing only: every DP cell is computed by the sm_100a kernels in
+spaln_b200/csrc.  There is no CPU fallback -- if the shared library is missing
+or no CUDA device is usable, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libgspaln.so"
+
+MAXQUANT = 8
+MAXDIM = 32
+
+FORWARD_WIP = 0
+SCOREONLY_WIP = 1
+
+EXPORTS = [
+    "gspaln_create", "gspaln_destroy", "gspaln_submit", "gspaln_upload", "gspaln_run",
+    "gspaln_download", "gspaln_get_timing", "gspaln_last_error", "gspaln_device_count",
+    "gspaln_version", "gspaln_task_cells",
+]
+
+
+class GspalnParams(C.Structure):
+    _fields_ = [
+        ("gop", C.c_int32), ("gep", C.c_int32), ("lgop", C.c_int32), ("lgep", C.c_int32),
+        ("noll", C.c_int32), ("ipen", C.c_int32), ("llmt", C.c_int32), ("nquant", C.c_int32),
+        ("quant_len", C.c_int32 * MAXQUANT), ("quant_pen", C.c_int32 * MAXQUANT),
+        ("avmch", C.c_int32), ("local", C.c_int32), ("spj", C.c_int32),
+        ("simdim", C.c_int32), ("gappen1", C.c_int32),
+        ("simmtx", C.c_int32 * (MAXDIM * MAXDIM)),
+    ]
+
+
+class GspalnTask(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("a", C.c_void_p), ("b", C.c_void_p), ("sig5", C.c_void_p), ("sig3", C.c_void_p),
+        ("a_left", C.c_int32), ("a_right", C.c_int32), ("b_left", C.c_int32), ("b_right", C.c_int32),
+        ("a_exgl", C.c_int32), ("a_exgr", C.c_int32), ("b_exgl", C.c_int32), ("b_exgr", C.c_int32),
+        ("lw", C.c_int32), ("up", C.c_int32), ("skl_cap", C.c_int32),
+    ]
+
+
+class GspalnResult(C.Structure):
+    _fields_ = [
+        ("score", C.c_int32), ("status", C.c_int32), ("n_skl", C.c_int32), ("reserved", C.c_int32),
+        ("cells", C.c_int64), ("skl", C.c_void_p),
+    ]
+
+
+class GspalnTiming(C.Structure):
+    _fields_ = [
+        ("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float),
+        ("launches", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+        ("trace_bytes", C.c_int64), ("cells", C.c_int64),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load libgspaln.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the DP engine)")
+    lib = C.CDLL(str(LIB_PATH))
+    lib.gspaln_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(GspalnParams), C.c_int]
+    lib.gspaln_create.restype = C.c_int
+    lib.gspaln_destroy.argtypes = [C.c_void_p]
+    lib.gspaln_destroy.restype = None
+    lib.gspaln_submit.argtypes = [C.c_void_p, C.POINTER(GspalnTask), C.c_int, C.POINTER(GspalnResult)]
+    lib.gspaln_upload.argtypes = [C.c_void_p, C.POINTER(GspalnTask), C.c_int]
+    lib.gspaln_run.argtypes = [C.c_void_p]
+    lib.gspaln_download.argtypes = [C.c_void_p, C.POINTER(GspalnResult)]
+    lib.gspaln_get_timing.argtypes = [C.c_void_p, C.POINTER(GspalnTiming)]
+    lib.gspaln_last_error.argtypes = [C.c_void_p]
+    lib.gspaln_last_error.restype = C.c_char_p
+    lib.gspaln_device_count.restype = C.c_int
+    lib.gspaln_version.restype = C.c_char_p
+    lib.gspaln_task_cells.argtypes = [C.POINTER(GspalnTask)]
+    lib.gspaln_task_cells.restype = C.c_int64
+    _lib = lib
+    return lib
+
+
+def make_params(p: dict) -> GspalnParams:
+    """p uses the reference's own names (PwdB / IntronPrm / algmode fields)."""
+    gp = GspalnParams()
+    gp.gop, gp.gep = int(p["BasicGOP"]), int(p["BasicGEP"])
+    gp.lgop, gp.lgep = int(p["LongGOP"]), int(p["LongGEP"])
+    gp.noll = int(p["Noll"])
+    gp.ipen = int(p["GapWI"])
+    gp.llmt = int(p["llmt"])
+    gp.nquant = int(p["nquant"])
+    for j in range(gp.nquant):
+        gp.quant_len[j] = int(p["quant_len"][j])
+        gp.quant_pen[j] = int(p["quant_pen"][j])
+    gp.avmch = int(p["avmch"])
+    gp.local = 1 if (int(p["lcl"]) & 16) else 0
+    gp.spj = int(p.get("spj", 1))
+    d = int(p["simdim"])
+    gp.simdim = d
+    gp.gappen1 = int(p["GapPenalty1"])
+    sim = np.asarray(p["simmtx"], np.int32).reshape(d, d)
+    flat = sim.ravel()
+    for i in range(d * d):
+        gp.simmtx[i] = int(flat[i])
+    return gp

@@ -1,0 +1,380 @@
+// gspaln.cu -- host side of the C-ABI declared in include/gspaln.h.
+//
+// Owns the device pools (query codes, genome columns, band buffers, trace
+// matrix, corner records), packs a batch of problems into them, launches the
+// persistent DP kernels on the engine's own stream and times every phase with
+// CUDA events on that stream.  There is no CPU implementation behind this
+// API: without a CUDA device gspaln_create() fails with GSPALN_ENODEV.
+#include "../../include/gspaln.h"
+#include "gspaln_kernels.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace gspaln;
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}   // namespace
+
+struct gspaln_ctx {
+    int device = 0;
+    int sm_count = 0;
+    gspaln_params prm;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DevBuf<DevParams> d_prm;
+    DevBuf<DevTask> d_tasks;
+    DevBuf<int> d_order;
+    DevBuf<int> d_ticket;
+    DevBuf<unsigned char> d_apool;
+    DevBuf<ColInfo> d_cpool;
+    DevBuf<unsigned> d_band;
+    DevBuf<unsigned char> d_trace;
+    DevBuf<int2> d_skl;
+    DevBuf<DevResult> d_res;
+    PinBuf<DevTask> h_tasks;
+    PinBuf<int> h_order;
+    PinBuf<unsigned char> h_apool;
+    PinBuf<ColInfo> h_cpool;
+    PinBuf<int2> h_skl;
+    PinBuf<DevResult> h_res;
+    // resident batch
+    int n = 0;
+    int n_trace = 0, n_score = 0;
+    size_t a_bytes = 0, c_elems = 0, band_elems = 0, trace_bytes = 0, skl_elems = 0;
+    std::vector<int64_t> cells;
+    std::vector<int> skl_cap;
+    gspaln_timing tim;
+    std::string err;
+    int grid_trace = 0, grid_score = 0;
+};
+
+namespace {
+
+int fail(gspaln_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, GSPALN_ECUDA, #call, e_); } while (0)
+
+int64_t task_cells(const gspaln_task& t)
+{
+    // rows m in (a_left, a_right], columns max(m + lw, b_left) < n <= min(m + up + 1, b_right)
+    int64_t cells = 0;
+    for (int m = t.a_left + 1; m <= t.a_right; ++m) {
+        int lo = std::max(m + t.lw, t.b_left);
+        int hi = std::min(m + t.up + 1, t.b_right);
+        if (hi > lo) cells += hi - lo;
+    }
+    return cells;
+}
+
+}   // namespace
+
+extern "C" {
+
+const char* gspaln_version(void) { return "gspaln 0.1 (sm_100a)"; }
+
+int gspaln_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int64_t gspaln_task_cells(const gspaln_task* t) { return t ? task_cells(*t) : 0; }
+
+const char* gspaln_last_error(const gspaln_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
+{
+    if (!out || !prm) return GSPALN_EINVAL;
+    *out = nullptr;
+    if (prm->noll != 2 || prm->simdim <= 0 || prm->simdim >= ZROW ||
+        prm->nquant < 1 || prm->nquant > GSPALN_MAXQUANT || prm->avmch <= 0)
+        return GSPALN_EINVAL;
+    int ndev = gspaln_device_count();
+    if (ndev <= 0 || device < 0 || device >= ndev) return GSPALN_ENODEV;
+    gspaln_ctx* ctx = new gspaln_ctx;
+    ctx->device = device;
+    ctx->prm = *prm;
+    memset(&ctx->tim, 0, sizeof(ctx->tim));
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { gspaln_destroy(ctx); return GSPALN_ECUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+
+    DevParams P;
+    memset(&P, 0, sizeof(P));
+    P.ge = (short) prm->gep;                        // Splat() narrows to short
+    P.gn = (short) (prm->gep + prm->gop);
+    P.ipen = (short) (prm->spj ? prm->ipen : NEV);
+    P.mil = (short) prm->llmt;
+    P.nquant = prm->nquant;
+    for (int j = 0; j < prm->nquant; ++j) {
+        P.quant[j] = (short) prm->quant_len[j];
+        P.mean[j] = (short) prm->quant_pen[j];
+    }
+    P.avmch = prm->avmch; P.local = prm->local ? 1 : 0; P.spj = prm->spj ? 1 : 0;
+    P.simdim = prm->simdim; P.gappen1 = prm->gappen1; P.gop = prm->gop; P.gep = prm->gep;
+    for (int q = 0; q < prm->simdim; ++q)
+        for (int g = 0; g < prm->simdim; ++g)
+            P.mtxT[g * MTX_LD + q] = (short) prm->simmtx[q * prm->simdim + g];
+    if (ctx->d_prm.reserve(1) != cudaSuccess || ctx->d_ticket.reserve(4) != cudaSuccess ||
+        cudaMemcpy(ctx->d_prm.p, &P, sizeof(P), cudaMemcpyHostToDevice) != cudaSuccess) {
+        gspaln_destroy(ctx);
+        return GSPALN_ENOMEM;
+    }
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dp_wip_kernel<true>, 32 * WARPS_PER_CTA, 0);
+    ctx->grid_trace = std::max(1, occ) * ctx->sm_count;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dp_wip_kernel<false>, 32 * WARPS_PER_CTA, 0);
+    ctx->grid_score = std::max(1, occ) * ctx->sm_count;
+    *out = ctx;
+    return GSPALN_OK;
+}
+
+void gspaln_destroy(gspaln_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->d_prm.release(); ctx->d_tasks.release(); ctx->d_order.release(); ctx->d_ticket.release();
+    ctx->d_apool.release(); ctx->d_cpool.release(); ctx->d_band.release(); ctx->d_trace.release();
+    ctx->d_skl.release(); ctx->d_res.release();
+    ctx->h_tasks.release(); ctx->h_order.release(); ctx->h_apool.release(); ctx->h_cpool.release();
+    ctx->h_skl.release(); ctx->h_res.release();
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
+{
+    if (!ctx || !tasks || n < 0) return GSPALN_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    ctx->n = 0;
+    // ---- layout
+    size_t a_bytes = 0, c_elems = 0, band_elems = 0, trace_bytes = 0, skl_elems = 0;
+    ctx->cells.assign(n, 0);
+    ctx->skl_cap.assign(n, 0);
+    std::vector<DevTask> dt(n);
+    int n_trace = 0, n_score = 0;
+    for (int i = 0; i < n; ++i) {
+        const gspaln_task& t = tasks[i];
+        if (t.a_right < t.a_left || t.b_right < t.b_left || t.up < t.lw ||
+            (t.kind != GSPALN_FORWARD_WIP && t.kind != GSPALN_SCOREONLY_WIP) ||
+            !t.a || !t.b || (ctx->prm.spj && (!t.sig5 || !t.sig3)))
+            return fail(ctx, GSPALN_EINVAL, "bad task");
+        DevTask& d = dt[i];
+        d.kind = t.kind;
+        d.a_left = t.a_left; d.a_right = t.a_right; d.b_left = t.b_left; d.b_right = t.b_right;
+        d.lw = t.lw; d.up = t.up;
+        d.flags = (t.a_exgl ? 1 : 0) | (t.a_exgr ? 2 : 0) | (t.b_exgl ? 4 : 0) | (t.b_exgr ? 8 : 0);
+        d.skl_cap = t.kind == GSPALN_FORWARD_WIP ? std::max(0, t.skl_cap) : 0;
+        d.pad0 = 0;
+        const int mw = t.a_right - t.a_left, nw = t.b_right - t.b_left;
+        const int width = t.up - t.lw + 3;
+        d.a_off = (long long) a_bytes;      a_bytes += align_up((size_t) mw + 1, 16);
+        d.col_off = (long long) c_elems;    c_elems += align_up((size_t) nw + 2, 4);
+        d.band_off = (long long) band_elems; band_elems += align_up((size_t) width + 2 * NELEM, 32);
+        d.trace_off = (long long) trace_bytes;
+        d.skl_off = (long long) skl_elems;
+        if (t.kind == GSPALN_FORWARD_WIP) {
+            const size_t nstrips = (mw + NELEM - 1) / NELEM;
+            trace_bytes += align_up(nstrips * (size_t) (width + TRACE_PAD) * NELEM + 64, 256);
+            skl_elems += (size_t) d.skl_cap;
+            ++n_trace;
+        } else
+            ++n_score;
+        ctx->cells[i] = task_cells(t);
+        ctx->skl_cap[i] = d.skl_cap;
+    }
+    if (ctx->h_tasks.reserve(n + 1) != cudaSuccess || ctx->h_order.reserve(n + 1) != cudaSuccess ||
+        ctx->h_apool.reserve(a_bytes + 16) != cudaSuccess || ctx->h_cpool.reserve(c_elems + 4) != cudaSuccess ||
+        ctx->h_res.reserve(n + 1) != cudaSuccess || ctx->h_skl.reserve(skl_elems + 1) != cudaSuccess)
+        return fail(ctx, GSPALN_ENOMEM, "pinned host allocation");
+    if (ctx->d_tasks.reserve(n + 1) != cudaSuccess || ctx->d_order.reserve(n + 1) != cudaSuccess ||
+        ctx->d_apool.reserve(a_bytes + 16) != cudaSuccess || ctx->d_cpool.reserve(c_elems + 4) != cudaSuccess ||
+        ctx->d_band.reserve(band_elems + 32) != cudaSuccess || ctx->d_trace.reserve(trace_bytes + 256) != cudaSuccess ||
+        ctx->d_skl.reserve(skl_elems + 1) != cudaSuccess || ctx->d_res.reserve(n + 1) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, GSPALN_ENOMEM, "device allocation");
+    }
+    // ---- pack (host work is part of the end-to-end path)
+    for (int i = 0; i < n; ++i) {
+        const gspaln_task& t = tasks[i];
+        const DevTask& d = dt[i];
+        const int mw = t.a_right - t.a_left, nw = t.b_right - t.b_left;
+        memcpy(ctx->h_apool.p + d.a_off, t.a + t.a_left, (size_t) mw);
+        ColInfo* col = ctx->h_cpool.p + d.col_off;
+        for (int j = 0; j <= nw; ++j) {
+            const int c = t.b_left + j;             // column c pairs genome residue at(c - 1)
+            ColInfo ci;
+            ci.sig5 = ctx->prm.spj ? t.sig5[c] : 0;
+            ci.sig3 = ctx->prm.spj ? t.sig3[c] : 0;
+            ci.code = j > 0 ? t.b[c - 1] : 0;
+            ci.pad[0] = ci.pad[1] = ci.pad[2] = 0;
+            col[j] = ci;
+        }
+        ctx->h_tasks.p[i] = d;
+    }
+    // largest problems first (longest-processing-time order for the ticket queue)
+    std::iota(ctx->h_order.p, ctx->h_order.p + n, 0);
+    std::stable_sort(ctx->h_order.p, ctx->h_order.p + n,
+                     [&](int x, int y) { return ctx->cells[x] > ctx->cells[y]; });
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_tasks.p, ctx->h_tasks.p, sizeof(DevTask) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.p, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_apool.p, ctx->h_apool.p, a_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_cpool.p, ctx->h_cpool.p, sizeof(ColInfo) * c_elems, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->tim.h2d_ms = ms;
+    ctx->tim.h2d_bytes = (int64_t) (sizeof(DevTask) * n + sizeof(int) * n + a_bytes + sizeof(ColInfo) * c_elems);
+    ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score;
+    ctx->a_bytes = a_bytes; ctx->c_elems = c_elems; ctx->band_elems = band_elems;
+    ctx->trace_bytes = trace_bytes; ctx->skl_elems = skl_elems;
+    int64_t cells = 0, tb = 0;
+    for (int i = 0; i < n; ++i) {
+        cells += ctx->cells[i];
+        if (tasks[i].kind == GSPALN_FORWARD_WIP) tb += ctx->cells[i];
+    }
+    ctx->tim.cells = cells;
+    ctx->tim.trace_bytes = tb;
+    return GSPALN_OK;
+}
+
+int gspaln_run(gspaln_ctx* ctx)
+{
+    if (!ctx) return GSPALN_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n;
+    int launches = 0;
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (n > 0) {
+        const int warps_needed = n;
+        if (ctx->n_trace) {
+            CK(cudaMemsetAsync(ctx->d_ticket.p, 0, sizeof(int), ctx->stream));
+            int grid = std::min(ctx->grid_trace, (warps_needed + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+            dp_wip_kernel<true><<<grid, 32 * WARPS_PER_CTA, 0, ctx->stream>>>(
+                ctx->d_prm.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p,
+                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, ctx->d_trace.p, ctx->d_skl.p, ctx->d_res.p);
+            ++launches;
+        }
+        if (ctx->n_score) {
+            CK(cudaMemsetAsync(ctx->d_ticket.p + 1, 0, sizeof(int), ctx->stream));
+            int grid = std::min(ctx->grid_score, (warps_needed + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+            dp_wip_kernel<false><<<grid, 32 * WARPS_PER_CTA, 0, ctx->stream>>>(
+                ctx->d_prm.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p + 1,
+                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, ctx->d_trace.p, ctx->d_skl.p, ctx->d_res.p);
+            ++launches;
+        }
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+    ctx->tim.kernel_ms = ms;
+    ctx->tim.launches = launches;
+    return GSPALN_OK;
+}
+
+int gspaln_download(gspaln_ctx* ctx, gspaln_result* results)
+{
+    if (!ctx || (!results && ctx->n)) return GSPALN_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n;
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (n) CK(cudaMemcpyAsync(ctx->h_res.p, ctx->d_res.p, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->skl_elems)
+        CK(cudaMemcpyAsync(ctx->h_skl.p, ctx->d_skl.p, sizeof(int2) * ctx->skl_elems, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+    ctx->tim.d2h_ms = ms;
+    ctx->tim.d2h_bytes = (int64_t) (sizeof(DevResult) * n + sizeof(int2) * ctx->skl_elems);
+    for (int i = 0; i < n; ++i) {
+        const DevResult& r = ctx->h_res.p[i];
+        gspaln_result& o = results[i];
+        o.score = r.score; o.status = r.status; o.n_skl = r.n_skl; o.reserved = 0;
+        o.cells = ctx->cells[i];
+        const DevTask& d = ctx->h_tasks.p[i];
+        if (o.skl && d.skl_cap > 0) {
+            const int cnt = std::min(r.n_skl, d.skl_cap);
+            memcpy(o.skl, ctx->h_skl.p + d.skl_off, sizeof(int2) * (size_t) std::max(0, cnt));
+        }
+    }
+    return GSPALN_OK;
+}
+
+int gspaln_submit(gspaln_ctx* ctx, const gspaln_task* tasks, int n, gspaln_result* results)
+{
+    int rc = gspaln_upload(ctx, tasks, n);
+    if (rc == GSPALN_OK) rc = gspaln_run(ctx);
+    if (rc == GSPALN_OK) rc = gspaln_download(ctx, results);
+    return rc;
+}
+
+int gspaln_get_timing(const gspaln_ctx* ctx, gspaln_timing* out)
+{
+    if (!ctx || !out) return GSPALN_EINVAL;
+    *out = ctx->tim;
+    return GSPALN_OK;
+}
+
+}   // extern "C"

@@ -1,0 +1,185 @@
+"""Host-side mirror of the reference's DP call surface for the spliced-DP path.
+
+Reference surface (C++): `SimdAln2s1(seqs, pwd, wdw, spjcs, cip, mode)` followed
+by `forwardS1_wip(mfd)` / `scoreonlyS1_wip()` (src/fwd2s1_simd.h:184-196), one
+problem per call.  Here a `Problem` carries exactly the inputs that constructor
+reads (query / genome codes and ranges, end-gap flags, Exinon splice-signal
+table, band window) and `Engine.forwardS1_wip(problems)` /
+`Engine.scoreonlyS1_wip(problems)` run a whole batch on the GPU through the
+C-ABI (include/gspaln.h).  Results are the reference's: the VTYPE score and the
+(m, n) corner list appended to the caller's Mfile.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+
+
+@dataclass
+class Problem:
+    a: np.ndarray           # uint8 query codes, a[i] == *Seq::at(i)
+    b: np.ndarray           # uint8 genome codes
+    sig5: np.ndarray        # int16, Exinon::data_n[n].sig5 by column n (len >= b_right + 1)
+    sig3: np.ndarray        # int16
+    a_left: int
+    a_right: int
+    b_left: int
+    b_right: int
+    lw: int
+    up: int
+    a_exgl: int = 1
+    a_exgr: int = 1
+    b_exgl: int = 1
+    b_exgr: int = 1
+    skl_cap: int = 0        # 0: a_len + b_len + 8
+
+    @staticmethod
+    def from_export(ex: dict, lw: int, up: int) -> "Problem":
+        """ex: tests/ref_harness.py::RefTask.export() layout (arrays start at at(-1))."""
+        return Problem(a=np.ascontiguousarray(ex["a"][1:], np.uint8),
+                       b=np.ascontiguousarray(ex["b"][1:], np.uint8),
+                       sig5=np.ascontiguousarray(ex["sig5"], np.int16),
+                       sig3=np.ascontiguousarray(ex["sig3"], np.int16),
+                       a_left=ex["a_left"], a_right=ex["a_right"],
+                       b_left=ex["b_left"], b_right=ex["b_right"], lw=lw, up=up,
+                       a_exgl=ex["a_exgl"], a_exgr=ex["a_exgr"],
+                       b_exgl=ex["b_exgl"], b_exgr=ex["b_exgr"])
+
+
+@dataclass
+class Result:
+    score: int
+    status: int
+    skl: np.ndarray         # (n, 2) int32 corners, alignment end first
+    cells: int
+
+
+@dataclass
+class Timing:
+    h2d_ms: float = 0.0
+    kernel_ms: float = 0.0
+    d2h_ms: float = 0.0
+    launches: int = 0
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
+    trace_bytes: int = 0
+    cells: int = 0
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One engine per (parameter set, device); not thread-safe."""
+
+    def __init__(self, params: dict, device: int = 0):
+        self.lib = capi.load()
+        self._gp = capi.make_params(params)
+        self._h = C.c_void_p()
+        rc = self.lib.gspaln_create(C.byref(self._h), C.byref(self._gp), device)
+        if rc != 0:
+            raise EngineError(f"gspaln_create failed ({rc}): no usable CUDA device or bad "
+                              "parameters; the DP engine has no CPU fallback")
+        self.device = device
+        self._tasks = None
+        self._keep = None
+        self._n = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.gspaln_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------
+    def _pack(self, problems, kind):
+        n = len(problems)
+        arr = (capi.GspalnTask * max(n, 1))()
+        keep = []
+        for i, p in enumerate(problems):
+            a = np.ascontiguousarray(p.a, np.uint8)
+            b = np.ascontiguousarray(p.b, np.uint8)
+            s5 = np.ascontiguousarray(p.sig5, np.int16)
+            s3 = np.ascontiguousarray(p.sig3, np.int16)
+            if len(a) < p.a_right or len(b) < p.b_right or len(s5) <= p.b_right or len(s3) <= p.b_right:
+                raise ValueError("problem arrays shorter than the stated ranges")
+            keep.append((a, b, s5, s3))
+            t = arr[i]
+            t.kind = kind
+            t.a, t.b = a.ctypes.data, b.ctypes.data
+            t.sig5, t.sig3 = s5.ctypes.data, s3.ctypes.data
+            t.a_left, t.a_right, t.b_left, t.b_right = p.a_left, p.a_right, p.b_left, p.b_right
+            t.a_exgl, t.a_exgr, t.b_exgl, t.b_exgr = p.a_exgl, p.a_exgr, p.b_exgl, p.b_exgr
+            t.lw, t.up = p.lw, p.up
+            cap = p.skl_cap or ((p.a_right - p.a_left) + (p.b_right - p.b_left) + 8)
+            t.skl_cap = cap if kind == capi.FORWARD_WIP else 0
+        return arr, keep
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.gspaln_last_error(self._h)
+            raise EngineError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def _results(self, n, arr):
+        res = (capi.GspalnResult * max(n, 1))()
+        bufs = []
+        for i in range(n):
+            cap = arr[i].skl_cap
+            buf = np.zeros((max(cap, 1), 2), np.int32)
+            bufs.append(buf)
+            res[i].skl = buf.ctypes.data if cap > 0 else None
+        return res, bufs
+
+    def _collect(self, n, res, bufs, arr):
+        out = []
+        for i in range(n):
+            k = min(res[i].n_skl, arr[i].skl_cap)
+            out.append(Result(int(res[i].score), int(res[i].status), bufs[i][:max(k, 0)].copy(),
+                              int(res[i].cells)))
+        return out
+
+    # ---- one-shot (host buffers in, host results out) -------------------
+    def submit(self, problems, kind=capi.FORWARD_WIP):
+        arr, keep = self._pack(problems, kind)
+        n = len(problems)
+        res, bufs = self._results(n, arr)
+        self._check(self.lib.gspaln_submit(self._h, arr, n, res), "gspaln_submit")
+        self._n = n
+        return self._collect(n, res, bufs, arr)
+
+    def forwardS1_wip(self, problems):
+        return self.submit(problems, capi.FORWARD_WIP)
+
+    def scoreonlyS1_wip(self, problems):
+        return self.submit(problems, capi.SCOREONLY_WIP)
+
+    # ---- split form (batch resident in HBM) -----------------------------
+    def upload(self, problems, kind=capi.FORWARD_WIP):
+        arr, keep = self._pack(problems, kind)
+        self._check(self.lib.gspaln_upload(self._h, arr, len(problems)), "gspaln_upload")
+        self._tasks, self._keep, self._n = arr, keep, len(problems)
+
+    def run(self):
+        self._check(self.lib.gspaln_run(self._h), "gspaln_run")
+
+    def download(self):
+        n = self._n
+        res, bufs = self._results(n, self._tasks)
+        self._check(self.lib.gspaln_download(self._h, res), "gspaln_download")
+        return self._collect(n, res, bufs, self._tasks)
+
+    def timing(self) -> Timing:
+        t = capi.GspalnTiming()
+        self.lib.gspaln_get_timing(self._h, C.byref(t))
+        return Timing(t.h2d_ms, t.kernel_ms, t.d2h_ms, t.launches, t.h2d_bytes, t.d2h_bytes,
+                      t.trace_bytes, t.cells)

@@ -78,3 +78,56 @@ def plant_gene(rng, qlen_range=(300, 900), n_exons=None, flank=(200, 800),
 def random_pair(rng, qlen, glen, gc=0.41):
     return (random_dna(rng, glen, gc).tobytes().decode(),
             random_dna(rng, qlen, gc).tobytes().decode())
+
+
+# ---------------------------------------------------------------------------
+# code-level helpers (no reference needed)
+# ---------------------------------------------------------------------------
+# residue codes of the reference's DNA alphabet (src/seq.h: A=2, C=3, G=5, T=9)
+DNA_CODE = np.zeros(256, np.uint8)
+for _ch, _c in (("A", 2), ("C", 3), ("G", 5), ("T", 9), ("N", 16)):
+    DNA_CODE[ord(_ch)] = _c
+    DNA_CODE[ord(_ch.lower())] = _c
+
+
+def encode_dna(s: str) -> np.ndarray:
+    return DNA_CODE[np.frombuffer(s.encode(), np.uint8)]
+
+
+def synthetic_signals(bcodes: np.ndarray, rng, scale: float = 1.0):
+    """Splice-signal tables shaped like Exinon::data_n (src/codepot.cc:479-523)
+    without the PSSM scan: per column n a 5' score driven by the dinucleotide
+    at(n), at(n+1) and a 3' score driven by at(n-2), at(n-1), plus noise.
+    The magnitudes follow the reference's tables for Dictyostelium (x10 scale):
+    GT ~ +40, GC/AT ~ -78, others ~ -250;  AG ~ +27, AC ~ -95, others ~ -260.
+    Returns (sig5, sig3) int16 arrays indexed by column n in [0, len + 1]."""
+    L = len(bcodes)
+    c = np.concatenate([[0], bcodes.astype(np.int64), [0, 0]])     # c[i + 1] = at(i)
+    n = np.arange(L + 2)
+    x, y = c[np.minimum(n + 1, L + 2)], c[np.minimum(n + 2, L + 2)]   # at(n), at(n+1)
+    s5 = np.full(L + 2, -250.0)
+    s5[(x == 5) & (y == 9)] = 40.0
+    s5[(x == 5) & (y == 3)] = -77.0
+    s5[(x == 2) & (y == 9)] = -78.0
+    u, v = c[np.maximum(n - 1, 0)], c[n]                            # at(n-2), at(n-1)
+    s3 = np.full(L + 2, -260.0)
+    s3[(u == 2) & (v == 5)] = 27.0
+    s3[(u == 2) & (v == 3)] = -95.0
+    s5 = s5 * scale + rng.normal(0, 20.0, L + 2)
+    s3 = s3 * scale + rng.normal(0, 20.0, L + 2)
+    s5[0] = s3[0] = 0
+    s5[L + 1] = s3[L + 1] = 0
+    return s5.astype(np.int16), s3.astype(np.int16)
+
+
+def stripe(a_left, a_right, b_left, b_right, sh=100):
+    """band window exactly as `stripe()` (src/aln2.cc:156-176), cmode 0"""
+    up = b_right - a_right
+    lw = b_left - a_left
+    if up < lw:
+        up, lw = lw, up
+    up += sh
+    lw -= sh
+    up = min(up, b_right - a_left)
+    lw = max(lw, b_left - a_right)
+    return lw, up

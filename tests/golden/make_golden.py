@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference
+(oracle/_ref/libspaln_ref.so, built by oracle/Makefile from /root/reference).
+
+Each fixture holds, for one reference option string, the frozen parameters,
+the raw inputs of a set of DP problems (query / genome codes, Exinon splice
+signal table, ranges, end-gap flags, band) and the reference's outputs for
+SimdAln2s1::forwardS1_wip (score + trace-back corners) and scoreonlyS1_wip.
+
+Run in the build container only (needs /root/reference at build time of
+oracle/_ref):   python tests/golden/make_golden.py
+The reference keeps its parameters in process globals, so every option string
+is generated in its own subprocess.
+"""
+from __future__ import annotations
+
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE.parent))
+sys.path.insert(0, str(HERE.parent.parent))
+
+CONFIGS = {
+    # name: (reference options, seed)
+    "dna_A2_global": ("-Q0 -A2 -S1 -yX0 -TDictyost", 11),
+    "dna_A2_local": ("-Q0 -A2 -S1 -yX0 -LS -TDictyost", 12),
+    "dna_A3_global": ("-Q0 -A3 -S1 -yX0 -TDictyost", 13),
+    "dna_A2_tetrapod": ("-Q0 -A2 -S1 -TTetrapod", 14),
+}
+
+
+def gen(name: str):
+    import ref_harness as R
+    from spaln_b200 import workload as synth
+
+    opts, seed = CONFIGS[name]
+    ref = R.Reference(opts)
+    p = ref.params()
+    rng = np.random.default_rng(seed)
+    out = {"opts": np.array(opts)}
+    for k, v in p.items():
+        out["prm_" + k] = np.asarray(v)
+    probs = []
+
+    def add(g, q, comrev=False, tag="", **setkw):
+        t = ref.task(g, q, comrev)
+        if setkw:
+            t.set(**setkw)
+        lw, up = t.stripe(p["sh"])
+        ex = t.export()
+        r = t.kernel(lw, up, 0, cap=1 << 16)
+        r1 = t.kernel(lw, up, 1)
+        i = len(probs)
+        pre = f"p{i}_"
+        out[pre + "a"] = ex["a"]
+        out[pre + "b"] = ex["b"]
+        out[pre + "sig5"] = ex["sig5"]
+        out[pre + "sig3"] = ex["sig3"]
+        out[pre + "geom"] = np.array([ex["a_left"], ex["a_right"], ex["b_left"], ex["b_right"],
+                                      ex["a_exgl"], ex["a_exgr"], ex["b_exgl"], ex["b_exgr"],
+                                      lw, up], np.int32)
+        out[pre + "score"] = np.int32(r["score"])
+        out[pre + "skl"] = r["skl"].astype(np.int32)
+        out[pre + "score_only"] = np.int32(r1["score"])
+        out[pre + "tag"] = np.array(tag)
+        probs.append(i)
+        t.close()
+
+    # planted genes, both orientations of the query
+    for i in range(10):
+        g, q, _ = synth.plant_gene(rng, qlen_range=(60, 500), flank=(50, 300))
+        add(g, q, tag="gene")
+        if i % 3 == 0:
+            add(g, q, comrev=True, tag="gene_rc")
+    # end-gap variants and sub-ranges (UDH post-work style: all four flags 0)
+    g, q, _ = synth.plant_gene(rng, qlen_range=(150, 300), flank=(60, 200))
+    add(g, q, tag="global_left", a_exgl=0, b_exgl=0)
+    add(g, q, tag="global_right", a_exgr=0, b_exgr=0)
+    add(g, q, tag="global_all", a_exgl=0, a_exgr=0, b_exgl=0, b_exgr=0)
+    add(g, q, tag="subrange", a_left=17, a_right=len(q) - 9, b_left=33, b_right=len(g) - 41)
+    add(g, q, tag="subrange_global", a_left=5, a_right=len(q) - 3, b_left=20, b_right=len(g) - 10,
+        a_exgl=0, a_exgr=0, b_exgl=0, b_exgr=0)
+    # ragged / tiny shapes: fewer rows than one strip, exact strip multiples
+    for ql in (1, 2, 7, 15, 16, 17, 31, 32, 33, 48):
+        g2, q2 = synth.random_pair(rng, ql, int(rng.integers(40, 300)))
+        add(g2, q2, tag=f"tiny{ql}")
+    # one query long enough to cross the int16 re-basing check point (> 1472 rows)
+    g, q, _ = synth.plant_gene(rng, qlen_range=(1700, 1900), n_exons=3, flank=(40, 80))
+    add(g, q, tag="rebase")
+    out["n"] = np.int32(len(probs))
+    path = HERE / f"{name}.npz"
+    np.savez_compressed(path, **out)
+    print(name, "problems:", len(probs), "->", path, f"{path.stat().st_size / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        gen(sys.argv[1])
+    else:
+        for name in CONFIGS:
+            subprocess.run([sys.executable, __file__, name], check=True)

@@ -1,0 +1,27 @@
+"""Reader of tests/golden/*.npz (written by tests/golden/make_golden.py)."""
+from pathlib import Path
+
+import numpy as np
+
+GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
+GOLDEN_NAMES = ["dna_A2_global", "dna_A2_local", "dna_A3_global", "dna_A2_tetrapod"]
+GEOM_KEYS = ["a_left", "a_right", "b_left", "b_right", "a_exgl", "a_exgr", "b_exgl", "b_exgr",
+             "lw", "up"]
+
+
+def load(name):
+    z = np.load(GOLDEN_DIR / f"{name}.npz")
+    prm = {}
+    for k in z.files:
+        if k.startswith("prm_"):
+            v = z[k]
+            prm[k[4:]] = v if v.ndim else int(v)
+    probs = []
+    for i in range(int(z["n"])):
+        pre = f"p{i}_"
+        d = {"a": z[pre + "a"], "b": z[pre + "b"], "sig5": z[pre + "sig5"], "sig3": z[pre + "sig3"],
+             "score": int(z[pre + "score"]), "skl": z[pre + "skl"],
+             "score_only": int(z[pre + "score_only"]), "tag": str(z[pre + "tag"])}
+        d.update({k: int(v) for k, v in zip(GEOM_KEYS, z[pre + "geom"])})
+        probs.append(d)
+    return prm, probs

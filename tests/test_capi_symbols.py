@@ -1,0 +1,62 @@
+"""CPU: the C-ABI library loads and exports every symbol include/gspaln.h declares
+(no compute calls: there is no GPU here and no CPU fallback)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_functions():
+    txt = (ROOT / "include" / "gspaln.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(gspaln_[a-z_]+)\s*\(", txt)))
+
+
+def test_header_declares_expected_surface():
+    from spaln_b200 import capi
+    assert declared_functions() == sorted(capi.EXPORTS)
+
+
+def test_library_exports_all_symbols():
+    from spaln_b200 import capi
+    if not capi.LIB_PATH.exists():
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(str(capi.LIB_PATH))
+    for name in declared_functions():
+        assert hasattr(lib, name), name
+    lib.gspaln_version.restype = ctypes.c_char_p
+    assert b"gspaln" in lib.gspaln_version()
+
+
+def test_struct_layouts_match_header():
+    from spaln_b200 import capi
+    # sizes implied by include/gspaln.h on LP64
+    assert ctypes.sizeof(capi.GspalnParams) == 4 * (8 + 8 + 8 + 5) + 4 * 32 * 32
+    assert ctypes.sizeof(capi.GspalnTask) == 8 + 4 * 8 + 4 * 11 + 4
+    assert ctypes.sizeof(capi.GspalnResult) == 32
+
+
+def test_no_cpu_fallback_without_device():
+    """Engine creation must fail loudly when there is no CUDA device."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import golden_io
+    from spaln_b200 import Engine, EngineError
+    prm, _ = golden_io.load("dna_A2_global")
+    with pytest.raises(EngineError):
+        Engine(prm)
+
+
+def test_task_cells_host_helper():
+    from spaln_b200 import capi
+    lib = capi.load()
+    t = capi.GspalnTask()
+    t.a_left, t.a_right, t.b_left, t.b_right, t.lw, t.up = 0, 10, 0, 50, -5, 45
+    # row m: columns max(m-5,0) < n <= min(m+46,50)
+    want = sum(min(m + 46, 50) - max(m - 5, 0) for m in range(1, 11))
+    assert lib.gspaln_task_cells(ctypes.byref(t)) == want

@@ -1,0 +1,141 @@
+"""GPU: the CUDA path (through the C-ABI) against (1) golden vectors from the
+unmodified reference, (2) the C oracle on seeded inputs, (3) size-independent
+properties at larger sizes.  Bar: bit-exact scores and trace-back corners."""
+import numpy as np
+import pytest
+
+import golden_io
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(prm):
+    from spaln_b200 import Engine
+    return Engine(prm, device=0)
+
+
+def _problems(probs):
+    from spaln_b200 import Problem
+    return [Problem.from_export(pb, pb["lw"], pb["up"]) for pb in probs]
+
+
+@pytest.mark.parametrize("name", golden_io.GOLDEN_NAMES)
+def test_forward_wip_matches_reference_golden(name):
+    prm, probs = golden_io.load(name)
+    eng = _engine(prm)
+    res = eng.forwardS1_wip(_problems(probs))
+    for i, (pb, r) in enumerate(zip(probs, res)):
+        assert r.status == 0, (name, i, pb["tag"])
+        assert r.score == pb["score"], (name, i, pb["tag"], r.score, pb["score"])
+        assert np.array_equal(r.skl, pb["skl"]), (name, i, pb["tag"])
+    eng.close()
+
+
+@pytest.mark.parametrize("name", golden_io.GOLDEN_NAMES)
+def test_scoreonly_wip_matches_reference_golden(name):
+    prm, probs = golden_io.load(name)
+    eng = _engine(prm)
+    res = eng.scoreonlyS1_wip(_problems(probs))
+    for i, (pb, r) in enumerate(zip(probs, res)):
+        assert r.score == pb["score_only"], (name, i, pb["tag"], r.score, pb["score_only"])
+    eng.close()
+
+
+def _synthetic(prm, rng, n, qlen, flank, intron_scale=1.0, flags=None, sub=None):
+    from spaln_b200 import workload
+    out = []
+    for _ in range(n):
+        g, q, _t = workload.plant_gene(rng, qlen_range=qlen, flank=flank, intron_scale=intron_scale)
+        a = workload.encode_dna(q)
+        b = workload.encode_dna(g)
+        s5, s3 = workload.synthetic_signals(b, rng)
+        al, ar, bl, br = 0, len(a), 0, len(b)
+        if sub:
+            al, ar, bl, br = sub[0], len(a) - sub[1], sub[2], len(b) - sub[3]
+        lw, up = workload.stripe(al, ar, bl, br, int(prm["sh"]))
+        f = flags or (1, 1, 1, 1)
+        out.append({"a": np.concatenate([[0], a, [0]]).astype(np.uint8),
+                    "b": np.concatenate([[0], b, [0]]).astype(np.uint8),
+                    "sig5": s5, "sig3": s3, "a_left": al, "a_right": ar, "b_left": bl,
+                    "b_right": br, "a_exgl": f[0], "a_exgr": f[1], "b_exgl": f[2], "b_exgr": f[3],
+                    "lw": lw, "up": up})
+    return out
+
+
+@pytest.mark.parametrize("name,flags,sub", [
+    ("dna_A2_global", None, None),
+    ("dna_A2_global", (0, 0, 0, 0), None),
+    ("dna_A2_global", (1, 0, 0, 1), (7, 3, 11, 5)),
+    ("dna_A2_local", None, None),
+    ("dna_A3_global", None, None),
+])
+def test_forward_wip_matches_oracle_seeded(oracle, name, flags, sub):
+    prm, _ = golden_io.load(name)
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(repr((name, flags, sub)).encode()))
+    probs = _synthetic(prm, rng, 24, (30, 700), (30, 400), flags=flags, sub=sub)
+    probs += _synthetic(prm, rng, 3, (1500, 2200), (100, 300), flags=flags, sub=sub)   # re-basing
+    eng = _engine(prm)
+    res = eng.forwardS1_wip(_problems(probs))
+    sco = eng.scoreonlyS1_wip(_problems(probs))
+    for i, (pb, r, s) in enumerate(zip(probs, res, sco)):
+        o = oracle.forward_wip(prm, pb)
+        assert r.status == 0
+        assert r.score == o["score"], (i, r.score, o["score"])
+        assert np.array_equal(r.skl, o["skl"]), i
+        assert s.score == oracle.scoreonly_wip(prm, pb)["score"], i
+    eng.close()
+
+
+def test_long_introns_match_oracle(oracle):
+    """intron-length counter beyond the quantile table / int16 range"""
+    prm, _ = golden_io.load("dna_A2_global")
+    rng = np.random.default_rng(77)
+    probs = _synthetic(prm, rng, 2, (300, 500), (50, 100), intron_scale=300.0)
+    eng = _engine(prm)
+    res = eng.forwardS1_wip(_problems(probs))
+    for pb, r in zip(probs, res):
+        o = oracle.forward_wip(prm, pb, cap=1 << 17)
+        assert r.score == o["score"]
+        assert np.array_equal(r.skl, o["skl"])
+    eng.close()
+
+
+def test_batch_properties_full_size():
+    """BASELINE config-2 sized problems (1-3 kb cDNA): properties that do not
+    need the oracle -- resubmission is idempotent, batch order does not matter,
+    score-only equals the trace-back score, corner lists are monotone walks
+    that start at the reported end and stay inside the matrix."""
+    prm, _ = golden_io.load("dna_A2_global")
+    rng = np.random.default_rng(5)
+    probs = _synthetic(prm, rng, 48, (1000, 3000), (500, 3000))
+    P = _problems(probs)
+    eng = _engine(prm)
+    r1 = eng.forwardS1_wip(P)
+    r2 = eng.forwardS1_wip(P[::-1])[::-1]
+    so = eng.scoreonlyS1_wip(P)
+    for pb, x, y, s in zip(probs, r1, r2, so):
+        assert x.status == 0
+        assert x.score == y.score and np.array_equal(x.skl, y.skl)
+        assert x.score == s.score
+        skl = x.skl
+        assert len(skl) >= 2
+        assert np.all(np.diff(skl[:, 0]) <= 0) and np.all(np.diff(skl[:, 1]) <= 0)
+        assert skl[:, 0].min() >= pb["a_left"] and skl[:, 0].max() <= pb["a_right"]
+        assert skl[:, 1].min() >= pb["b_left"] and skl[:, 1].max() <= pb["b_right"]
+        assert x.cells > 0
+    # planted genes must be recovered with a clearly positive score
+    assert np.median([x.score for x in r1]) > 5000
+    eng.close()
+
+
+def test_empty_batch_and_overflow():
+    prm, probs = golden_io.load("dna_A2_global")
+    eng = _engine(prm)
+    assert eng.forwardS1_wip([]) == []
+    P = _problems(probs[:1])
+    P[0].skl_cap = 2
+    r = eng.forwardS1_wip(P)[0]
+    assert r.status == 1 and r.score == probs[0]["score"]
+    assert np.array_equal(r.skl, probs[0]["skl"][:2])
+    eng.close()
