@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the spliced-alignment DP hot path.
+
+  python bench.py --gpus N --steps K --warmup W            (our engine, CUDA)
+  python bench.py --impl reference --gpus N --steps K ...  (reference CPU SIMD path)
+
+Workload (BASELINE.json configs[1]): synthetic cDNAs of 1-3 kb, each against its
+genomic locus (+- 0.5-5 kb flanks), DNA->DNA spliced alignment, band = stripe()
+with the default shoulder.  One step = one pass of SimdAln2s1::forwardS1_wip
+semantics (score + trace-back corners) over the whole query set.  Metric: GCUPS
+(band cells of the scalar reference loop per second, 1e9).
+
+Rank layout: one process per GPU; queries are sharded by rank (independent
+problems, no data-path collective), weak scaling (fixed queries per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+# frozen reference parameters for `-Q0 -A2 -yX0 -TDictyost` as dumped by the
+# reference itself into tests/golden/dna_A2_global.npz (prm_* keys)
+PARAM_FIXTURE = "dna_A2_global"
+REF_OPTS = "-Q0 -A2 -S1 -yX0 -V2G -TDictyost"
+METRIC = "GCUPS (spliced-DP band cells/s, 1e9) forwardS1_wip, 10k synthetic cDNA 1-3 kb vs genomic loci"
+B_CELL = 2.0    # algorithmic bytes per cell: 1 B trace + 16 B per (column x 16-row strip), DESIGN.md
+
+
+def load_params():
+    import golden_io
+    prm, _ = golden_io.load(PARAM_FIXTURE)
+    return prm
+
+
+def make_workload(n_queries, seed):
+    from spaln_b200 import workload
+    rng = np.random.default_rng(seed)
+    return [workload.config2_problem(rng) for _ in range(n_queries)]
+
+
+def to_problems(raw):
+    from spaln_b200 import Problem
+    return [Problem(a=r["a"], b=r["b"], sig5=r["sig5"], sig3=r["sig3"], a_left=r["a_left"],
+                    a_right=r["a_right"], b_left=r["b_left"], b_right=r["b_right"], lw=r["lw"],
+                    up=r["up"], a_exgl=1, a_exgr=1, b_exgl=1, b_exgr=1, skl_cap=512) for r in raw]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+# ---------------------------------------------------------------------------
+# reference CPU path (oracle/_ref): the one place bench.py executes oracle/
+# ---------------------------------------------------------------------------
+def reference_run(raw, steps, warmup, threads):
+    """Times SimdAln2s1::forwardS1_wip of the unmodified reference (AVX2 build)
+    on `raw` problems with `threads` host threads.  Returns (gcups per step list,
+    cells per step, results of last step)."""
+    import ref_harness as R
+    if not R.available():
+        return None
+    ref = R.Reference._instance or R.Reference(REF_OPTS)
+    tasks = []
+    for r in raw:
+        t = ref.task(r["genome_str"], r["query_str"])
+        ex = t.export()
+        assert np.array_equal(ex["a"][1:-1], r["a"]) and np.array_equal(ex["b"][1:-1], r["b"])
+        t.inject(r["sig5"], r["sig3"])
+        tasks.append(t)
+    cells = sum(int(r["cells"]) for r in raw)
+    out = [None] * len(tasks)
+
+    def work(tid):
+        for i in range(tid, len(tasks), threads):
+            out[i] = tasks[i].kernel(raw[i]["lw"], raw[i]["up"], 0, cap=4096)
+
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+        [x.start() for x in th]
+        [x.join() for x in th]
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    for t in tasks:
+        t.close()
+    return times, cells, out
+
+
+def host_cells(raw):
+    import ctypes as C
+    from spaln_b200 import capi
+    lib = capi.load()
+    for r in raw:
+        t = capi.GspalnTask()
+        t.a_left, t.a_right, t.b_left, t.b_right = r["a_left"], r["a_right"], r["b_left"], r["b_right"]
+        t.lw, t.up = r["lw"], r["up"]
+        r["cells"] = int(lib.gspaln_task_cells(C.byref(t)))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gspaln", choices=["gspaln", "reference"])
+    ap.add_argument("--queries", type=int, default=10000, help="queries per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="problems in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_gpus = args.gpus
+    prm = load_params()
+    ncores = os.cpu_count() or 1
+    workload_name = (f"config2: {args.queries} synthetic cDNA 1-3 kb x genomic locus (+-0.5-5 kb), "
+                     "DNA spliced, band=stripe(sh=100), -A2 semantics, trace-back kernel (-V raised)")
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        nsample = max(ncores, min(args.cpu_sample, 4 * ncores))
+        raw = make_workload(nsample, seed=20251017)
+        host_cells(raw)
+        r = reference_run(raw, args.steps, max(1, args.warmup), ncores)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
+            return 0
+        times, cells, _ = r
+        ms = 1e3 * float(np.mean(times))
+        val = cells / (ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": val, "unit": "GCUPS", "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(1, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": workload_name, "sample": f"{nsample} problems of the workload per step"},
+            "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": ncores, "kind": "reference",
+                             "sample": f"{nsample} config-2 problems ({cells / 1e6:.0f} Mcells) per step, "
+                                       f"SimdAln2s1::forwardS1_wip AVX2, {ncores} threads"},
+            "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        print("bench.py: no CUDA device; the DP engine has no CPU fallback", file=sys.stderr)
+        return 2
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from spaln_b200 import Engine
+    raw = make_workload(args.queries, seed=20251017 + 7919 * rank)
+    host_cells(raw)
+    problems = to_problems(raw)
+    cells_step = sum(r["cells"] for r in raw)
+    eng = Engine(prm, device=local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`)
+    eng.upload(problems)
+    for _ in range(args.warmup):
+        eng.run()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    kern_ms = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.run()                                   # blocks until the stream drains
+        kern_ms.append(eng.timing().kernel_ms)      # CUDA events on the launching stream
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    tm = eng.timing()
+    launches_per_step = tm.launches
+    dev_s = sum(kern_ms) * 1e-3
+    res = eng.download()
+    bad = sum(1 for r in res if r.status != 0)
+
+    # ---- end to end through the public API with host buffers (`e2e`)
+    e2e_steps = max(1, min(args.steps, 2))
+    eng.submit(problems[: max(1, len(problems) // 50)])     # warm the pinned/device pools
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res2 = eng.forwardS1_wip(problems)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    tm2 = eng.timing()
+
+    if world > 1:
+        t = torch.tensor([dev_s, wall, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, wall, e2e_s = [float(x) for x in t.tolist()]
+        c = torch.tensor([cells_step, bad], dtype=torch.int64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        cells_total, bad = int(c[0]), int(c[1])
+    else:
+        cells_total = cells_step
+
+    if rank == 0:
+        ms_per_step = 1e3 * dev_s / args.steps
+        value = cells_total / (ms_per_step * 1e-3) / 1e9
+        peak, peak_kind = measured_peak()
+        k_ms = float(np.mean(kern_ms))
+        achieved = cells_step * B_CELL / (k_ms * 1e-3) / 1e9       # GB/s of this rank's kernel
+        line = {
+            "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16", "data": "synthetic",
+            "config": {"workload": workload_name, "queries_per_gpu": args.queries,
+                       "cells_per_step_per_gpu": cells_step,
+                       "l2_policy": "inputs+trace per step far larger than L2 (no flush needed)",
+                       "parallelism": f"query-shard x{n_gpus}, no data-path collective"},
+            "wall_ms_per_step": 1e3 * wall / args.steps,
+            "queries_per_s": args.queries * n_gpus / (ms_per_step * 1e-3),
+            "clocks": clocks,
+            "e2e": {"value": cells_total / e2e_s / 1e9, "unit": "GCUPS",
+                    "h2d_bytes_per_step": int(tm2.h2d_bytes), "d2h_bytes_per_step": int(tm2.d2h_bytes),
+                    "queries_per_s": args.queries * n_gpus / e2e_s,
+                    "phases_ms": {"h2d": tm2.h2d_ms, "kernel": tm2.kernel_ms, "d2h": tm2.d2h_ms,
+                                  "total": 1e3 * e2e_s}},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "bytes_per_cell": B_CELL, "kernel": "dp_wip_kernel<true>",
+                         "kernel_ms": k_ms,
+                         "note": "integer-ALU bound DP: see DESIGN.md (HBM roof is not the binding one)"},
+            "status_errors": bad,
+        }
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            nsample = min(args.cpu_sample, len(raw))
+            sample = raw[:nsample]
+            r = reference_run(sample, 1, 1, ncores)
+            if r is not None:
+                times, cells, out = r
+                # the reference results must equal ours on the sample
+                mism = sum(1 for i in range(nsample)
+                           if out[i]["score"] != res2[i].score or not np.array_equal(out[i]["skl"], res2[i].skl))
+                line["cpu_baseline"] = {
+                    "value": cells / float(np.mean(times)) / 1e9, "unit": "GCUPS", "cores": ncores,
+                    "kind": "reference",
+                    "sample": f"first {nsample} problems of the step ({cells / 1e6:.0f} Mcells), "
+                              f"SimdAln2s1::forwardS1_wip AVX2 build, {ncores} threads",
+                    "parity_mismatches_on_sample": mism}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": ncores, "kind": "reference",
+                                        "sample": "oracle/_ref not available"}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -84,7 +84,8 @@ struct gspaln_ctx {
     // resident batch
     int n = 0;
     int n_trace = 0, n_score = 0;
-    size_t a_bytes = 0, c_elems = 0, band_elems = 0, trace_bytes = 0, skl_elems = 0;
+    size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, skl_elems = 0;
+    int grid_run_trace = 0, grid_run_score = 0;
     std::vector<int64_t> cells;
     std::vector<int> skl_cap;
     gspaln_timing tim;
@@ -205,7 +206,7 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
     CK(cudaSetDevice(ctx->device));
     ctx->n = 0;
     // ---- layout
-    size_t a_bytes = 0, c_elems = 0, band_elems = 0, trace_bytes = 0, skl_elems = 0;
+    size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, skl_elems = 0;
     ctx->cells.assign(n, 0);
     ctx->skl_cap.assign(n, 0);
     std::vector<DevTask> dt(n);
@@ -227,12 +228,12 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         const int width = t.up - t.lw + 3;
         d.a_off = (long long) a_bytes;      a_bytes += align_up((size_t) mw + 1, 16);
         d.col_off = (long long) c_elems;    c_elems += align_up((size_t) nw + 2, 4);
-        d.band_off = (long long) band_elems; band_elems += align_up((size_t) width + 2 * NELEM, 32);
-        d.trace_off = (long long) trace_bytes;
+        band_slab = std::max(band_slab, align_up((size_t) width + 2 * NELEM, 32));
         d.skl_off = (long long) skl_elems;
+        d.pad1 = 0;
         if (t.kind == GSPALN_FORWARD_WIP) {
             const size_t nstrips = (mw + NELEM - 1) / NELEM;
-            trace_bytes += align_up(nstrips * (size_t) (width + TRACE_PAD) * NELEM + 64, 256);
+            trace_slab = std::max(trace_slab, align_up(nstrips * (size_t) (width + TRACE_PAD) * NELEM + 64, 256));
             skl_elems += (size_t) d.skl_cap;
             ++n_trace;
         } else
@@ -246,10 +247,30 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         return fail(ctx, GSPALN_ENOMEM, "pinned host allocation");
     if (ctx->d_tasks.reserve(n + 1) != cudaSuccess || ctx->d_order.reserve(n + 1) != cudaSuccess ||
         ctx->d_apool.reserve(a_bytes + 16) != cudaSuccess || ctx->d_cpool.reserve(c_elems + 4) != cudaSuccess ||
-        ctx->d_band.reserve(band_elems + 32) != cudaSuccess || ctx->d_trace.reserve(trace_bytes + 256) != cudaSuccess ||
         ctx->d_skl.reserve(skl_elems + 1) != cudaSuccess || ctx->d_res.reserve(n + 1) != cudaSuccess) {
         cudaGetLastError();
         return fail(ctx, GSPALN_ENOMEM, "device allocation");
+    }
+    // per-warp workspaces; shrink the grid if the trace slabs would not fit
+    {
+        auto ctas = [&](int full, int count) {
+            return std::max(1, std::min(full, (count + WARPS_PER_CTA - 1) / WARPS_PER_CTA));
+        };
+        int gt = n_trace ? ctas(ctx->grid_trace, n_trace) : 0;
+        int gs = n_score ? ctas(ctx->grid_score, n_score) : 0;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        free_b += ctx->d_trace.cap + ctx->d_band.cap * sizeof(unsigned);
+        const size_t budget = (size_t) (0.85 * (double) free_b);
+        while (gt > 1 && (size_t) gt * WARPS_PER_CTA * (trace_slab + band_slab * 4) > budget) gt = gt * 3 / 4;
+        const size_t warps = (size_t) std::max(gt, gs) * WARPS_PER_CTA;
+        if (ctx->d_band.reserve(warps * band_slab + 32) != cudaSuccess ||
+            ctx->d_trace.reserve((size_t) gt * WARPS_PER_CTA * trace_slab + 256) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, GSPALN_ENOMEM, "device workspace allocation");
+        }
+        ctx->grid_run_trace = gt;
+        ctx->grid_run_score = gs;
     }
     // ---- pack (host work is part of the end-to-end path)
     for (int i = 0; i < n; ++i) {
@@ -285,8 +306,8 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
     ctx->tim.h2d_ms = ms;
     ctx->tim.h2d_bytes = (int64_t) (sizeof(DevTask) * n + sizeof(int) * n + a_bytes + sizeof(ColInfo) * c_elems);
     ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score;
-    ctx->a_bytes = a_bytes; ctx->c_elems = c_elems; ctx->band_elems = band_elems;
-    ctx->trace_bytes = trace_bytes; ctx->skl_elems = skl_elems;
+    ctx->a_bytes = a_bytes; ctx->c_elems = c_elems; ctx->band_slab = band_slab;
+    ctx->trace_slab = trace_slab; ctx->skl_elems = skl_elems;
     int64_t cells = 0, tb = 0;
     for (int i = 0; i < n; ++i) {
         cells += ctx->cells[i];
@@ -305,21 +326,20 @@ int gspaln_run(gspaln_ctx* ctx)
     int launches = 0;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (n > 0) {
-        const int warps_needed = n;
         if (ctx->n_trace) {
             CK(cudaMemsetAsync(ctx->d_ticket.p, 0, sizeof(int), ctx->stream));
-            int grid = std::min(ctx->grid_trace, (warps_needed + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-            dp_wip_kernel<true><<<grid, 32 * WARPS_PER_CTA, 0, ctx->stream>>>(
+            dp_wip_kernel<true><<<ctx->grid_run_trace, 32 * WARPS_PER_CTA, 0, ctx->stream>>>(
                 ctx->d_prm.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p,
-                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, ctx->d_trace.p, ctx->d_skl.p, ctx->d_res.p);
+                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
+                ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p);
             ++launches;
         }
         if (ctx->n_score) {
             CK(cudaMemsetAsync(ctx->d_ticket.p + 1, 0, sizeof(int), ctx->stream));
-            int grid = std::min(ctx->grid_score, (warps_needed + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-            dp_wip_kernel<false><<<grid, 32 * WARPS_PER_CTA, 0, ctx->stream>>>(
+            dp_wip_kernel<false><<<ctx->grid_run_score, 32 * WARPS_PER_CTA, 0, ctx->stream>>>(
                 ctx->d_prm.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p + 1,
-                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, ctx->d_trace.p, ctx->d_skl.p, ctx->d_res.p);
+                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
+                ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p);
             ++launches;
         }
         CK(cudaGetLastError());

@@ -58,9 +58,8 @@ struct DevTask {
     int pad0;
     long long a_off;            // into query-code pool; element 0 == a->at(a_left)
     long long col_off;          // into ColInfo pool; element 0 == column b_left
-    long long band_off;         // into band pool (uint32 per diagonal)
-    long long trace_off;        // into trace pool (bytes)
     long long skl_off;          // into corner pool (int2)
+    long long pad1;
 };
 
 struct DevResult {
@@ -356,8 +355,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA)
 dp_wip_kernel(const DevParams* __restrict__ gP, const DevTask* __restrict__ tasks,
               const int* __restrict__ order, int ntasks, int* ticket,
               const unsigned char* __restrict__ apool, const ColInfo* __restrict__ cpool,
-              unsigned* bandpool, unsigned char* tracepool, int2* sklpool,
-              DevResult* results)
+              unsigned* bandpool, long long band_slab, unsigned char* tracepool,
+              long long trace_slab, int2* sklpool, DevResult* results)
 {
     __shared__ DevParams sP;
     {
@@ -368,6 +367,11 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const DevTask* __restrict__ task
     __syncthreads();
     const DevParams& P = sP;
     const int lane = threadIdx.x & 31;
+    // per-warp workspace: band rows and trace matrix are reused by every
+    // problem this warp picks up (the walk runs before the next forward pass)
+    const long long wslot = (long long) blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    unsigned* band = bandpool + wslot * band_slab;
+    unsigned char* trace = TRACE ? tracepool + wslot * trace_slab : nullptr;
 
     for (;;) {
         int tk = 0;
@@ -379,8 +383,6 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const DevTask* __restrict__ task
         if ((t.kind == 0) != TRACE) continue;       // handled by the other instantiation
         const unsigned char* aseq = apool + t.a_off;
         const ColInfo* cols = cpool + t.col_off;
-        unsigned* band = bandpool + t.band_off;
-        unsigned char* trace = TRACE ? tracepool + t.trace_off : nullptr;
         const int width = t.up - t.lw + 3;
         const int buf_size = width + 2 * NELEM;
         const bool a_exgl = t.flags & 1, a_exgr = t.flags & 2, b_exgl = t.flags & 4, b_exgr = t.flags & 8;

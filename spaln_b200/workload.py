@@ -131,3 +131,73 @@ def stripe(a_left, a_right, b_left, b_right, sh=100):
     up = min(up, b_right - a_left)
     lw = max(lw, b_left - a_right)
     return lw, up
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json config 2: synthetic cDNA (1-3 kb) against its genomic locus
+# ---------------------------------------------------------------------------
+def config2_pair(rng, qlen_range=(1000, 3000), flank=(500, 5000), intron_scale=1.0,
+                 sub=0.01, indel=0.002, gc=0.41):
+    """One (genome segment, cDNA) pair of the config-2 shape:
+    exon lengths ~ LogNormal(ln 150, 0.6) clipped to [30, 2000] drawn until the
+    transcript reaches a target length U[1000, 3000]; GT..AG introns from a
+    heavy-tailed length model; locus +- U[500, 5000] nt flanks; 1 % substitutions
+    and 0.2 % indels in the query.  Returns code arrays (uint8) and exon truth."""
+    target = int(rng.integers(qlen_range[0], qlen_range[1] + 1))
+    exl = []
+    tot = 0
+    while tot < target:
+        e = int(np.clip(rng.lognormal(np.log(150.0), 0.6), 30, 2000))
+        e = min(e, target - tot) if target - tot >= 30 else e
+        exl.append(e)
+        tot += e
+    introns = intron_lengths(rng, len(exl) - 1, intron_scale)
+    fl = int(rng.integers(flank[0], flank[1] + 1))
+    fr = int(rng.integers(flank[0], flank[1] + 1))
+    glen = fl + fr + tot + int(introns.sum())
+    genome = random_dna(rng, glen, gc)
+    pos = fl
+    mrna = []
+    truth = []
+    for i, e in enumerate(exl):
+        mrna.append(genome[pos:pos + e])
+        truth.append((pos, pos + e))
+        pos += e
+        if i < len(exl) - 1:
+            il = int(introns[i])
+            genome[pos:pos + 2] = np.frombuffer(b"GT", np.uint8)
+            genome[pos + il - 2:pos + il] = np.frombuffer(b"AG", np.uint8)
+            pos += il
+    q = np.concatenate(mrna).copy()
+    nsub = rng.binomial(len(q), sub)
+    if nsub:
+        idx = rng.choice(len(q), size=nsub, replace=False)
+        q[idx] = ALPHA[rng.integers(0, 4, size=nsub)]
+    nind = rng.binomial(len(q), indel)
+    if nind:
+        where = np.sort(rng.choice(np.arange(1, len(q) - 1), size=nind, replace=False))
+        keep = np.ones(len(q), bool)
+        dele = rng.random(nind) < 0.5
+        keep[where[dele]] = False
+        ins_at = where[~dele]
+        q = np.insert(q, ins_at, ALPHA[rng.integers(0, 4, size=len(ins_at))]) if len(ins_at) else q
+        if dele.any():
+            # positions shift after insertion; recompute a deletion mask on the new array
+            shift = np.searchsorted(ins_at, where[dele])
+            keep2 = np.ones(len(q), bool)
+            keep2[where[dele] + shift] = False
+            q = q[keep2]
+    return genome, q, truth
+
+
+def config2_problem(rng, sh=100, **kw):
+    """config-2 pair -> raw DP inputs (codes, synthetic splice-signal tables, band)."""
+    g, q, truth = config2_pair(rng, **kw)
+    a = DNA_CODE[q]
+    b = DNA_CODE[g]
+    s5, s3 = synthetic_signals(b, rng)
+    lw, up = stripe(0, len(a), 0, len(b), sh)
+    return {"a": a, "b": b, "sig5": s5, "sig3": s3, "a_left": 0, "a_right": len(a),
+            "b_left": 0, "b_right": len(b), "a_exgl": 1, "a_exgr": 1, "b_exgl": 1, "b_exgr": 1,
+            "lw": lw, "up": up, "truth": truth,
+            "genome_str": g.tobytes().decode(), "query_str": q.tobytes().decode()}
