@@ -75,6 +75,9 @@ int ref_setup(const char* optstr, const char* genome_fa, const char* query_fa)
 	if (!seqs[1]->getseq(genome_fa)) return -1;
 	if (!seqs[0]->getseq(query_fa)) return -2;
 	g_pwd = SetUpPwd(seqs);
+	// Aln2s1's constructor flattens the ILD under -A3 (src/fwd2s1.cc:125);
+	// kernel-level calls bypass that constructor, so apply it here
+	if ((algmode.alg & 3) == 3) IntronPrm.nquant = 1;
 	b_intr = seqs[1]->inex.intr;
 	if (seqs[0]->inex.intr || seqs[1]->inex.intr) makeStdSig53();
 	clearseq(seqs, 3);

@@ -66,6 +66,9 @@ struct gspaln_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf<DevParams> d_prm;
+    DevBuf<int2> d_pen;
+    int pen_cap = 0;
+    size_t smem_bytes = 0;
     DevBuf<DevTask> d_tasks;
     DevBuf<int> d_order;
     DevBuf<int> d_ticket;
@@ -106,6 +109,26 @@ int fail(gspaln_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, GSPALN_ECUDA, #call, e_); } while (0)
 
+using KernelFn = void (*)(const DevParams*, const int2*, const DevTask*, const int*, int, int*,
+                          const unsigned char*, const ColInfo*, unsigned*, long long,
+                          unsigned char*, long long, int2*, DevResult*);
+
+KernelFn kernel_fn(bool trace, bool local, bool spj)
+{
+    static const KernelFn tab[8] = {
+        dp_wip_kernel<false, false, false>, dp_wip_kernel<false, false, true>,
+        dp_wip_kernel<false, true, false>, dp_wip_kernel<false, true, true>,
+        dp_wip_kernel<true, false, false>, dp_wip_kernel<true, false, true>,
+        dp_wip_kernel<true, true, false>, dp_wip_kernel<true, true, true>,
+    };
+    return tab[(trace ? 4 : 0) | (local ? 2 : 0) | (spj ? 1 : 0)];
+}
+
+const void* kernel_ptr(bool trace, bool local, bool spj)
+{
+    return reinterpret_cast<const void*>(kernel_fn(trace, local, spj));
+}
+
 int64_t task_cells(const gspaln_task& t)
 {
     // rows m in (a_left, a_right], columns max(m + lw, b_left) < n <= min(m + up + 1, b_right)
@@ -140,7 +163,8 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
     if (!out || !prm) return GSPALN_EINVAL;
     *out = nullptr;
     if (prm->noll != 2 || prm->simdim <= 0 || prm->simdim >= ZROW ||
-        prm->nquant < 1 || prm->nquant > GSPALN_MAXQUANT || prm->avmch <= 0)
+        prm->nquant < 1 || prm->nquant > GSPALN_MAXQUANT || prm->avmch <= 0 ||
+        (short) prm->gep > 0 || (short) (prm->gep + prm->gop) > 0)     // kernels clamp gap terms on the low side only
         return GSPALN_EINVAL;
     int ndev = gspaln_device_count();
     if (ndev <= 0 || device < 0 || device >= ndev) return GSPALN_ENODEV;
@@ -172,16 +196,43 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
     for (int q = 0; q < prm->simdim; ++q)
         for (int g = 0; g < prm->simdim; ++g)
             P.mtxT[g * MTX_LD + q] = (short) prm->simmtx[q * prm->simdim + g];
+    // binned intron-length penalty as a table over the (saturating) length
+    // counter: src/fwd2s1_wip_simd.h:389-396.  Entry h: {penalty, lower clamp};
+    // lengths <= llmt give exactly nevsel.
+    int cap = std::max(0, P.mil);
+    for (int j = 0; j + 1 < P.nquant; ++j) cap = std::max(cap, P.quant[j]);
+    cap += 1;
+    std::vector<int2> pen(cap + 1);
+    for (int h = 0; h <= cap; ++h) {
+        int pv = P.mean[0];
+        for (int j = 1; j < P.nquant; ++j) if (h > P.quant[j - 1]) pv = P.mean[j];
+        const bool valid = h > P.mil;
+        pen[h] = make_int2(valid ? pv : PEN_INVALID, valid ? -32768 : NEV);
+    }
+    P.pen_cap = cap;
+    ctx->pen_cap = cap;
+    ctx->smem_bytes = sizeof(RingEntry) * RING * CTA_THREADS + sizeof(int2) * (size_t) (cap + 1);
+    if (ctx->smem_bytes > 108 * 1024) {     // two CTAs per SM must fit
+        gspaln_destroy(ctx);
+        return GSPALN_EINVAL;
+    }
     if (ctx->d_prm.reserve(1) != cudaSuccess || ctx->d_ticket.reserve(4) != cudaSuccess ||
+        ctx->d_pen.reserve(cap + 1) != cudaSuccess ||
+        cudaMemcpy(ctx->d_pen.p, pen.data(), sizeof(int2) * (cap + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(ctx->d_prm.p, &P, sizeof(P), cudaMemcpyHostToDevice) != cudaSuccess) {
         gspaln_destroy(ctx);
         return GSPALN_ENOMEM;
     }
+    const void* kt = kernel_ptr(true, P.local, P.spj);
+    const void* ks = kernel_ptr(false, P.local, P.spj);
+    cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_bytes);
+    cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_bytes);
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dp_wip_kernel<true>, 32 * WARPS_PER_CTA, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kt, CTA_THREADS, ctx->smem_bytes);
     ctx->grid_trace = std::max(1, occ) * ctx->sm_count;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dp_wip_kernel<false>, 32 * WARPS_PER_CTA, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ks, CTA_THREADS, ctx->smem_bytes);
     ctx->grid_score = std::max(1, occ) * ctx->sm_count;
+    if (cudaGetLastError() != cudaSuccess) { gspaln_destroy(ctx); return GSPALN_ECUDA; }
     *out = ctx;
     return GSPALN_OK;
 }
@@ -190,7 +241,7 @@ void gspaln_destroy(gspaln_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    ctx->d_prm.release(); ctx->d_tasks.release(); ctx->d_order.release(); ctx->d_ticket.release();
+    ctx->d_prm.release(); ctx->d_pen.release(); ctx->d_tasks.release(); ctx->d_order.release(); ctx->d_ticket.release();
     ctx->d_apool.release(); ctx->d_cpool.release(); ctx->d_band.release(); ctx->d_trace.release();
     ctx->d_skl.release(); ctx->d_res.release();
     ctx->h_tasks.release(); ctx->h_order.release(); ctx->h_apool.release(); ctx->h_cpool.release();
@@ -326,18 +377,19 @@ int gspaln_run(gspaln_ctx* ctx)
     int launches = 0;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (n > 0) {
+        const bool local = ctx->prm.local != 0, spj = ctx->prm.spj != 0;
         if (ctx->n_trace) {
             CK(cudaMemsetAsync(ctx->d_ticket.p, 0, sizeof(int), ctx->stream));
-            dp_wip_kernel<true><<<ctx->grid_run_trace, 32 * WARPS_PER_CTA, 0, ctx->stream>>>(
-                ctx->d_prm.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p,
+            kernel_fn(true, local, spj)<<<ctx->grid_run_trace, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+                ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p,
                 ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
                 ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p);
             ++launches;
         }
         if (ctx->n_score) {
             CK(cudaMemsetAsync(ctx->d_ticket.p + 1, 0, sizeof(int), ctx->stream));
-            dp_wip_kernel<false><<<ctx->grid_run_score, 32 * WARPS_PER_CTA, 0, ctx->stream>>>(
-                ctx->d_prm.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p + 1,
+            kernel_fn(false, local, spj)<<<ctx->grid_run_score, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+                ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p + 1,
                 ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
                 ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p);
             ++launches;

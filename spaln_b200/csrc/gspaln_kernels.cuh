@@ -4,18 +4,24 @@
 // the reference (src/fwd2s1_wip_simd.h:42-474, src/fwd2s1_simd.cc:163-262,
 // src/rhomb_coord.h:65-235) at the AVX2 lane count (strips of 16 query rows).
 //
-// Mapping (NOT the reference's): one warp owns one DP problem.  A lane owns one
-// 16-row strip and walks it column by column with the four per-row state
-// words (H, E, best-donor value, intron length) of all 16 rows in registers;
-// the vertical dependency runs down the column inside the thread.  The 32
-// strips of a pass form a systolic chain: lane t is LAG columns behind lane
-// t-1 and receives the (H, F) of the row above through the task's
-// diagonal-indexed band buffer in global memory (one packed int16x2 word per
-// diagonal, L2 resident, read with ld.global.cg one iteration ahead).  The
-// band buffer has exactly the reference's hv[]/fv[] semantics, including
-// entries that persist because a strip did not overwrite them.
-// Trace codes leave as one 16-byte store per lane per column.
+// Mapping (NOT the reference's): one warp owns one DP problem.  A thread owns
+// one 16-row strip and evaluates it along anti-diagonals: at step n its row k
+// sits on column n - k, so the 16 cell updates of a step are independent
+// (ILP 16, no serial chain) and all rows of a strip start and stop together,
+// exactly like the lanes of the reference's vector -- including the cells
+// that lie outside the matrix.  All per-row state (H of the last two steps,
+// F, E, best donor value, intron length) lives in registers.  The 32 strips
+// of a pass form a systolic chain: thread t runs 15 + LAG steps behind
+// thread t-1 and receives the (H, F) of the row above it through the
+// problem's diagonal-indexed band buffer in global memory (one packed
+// int16x2 word per diagonal, L2 resident, fetched with ld.global.cg one
+// iteration ahead).  The band buffer has exactly the reference's hv[]/fv[]
+// semantics, including entries that persist because nobody overwrote them.
+// Per-column inputs (substitution-table row, 3'/5' signals) sit in a small
+// per-thread shared-memory ring so that row k can read column n - k with an
+// immediate offset.  Trace codes leave as one 16-byte store per thread/step.
 #pragma once
+#include <climits>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -24,12 +30,15 @@ namespace gspaln {
 constexpr int NELEM = 16;               // rows per strip == reference nelem (AVX2)
 constexpr int NEV = -32768 + 1024;      // nevsel, src/fwd2s1_simd.h:47,202
 constexpr int CHECK_SCR = 29490;        // int(0.9 * SHRT_MAX), src/fwd2s1_simd.h:44
-constexpr int LAG = 2;                  // systolic lag between neighbouring strips (columns)
-constexpr int TRACE_PAD = 46;           // trace columns per strip = width + TRACE_PAD
+constexpr int LAG = 2;                  // extra systolic lag (iterations) hiding the band-load latency
+constexpr int TRACE_PAD = 36;           // trace steps per strip <= width + 31; slab stride width + TRACE_PAD
 constexpr int MAXQ = 8;
-constexpr int MTX_LD = 32;              // leading dimension of the substitution table in smem
-constexpr int ZROW = 31;                // all-zero row: lanes outside the matrix score 0
+constexpr int MTX_LD = 32;              // leading dimension of the substitution table
+constexpr int ZROW = 31;                // all-zero row / column: cells outside the matrix score 0
 constexpr int WARPS_PER_CTA = 4;
+constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
+constexpr int RING = 32;                // doubled 16-entry ring of per-column inputs
+constexpr int PEN_INVALID = -200000;    // added to an int16: always far below the int16 range
 
 // TraceBackCode, src/rhomb_coord.h:36-61
 enum : unsigned { TB_DIAG = 1, TB_HORI = 2, TB_VERT = 8, TB_ACCR = 14,
@@ -40,7 +49,8 @@ struct DevParams {
     int ipen, mil, nquant;
     int quant[MAXQ], mean[MAXQ];
     int avmch, local, spj, simdim, gappen1, gop, gep;
-    short mtxT[MTX_LD * MTX_LD];    // [genome code][query code], row ZROW == 0
+    int pen_cap;                // pen table has pen_cap + 1 entries
+    short mtxT[MTX_LD * MTX_LD];    // [genome code][query code]; row/col ZROW == 0
 };
 
 struct ColInfo {                // one genome column (8 B)
@@ -66,7 +76,16 @@ struct DevResult {
     int score, status, n_skl, pad;
 };
 
+// per-column inputs as the rows consume them
+struct __align__(16) RingEntry {
+    int prof;                   // byte offset of the substitution-table row of this column's residue
+    int s3;                     // acceptor signal
+    int s5;                     // donor signal + mean intron penalty
+    int pad;
+};
+
 __device__ __forceinline__ int sat16(int x) { return max(min(x, 32767), -32768); }
+__device__ __forceinline__ int satlo(int x) { return max(x, -32768); }     // addend <= 0
 __device__ __forceinline__ int lo16(unsigned w) { return (int) (short) (w & 0xffffu); }
 __device__ __forceinline__ int hi16(unsigned w) { return (int) (short) (w >> 16); }
 __device__ __forceinline__ unsigned pack16(int lo, int hi)
@@ -98,179 +117,238 @@ __device__ __forceinline__ StripGeom strip_geom(const DevTask& t, int ml)
 
 struct WarpMax { int val, mr, nr; };
 
+// shared-memory carve-up of one CTA
+struct SmemLayout {
+    RingEntry* ring;            // [RING][CTA_THREADS]
+    const int2* pen;            // [pen_cap + 1] {penalty, lower clamp}
+    const short* mtx;           // [MTX_LD * MTX_LD]
+};
+
 // ---------------------------------------------------------------------------
-// one pass: strips ml0, ml0+16, ... (nstr <= 32), lane t owns strip t
+// one step of one strip: 16 independent cell updates (rows 15 .. 0)
+//   HN: H of the previous step (read as "left" and, shifted by one row, as
+//       "up"); HO: H of two steps ago (read shifted as "diag"); the new H
+//       overwrites HO, so callers alternate the two arrays.
 // ---------------------------------------------------------------------------
-template <bool TRACE>
-__device__ void run_pass(const DevParams& P, const short* __restrict__ smtx,
+template <bool TRACE, bool LOCAL, bool SPJ>
+__device__ __forceinline__ void strip_step(
+    int (&HO)[NELEM], const int (&HN)[NELEM], int (&F)[NELEM], int (&E)[NELEM],
+    int (&V2)[NELEM], int (&IL)[NELEM], const int (&arow)[NELEM],
+    const char* __restrict__ ring_hi, const char* __restrict__ mtx_bytes,
+    const int2* __restrict__ pen_tab, int pen_cap,
+    int up_h, int up_f, int up_d, int gn, int ge, int floorL, unsigned (&tw)[4],
+    int& best_v, int& best_k)
+{
+    if (TRACE) { tw[0] = tw[1] = tw[2] = tw[3] = 0u; }
+#pragma unroll
+    for (int k = NELEM - 1; k >= 0; --k) {
+        // column n - k of this row: ring slot (n & 15) + 16 - k
+        const RingEntry re = *reinterpret_cast<const RingEntry*>(
+            ring_hi - k * (CTA_THREADS * (int) sizeof(RingEntry)));
+        const int left = HN[k];
+        const int uh = k ? HN[k ? k - 1 : 0] : up_h;
+        const int uf = k ? F[k ? k - 1 : 0] : up_f;
+        const int dg = k ? HO[k ? k - 1 : 0] : up_d;
+        unsigned hb = 0;
+        // horizontal: genome residue against a gap (gn, ge <= 0: only the low side can saturate)
+        int x = satlo(left + gn);
+        int e = satlo(E[k] + ge);
+        if (!(e > x)) { e = x; hb = TB_NHOR; }
+        E[k] = e;
+        // vertical: query residue against a gap
+        int f = satlo(uf + ge);
+        x = satlo(uh + gn);
+        if (!(f > x)) { f = x; hb |= TB_NVER; }
+        F[k] = f;
+        // diagonal
+        const int pv = *reinterpret_cast<const short*>(mtx_bytes + re.prof + arow[k]);
+        int h = sat16(pv + dg);
+        unsigned pb = TB_DIAG;
+        if (f > h) { h = f; pb = TB_VERT; }
+        if (e > h) { h = e; pb = TB_HORI; }
+        bool acc = false;
+        if (SPJ) {
+            // acceptor: best donor of this row + 3' signal + binned length penalty,
+            // only if the intron is longer than the lower limit
+            const int q0 = sat16(V2[k] + re.s3);
+            const int2 pq = pen_tab[min(IL[k], pen_cap)];
+            const int q = min(max(q0 + pq.x, pq.y), 32767);
+            if (q > h) { h = q; pb = TB_ACCR; acc = true; }
+        }
+        if (LOCAL) { if (h < floorL) { h = floorL; hb = 0; } }
+        if (SPJ) {
+            // donor
+            int q = sat16(h + re.s5);
+            if (TRACE && acc) q = NEV;          // no empty intron
+            const bool don = q > V2[k];
+            V2[k] = max(V2[k], q);
+            IL[k] = don ? 0 : IL[k];
+            if (TRACE && don) hb |= TB_DONR;
+            IL[k] = min(IL[k] + 1, 32767);
+        }
+        if (LOCAL) {
+            if (h >= best_v) { best_v = h; best_k = k; }    // descending k: ties end at the lowest row
+        }
+        HO[k] = h;
+        if (TRACE) tw[k >> 2] |= (hb | pb) << (8 * (k & 3));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// one pass: strips ml0, ml0+16, ... (nstr <= 32), thread t owns strip t
+// ---------------------------------------------------------------------------
+template <bool TRACE, bool LOCAL, bool SPJ>
+__device__ void run_pass(const DevParams& P, const SmemLayout& sm,
                          const DevTask& t, const unsigned char* __restrict__ aseq,
                          const ColInfo* __restrict__ cols, unsigned* band,
                          unsigned char* trace, int ml0, int nstr, bool localL_now,
                          bool localR, int accscr, WarpMax& wmax)
 {
     const int lane = threadIdx.x & 31;
-    const bool mine = lane < nstr;
     const StripGeom g = strip_geom<TRACE>(t, ml0 + NELEM * lane);
     const int j8 = g.j9 - 1;
-    const int span = g.n_last - g.n_start;          // steps - 1
-    const bool live = mine && span >= 0;
-    const int clo = g.n_start - j8;                 // first column touched by any row
-    const int chi = g.n_last;                       // last column touched
+    const int nsteps = g.n_last - g.n_start + 1;
+    const bool live = lane < nstr && nsteps > 0;
     const int width = t.up - t.lw + 3;
 
-    // Systolic schedule: in iteration i lane t works on column
-    //     c = c0 + i - LAG * t,
-    // i.e. lane t reaches a column LAG iterations after lane t-1 did.  c0 is
-    // chosen so that every lane meets its first column at some i >= 0.
-    int c0 = live ? clo + LAG * lane : INT_MAX;
-    int cend = live ? chi + LAG * lane : INT_MIN;
+    // Systolic schedule.  Thread t needs, at its step n, the band entry of
+    // column n, which thread t-1 (a full strip) produces at ITS step n + 15.
+    // With step j of thread t executed in iteration j + off_t this requires
+    //   off_t = off_{t-1} + (n_start_t - n_start_{t-1}) + 15 + LAG,
+    // which telescopes to the closed form below.
+    const int n_start0 = __shfl_sync(0xffffffffu, g.n_start, 0);
+    const int off = (g.n_start - n_start0) + (NELEM - 1 + LAG) * lane;
+    int niter = live ? off + nsteps : 0;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, o));
-        cend = max(cend, __shfl_xor_sync(0xffffffffu, cend, o));
-    }
-    if (c0 == INT_MAX) return;                      // nothing to do in this pass
-    const int niter = cend - c0 + 1;
+    for (int o = 16; o; o >>= 1) niter = max(niter, __shfl_xor_sync(0xffffffffu, niter, o));
+    if (niter == 0) return;
 
-    int H[NELEM], E[NELEM], V2[NELEM], IL[NELEM], arow[NELEM];
+    int HA[NELEM], HB[NELEM], F[NELEM], E[NELEM], V2[NELEM], IL[NELEM], arow[NELEM];
 #pragma unroll
     for (int k = 0; k < NELEM; ++k) {
-        H[k] = NEV; E[k] = NEV; V2[k] = NEV; IL[k] = 0;
-        arow[k] = (live && k < g.j9) ? aseq[(g.ml - t.a_left) + k] : 0;
+        HA[k] = NEV; HB[k] = NEV; F[k] = NEV; E[k] = NEV; V2[k] = NEV; IL[k] = 0;
+        // rows beyond the last query residue score 0 (reference: pv_a stays 0)
+        arow[k] = (live && k < g.j9) ? 2 * (int) aseq[(g.ml - t.a_left) + k] : 2 * ZROW;
     }
-    const int gn = P.gn, ge = P.ge, mil = P.mil;
+    const int gn = P.gn, ge = P.ge;
     const int floorL = localL_now ? 0 : INT_MIN;
     int prev_uh = NEV;
-    // best local-mode cell of this lane: value, step (n = c + k), row index
-    int bval = INT_MIN, bstep = 0, bk = 0;
+    int bval = INT_MIN, bstep = 0, bk = 0;      // best local-mode cell of this strip
 
-    unsigned char* tr_base = trace + ((long long) (lane + (ml0 - t.a_left) / NELEM) * (width + TRACE_PAD)) * NELEM;
-    const int tr_c0 = t.lw + g.ml - (NELEM - 1);
-    const int band_bias = g.ml + t.lw - 1;          // entry index of diagonal d = c - ml: c - band_bias
+    unsigned char* tr_base = TRACE
+        ? trace + ((long long) (lane + (ml0 - t.a_left) / NELEM) * (width + TRACE_PAD)) * NELEM
+        : nullptr;
+    const int band_bias = g.ml + t.lw - 1;      // band entry of column c (diagonal c - ml): c - band_bias
+    RingEntry* ring = sm.ring + threadIdx.x;    // slot s at ring[s * CTA_THREADS]
+    const char* mtx_bytes = reinterpret_cast<const char*>(sm.mtx);
+    const int ipen = P.ipen;
 
-    // software pipeline registers
-    unsigned nxt_band = 0;
-    ColInfo nxt_col = ColInfo{0, 0, 0, {0, 0, 0}};
-    {
-        const int c = c0 - LAG * lane;              // column of iteration 0
-        if (live && c >= g.n_start && c <= g.n_last) nxt_band = __ldcg(band + (c - band_bias));
-        if (live && c >= t.b_left && c <= t.b_right) nxt_col = cols[c - t.b_left];
-    }
-
-    for (int i = 0; i < niter; ++i) {
-        const int c = c0 + i - LAG * lane;          // this lane's column in iteration i
-        const unsigned cur_band = nxt_band;
-        const ColInfo cur_col = nxt_col;
-        const bool in_box = live && c >= clo && c <= chi;
-        {
-            const int cn = c + 1;
-            if (live && cn >= g.n_start && cn <= g.n_last) nxt_band = __ldcg(band + (cn - band_bias));
-            if (live && cn >= t.b_left && cn <= t.b_right) nxt_col = cols[cn - t.b_left];
+    auto col_entry = [&](int c, bool with_sig) -> RingEntry {
+        RingEntry re;
+        re.pad = 0;
+        re.prof = ZROW * (MTX_LD * 2);
+        re.s3 = 0; re.s5 = 0;
+        if (c >= t.b_left && c <= t.b_right) {
+            // one 8-byte load: {sig5 | sig3 << 16, code}
+            const uint2 ci = __ldg(reinterpret_cast<const uint2*>(cols + (c - t.b_left)));
+            // column b_left carries signals but pairs no residue (ke == 0)
+            if (c > t.b_left) re.prof = (int) (ci.y & 0xffu) * (MTX_LD * 2);
+            if (SPJ && with_sig) {
+                re.s3 = hi16(ci.x);
+                re.s5 = (int) (short) (lo16(ci.x) + ipen);
+            }
         }
-        if (in_box) {
-            const bool bvalid = c > t.b_left && c <= t.b_right;
-            const bool svalid = P.spj && c >= g.n_start && c <= t.b_right;
-            const short* prof = smtx + (bvalid ? (int) cur_col.code : ZROW) * MTX_LD;
-            const int s3 = svalid ? (int) cur_col.sig3 : 0;
-            const int s5 = svalid ? (int) (short) ((int) cur_col.sig5 + P.ipen) : 0;
-            // row above the strip: band buffer (hv[r+1], fv[r+1], hv[r])
-            const bool top = c >= g.n_start;        // row 0 active (c <= n_last holds: c <= chi)
-            int up_h = NEV, up_f = NEV, diag = NEV;
-            if (top) {
-                up_h = lo16(cur_band);
-                up_f = hi16(cur_band);
-                diag = (c == g.n_start) ? lo16(__ldcg(band + (c - 1 - band_bias))) : prev_uh;
-                prev_uh = up_h;
+        return re;
+    };
+
+    unsigned nxt_band = 0;
+    RingEntry nxt_col = col_entry(INT_MIN / 2, false);
+
+    for (int i = -1; i < niter; ++i) {
+        const int j = i - off;
+        if (live && j == -1) {
+            // One iteration before the first step: the entries of columns
+            // n_start - 1 and n_start are final by now (written >= LAG - 1
+            // iterations ago by the strip above).
+            nxt_band = __ldcg(band + (g.n_start - band_bias));
+            prev_uh = lo16(__ldcg(band + (g.n_start - 1 - band_bias)));
+            nxt_col = col_entry(g.n_start, g.n_start <= t.b_right);
+            // ring pre-fill: the 15 columns left of n_start pair residues (if
+            // inside the sequence) but carry no splice signal (s3_a / s5_a
+            // start as zeros, src/fwd2s1_wip_simd.h:291)
+#pragma unroll 1
+            for (int d = 1; d < NELEM; ++d) {
+                const int c = g.n_start - d;
+                const RingEntry re = col_entry(c, false);
+                ring[(c & 15) * CTA_THREADS] = re;
+                ring[((c & 15) + 16) * CTA_THREADS] = re;
             }
-            unsigned tw[4] = {0u, 0u, 0u, 0u};
-            int out_h = NEV, out_f = NEV;
-            const int rel0 = c - g.n_start;         // rel0 + k in [0, span] <=> row k active
+        } else if (live && j >= 0 && j < nsteps) {
+            const int n = g.n_start + j;
+            const unsigned cur_band = nxt_band;
+            const RingEntry cur_col = nxt_col;
+            if (j + 1 < nsteps) {
+                nxt_band = __ldcg(band + (n + 1 - band_bias));
+                nxt_col = col_entry(n + 1, n + 1 <= t.b_right);
+            }
+            const int slot = n & 15;
+            ring[slot * CTA_THREADS] = cur_col;
+            ring[(slot + 16) * CTA_THREADS] = cur_col;
+            const char* ring_hi = reinterpret_cast<const char*>(ring + (slot + 16) * CTA_THREADS);
+            const int up_h = lo16(cur_band), up_f = hi16(cur_band), up_d = prev_uh;
+            prev_uh = up_h;
+            unsigned tw[4];
+            int sv = INT_MIN, sk = 0;
+            if (j & 1)
+                strip_step<TRACE, LOCAL, SPJ>(HB, HA, F, E, V2, IL, arow, ring_hi, mtx_bytes, sm.pen,
+                                              P.pen_cap, up_h, up_f, up_d, gn, ge, floorL, tw, sv, sk);
+            else
+                strip_step<TRACE, LOCAL, SPJ>(HA, HB, F, E, V2, IL, arow, ring_hi, mtx_bytes, sm.pen,
+                                              P.pen_cap, up_h, up_f, up_d, gn, ge, floorL, tw, sv, sk);
+            if (LOCAL && localR) {
+                // vmax over the j9 real rows of this step; strictly greater wins (earlier steps keep ties)
+                int v = INT_MIN, kk = 0;
+                if (g.j9 == NELEM) { v = sv; kk = sk; }
+                else {
 #pragma unroll
-            for (int k = 0; k < NELEM; ++k) {
-                const bool act = (k < g.j9) && ((unsigned) (rel0 + k) <= (unsigned) span);
-                if (act) {
-                    const int left = H[k];
-                    unsigned hb = 0;
-                    // horizontal: genome residue against a gap
-                    int x = sat16(left + gn);
-                    int e = sat16(E[k] + ge);
-                    if (!(e > x)) { e = x; hb = TB_NHOR; }
-                    E[k] = e;
-                    // vertical: query residue against a gap
-                    int f = sat16(up_f + ge);
-                    x = sat16(up_h + gn);
-                    if (!(f > x)) { f = x; hb |= TB_NVER; }
-                    // diagonal
-                    int h = sat16((int) prof[arow[k]] + diag);
-                    unsigned pb = TB_DIAG;
-                    if (f > h) { h = f; pb = TB_VERT; }
-                    if (e > h) { h = e; pb = TB_HORI; }
-                    bool acc = false;
-                    if (P.spj) {
-                        // acceptor: best donor so far + 3' signal + binned length penalty
-                        int q = sat16(V2[k] + s3);
-                        int pen = P.mean[0];
-#pragma unroll
-                        for (int j = 1; j < MAXQ; ++j)
-                            if (j < P.nquant && IL[k] > P.quant[j - 1]) pen = P.mean[j];
-                        q = sat16(q + pen);
-                        if (!(IL[k] > mil)) q = NEV;
-                        if (q > h) { h = q; pb = TB_ACCR; acc = true; }
+                    for (int k = NELEM - 1; k >= 0; --k) {
+                        const int hv = (j & 1) ? HB[k] : HA[k];
+                        if (k < g.j9 && hv >= v) { v = hv; kk = k; }
                     }
-                    if (h < floorL) { h = floorL; hb = 0; }
-                    if (P.spj) {
-                        // donor
-                        int q = sat16(h + s5);
-                        if (TRACE && acc) q = NEV;
-                        if (q > V2[k]) { V2[k] = q; IL[k] = 0; if (TRACE) hb |= TB_DONR; }
-                        IL[k] = min(IL[k] + 1, 32767);
-                    }
-                    if (localR) {
-                        const int step = c + k;
-                        if (h > bval || (h == bval && (step < bstep || (step == bstep && k < bk)))) {
-                            bval = h; bstep = step; bk = k;
-                        }
-                    }
-                    diag = left;
-                    H[k] = h;
-                    up_h = h;
-                    up_f = f;
-                    if (TRACE) tw[k >> 2] |= (hb | pb) << (8 * (k & 3));
-                    if (k == j8) { out_h = h; out_f = f; }
-                } else {
-                    // row not started yet (or finished): the row below sees the
-                    // initial lane contents
-                    diag = H[k];
-                    up_h = H[k];
-                    up_f = NEV;
                 }
-            }
-            if (TRACE) {
-                *reinterpret_cast<uint4*>(tr_base + (long long) (c - tr_c0) * NELEM) =
-                    make_uint4(tw[0], tw[1], tw[2], tw[3]);
+                if (v > bval) { bval = v; bstep = n; bk = kk; }
             }
             // bottom row of the strip -> band buffer (src/fwd2s1_wip_simd.h:438-442)
-            const int rb = c - g.n_start + j8;      // bottom row active?
-            if ((unsigned) rb <= (unsigned) span && c > t.b_left) {
-                const int r0 = c - (g.ml + g.j9);
-                if (r0 >= t.lw && r0 <= t.up)
-                    __stcg(band + (r0 - t.lw + 1), pack16(out_h, out_f));
+            int out_h, out_f;
+            if (g.j9 == NELEM) {
+                out_h = (j & 1) ? HB[NELEM - 1] : HA[NELEM - 1];
+                out_f = F[NELEM - 1];
+            } else {
+                out_h = NEV; out_f = NEV;
+#pragma unroll
+                for (int k = 0; k < NELEM - 1; ++k)
+                    if (k == j8) { out_h = (j & 1) ? HB[k] : HA[k]; out_f = F[k]; }
             }
+            if (TRACE)
+                *reinterpret_cast<uint4*>(tr_base + (long long) j * NELEM) = make_uint4(tw[0], tw[1], tw[2], tw[3]);
+            const int cb = n - j8;                  // column of the bottom row
+            const int r0 = cb - (g.ml + g.j9);
+            if (cb > t.b_left && r0 >= t.lw && r0 <= t.up)
+                __stcg(band + (r0 - t.lw + 1), pack16(out_h, out_f));
         }
         __syncwarp();
     }
 
-    if (localR) {
+    if (LOCAL && localR) {
         // reference order: strips ascending, then step, then lane (first max)
-        int v = (live && bval > INT_MIN) ? bval : INT_MIN;
-        int best = v, who = lane;
+        int best = (live && bval > INT_MIN) ? bval : INT_MIN, who = lane;
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
-            int ov = __shfl_xor_sync(0xffffffffu, best, o);
-            int ow = __shfl_xor_sync(0xffffffffu, who, o);
+            const int ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ow = __shfl_xor_sync(0xffffffffu, who, o);
             if (ov > best || (ov == best && ow < who)) { best = ov; who = ow; }
         }
-        // reference: k1 = lane + 1; mr = ml + k1; nr = n - k1 + 1 with n = step
+        // reference: k1 = lane + 1; mr = ml + k1; nr = n - k1 + 1
         const int mr = __shfl_sync(0xffffffffu, g.ml + bk + 1, who);
         const int nr = __shfl_sync(0xffffffffu, bstep - bk, who);
         if (best > INT_MIN && best + accscr > wmax.val) {
@@ -295,10 +373,9 @@ struct TraceView {
             return (!(T.flags & 1) && cur_n >= 1) ? TB_HORI : 0u;
         const int s = (cur_m - 1) / NELEM, k = (cur_m - 1) % NELEM;
         const StripGeom g = strip_geom<true>(T, T.a_left + s * NELEM);
-        const int c = cur_n + T.b_left;
-        if (c < g.n_start - k || c > g.n_last - k) return 0u;
-        const long long off = ((long long) s * (width + TRACE_PAD) + (c - (T.lw + g.ml - (NELEM - 1)))) * NELEM + k;
-        return trace[off];
+        const int j = cur_n + T.b_left + k - g.n_start;     // step at which row k sat on this column
+        if (j < 0 || j > g.n_last - g.n_start) return 0u;
+        return trace[((long long) s * (width + TRACE_PAD) + j) * NELEM + k];
     }
 };
 
@@ -350,14 +427,16 @@ __device__ int walk_trace(const DevTask& t, const unsigned char* trace, int m_ab
 // ---------------------------------------------------------------------------
 // persistent kernel: each warp pulls problems from a global ticket counter
 // ---------------------------------------------------------------------------
-template <bool TRACE>
-__global__ void __launch_bounds__(32 * WARPS_PER_CTA)
-dp_wip_kernel(const DevParams* __restrict__ gP, const DevTask* __restrict__ tasks,
+template <bool TRACE, bool LOCAL, bool SPJ>
+__global__ void __launch_bounds__(CTA_THREADS)
+dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
+              const DevTask* __restrict__ tasks,
               const int* __restrict__ order, int ntasks, int* ticket,
               const unsigned char* __restrict__ apool, const ColInfo* __restrict__ cpool,
               unsigned* bandpool, long long band_slab, unsigned char* tracepool,
               long long trace_slab, int2* sklpool, DevResult* results)
 {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ DevParams sP;
     {
         const int* src = reinterpret_cast<const int*>(gP);
@@ -366,6 +445,14 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const DevTask* __restrict__ task
     }
     __syncthreads();
     const DevParams& P = sP;
+    SmemLayout sm;
+    sm.ring = reinterpret_cast<RingEntry*>(smem_raw);
+    int2* spen = reinterpret_cast<int2*>(smem_raw + sizeof(RingEntry) * RING * CTA_THREADS);
+    for (int i = threadIdx.x; i <= P.pen_cap; i += blockDim.x) spen[i] = gpen[i];
+    sm.pen = spen;
+    sm.mtx = sP.mtxT;
+    __syncthreads();
+
     const int lane = threadIdx.x & 31;
     // per-warp workspace: band rows and trace matrix are reused by every
     // problem this warp picks up (the walk runs before the next forward pass)
@@ -386,8 +473,8 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const DevTask* __restrict__ task
         const int width = t.up - t.lw + 3;
         const int buf_size = width + 2 * NELEM;
         const bool a_exgl = t.flags & 1, a_exgr = t.flags & 2, b_exgl = t.flags & 4, b_exgr = t.flags & 8;
-        const bool LocalL = P.local && a_exgl && b_exgl;
-        const bool LocalR = P.local && a_exgr && b_exgr;
+        const bool LocalL = LOCAL && a_exgl && b_exgl;
+        const bool LocalR = LOCAL && a_exgr && b_exgr;
 
         // ---- fhinitS1 (src/fwd2s1_simd.cc:163-184); entry i <-> diagonal lw - 1 + i
         for (int i = lane; i < buf_size; i += 32) band[i] = pack16(NEV, NEV);
@@ -429,8 +516,8 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const DevTask* __restrict__ task
             int nstr = min(32, (t.a_right - ml0 + NELEM - 1) / NELEM);
             if (mc >= ml0 && mc < ml0 + nstr * NELEM && ((mc - ml0) % NELEM) == 0)
                 nstr = (mc - ml0) / NELEM + 1;
-            run_pass<TRACE>(P, P.mtxT, t, aseq, cols, band, trace, ml0, nstr,
-                            LocalL && !accscr, LocalR, accscr, wmax);
+            run_pass<TRACE, LOCAL, SPJ>(P, sm, t, aseq, cols, band, trace, ml0, nstr,
+                                        LocalL && !accscr, LocalR, accscr, wmax);
             const int last_ml = ml0 + (nstr - 1) * NELEM;
             if (last_ml == mc) {
                 // src/fwd2s1_wip_simd.h:454-465
