@@ -69,6 +69,7 @@ struct gspaln_ctx {
     DevBuf<int2> d_pen;
     int pen_cap = 0;
     size_t smem_bytes = 0;
+    unsigned char perm[32];
     DevBuf<DevTask> d_tasks;
     DevBuf<int> d_order;
     DevBuf<int> d_ticket;
@@ -193,9 +194,21 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
     }
     P.avmch = prm->avmch; P.local = prm->local ? 1 : 0; P.spj = prm->spj ? 1 : 0;
     P.simdim = prm->simdim; P.gappen1 = prm->gappen1; P.gop = prm->gop; P.gep = prm->gep;
+    // residue code -> table index.  The four unambiguous nucleotides of the
+    // reference's DNA alphabet (A=2, C=3, G=5, T=9) go first so that their 16
+    // pairs fall into 16 distinct shared-memory banks (row stride MTX_LD).
+    {
+        int nxt = 0;
+        bool used[32] = {false};
+        if (prm->simdim == 17)
+            for (int c : {2, 3, 5, 9}) { P.perm[c] = (unsigned char) nxt++; used[c] = true; }
+        for (int c = 0; c < 32; ++c)
+            if (!used[c]) P.perm[c] = (unsigned char) (c < prm->simdim ? nxt++ : ZROW);
+    }
     for (int q = 0; q < prm->simdim; ++q)
         for (int g = 0; g < prm->simdim; ++g)
-            P.mtxT[g * MTX_LD + q] = (short) prm->simmtx[q * prm->simdim + g];
+            P.mtxT[P.perm[g] * MTX_LD + P.perm[q]] = (short) prm->simmtx[q * prm->simdim + g];
+    memcpy(ctx->perm, P.perm, 32);
     // binned intron-length penalty as a table over the (saturating) length
     // counter: src/fwd2s1_wip_simd.h:389-396.  Entry h: {penalty, lower clamp};
     // lengths <= llmt give exactly nevsel.
@@ -328,14 +341,14 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         const gspaln_task& t = tasks[i];
         const DevTask& d = dt[i];
         const int mw = t.a_right - t.a_left, nw = t.b_right - t.b_left;
-        memcpy(ctx->h_apool.p + d.a_off, t.a + t.a_left, (size_t) mw);
+        for (int j = 0; j < mw; ++j) ctx->h_apool.p[d.a_off + j] = ctx->perm[t.a[t.a_left + j] & 31];
         ColInfo* col = ctx->h_cpool.p + d.col_off;
         for (int j = 0; j <= nw; ++j) {
             const int c = t.b_left + j;             // column c pairs genome residue at(c - 1)
             ColInfo ci;
             ci.sig5 = ctx->prm.spj ? t.sig5[c] : 0;
             ci.sig3 = ctx->prm.spj ? t.sig3[c] : 0;
-            ci.code = j > 0 ? t.b[c - 1] : 0;
+            ci.code = j > 0 ? ctx->perm[t.b[c - 1] & 31] : 0;
             ci.pad[0] = ci.pad[1] = ci.pad[2] = 0;
             col[j] = ci;
         }

@@ -33,7 +33,8 @@ constexpr int CHECK_SCR = 29490;        // int(0.9 * SHRT_MAX), src/fwd2s1_simd.
 constexpr int LAG = 2;                  // extra systolic lag (iterations) hiding the band-load latency
 constexpr int TRACE_PAD = 36;           // trace steps per strip <= width + 31; slab stride width + TRACE_PAD
 constexpr int MAXQ = 8;
-constexpr int MTX_LD = 32;              // leading dimension of the substitution table
+constexpr int MTX_LD = 36;              // row stride (words) of the substitution table: with the four
+                                        // common residues remapped to 0..3 their 16 pairs hit 16 distinct banks
 constexpr int ZROW = 31;                // all-zero row / column: cells outside the matrix score 0
 constexpr int WARPS_PER_CTA = 4;
 constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
@@ -50,12 +51,13 @@ struct DevParams {
     int quant[MAXQ], mean[MAXQ];
     int avmch, local, spj, simdim, gappen1, gop, gep;
     int pen_cap;                // pen table has pen_cap + 1 entries
-    short mtxT[MTX_LD * MTX_LD];    // [genome code][query code]; row/col ZROW == 0
+    int mtxT[32 * MTX_LD];      // [genome index][query index] (remapped codes); row/col ZROW == 0
+    unsigned char perm[32];     // residue code -> table index
 };
 
 struct ColInfo {                // one genome column (8 B)
     short sig5, sig3;           // Exinon::data_n[n]
-    unsigned char code;         // *b->at(n - 1)
+    unsigned char code;         // table index of *b->at(n - 1) (DevParams::perm applied on the host)
     unsigned char pad[3];
 };
 
@@ -121,7 +123,7 @@ struct WarpMax { int val, mr, nr; };
 struct SmemLayout {
     RingEntry* ring;            // [RING][CTA_THREADS]
     const int2* pen;            // [pen_cap + 1] {penalty, lower clamp}
-    const short* mtx;           // [MTX_LD * MTX_LD]
+    const int* mtx;             // [32 * MTX_LD]
 };
 
 // ---------------------------------------------------------------------------
@@ -161,7 +163,7 @@ __device__ __forceinline__ void strip_step(
         if (!(f > x)) { f = x; hb |= TB_NVER; }
         F[k] = f;
         // diagonal
-        const int pv = *reinterpret_cast<const short*>(mtx_bytes + re.prof + arow[k]);
+        const int pv = *reinterpret_cast<const int*>(mtx_bytes + re.prof + arow[k]);
         int h = sat16(pv + dg);
         unsigned pb = TB_DIAG;
         if (f > h) { h = f; pb = TB_VERT; }
@@ -228,7 +230,7 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
     for (int k = 0; k < NELEM; ++k) {
         HA[k] = NEV; HB[k] = NEV; F[k] = NEV; E[k] = NEV; V2[k] = NEV; IL[k] = 0;
         // rows beyond the last query residue score 0 (reference: pv_a stays 0)
-        arow[k] = (live && k < g.j9) ? 2 * (int) aseq[(g.ml - t.a_left) + k] : 2 * ZROW;
+        arow[k] = (live && k < g.j9) ? 4 * (int) aseq[(g.ml - t.a_left) + k] : 4 * ZROW;
     }
     const int gn = P.gn, ge = P.ge;
     const int floorL = localL_now ? 0 : INT_MIN;
@@ -246,13 +248,13 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
     auto col_entry = [&](int c, bool with_sig) -> RingEntry {
         RingEntry re;
         re.pad = 0;
-        re.prof = ZROW * (MTX_LD * 2);
+        re.prof = ZROW * (MTX_LD * 4);
         re.s3 = 0; re.s5 = 0;
         if (c >= t.b_left && c <= t.b_right) {
             // one 8-byte load: {sig5 | sig3 << 16, code}
             const uint2 ci = __ldg(reinterpret_cast<const uint2*>(cols + (c - t.b_left)));
             // column b_left carries signals but pairs no residue (ke == 0)
-            if (c > t.b_left) re.prof = (int) (ci.y & 0xffu) * (MTX_LD * 2);
+            if (c > t.b_left) re.prof = (int) (ci.y & 0xffu) * (MTX_LD * 4);
             if (SPJ && with_sig) {
                 re.s3 = hi16(ci.x);
                 re.s5 = (int) (short) (lo16(ci.x) + ipen);
@@ -299,7 +301,7 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
             prev_uh = up_h;
             unsigned tw[4];
             int sv = INT_MIN, sk = 0;
-            if (j & 1)
+            if (i & 1)      // warp-uniform ping-pong (every thread steps once per iteration)
                 strip_step<TRACE, LOCAL, SPJ>(HB, HA, F, E, V2, IL, arow, ring_hi, mtx_bytes, sm.pen,
                                               P.pen_cap, up_h, up_f, up_d, gn, ge, floorL, tw, sv, sk);
             else
@@ -312,7 +314,7 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
                 else {
 #pragma unroll
                     for (int k = NELEM - 1; k >= 0; --k) {
-                        const int hv = (j & 1) ? HB[k] : HA[k];
+                        const int hv = (i & 1) ? HB[k] : HA[k];
                         if (k < g.j9 && hv >= v) { v = hv; kk = k; }
                     }
                 }
@@ -321,13 +323,13 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
             // bottom row of the strip -> band buffer (src/fwd2s1_wip_simd.h:438-442)
             int out_h, out_f;
             if (g.j9 == NELEM) {
-                out_h = (j & 1) ? HB[NELEM - 1] : HA[NELEM - 1];
+                out_h = (i & 1) ? HB[NELEM - 1] : HA[NELEM - 1];
                 out_f = F[NELEM - 1];
             } else {
                 out_h = NEV; out_f = NEV;
 #pragma unroll
                 for (int k = 0; k < NELEM - 1; ++k)
-                    if (k == j8) { out_h = (j & 1) ? HB[k] : HA[k]; out_f = F[k]; }
+                    if (k == j8) { out_h = (i & 1) ? HB[k] : HA[k]; out_f = F[k]; }
             }
             if (TRACE)
                 *reinterpret_cast<uint4*>(tr_base + (long long) j * NELEM) = make_uint4(tw[0], tw[1], tw[2], tw[3]);
