@@ -1,0 +1,124 @@
+// gspaln_spaln_adapter.hpp -- header-only adapter that lets the reference (ogotoh/spaln)
+// call libgspaln at its SimdAln2s1 seam.  It is compiled INSIDE a Spaln translation unit:
+// it expects the reference's own headers (aln.h -> seq.h, codepot.h, mfile.h) to be included
+// first and uses their types (Seq, PwdB, WINDOW, SKL, Mfile, IntronPrm, algmode).
+//
+// Replaces (all paths relative to the reference tree):
+//   SimdAln2s1 ctor + forwardS1_wip(Mfile*)   src/fwd2s1_simd.h:191-333, src/fwd2s1_wip_simd.h:233-474
+//   SimdAln2s1 ctor + scoreonlyS1_wip()       src/fwd2s1_wip_simd.h:42-231
+// See INTEGRATION.md for the three-line patch of src/fwd2s1.cc.
+#ifndef GSPALN_SPALN_ADAPTER_HPP
+#define GSPALN_SPALN_ADAPTER_HPP
+
+#include "gspaln.h"
+
+#include <cstdlib>
+#include <vector>
+
+namespace gspaln {
+
+class SpalnEngine {
+    gspaln_ctx* ctx_ = nullptr;
+    std::vector<short> sig5_, sig3_;
+    std::vector<int> skl_;
+
+    static void die(const char* what, int rc, const gspaln_ctx* c)
+    {
+        // the reference's own error convention: fatal() == message + exit(1) (src/adddef.h:173-182)
+        fatal("gspaln: %s failed (%d): %s\n", what, rc, c ? gspaln_last_error(c) : "");
+    }
+
+    void fill(gspaln_task& t, const Seq** seqs, const WINDOW& wdw, int kind)
+    {
+        const Seq* a = seqs[0];
+        const Seq* b = seqs[1];
+        t.kind = kind;
+        t.a = a->at(0);
+        t.b = b->at(0);
+        t.a_left = a->left; t.a_right = a->right;
+        t.b_left = b->left; t.b_right = b->right;
+        t.a_exgl = a->inex.exgl; t.a_exgr = a->inex.exgr;
+        t.b_exgl = b->inex.exgl; t.b_exgr = b->inex.exgr;
+        t.lw = wdw.lw; t.up = wdw.up;
+        // Exinon::data_n is an array of {short sig5, sig3; char phs5, phs3}; the kernels take
+        // the two signal columns (src/codepot.h:27-32,104)
+        const int n = b->right + 2;
+        sig5_.assign(n, 0); sig3_.assign(n, 0);
+        if (b->inex.intr && b->exin)
+            for (int i = b->left; i <= b->right; ++i) {
+                const SGPT2* g = b->exin->score_n(i);
+                sig5_[i] = g->sig5; sig3_[i] = g->sig3;
+            }
+        t.sig5 = sig5_.data(); t.sig3 = sig3_.data();
+        t.skl_cap = 0;
+    }
+
+public:
+    // freezes the globals the reference kernels read into gspaln_params
+    explicit SpalnEngine(const PwdB* pwd, int device = 0, bool spliced = true)
+    {
+        gspaln_params p = gspaln_params();
+        p.gop = pwd->BasicGOP; p.gep = pwd->BasicGEP;
+        p.lgop = pwd->LongGOP; p.lgep = pwd->LongGEP;
+        p.noll = pwd->Noll;
+        p.ipen = (spliced && pwd->IntPen) ? pwd->IntPen->Penalty() : 0;
+        p.llmt = IntronPrm.llmt;
+        p.nquant = IntronPrm.nquant;
+        for (int j = 0; j < p.nquant && j < GSPALN_MAXQUANT && pwd->IntPen && pwd->IntPen->qm; ++j) {
+            p.quant_len[j] = pwd->IntPen->qm[j].len;
+            p.quant_pen[j] = pwd->IntPen->qm[j].pen;
+        }
+        p.avmch = (int) pwd->simmtx->AvTrc();
+        p.local = (algmode.lcl & 16) ? 1 : 0;
+        p.spj = spliced ? 1 : 0;
+        p.simdim = pwd->simmtx->dim;
+        p.gappen1 = pwd->GapPenalty(1);
+        for (int q = 0; q < p.simdim; ++q)
+            for (int g = 0; g < p.simdim; ++g)
+                p.simmtx[q * p.simdim + g] = pwd->simmtx->mtx[q][g];
+        int rc = gspaln_create(&ctx_, &p, device);
+        if (rc != GSPALN_OK) die("gspaln_create", rc, ctx_);
+    }
+    ~SpalnEngine() { gspaln_destroy(ctx_); }
+    SpalnEngine(const SpalnEngine&) = delete;
+    SpalnEngine& operator=(const SpalnEngine&) = delete;
+
+    // == SimdAln2s1(seqs, pwd, wdw, spjcs, cip, 1).forwardS1_wip(mfd)
+    VTYPE forwardS1_wip(const Seq** seqs, const WINDOW& wdw, Mfile* mfd)
+    {
+        gspaln_task t;
+        gspaln_result r;
+        fill(t, seqs, wdw, GSPALN_FORWARD_WIP);
+        int cap = (t.a_right - t.a_left) + (t.b_right - t.b_left) + 8;
+        for (;;) {
+            skl_.assign(2 * (size_t) cap, 0);
+            t.skl_cap = cap;
+            r.skl = skl_.data();
+            int rc = gspaln_submit(ctx_, &t, 1, &r);
+            if (rc != GSPALN_OK) die("gspaln_submit", rc, ctx_);
+            if (r.status != GSPALN_ST_SKL_OVERFLOW) break;
+            cap = r.n_skl + 8;
+        }
+        if (r.status == GSPALN_ST_BAD_TRACE) fatal("Unexpected dir\n");     // src/rhomb_coord.h:216
+        for (int i = 0; i < r.n_skl; ++i) {
+            SKL wsk = {skl_[2 * i], skl_[2 * i + 1]};
+            mfd->write((UPTR) &wsk);
+        }
+        return (VTYPE) r.score;
+    }
+
+    // == SimdAln2s1(seqs, pwd, wdw, spjcs, cip, 1).scoreonlyS1_wip()
+    VTYPE scoreonlyS1_wip(const Seq** seqs, const WINDOW& wdw)
+    {
+        gspaln_task t;
+        gspaln_result r;
+        fill(t, seqs, wdw, GSPALN_SCOREONLY_WIP);
+        r.skl = 0;
+        int rc = gspaln_submit(ctx_, &t, 1, &r);
+        if (rc != GSPALN_OK) die("gspaln_submit", rc, ctx_);
+        return (VTYPE) r.score;
+    }
+};
+
+}   // namespace gspaln
+#endif

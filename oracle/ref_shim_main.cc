@@ -25,6 +25,8 @@ int shim_s1_kernel(const Seq** seqs, const PwdB* pwd, int lw, int up,
 int shim_s1_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up,
 	int* score, int* skl_out, int cap, double* seconds);
 int shim_s1_nelem();
+int shim_s1_adapter(const Seq** seqs, const PwdB* pwd, int lw, int up,
+	int kind, int device, int* score, int* skl_out, int cap);
 }
 
 namespace {
@@ -226,6 +228,15 @@ int ref_task_kernel(void* h, int lw, int up, int kind, int n_imd, int mode,
 	RefTask* t = (RefTask*) h;
 	return shim_s1_kernel((const Seq**) t->sqs, g_pwd, lw, up, kind, n_imd,
 	    mode, score, skl_out, cap, cpos_out, seconds);
+}
+
+// drop-in check: the same problem through include/gspaln_spaln_adapter.hpp (needs a GPU)
+int ref_task_adapter(void* h, int lw, int up, int kind, int device,
+	int* score, int* skl_out, int cap)
+{
+	RefTask* t = (RefTask*) h;
+	return shim_s1_adapter((const Seq**) t->sqs, g_pwd, lw, up, kind, device,
+	    score, skl_out, cap);
 }
 
 int ref_task_lsp(void* h, int lw, int up, int* score, int* skl_out, int cap,

@@ -13,6 +13,10 @@
 #include <chrono>
 #include <cwchar>
 #include "fwd2s1.cc"
+// the adapter a Spaln maintainer would add (include/gspaln_spaln_adapter.hpp),
+// compiled here against the reference headers so that tests can run it as a
+// true drop-in inside the reference process
+#include "gspaln_spaln_adapter.hpp"
 
 namespace {
 
@@ -99,5 +103,21 @@ int shim_s1_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up,
 }
 
 int shim_s1_nelem() { return Simd_functions<short>::Nelem; }
+
+// same call as shim_s1_kernel(kind 0 | 1) but through the gspaln adapter (GPU)
+int shim_s1_adapter(const Seq** seqs, const PwdB* pwd, int lw, int up,
+	int kind, int device, int* score, int* skl_out, int cap)
+{
+	static gspaln::SpalnEngine* eng = 0;
+	if (!eng) eng = new gspaln::SpalnEngine(pwd, device, seqs[1]->inex.intr);
+	WINDOW wdw = {lw, up, up - lw + 3};
+	if (kind == 1) {
+	    *score = eng->scoreonlyS1_wip(seqs, wdw);
+	    return 0;
+	}
+	Mfile mfd(sizeof(SKL));
+	*score = eng->forwardS1_wip(seqs, wdw, &mfd);
+	return copy_out(mfd, (SKL*) skl_out, cap);
+}
 
 }	// extern "C"

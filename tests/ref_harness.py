@@ -71,6 +71,8 @@ class Reference:
                                       C.c_void_p, C.c_void_p]
         L.ref_task_lsp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_task_adapter.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_int]
         L.ref_get_params.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         self.tmp = tempfile.TemporaryDirectory(prefix="spaln_ref_")
         g = os.path.join(self.tmp.name, "g0.fa")
@@ -174,6 +176,14 @@ class RefTask:
                                      cpos.ctypes.data, C.byref(secs))
         return {"score": score.value, "skl": skl[:n].copy(), "cpos": cpos,
                 "seconds": secs.value}
+
+    def adapter(self, lw, up, kind=0, device=0, cap=1 << 16):
+        """the same problem through include/gspaln_spaln_adapter.hpp (GPU drop-in)"""
+        score = C.c_int(0)
+        skl = np.zeros((cap, 2), np.int32)
+        n = self.lib.ref_task_adapter(self.h, lw, up, kind, device, C.byref(score),
+                                      skl.ctypes.data, cap)
+        return {"score": score.value, "skl": skl[:n].copy()}
 
     def lsp(self, lw, up, cap=1 << 16):
         score = C.c_int(0)
