@@ -7,12 +7,14 @@ or no CUDA device is usable, the calls raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libgspaln.so"
+# GSPALN_LIB: alternative build of the same library (kernel experiments)
+LIB_PATH = Path(os.environ.get("GSPALN_LIB", PKG / "libgspaln.so"))
 
 MAXQUANT = 8
 MAXDIM = 32

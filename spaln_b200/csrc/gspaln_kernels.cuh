@@ -4,15 +4,16 @@
 // the reference (src/fwd2s1_wip_simd.h:42-474, src/fwd2s1_simd.cc:163-262,
 // src/rhomb_coord.h:65-235) at the AVX2 lane count (strips of 16 query rows).
 //
-// Mapping (NOT the reference's): one warp owns one DP problem.  A thread owns
-// one 16-row strip and evaluates it along anti-diagonals: at step n its row k
-// sits on column n - k, so the 16 cell updates of a step are independent
-// (ILP 16, no serial chain) and all rows of a strip start and stop together,
+// Mapping (NOT the reference's): one warp owns one DP problem.  TPS = 2
+// neighbouring threads own one 16-row strip (NR = 8 rows each, lock step,
+// joined by two warp shuffles per step) and evaluate it along anti-diagonals:
+// at step n strip row k sits on column n - k, so the cell updates of a step
+// are independent (no serial chain) and all rows of a strip start and stop together,
 // exactly like the lanes of the reference's vector -- including the cells
 // that lie outside the matrix.  All per-row state (H of the last two steps,
-// F, E, best donor value, intron length) lives in registers.  The 32 strips
-// of a pass form a systolic chain: thread t runs 15 + LAG steps behind
-// thread t-1 and receives the (H, F) of the row above it through the
+// F, E, best donor value, intron length) lives in registers.  The 16 strips
+// of a pass form a systolic chain: strip s runs 15 + LAG steps behind
+// strip s-1 and receives the (H, F) of the row above it through the
 // problem's diagonal-indexed band buffer in global memory (one packed
 // int16x2 word per diagonal, L2 resident, fetched with ld.global.cg one
 // iteration ahead).  The band buffer has exactly the reference's hv[]/fv[]
@@ -28,6 +29,12 @@
 namespace gspaln {
 
 constexpr int NELEM = 16;               // rows per strip == reference nelem (AVX2)
+#ifndef GSPALN_NR
+#define GSPALN_NR 8
+#endif
+constexpr int NR = GSPALN_NR;           // strip rows owned by one thread
+constexpr int TPS = NELEM / NR;         // threads per strip (run in lock step)
+constexpr int SPP = 32 / TPS;           // strips per pass of one warp
 constexpr int NEV = -32768 + 1024;      // nevsel, src/fwd2s1_simd.h:47,202
 constexpr int CHECK_SCR = 29490;        // int(0.9 * SHRT_MAX), src/fwd2s1_simd.h:44
 constexpr int LAG = 2;                  // extra systolic lag (iterations) hiding the band-load latency
@@ -127,24 +134,30 @@ struct SmemLayout {
 };
 
 // ---------------------------------------------------------------------------
-// one step of one strip: 16 independent cell updates (rows 15 .. 0)
+// one step of one thread: NR independent cell updates (its rows NR-1 .. 0)
 //   HN: H of the previous step (read as "left" and, shifted by one row, as
 //       "up"); HO: H of two steps ago (read shifted as "diag"); the new H
 //       overwrites HO, so callers alternate the two arrays.
+//   NJ: minus the step index at which the row's intron-length counter was
+//       last reset (counter value == step + NJ; saturation is implied by the
+//       clamp to the table size).
 // ---------------------------------------------------------------------------
 template <bool TRACE, bool LOCAL, bool SPJ>
 __device__ __forceinline__ void strip_step(
-    int (&HO)[NELEM], const int (&HN)[NELEM], int (&F)[NELEM], int (&E)[NELEM],
-    int (&V2)[NELEM], int (&IL)[NELEM], const int (&arow)[NELEM],
+    int (&HO)[NR], const int (&HN)[NR], int (&F)[NR], int (&E)[NR],
+    int (&V2)[NR], int (&NJ)[NR], const int (&arow)[NR],
     const char* __restrict__ ring_hi, const char* __restrict__ mtx_bytes,
-    const int2* __restrict__ pen_tab, int pen_cap,
-    int up_h, int up_f, int up_d, int gn, int ge, int floorL, unsigned (&tw)[4],
+    const int2* __restrict__ pen_tab, int pen_cap, int step,
+    int up_h, int up_f, int up_d, int gn, int ge, int floorL, unsigned (&tw)[NR / 4],
     int& best_v, int& best_k)
 {
-    if (TRACE) { tw[0] = tw[1] = tw[2] = tw[3] = 0u; }
+    if (TRACE) {
 #pragma unroll
-    for (int k = NELEM - 1; k >= 0; --k) {
-        // column n - k of this row: ring slot (n & 15) + 16 - k
+        for (int w = 0; w < NR / 4; ++w) tw[w] = 0u;
+    }
+#pragma unroll
+    for (int k = NR - 1; k >= 0; --k) {
+        // column n - (row index in the strip): ring slot (n & 15) + 16 - row
         const RingEntry re = *reinterpret_cast<const RingEntry*>(
             ring_hi - k * (CTA_THREADS * (int) sizeof(RingEntry)));
         const int left = HN[k];
@@ -173,7 +186,7 @@ __device__ __forceinline__ void strip_step(
             // acceptor: best donor of this row + 3' signal + binned length penalty,
             // only if the intron is longer than the lower limit
             const int q0 = sat16(V2[k] + re.s3);
-            const int2 pq = pen_tab[min(IL[k], pen_cap)];
+            const int2 pq = pen_tab[min(step + NJ[k], pen_cap)];
             const int q = min(max(q0 + pq.x, pq.y), 32767);
             if (q > h) { h = q; pb = TB_ACCR; acc = true; }
         }
@@ -184,9 +197,8 @@ __device__ __forceinline__ void strip_step(
             if (TRACE && acc) q = NEV;          // no empty intron
             const bool don = q > V2[k];
             V2[k] = max(V2[k], q);
-            IL[k] = don ? 0 : IL[k];
+            NJ[k] = don ? -step : NJ[k];        // counter := 0, then += 1 at the end of this step
             if (TRACE && don) hb |= TB_DONR;
-            IL[k] = min(IL[k] + 1, 32767);
         }
         if (LOCAL) {
             if (h >= best_v) { best_v = h; best_k = k; }    // descending k: ties end at the lowest row
@@ -197,7 +209,9 @@ __device__ __forceinline__ void strip_step(
 }
 
 // ---------------------------------------------------------------------------
-// one pass: strips ml0, ml0+16, ... (nstr <= 32), thread t owns strip t
+// one pass: strips ml0, ml0+16, ... (nstr <= SPP).  A strip is shared by TPS
+// neighbouring threads (NR rows each) that run in lock step; the lower thread
+// takes the (H, F) of the row above it from its neighbour by warp shuffle.
 // ---------------------------------------------------------------------------
 template <bool TRACE, bool LOCAL, bool SPJ>
 __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
@@ -207,52 +221,64 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
                          bool localR, int accscr, WarpMax& wmax)
 {
     const int lane = threadIdx.x & 31;
-    const StripGeom g = strip_geom<TRACE>(t, ml0 + NELEM * lane);
+    const int sidx = lane / TPS;                // strip of this thread within the pass
+    const int sub = lane % TPS;                 // which NR-row slice of the strip
+    const int row0 = sub * NR;                  // first strip row owned by this thread
+    const StripGeom g = strip_geom<TRACE>(t, ml0 + NELEM * sidx);
     const int j8 = g.j9 - 1;
     const int nsteps = g.n_last - g.n_start + 1;
-    const bool live = lane < nstr && nsteps > 0;
+    const bool live = sidx < nstr && nsteps > 0;
     const int width = t.up - t.lw + 3;
 
-    // Systolic schedule.  Thread t needs, at its step n, the band entry of
-    // column n, which thread t-1 (a full strip) produces at ITS step n + 15.
-    // With step j of thread t executed in iteration j + off_t this requires
-    //   off_t = off_{t-1} + (n_start_t - n_start_{t-1}) + 15 + LAG,
+    // Systolic schedule.  Strip s needs, at its step n, the band entry of
+    // column n, which strip s-1 (a full strip) produces at ITS step n + 15.
+    // With step j of strip s executed in iteration j + off_s this requires
+    //   off_s = off_{s-1} + (n_start_s - n_start_{s-1}) + 15 + LAG,
     // which telescopes to the closed form below.
     const int n_start0 = __shfl_sync(0xffffffffu, g.n_start, 0);
-    const int off = (g.n_start - n_start0) + (NELEM - 1 + LAG) * lane;
+    const int off = (g.n_start - n_start0) + (NELEM - 1 + LAG) * sidx;
     int niter = live ? off + nsteps : 0;
 #pragma unroll
     for (int o = 16; o; o >>= 1) niter = max(niter, __shfl_xor_sync(0xffffffffu, niter, o));
     if (niter == 0) return;
 
-    int HA[NELEM], HB[NELEM], F[NELEM], E[NELEM], V2[NELEM], IL[NELEM], arow[NELEM];
+    int HA[NR], HB[NR], F[NR], E[NR], V2[NR], NJ[NR], arow[NR];
 #pragma unroll
-    for (int k = 0; k < NELEM; ++k) {
-        HA[k] = NEV; HB[k] = NEV; F[k] = NEV; E[k] = NEV; V2[k] = NEV; IL[k] = 0;
+    for (int k = 0; k < NR; ++k) {
+        HA[k] = NEV; HB[k] = NEV; F[k] = NEV; E[k] = NEV; V2[k] = NEV; NJ[k] = 0;
         // rows beyond the last query residue score 0 (reference: pv_a stays 0)
-        arow[k] = (live && k < g.j9) ? 4 * (int) aseq[(g.ml - t.a_left) + k] : 4 * ZROW;
+        arow[k] = (live && row0 + k < g.j9) ? 4 * (int) aseq[(g.ml - t.a_left) + row0 + k] : 4 * ZROW;
     }
     const int gn = P.gn, ge = P.ge;
     const int floorL = localL_now ? 0 : INT_MIN;
     int prev_uh = NEV;
-    int bval = INT_MIN, bstep = 0, bk = 0;      // best local-mode cell of this strip
+    int bval = INT_MIN, bstep = 0, bk = 0;      // best local-mode cell of this thread
 
     unsigned char* tr_base = TRACE
-        ? trace + ((long long) (lane + (ml0 - t.a_left) / NELEM) * (width + TRACE_PAD)) * NELEM
+        ? trace + ((long long) (sidx + (ml0 - t.a_left) / NELEM) * (width + TRACE_PAD)) * NELEM + row0
         : nullptr;
     const int band_bias = g.ml + t.lw - 1;      // band entry of column c (diagonal c - ml): c - band_bias
     RingEntry* ring = sm.ring + threadIdx.x;    // slot s at ring[s * CTA_THREADS]
     const char* mtx_bytes = reinterpret_cast<const char*>(sm.mtx);
     const int ipen = P.ipen;
+    // the thread that holds the strip's last row writes the band buffer
+    const bool owns_bottom = live && j8 >= row0 && j8 < row0 + NR;
+    const int kbot = j8 - row0;
 
-    auto col_entry = [&](int c, bool with_sig) -> RingEntry {
+    // Column inputs are prefetched RAW one iteration ahead (no dependent ALU
+    // work behind the load) and decoded when the column is entered.
+    auto col_fetch = [&](int c) -> uint2 {
+        // one 8-byte load: {sig5 | sig3 << 16, code}
+        if (c >= t.b_left && c <= t.b_right)
+            return __ldg(reinterpret_cast<const uint2*>(cols + (c - t.b_left)));
+        return make_uint2(0u, 0xffffffffu);
+    };
+    auto col_decode = [&](uint2 ci, int c, bool with_sig) -> RingEntry {
         RingEntry re;
         re.pad = 0;
         re.prof = ZROW * (MTX_LD * 4);
         re.s3 = 0; re.s5 = 0;
-        if (c >= t.b_left && c <= t.b_right) {
-            // one 8-byte load: {sig5 | sig3 << 16, code}
-            const uint2 ci = __ldg(reinterpret_cast<const uint2*>(cols + (c - t.b_left)));
+        if (ci.y != 0xffffffffu) {
             // column b_left carries signals but pairs no residue (ke == 0)
             if (c > t.b_left) re.prof = (int) (ci.y & 0xffu) * (MTX_LD * 4);
             if (SPJ && with_sig) {
@@ -264,99 +290,123 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
     };
 
     unsigned nxt_band = 0;
-    RingEntry nxt_col = col_entry(INT_MIN / 2, false);
+    uint2 nxt_col = make_uint2(0u, 0xffffffffu);
 
     for (int i = -1; i < niter; ++i) {
         const int j = i - off;
+        // neighbour exchange inside a strip: bottom row of the thread above, as
+        // of the previous step (every thread of the warp takes part)
+        int sh_h = NEV, sh_f = NEV;
+        if (TPS > 1) {
+            sh_h = __shfl_up_sync(0xffffffffu, (i & 1) ? HA[NR - 1] : HB[NR - 1], 1);
+            sh_f = __shfl_up_sync(0xffffffffu, F[NR - 1], 1);
+        }
         if (live && j == -1) {
             // One iteration before the first step: the entries of columns
             // n_start - 1 and n_start are final by now (written >= LAG - 1
             // iterations ago by the strip above).
-            nxt_band = __ldcg(band + (g.n_start - band_bias));
-            prev_uh = lo16(__ldcg(band + (g.n_start - 1 - band_bias)));
-            nxt_col = col_entry(g.n_start, g.n_start <= t.b_right);
+            if (sub == 0) {
+                nxt_band = __ldcg(band + (g.n_start - band_bias));
+                prev_uh = lo16(__ldcg(band + (g.n_start - 1 - band_bias)));
+            }
+            nxt_col = col_fetch(g.n_start);
             // ring pre-fill: the 15 columns left of n_start pair residues (if
             // inside the sequence) but carry no splice signal (s3_a / s5_a
             // start as zeros, src/fwd2s1_wip_simd.h:291)
 #pragma unroll 1
             for (int d = 1; d < NELEM; ++d) {
                 const int c = g.n_start - d;
-                const RingEntry re = col_entry(c, false);
+                const RingEntry re = col_decode(col_fetch(c), c, false);
                 ring[(c & 15) * CTA_THREADS] = re;
                 ring[((c & 15) + 16) * CTA_THREADS] = re;
             }
         } else if (live && j >= 0 && j < nsteps) {
             const int n = g.n_start + j;
             const unsigned cur_band = nxt_band;
-            const RingEntry cur_col = nxt_col;
+            const RingEntry cur_col = col_decode(nxt_col, n, n <= t.b_right);
             if (j + 1 < nsteps) {
-                nxt_band = __ldcg(band + (n + 1 - band_bias));
-                nxt_col = col_entry(n + 1, n + 1 <= t.b_right);
+                if (sub == 0) nxt_band = __ldcg(band + (n + 1 - band_bias));
+                nxt_col = col_fetch(n + 1);
             }
             const int slot = n & 15;
             ring[slot * CTA_THREADS] = cur_col;
             ring[(slot + 16) * CTA_THREADS] = cur_col;
-            const char* ring_hi = reinterpret_cast<const char*>(ring + (slot + 16) * CTA_THREADS);
-            const int up_h = lo16(cur_band), up_f = hi16(cur_band), up_d = prev_uh;
+            const char* ring_hi = reinterpret_cast<const char*>(ring + (slot + 16 - row0) * CTA_THREADS);
+            int up_h, up_f, up_d;
+            if (sub == 0) {
+                up_h = lo16(cur_band); up_f = hi16(cur_band);
+            } else {
+                up_h = sh_h; up_f = sh_f;
+            }
+            up_d = prev_uh;
             prev_uh = up_h;
-            unsigned tw[4];
+            unsigned tw[NR / 4];
             int sv = INT_MIN, sk = 0;
             if (i & 1)      // warp-uniform ping-pong (every thread steps once per iteration)
-                strip_step<TRACE, LOCAL, SPJ>(HB, HA, F, E, V2, IL, arow, ring_hi, mtx_bytes, sm.pen,
-                                              P.pen_cap, up_h, up_f, up_d, gn, ge, floorL, tw, sv, sk);
+                strip_step<TRACE, LOCAL, SPJ>(HB, HA, F, E, V2, NJ, arow, ring_hi, mtx_bytes, sm.pen,
+                                              P.pen_cap, j, up_h, up_f, up_d, gn, ge, floorL, tw, sv, sk);
             else
-                strip_step<TRACE, LOCAL, SPJ>(HA, HB, F, E, V2, IL, arow, ring_hi, mtx_bytes, sm.pen,
-                                              P.pen_cap, up_h, up_f, up_d, gn, ge, floorL, tw, sv, sk);
+                strip_step<TRACE, LOCAL, SPJ>(HA, HB, F, E, V2, NJ, arow, ring_hi, mtx_bytes, sm.pen,
+                                              P.pen_cap, j, up_h, up_f, up_d, gn, ge, floorL, tw, sv, sk);
             if (LOCAL && localR) {
-                // vmax over the j9 real rows of this step; strictly greater wins (earlier steps keep ties)
+                // vmax over the real rows of this step; strictly greater wins (earlier steps keep ties)
                 int v = INT_MIN, kk = 0;
-                if (g.j9 == NELEM) { v = sv; kk = sk; }
+                if (row0 + NR <= g.j9) { v = sv; kk = sk; }
                 else {
 #pragma unroll
-                    for (int k = NELEM - 1; k >= 0; --k) {
+                    for (int k = NR - 1; k >= 0; --k) {
                         const int hv = (i & 1) ? HB[k] : HA[k];
-                        if (k < g.j9 && hv >= v) { v = hv; kk = k; }
+                        if (row0 + k < g.j9 && hv >= v) { v = hv; kk = k; }
                     }
                 }
-                if (v > bval) { bval = v; bstep = n; bk = kk; }
+                if (v > bval) { bval = v; bstep = n; bk = row0 + kk; }
+            }
+            if (TRACE) {
+                if (NR == 16)
+                    *reinterpret_cast<uint4*>(tr_base + (long long) j * NELEM) = make_uint4(tw[0], tw[1], tw[NR / 4 - 2], tw[NR / 4 - 1]);
+                else if (NR == 8)
+                    *reinterpret_cast<uint2*>(tr_base + (long long) j * NELEM) = make_uint2(tw[0], tw[NR / 4 - 1]);
+                else
+                    *reinterpret_cast<unsigned*>(tr_base + (long long) j * NELEM) = tw[0];
             }
             // bottom row of the strip -> band buffer (src/fwd2s1_wip_simd.h:438-442)
-            int out_h, out_f;
-            if (g.j9 == NELEM) {
-                out_h = (i & 1) ? HB[NELEM - 1] : HA[NELEM - 1];
-                out_f = F[NELEM - 1];
-            } else {
-                out_h = NEV; out_f = NEV;
+            if (owns_bottom) {
+                int out_h = (i & 1) ? HB[NR - 1] : HA[NR - 1];
+                int out_f = F[NR - 1];
+                if (kbot != NR - 1) {
 #pragma unroll
-                for (int k = 0; k < NELEM - 1; ++k)
-                    if (k == j8) { out_h = (i & 1) ? HB[k] : HA[k]; out_f = F[k]; }
+                    for (int k = 0; k < NR - 1; ++k)
+                        if (k == kbot) { out_h = (i & 1) ? HB[k] : HA[k]; out_f = F[k]; }
+                }
+                const int cb = n - j8;                  // column of the bottom row
+                const int r0 = cb - (g.ml + g.j9);
+                if (cb > t.b_left && r0 >= t.lw && r0 <= t.up)
+                    __stcg(band + (r0 - t.lw + 1), pack16(out_h, out_f));
             }
-            if (TRACE)
-                *reinterpret_cast<uint4*>(tr_base + (long long) j * NELEM) = make_uint4(tw[0], tw[1], tw[2], tw[3]);
-            const int cb = n - j8;                  // column of the bottom row
-            const int r0 = cb - (g.ml + g.j9);
-            if (cb > t.b_left && r0 >= t.lw && r0 <= t.up)
-                __stcg(band + (r0 - t.lw + 1), pack16(out_h, out_f));
+        } else if (TPS > 1) {
+            prev_uh = NEV;      // (inactive) keep the exchange registers defined
         }
         __syncwarp();
     }
 
     if (LOCAL && localR) {
         // reference order: strips ascending, then step, then lane (first max)
-        int best = (live && bval > INT_MIN) ? bval : INT_MIN, who = lane;
+        int bv = (live && bval > INT_MIN) ? bval : INT_MIN;
+        int bs = bstep, bkk = bk, bst = sidx;
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
-            const int ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int ow = __shfl_xor_sync(0xffffffffu, who, o);
-            if (ov > best || (ov == best && ow < who)) { best = ov; who = ow; }
+            const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bkk, o);
+            const int ot = __shfl_xor_sync(0xffffffffu, bst, o);
+            const bool take = ov > bv || (ov == bv && (ot < bst || (ot == bst && (os < bs || (os == bs && ok < bkk)))));
+            if (take) { bv = ov; bs = os; bkk = ok; bst = ot; }
         }
         // reference: k1 = lane + 1; mr = ml + k1; nr = n - k1 + 1
-        const int mr = __shfl_sync(0xffffffffu, g.ml + bk + 1, who);
-        const int nr = __shfl_sync(0xffffffffu, bstep - bk, who);
-        if (best > INT_MIN && best + accscr > wmax.val) {
-            wmax.val = best + accscr;
-            wmax.mr = mr;
-            wmax.nr = nr;
+        if (bv > INT_MIN && bv + accscr > wmax.val) {
+            wmax.val = bv + accscr;
+            wmax.mr = ml0 + NELEM * bst + bkk + 1;
+            wmax.nr = bs - bkk;
         }
     }
 }
@@ -430,7 +480,7 @@ __device__ int walk_trace(const DevTask& t, const unsigned char* trace, int m_ab
 // persistent kernel: each warp pulls problems from a global ticket counter
 // ---------------------------------------------------------------------------
 template <bool TRACE, bool LOCAL, bool SPJ>
-__global__ void __launch_bounds__(CTA_THREADS)
+__global__ void __launch_bounds__(CTA_THREADS, 3)
 dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
               const DevTask* __restrict__ tasks,
               const int* __restrict__ order, int ntasks, int* ticket,
@@ -515,7 +565,7 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
         WarpMax wmax{NEV, t.a_right, t.b_right};
         int ml0 = t.a_left;
         while (ml0 < t.a_right) {
-            int nstr = min(32, (t.a_right - ml0 + NELEM - 1) / NELEM);
+            int nstr = min(SPP, (t.a_right - ml0 + NELEM - 1) / NELEM);
             if (mc >= ml0 && mc < ml0 + nstr * NELEM && ((mc - ml0) % NELEM) == 0)
                 nstr = (mc - ml0) / NELEM + 1;
             run_pass<TRACE, LOCAL, SPJ>(P, sm, t, aseq, cols, band, trace, ml0, nstr,
