@@ -527,3 +527,546 @@ int so_forward_wip(const so_params* p, const so_task* t, int32_t* score,
     free(c.vbuf);
     return cnt;
 }
+
+/* =========================================================================
+ * Unidirectional Hirschberg forward pass with quantised intron penalty:
+ * SimdAln2s1::hirschbergS1_wip (src/fwd2s1_wip_simd.h:476-864), single affine.
+ * Besides H/F/E every lane carries a link (`hc`: the diagonal where the path
+ * crossed the previous intermediate row, or its start diagonal) and, in local
+ * mode, the left-end row (`hb`).  At the n_im intermediate rows the links are
+ * recorded (UdhIntermediate, src/udh_intermediate.h:29-67) and reset; the
+ * back-walk at the end turns them into the crossing records cpos[][10].
+ * ========================================================================= */
+#define END_OF_ULK (INT_MAX - 2)            /* src/aln.h:49 */
+#define NEVSEL32 (INT_MIN / 16 * 7)         /* src/cmn.h:79 */
+
+typedef struct {
+    int mi;
+    int* buf;
+    int* hlnk[2];
+    int* vlnk[2];
+} so_imd;
+
+static int imd_init(so_imd* im, int mi, int lw, int width)
+{
+    const int nol = 2;
+    size_t u_size = (size_t) nol * width;
+    im->mi = mi;
+    im->buf = (int*) malloc(2 * u_size * sizeof(int));
+    if (!im->buf) return -1;
+    for (size_t i = 0; i < 2 * u_size; ++i) im->buf[i] = END_OF_ULK;
+    im->hlnk[0] = im->buf - lw + 1;
+    im->vlnk[0] = im->hlnk[0] + u_size;
+    im->hlnk[1] = im->hlnk[0] + width;
+    im->vlnk[1] = im->vlnk[0] + width;
+    return 0;
+}
+
+int so_hirschberg_wip(const so_params* p, const so_task* t, int n_im,
+                      int32_t* score, int32_t* cpos /* (n_im+1) x 10 */,
+                      int32_t* ranges /* a_left, a_right, b_left, b_right after the call */)
+{
+    if (p->noll != 2 || n_im < 1) return -3;
+    so_ctx c;
+    if (ctx_init(&c, p, t)) return -1;
+    const int lw = t->lw, up = t->up, width = c.width;
+    int a_left = t->a_left, a_right = t->a_right, b_left = t->b_left, b_right = t->b_right;
+    const int LocalL = p->local && t->a_exgl && t->b_exgl;
+    const int LocalR = p->local && t->a_exgr && t->b_exgr;
+    /* band rows of the links: bbuf (hb, fb) and cbuf (hc, fc) */
+    size_t nb = (size_t) 2 * c.buf_size;
+    var_t* bbuf = (var_t*) malloc(nb * sizeof(var_t));
+    int* cbuf = (int*) malloc(nb * sizeof(int));
+    so_imd* imds = (so_imd*) calloc(n_im, sizeof(so_imd));
+    if (!bbuf || !cbuf || !imds) return -1;
+    var_t* hb = bbuf - lw + 1; var_t* fb = hb + c.buf_size;
+    int* hc = cbuf - lw + 1; int* fc = hc + c.buf_size;
+    memset(cbuf, 0, nb * sizeof(int));
+    for (int i = 0; i <= n_im; ++i) cpos[10 * i + 0] = cpos[10 * i + 2] = END_OF_ULK;
+
+    /* ---- fhinitS1, mode > 1 without Vmf (src/fwd2s1_simd.cc:163-238) */
+    fhinit(&c);
+    {
+        const int ru = up + 2 * NELEM;
+        const int rl = b_left - a_left;
+        for (size_t i = 0; i < nb; ++i) bbuf[i] = (var_t) a_left;
+        hc[rl] = rl;
+        if (t->a_exgl) { for (int r = rl; r < ru; ++r) hc[r] = r; }
+        else { for (int r = rl + 1; r <= ru; ++r) hc[r] = rl; }
+        if (t->b_exgl) {
+            int r = lw - 1;
+            var_t m = (var_t) a_left;
+            var_t* e = hb + rl;
+            while (r < rl) { hc[r] = r; ++r; *e-- = m++; }
+        } else {
+            for (int r = lw - 1; r < rl; ++r) hc[r] = rl;
+        }
+        for (int i = 0; i < c.buf_size; ++i) fc[lw - 1 + i] = hc[lw - 1 + i];
+    }
+
+    /* ---- intermediates (src/fwd2s1_wip_simd.h:505-510; Udh_Imds ctor) */
+    int mm = (a_right - a_left + n_im) / (n_im + 1);
+    {
+        int mi = a_left;
+        for (int i = 0; i < n_im; ++i)
+            if (imd_init(&imds[i], mi += mm, lw, width)) return -1;
+    }
+    so_imd* imd = &imds[0];
+    mm = a_left + (imd->mi - a_left - 1) / NELEM * NELEM;
+    int k9 = imd->mi - mm, k8 = k9 - 1;
+    int rlst = INT_MAX;
+
+    const int md = checkpoint(p, 0);
+    int mc = a_left + md;
+    int accscr = 0;
+    struct { int val, ulk, ml, mr, nr; } maxh = { NEVSEL16, END_OF_ULK, a_left, a_right, b_right };
+
+    /* lane state; the link lanes are NOT reset between strips in the reference */
+    var_t HA[2][NP1], FA[NP1], S5[NP1], S3[NP1], PV[NELEM], PS[NELEM], PB[NELEM];
+    var_t HBA[2][NP1], FBA[NP1];
+    int HCA[2][NP1], FCA[NP1];
+    memset(HCA, 0, sizeof(HCA)); memset(FCA, 0, sizeof(FCA));
+
+    for (int ml = a_left, ii = 0; ml < a_right; ml += NELEM) {
+        const int j9 = NELEM < a_right - ml ? NELEM : a_right - ml;
+        const int j8 = j9 - 1;
+        int n = b_left > lw + ml ? b_left : lw + ml;
+        const int lim = b_right < up + (ml + j9) + 1 ? b_right : up + (ml + j9) + 1;
+        const int n9 = lim + j9;
+        int r = n - (ml + 1);
+        int donor_r = r;
+        for (int k = 0; k < NP1; ++k) {
+            HA[0][k] = HA[1][k] = FA[k] = NEVSEL16;
+            HBA[0][k] = HBA[1][k] = FBA[k] = 0;
+            S5[k] = S3[k] = 0;
+        }
+        var_t ev[NELEM], eb[NELEM], hv2[NELEM], hb2[NELEM], hil[NELEM];
+        int ec[NELEM], hc2[NELEM];
+        for (int k = 0; k < NELEM; ++k) {
+            PV[k] = 0; PS[k] = 0;
+            ev[k] = NEVSEL16; eb[k] = 0; ec[k] = 0;
+            hv2[k] = NEVSEL16; hb2[k] = 0; hc2[k] = 0; hil[k] = 0;
+        }
+        const int is_imd_ = ml == mm;
+
+        for (int ph = 0; n < n9; ++n, ++r, ph = 1 - ph) {
+            const int q = 1 - ph, pp = ph;
+            const int r0 = r - 2 * j8;
+            const int rj = r - 2 * k8;
+            const int kb = n - b_right > 0 ? n - b_right : 0;
+            const int ke = j9 < n - b_left ? j9 : n - b_left;
+            const int is_imd = is_imd_ && rj >= lw && rj <= up;
+            var_t Hleft[NELEM], Hup[NELEM], Fup[NELEM], Hdg[NELEM], s3[NELEM], s5[NELEM];
+            var_t HBleft[NELEM], HBup[NELEM], FBup[NELEM], HBdg[NELEM];
+            int HCleft[NELEM], HCup[NELEM], FCup[NELEM], HCdg[NELEM];
+
+            for (int k = 0; k < NELEM; ++k) {
+                Hleft[k] = HA[q][k + 1]; HBleft[k] = HBA[q][k + 1]; HCleft[k] = HCA[q][k + 1];
+            }
+            HA[q][0] = c.hv[r + 1]; if (LocalL) HBA[q][0] = hb[r + 1]; HCA[q][0] = hc[r + 1];
+            FA[0] = c.fv[r + 1]; if (LocalL) FBA[0] = fb[r + 1]; FCA[0] = fc[r + 1];
+            for (int k = 0; k < NELEM; ++k) {
+                Hup[k] = HA[q][k]; HBup[k] = HBA[q][k]; HCup[k] = HCA[q][k];
+                Fup[k] = FA[k]; FBup[k] = FBA[k]; FCup[k] = FCA[k];
+            }
+            if (kb) for (int k = 0; k < NELEM; ++k) PV[k] = 0;
+            for (int k = kb; k < ke; ++k)
+                PV[k] = (var_t) p->simmtx[t->a[ml + k] * p->simdim + t->b[n - 1 - k]];
+            var_t pvv[NELEM];
+            for (int k = 0; k < NELEM; ++k) pvv[k] = PV[k];
+            HA[pp][0] = c.hv[r]; if (LocalL) HBA[pp][0] = hb[r]; HCA[pp][0] = hc[r];
+            for (int k = 0; k < NELEM; ++k) { Hdg[k] = HA[pp][k]; HBdg[k] = HBA[pp][k]; HCdg[k] = HCA[pp][k]; }
+            if (p->spj) {
+                S3[0] = kb ? 0 : t->sig3[n];
+                S5[0] = kb ? 0 : (var_t) (t->sig5[n] + c.ipen);
+                for (int k = 0; k < NELEM; ++k) { s3[k] = S3[k]; s5[k] = S5[k]; }
+                for (int k = 0; k < NELEM; ++k) { S3[k + 1] = s3[k]; S5[k + 1] = s5[k]; }
+            }
+
+            var_t hreg[NELEM], hbreg[NELEM];
+            int hcreg[NELEM];
+            var_t pbv[NELEM], accv[NELEM];
+            for (int k = 0; k < NELEM; ++k) {
+                var_t x, e, f, h, hbv;
+                int hcv;
+                /* horizontal */
+                x = adds16(Hleft[k], c.gn);
+                e = adds16(ev[k], c.ge);
+                if (!(e > x)) { e = x; if (LocalL) eb[k] = HBleft[k]; ec[k] = HCleft[k]; }
+                ev[k] = e;
+                /* vertical */
+                f = adds16(Fup[k], c.ge);
+                x = adds16(Hup[k], c.gn);
+                var_t fbv = FBup[k];
+                int fcv = FCup[k];
+                if (!(f > x)) { f = x; fbv = HBup[k]; fcv = HCup[k]; }
+                FA[k + 1] = f; if (LocalL) FBA[k + 1] = fbv; FCA[k + 1] = fcv;
+                /* diagonal, best of three */
+                h = adds16(pvv[k], Hdg[k]); hbv = HBdg[k]; hcv = HCdg[k];
+                var_t pb = 0;
+                if (f > h) { h = f; hbv = fbv; hcv = fcv; pb = 2; }
+                if (e > h) { h = e; hbv = eb[k]; hcv = ec[k]; pb = 1; }
+                pbv[k] = pb;
+                /* acceptor */
+                accv[k] = 0;
+                if (p->spj) {
+                    var_t qv = adds16(hv2[k], s3[k]);
+                    var_t pen = c.mean[0];
+                    for (int j = 1; j < p->nquant; ++j)
+                        if (hil[k] > c.quant[j - 1]) pen = c.mean[j];
+                    qv = adds16(qv, pen);
+                    if (!(hil[k] > c.mil)) qv = NEVSEL16;
+                    if (qv > h) { h = qv; hbv = hb2[k]; hcv = hc2[k]; accv[k] = 1; }
+                }
+                if (LocalL && !accscr && 0 > h) h = 0;
+                hreg[k] = h; hbreg[k] = hbv; hcreg[k] = hcv;
+            }
+            if (is_imd) for (int k = 0; k < NELEM; ++k) PV[k] = pbv[k];      /* Store(pv_a, pb_v) */
+            if (p->spj && is_imd) {
+                for (int k = 0; k < NELEM; ++k) PS[k] = accv[k];
+                if (PS[k8]) {
+                    imd->hlnk[0][rj] = donor_r;
+                    imd->hlnk[1][rj] = donor_r + width;
+                    rlst = rj;
+                }
+            }
+            for (int k = 0; k < NELEM; ++k) {
+                HA[pp][k + 1] = hreg[k];
+                if (LocalL) HBA[pp][k + 1] = hbreg[k];
+                HCA[pp][k + 1] = hcreg[k];
+            }
+            if (LocalL && !accscr) {
+                for (int k = kb; k < ke; ++k) {
+                    const int kp1 = k + 1;
+                    if (HA[pp][kp1] == 0) {
+                        HBA[pp][kp1] = (var_t) (ml + kp1);
+                        HCA[pp][kp1] = r - 2 * k;
+                    }
+                }
+            }
+            if (LocalR) {
+                int best = 1;
+                for (int k = 2; k <= j9; ++k) if (HA[pp][k] > HA[pp][best]) best = k;
+                if (HA[pp][best] + accscr > maxh.val) {
+                    maxh.val = HA[pp][best] + accscr;
+                    maxh.ml = HBA[pp][best];
+                    maxh.ulk = HCA[pp][best];
+                    maxh.mr = ml + best;
+                    maxh.nr = n - best + 1;
+                }
+            }
+            /* donor (registers hreg/hbreg/hcreg, not the patched lane arrays) */
+            if (p->spj) {
+                for (int k = 0; k < NELEM; ++k) {
+                    var_t qv = adds16(hreg[k], s5[k]);
+                    int don = qv > hv2[k];
+                    if (don) {
+                        hv2[k] = qv;
+                        if (LocalL) hb2[k] = hbreg[k];
+                        hc2[k] = hcreg[k];
+                        hil[k] = 0;
+                    }
+                    hil[k] = adds16(hil[k], 1);
+                    if (is_imd) PB[k] = (var_t) don;
+                }
+                if (is_imd && PB[k8]) donor_r = rj;
+            }
+            /* intermediate row */
+            if (is_imd) {
+                if (PV[k8] == 0) rlst = rj;
+                if (PV[k8] == 1) imd->hlnk[0][rj] = rlst;
+                imd->vlnk[0][rj] = HCA[pp][k9];
+                HCA[pp][k9] = rj;
+                imd->vlnk[1][rj] = FCA[k9];
+                FCA[k9] = rj + width;
+            }
+            if (j9 == ke && lw <= r0 && r0 <= up) {
+                c.hv[r0] = HA[pp][j9];
+                if (LocalL) hb[r0] = HBA[pp][j9];
+                hc[r0] = HCA[pp][j9];
+                c.fv[r0] = FA[j9];
+                if (LocalL) fb[r0] = FBA[j9];
+                fc[r0] = FCA[j9];
+            }
+        }
+        rebase(&c, ml, md, &mc, &accscr);
+        if (is_imd_ && ++ii < n_im) {
+            imd = &imds[ii];
+            mm = a_left + (imd->mi - a_left - 1) / NELEM * NELEM;
+            k9 = imd->mi - mm;
+            k8 = k9 - 1;
+        }
+    }
+
+    if (LocalR) {
+        a_right = maxh.mr;
+        b_right = maxh.nr;
+    } else {
+        /* fhlastS1 with mode > 1 (src/fwd2s1_simd.cc:241-262) */
+        so_maxh mh = { maxh.val, maxh.mr, maxh.nr };
+        const int rr = t->b_right - t->a_right;
+        int maxr = rr;
+        if (t->a_exgr) {
+            int r = lw > t->b_left - t->a_right ? lw : t->b_left - t->a_right;
+            maxr = argvmax(c.hv, r, rr - r);
+        }
+        if (t->b_exgr) {
+            int r = up - 1 < t->b_right - t->a_left ? up - 1 : t->b_right - t->a_left;
+            int max_vert = argvmax(c.hv, rr, r - rr);
+            if (c.hv[max_vert] > c.hv[maxr]) maxr = max_vert;
+        }
+        mh.val = c.hv[maxr];
+        if (maxr > rr) mh.mr = t->b_right - maxr;
+        else mh.nr = t->a_right + maxr;
+        maxh.val = mh.val + accscr; maxh.mr = mh.mr; maxh.nr = mh.nr;
+        maxh.ulk = hc[maxr];
+        maxh.ml = LocalL ? hb[maxr] : a_left;
+        a_right = maxh.mr;
+        b_right = maxh.nr;
+    }
+
+    /* ---- back-walk over the intermediates (src/fwd2s1_wip_simd.h:825-863) */
+    int i = n_im;
+    while (--i >= 0 && imds[i].mi > a_right) ;
+    if (i < 0 && imds[0].mi > a_right) cpos[2] = b_right;
+    int r = maxh.ulk;
+    for ( ; i >= 0 && (imd = &imds[i])->mi > maxh.ml; --i) {
+        int cc = 0, d = 0;
+        for ( ; r >= up; r -= width) ++d;
+        if (lw < imd->vlnk[d][r] && imd->vlnk[d][r] < up) {
+            cpos[10 * i + cc++] = imd->mi;
+            cpos[10 * i + cc++] = (d > 0) ? 1 : 0;
+            for (int rp = imd->hlnk[d][r]; lw <= rp && rp < up && r != rp; rp = imd->hlnk[d][r = rp])
+                cpos[10 * i + cc++] = r + imd->mi;
+            cpos[10 * i + cc++] = r + imd->mi;
+            cpos[10 * i + cc] = END_OF_ULK;
+            r = imd->vlnk[d][r];
+            if (r == END_OF_ULK) break;
+        } else
+            cpos[10 * i + 0] = END_OF_ULK;
+    }
+    for ( ; r > up; r -= width) ;
+    if (LocalL) {
+        a_left = maxh.ml;
+        b_left = r + a_left;
+    } else {
+        const int rl = b_left - a_left;
+        if (t->b_exgl && rl > r) {
+            a_left = b_left - r;
+            for (int j = 0; j < n_im && imds[j].mi < a_left; ++j) cpos[10 * j + 0] = END_OF_ULK;
+        }
+        if (t->a_exgl && rl < r) b_left = a_left + r;
+    }
+    ++i;
+    int bad = 0;
+    if (i >= 0 && i < n_im && imds[i].mi < a_left) bad = 1;
+    if (!bad && cpos[10 * i + 2] < b_left) bad = 1;
+    *score = bad ? NEVSEL32 : maxh.val;
+    ranges[0] = a_left; ranges[1] = a_right; ranges[2] = b_left; ranges[3] = b_right;
+    for (int k = 0; k < n_im; ++k) free(imds[k].buf);
+    free(imds); free(bbuf); free(cbuf); free(c.vbuf);
+    return 0;
+}
+
+/* =========================================================================
+ * The DP driver: Aln2s1::lspS_ng (src/fwd2s1.cc:1801-1897) with its helpers
+ * trcbkalignS_ng (1667-1710, SIMD branch), mimd_postwork (1714-1756),
+ * rcsv_postwork (1758-1799), diagonalS_ng (1629-1665) and stripe
+ * (src/aln2.cc:156-176), for simd = 2 | 3 (-A2 / -A3) and single affine gaps.
+ * Problems with fewer than 8 query rows go to the scalar exact-ILD kernel in
+ * the reference (src/fwd2s1.cc:1676); that kernel is not restated here, so
+ * such calls set `unsupported`.
+ * ========================================================================= */
+#include <math.h>
+
+typedef struct {
+    const so_params* p;
+    so_lsp_opts o;
+    int32_t* skl;
+    int cap, n;
+    int unsupported;
+} so_drv;
+
+static void drv_write(so_drv* d, int m, int n)
+{
+    if (d->n < d->cap) { d->skl[2 * d->n] = m; d->skl[2 * d->n + 1] = n; }
+    ++d->n;
+}
+
+static void so_stripe(so_task* t, int sh)
+{
+    if (sh < 0) {
+        int am = t->a_right - t->a_left, bn = t->b_right - t->b_left;
+        int shorter = am < bn ? am : bn;
+        sh = -sh * shorter / 100;
+    }
+    int up = t->b_right - t->a_right;
+    int lw = t->b_left - t->a_left;
+    if (up < lw) { int x = up; up = lw; lw = x; }
+    up += sh; lw -= sh;
+    int q;
+    if ((q = t->b_right - t->a_left) < up) up = q;
+    if ((q = t->b_left - t->a_right) > lw) lw = q;
+    t->up = up; t->lw = lw;
+}
+
+static int gap_ext_pen(const so_params* p, int i) { (void) i; return p->gep; }   /* codonk1 == LARGEN */
+static int gap_penalty(const so_params* p, int i) { return i == 0 ? 0 : p->gop + i * p->gep; }
+static int unp_penalty(const so_params* p, int d) { return d * p->gep; }
+
+static int drv_trcbk(so_drv* d, const so_task* t)
+{
+    const int width = t->up - t->lw + 3;
+    if (width < 0) return NEVSEL32;
+    const int m = t->a_right - t->a_left;
+    if (m < 8) { d->unsupported = 1; return NEVSEL32; }
+    int32_t score = 0;
+    int room = d->cap > d->n ? d->cap - d->n : 0;
+    int cnt = so_forward_wip(d->p, t, &score, d->skl + 2 * (d->n < d->cap ? d->n : d->cap), room, 0);
+    if (cnt < 0) { d->unsupported = 1; return NEVSEL32; }
+    d->n += cnt;
+    return score;
+}
+
+static int drv_diagonal(so_drv* d, const so_task* t)
+{
+    const so_params* p = d->p;
+    const int LocalL = p->local && t->a_exgl && t->b_exgl;
+    const int LocalR = p->local && t->a_exgr && t->b_exgr;
+    const int dlt = p->local ? 0 : ((t->b_right - t->b_left) - (t->a_right - t->a_left));
+    /* dlt < 0 swaps the roles of a and b */
+    const uint8_t* as = dlt < 0 ? t->b : t->a;
+    const uint8_t* bs = dlt < 0 ? t->a : t->b;
+    int al = dlt < 0 ? t->b_left : t->a_left, ar = dlt < 0 ? t->b_right : t->a_right;
+    int bl = dlt < 0 ? t->a_left : t->b_left;
+    int mL = al, mR = ar;
+    int scr = 0, maxh = NEVSEL32;
+    for (int m = al, k = 0; m++ < ar; ++k) {
+        int x = as[al + k], y = bs[bl + k];
+        scr += dlt < 0 ? p->simmtx[y * p->simdim + x] : p->simmtx[x * p->simdim + y];
+        if (LocalL && scr < 0) { scr = 0; mL = m; }
+        if (LocalR && scr > maxh) { maxh = scr; mR = m; }
+    }
+    int r = bl - al;
+    if (dlt < 0) r -= dlt;
+    drv_write(d, mL, mL + r);
+    drv_write(d, mR, mR + r);
+    return LocalR ? maxh : scr;
+}
+
+static int drv_lsp(so_drv* d, so_task* t);
+
+static void drv_mimd_postwork(so_drv* d, so_task* t, const int32_t* cpos, int n_imd)
+{
+    const int aleft = t->a_left, bleft = t->b_left;
+    t->a_exgl = t->b_exgl = t->a_exgr = t->b_exgr = 0;
+    int i = n_imd;
+    while (--i >= 0 && cpos[10 * i] == END_OF_ULK) ;
+    for ( ; i >= 0 && cpos[10 * i] != END_OF_ULK; --i) {
+        int c = 0;
+        t->a_left = cpos[10 * i + c];
+        t->b_exgl = cpos[10 * i + (++c)];
+        t->b_left = cpos[10 * i + (++c)];
+        if (t->b_left < 0 || t->b_left > t->b_right) break;
+        while (cpos[10 * i + (++c)] < END_OF_ULK) drv_write(d, t->a_left, cpos[10 * i + c]);
+        so_stripe(t, d->o.sh);
+        drv_trcbk(d, t);
+        t->a_right = t->a_left;
+        t->b_right = cpos[10 * i + c - 1];
+    }
+    if ((i < 0 && cpos[0] != END_OF_ULK) || cpos[2] != END_OF_ULK) {
+        t->a_left = aleft;
+        t->b_left = bleft;
+        so_stripe(t, d->o.sh);
+        drv_trcbk(d, t);
+    }
+}
+
+static void drv_rcsv_postwork(so_drv* d, so_task* t, const int32_t* cpos)
+{
+    t->a_exgl = t->b_exgl = t->a_exgr = t->b_exgr = 0;
+    int c = 0;
+    if (cpos[c++] < END_OF_ULK) {
+        while (cpos[++c] < END_OF_ULK) drv_write(d, cpos[0], cpos[c]);
+        const int aright = t->a_right, bright = t->b_right;
+        t->a_right = cpos[0];
+        t->b_right = cpos[c - 1];
+        so_stripe(t, d->o.sh);
+        drv_lsp(d, t);
+        t->a_left = cpos[0];
+        t->b_exgl = cpos[1];
+        t->b_left = cpos[2];
+        t->a_right = aright;
+        t->b_right = bright;
+        so_stripe(t, d->o.sh);
+        drv_lsp(d, t);
+    } else if (d->p->local) {
+        so_stripe(t, d->o.sh);
+        drv_trcbk(d, t);
+    }
+}
+
+static int drv_lsp(so_drv* d, so_task* t)
+{
+    const so_params* p = d->p;
+    const int m = t->a_right - t->a_left;
+    const int n = t->b_right - t->b_left;
+    if (!m && !n) return 0;
+    const int aexgl = t->a_exgl, aexgr = t->a_exgr, bexgl = t->b_exgl, bexgr = t->b_exgr;
+    if (!m || !n) {
+        drv_write(d, t->a_left, t->b_left);
+        drv_write(d, t->a_right, t->b_right);
+        if (m) return (aexgl || aexgr) ? gap_ext_pen(p, m) : gap_penalty(p, m);
+        return (bexgl || bexgr) ? gap_ext_pen(p, n) : unp_penalty(p, n);
+    }
+    if (t->up == t->lw) return drv_diagonal(d, t);
+    if (abs(n - m) < 8 || m == 1 || n == 1) return drv_trcbk(d, t);
+    int n_imd = 1;
+    int recursive = d->o.alg & 4;
+    const float coef_B = 2.f, coef_C = (float) ((p->noll + 1) * 4);
+    float cvol = (float) m * (n + m);                   /* rhombic, simd >= 2 */
+    if (coef_B * cvol < d->o.max_vmf_space) return drv_trcbk(d, t);
+    if (!recursive) {
+        const double z = 2. * m * coef_B / coef_C;
+        const int imd1 = (int) (pow(z, 1. / 3) + 0.5) - 1;
+        const float spc = coef_C * n * imd1 + coef_B * cvol / (imd1 + 1) / (imd1 + 1);
+        if (spc > d->o.max_vmf_space) recursive = 1;
+        else {
+            const int imd3 = m / NELEM;
+            if (d->o.ubh) n_imd = d->o.ubh;
+            else n_imd = imd1 < imd3 ? imd1 : imd3;
+            int imd_intvl = (m + n_imd) / (n_imd + 1);
+            if (imd_intvl * n_imd == m) --n_imd;
+            if (n_imd == 0) return drv_trcbk(d, t);
+        }
+    }
+    so_task saved = *t;
+    int32_t* cpos = (int32_t*) malloc(sizeof(int32_t) * 10 * (n_imd + 1));
+    int32_t ranges[4];
+    int32_t scr = 0;
+    if (so_hirschberg_wip(p, t, n_imd, &scr, cpos, ranges) < 0) { d->unsupported = 1; free(cpos); return NEVSEL32; }
+    t->a_left = ranges[0]; t->a_right = ranges[1]; t->b_left = ranges[2]; t->b_right = ranges[3];
+    if (scr > NEVSEL32) {
+        if (cpos[0] == END_OF_ULK) {
+            drv_write(d, t->a_left, t->b_left);
+            drv_write(d, t->a_right, t->b_right);
+        } else if (recursive)
+            drv_rcsv_postwork(d, t, cpos);
+        else
+            drv_mimd_postwork(d, t, cpos, n_imd);
+    }
+    *t = saved;
+    free(cpos);
+    return scr;
+}
+
+int so_lsp(const so_params* p, const so_task* t0, const so_lsp_opts* o, int32_t* score,
+           int32_t* skl, int cap, int* unsupported)
+{
+    so_drv d;
+    d.p = p; d.o = *o; d.skl = skl; d.cap = cap; d.n = 0; d.unsupported = 0;
+    so_task t = *t0;
+    *score = drv_lsp(&d, &t);
+    if (unsupported) *unsupported = d.unsupported;
+    return d.n;
+}

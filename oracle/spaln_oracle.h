@@ -64,6 +64,24 @@ int so_forward_wip(const so_params* p, const so_task* t, int32_t* score,
 /* scoreonlyS1_wip */
 int so_scoreonly_wip(const so_params* p, const so_task* t, int32_t* score);
 
+/* hirschbergS1_wip (src/fwd2s1_wip_simd.h:476-864), single affine.  cpos holds
+ * (n_im + 1) x 10 ints (Dim10 records); ranges receives a_left, a_right, b_left,
+ * b_right as the reference leaves them in the Seq objects. */
+int so_hirschberg_wip(const so_params* p, const so_task* t, int n_im,
+                      int32_t* score, int32_t* cpos, int32_t* ranges);
+
+/* Aln2s1::lspS_ng driver (trace-back vs multi-intermediate Hirschberg dispatch,
+ * src/fwd2s1.cc:1801-1897) */
+typedef struct {
+    int32_t max_vmf_space;  /* MaxVmfSpace (-V), src/vmf.h:26 */
+    int32_t sh;             /* alprm.sh band shoulder */
+    int32_t ubh;            /* alprm.ubh: forced number of intermediates (0 = automatic) */
+    int32_t alg;            /* algmode.alg (bit 2: recursive single-intermediate) */
+} so_lsp_opts;
+
+int so_lsp(const so_params* p, const so_task* t, const so_lsp_opts* o, int32_t* score,
+           int32_t* skl, int cap, int* unsupported);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,10 @@ def lib():
         _lib.so_forward_wip.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_void_p]
         _lib.so_scoreonly_wip.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.so_hirschberg_wip.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
+        _lib.so_lsp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_int, C.c_void_p]
     return _lib
 
 
@@ -113,3 +117,32 @@ def scoreonly_wip(p: dict, t: dict):
     if rc < 0:
         raise RuntimeError("so_scoreonly_wip failed")
     return {"score": score.value}
+
+
+def hirschberg_wip(p: dict, t: dict, n_im: int):
+    sp, st = make_params(p), make_task(t)
+    score = C.c_int32(0)
+    cpos = np.zeros((n_im + 1, 10), np.int32)
+    ranges = np.zeros(4, np.int32)
+    rc = lib().so_hirschberg_wip(C.byref(sp), C.byref(st), n_im, C.byref(score),
+                                 cpos.ctypes.data, ranges.ctypes.data)
+    if rc < 0:
+        raise RuntimeError(f"so_hirschberg_wip failed: {rc}")
+    return {"score": score.value, "cpos": cpos, "ranges": ranges.tolist()}
+
+
+class SoLspOpts(C.Structure):
+    _fields_ = [("max_vmf_space", C.c_int32), ("sh", C.c_int32), ("ubh", C.c_int32),
+                ("alg", C.c_int32)]
+
+
+def lsp(p: dict, t: dict, cap: int = 1 << 16, max_vmf_space=None):
+    sp, st = make_params(p), make_task(t)
+    o = SoLspOpts(int(max_vmf_space if max_vmf_space is not None else p["MaxVmfSpace"]),
+                  int(p["sh"]), int(p["ubh"]), int(p["alg"]))
+    score = C.c_int32(0)
+    unsup = C.c_int(0)
+    skl = np.zeros((cap, 2), np.int32)
+    n = lib().so_lsp(C.byref(sp), C.byref(st), C.byref(o), C.byref(score), skl.ctypes.data, cap,
+                     C.byref(unsup))
+    return {"score": score.value, "skl": skl[:min(n, cap)].copy(), "unsupported": bool(unsup.value)}

@@ -171,11 +171,16 @@ class RefTask:
         secs = C.c_double(0)
         skl = np.zeros((cap, 2), np.int32)
         cpos = np.zeros((n_imd + 1, 10), np.int32)
+        before = self.info()
         n = self.lib.ref_task_kernel(self.h, lw, up, kind, n_imd, mode,
                                      C.byref(score), skl.ctypes.data, cap,
                                      cpos.ctypes.data, C.byref(secs))
+        after = self.info()
+        if kind == 2:       # the Hirschberg pass narrows the Seq ranges: report, then restore
+            self.set(**before)
         return {"score": score.value, "skl": skl[:n].copy(), "cpos": cpos,
-                "seconds": secs.value}
+                "seconds": secs.value,
+                "ranges": [after["a_left"], after["a_right"], after["b_left"], after["b_right"]]}
 
     def adapter(self, lw, up, kind=0, device=0, cap=1 << 16):
         """the same problem through include/gspaln_spaln_adapter.hpp (GPU drop-in)"""
