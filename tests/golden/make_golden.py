@@ -30,6 +30,10 @@ CONFIGS = {
     "dna_A2_local": ("-Q0 -A2 -S1 -yX0 -LS -TDictyost", 12),
     "dna_A3_global": ("-Q0 -A3 -S1 -yX0 -TDictyost", 13),
     "dna_A2_tetrapod": ("-Q0 -A2 -S1 -TTetrapod", 14),
+    # small -V forces the unidirectional-Hirschberg path on small inputs (SURVEY section 4 pin d)
+    "dna_A2_udh": ("-Q0 -A2 -S1 -yX0 -V256K -TDictyost", 15),
+    "dna_A2_udh_local": ("-Q0 -A2 -S1 -yX0 -V256K -LS -TDictyost", 16),
+    "dna_A6_udh_recursive": ("-Q0 -A6 -S1 -yX0 -V128K -TDictyost", 17),
 }
 
 
@@ -45,6 +49,7 @@ def gen(name: str):
     for k, v in p.items():
         out["prm_" + k] = np.asarray(v)
     probs = []
+    udh = "udh" in name
 
     def add(g, q, comrev=False, tag="", **setkw):
         t = ref.task(g, q, comrev)
@@ -67,12 +72,28 @@ def gen(name: str):
         out[pre + "skl"] = r["skl"].astype(np.int32)
         out[pre + "score_only"] = np.int32(r1["score"])
         out[pre + "tag"] = np.array(tag)
+        if udh:
+            # the whole driver (Aln2s1::lspS_ng) and the Hirschberg pass alone
+            rl = t.lsp(lw, up)
+            out[pre + "lsp_score"] = np.int32(rl["score"])
+            out[pre + "lsp_skl"] = rl["skl"].astype(np.int32)
+            m = ex["a_right"] - ex["a_left"]
+            width = up - lw + 3
+            mode = 2 if (max(abs(lw), up) + width) < 32767 else 4
+            n_im = max(1, min(3, m // 16))
+            if m >= 16:
+                rh = t.kernel(lw, up, 2, n_imd=n_im, mode=mode)
+                out[pre + "udh_nim"] = np.int32(n_im)
+                out[pre + "udh_score"] = np.int32(rh["score"])
+                out[pre + "udh_cpos"] = rh["cpos"].astype(np.int32)
+                out[pre + "udh_ranges"] = np.array(rh["ranges"], np.int32)
         probs.append(i)
         t.close()
 
     # planted genes, both orientations of the query
     for i in range(10):
-        g, q, _ = synth.plant_gene(rng, qlen_range=(60, 500), flank=(50, 300))
+        g, q, _ = synth.plant_gene(rng, qlen_range=(60, 900) if udh else (60, 500),
+                                   flank=(50, 900) if udh else (50, 300))
         add(g, q, tag="gene")
         if i % 3 == 0:
             add(g, q, comrev=True, tag="gene_rc")

@@ -5,6 +5,7 @@ import numpy as np
 
 GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
 GOLDEN_NAMES = ["dna_A2_global", "dna_A2_local", "dna_A3_global", "dna_A2_tetrapod"]
+UDH_NAMES = ["dna_A2_udh", "dna_A2_udh_local", "dna_A6_udh_recursive"]
 GEOM_KEYS = ["a_left", "a_right", "b_left", "b_right", "a_exgl", "a_exgr", "b_exgl", "b_exgr",
              "lw", "up"]
 
@@ -23,5 +24,9 @@ def load(name):
              "score": int(z[pre + "score"]), "skl": z[pre + "skl"],
              "score_only": int(z[pre + "score_only"]), "tag": str(z[pre + "tag"])}
         d.update({k: int(v) for k, v in zip(GEOM_KEYS, z[pre + "geom"])})
+        for k in ("lsp_score", "lsp_skl", "udh_nim", "udh_score", "udh_cpos", "udh_ranges"):
+            if pre + k in z.files:
+                v = z[pre + k]
+                d[k] = v if v.ndim else int(v)
         probs.append(d)
     return prm, probs

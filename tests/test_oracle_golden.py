@@ -26,3 +26,39 @@ def test_golden_covers_edge_cases():
     # the re-basing case really exceeds the int16 range
     rb = [p for p in probs if p["tag"] == "rebase"][0]
     assert rb["score"] > 32767
+
+
+EOU = 2 ** 31 - 1 - 2     # end_of_ulk, src/aln.h:49
+
+
+def cpos_equal(a, b):
+    """Dim10 records are only defined up to their end_of_ulk terminator"""
+    for ra, rb in zip(a.tolist(), b.tolist()):
+        if ra[0] == EOU and rb[0] == EOU and ra[2] == rb[2]:
+            continue
+        ka = ra.index(EOU) if EOU in ra else 10
+        kb = rb.index(EOU) if EOU in rb else 10
+        if ra[:ka] != rb[:kb]:
+            return False
+    return True
+
+
+@pytest.mark.parametrize("name", golden_io.UDH_NAMES)
+def test_oracle_udh_matches_reference_golden(oracle, name):
+    """hirschbergS1_wip alone and the whole lspS_ng driver under a small -V"""
+    prm, probs = golden_io.load(name)
+    n_udh = n_lsp = 0
+    for i, pb in enumerate(probs):
+        if "udh_nim" in pb:
+            o = oracle.hirschberg_wip(prm, pb, pb["udh_nim"])
+            assert o["score"] == pb["udh_score"], (name, i, pb["tag"])
+            assert o["ranges"] == pb["udh_ranges"].tolist(), (name, i, pb["tag"])
+            assert cpos_equal(o["cpos"], pb["udh_cpos"]), (name, i, pb["tag"])
+            n_udh += 1
+        o = oracle.lsp(prm, pb)
+        if o["unsupported"]:        # < 8 query rows: scalar kernel of the reference, not restated
+            continue
+        assert o["score"] == pb["lsp_score"], (name, i, pb["tag"])
+        assert np.array_equal(o["skl"], pb["lsp_skl"]), (name, i, pb["tag"])
+        n_lsp += 1
+    assert n_udh >= 20 and n_lsp >= 20
