@@ -54,13 +54,17 @@ enum {
 
 enum {                          /* gspaln_task.kind */
     GSPALN_FORWARD_WIP = 0,     /* score + trace-back corners */
-    GSPALN_SCOREONLY_WIP = 1    /* score only */
+    GSPALN_SCOREONLY_WIP = 1,   /* score only */
+    GSPALN_HIRSCHBERG_WIP = 2   /* SimdAln2s1::hirschbergS1_wip(Dim10* cpos, n_imd)
+                                   (src/fwd2s1_wip_simd.h:476-864): score, crossing records
+                                   and the narrowed sequence ranges; global / semi-global only */
 };
 
 enum {                          /* gspaln_result.status */
     GSPALN_ST_OK = 0,
     GSPALN_ST_SKL_OVERFLOW = 1, /* more corners than skl_cap: n_skl is the needed count */
-    GSPALN_ST_BAD_TRACE = 2     /* reference would have called fatal("Unexpected dir") */
+    GSPALN_ST_BAD_TRACE = 2,    /* reference would have called fatal("Unexpected dir") */
+    GSPALN_ST_UNSUPPORTED = 3   /* needs a kernel that is not on the device yet */
 };
 
 /* frozen scoring parameters (reference globals -> one POD) */
@@ -96,6 +100,7 @@ typedef struct gspaln_task {
     int32_t b_exgl, b_exgr;
     int32_t lw, up;             /* WINDOW (src/cmn.h:133); width = up - lw + 3 */
     int32_t skl_cap;            /* capacity of result.skl in corners */
+    int32_t n_imd;              /* GSPALN_HIRSCHBERG_WIP: number of intermediate rows (>= 1) */
 } gspaln_task;
 
 typedef struct gspaln_result {
@@ -105,6 +110,10 @@ typedef struct gspaln_result {
     int32_t reserved;
     int64_t cells;              /* query rows x band columns evaluated (throughput accounting) */
     int32_t* skl;               /* caller buffer: skl[2*i] = m, skl[2*i+1] = n */
+    int32_t ranges[4];          /* HIRSCHBERG: a.left, a.right, b.left, b.right as the reference
+                                   leaves them in the Seq objects (src/fwd2s1_wip_simd.h:812-861) */
+    int32_t* cpos;              /* HIRSCHBERG: caller buffer, (n_imd + 1) x 10 int32 (Dim10 records,
+                                   src/udh_intermediate.h:90; rows end with INT_MAX - 2) */
 } gspaln_result;
 
 typedef struct gspaln_ctx gspaln_ctx;

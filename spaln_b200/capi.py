@@ -21,6 +21,8 @@ MAXDIM = 32
 
 FORWARD_WIP = 0
 SCOREONLY_WIP = 1
+HIRSCHBERG_WIP = 2
+END_OF_ULK = 2 ** 31 - 1 - 2
 
 EXPORTS = [
     "gspaln_create", "gspaln_destroy", "gspaln_submit", "gspaln_upload", "gspaln_run",
@@ -46,7 +48,7 @@ class GspalnTask(C.Structure):
         ("a", C.c_void_p), ("b", C.c_void_p), ("sig5", C.c_void_p), ("sig3", C.c_void_p),
         ("a_left", C.c_int32), ("a_right", C.c_int32), ("b_left", C.c_int32), ("b_right", C.c_int32),
         ("a_exgl", C.c_int32), ("a_exgr", C.c_int32), ("b_exgl", C.c_int32), ("b_exgr", C.c_int32),
-        ("lw", C.c_int32), ("up", C.c_int32), ("skl_cap", C.c_int32),
+        ("lw", C.c_int32), ("up", C.c_int32), ("skl_cap", C.c_int32), ("n_imd", C.c_int32),
     ]
 
 
@@ -54,6 +56,7 @@ class GspalnResult(C.Structure):
     _fields_ = [
         ("score", C.c_int32), ("status", C.c_int32), ("n_skl", C.c_int32), ("reserved", C.c_int32),
         ("cells", C.c_int64), ("skl", C.c_void_p),
+        ("ranges", C.c_int32 * 4), ("cpos", C.c_void_p),
     ]
 
 

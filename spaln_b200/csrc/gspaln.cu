@@ -7,6 +7,7 @@
 // API: without a CUDA device gspaln_create() fails with GSPALN_ENODEV.
 #include "../../include/gspaln.h"
 #include "gspaln_kernels.cuh"
+#include "gspaln_udh.cuh"
 
 #include <algorithm>
 #include <climits>
@@ -79,17 +80,23 @@ struct gspaln_ctx {
     DevBuf<unsigned char> d_trace;
     DevBuf<int2> d_skl;
     DevBuf<DevResult> d_res;
+    DevBuf<int> d_udh;              // per-warp UDH workspace (link band + intermediates)
+    DevBuf<int> d_cpos;
+    DevBuf<DevUdhOut> d_ures;
     PinBuf<DevTask> h_tasks;
     PinBuf<int> h_order;
     PinBuf<unsigned char> h_apool;
     PinBuf<ColInfo> h_cpool;
     PinBuf<int2> h_skl;
     PinBuf<DevResult> h_res;
+    PinBuf<int> h_cpos;
+    PinBuf<DevUdhOut> h_ures;
     // resident batch
     int n = 0;
-    int n_trace = 0, n_score = 0;
+    int n_trace = 0, n_score = 0, n_udh = 0;
     size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, skl_elems = 0;
-    int grid_run_trace = 0, grid_run_score = 0;
+    size_t udh_slab = 0, cpos_elems = 0;
+    int grid_run_trace = 0, grid_run_score = 0, grid_run_udh = 0, grid_udh = 0;
     std::vector<int64_t> cells;
     std::vector<int> skl_cap;
     gspaln_timing tim;
@@ -245,6 +252,12 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
     ctx->grid_trace = std::max(1, occ) * ctx->sm_count;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ks, CTA_THREADS, ctx->smem_bytes);
     ctx->grid_score = std::max(1, occ) * ctx->sm_count;
+    {
+        const void* ku = P.spj ? (const void*) dp_udh_kernel<true> : (const void*) dp_udh_kernel<false>;
+        cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_bytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ku, CTA_THREADS, ctx->smem_bytes);
+        ctx->grid_udh = std::max(1, occ) * ctx->sm_count;
+    }
     if (cudaGetLastError() != cudaSuccess) { gspaln_destroy(ctx); return GSPALN_ECUDA; }
     *out = ctx;
     return GSPALN_OK;
@@ -256,9 +269,9 @@ void gspaln_destroy(gspaln_ctx* ctx)
     cudaSetDevice(ctx->device);
     ctx->d_prm.release(); ctx->d_pen.release(); ctx->d_tasks.release(); ctx->d_order.release(); ctx->d_ticket.release();
     ctx->d_apool.release(); ctx->d_cpool.release(); ctx->d_band.release(); ctx->d_trace.release();
-    ctx->d_skl.release(); ctx->d_res.release();
+    ctx->d_skl.release(); ctx->d_res.release(); ctx->d_udh.release(); ctx->d_cpos.release(); ctx->d_ures.release();
     ctx->h_tasks.release(); ctx->h_order.release(); ctx->h_apool.release(); ctx->h_cpool.release();
-    ctx->h_skl.release(); ctx->h_res.release();
+    ctx->h_skl.release(); ctx->h_res.release(); ctx->h_cpos.release(); ctx->h_ures.release();
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -271,6 +284,8 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
     ctx->n = 0;
     // ---- layout
     size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, skl_elems = 0;
+    size_t udh_slab = 0, cpos_elems = 0;
+    int n_udh = 0;
     ctx->cells.assign(n, 0);
     ctx->skl_cap.assign(n, 0);
     std::vector<DevTask> dt(n);
@@ -278,7 +293,8 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
     for (int i = 0; i < n; ++i) {
         const gspaln_task& t = tasks[i];
         if (t.a_right < t.a_left || t.b_right < t.b_left || t.up < t.lw ||
-            (t.kind != GSPALN_FORWARD_WIP && t.kind != GSPALN_SCOREONLY_WIP) ||
+            (t.kind != GSPALN_FORWARD_WIP && t.kind != GSPALN_SCOREONLY_WIP && t.kind != GSPALN_HIRSCHBERG_WIP) ||
+            (t.kind == GSPALN_HIRSCHBERG_WIP && (t.n_imd < 1 || t.a_right - t.a_left < 2)) ||
             !t.a || !t.b || (ctx->prm.spj && (!t.sig5 || !t.sig3)))
             return fail(ctx, GSPALN_EINVAL, "bad task");
         DevTask& d = dt[i];
@@ -300,6 +316,13 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             trace_slab = std::max(trace_slab, align_up(nstrips * (size_t) (width + TRACE_PAD) * NELEM + 64, 256));
             skl_elems += (size_t) d.skl_cap;
             ++n_trace;
+        } else if (t.kind == GSPALN_HIRSCHBERG_WIP) {
+            d.pad0 = t.n_imd;
+            d.pad1 = (long long) cpos_elems;
+            cpos_elems += (size_t) 10 * (t.n_imd + 1);
+            udh_slab = std::max(udh_slab, align_up(2 * ((size_t) width + 2 * NELEM + 2) +
+                                                   (size_t) t.n_imd * 4 * width + 8, 64));
+            ++n_udh;
         } else
             ++n_score;
         ctx->cells[i] = task_cells(t);
@@ -307,11 +330,13 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
     }
     if (ctx->h_tasks.reserve(n + 1) != cudaSuccess || ctx->h_order.reserve(n + 1) != cudaSuccess ||
         ctx->h_apool.reserve(a_bytes + 16) != cudaSuccess || ctx->h_cpool.reserve(c_elems + 4) != cudaSuccess ||
-        ctx->h_res.reserve(n + 1) != cudaSuccess || ctx->h_skl.reserve(skl_elems + 1) != cudaSuccess)
+        ctx->h_res.reserve(n + 1) != cudaSuccess || ctx->h_skl.reserve(skl_elems + 1) != cudaSuccess ||
+        ctx->h_cpos.reserve(cpos_elems + 1) != cudaSuccess || ctx->h_ures.reserve(n + 1) != cudaSuccess)
         return fail(ctx, GSPALN_ENOMEM, "pinned host allocation");
     if (ctx->d_tasks.reserve(n + 1) != cudaSuccess || ctx->d_order.reserve(n + 1) != cudaSuccess ||
         ctx->d_apool.reserve(a_bytes + 16) != cudaSuccess || ctx->d_cpool.reserve(c_elems + 4) != cudaSuccess ||
-        ctx->d_skl.reserve(skl_elems + 1) != cudaSuccess || ctx->d_res.reserve(n + 1) != cudaSuccess) {
+        ctx->d_skl.reserve(skl_elems + 1) != cudaSuccess || ctx->d_res.reserve(n + 1) != cudaSuccess ||
+        ctx->d_cpos.reserve(cpos_elems + 1) != cudaSuccess || ctx->d_ures.reserve(n + 1) != cudaSuccess) {
         cudaGetLastError();
         return fail(ctx, GSPALN_ENOMEM, "device allocation");
     }
@@ -327,7 +352,13 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         free_b += ctx->d_trace.cap + ctx->d_band.cap * sizeof(unsigned);
         const size_t budget = (size_t) (0.85 * (double) free_b);
         while (gt > 1 && (size_t) gt * WARPS_PER_CTA * (trace_slab + band_slab * 4) > budget) gt = gt * 3 / 4;
-        const size_t warps = (size_t) std::max(gt, gs) * WARPS_PER_CTA;
+        int gu = n_udh ? ctas(ctx->grid_udh, n_udh) : 0;
+        const size_t warps = (size_t) std::max(std::max(gt, gs), gu) * WARPS_PER_CTA;
+        if (ctx->d_udh.reserve((size_t) gu * WARPS_PER_CTA * udh_slab + 64) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, GSPALN_ENOMEM, "device UDH workspace allocation");
+        }
+        ctx->grid_run_udh = gu;
         if (ctx->d_band.reserve(warps * band_slab + 32) != cudaSuccess ||
             ctx->d_trace.reserve((size_t) gt * WARPS_PER_CTA * trace_slab + 256) != cudaSuccess) {
             cudaGetLastError();
@@ -369,7 +400,8 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
     ctx->tim.h2d_ms = ms;
     ctx->tim.h2d_bytes = (int64_t) (sizeof(DevTask) * n + sizeof(int) * n + a_bytes + sizeof(ColInfo) * c_elems);
-    ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score;
+    ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score; ctx->n_udh = n_udh;
+    ctx->udh_slab = udh_slab; ctx->cpos_elems = cpos_elems;
     ctx->a_bytes = a_bytes; ctx->c_elems = c_elems; ctx->band_slab = band_slab;
     ctx->trace_slab = trace_slab; ctx->skl_elems = skl_elems;
     int64_t cells = 0, tb = 0;
@@ -407,6 +439,15 @@ int gspaln_run(gspaln_ctx* ctx)
                 ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p);
             ++launches;
         }
+        if (ctx->n_udh) {
+            CK(cudaMemsetAsync(ctx->d_ticket.p + 2, 0, sizeof(int), ctx->stream));
+            auto ku = spj ? dp_udh_kernel<true> : dp_udh_kernel<false>;
+            ku<<<ctx->grid_run_udh, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+                ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p + 2,
+                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
+                ctx->d_udh.p, (long long) ctx->udh_slab, ctx->d_cpos.p, ctx->d_ures.p);
+            ++launches;
+        }
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -427,6 +468,10 @@ int gspaln_download(gspaln_ctx* ctx, gspaln_result* results)
     if (n) CK(cudaMemcpyAsync(ctx->h_res.p, ctx->d_res.p, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (ctx->skl_elems)
         CK(cudaMemcpyAsync(ctx->h_skl.p, ctx->d_skl.p, sizeof(int2) * ctx->skl_elems, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->n_udh) {
+        CK(cudaMemcpyAsync(ctx->h_ures.p, ctx->d_ures.p, sizeof(DevUdhOut) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_cpos.p, ctx->d_cpos.p, sizeof(int) * ctx->cpos_elems, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
@@ -439,6 +484,13 @@ int gspaln_download(gspaln_ctx* ctx, gspaln_result* results)
         o.score = r.score; o.status = r.status; o.n_skl = r.n_skl; o.reserved = 0;
         o.cells = ctx->cells[i];
         const DevTask& d = ctx->h_tasks.p[i];
+        if (d.kind == GSPALN_HIRSCHBERG_WIP) {
+            const DevUdhOut& u = ctx->h_ures.p[i];
+            o.score = u.score; o.status = u.status; o.n_skl = 0;
+            o.ranges[0] = u.a_left; o.ranges[1] = u.a_right; o.ranges[2] = u.b_left; o.ranges[3] = u.b_right;
+            if (o.cpos) memcpy(o.cpos, ctx->h_cpos.p + d.pad1, sizeof(int) * 10 * (size_t) (d.pad0 + 1));
+            continue;
+        }
         if (o.skl && d.skl_cap > 0) {
             const int cnt = std::min(r.n_skl, d.skl_cap);
             memcpy(o.skl, ctx->h_skl.p + d.skl_off, sizeof(int2) * (size_t) std::max(0, cnt));

@@ -1,0 +1,525 @@
+// gspaln_udh.cuh -- unidirectional-Hirschberg forward pass on sm_100a.
+//
+// Semantics: SimdAln2s1::hirschbergS1_wip of the reference
+// (src/fwd2s1_wip_simd.h:476-864; link initialisation src/fwd2s1_simd.cc:205-238;
+// intermediates src/udh_intermediate.h:29-88) for single affine gaps in the
+// global / semi-global modes.  No trace matrix is written: every cell carries a
+// link (the diagonal on which its path crossed the previous intermediate row,
+// or started) next to H, F, E and the best-donor value.  At the n_imd
+// intermediate rows the links are recorded into per-problem arrays and reset;
+// a back-walk over those arrays produces the crossing records (`Dim10 cpos[]`)
+// from which the host driver cuts the problem into blocks (mimd_postwork).
+//
+// Mapping: same systolic scheme as gspaln_kernels.cuh (anti-diagonal evaluation
+// inside a thread, strips chained through the diagonal-indexed band buffer),
+// with NRU = 4 rows per thread (4 threads per strip, 8 strips per pass) to keep
+// the doubled per-row state in registers.  The band buffer carries a second
+// word pair {H link, F link} per diagonal.
+#pragma once
+#include "gspaln_kernels.cuh"
+
+namespace gspaln {
+
+constexpr int NRU = 4;                  // strip rows per thread in the UDH kernel
+constexpr int TPSU = NELEM / NRU;       // threads per strip
+constexpr int SPPU = 32 / TPSU;         // strips per pass
+constexpr int END_OF_ULK = INT_MAX - 2; // src/aln.h:49
+constexpr int NEVSEL32 = INT_MIN / 16 * 7;  // NEVSEL, src/cmn.h:79
+
+// per-row event bits handed from the cell loop to the intermediate-row logic
+enum : unsigned { EV_HORI = 1, EV_VERT = 2, EV_ACC = 4, EV_DON = 8 };
+
+template <bool SPJ>
+__device__ __forceinline__ void strip_step_udh(
+    int (&HO)[NRU], const int (&HN)[NRU], int (&F)[NRU], int (&E)[NRU],
+    int (&V2)[NRU], int (&NJ)[NRU],
+    int (&CO)[NRU], const int (&CN)[NRU], int (&FC)[NRU], int (&EC)[NRU], int (&C2)[NRU],
+    const int (&arow)[NRU],
+    const char* __restrict__ ring_hi, const char* __restrict__ mtx_bytes,
+    const int2* __restrict__ pen_tab, int pen_cap, int step,
+    int up_h, int up_f, int up_d, int up_c, int up_fc, int up_dc,
+    int gn, int ge, unsigned& events)
+{
+    events = 0u;
+#pragma unroll
+    for (int k = NRU - 1; k >= 0; --k) {
+        const RingEntry re = *reinterpret_cast<const RingEntry*>(
+            ring_hi - k * (CTA_THREADS * (int) sizeof(RingEntry)));
+        const int left = HN[k], lc = CN[k];
+        const int uh = k ? HN[k ? k - 1 : 0] : up_h;
+        const int uf = k ? F[k ? k - 1 : 0] : up_f;
+        const int dg = k ? HO[k ? k - 1 : 0] : up_d;
+        const int uc = k ? CN[k ? k - 1 : 0] : up_c;
+        const int ufc = k ? FC[k ? k - 1 : 0] : up_fc;
+        const int dc = k ? CO[k ? k - 1 : 0] : up_dc;
+        unsigned ev = 0;
+        // horizontal
+        int x = satlo(left + gn);
+        int e = satlo(E[k] + ge);
+        if (!(e > x)) { e = x; EC[k] = lc; }
+        E[k] = e;
+        // vertical
+        int f = satlo(uf + ge);
+        x = satlo(uh + gn);
+        int fcl = ufc;
+        if (!(f > x)) { f = x; fcl = uc; }
+        F[k] = f; FC[k] = fcl;
+        // diagonal, best of three
+        const int pv = *reinterpret_cast<const int*>(mtx_bytes + re.prof + arow[k]);
+        int h = sat16(pv + dg);
+        int hc = dc;
+        if (f > h) { h = f; hc = fcl; ev = EV_VERT; }
+        if (e > h) { h = e; hc = EC[k]; ev = EV_HORI; }
+        if (SPJ) {
+            const int q0 = sat16(V2[k] + re.s3);
+            const int2 pq = pen_tab[min(step + NJ[k], pen_cap)];
+            const int q = min(max(q0 + pq.x, pq.y), 32767);
+            if (q > h) { h = q; hc = C2[k]; ev |= EV_ACC; }
+            // donor (no empty-intron guard in the Hirschberg pass)
+            const int qd = sat16(h + re.s5);
+            if (qd > V2[k]) { V2[k] = qd; C2[k] = hc; NJ[k] = -step; ev |= EV_DON; }
+        }
+        HO[k] = h;
+        CO[k] = hc;
+        events |= ev << (4 * k);
+    }
+}
+
+struct UdhTaskView {
+    int* bandc;         // {H link, F link} per diagonal (int2), buf_size entries
+    int* imd;           // n_imd x 4 x width: hlnk0, hlnk1, vlnk0, vlnk1
+    int n_imd, n_active, mm0;
+};
+
+template <bool SPJ>
+__device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
+                             const DevTask& t, const UdhTaskView& uv,
+                             const unsigned char* __restrict__ aseq,
+                             const ColInfo* __restrict__ cols, unsigned* band,
+                             int ml0, int nstr, int& rlst_io)
+{
+    const int lane = threadIdx.x & 31;
+    const int sidx = lane / TPSU;
+    const int sub = lane % TPSU;
+    const int row0 = sub * NRU;
+    const StripGeom g = strip_geom<false>(t, ml0 + NELEM * sidx);    // `n < n9`
+    const int j8 = g.j9 - 1;
+    const int nsteps = g.n_last - g.n_start + 1;
+    const bool live = sidx < nstr && nsteps > 0;
+    const int width = t.up - t.lw + 3;
+
+    const int n_start0 = __shfl_sync(0xffffffffu, g.n_start, 0);
+    const int off = (g.n_start - n_start0) + (NELEM - 1 + LAG) * sidx;
+    int niter = live ? off + nsteps : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) niter = max(niter, __shfl_xor_sync(0xffffffffu, niter, o));
+    if (niter == 0) return;
+
+    // Which intermediate row (if any) lies in this strip?  mi_i = a_left + mm0 (i + 1).
+    // The reference advances to the next intermediate only after the strip holding the
+    // current one, so only the strictly increasing prefix (n_active) is ever visited.
+    int imd_i = -1, k8 = -1;
+    if (live && uv.n_active > 0) {
+        const int lo = g.ml + 1 - t.a_left;                 // first row of the strip, relative
+        int i = (lo + uv.mm0 - 1) / uv.mm0 - 1;             // smallest i with mi_i >= first row
+        if (i < 0) i = 0;
+        const int mi = t.a_left + uv.mm0 * (i + 1);
+        if (i < uv.n_active && mi >= g.ml + 1 && mi <= g.ml + NELEM && mi <= t.a_right) {
+            imd_i = i;
+            k8 = mi - g.ml - 1;                             // strip row of the intermediate
+        }
+    }
+    const bool has_imd = imd_i >= 0 && k8 >= row0 && k8 < row0 + NRU;
+    const int k8l = k8 - row0;
+    int* hl0 = uv.imd + (long long) max(imd_i, 0) * 4 * width - (t.lw - 1);   // index by diagonal
+    int* hl1 = hl0 + width;
+    int* vl0 = hl0 + 2 * width;
+    int* vl1 = hl0 + 3 * width;
+    int donor_r = g.n_start - (g.ml + 1);
+    int rlst = rlst_io;
+
+    int HA[NRU], HB[NRU], F[NRU], E[NRU], V2[NRU], NJ[NRU], arow[NRU];
+    int CA[NRU], CB[NRU], FC[NRU], EC[NRU], C2[NRU];
+#pragma unroll
+    for (int k = 0; k < NRU; ++k) {
+        HA[k] = NEV; HB[k] = NEV; F[k] = NEV; E[k] = NEV; V2[k] = NEV; NJ[k] = 0;
+        CA[k] = 0; CB[k] = 0; FC[k] = 0; EC[k] = 0; C2[k] = 0;
+        arow[k] = (live && row0 + k < g.j9) ? 4 * (int) aseq[(g.ml - t.a_left) + row0 + k] : 4 * ZROW;
+    }
+    const int gn = P.gn, ge = P.ge;
+    int prev_uh = NEV, prev_uc = 0;
+    const int band_bias = g.ml + t.lw - 1;
+    RingEntry* ring = sm.ring + threadIdx.x;
+    const char* mtx_bytes = reinterpret_cast<const char*>(sm.mtx);
+    const int ipen = P.ipen;
+    const bool owns_bottom = live && j8 >= row0 && j8 < row0 + NRU;
+    const int kbot = j8 - row0;
+    const int2* bandc = reinterpret_cast<const int2*>(uv.bandc);
+
+    auto col_fetch = [&](int c) -> uint2 {
+        if (c >= t.b_left && c <= t.b_right)
+            return __ldg(reinterpret_cast<const uint2*>(cols + (c - t.b_left)));
+        return make_uint2(0u, 0xffffffffu);
+    };
+    auto col_decode = [&](uint2 ci, int c, bool with_sig) -> RingEntry {
+        RingEntry re;
+        re.pad = 0;
+        re.prof = ZROW * (MTX_LD * 4);
+        re.s3 = 0; re.s5 = 0;
+        if (ci.y != 0xffffffffu) {
+            if (c > t.b_left) re.prof = (int) (ci.y & 0xffu) * (MTX_LD * 4);
+            if (SPJ && with_sig) {
+                re.s3 = hi16(ci.x);
+                re.s5 = (int) (short) (lo16(ci.x) + ipen);
+            }
+        }
+        return re;
+    };
+
+    unsigned nxt_band = 0;
+    int2 nxt_bandc = make_int2(0, 0);
+    uint2 nxt_col = make_uint2(0u, 0xffffffffu);
+
+    for (int i = -1; i < niter; ++i) {
+        const int j = i - off;
+        const int sh_h = __shfl_up_sync(0xffffffffu, (i & 1) ? HA[NRU - 1] : HB[NRU - 1], 1);
+        const int sh_f = __shfl_up_sync(0xffffffffu, F[NRU - 1], 1);
+        const int sh_c = __shfl_up_sync(0xffffffffu, (i & 1) ? CA[NRU - 1] : CB[NRU - 1], 1);
+        const int sh_fc = __shfl_up_sync(0xffffffffu, FC[NRU - 1], 1);
+        if (live && j == -1) {
+            if (sub == 0) {
+                nxt_band = __ldcg(band + (g.n_start - band_bias));
+                nxt_bandc = __ldcg(bandc + (g.n_start - band_bias));
+                prev_uh = lo16(__ldcg(band + (g.n_start - 1 - band_bias)));
+                prev_uc = __ldcg(bandc + (g.n_start - 1 - band_bias)).x;
+            }
+            nxt_col = col_fetch(g.n_start);
+#pragma unroll 1
+            for (int d = 1; d < NELEM; ++d) {
+                const int c = g.n_start - d;
+                const RingEntry re = col_decode(col_fetch(c), c, false);
+                ring[(c & 15) * CTA_THREADS] = re;
+                ring[((c & 15) + 16) * CTA_THREADS] = re;
+            }
+        } else if (live && j >= 0 && j < nsteps) {
+            const int n = g.n_start + j;
+            const unsigned cur_band = nxt_band;
+            const int2 cur_bandc = nxt_bandc;
+            const RingEntry cur_col = col_decode(nxt_col, n, n <= t.b_right);
+            if (j + 1 < nsteps) {
+                if (sub == 0) {
+                    nxt_band = __ldcg(band + (n + 1 - band_bias));
+                    nxt_bandc = __ldcg(bandc + (n + 1 - band_bias));
+                }
+                nxt_col = col_fetch(n + 1);
+            }
+            const int slot = n & 15;
+            ring[slot * CTA_THREADS] = cur_col;
+            ring[(slot + 16) * CTA_THREADS] = cur_col;
+            const char* ring_hi = reinterpret_cast<const char*>(ring + (slot + 16 - row0) * CTA_THREADS);
+            int up_h, up_f, up_c, up_fc;
+            if (sub == 0) {
+                up_h = lo16(cur_band); up_f = hi16(cur_band);
+                up_c = cur_bandc.x; up_fc = cur_bandc.y;
+            } else {
+                up_h = sh_h; up_f = sh_f; up_c = sh_c; up_fc = sh_fc;
+            }
+            const int up_d = prev_uh, up_dc = prev_uc;
+            prev_uh = up_h; prev_uc = up_c;
+            unsigned events;
+            if (i & 1)
+                strip_step_udh<SPJ>(HB, HA, F, E, V2, NJ, CB, CA, FC, EC, C2, arow, ring_hi, mtx_bytes,
+                                    sm.pen, P.pen_cap, j, up_h, up_f, up_d, up_c, up_fc, up_dc, gn, ge, events);
+            else
+                strip_step_udh<SPJ>(HA, HB, F, E, V2, NJ, CA, CB, FC, EC, C2, arow, ring_hi, mtx_bytes,
+                                    sm.pen, P.pen_cap, j, up_h, up_f, up_d, up_c, up_fc, up_dc, gn, ge, events);
+            // ---- intermediate row (src/fwd2s1_wip_simd.h:694-705, 760-773)
+            if (has_imd) {
+                const int rj = (n - k8) - (g.ml + k8 + 1);
+                if (rj >= t.lw && rj <= t.up) {
+                    const unsigned ev = (events >> (4 * k8l)) & 15u;
+                    if (ev & EV_ACC) { hl0[rj] = donor_r; hl1[rj] = donor_r + width; rlst = rj; }
+                    if (ev & EV_DON) donor_r = rj;
+                    if (!(ev & (EV_HORI | EV_VERT))) rlst = rj;         // diagonal
+                    if (ev & EV_HORI) hl0[rj] = rlst;
+                    int hcv = 0, fcv = 0;
+#pragma unroll
+                    for (int k = 0; k < NRU; ++k)
+                        if (k == k8l) { hcv = (i & 1) ? CB[k] : CA[k]; fcv = FC[k]; }
+                    vl0[rj] = hcv;
+                    vl1[rj] = fcv;
+#pragma unroll
+                    for (int k = 0; k < NRU; ++k)
+                        if (k == k8l) {
+                            if (i & 1) CB[k] = rj; else CA[k] = rj;
+                            FC[k] = rj + width;
+                        }
+                }
+            }
+            if (owns_bottom) {
+                int out_h = (i & 1) ? HB[NRU - 1] : HA[NRU - 1];
+                int out_f = F[NRU - 1];
+                int out_c = (i & 1) ? CB[NRU - 1] : CA[NRU - 1];
+                int out_fc = FC[NRU - 1];
+                if (kbot != NRU - 1) {
+#pragma unroll
+                    for (int k = 0; k < NRU - 1; ++k)
+                        if (k == kbot) {
+                            out_h = (i & 1) ? HB[k] : HA[k]; out_f = F[k];
+                            out_c = (i & 1) ? CB[k] : CA[k]; out_fc = FC[k];
+                        }
+                }
+                const int cb = n - j8;
+                const int r0 = cb - (g.ml + g.j9);
+                if (cb > t.b_left && r0 >= t.lw && r0 <= t.up) {
+                    __stcg(band + (r0 - t.lw + 1), pack16(out_h, out_f));
+                    __stcg(reinterpret_cast<int2*>(uv.bandc) + (r0 - t.lw + 1), make_int2(out_c, out_fc));
+                }
+            }
+        } else {
+            prev_uh = NEV; prev_uc = 0;
+        }
+        __syncwarp();
+    }
+    // rlst after this pass: the value left by the thread that handled the LAST
+    // intermediate of the pass (intermediates of one pass run concurrently; the
+    // reference runs them in order -- see DESIGN.md for the tie this leaves open)
+    int who = has_imd ? lane : -1;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) who = max(who, __shfl_xor_sync(0xffffffffu, who, o));
+    if (who >= 0) rlst_io = __shfl_sync(0xffffffffu, rlst, who);
+}
+
+struct DevUdhOut {                      // per problem
+    int score, status;
+    int a_left, a_right, b_left, b_right;
+    int pad0, pad1;
+};
+
+template <bool SPJ>
+__global__ void __launch_bounds__(CTA_THREADS, 3)
+dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
+              const DevTask* __restrict__ tasks, const int* __restrict__ order, int ntasks, int* ticket,
+              const unsigned char* __restrict__ apool, const ColInfo* __restrict__ cpool,
+              unsigned* bandpool, long long band_slab, int* udhpool, long long udh_slab,
+              int* cpospool, DevUdhOut* results)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ DevParams sP;
+    {
+        const int* src = reinterpret_cast<const int*>(gP);
+        int* dst = reinterpret_cast<int*>(&sP);
+        for (int i = threadIdx.x; i < (int) (sizeof(DevParams) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const DevParams& P = sP;
+    SmemLayout sm;
+    sm.ring = reinterpret_cast<RingEntry*>(smem_raw);
+    int2* spen = reinterpret_cast<int2*>(smem_raw + sizeof(RingEntry) * RING * CTA_THREADS);
+    for (int i = threadIdx.x; i <= P.pen_cap; i += blockDim.x) spen[i] = gpen[i];
+    sm.pen = spen;
+    sm.mtx = sP.mtxT;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const long long wslot = (long long) blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    unsigned* band = bandpool + wslot * band_slab;
+    int* uslab = udhpool + wslot * udh_slab;
+
+    for (;;) {
+        int tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (tk >= ntasks) break;
+        const int ti = order[tk];
+        const DevTask t = tasks[ti];
+        if (t.kind != 2) continue;
+        const unsigned char* aseq = apool + t.a_off;
+        const ColInfo* cols = cpool + t.col_off;
+        const int width = t.up - t.lw + 3;
+        const int buf_size = width + 2 * NELEM;
+        const bool a_exgl = t.flags & 1, a_exgr = t.flags & 2, b_exgl = t.flags & 4, b_exgr = t.flags & 8;
+        const int n_imd = t.pad0;
+        int* cpos = cpospool + t.pad1;
+
+        UdhTaskView uv;
+        uv.bandc = uslab;
+        uv.imd = uslab + 2 * (long long) ((buf_size + 1) & ~1);
+        uv.n_imd = n_imd;
+        uv.mm0 = (t.a_right - t.a_left + n_imd) / (n_imd + 1);
+        {
+            // strictly increasing prefix of the strips that hold an intermediate row
+            int na = 0, prev = INT_MIN;
+            for (int i = 0; i < n_imd; ++i) {
+                const int mi = t.a_left + uv.mm0 * (i + 1);
+                const int mm = t.a_left + (mi - t.a_left - 1) / NELEM * NELEM;
+                if (mm <= prev || mm >= t.a_right) break;
+                prev = mm; ++na;
+            }
+            uv.n_active = na;
+        }
+
+        // ---- fhinitS1: scores (src/fwd2s1_simd.cc:163-184) and links (205-238)
+        for (int i = lane; i < buf_size; i += 32) band[i] = pack16(NEV, NEV);
+        for (long long i = lane; i < (long long) n_imd * 4 * width; i += 32) uv.imd[i] = END_OF_ULK;
+        for (int i = lane; i <= n_imd; i += 32) { cpos[10 * i + 0] = END_OF_ULK; cpos[10 * i + 2] = END_OF_ULK; }
+        __syncwarp();
+        {
+            const int rl = t.b_left - t.a_left;
+            const int ru = t.up + 2 * NELEM;
+            int rr = t.b_right - t.a_left;
+            if (t.up < rr) rr = t.up;
+            if (b_exgl)
+                for (int r = t.lw + lane; r < rl; r += 32) band[r - t.lw + 1] = pack16(0, NEV);
+            if (a_exgl) {
+                for (int r = rl + lane; r <= rr; r += 32) band[r - t.lw + 1] = pack16(0, NEV);
+            } else if (lane == 0) {
+                int r = rl;
+                int v = 0;
+                band[r - t.lw + 1] = pack16(0, NEV);
+                ++r;
+                v = (short) P.gappen1;
+                band[r - t.lw + 1] = pack16(v, NEV);
+                if (P.gep) {
+                    int x = (NEV - P.gop) / P.gep + rl;
+                    if (x < rr) rr = x;
+                    while (++r < rr) { v = (short) (v + P.gep); band[r - t.lw + 1] = pack16(v, NEV); }
+                } else {
+                    for (int q = r; q < rr; ++q) band[q - t.lw + 1] = pack16(v, NEV);
+                }
+            }
+            // links: hc[r] = own diagonal along free ends, else the corner diagonal; fc = hc
+            int2* bc = reinterpret_cast<int2*>(uv.bandc);
+            for (int i = lane; i < buf_size; i += 32) {
+                const int r = t.lw - 1 + i;
+                int v;
+                if (r < rl) v = b_exgl ? r : rl;
+                else if (r == rl) v = rl;
+                else v = a_exgl ? (r < ru ? r : rl) : rl;
+                if (r > ru) v = 0;
+                bc[i] = make_int2(v, v);
+            }
+        }
+        __threadfence_block();
+        __syncwarp();
+
+        int accscr = 0;
+        const int md = checkpoint(P.avmch, 0);
+        int mc = md + t.a_left;
+        int rlst = INT_MAX;
+        int ml0 = t.a_left;
+        while (ml0 < t.a_right) {
+            int nstr = min(SPPU, (t.a_right - ml0 + NELEM - 1) / NELEM);
+            if (mc >= ml0 && mc < ml0 + nstr * NELEM && ((mc - ml0) % NELEM) == 0)
+                nstr = (mc - ml0) / NELEM + 1;
+            run_pass_udh<SPJ>(P, sm, t, uv, aseq, cols, band, ml0, nstr, rlst);
+            const int last_ml = ml0 + (nstr - 1) * NELEM;
+            if (last_ml == mc) {
+                const int nmax = t.up - t.lw;
+                int cm = lo16(__ldcg(band + 1));
+                for (int i = lane; i < nmax; i += 32) cm = max(cm, lo16(__ldcg(band + 1 + i)));
+#pragma unroll
+                for (int o = 16; o; o >>= 1) cm = max(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+                const int d = checkpoint(P.avmch, cm);
+                if (d < md / 2) {
+                    const int nn = width / NELEM * NELEM;
+                    for (int i = lane; i < width; i += 32) {
+                        const unsigned w = __ldcg(band + i);
+                        int h = lo16(w) - cm, f = hi16(w) - cm;
+                        if (i < nn) { h = sat16(h); f = sat16(f); }
+                        else { h = (short) h; f = (short) f; }
+                        __stcg(band + i, pack16(h, f));
+                    }
+                    accscr += cm;
+                    mc += md;
+                } else
+                    mc += d;
+                __syncwarp();
+            }
+            ml0 += nstr * NELEM;
+        }
+        __threadfence_block();
+        __syncwarp();
+
+        // ---- fhlastS1 with links (src/fwd2s1_simd.cc:241-262) ...
+        const int rr = t.b_right - t.a_right;
+        int maxr = rr;
+        auto argmax = [&](int from, int n) -> int {
+            int bv = INT_MIN, bi = INT_MAX;
+            for (int i = lane; i < n; i += 32) {
+                const int v = lo16(__ldcg(band + (from + i - t.lw + 1)));
+                if (v > bv) { bv = v; bi = from + i; }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            return n <= 0 ? from : bi;
+        };
+        if (a_exgr) {
+            const int r = max(t.lw, t.b_left - t.a_right);
+            maxr = argmax(r, rr - r);
+        }
+        if (b_exgr) {
+            const int r = min(t.up - 1, t.b_right - t.a_left);
+            const int mv = argmax(rr, r - rr);
+            if (lo16(__ldcg(band + (mv - t.lw + 1))) > lo16(__ldcg(band + (maxr - t.lw + 1)))) maxr = mv;
+        }
+        if (lane == 0) {
+            // ... and the back-walk over the intermediates (src/fwd2s1_wip_simd.h:825-863)
+            const int lw = t.lw, up = t.up;
+            int val = lo16(__ldcg(band + (maxr - lw + 1))) + accscr;
+            int a_left = t.a_left, a_right = t.a_right, b_left = t.b_left, b_right = t.b_right;
+            if (maxr > rr) a_right = t.b_right - maxr; else b_right = t.a_right + maxr;
+            int r = __ldcg(reinterpret_cast<const int2*>(uv.bandc) + (maxr - lw + 1)).x;
+            const int maxh_ml = a_left;
+            auto MI = [&](int i) { return t.a_left + uv.mm0 * (i + 1); };
+            auto L = [&](int i, int which, int d, int rr_) -> int& {
+                return uv.imd[(long long) i * 4 * width + (which * 2 + d) * width + (rr_ - (lw - 1))];
+            };
+            int i = n_imd;
+            while (--i >= 0 && MI(i) > a_right) ;
+            if (i < 0 && MI(0) > a_right) cpos[2] = b_right;
+            for ( ; i >= 0 && MI(i) > maxh_ml; --i) {
+                int cc = 0, d = 0;
+                for ( ; r >= up; r -= width) ++d;
+                const int v = L(i, 1, d, r);
+                if (lw < v && v < up) {
+                    cpos[10 * i + cc++] = MI(i);
+                    cpos[10 * i + cc++] = d > 0 ? 1 : 0;
+                    for (int rp = L(i, 0, d, r); lw <= rp && rp < up && r != rp; rp = L(i, 0, d, r = rp))
+                        if (cc < 9) cpos[10 * i + cc++] = r + MI(i);
+                    if (cc < 9) cpos[10 * i + cc++] = r + MI(i);
+                    cpos[10 * i + cc] = END_OF_ULK;
+                    r = L(i, 1, d, r);
+                    if (r == END_OF_ULK) break;
+                } else
+                    cpos[10 * i + 0] = END_OF_ULK;
+            }
+            for ( ; r > up; r -= width) ;
+            {
+                const int rl = b_left - a_left;
+                if (b_exgl && rl > r) {
+                    a_left = b_left - r;
+                    for (int jx = 0; jx < n_imd && MI(jx) < a_left; ++jx) cpos[10 * jx + 0] = END_OF_ULK;
+                }
+                if (a_exgl && rl < r) b_left = a_left + r;
+            }
+            ++i;
+            bool bad = false;
+            if (i >= 0 && i < n_imd && MI(i) < a_left) bad = true;
+            if (!bad && cpos[10 * i + 2] < b_left) bad = true;
+            DevUdhOut o;
+            o.score = bad ? NEVSEL32 : val;
+            o.status = 0;
+            o.a_left = a_left; o.a_right = a_right; o.b_left = b_left; o.b_right = b_right;
+            o.pad0 = o.pad1 = 0;
+            results[ti] = o;
+        }
+        __syncwarp();
+    }
+}
+
+}   // namespace gspaln

@@ -36,6 +36,7 @@ class Problem:
     b_exgl: int = 1
     b_exgr: int = 1
     skl_cap: int = 0        # 0: a_len + b_len + 8
+    n_imd: int = 0          # hirschbergS1_wip only: number of intermediate rows
 
     @staticmethod
     def from_export(ex: dict, lw: int, up: int) -> "Problem":
@@ -56,6 +57,8 @@ class Result:
     status: int
     skl: np.ndarray         # (n, 2) int32 corners, alignment end first
     cells: int
+    ranges: tuple = ()      # hirschbergS1_wip: (a_left, a_right, b_left, b_right) afterwards
+    cpos: np.ndarray = None  # hirschbergS1_wip: (n_imd + 1, 10) crossing records
 
 
 @dataclass
@@ -123,6 +126,7 @@ class Engine:
             t.lw, t.up = p.lw, p.up
             cap = p.skl_cap or ((p.a_right - p.a_left) + (p.b_right - p.b_left) + 8)
             t.skl_cap = cap if kind == capi.FORWARD_WIP else 0
+            t.n_imd = int(p.n_imd) if kind == capi.HIRSCHBERG_WIP else 0
         return arr, keep
 
     def _check(self, rc, what):
@@ -136,16 +140,18 @@ class Engine:
         for i in range(n):
             cap = arr[i].skl_cap
             buf = np.zeros((max(cap, 1), 2), np.int32)
-            bufs.append(buf)
+            cp = np.zeros((arr[i].n_imd + 1, 10), np.int32) if arr[i].kind == capi.HIRSCHBERG_WIP else None
+            bufs.append((buf, cp))
             res[i].skl = buf.ctypes.data if cap > 0 else None
+            res[i].cpos = cp.ctypes.data if cp is not None else None
         return res, bufs
 
     def _collect(self, n, res, bufs, arr):
         out = []
         for i in range(n):
             k = min(res[i].n_skl, arr[i].skl_cap)
-            out.append(Result(int(res[i].score), int(res[i].status), bufs[i][:max(k, 0)].copy(),
-                              int(res[i].cells)))
+            out.append(Result(int(res[i].score), int(res[i].status), bufs[i][0][:max(k, 0)].copy(),
+                              int(res[i].cells), tuple(int(x) for x in res[i].ranges), bufs[i][1]))
         return out
 
     # ---- one-shot (host buffers in, host results out) -------------------
@@ -162,6 +168,10 @@ class Engine:
 
     def scoreonlyS1_wip(self, problems):
         return self.submit(problems, capi.SCOREONLY_WIP)
+
+    def hirschbergS1_wip(self, problems):
+        """problems carry n_imd; results carry score, ranges and cpos (Dim10 records)"""
+        return self.submit(problems, capi.HIRSCHBERG_WIP)
 
     # ---- split form (batch resident in HBM) -----------------------------
     def upload(self, problems, kind=capi.FORWARD_WIP):

@@ -36,8 +36,8 @@ def test_struct_layouts_match_header():
     from spaln_b200 import capi
     # sizes implied by include/gspaln.h on LP64
     assert ctypes.sizeof(capi.GspalnParams) == 4 * (8 + 8 + 8 + 5) + 4 * 32 * 32
-    assert ctypes.sizeof(capi.GspalnTask) == 8 + 4 * 8 + 4 * 11 + 4
-    assert ctypes.sizeof(capi.GspalnResult) == 32
+    assert ctypes.sizeof(capi.GspalnTask) == 8 + 4 * 8 + 4 * 12
+    assert ctypes.sizeof(capi.GspalnResult) == 32 + 16 + 8
 
 
 def test_no_cpu_fallback_without_device():

@@ -138,3 +138,60 @@ def test_empty_batch_and_overflow():
     assert r.status == 1 and r.score == probs[0]["score"]
     assert np.array_equal(r.skl, probs[0]["skl"][:2])
     eng.close()
+
+
+# ---------------------------------------------------------------------------
+# unidirectional Hirschberg pass (hirschbergS1_wip)
+# ---------------------------------------------------------------------------
+def _cpos_equal(a, b):
+    from spaln_b200.capi import END_OF_ULK as EOU
+    for ra, rb in zip(a.tolist(), b.tolist()):
+        if ra[0] == EOU and rb[0] == EOU and ra[2] == rb[2]:
+            continue
+        ka = ra.index(EOU) if EOU in ra else 10
+        kb = rb.index(EOU) if EOU in rb else 10
+        if ra[:ka] != rb[:kb]:
+            return False
+    return True
+
+
+@pytest.mark.parametrize("name", ["dna_A2_udh", "dna_A6_udh_recursive"])
+def test_hirschberg_wip_matches_reference_golden(name):
+    prm, probs = golden_io.load(name)
+    sel = [pb for pb in probs if "udh_nim" in pb
+           and pb["udh_ranges"][0] <= pb["udh_ranges"][1] and pb["udh_ranges"][2] <= pb["udh_ranges"][3]]
+    assert len(sel) >= 20
+    P = _problems(sel)
+    for p, pb in zip(P, sel):
+        p.n_imd = pb["udh_nim"]
+    eng = _engine(prm)
+    res = eng.hirschbergS1_wip(P)
+    for i, (pb, r) in enumerate(zip(sel, res)):
+        assert r.status == 0
+        assert r.score == pb["udh_score"], (name, i, pb["tag"], r.score, pb["udh_score"])
+        assert list(r.ranges) == pb["udh_ranges"].tolist(), (name, i, pb["tag"])
+        assert _cpos_equal(r.cpos, pb["udh_cpos"]), (name, i, pb["tag"])
+    eng.close()
+
+
+@pytest.mark.parametrize("flags", [None, (0, 0, 0, 0), (1, 0, 0, 1)])
+def test_hirschberg_wip_matches_oracle_seeded(oracle, flags):
+    prm, _ = golden_io.load("dna_A2_global")
+    rng = np.random.default_rng(4242 + (sum(flags) if flags else 9))
+    probs = _synthetic(prm, rng, 20, (60, 900), (40, 500), flags=flags)
+    probs += _synthetic(prm, rng, 3, (1500, 2400), (100, 400), flags=flags)     # re-basing
+    nims = []
+    for pb in probs:
+        m = pb["a_right"] - pb["a_left"]
+        nims.append(int(rng.integers(1, max(2, min(9, m // 16)))))
+    P = _problems(probs)
+    for p, k in zip(P, nims):
+        p.n_imd = k
+    eng = _engine(prm)
+    res = eng.hirschbergS1_wip(P)
+    for i, (pb, r, k) in enumerate(zip(probs, res, nims)):
+        o = oracle.hirschberg_wip(prm, pb, k)
+        assert r.score == o["score"], (i, k, r.score, o["score"])
+        assert list(r.ranges) == o["ranges"], (i, k)
+        assert _cpos_equal(r.cpos, o["cpos"]), (i, k)
+    eng.close()

@@ -49,7 +49,11 @@ def test_oracle_udh_matches_reference_golden(oracle, name):
     prm, probs = golden_io.load(name)
     n_udh = n_lsp = 0
     for i, pb in enumerate(probs):
-        if "udh_nim" in pb:
+        rg = pb.get("udh_ranges")
+        # Degenerate outputs (alignment "ending" left of its start) come from link lanes the
+        # reference never initialises before the first strip (hc_a: src/fwd2s1_simd.h:253-255,
+        # only hb_a is cleared at src/fwd2s1_wip_simd.h:524); they are not reproducible.
+        if "udh_nim" in pb and rg[0] <= rg[1] and rg[2] <= rg[3]:
             o = oracle.hirschberg_wip(prm, pb, pb["udh_nim"])
             assert o["score"] == pb["udh_score"], (name, i, pb["tag"])
             assert o["ranges"] == pb["udh_ranges"].tolist(), (name, i, pb["tag"])
