@@ -145,6 +145,25 @@ int  gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n);
 int  gspaln_run(gspaln_ctx* ctx);
 int  gspaln_download(gspaln_ctx* ctx, gspaln_result* results);
 
+/* The DP driver: Aln2s1::lspS_ng (src/fwd2s1.cc:1801-1897) over a batch.  Each task is one
+ * lspS_ng call (task.kind is ignored).  The driver decides per problem between trace-back
+ * (trcbkalignS_ng, src/fwd2s1.cc:1667-1710) and the multi-intermediate unidirectional
+ * Hirschberg method with the reference's own space estimate, runs the Hirschberg passes and
+ * the block re-alignments of mimd_postwork / rcsv_postwork (src/fwd2s1.cc:1714-1799) as
+ * further device batches, and returns the corner list in the order the reference writes
+ * it to its Mfile.  Pieces that need a kernel which is not on the device yet (fewer than 8
+ * query rows -> the reference's scalar kernel; local-mode Hirschberg) set
+ * GSPALN_ST_UNSUPPORTED on that problem. */
+typedef struct gspaln_lsp_opts {
+    int32_t max_vmf_space;      /* MaxVmfSpace (-V; default 32 MiB, src/vmf.h:26) */
+    int32_t sh;                 /* alprm.sh: band shoulder for the block re-alignments */
+    int32_t ubh;                /* alprm.ubh: forced number of intermediates (0 = automatic) */
+    int32_t alg;                /* algmode.alg (bit 2: recursive single-intermediate method) */
+} gspaln_lsp_opts;
+
+int  gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n, const gspaln_lsp_opts* opts,
+                gspaln_result* results);
+
 int  gspaln_get_timing(const gspaln_ctx* ctx, gspaln_timing* out);
 const char* gspaln_last_error(const gspaln_ctx* ctx);
 int  gspaln_device_count(void);

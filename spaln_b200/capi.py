@@ -27,7 +27,7 @@ END_OF_ULK = 2 ** 31 - 1 - 2
 EXPORTS = [
     "gspaln_create", "gspaln_destroy", "gspaln_submit", "gspaln_upload", "gspaln_run",
     "gspaln_download", "gspaln_get_timing", "gspaln_last_error", "gspaln_device_count",
-    "gspaln_version", "gspaln_task_cells",
+    "gspaln_version", "gspaln_task_cells", "gspaln_lsp",
 ]
 
 
@@ -60,6 +60,10 @@ class GspalnResult(C.Structure):
     ]
 
 
+class GspalnLspOpts(C.Structure):
+    _fields_ = [("max_vmf_space", C.c_int32), ("sh", C.c_int32), ("ubh", C.c_int32), ("alg", C.c_int32)]
+
+
 class GspalnTiming(C.Structure):
     _fields_ = [
         ("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float),
@@ -89,6 +93,8 @@ def load():
     lib.gspaln_upload.argtypes = [C.c_void_p, C.POINTER(GspalnTask), C.c_int]
     lib.gspaln_run.argtypes = [C.c_void_p]
     lib.gspaln_download.argtypes = [C.c_void_p, C.POINTER(GspalnResult)]
+    lib.gspaln_lsp.argtypes = [C.c_void_p, C.POINTER(GspalnTask), C.c_int, C.POINTER(GspalnLspOpts),
+                               C.POINTER(GspalnResult)]
     lib.gspaln_get_timing.argtypes = [C.c_void_p, C.POINTER(GspalnTiming)]
     lib.gspaln_last_error.argtypes = [C.c_void_p]
     lib.gspaln_last_error.restype = C.c_char_p

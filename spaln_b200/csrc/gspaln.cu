@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -515,3 +516,4 @@ int gspaln_get_timing(const gspaln_ctx* ctx, gspaln_timing* out)
 }
 
 }   // extern "C"
+#include "gspaln_lsp.inl"

@@ -1,0 +1,352 @@
+// gspaln_lsp.inl -- host driver: Aln2s1::lspS_ng over a batch (included by gspaln.cu).
+//
+// Reference: lspS_ng src/fwd2s1.cc:1801-1897, trcbkalignS_ng 1667-1710 (SIMD branch),
+// mimd_postwork 1714-1756, rcsv_postwork 1758-1799, diagonalS_ng 1629-1665,
+// stripe src/aln2.cc:156-176.  The reference recurses problem by problem; here
+// every level of that recursion becomes one device batch (all Hirschberg passes
+// and all block re-alignments of a level run together).
+
+namespace {
+
+struct LspGeo {
+    int a_left, a_right, b_left, b_right;
+    int a_exgl, a_exgr, b_exgl, b_exgr;
+    int lw, up;
+};
+
+struct LspPiece {
+    int kind;                   // 0 literal corners, 1 forward-task result, 2 child item
+    int ref;
+    std::vector<int2> lit;
+};
+
+struct LspItem {
+    int root;                   // original problem
+    LspGeo g;
+    int score = 0;
+    bool recursive = false;
+    int n_imd = 0;
+    std::vector<LspPiece> pieces;
+};
+
+struct LspFwd {                 // one trcbkalignS_ng call
+    int root;
+    LspGeo g;
+    int score = 0;
+    std::vector<int2> skl;
+};
+
+void lsp_stripe(LspGeo& g, int sh)
+{
+    if (sh < 0) {
+        const int shorter = std::min(g.a_right - g.a_left, g.b_right - g.b_left);
+        sh = -sh * shorter / 100;
+    }
+    int up = g.b_right - g.a_right;
+    int lw = g.b_left - g.a_left;
+    if (up < lw) std::swap(up, lw);
+    up += sh; lw -= sh;
+    int q;
+    if ((q = g.b_right - g.a_left) < up) up = q;
+    if ((q = g.b_left - g.a_right) > lw) lw = q;
+    g.up = up; g.lw = lw;
+}
+
+gspaln_task lsp_task(const gspaln_task& base, const LspGeo& g, int kind, int n_imd)
+{
+    gspaln_task t = base;
+    t.kind = kind;
+    t.a_left = g.a_left; t.a_right = g.a_right; t.b_left = g.b_left; t.b_right = g.b_right;
+    t.a_exgl = g.a_exgl; t.a_exgr = g.a_exgr; t.b_exgl = g.b_exgl; t.b_exgr = g.b_exgr;
+    t.lw = g.lw; t.up = g.up;
+    t.n_imd = n_imd;
+    t.skl_cap = kind == GSPALN_FORWARD_WIP ? (g.a_right - g.a_left) + (g.b_right - g.b_left) + 8 : 0;
+    return t;
+}
+
+}   // namespace
+
+extern "C" int gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
+                          const gspaln_lsp_opts* opts, gspaln_result* results)
+{
+    if (!ctx || !opts || n < 0 || (n && (!tasks || !results))) return GSPALN_EINVAL;
+    const gspaln_params& P = ctx->prm;
+    const int NEVSEL = INT_MIN / 16 * 7;
+    const int EOU = INT_MAX - 2;
+    std::vector<LspItem> items;
+    std::vector<LspFwd> fwds;
+    std::vector<int> status(n, GSPALN_ST_OK);
+    std::vector<int> pending;
+    items.reserve(2 * (size_t) n);
+    for (int i = 0; i < n; ++i) {
+        const gspaln_task& t = tasks[i];
+        LspItem it;
+        it.root = i;
+        it.g = LspGeo{t.a_left, t.a_right, t.b_left, t.b_right, t.a_exgl, t.a_exgr, t.b_exgl, t.b_exgr, t.lw, t.up};
+        items.push_back(it);
+        pending.push_back(i);
+    }
+    auto lit2 = [](LspItem& it, int m0, int n0, int m1, int n1) {
+        LspPiece p; p.kind = 0; p.ref = -1;
+        p.lit.push_back(make_int2(m0, n0)); p.lit.push_back(make_int2(m1, n1));
+        it.pieces.push_back(std::move(p));
+    };
+    // returns the index of the queued forward task or -1 (nothing to do / unsupported)
+    auto queue_trcbk = [&](int item, const LspGeo& g) -> int {
+        if (g.up - g.lw + 3 < 0) return -1;
+        if (g.a_right - g.a_left < 8) { status[items[item].root] = GSPALN_ST_UNSUPPORTED; return -1; }
+        LspFwd f; f.root = items[item].root; f.g = g;
+        fwds.push_back(std::move(f));
+        LspPiece p; p.kind = 1; p.ref = (int) fwds.size() - 1;
+        items[item].pieces.push_back(std::move(p));
+        return p.ref;
+    };
+    size_t fwd_done = 0;
+    int64_t cells_total = 0;
+    float kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
+    int launches = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
+
+    while (!pending.empty()) {
+        // ---- classify (lspS_ng head) and build this level's batch
+        std::vector<int> udh_items;         // items waiting for a Hirschberg pass
+        std::vector<int> score_from_fwd;    // (item, fwd) pairs: item score = forward score
+        std::vector<std::pair<int, int>> item_fwd;
+        for (int id : pending) {
+            LspItem& it = items[id];
+            const LspGeo& g = it.g;
+            const gspaln_task& base = tasks[it.root];
+            const int m = g.a_right - g.a_left, nn = g.b_right - g.b_left;
+            if (!m && !nn) { it.score = 0; continue; }
+            if (!m || !nn) {
+                lit2(it, g.a_left, g.b_left, g.a_right, g.b_right);
+                if (m) it.score = (g.a_exgl || g.a_exgr) ? P.gep : (P.gop + m * P.gep);
+                else it.score = (g.b_exgl || g.b_exgr) ? P.gep : nn * P.gep;
+                continue;
+            }
+            if (g.up == g.lw) {
+                // diagonalS_ng (src/fwd2s1.cc:1629-1665)
+                const bool LocalL = P.local && g.a_exgl && g.b_exgl, LocalR = P.local && g.a_exgr && g.b_exgr;
+                const int dlt = P.local ? 0 : (nn - m);
+                const uint8_t* as = dlt < 0 ? base.b : base.a;
+                const uint8_t* bs = dlt < 0 ? base.a : base.b;
+                const int al = dlt < 0 ? g.b_left : g.a_left, ar = dlt < 0 ? g.b_right : g.a_right;
+                const int bl = dlt < 0 ? g.a_left : g.b_left;
+                int mL = al, mR = ar, scr = 0, maxh = NEVSEL;
+                for (int mm = al, k = 0; mm++ < ar; ++k) {
+                    const int x = as[al + k], y = bs[bl + k];
+                    scr += dlt < 0 ? P.simmtx[y * P.simdim + x] : P.simmtx[x * P.simdim + y];
+                    if (LocalL && scr < 0) { scr = 0; mL = mm; }
+                    if (LocalR && scr > maxh) { maxh = scr; mR = mm; }
+                }
+                int r = bl - al;
+                if (dlt < 0) r -= dlt;
+                lit2(it, mL, mL + r, mR, mR + r);
+                it.score = LocalR ? maxh : scr;
+                continue;
+            }
+            bool trcbk = std::abs(nn - m) < 8 || m == 1 || nn == 1;
+            int n_imd = 1;
+            bool recursive = (opts->alg & 4) != 0;
+            const float coef_B = 2.f, coef_C = (float) ((P.noll + 1) * 4);
+            const float cvol = (float) m * (nn + m);            // rhombic (simd >= 2)
+            if (!trcbk && coef_B * cvol < opts->max_vmf_space) trcbk = true;
+            if (!trcbk && !recursive) {
+                const double z = 2. * m * coef_B / coef_C;
+                const int imd1 = (int) (pow(z, 1. / 3) + 0.5) - 1;
+                const float spc = coef_C * nn * imd1 + coef_B * cvol / (imd1 + 1) / (imd1 + 1);
+                if (spc > opts->max_vmf_space) recursive = true;
+                else {
+                    const int imd3 = m / NELEM;
+                    n_imd = opts->ubh ? opts->ubh : std::min(imd1, imd3);
+                    const int imd_intvl = (m + n_imd) / (n_imd + 1);
+                    if (imd_intvl * n_imd == m) --n_imd;
+                    if (n_imd == 0) trcbk = true;
+                }
+            }
+            if (trcbk) {
+                const int f = queue_trcbk(id, g);
+                if (f >= 0) item_fwd.push_back({id, f}); else it.score = NEVSEL;
+                continue;
+            }
+            if (P.local && ((g.a_exgl && g.b_exgl) || (g.a_exgr && g.b_exgr))) {
+                status[it.root] = GSPALN_ST_UNSUPPORTED;        // local-mode Hirschberg pass
+                it.score = NEVSEL;
+                continue;
+            }
+            it.recursive = recursive;
+            it.n_imd = n_imd;
+            udh_items.push_back(id);
+        }
+        pending.clear();
+
+        // ---- one device batch: all Hirschberg passes + all queued trace-back problems
+        std::vector<gspaln_task> batch;
+        std::vector<gspaln_result> bres;
+        std::vector<std::vector<int>> cposbuf(udh_items.size());
+        for (size_t k = 0; k < udh_items.size(); ++k) {
+            const LspItem& it = items[udh_items[k]];
+            batch.push_back(lsp_task(tasks[it.root], it.g, GSPALN_HIRSCHBERG_WIP, it.n_imd));
+            cposbuf[k].assign(10 * (size_t) (it.n_imd + 1), 0);
+        }
+        const size_t fwd_first = fwd_done;
+        std::vector<std::vector<int>> sklbuf(fwds.size() - fwd_first);
+        for (size_t f = fwd_first; f < fwds.size(); ++f) {
+            batch.push_back(lsp_task(tasks[fwds[f].root], fwds[f].g, GSPALN_FORWARD_WIP, 0));
+            sklbuf[f - fwd_first].assign(2 * (size_t) batch.back().skl_cap, 0);
+        }
+        bres.resize(batch.size());
+        for (size_t k = 0; k < udh_items.size(); ++k) { bres[k].skl = nullptr; bres[k].cpos = cposbuf[k].data(); }
+        for (size_t f = fwd_first; f < fwds.size(); ++f) {
+            bres[udh_items.size() + (f - fwd_first)].skl = sklbuf[f - fwd_first].data();
+            bres[udh_items.size() + (f - fwd_first)].cpos = nullptr;
+        }
+        if (!batch.empty()) {
+            int rc = gspaln_submit(ctx, batch.data(), (int) batch.size(), bres.data());
+            if (rc != GSPALN_OK) return rc;
+            kernel_ms += ctx->tim.kernel_ms; h2d_ms += ctx->tim.h2d_ms; d2h_ms += ctx->tim.d2h_ms;
+            launches += ctx->tim.launches; h2d_bytes += ctx->tim.h2d_bytes; d2h_bytes += ctx->tim.d2h_bytes;
+            cells_total += ctx->tim.cells;
+        }
+        // forward results
+        for (size_t f = fwd_first; f < fwds.size(); ++f) {
+            const gspaln_result& r = bres[udh_items.size() + (f - fwd_first)];
+            fwds[f].score = r.score;
+            if (r.status != GSPALN_ST_OK) status[fwds[f].root] = r.status;
+            const int cnt = std::min(r.n_skl, batch[udh_items.size() + (f - fwd_first)].skl_cap);
+            const int* s = sklbuf[f - fwd_first].data();
+            fwds[f].skl.resize(std::max(cnt, 0));
+            for (int k = 0; k < cnt; ++k) fwds[f].skl[k] = make_int2(s[2 * k], s[2 * k + 1]);
+        }
+        fwd_done = fwds.size();
+        for (auto& pr : item_fwd) items[pr.first].score = fwds[pr.second].score;
+
+        // ---- post-work of the Hirschberg passes: next level
+        for (size_t k = 0; k < udh_items.size(); ++k) {
+            const int id = udh_items[k];
+            const gspaln_result& r = bres[k];
+            const int* cpos = cposbuf[k].data();
+            items[id].score = r.score;
+            if (!(r.score > NEVSEL)) continue;
+            LspGeo g = items[id].g;
+            g.a_left = r.ranges[0]; g.a_right = r.ranges[1]; g.b_left = r.ranges[2]; g.b_right = r.ranges[3];
+            const int n_imd = items[id].n_imd;
+            if (cpos[0] == EOU) {
+                lit2(items[id], g.a_left, g.b_left, g.a_right, g.b_right);
+            } else if (items[id].recursive) {
+                // rcsv_postwork
+                g.a_exgl = g.b_exgl = g.a_exgr = g.b_exgr = 0;
+                int c = 0;
+                if (cpos[c++] < EOU) {
+                    LspPiece p; p.kind = 0; p.ref = -1;
+                    while (cpos[++c] < EOU) p.lit.push_back(make_int2(cpos[0], cpos[c]));
+                    items[id].pieces.push_back(std::move(p));
+                    const int aright = g.a_right, bright = g.b_right;
+                    LspGeo g1 = g;
+                    g1.a_right = cpos[0]; g1.b_right = cpos[c - 1];
+                    lsp_stripe(g1, opts->sh);
+                    LspGeo g2 = g1;
+                    g2.a_left = cpos[0]; g2.b_exgl = cpos[1]; g2.b_left = cpos[2];
+                    g2.a_right = aright; g2.b_right = bright;
+                    lsp_stripe(g2, opts->sh);
+                    for (const LspGeo& gg : {g1, g2}) {
+                        LspItem child; child.root = items[id].root; child.g = gg;
+                        items.push_back(child);
+                        const int cid = (int) items.size() - 1;
+                        LspPiece cp; cp.kind = 2; cp.ref = cid;
+                        items[id].pieces.push_back(std::move(cp));
+                        pending.push_back(cid);
+                    }
+                } else if (P.local) {
+                    lsp_stripe(g, opts->sh);
+                    queue_trcbk(id, g);
+                }
+            } else {
+                // mimd_postwork
+                const int aleft = g.a_left, bleft = g.b_left;
+                g.a_exgl = g.b_exgl = g.a_exgr = g.b_exgr = 0;
+                int i = n_imd;
+                while (--i >= 0 && cpos[10 * i] == EOU) ;
+                for ( ; i >= 0 && cpos[10 * i] != EOU; --i) {
+                    int c = 0;
+                    g.a_left = cpos[10 * i + c];
+                    g.b_exgl = cpos[10 * i + (++c)];
+                    g.b_left = cpos[10 * i + (++c)];
+                    if (g.b_left < 0 || g.b_left > g.b_right) break;
+                    LspPiece p; p.kind = 0; p.ref = -1;
+                    while (cpos[10 * i + (++c)] < EOU) p.lit.push_back(make_int2(g.a_left, cpos[10 * i + c]));
+                    if (!p.lit.empty()) items[id].pieces.push_back(std::move(p));
+                    lsp_stripe(g, opts->sh);
+                    queue_trcbk(id, g);
+                    g.a_right = g.a_left;
+                    g.b_right = cpos[10 * i + c - 1];
+                }
+                if ((i < 0 && cpos[0] != EOU) || cpos[2] != EOU) {
+                    g.a_left = aleft;
+                    g.b_left = bleft;
+                    lsp_stripe(g, opts->sh);
+                    queue_trcbk(id, g);
+                }
+            }
+        }
+        // block re-alignments queued by the post-work run with the next level
+        if (pending.empty() && fwd_done < fwds.size()) pending.push_back(-1);
+        if (!pending.empty() && pending.back() == -1) {
+            pending.pop_back();
+            // a level with only forward tasks: loop once more with no items to classify
+            std::vector<gspaln_task> b2;
+            std::vector<gspaln_result> r2;
+            std::vector<std::vector<int>> s2(fwds.size() - fwd_done);
+            for (size_t f = fwd_done; f < fwds.size(); ++f) {
+                b2.push_back(lsp_task(tasks[fwds[f].root], fwds[f].g, GSPALN_FORWARD_WIP, 0));
+                s2[f - fwd_done].assign(2 * (size_t) b2.back().skl_cap, 0);
+            }
+            r2.resize(b2.size());
+            for (size_t f = 0; f < b2.size(); ++f) { r2[f].skl = s2[f].data(); r2[f].cpos = nullptr; }
+            int rc = gspaln_submit(ctx, b2.data(), (int) b2.size(), r2.data());
+            if (rc != GSPALN_OK) return rc;
+            kernel_ms += ctx->tim.kernel_ms; h2d_ms += ctx->tim.h2d_ms; d2h_ms += ctx->tim.d2h_ms;
+            launches += ctx->tim.launches; h2d_bytes += ctx->tim.h2d_bytes; d2h_bytes += ctx->tim.d2h_bytes;
+            cells_total += ctx->tim.cells;
+            for (size_t f = 0; f < b2.size(); ++f) {
+                LspFwd& F = fwds[fwd_done + f];
+                F.score = r2[f].score;
+                if (r2[f].status != GSPALN_ST_OK) status[F.root] = r2[f].status;
+                const int cnt = std::min(r2[f].n_skl, b2[f].skl_cap);
+                F.skl.resize(std::max(cnt, 0));
+                for (int k = 0; k < cnt; ++k) F.skl[k] = make_int2(s2[f][2 * k], s2[f][2 * k + 1]);
+            }
+            fwd_done = fwds.size();
+        }
+    }
+
+    // ---- assemble the corner lists in the reference's write order (depth first)
+    for (int i = 0; i < n; ++i) {
+        gspaln_result& o = results[i];
+        std::vector<int2> out;
+        std::vector<std::pair<int, size_t>> stack;      // (item, next piece)
+        stack.push_back({i, 0});
+        while (!stack.empty()) {
+            auto& top = stack.back();
+            const LspItem& it = items[top.first];
+            if (top.second >= it.pieces.size()) { stack.pop_back(); continue; }
+            const LspPiece& p = it.pieces[top.second++];
+            if (p.kind == 0) out.insert(out.end(), p.lit.begin(), p.lit.end());
+            else if (p.kind == 1) out.insert(out.end(), fwds[p.ref].skl.begin(), fwds[p.ref].skl.end());
+            else stack.push_back({p.ref, 0});
+        }
+        o.score = items[i].score;
+        o.status = status[i];
+        o.n_skl = (int) out.size();
+        o.reserved = 0;
+        o.cells = task_cells(tasks[i]);
+        const int cap = tasks[i].skl_cap;
+        if (o.status == GSPALN_ST_OK && o.n_skl > cap) o.status = GSPALN_ST_SKL_OVERFLOW;
+        if (o.skl)
+            for (int k = 0; k < std::min(o.n_skl, cap); ++k) { o.skl[2 * k] = out[k].x; o.skl[2 * k + 1] = out[k].y; }
+    }
+    ctx->tim.kernel_ms = kernel_ms; ctx->tim.h2d_ms = h2d_ms; ctx->tim.d2h_ms = d2h_ms;
+    ctx->tim.launches = launches; ctx->tim.h2d_bytes = h2d_bytes; ctx->tim.d2h_bytes = d2h_bytes;
+    ctx->tim.cells = cells_total;
+    return GSPALN_OK;
+}

@@ -173,6 +173,18 @@ class Engine:
         """problems carry n_imd; results carry score, ranges and cpos (Dim10 records)"""
         return self.submit(problems, capi.HIRSCHBERG_WIP)
 
+    def lspS_ng(self, problems, max_vmf_space=32 * 1024 * 1024, sh=100, ubh=0, alg=2):
+        """Aln2s1::lspS_ng over a batch (src/fwd2s1.cc:1801-1897): trace-back vs
+        multi-intermediate Hirschberg dispatch with the reference's space estimate, block
+        re-alignments included.  Returns score + corner list in Mfile order."""
+        arr, keep = self._pack(problems, capi.FORWARD_WIP)
+        n = len(problems)
+        res, bufs = self._results(n, arr)
+        o = capi.GspalnLspOpts(int(max_vmf_space), int(sh), int(ubh), int(alg))
+        self._check(self.lib.gspaln_lsp(self._h, arr, n, C.byref(o), res), "gspaln_lsp")
+        self._n = n
+        return self._collect(n, res, bufs, arr)
+
     # ---- split form (batch resident in HBM) -----------------------------
     def upload(self, problems, kind=capi.FORWARD_WIP):
         arr, keep = self._pack(problems, kind)

@@ -195,3 +195,53 @@ def test_hirschberg_wip_matches_oracle_seeded(oracle, flags):
         assert list(r.ranges) == o["ranges"], (i, k)
         assert _cpos_equal(r.cpos, o["cpos"]), (i, k)
     eng.close()
+
+
+# ---------------------------------------------------------------------------
+# the whole driver: lspS_ng (trace-back vs UDH dispatch + block re-alignment)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["dna_A2_udh", "dna_A6_udh_recursive", "dna_A2_global"])
+def test_lsp_driver_matches_reference_golden(oracle, name):
+    prm, probs = golden_io.load(name)
+    eng = _engine(prm)
+    res = eng.lspS_ng(_problems(probs), max_vmf_space=int(prm["MaxVmfSpace"]), sh=int(prm["sh"]),
+                      ubh=int(prm["ubh"]), alg=int(prm["alg"]))
+    n_ok = 0
+    for i, (pb, r) in enumerate(zip(probs, res)):
+        if r.status == 3:           # a block with < 8 query rows (scalar kernel of the reference)
+            assert oracle.lsp(prm, pb)["unsupported"]
+            continue
+        assert r.status == 0, (name, i, pb["tag"])
+        want_score = pb.get("lsp_score", pb["score"])
+        want_skl = pb.get("lsp_skl", pb["skl"])
+        if "lsp_score" not in pb and (pb["a_right"] - pb["a_left"]) < 8:
+            continue
+        assert r.score == want_score, (name, i, pb["tag"], r.score, want_score)
+        assert np.array_equal(r.skl, want_skl), (name, i, pb["tag"])
+        n_ok += 1
+    assert n_ok >= 20
+    eng.close()
+
+
+def test_lsp_driver_matches_oracle_seeded(oracle):
+    """default -V (32 MiB): config-2 sized problems mix trace-back and UDH dispatch"""
+    prm, _ = golden_io.load("dna_A2_global")
+    rng = np.random.default_rng(31337)
+    probs = _synthetic(prm, rng, 10, (1000, 3000), (500, 4000))
+    probs += _synthetic(prm, rng, 10, (100, 900), (100, 900))
+    eng = _engine(prm)
+    for vmf in (int(prm["MaxVmfSpace"]), 1 << 20):
+        res = eng.lspS_ng(_problems(probs), max_vmf_space=vmf, sh=int(prm["sh"]), alg=2)
+        n_udh = 0
+        for i, (pb, r) in enumerate(zip(probs, res)):
+            o = oracle.lsp(prm, pb, cap=1 << 16, max_vmf_space=vmf)
+            if o["unsupported"]:
+                assert r.status == 3
+                continue
+            m, n = pb["a_right"] - pb["a_left"], pb["b_right"] - pb["b_left"]
+            n_udh += 2.0 * m * (n + m) >= vmf
+            assert r.status == 0
+            assert r.score == o["score"], (vmf, i, r.score, o["score"])
+            assert np.array_equal(r.skl, o["skl"]), (vmf, i)
+        assert n_udh >= 5
+    eng.close()
