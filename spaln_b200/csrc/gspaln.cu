@@ -17,6 +17,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace gspaln;
@@ -368,23 +369,48 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         ctx->grid_run_trace = gt;
         ctx->grid_run_score = gs;
     }
-    // ---- pack (host work is part of the end-to-end path)
-    for (int i = 0; i < n; ++i) {
-        const gspaln_task& t = tasks[i];
-        const DevTask& d = dt[i];
-        const int mw = t.a_right - t.a_left, nw = t.b_right - t.b_left;
-        for (int j = 0; j < mw; ++j) ctx->h_apool.p[d.a_off + j] = ctx->perm[t.a[t.a_left + j] & 31];
-        ColInfo* col = ctx->h_cpool.p + d.col_off;
-        for (int j = 0; j <= nw; ++j) {
-            const int c = t.b_left + j;             // column c pairs genome residue at(c - 1)
-            ColInfo ci;
-            ci.sig5 = ctx->prm.spj ? t.sig5[c] : 0;
-            ci.sig3 = ctx->prm.spj ? t.sig3[c] : 0;
-            ci.code = j > 0 ? ctx->perm[t.b[c - 1] & 31] : 0;
-            ci.pad[0] = ci.pad[1] = ci.pad[2] = 0;
-            col[j] = ci;
+    // ---- pack (host work is part of the end-to-end path): problems are dealt to a
+    // few host threads; every problem writes a disjoint slice of the pinned pools
+    {
+        auto pack_range = [&](int lo, int hi) {
+            for (int i = lo; i < hi; ++i) {
+                const gspaln_task& t = tasks[i];
+                const DevTask& d = dt[i];
+                const int mw = t.a_right - t.a_left, nw = t.b_right - t.b_left;
+                unsigned char* ap = ctx->h_apool.p + d.a_off;
+                for (int j = 0; j < mw; ++j) ap[j] = ctx->perm[t.a[t.a_left + j] & 31];
+                ColInfo* col = ctx->h_cpool.p + d.col_off;
+                const bool spj = ctx->prm.spj != 0;
+                for (int j = 0; j <= nw; ++j) {
+                    const int c = t.b_left + j;     // column c pairs genome residue at(c - 1)
+                    ColInfo ci;
+                    ci.sig5 = spj ? t.sig5[c] : 0;
+                    ci.sig3 = spj ? t.sig3[c] : 0;
+                    ci.code = j > 0 ? ctx->perm[t.b[c - 1] & 31] : 0;
+                    ci.pad[0] = ci.pad[1] = ci.pad[2] = 0;
+                    col[j] = ci;
+                }
+                ctx->h_tasks.p[i] = d;
+            }
+        };
+        const size_t work = c_elems + a_bytes;
+        int nthr = (int) std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+        if (work < (1u << 20) || n < 2 * nthr) nthr = 1;
+        if (nthr == 1) pack_range(0, n);
+        else {
+            // contiguous ranges balanced by column count
+            std::vector<std::thread> pool;
+            size_t acc = 0, per = (work + nthr - 1) / nthr;
+            int lo = 0;
+            for (int i = 0; i < n; ++i) {
+                acc += (size_t) (tasks[i].b_right - tasks[i].b_left) + (tasks[i].a_right - tasks[i].a_left);
+                if (acc >= per || i == n - 1) {
+                    pool.emplace_back(pack_range, lo, i + 1);
+                    lo = i + 1; acc = 0;
+                }
+            }
+            for (auto& th : pool) th.join();
         }
-        ctx->h_tasks.p[i] = d;
     }
     // largest problems first (longest-processing-time order for the ticket queue)
     std::iota(ctx->h_order.p, ctx->h_order.p + n, 0);

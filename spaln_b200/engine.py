@@ -77,6 +77,37 @@ class EngineError(RuntimeError):
     pass
 
 
+_RESULT_DTYPE = np.dtype([("score", "<i4"), ("status", "<i4"), ("n_skl", "<i4"), ("reserved", "<i4"),
+                          ("cells", "<i8"), ("skl", "<u8"), ("ranges", "<i4", (4,)), ("cpos", "<u8")])
+assert _RESULT_DTYPE.itemsize == C.sizeof(capi.GspalnResult)
+
+
+class PackedBatch:
+    """Task descriptors marshalled once (the sequence / signal buffers stay host numpy
+    arrays and are packed + copied to the device by every submit) plus a flat result area."""
+
+    def __init__(self, arr, keep, n):
+        self.arr, self.keep, self.n = arr, keep, n
+        caps = np.array([arr[i].skl_cap for i in range(n)], np.int64)
+        self.off = np.concatenate([[0], np.cumsum(caps)])
+        self.skl = np.zeros((max(int(self.off[-1]), 1), 2), np.int32)
+        self.res = np.zeros(max(n, 1), _RESULT_DTYPE)
+        self.res["skl"][:n] = self.skl.ctypes.data + 8 * self.off[:-1].astype(np.uint64)
+        self.res["skl"][:n][caps == 0] = 0
+
+    @property
+    def scores(self):
+        return self.res["score"][:self.n]
+
+    @property
+    def status(self):
+        return self.res["status"][:self.n]
+
+    def corners(self, i):
+        k = min(int(self.res["n_skl"][i]), int(self.off[i + 1] - self.off[i]))
+        return self.skl[self.off[i]:self.off[i] + k]
+
+
 class Engine:
     """One engine per (parameter set, device); not thread-safe."""
 
@@ -162,6 +193,16 @@ class Engine:
         self._check(self.lib.gspaln_submit(self._h, arr, n, res), "gspaln_submit")
         self._n = n
         return self._collect(n, res, bufs, arr)
+
+    def pack(self, problems, kind=capi.FORWARD_WIP) -> PackedBatch:
+        arr, keep = self._pack(problems, kind)
+        return PackedBatch(arr, keep, len(problems))
+
+    def submit_packed(self, batch: PackedBatch) -> PackedBatch:
+        """host buffers in, host results out (scores / status / corners in `batch`)"""
+        res = batch.res.ctypes.data_as(C.POINTER(capi.GspalnResult))
+        self._check(self.lib.gspaln_submit(self._h, batch.arr, batch.n, res), "gspaln_submit")
+        return batch
 
     def forwardS1_wip(self, problems):
         return self.submit(problems, capi.FORWARD_WIP)

@@ -245,3 +245,15 @@ def test_lsp_driver_matches_oracle_seeded(oracle):
             assert np.array_equal(r.skl, o["skl"]), (vmf, i)
         assert n_udh >= 5
     eng.close()
+
+
+def test_packed_batch_api_equals_object_api():
+    prm, probs = golden_io.load("dna_A2_global")
+    eng = _engine(prm)
+    P = _problems(probs)
+    want = eng.forwardS1_wip(P)
+    b = eng.submit_packed(eng.pack(P))
+    for i, w in enumerate(want):
+        assert b.scores[i] == w.score and b.status[i] == w.status
+        assert np.array_equal(b.corners(i), w.skl)
+    eng.close()
