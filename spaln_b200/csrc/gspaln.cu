@@ -139,6 +139,22 @@ const void* kernel_ptr(bool trace, bool local, bool spj)
     return reinterpret_cast<const void*>(kernel_fn(trace, local, spj));
 }
 
+using UdhKernelFn = void (*)(const DevParams*, const int2*, const DevTask*, const int*, int, int*,
+                             const unsigned char*, const ColInfo*, unsigned*, long long, int*,
+                             long long, int*, DevUdhOut*);
+
+UdhKernelFn udh_kernel_fn(bool spj, bool local)
+{
+    static const UdhKernelFn tab[4] = {dp_udh_kernel<false, false>, dp_udh_kernel<true, false>,
+                                       dp_udh_kernel<false, true>, dp_udh_kernel<true, true>};
+    return tab[(local ? 2 : 0) | (spj ? 1 : 0)];
+}
+
+const void* udh_kernel_ptr(bool spj, bool local)
+{
+    return reinterpret_cast<const void*>(udh_kernel_fn(spj, local));
+}
+
 int64_t task_cells(const gspaln_task& t)
 {
     // rows m in (a_left, a_right], columns max(m + lw, b_left) < n <= min(m + up + 1, b_right)
@@ -255,7 +271,7 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ks, CTA_THREADS, ctx->smem_bytes);
     ctx->grid_score = std::max(1, occ) * ctx->sm_count;
     {
-        const void* ku = P.spj ? (const void*) dp_udh_kernel<true> : (const void*) dp_udh_kernel<false>;
+        const void* ku = udh_kernel_ptr(P.spj, P.local);
         cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_bytes);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ku, CTA_THREADS, ctx->smem_bytes);
         ctx->grid_udh = std::max(1, occ) * ctx->sm_count;
@@ -322,7 +338,7 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             d.pad0 = t.n_imd;
             d.pad1 = (long long) cpos_elems;
             cpos_elems += (size_t) 10 * (t.n_imd + 1);
-            udh_slab = std::max(udh_slab, align_up(2 * ((size_t) width + 2 * NELEM + 2) +
+            udh_slab = std::max(udh_slab, align_up(4 * ((size_t) width + 2 * NELEM + 2) +
                                                    (size_t) t.n_imd * 4 * width + 8, 64));
             ++n_udh;
         } else
@@ -468,7 +484,7 @@ int gspaln_run(gspaln_ctx* ctx)
         }
         if (ctx->n_udh) {
             CK(cudaMemsetAsync(ctx->d_ticket.p + 2, 0, sizeof(int), ctx->stream));
-            auto ku = spj ? dp_udh_kernel<true> : dp_udh_kernel<false>;
+            auto ku = udh_kernel_fn(spj, local);
             ku<<<ctx->grid_run_udh, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
                 ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p + 2,
                 ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,

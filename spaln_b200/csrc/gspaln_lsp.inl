@@ -169,11 +169,6 @@ extern "C" int gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
                 if (f >= 0) item_fwd.push_back({id, f}); else it.score = NEVSEL;
                 continue;
             }
-            if (P.local && ((g.a_exgl && g.b_exgl) || (g.a_exgr && g.b_exgr))) {
-                status[it.root] = GSPALN_ST_UNSUPPORTED;        // local-mode Hirschberg pass
-                it.score = NEVSEL;
-                continue;
-            }
             it.recursive = recursive;
             it.n_imd = n_imd;
             udh_items.push_back(id);

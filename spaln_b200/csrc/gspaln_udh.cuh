@@ -2,8 +2,8 @@
 //
 // Semantics: SimdAln2s1::hirschbergS1_wip of the reference
 // (src/fwd2s1_wip_simd.h:476-864; link initialisation src/fwd2s1_simd.cc:205-238;
-// intermediates src/udh_intermediate.h:29-88) for single affine gaps in the
-// global / semi-global modes.  No trace matrix is written: every cell carries a
+// intermediates src/udh_intermediate.h:29-88) for single affine gaps, global,
+// semi-global and local (-LS: left-end lanes `hb`, running maximum) modes.  No trace matrix is written: every cell carries a
 // link (the diagonal on which its path crossed the previous intermediate row,
 // or started) next to H, F, E and the best-donor value.  At the n_imd
 // intermediate rows the links are recorded into per-problem arrays and reset;
@@ -29,11 +29,27 @@ constexpr int NEVSEL32 = INT_MIN / 16 * 7;  // NEVSEL, src/cmn.h:79
 // per-row event bits handed from the cell loop to the intermediate-row logic
 enum : unsigned { EV_HORI = 1, EV_VERT = 2, EV_ACC = 4, EV_DON = 8 };
 
-template <bool SPJ>
+// left-end rows of local alignments (`hb` lanes of the reference), LOCAL only
+struct LocalLanes {
+    int BA[NRU], BB[NRU], FB[NRU], EB[NRU], B2[NRU];
+};
+
+struct LocalStep {              // per-step inputs / outputs of the local-mode extras
+    int up_b, up_fb, up_db;     // hb of the row above: H (prev step), F, H (two steps ago)
+    bool localL_now;            // LocalL && !accscr
+    bool track;                 // LocalR
+    int row_first;              // absolute query row of this thread's row 0 (m coordinate)
+    int diag0;                  // diagonal of this thread's row 0 at this step
+    int j9_left;                // number of real rows of the strip still below row0 (j9 - row0)
+    int bv, bk, bml, bulk;      // best cell of the step: value, row, left end, link
+};
+
+template <bool SPJ, bool LOCAL>
 __device__ __forceinline__ void strip_step_udh(
     int (&HO)[NRU], const int (&HN)[NRU], int (&F)[NRU], int (&E)[NRU],
     int (&V2)[NRU], int (&NJ)[NRU],
     int (&CO)[NRU], const int (&CN)[NRU], int (&FC)[NRU], int (&EC)[NRU], int (&C2)[NRU],
+    int (&BO)[NRU], const int (&BN)[NRU], LocalLanes& LL, LocalStep& ls,
     const int (&arow)[NRU],
     const char* __restrict__ ring_hi, const char* __restrict__ mtx_bytes,
     const int2* __restrict__ pen_tab, int pen_cap, int step,
@@ -41,6 +57,7 @@ __device__ __forceinline__ void strip_step_udh(
     int gn, int ge, unsigned& events)
 {
     events = 0u;
+    if (LOCAL) { ls.bv = INT_MIN; ls.bk = 0; ls.bml = 0; ls.bulk = 0; }
 #pragma unroll
     for (int k = NRU - 1; k >= 0; --k) {
         const RingEntry re = *reinterpret_cast<const RingEntry*>(
@@ -53,31 +70,51 @@ __device__ __forceinline__ void strip_step_udh(
         const int ufc = k ? FC[k ? k - 1 : 0] : up_fc;
         const int dc = k ? CO[k ? k - 1 : 0] : up_dc;
         unsigned ev = 0;
+        int lb = 0, ub = 0, ufb = 0, db = 0;
+        if (LOCAL) {
+            lb = BN[k];
+            ub = k ? BN[k ? k - 1 : 0] : ls.up_b;
+            ufb = k ? LL.FB[k ? k - 1 : 0] : ls.up_fb;
+            db = k ? BO[k ? k - 1 : 0] : ls.up_db;
+        }
         // horizontal
         int x = satlo(left + gn);
         int e = satlo(E[k] + ge);
-        if (!(e > x)) { e = x; EC[k] = lc; }
+        if (!(e > x)) { e = x; EC[k] = lc; if (LOCAL) LL.EB[k] = lb; }
         E[k] = e;
         // vertical
         int f = satlo(uf + ge);
         x = satlo(uh + gn);
-        int fcl = ufc;
-        if (!(f > x)) { f = x; fcl = uc; }
+        int fcl = ufc, fbl = ufb;
+        if (!(f > x)) { f = x; fcl = uc; fbl = ub; }
         F[k] = f; FC[k] = fcl;
+        if (LOCAL) LL.FB[k] = fbl;
         // diagonal, best of three
         const int pv = *reinterpret_cast<const int*>(mtx_bytes + re.prof + arow[k]);
         int h = sat16(pv + dg);
-        int hc = dc;
-        if (f > h) { h = f; hc = fcl; ev = EV_VERT; }
-        if (e > h) { h = e; hc = EC[k]; ev = EV_HORI; }
+        int hc = dc, hbv = db;
+        if (f > h) { h = f; hc = fcl; hbv = fbl; ev = EV_VERT; }
+        if (e > h) { h = e; hc = EC[k]; if (LOCAL) hbv = LL.EB[k]; ev = EV_HORI; }
         if (SPJ) {
             const int q0 = sat16(V2[k] + re.s3);
             const int2 pq = pen_tab[min(step + NJ[k], pen_cap)];
             const int q = min(max(q0 + pq.x, pq.y), 32767);
-            if (q > h) { h = q; hc = C2[k]; ev |= EV_ACC; }
-            // donor (no empty-intron guard in the Hirschberg pass)
+            if (q > h) { h = q; hc = C2[k]; if (LOCAL) hbv = LL.B2[k]; ev |= EV_ACC; }
+        }
+        if (LOCAL && ls.localL_now && h < 0) h = 0;
+        if (SPJ) {
+            // donor (no empty-intron guard in the Hirschberg pass); links as of before the
+            // local restart patch below
             const int qd = sat16(h + re.s5);
-            if (qd > V2[k]) { V2[k] = qd; C2[k] = hc; NJ[k] = -step; ev |= EV_DON; }
+            if (qd > V2[k]) { V2[k] = qd; C2[k] = hc; if (LOCAL) LL.B2[k] = hbv; NJ[k] = -step; ev |= EV_DON; }
+        }
+        if (LOCAL) {
+            // a cell of score 0 inside the matrix starts a new local alignment
+            // (src/fwd2s1_wip_simd.h:719-727)
+            const bool inside = re.pad != 0 && k < ls.j9_left;
+            if (ls.localL_now && inside && h == 0) { hbv = (short) (ls.row_first + k); hc = ls.diag0 - 2 * k; }
+            if (ls.track && k < ls.j9_left && h >= ls.bv) { ls.bv = h; ls.bk = k; ls.bml = hbv; ls.bulk = hc; }
+            BO[k] = hbv;
         }
         HO[k] = h;
         CO[k] = hc;
@@ -85,18 +122,22 @@ __device__ __forceinline__ void strip_step_udh(
     }
 }
 
+struct UdhBest { int val, ml, ulk, mr, nr; };     // Rvulmn of the reference (src/fwd2s1_simd.h:49-55)
+
 struct UdhTaskView {
     int* bandc;         // {H link, F link} per diagonal (int2), buf_size entries
+    int* bandb;         // {H left end, F left end} per diagonal (int2), LOCAL only
     int* imd;           // n_imd x 4 x width: hlnk0, hlnk1, vlnk0, vlnk1
     int n_imd, n_active, mm0;
 };
 
-template <bool SPJ>
+template <bool SPJ, bool LOCAL>
 __device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
                              const DevTask& t, const UdhTaskView& uv,
                              const unsigned char* __restrict__ aseq,
                              const ColInfo* __restrict__ cols, unsigned* band,
-                             int ml0, int nstr, int& rlst_io)
+                             int ml0, int nstr, int& rlst_io,
+                             bool localL, bool localL_now, bool localR, int accscr, UdhBest& wbest)
 {
     const int lane = threadIdx.x & 31;
     const int sidx = lane / TPSU;
@@ -140,10 +181,19 @@ __device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
 
     int HA[NRU], HB[NRU], F[NRU], E[NRU], V2[NRU], NJ[NRU], arow[NRU];
     int CA[NRU], CB[NRU], FC[NRU], EC[NRU], C2[NRU];
+    LocalLanes LL;
+    LocalStep ls;
+    ls.localL_now = localL_now; ls.track = localR;
+    ls.row_first = g.ml + row0 + 1;
+    ls.j9_left = g.j9 - row0;
+    ls.up_b = ls.up_fb = ls.up_db = 0; ls.diag0 = 0;
+    int prev_ub = 0;
+    int bval = INT_MIN, bstep = 0, bk = 0, bml = 0, bulk = 0;
 #pragma unroll
     for (int k = 0; k < NRU; ++k) {
         HA[k] = NEV; HB[k] = NEV; F[k] = NEV; E[k] = NEV; V2[k] = NEV; NJ[k] = 0;
         CA[k] = 0; CB[k] = 0; FC[k] = 0; EC[k] = 0; C2[k] = 0;
+        LL.BA[k] = 0; LL.BB[k] = 0; LL.FB[k] = 0; LL.EB[k] = 0; LL.B2[k] = 0;
         arow[k] = (live && row0 + k < g.j9) ? 4 * (int) aseq[(g.ml - t.a_left) + row0 + k] : 4 * ZROW;
     }
     const int gn = P.gn, ge = P.ge;
@@ -155,6 +205,7 @@ __device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
     const bool owns_bottom = live && j8 >= row0 && j8 < row0 + NRU;
     const int kbot = j8 - row0;
     const int2* bandc = reinterpret_cast<const int2*>(uv.bandc);
+    const int2* bandb = reinterpret_cast<const int2*>(uv.bandb);
 
     auto col_fetch = [&](int c) -> uint2 {
         if (c >= t.b_left && c <= t.b_right)
@@ -167,7 +218,7 @@ __device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
         re.prof = ZROW * (MTX_LD * 4);
         re.s3 = 0; re.s5 = 0;
         if (ci.y != 0xffffffffu) {
-            if (c > t.b_left) re.prof = (int) (ci.y & 0xffu) * (MTX_LD * 4);
+            if (c > t.b_left) { re.prof = (int) (ci.y & 0xffu) * (MTX_LD * 4); re.pad = 1; }
             if (SPJ && with_sig) {
                 re.s3 = hi16(ci.x);
                 re.s5 = (int) (short) (lo16(ci.x) + ipen);
@@ -177,7 +228,7 @@ __device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
     };
 
     unsigned nxt_band = 0;
-    int2 nxt_bandc = make_int2(0, 0);
+    int2 nxt_bandc = make_int2(0, 0), nxt_bandb = make_int2(0, 0);
     uint2 nxt_col = make_uint2(0u, 0xffffffffu);
 
     for (int i = -1; i < niter; ++i) {
@@ -186,12 +237,21 @@ __device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
         const int sh_f = __shfl_up_sync(0xffffffffu, F[NRU - 1], 1);
         const int sh_c = __shfl_up_sync(0xffffffffu, (i & 1) ? CA[NRU - 1] : CB[NRU - 1], 1);
         const int sh_fc = __shfl_up_sync(0xffffffffu, FC[NRU - 1], 1);
+        int sh_b = 0, sh_fb = 0;
+        if (LOCAL) {
+            sh_b = __shfl_up_sync(0xffffffffu, (i & 1) ? LL.BA[NRU - 1] : LL.BB[NRU - 1], 1);
+            sh_fb = __shfl_up_sync(0xffffffffu, LL.FB[NRU - 1], 1);
+        }
         if (live && j == -1) {
             if (sub == 0) {
                 nxt_band = __ldcg(band + (g.n_start - band_bias));
                 nxt_bandc = __ldcg(bandc + (g.n_start - band_bias));
                 prev_uh = lo16(__ldcg(band + (g.n_start - 1 - band_bias)));
                 prev_uc = __ldcg(bandc + (g.n_start - 1 - band_bias)).x;
+                if (LOCAL && localL) {
+                    nxt_bandb = __ldcg(bandb + (g.n_start - band_bias));
+                    prev_ub = __ldcg(bandb + (g.n_start - 1 - band_bias)).x;
+                }
             }
             nxt_col = col_fetch(g.n_start);
 #pragma unroll 1
@@ -204,12 +264,13 @@ __device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
         } else if (live && j >= 0 && j < nsteps) {
             const int n = g.n_start + j;
             const unsigned cur_band = nxt_band;
-            const int2 cur_bandc = nxt_bandc;
+            const int2 cur_bandc = nxt_bandc, cur_bandb = nxt_bandb;
             const RingEntry cur_col = col_decode(nxt_col, n, n <= t.b_right);
             if (j + 1 < nsteps) {
                 if (sub == 0) {
                     nxt_band = __ldcg(band + (n + 1 - band_bias));
                     nxt_bandc = __ldcg(bandc + (n + 1 - band_bias));
+                    if (LOCAL && localL) nxt_bandb = __ldcg(bandb + (n + 1 - band_bias));
                 }
                 nxt_col = col_fetch(n + 1);
             }
@@ -226,13 +287,26 @@ __device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
             }
             const int up_d = prev_uh, up_dc = prev_uc;
             prev_uh = up_h; prev_uc = up_c;
+            if (LOCAL) {
+                // hb lanes are only maintained when both left ends are free (LocalL)
+                if (sub == 0) { ls.up_b = cur_bandb.x; ls.up_fb = cur_bandb.y; }
+                else { ls.up_b = sh_b; ls.up_fb = sh_fb; }
+                ls.up_db = prev_ub;
+                prev_ub = ls.up_b;
+                ls.diag0 = (n - row0) - (g.ml + row0 + 1);
+            }
             unsigned events;
             if (i & 1)
-                strip_step_udh<SPJ>(HB, HA, F, E, V2, NJ, CB, CA, FC, EC, C2, arow, ring_hi, mtx_bytes,
-                                    sm.pen, P.pen_cap, j, up_h, up_f, up_d, up_c, up_fc, up_dc, gn, ge, events);
+                strip_step_udh<SPJ, LOCAL>(HB, HA, F, E, V2, NJ, CB, CA, FC, EC, C2, LL.BB, LL.BA, LL, ls,
+                                           arow, ring_hi, mtx_bytes, sm.pen, P.pen_cap, j,
+                                           up_h, up_f, up_d, up_c, up_fc, up_dc, gn, ge, events);
             else
-                strip_step_udh<SPJ>(HA, HB, F, E, V2, NJ, CA, CB, FC, EC, C2, arow, ring_hi, mtx_bytes,
-                                    sm.pen, P.pen_cap, j, up_h, up_f, up_d, up_c, up_fc, up_dc, gn, ge, events);
+                strip_step_udh<SPJ, LOCAL>(HA, HB, F, E, V2, NJ, CA, CB, FC, EC, C2, LL.BA, LL.BB, LL, ls,
+                                           arow, ring_hi, mtx_bytes, sm.pen, P.pen_cap, j,
+                                           up_h, up_f, up_d, up_c, up_fc, up_dc, gn, ge, events);
+            if (LOCAL && localR && ls.bv > bval) {      // strictly greater: earlier steps keep ties
+                bval = ls.bv; bstep = n; bk = row0 + ls.bk; bml = ls.bml; bulk = ls.bulk;
+            }
             // ---- intermediate row (src/fwd2s1_wip_simd.h:694-705, 760-773)
             if (has_imd) {
                 const int rj = (n - k8) - (g.ml + k8 + 1);
@@ -261,12 +335,15 @@ __device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
                 int out_f = F[NRU - 1];
                 int out_c = (i & 1) ? CB[NRU - 1] : CA[NRU - 1];
                 int out_fc = FC[NRU - 1];
+                int out_b = (i & 1) ? LL.BB[NRU - 1] : LL.BA[NRU - 1];
+                int out_fb = LL.FB[NRU - 1];
                 if (kbot != NRU - 1) {
 #pragma unroll
                     for (int k = 0; k < NRU - 1; ++k)
                         if (k == kbot) {
                             out_h = (i & 1) ? HB[k] : HA[k]; out_f = F[k];
                             out_c = (i & 1) ? CB[k] : CA[k]; out_fc = FC[k];
+                            out_b = (i & 1) ? LL.BB[k] : LL.BA[k]; out_fb = LL.FB[k];
                         }
                 }
                 const int cb = n - j8;
@@ -274,12 +351,36 @@ __device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
                 if (cb > t.b_left && r0 >= t.lw && r0 <= t.up) {
                     __stcg(band + (r0 - t.lw + 1), pack16(out_h, out_f));
                     __stcg(reinterpret_cast<int2*>(uv.bandc) + (r0 - t.lw + 1), make_int2(out_c, out_fc));
+                    if (LOCAL && localL)
+                        __stcg(reinterpret_cast<int2*>(uv.bandb) + (r0 - t.lw + 1), make_int2(out_b, out_fb));
                 }
             }
         } else {
-            prev_uh = NEV; prev_uc = 0;
+            prev_uh = NEV; prev_uc = 0; prev_ub = 0;
         }
         __syncwarp();
+    }
+    if (LOCAL && localR) {
+        // reference order: strips ascending, then step, then lane (first max)
+        int bv = (live && bval > INT_MIN) ? bval : INT_MIN;
+        int bs = bstep, bkk = bk, bst = sidx, bm = bml, bu = bulk;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bkk, o);
+            const int ot = __shfl_xor_sync(0xffffffffu, bst, o);
+            const int om = __shfl_xor_sync(0xffffffffu, bm, o);
+            const int ou = __shfl_xor_sync(0xffffffffu, bu, o);
+            const bool take = ov > bv || (ov == bv && (ot < bst || (ot == bst && (os < bs || (os == bs && ok < bkk)))));
+            if (take) { bv = ov; bs = os; bkk = ok; bst = ot; bm = om; bu = ou; }
+        }
+        if (bv > INT_MIN && bv + accscr > wbest.val) {
+            wbest.val = bv + accscr;
+            wbest.ml = bm; wbest.ulk = bu;
+            wbest.mr = ml0 + NELEM * bst + bkk + 1;
+            wbest.nr = bs - bkk;
+        }
     }
     // rlst after this pass: the value left by the thread that handled the LAST
     // intermediate of the pass (intermediates of one pass run concurrently; the
@@ -296,7 +397,7 @@ struct DevUdhOut {                      // per problem
     int pad0, pad1;
 };
 
-template <bool SPJ>
+template <bool SPJ, bool LOCAL>
 __global__ void __launch_bounds__(CTA_THREADS, 3)
 dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
               const DevTask* __restrict__ tasks, const int* __restrict__ order, int ntasks, int* ticket,
@@ -342,9 +443,12 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
         const int n_imd = t.pad0;
         int* cpos = cpospool + t.pad1;
 
+        const bool LocalL = LOCAL && a_exgl && b_exgl;
+        const bool LocalR = LOCAL && a_exgr && b_exgr;
         UdhTaskView uv;
         uv.bandc = uslab;
-        uv.imd = uslab + 2 * (long long) ((buf_size + 1) & ~1);
+        uv.bandb = uslab + 2 * (long long) ((buf_size + 1) & ~1);
+        uv.imd = uslab + 4 * (long long) ((buf_size + 1) & ~1);
         uv.n_imd = n_imd;
         uv.mm0 = (t.a_right - t.a_left + n_imd) / (n_imd + 1);
         {
@@ -398,6 +502,12 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
                 else v = a_exgl ? (r < ru ? r : rl) : rl;
                 if (r > ru) v = 0;
                 bc[i] = make_int2(v, v);
+                if (LOCAL) {
+                    // left-end rows: a.left everywhere; along the free left edge of b the row itself
+                    int hbv = (short) t.a_left;
+                    if (b_exgl && r >= t.lw && r <= rl) hbv = (short) (t.a_left + (rl - r));
+                    reinterpret_cast<int2*>(uv.bandb)[i] = make_int2(hbv, (short) t.a_left);
+                }
             }
         }
         __threadfence_block();
@@ -407,12 +517,14 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
         const int md = checkpoint(P.avmch, 0);
         int mc = md + t.a_left;
         int rlst = INT_MAX;
+        UdhBest wbest{NEV, END_OF_ULK, t.a_left, t.a_right, t.b_right};
         int ml0 = t.a_left;
         while (ml0 < t.a_right) {
             int nstr = min(SPPU, (t.a_right - ml0 + NELEM - 1) / NELEM);
             if (mc >= ml0 && mc < ml0 + nstr * NELEM && ((mc - ml0) % NELEM) == 0)
                 nstr = (mc - ml0) / NELEM + 1;
-            run_pass_udh<SPJ>(P, sm, t, uv, aseq, cols, band, ml0, nstr, rlst);
+            run_pass_udh<SPJ, LOCAL>(P, sm, t, uv, aseq, cols, band, ml0, nstr, rlst,
+                                     LocalL, LocalL && !accscr, LocalR, accscr, wbest);
             const int last_ml = ml0 + (nstr - 1) * NELEM;
             if (last_ml == mc) {
                 const int nmax = t.up - t.lw;
@@ -458,23 +570,31 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
             }
             return n <= 0 ? from : bi;
         };
-        if (a_exgr) {
-            const int r = max(t.lw, t.b_left - t.a_right);
-            maxr = argmax(r, rr - r);
-        }
-        if (b_exgr) {
-            const int r = min(t.up - 1, t.b_right - t.a_left);
-            const int mv = argmax(rr, r - rr);
-            if (lo16(__ldcg(band + (mv - t.lw + 1))) > lo16(__ldcg(band + (maxr - t.lw + 1)))) maxr = mv;
+        if (!LocalR) {
+            if (a_exgr) {
+                const int r = max(t.lw, t.b_left - t.a_right);
+                maxr = argmax(r, rr - r);
+            }
+            if (b_exgr) {
+                const int r = min(t.up - 1, t.b_right - t.a_left);
+                const int mv = argmax(rr, r - rr);
+                if (lo16(__ldcg(band + (mv - t.lw + 1))) > lo16(__ldcg(band + (maxr - t.lw + 1)))) maxr = mv;
+            }
         }
         if (lane == 0) {
-            // ... and the back-walk over the intermediates (src/fwd2s1_wip_simd.h:825-863)
+            // ... and the back-walk over the intermediates (src/fwd2s1_wip_simd.h:812-863)
             const int lw = t.lw, up = t.up;
-            int val = lo16(__ldcg(band + (maxr - lw + 1))) + accscr;
             int a_left = t.a_left, a_right = t.a_right, b_left = t.b_left, b_right = t.b_right;
-            if (maxr > rr) a_right = t.b_right - maxr; else b_right = t.a_right + maxr;
-            int r = __ldcg(reinterpret_cast<const int2*>(uv.bandc) + (maxr - lw + 1)).x;
-            const int maxh_ml = a_left;
+            int val, r, maxh_ml;
+            if (LocalR) {
+                val = wbest.val; r = wbest.ulk; maxh_ml = wbest.ml;
+                a_right = wbest.mr; b_right = wbest.nr;
+            } else {
+                val = lo16(__ldcg(band + (maxr - lw + 1))) + accscr;
+                if (maxr > rr) a_right = t.b_right - maxr; else b_right = t.a_right + maxr;
+                r = __ldcg(reinterpret_cast<const int2*>(uv.bandc) + (maxr - lw + 1)).x;
+                maxh_ml = LocalL ? __ldcg(reinterpret_cast<const int2*>(uv.bandb) + (maxr - lw + 1)).x : a_left;
+            }
             auto MI = [&](int i) { return t.a_left + uv.mm0 * (i + 1); };
             auto L = [&](int i, int which, int d, int rr_) -> int& {
                 return uv.imd[(long long) i * 4 * width + (which * 2 + d) * width + (rr_ - (lw - 1))];
@@ -482,7 +602,7 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
             int i = n_imd;
             while (--i >= 0 && MI(i) > a_right) ;
             if (i < 0 && MI(0) > a_right) cpos[2] = b_right;
-            for ( ; i >= 0 && MI(i) > maxh_ml; --i) {
+            for ( ; r < END_OF_ULK && i >= 0 && MI(i) > maxh_ml; --i) {
                 int cc = 0, d = 0;
                 for ( ; r >= up; r -= width) ++d;
                 const int v = L(i, 1, d, r);
@@ -499,7 +619,10 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
                     cpos[10 * i + 0] = END_OF_ULK;
             }
             for ( ; r > up; r -= width) ;
-            {
+            if (LocalL) {
+                a_left = maxh_ml;
+                b_left = r + a_left;
+            } else {
                 const int rl = b_left - a_left;
                 if (b_exgl && rl > r) {
                     a_left = b_left - r;

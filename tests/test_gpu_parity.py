@@ -155,7 +155,7 @@ def _cpos_equal(a, b):
     return True
 
 
-@pytest.mark.parametrize("name", ["dna_A2_udh", "dna_A6_udh_recursive"])
+@pytest.mark.parametrize("name", ["dna_A2_udh", "dna_A6_udh_recursive", "dna_A2_udh_local"])
 def test_hirschberg_wip_matches_reference_golden(name):
     prm, probs = golden_io.load(name)
     sel = [pb for pb in probs if "udh_nim" in pb
@@ -174,9 +174,11 @@ def test_hirschberg_wip_matches_reference_golden(name):
     eng.close()
 
 
-@pytest.mark.parametrize("flags", [None, (0, 0, 0, 0), (1, 0, 0, 1)])
-def test_hirschberg_wip_matches_oracle_seeded(oracle, flags):
-    prm, _ = golden_io.load("dna_A2_global")
+@pytest.mark.parametrize("flags,fixture", [(None, "dna_A2_global"), ((0, 0, 0, 0), "dna_A2_global"),
+                                           ((1, 0, 0, 1), "dna_A2_global"), (None, "dna_A2_local"),
+                                           ((1, 0, 1, 0), "dna_A2_local"), ((0, 1, 0, 1), "dna_A2_local")])
+def test_hirschberg_wip_matches_oracle_seeded(oracle, flags, fixture):
+    prm, _ = golden_io.load(fixture)
     rng = np.random.default_rng(4242 + (sum(flags) if flags else 9))
     probs = _synthetic(prm, rng, 20, (60, 900), (40, 500), flags=flags)
     probs += _synthetic(prm, rng, 3, (1500, 2400), (100, 400), flags=flags)     # re-basing
@@ -200,7 +202,7 @@ def test_hirschberg_wip_matches_oracle_seeded(oracle, flags):
 # ---------------------------------------------------------------------------
 # the whole driver: lspS_ng (trace-back vs UDH dispatch + block re-alignment)
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["dna_A2_udh", "dna_A6_udh_recursive", "dna_A2_global"])
+@pytest.mark.parametrize("name", ["dna_A2_udh", "dna_A6_udh_recursive", "dna_A2_global", "dna_A2_udh_local"])
 def test_lsp_driver_matches_reference_golden(oracle, name):
     prm, probs = golden_io.load(name)
     eng = _engine(prm)
