@@ -25,6 +25,8 @@ int shim_s1_kernel(const Seq** seqs, const PwdB* pwd, int lw, int up,
 int shim_s1_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up,
 	int* score, int* skl_out, int cap, double* seconds);
 int shim_s1_nelem();
+int shim_h1_kernel(const Seq** seqs, const PwdB* pwd, int lw, int up, int kind,
+	int* score, int* skl_out, int cap, double* seconds);
 int shim_s1_adapter(const Seq** seqs, const PwdB* pwd, int lw, int up,
 	int kind, int device, int* score, int* skl_out, int cap);
 }
@@ -141,6 +143,7 @@ void* ref_task_new(const char* genome_fa, const char* query_fa, int comrev_query
 	a->inex.intr = 0;
 	b->inex.intr = b_intr;
 	if (comrev_query) a->comrev();
+	if (g_pwd->DvsP == 1) b->nuc2tron();		// protein query: src/spaln.cc:748-753
 	if (!b->exin) b->exin = new Exinon(b, g_pwd, false);
 	if (algmode.lcl & 16) {
 	    a->exg_seq(1, 1);
@@ -212,6 +215,49 @@ void ref_task_inject(void* h, const short* sig5, const short* sig3)
 	    g->sig5 = sig5[n];
 	    g->sig3 = sig3[n];
 	}
+}
+
+// protein x genome: SGPT6 table (8 shorts per column n = 0 .. b.len + 1:
+// sig5, sig3, sigS, sigT, sigE, sigI, phs5, phs3) and the frozen protein parameters
+void ref_task_export_p(void* h, unsigned char* a_codes, unsigned char* b_codes, short* sgpt6)
+{
+	RefTask* t = (RefTask*) h;
+	const Seq* a = t->sqs[0];
+	const Seq* b = t->sqs[1];
+	for (int i = -1; i <= a->len; ++i) a_codes[i + 1] = *a->at(i);
+	for (int i = -1; i <= b->len; ++i) b_codes[i + 1] = *b->at(i);
+	for (int n = 0; n <= b->len + 1; ++n) {
+	    const SGPT6* g = b->exin->score_p(n);
+	    short* o = sgpt6 + 8 * n;
+	    o[0] = g->sig5; o[1] = g->sig3; o[2] = g->sigS; o[3] = g->sigT;
+	    o[4] = g->sigE; o[5] = g->sigI; o[6] = g->phs5; o[7] = g->phs3;
+	}
+}
+
+int ref_get_params_p(int* out, int cap)
+{
+	if (!g_pwd) return -1;
+	const PwdB* p = g_pwd;
+	int vals[] = {p->GapW1, p->GapW2, p->GapW3, p->GapW3L, p->GapE1, p->GapE2, p->ExtraGOP,
+	    p->codonk1, (int) alprm2.termk1, p->simmtx->rows, p->simmtx->cols};
+	int nv = sizeof(vals) / sizeof(int);
+	for (int i = 0; i < nv && i < cap; ++i) out[i] = vals[i];
+	return nv;
+}
+
+int ref_task_kernel_p(void* h, int lw, int up, int kind, int* score, int* skl_out, int cap,
+	double* seconds)
+{
+	RefTask* t = (RefTask*) h;
+	return shim_h1_kernel((const Seq**) t->sqs, g_pwd, lw, up, kind, score, skl_out, cap, seconds);
+}
+
+void ref_task_stripe31(void* h, int sh, int* lwup)
+{
+	RefTask* t = (RefTask*) h;
+	WINDOW w;
+	stripe31((const Seq**) t->sqs, &w, sh);
+	lwup[0] = w.lw; lwup[1] = w.up; lwup[2] = w.width;
 }
 
 void ref_task_stripe(void* h, int sh, int* lwup)

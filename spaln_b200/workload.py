@@ -201,3 +201,53 @@ def config2_problem(rng, sh=100, **kw):
             "b_left": 0, "b_right": len(b), "a_exgl": 1, "a_exgr": 1, "b_exgl": 1, "b_exgr": 1,
             "lw": lw, "up": up, "truth": truth,
             "genome_str": g.tobytes().decode(), "query_str": q.tobytes().decode()}
+
+
+# ---------------------------------------------------------------------------
+# protein x genome (BASELINE.json config 3 shape)
+# ---------------------------------------------------------------------------
+_CODONS = {}
+_BASES = "TCAG"
+_AAS = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"
+for _i, _aa in enumerate(_AAS):
+    _CODONS.setdefault(_aa, []).append(_BASES[_i // 16] + _BASES[(_i // 4) % 4] + _BASES[_i % 4])
+_AA_LETTERS = "ACDEFGHIKLMNPQRSTVWY"
+
+
+def plant_protein_gene(rng, plen_range=(100, 400), n_exons=None, flank=(100, 600),
+                       intron_scale=1.0, sub=0.05, gc=0.41):
+    """returns (genome segment, protein query, CDS exon truth).  The CDS (start codon ..
+    stop codon) is cut into exons at arbitrary codon phases; introns are GT..AG."""
+    plen = int(rng.integers(plen_range[0], plen_range[1] + 1))
+    prot = ["M"] + [_AA_LETTERS[i] for i in rng.integers(0, 20, size=plen - 1)]
+    cds = "".join(_CODONS[a][int(rng.integers(0, len(_CODONS[a])))] for a in prot) + "TAA"
+    L = len(cds)
+    if n_exons is None:
+        n_exons = 1 + int(rng.poisson(2))
+    n_exons = max(1, min(n_exons, L // 40))
+    cuts = np.sort(rng.choice(np.arange(20, L - 20), size=n_exons - 1, replace=False)) if n_exons > 1 else []
+    bounds = [0] + [int(c) for c in cuts] + [L]
+    introns = intron_lengths(rng, n_exons - 1, intron_scale)
+    fl = int(rng.integers(flank[0], flank[1] + 1))
+    fr = int(rng.integers(flank[0], flank[1] + 1))
+    parts = [random_dna(rng, fl, gc).tobytes().decode()]
+    truth = []
+    pos = fl
+    for i in range(n_exons):
+        ex = cds[bounds[i]:bounds[i + 1]]
+        parts.append(ex)
+        truth.append((pos, pos + len(ex)))
+        pos += len(ex)
+        if i < n_exons - 1:
+            il = int(introns[i])
+            it = random_dna(rng, il, gc)
+            it[:2] = np.frombuffer(b"GT", np.uint8)
+            it[-2:] = np.frombuffer(b"AG", np.uint8)
+            parts.append(it.tobytes().decode())
+            pos += il
+    parts.append(random_dna(rng, fr, gc).tobytes().decode())
+    q = list(prot)
+    nsub = rng.binomial(len(q), sub)
+    for j in rng.choice(len(q), size=nsub, replace=False):
+        q[int(j)] = _AA_LETTERS[int(rng.integers(0, 20))]
+    return "".join(parts), "".join(q), truth

@@ -48,7 +48,7 @@ class Reference:
 
     _instance = None
 
-    def __init__(self, opts: str = "-Q0 -A2 -S1 -yX0 -TDictyost"):
+    def __init__(self, opts: str = "-Q0 -A2 -S1 -yX0 -TDictyost", protein: bool = False):
         if Reference._instance is not None:
             raise RuntimeError("reference already set up in this process")
         if not available():
@@ -73,12 +73,18 @@ class Reference:
                                    C.c_void_p, C.c_int, C.c_void_p]
         L.ref_task_adapter.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_task_export_p.argtypes = [C.c_void_p] * 4
+        L.ref_get_params_p.argtypes = [C.c_void_p, C.c_int]
+        L.ref_task_kernel_p.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_void_p]
+        L.ref_task_stripe31.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ref_get_params.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         self.tmp = tempfile.TemporaryDirectory(prefix="spaln_ref_")
         g = os.path.join(self.tmp.name, "g0.fa")
         q = os.path.join(self.tmp.name, "q0.fa")
         write_fasta(g, "g0", "ACGTTGCAAGTCCGATGCATGCAAGTCGATCGATGCTAGCTAGCATCGATCGACTAGCTAGCAT" * 4)
-        write_fasta(q, "q0", "ACGTTGCAAGTCCGATGCATGCAAGTCGATCGATGCTAGC")
+        write_fasta(q, "q0", "MKVLAAGIVGLLLAQWPSEFDHRNTYCMKVLAAGIVGLLLAQWPSEFDHRNTYC" if protein
+                    else "ACGTTGCAAGTCCGATGCATGCAAGTCGATCGATGCTAGC")
         rc = L.ref_setup(opts.encode(), g.encode(), q.encode())
         if rc < 0:
             raise RuntimeError(f"ref_setup failed: {rc}")
@@ -98,6 +104,12 @@ class Reference:
         p["quant_pen"] = q[:, 1].astype(np.int32).copy()
         d = p["simdim"]
         p["simmtx"] = sim[: d * d].reshape(d, d).copy()
+        if p["DvsP"] == 1:
+            pb = np.zeros(16, np.int32)
+            self.lib.ref_get_params_p(pb.ctypes.data, 16)
+            for i, name in enumerate(["GapW1", "GapW2", "GapW3", "GapW3L", "GapE1", "GapE2", "ExtraGOP",
+                                      "codonk1", "termk1", "sim_rows", "sim_cols"]):
+                p[name] = int(pb[i])
         return p
 
     def task(self, genome: str, query: str, comrev_query: bool = False) -> "RefTask":
@@ -155,6 +167,29 @@ class RefTask:
                                  s5.ctypes.data, s3.ctypes.data)
         i.update(a=a, b=b, sig5=s5, sig3=s3)
         return i
+
+    def export_p(self) -> dict:
+        """protein x genome problem: aa codes, tron codes, SGPT6 table"""
+        i = self.info()
+        a = np.zeros(i["alen"] + 2, np.uint8)
+        b = np.zeros(i["blen"] + 2, np.uint8)
+        g = np.zeros((i["blen"] + 2, 8), np.int16)
+        self.lib.ref_task_export_p(self.h, a.ctypes.data, b.ctypes.data, g.ctypes.data)
+        i.update(a=a, b=b, sgpt6=g)
+        return i
+
+    def stripe31(self, sh: int):
+        b = np.zeros(3, np.int32)
+        self.lib.ref_task_stripe31(self.h, sh, b.ctypes.data)
+        return int(b[0]), int(b[1])
+
+    def kernel_p(self, lw, up, kind=0, cap=1 << 16):
+        score = C.c_int(0)
+        secs = C.c_double(0)
+        skl = np.zeros((cap, 2), np.int32)
+        n = self.lib.ref_task_kernel_p(self.h, lw, up, kind, C.byref(score), skl.ctypes.data, cap,
+                                       C.byref(secs))
+        return {"score": score.value, "skl": skl[:n].copy(), "seconds": secs.value}
 
     def inject(self, sig5, sig3):
         s5 = np.ascontiguousarray(sig5, np.int16)
