@@ -110,6 +110,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic_per_cell():
+    """DRAM bytes per cell of the DP kernel from the committed `ncu --set full` capture"""
+    p = ROOT / "profiles" / "r01_traffic.json"
+    try:
+        return float(json.loads(p.read_text())["dram_bytes_per_cell"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -325,7 +334,11 @@ def main():
                                   "total": 1e3 * e2e_s}},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "frac": achieved / peak,
+                         "traffic": (measured_traffic_per_cell() * cells_step
+                                     if measured_traffic_per_cell() else None),
+                         "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes per cell x cells of this launch)",
+                         "peak_kind": peak_kind,
                          "bytes_per_cell": B_CELL, "kernel": "dp_wip_kernel<true>",
                          "kernel_ms": k_ms,
                          "note": "integer-ALU bound DP: see DESIGN.md (HBM roof is not the binding one)"},
