@@ -82,6 +82,32 @@ typedef struct {
 int so_lsp(const so_params* p, const so_task* t, const so_lsp_opts* o, int32_t* score,
            int32_t* skl, int cap, int* unsupported);
 
+/* ---- protein x genome: SimdAln2h1::forwardH1_wip (src/fwd2h1_wip_simd.h:50-336) ---- */
+typedef struct {
+    int32_t gop, gep;       /* PwdB::BasicGOP, BasicGEP */
+    int32_t lgep, codonk1;  /* PwdB::LongGEP, codonk1 (GapExtPen3) */
+    int32_t gw1, gw2, gw3;  /* PwdB::GapW1, GapW2 (frame shifts), GapW3 (codon gap open + ext) */
+    int32_t ipen, llmt, nquant;
+    int32_t quant_len[SO_MAXQUANT], quant_pen[SO_MAXQUANT];
+    int32_t avmch, local, lcl, spj, simdim;
+    const int32_t* simmtx;  /* [aa code][tron code] */
+} so_params_h;
+
+typedef struct {
+    const uint8_t* a;       /* amino-acid codes, a[i] == *a->at(i) */
+    const uint8_t* b;       /* tron codes (Seq::nuc2tron, src/seq.cc:774-798), b[i] == *b->at(i) */
+    const int16_t* sgpt6;   /* SGPT6 by column n in [0, b_len + 1]: sig5, sig3, sigS, sigT, sigE,
+                               sigI, phs5, phs3 (src/codepot.h:34-43) */
+    int32_t b_len;          /* Seq::len of the genomic segment (range of Exinon::good()) */
+    int32_t a_left, a_right, b_left, b_right;
+    int32_t a_exgl, a_exgr, b_exgl, b_exgr;     /* INEX flags, values 0..3 */
+    int32_t lw, up;         /* WINDOW from stripe31 (width = up - lw + 7) */
+} so_task_h;
+
+/* returns number of corners (want_trace) or 0; -1 allocation failure, -2 bad trace code */
+int so_forward_h1_wip(const so_params_h* p, const so_task_h* t, int want_trace, int32_t* score,
+                      int32_t* skl, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,7 +34,66 @@ CONFIGS = {
     "dna_A2_udh": ("-Q0 -A2 -S1 -yX0 -V256K -TDictyost", 15),
     "dna_A2_udh_local": ("-Q0 -A2 -S1 -yX0 -V256K -LS -TDictyost", 16),
     "dna_A6_udh_recursive": ("-Q0 -A6 -S1 -yX0 -V128K -TDictyost", 17),
+    # protein query x genomic segment (SimdAln2h1::forwardH1_wip)
+    "prot_A2_global": ("-Q0 -A2 -yX0 -TDictyost", 21),
+    "prot_A2_local": ("-Q0 -A2 -yX0 -LS -TDictyost", 22),
 }
+
+
+def gen_protein(name: str):
+    import ref_harness as R
+    from spaln_b200 import workload as synth
+
+    opts, seed = CONFIGS[name]
+    ref = R.Reference(opts, protein=True)
+    p = ref.params()
+    rng = np.random.default_rng(seed)
+    out = {"opts": np.array(opts)}
+    for k, v in p.items():
+        out["prm_" + k] = np.asarray(v)
+    n = 0
+
+    def add(g, q, tag="", **setkw):
+        nonlocal n
+        t = ref.task(g, q)
+        if setkw:
+            t.set(**setkw)
+        lw, up = t.stripe31(p["sh"])
+        ex = t.export_p()
+        r = t.kernel_p(lw, up, 0)
+        r1 = t.kernel_p(lw, up, 1)
+        pre = f"p{n}_"
+        out[pre + "a"] = ex["a"]
+        out[pre + "b"] = ex["b"]
+        out[pre + "sgpt6"] = ex["sgpt6"]
+        out[pre + "geom"] = np.array([ex["a_left"], ex["a_right"], ex["b_left"], ex["b_right"],
+                                      ex["a_exgl"], ex["a_exgr"], ex["b_exgl"], ex["b_exgr"],
+                                      lw, up, ex["blen"]], np.int32)
+        out[pre + "score"] = np.int32(r["score"])
+        out[pre + "skl"] = r["skl"].astype(np.int32)
+        out[pre + "score_only"] = np.int32(r1["score"])
+        out[pre + "tag"] = np.array(tag)
+        n += 1
+        t.close()
+
+    for i in range(10):
+        g, q, _ = synth.plant_protein_gene(rng, plen_range=(20, 200), flank=(40, 250))
+        add(g, q, tag="gene")
+    g, q, _ = synth.plant_protein_gene(rng, plen_range=(80, 150), flank=(60, 200))
+    add(g, q, tag="global_left", a_exgl=0, b_exgl=0)
+    add(g, q, tag="global_right", a_exgr=0, b_exgr=0)
+    add(g, q, tag="global_all", a_exgl=0, a_exgr=0, b_exgl=0, b_exgr=0)
+    add(g, q, tag="subrange", a_left=7, a_right=len(q) - 5, b_left=31, b_right=len(g) - 43)
+    for pl in (8, 15, 16, 17, 31, 32, 33):
+        g2, q2, _ = synth.plant_protein_gene(rng, plen_range=(pl, pl), n_exons=1, flank=(30, 120))
+        add(g2, q2, tag=f"tiny{pl}")
+    g, q, _ = synth.plant_protein_gene(rng, plen_range=(640, 700), n_exons=3, flank=(40, 80))
+    add(g, q, tag="rebase")     # > 544 rows: crosses the int16 re-basing check point
+    out["n"] = np.int32(n)
+    path = HERE / f"{name}.npz"
+    np.savez_compressed(path, **out)
+    print(name, "problems:", n, "->", path, f"{path.stat().st_size / 1024:.0f} KiB")
+
 
 
 def gen(name: str):
@@ -120,7 +179,7 @@ def gen(name: str):
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:
-        gen(sys.argv[1])
+        (gen_protein if sys.argv[1].startswith("prot") else gen)(sys.argv[1])
     else:
         for name in CONFIGS:
             subprocess.run([sys.executable, __file__, name], check=True)

@@ -30,3 +30,25 @@ def load(name):
                 d[k] = v if v.ndim else int(v)
         probs.append(d)
     return prm, probs
+
+
+PROTEIN_NAMES = ["prot_A2_global", "prot_A2_local"]
+GEOM_KEYS_P = GEOM_KEYS + ["blen"]
+
+
+def load_protein(name):
+    z = np.load(GOLDEN_DIR / f"{name}.npz")
+    prm = {}
+    for k in z.files:
+        if k.startswith("prm_"):
+            v = z[k]
+            prm[k[4:]] = v if v.ndim else int(v)
+    probs = []
+    for i in range(int(z["n"])):
+        pre = f"p{i}_"
+        d = {"a": z[pre + "a"], "b": z[pre + "b"], "sgpt6": z[pre + "sgpt6"],
+             "score": int(z[pre + "score"]), "skl": z[pre + "skl"],
+             "score_only": int(z[pre + "score_only"]), "tag": str(z[pre + "tag"])}
+        d.update({k: int(v) for k, v in zip(GEOM_KEYS_P, z[pre + "geom"])})
+        probs.append(d)
+    return prm, probs

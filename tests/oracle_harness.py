@@ -52,6 +52,7 @@ def lib():
                                            C.c_void_p, C.c_void_p]
         _lib.so_lsp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_void_p]
+        _lib.so_forward_h1_wip.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     return _lib
 
 
@@ -146,3 +147,54 @@ def lsp(p: dict, t: dict, cap: int = 1 << 16, max_vmf_space=None):
     n = lib().so_lsp(C.byref(sp), C.byref(st), C.byref(o), C.byref(score), skl.ctypes.data, cap,
                      C.byref(unsup))
     return {"score": score.value, "skl": skl[:min(n, cap)].copy(), "unsupported": bool(unsup.value)}
+
+
+# ---------------------------------------------------------------------------
+# protein x genome
+# ---------------------------------------------------------------------------
+class SoParamsH(C.Structure):
+    _fields_ = [("gop", C.c_int32), ("gep", C.c_int32), ("lgep", C.c_int32), ("codonk1", C.c_int32),
+                ("gw1", C.c_int32), ("gw2", C.c_int32), ("gw3", C.c_int32),
+                ("ipen", C.c_int32), ("llmt", C.c_int32), ("nquant", C.c_int32),
+                ("quant_len", C.c_int32 * MAXQ), ("quant_pen", C.c_int32 * MAXQ),
+                ("avmch", C.c_int32), ("local", C.c_int32), ("lcl", C.c_int32), ("spj", C.c_int32),
+                ("simdim", C.c_int32), ("simmtx", C.c_void_p)]
+
+
+class SoTaskH(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("sgpt6", C.c_void_p), ("b_len", C.c_int32),
+                ("a_left", C.c_int32), ("a_right", C.c_int32), ("b_left", C.c_int32), ("b_right", C.c_int32),
+                ("a_exgl", C.c_int32), ("a_exgr", C.c_int32), ("b_exgl", C.c_int32), ("b_exgr", C.c_int32),
+                ("lw", C.c_int32), ("up", C.c_int32)]
+
+
+def forward_h1_wip(p: dict, t: dict, want_trace=True, cap: int = 1 << 16):
+    sp = SoParamsH()
+    sp.gop, sp.gep, sp.lgep, sp.codonk1 = p["BasicGOP"], p["BasicGEP"], p["LongGEP"], p["codonk1"]
+    sp.gw1, sp.gw2, sp.gw3 = p["GapW1"], p["GapW2"], p["GapW3"]
+    sp.ipen, sp.llmt, sp.nquant = p["GapWI"], p["llmt"], p["nquant"]
+    for j in range(p["nquant"]):
+        sp.quant_len[j] = int(p["quant_len"][j])
+        sp.quant_pen[j] = int(p["quant_pen"][j])
+    sp.avmch = p["avmch"]
+    sp.local = 1 if (p["lcl"] & 16) else 0
+    sp.lcl = p["lcl"]
+    sp.spj = p.get("spj", 1)
+    sp.simdim = p["simdim"]
+    sim = np.ascontiguousarray(p["simmtx"], np.int32)
+    sp.simmtx = sim.ctypes.data
+    st = SoTaskH()
+    a = np.ascontiguousarray(t["a"], np.uint8)
+    b = np.ascontiguousarray(t["b"], np.uint8)
+    g = np.ascontiguousarray(t["sgpt6"], np.int16)
+    st.a, st.b, st.sgpt6 = a.ctypes.data + 1, b.ctypes.data + 1, g.ctypes.data
+    st.b_len = int(t["blen"])
+    for k in ("a_left", "a_right", "b_left", "b_right", "a_exgl", "a_exgr", "b_exgl", "b_exgr", "lw", "up"):
+        setattr(st, k, int(t[k]))
+    score = C.c_int32(0)
+    skl = np.zeros((cap, 2), np.int32)
+    n = lib().so_forward_h1_wip(C.byref(sp), C.byref(st), int(want_trace), C.byref(score),
+                                skl.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError(f"so_forward_h1_wip failed: {n}")
+    return {"score": score.value, "skl": skl[:n].copy()}
