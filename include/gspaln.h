@@ -173,6 +173,71 @@ const char* gspaln_version(void);
  * (inner-loop trip count of Aln2s1::forwardS_ng, src/fwd2s1.cc:252-276) */
 int64_t gspaln_task_cells(const gspaln_task* t);
 
+/* ======================================================================================
+ * Protein query x genomic segment: SimdAln2h1 (src/fwd2h1_simd.h:69-382).
+ *
+ *   gspaln_h_create      freezes what SimdAln2h1::forwardH1_wip / fhinitH1 / fhlastH1 read from
+ *                        PwdB (GapW1/W2/W3, BasicGOP/GEP, LongGEP, codonk1: src/aln.h:235-308),
+ *                        IntronPrm + IntronPenalty::qm, Simmtx::mtx[aa][tron], algmode.lcl.
+ *   gspaln_h_submit      kind GSPALN_FORWARD_WIP   = SimdAln2h1 ctor + forwardH1_wip(Mfile*)
+ *                        (src/fwd2h1_wip_simd.h:50-336) as called from Aln2h1::trcbkalignH_ng
+ *                        (src/fwd2h1.cc:2006-2019); kind GSPALN_SCOREONLY_WIP = forwardH1_wip(0)
+ *                        as called from HomScoreH_ng (src/fwd2h1.cc:3293-3307).
+ *   gspaln_result.skl    the corners Anti_rhomb_coord<SHORT>::traceback (step 3,
+ *                        src/rhomb_coord.h:222-235) appends to the caller's Mfile.
+ * ====================================================================================== */
+
+/* SGPT6, src/codepot.h:34-43 (same layout: 6 shorts + 2 chars, 14 bytes) */
+typedef struct gspaln_sgpt6 {
+    int16_t sig5, sig3, sigS, sigT, sigE, sigI;
+    int8_t phs5, phs3;
+} gspaln_sgpt6;
+
+typedef struct gspaln_h_params {
+    int32_t gop;                /* PwdB::BasicGOP */
+    int32_t gep;                /* PwdB::BasicGEP */
+    int32_t lgep;               /* PwdB::LongGEP  (GapExtPen3 beyond codonk1) */
+    int32_t codonk1;            /* PwdB::codonk1 */
+    int32_t gw1, gw2, gw3;      /* PwdB::GapW1, GapW2 (frame shifts), GapW3 (codon gap) */
+    int32_t ipen;               /* IntronPenalty::Penalty() == GapWI */
+    int32_t llmt;               /* IntronPrm.llmt */
+    int32_t nquant;             /* IntronPrm.nquant */
+    int32_t quant_len[GSPALN_MAXQUANT];
+    int32_t quant_pen[GSPALN_MAXQUANT];
+    int32_t avmch;              /* int(Simmtx::AvTrc()) */
+    int32_t lcl;                /* algmode.lcl (bit 4: local, bit 1: termination-codon bonus) */
+    int32_t spj;                /* Seq::inex.intr of the genomic sequence */
+    int32_t simdim;             /* row stride of simmtx below */
+    int32_t simmtx[GSPALN_MAXDIM * GSPALN_MAXDIM];  /* mtx[aa][tron] at [aa * simdim + tron] */
+} gspaln_h_params;
+
+typedef struct gspaln_h_task {
+    int32_t kind;               /* GSPALN_FORWARD_WIP or GSPALN_SCOREONLY_WIP */
+    const uint8_t* a;           /* amino-acid codes; a[i] == *Seq::at(i) */
+    const uint8_t* b;           /* tron codes (Seq::nuc2tron, src/seq.cc:774-798); b[i] == *Seq::at(i) */
+    const gspaln_sgpt6* sg;     /* Exinon::data_p[n], n in [0, b_len + 1] */
+    int32_t b_len;              /* Seq::len of the genomic segment (range of Exinon::good()) */
+    int32_t a_left, a_right, b_left, b_right;
+    int32_t a_exgl, a_exgr, b_exgl, b_exgr;     /* INEX values 0..3 */
+    int32_t lw, up;             /* WINDOW from stripe31 (src/aln2.cc:178-199); width = up - lw + 7 */
+    int32_t skl_cap;
+    int32_t n_imd;              /* reserved (hirschbergH1_wip) */
+} gspaln_h_task;
+
+typedef struct gspaln_h_ctx gspaln_h_ctx;
+
+int  gspaln_h_create(gspaln_h_ctx** out, const gspaln_h_params* prm, int device);
+void gspaln_h_destroy(gspaln_h_ctx* ctx);
+int  gspaln_h_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gspaln_result* results);
+int  gspaln_h_upload(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n);
+int  gspaln_h_run(gspaln_h_ctx* ctx);
+int  gspaln_h_download(gspaln_h_ctx* ctx, gspaln_result* results);
+int  gspaln_h_get_timing(const gspaln_h_ctx* ctx, gspaln_timing* out);
+const char* gspaln_h_last_error(const gspaln_h_ctx* ctx);
+/* amino acid x nucleotide band cells as the scalar reference counts them
+ * (Aln2h1::forwardH_ng inner loop, src/fwd2h1.cc:326-331) */
+int64_t gspaln_h_task_cells(const gspaln_h_task* t);
+
 #ifdef __cplusplus
 }
 #endif

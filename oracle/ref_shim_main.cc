@@ -234,6 +234,20 @@ void ref_task_export_p(void* h, unsigned char* a_codes, unsigned char* b_codes, 
 	}
 }
 
+// overwrite the SGPT6 table (same 8-shorts-per-column layout as ref_task_export_p): lets both
+// arms of a benchmark run on one synthetic table
+void ref_task_inject_p(void* h, const short* sgpt6)
+{
+	RefTask* t = (RefTask*) h;
+	const Seq* b = t->sqs[1];
+	for (int n = 0; n <= b->len + 1; ++n) {
+	    SGPT6* g = b->exin->score_p(n);
+	    const short* o = sgpt6 + 8 * n;
+	    g->sig5 = o[0]; g->sig3 = o[1]; g->sigS = o[2]; g->sigT = o[3];
+	    g->sigE = o[4]; g->sigI = o[5]; g->phs5 = (char) o[6]; g->phs3 = (char) o[7];
+	}
+}
+
 int ref_get_params_p(int* out, int cap)
 {
 	if (!g_pwd) return -1;

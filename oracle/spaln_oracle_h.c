@@ -286,6 +286,13 @@ int so_forward_h1_wip(const so_params_h* p, const so_task_h* t, int want_trace, 
                 }
             }
 
+            /* `if (AllZero(ph_v)) continue;` (src/fwd2h1_wip_simd.h:223): a phase slot none of
+             * whose 16 lanes carries an acceptor is skipped for the whole vector */
+            int any3[2] = { 0, 0 };
+            if (p->spj)
+                for (int kk = 0; kk < 2; ++kk)
+                    for (int k = 0; k < NELEM; ++k) if (p3v[kk][k]) any3[kk] = 1;
+
             uint16_t tb[NELEM];
             for (int k = 0; k < NELEM; ++k) {
                 unsigned hb, pb, eb;
@@ -316,6 +323,7 @@ int so_forward_h1_wip(const so_params_h* p, const so_task_h* t, int want_trace, 
                 unsigned ab = 0;
                 if (p->spj) {
                     for (int kk = 0; kk < 2; ++kk) {
+                        if (!any3[kk]) continue;
                         for (int fz = kk ? 2 : 0; fz < 3; ++fz) {
                             var_t qv = adds16(hiv[fz][k], s3v[kk][k]);
                             var_t pen = mean[0];
@@ -457,12 +465,23 @@ int so_forward_h1_wip(const so_params_h* p, const so_task_h* t, int want_trace, 
     int cnt = 0;
     if (want_trace) {
         int m = maxh.mr, n = maxh.nr;
-        unsigned code = *trb3_set_point(&trb, m, n);
+        unsigned code = 0;
+        /* fhlastH1 can return a start point right of b_right (its last-column scan moves mx but
+         * not maxr, src/fwd2h1_simd.h:764-788): the reference then reads outside its trace
+         * buffer (undefined).  Here such a walk stops at once. */
+        if (m - trb.m_base >= 0 && m - trb.m_base < trb.m_width && n - trb.n_base >= 0 &&
+            3 * (m - trb.m_base) + (n - trb.n_base) < trb.n_width)
+            code = *trb3_set_point(&trb, m, n);
+        else
+            trb3_set_point(&trb, trb.m_base, trb.n_base);
         m -= trb.m_base; n -= trb.n_base;
         while (code) {
             if (cnt < cap) { skl[2 * cnt] = m + trb.m_base; skl[2 * cnt + 1] = n + trb.n_base; }
             ++cnt;
             if (trb3_go_back(&trb, code, &m, &n, &code) < 0) { cnt = -2; break; }
+            /* a start point outside the matrix (reference: undefined for some mixed end-gap
+             * flag combinations) can make the walk cycle: give up instead of spinning */
+            if (cnt > 4 * (trb.m_width + trb.n_width)) { cnt = -2; break; }
         }
         if (cnt >= 0) {
             if (cnt < cap) { skl[2 * cnt] = m + trb.m_base; skl[2 * cnt + 1] = n + trb.n_base; }

@@ -3,10 +3,11 @@
 Only what the DP hot path needs lives here:
   csrc/       hand-written sm_100a CUDA kernels + the C-ABI (include/gspaln.h)
   capi.py     ctypes binding of that C-ABI
-  engine.py   host-side mirror of the reference's SimdAln2s1 call surface
+  engine.py   host-side mirror of the reference's SimdAln2s1 / SimdAln2h1 call surface
   workload.py seeded synthetic problems of the BASELINE.json shapes
 """
 from .capi import FORWARD_WIP, SCOREONLY_WIP  # noqa: F401
-from .engine import Engine, EngineError, PackedBatch, Problem, Result, Timing  # noqa: F401
+from .engine import (Engine, EngineError, EngineH, PackedBatch, Problem, ProblemH,  # noqa: F401
+                     Result, Timing)
 
 __version__ = "0.1.0"

@@ -28,6 +28,8 @@ EXPORTS = [
     "gspaln_create", "gspaln_destroy", "gspaln_submit", "gspaln_upload", "gspaln_run",
     "gspaln_download", "gspaln_get_timing", "gspaln_last_error", "gspaln_device_count",
     "gspaln_version", "gspaln_task_cells", "gspaln_lsp",
+    "gspaln_h_create", "gspaln_h_destroy", "gspaln_h_submit", "gspaln_h_upload", "gspaln_h_run",
+    "gspaln_h_download", "gspaln_h_get_timing", "gspaln_h_last_error", "gspaln_h_task_cells",
 ]
 
 
@@ -72,6 +74,43 @@ class GspalnTiming(C.Structure):
     ]
 
 
+class GspalnHParams(C.Structure):
+    _fields_ = [
+        ("gop", C.c_int32), ("gep", C.c_int32), ("lgep", C.c_int32), ("codonk1", C.c_int32),
+        ("gw1", C.c_int32), ("gw2", C.c_int32), ("gw3", C.c_int32),
+        ("ipen", C.c_int32), ("llmt", C.c_int32), ("nquant", C.c_int32),
+        ("quant_len", C.c_int32 * MAXQUANT), ("quant_pen", C.c_int32 * MAXQUANT),
+        ("avmch", C.c_int32), ("lcl", C.c_int32), ("spj", C.c_int32), ("simdim", C.c_int32),
+        ("simmtx", C.c_int32 * (MAXDIM * MAXDIM)),
+    ]
+
+
+class GspalnHTask(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("a", C.c_void_p), ("b", C.c_void_p), ("sg", C.c_void_p),
+        ("b_len", C.c_int32),
+        ("a_left", C.c_int32), ("a_right", C.c_int32), ("b_left", C.c_int32), ("b_right", C.c_int32),
+        ("a_exgl", C.c_int32), ("a_exgr", C.c_int32), ("b_exgl", C.c_int32), ("b_exgr", C.c_int32),
+        ("lw", C.c_int32), ("up", C.c_int32), ("skl_cap", C.c_int32), ("n_imd", C.c_int32),
+    ]
+
+
+# SGPT6 (src/codepot.h:34-43): 6 shorts + 2 chars
+SGPT6_DTYPE = np.dtype([("sig5", "<i2"), ("sig3", "<i2"), ("sigS", "<i2"), ("sigT", "<i2"),
+                        ("sigE", "<i2"), ("sigI", "<i2"), ("phs5", "i1"), ("phs3", "i1")])
+assert SGPT6_DTYPE.itemsize == 14
+
+
+def sgpt6_from_table(tab) -> np.ndarray:
+    """(n, 8) int16 table (sig5, sig3, sigS, sigT, sigE, sigI, phs5, phs3) -> SGPT6 records"""
+    tab = np.asarray(tab)
+    out = np.zeros(len(tab), SGPT6_DTYPE)
+    for i, k in enumerate(("sig5", "sig3", "sigS", "sigT", "sigE", "sigI", "phs5", "phs3")):
+        out[k] = tab[:, i]
+    return out
+
+
 _lib = None
 
 
@@ -102,6 +141,18 @@ def load():
     lib.gspaln_version.restype = C.c_char_p
     lib.gspaln_task_cells.argtypes = [C.POINTER(GspalnTask)]
     lib.gspaln_task_cells.restype = C.c_int64
+    lib.gspaln_h_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(GspalnHParams), C.c_int]
+    lib.gspaln_h_destroy.argtypes = [C.c_void_p]
+    lib.gspaln_h_destroy.restype = None
+    lib.gspaln_h_submit.argtypes = [C.c_void_p, C.POINTER(GspalnHTask), C.c_int, C.POINTER(GspalnResult)]
+    lib.gspaln_h_upload.argtypes = [C.c_void_p, C.POINTER(GspalnHTask), C.c_int]
+    lib.gspaln_h_run.argtypes = [C.c_void_p]
+    lib.gspaln_h_download.argtypes = [C.c_void_p, C.POINTER(GspalnResult)]
+    lib.gspaln_h_get_timing.argtypes = [C.c_void_p, C.POINTER(GspalnTiming)]
+    lib.gspaln_h_last_error.argtypes = [C.c_void_p]
+    lib.gspaln_h_last_error.restype = C.c_char_p
+    lib.gspaln_h_task_cells.argtypes = [C.POINTER(GspalnHTask)]
+    lib.gspaln_h_task_cells.restype = C.c_int64
     _lib = lib
     return lib
 
@@ -126,6 +177,27 @@ def make_params(p: dict) -> GspalnParams:
     gp.gappen1 = int(p["GapPenalty1"])
     sim = np.asarray(p["simmtx"], np.int32).reshape(d, d)
     flat = sim.ravel()
+    for i in range(d * d):
+        gp.simmtx[i] = int(flat[i])
+    return gp
+
+
+def make_h_params(p: dict) -> GspalnHParams:
+    """protein x genome parameter set; p uses the reference's names (PwdB / IntronPrm / algmode)"""
+    gp = GspalnHParams()
+    gp.gop, gp.gep = int(p["BasicGOP"]), int(p["BasicGEP"])
+    gp.lgep, gp.codonk1 = int(p["LongGEP"]), int(p["codonk1"])
+    gp.gw1, gp.gw2, gp.gw3 = int(p["GapW1"]), int(p["GapW2"]), int(p["GapW3"])
+    gp.ipen, gp.llmt, gp.nquant = int(p["GapWI"]), int(p["llmt"]), int(p["nquant"])
+    for j in range(gp.nquant):
+        gp.quant_len[j] = int(p["quant_len"][j])
+        gp.quant_pen[j] = int(p["quant_pen"][j])
+    gp.avmch = int(p["avmch"])
+    gp.lcl = int(p["lcl"])
+    gp.spj = int(p.get("spj", 1))
+    d = int(p["simdim"])
+    gp.simdim = d
+    flat = np.asarray(p["simmtx"], np.int32).reshape(d, d).ravel()
     for i in range(d * d):
         gp.simmtx[i] = int(flat[i])
     return gp

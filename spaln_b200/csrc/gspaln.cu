@@ -8,6 +8,7 @@
 #include "../../include/gspaln.h"
 #include "gspaln_kernels.cuh"
 #include "gspaln_udh.cuh"
+#include "gspaln_host.hpp"
 
 #include <algorithm>
 #include <climits>
@@ -21,46 +22,6 @@
 #include <vector>
 
 using namespace gspaln;
-
-namespace {
-
-template <typename T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t n)
-    {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = n + n / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-template <typename T>
-struct PinBuf {
-    T* p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t n)
-    {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        size_t want = n + n / 8 + 256;
-        cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
-
-inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-}   // namespace
 
 struct gspaln_ctx {
     int device = 0;

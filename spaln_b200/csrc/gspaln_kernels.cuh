@@ -432,7 +432,7 @@ struct TraceView {
 };
 
 // Anti_rhomb_coord<CHAR>::traceback + go_back (src/rhomb_coord.h:142-235), step = 1
-__device__ int walk_trace(const DevTask& t, const unsigned char* trace, int m_abs, int n_abs,
+static __device__ int walk_trace(const DevTask& t, const unsigned char* trace, int m_abs, int n_abs,
                           int2* skl, int cap, int* status)
 {
     TraceView tv{&t, trace, t.up - t.lw + 3};

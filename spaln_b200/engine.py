@@ -246,3 +246,139 @@ class Engine:
         self.lib.gspaln_get_timing(self._h, C.byref(t))
         return Timing(t.h2d_ms, t.kernel_ms, t.d2h_ms, t.launches, t.h2d_bytes, t.d2h_bytes,
                       t.trace_bytes, t.cells)
+
+
+# ---------------------------------------------------------------------------
+# protein query x genomic segment (SimdAln2h1, src/fwd2h1_simd.h:69-382)
+# ---------------------------------------------------------------------------
+@dataclass
+class ProblemH:
+    a: np.ndarray           # uint8 amino-acid codes, a[i] == *Seq::at(i)
+    b: np.ndarray           # uint8 tron codes of the genomic segment
+    sgpt6: np.ndarray       # SGPT6 records (capi.SGPT6_DTYPE) by column n in [0, b_len + 1]
+    b_len: int
+    a_left: int
+    a_right: int
+    b_left: int
+    b_right: int
+    lw: int
+    up: int
+    a_exgl: int = 1
+    a_exgr: int = 1
+    b_exgl: int = 1
+    b_exgr: int = 1
+    skl_cap: int = 0
+
+    @staticmethod
+    def from_export(ex: dict, lw: int, up: int) -> "ProblemH":
+        """ex: tests/ref_harness.py::RefTask.export_p() layout (arrays start at at(-1))."""
+        return ProblemH(a=np.ascontiguousarray(ex["a"][1:], np.uint8),
+                        b=np.ascontiguousarray(ex["b"][1:], np.uint8),
+                        sgpt6=capi.sgpt6_from_table(ex["sgpt6"]), b_len=int(ex["blen"]),
+                        a_left=ex["a_left"], a_right=ex["a_right"],
+                        b_left=ex["b_left"], b_right=ex["b_right"], lw=lw, up=up,
+                        a_exgl=ex["a_exgl"], a_exgr=ex["a_exgr"],
+                        b_exgl=ex["b_exgl"], b_exgr=ex["b_exgr"])
+
+
+class EngineH:
+    """Protein x genome engine: `forwardH1_wip(problems)` == one SimdAln2h1 construction +
+    forwardH1_wip(mfd) per problem (src/fwd2h1_wip_simd.h:50-336), batched on the GPU."""
+
+    def __init__(self, params: dict, device: int = 0):
+        self.lib = capi.load()
+        self._gp = capi.make_h_params(params)
+        self._h = C.c_void_p()
+        rc = self.lib.gspaln_h_create(C.byref(self._h), C.byref(self._gp), device)
+        if rc != 0:
+            raise EngineError(f"gspaln_h_create failed ({rc}): no usable CUDA device or bad "
+                              "parameters; the DP engine has no CPU fallback")
+        self.device = device
+        self._tasks = None
+        self._keep = None
+        self._n = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.gspaln_h_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _pack(self, problems, kind):
+        n = len(problems)
+        arr = (capi.GspalnHTask * max(n, 1))()
+        keep = []
+        for i, p in enumerate(problems):
+            a = np.ascontiguousarray(p.a, np.uint8)
+            b = np.ascontiguousarray(p.b, np.uint8)
+            sg = np.ascontiguousarray(p.sgpt6, capi.SGPT6_DTYPE)
+            if len(a) < p.a_right or len(b) < p.b_right or p.b_len < p.b_right or len(sg) < p.b_len + 2:
+                raise ValueError("problem arrays shorter than the stated ranges")
+            keep.append((a, b, sg))
+            t = arr[i]
+            t.kind = kind
+            t.a, t.b, t.sg = a.ctypes.data, b.ctypes.data, sg.ctypes.data
+            t.b_len = int(p.b_len)
+            t.a_left, t.a_right, t.b_left, t.b_right = p.a_left, p.a_right, p.b_left, p.b_right
+            t.a_exgl, t.a_exgr, t.b_exgl, t.b_exgr = p.a_exgl, p.a_exgr, p.b_exgl, p.b_exgr
+            t.lw, t.up = p.lw, p.up
+            cap = p.skl_cap or ((p.a_right - p.a_left) + (p.b_right - p.b_left) + 8)
+            t.skl_cap = cap if kind == capi.FORWARD_WIP else 0
+        return arr, keep
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.gspaln_h_last_error(self._h)
+            raise EngineError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def _results(self, n, arr):
+        res = (capi.GspalnResult * max(n, 1))()
+        bufs = []
+        for i in range(n):
+            cap = arr[i].skl_cap
+            buf = np.zeros((max(cap, 1), 2), np.int32)
+            bufs.append(buf)
+            res[i].skl = buf.ctypes.data if cap > 0 else None
+        return res, bufs
+
+    def _collect(self, n, res, bufs, arr):
+        return [Result(int(res[i].score), int(res[i].status),
+                       bufs[i][:max(min(res[i].n_skl, arr[i].skl_cap), 0)].copy(), int(res[i].cells))
+                for i in range(n)]
+
+    def submit(self, problems, kind=capi.FORWARD_WIP):
+        arr, keep = self._pack(problems, kind)
+        n = len(problems)
+        res, bufs = self._results(n, arr)
+        self._check(self.lib.gspaln_h_submit(self._h, arr, n, res), "gspaln_h_submit")
+        self._n = n
+        return self._collect(n, res, bufs, arr)
+
+    def forwardH1_wip(self, problems, trace=True):
+        """trace=False == forwardH1_wip(0) as HomScoreH_ng calls it (score only)"""
+        return self.submit(problems, capi.FORWARD_WIP if trace else capi.SCOREONLY_WIP)
+
+    def upload(self, problems, kind=capi.FORWARD_WIP):
+        arr, keep = self._pack(problems, kind)
+        self._check(self.lib.gspaln_h_upload(self._h, arr, len(problems)), "gspaln_h_upload")
+        self._tasks, self._keep, self._n = arr, keep, len(problems)
+
+    def run(self):
+        self._check(self.lib.gspaln_h_run(self._h), "gspaln_h_run")
+
+    def download(self):
+        n = self._n
+        res, bufs = self._results(n, self._tasks)
+        self._check(self.lib.gspaln_h_download(self._h, res), "gspaln_h_download")
+        return self._collect(n, res, bufs, self._tasks)
+
+    def timing(self) -> Timing:
+        t = capi.GspalnTiming()
+        self.lib.gspaln_h_get_timing(self._h, C.byref(t))
+        return Timing(t.h2d_ms, t.kernel_ms, t.d2h_ms, t.launches, t.h2d_bytes, t.d2h_bytes,
+                      t.trace_bytes, t.cells)

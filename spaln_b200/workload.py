@@ -251,3 +251,110 @@ def plant_protein_gene(rng, plen_range=(100, 400), n_exons=None, flank=(100, 600
     for j in rng.choice(len(q), size=nsub, replace=False):
         q[int(j)] = _AA_LETTERS[int(rng.integers(0, 20))]
     return "".join(parts), "".join(q), truth
+
+
+# residue codes of the reference (measured through oracle/_ref, see tests/tools): amino acids
+# (Seq code set of a protein) and "tron" codes = translated codon centred on a nucleotide
+# (Seq::nuc2tron, src/seq.cc:774-798); 23 = Ser (AGY), 24 = TGA, 25 = TAA / TAG
+AA_CODE = {'A': 3, 'C': 7, 'D': 6, 'E': 9, 'F': 16, 'G': 10, 'H': 11, 'I': 12, 'K': 14, 'L': 13,
+           'M': 15, 'N': 5, 'P': 17, 'Q': 8, 'R': 4, 'S': 18, 'T': 19, 'V': 22, 'W': 20, 'Y': 21}
+_TRON_AMB = 2
+_NT = {"A": 0, "C": 1, "G": 2, "T": 3}
+_TRON_TAB = np.zeros(64, np.uint8)
+for _i, _aa in enumerate(_AAS):
+    _cod = _BASES[_i // 16] + _BASES[(_i // 4) % 4] + _BASES[_i % 4]
+    _ix = _NT[_cod[0]] * 16 + _NT[_cod[1]] * 4 + _NT[_cod[2]]
+    if _aa == "*":
+        _TRON_TAB[_ix] = 24 if _cod == "TGA" else 25
+    elif _cod in ("AGC", "AGT"):
+        _TRON_TAB[_ix] = 23
+    else:
+        _TRON_TAB[_ix] = AA_CODE[_aa]
+
+
+def encode_protein(q: str) -> np.ndarray:
+    return np.array([AA_CODE[c] for c in q], np.uint8)
+
+
+def nuc2tron(g: str) -> np.ndarray:
+    """tron code of at(i) = translation of the codon (i-1, i, i+1); the two ends are ambiguous"""
+    v = np.array([_NT[c] for c in g], np.int64)
+    out = np.full(len(g), _TRON_AMB, np.uint8)
+    if len(g) >= 3:
+        out[1:-1] = _TRON_TAB[v[:-2] * 16 + v[1:-1] * 4 + v[2:]]
+    return out
+
+
+def stripe31(a_left, a_right, b_left, b_right, sh=100):
+    """stripe31() of the reference (src/aln2.cc:178-199), cmode 0"""
+    if sh < 0:
+        sh = -sh * min(a_right - a_left, b_right - b_left) // 100
+    sh *= 3
+    up = b_right - 3 * a_right
+    lw = b_left - 3 * a_left
+    if up < lw:
+        up, lw = lw, up
+    up += sh
+    lw -= sh
+    up = min(up, b_right - 3 * a_left)
+    lw = max(lw, b_left - 3 * a_right)
+    return int(lw), int(up)
+
+
+def synthetic_sgpt6(g: str, tron: np.ndarray, rng) -> np.ndarray:
+    """(len + 2, 8) int16 table in the layout of Exinon::data_p (sig5, sig3, sigS, sigT, sigE,
+    sigI, phs5, phs3), dinucleotide / codon driven with the magnitudes of the reference's
+    Dictyostelium tables: GT / AG sites score around +60, background around -520; phs5 / phs3
+    mark the three columns around a site (phase -1 / 0 / +1, 2 = both -1 and +1)."""
+    n = len(g)
+    gb = np.frombuffer(g.encode(), np.uint8)
+    t = np.zeros((n + 2, 8), np.int16)
+    t[:, 0] = rng.normal(-520, 60, n + 2).astype(np.int16)
+    t[:, 1] = rng.normal(-520, 60, n + 2).astype(np.int16)
+    t[:, 2] = rng.normal(-650, 90, n + 2).astype(np.int16)
+    t[:, 3] = -1360
+    t[:, 4] = rng.normal(0, 8, n + 2).astype(np.int16)
+    t[:, 6] = -2
+    t[:, 7] = -2
+    is_gt = np.zeros(n + 2, bool)
+    is_ag = np.zeros(n + 2, bool)
+    # donor boundary at column i: intron starts with nt at(i), at(i + 1) == "GT"
+    is_gt[:n - 1] = (gb[:-1] == ord("G")) & (gb[1:] == ord("T"))
+    # acceptor boundary at column i: intron ends with nt at(i - 2), at(i - 1) == "AG"
+    is_ag[2:n + 1] = (gb[:-1] == ord("A")) & (gb[1:] == ord("G"))
+    t[is_gt, 0] = rng.normal(60, 25, int(is_gt.sum())).astype(np.int16)
+    t[is_ag, 1] = rng.normal(50, 25, int(is_ag.sum())).astype(np.int16)
+    for col, site in ((6, is_gt), (7, is_ag)):
+        idx = np.nonzero(site)[0]
+        ph = np.full(n + 2, -2, np.int16)
+        for d in (-1, 0, 1):            # column c = i + d sees the site at phase d
+            c = idx + d
+            c = c[(c >= 0) & (c <= n + 1)]
+            both = ph[c] != -2
+            ph[c[~both]] = d
+            # a column already marked (phase -1 then +1 from two sites) becomes "both"
+            ph[c[both]] = np.where((ph[c[both]] == -1) & (d == 1), 2, ph[c[both]])
+        t[:, col] = ph
+    # start / stop signals on the codon that ends at column c (tron code of at(c - 2))
+    tr = np.concatenate([[_TRON_AMB, _TRON_AMB], tron, [_TRON_AMB]])[:n + 2]    # tr[c] = tron(at(c - 2))
+    t[tr == AA_CODE["M"], 2] = rng.normal(200, 40, int((tr == AA_CODE["M"]).sum())).astype(np.int16)
+    stop = tr >= 24
+    t[stop, 3] = rng.normal(320, 20, int(stop.sum())).astype(np.int16)
+    return t
+
+
+def protein_problem(rng, plen_range=(100, 400), flank=(100, 600), sh=100, intron_scale=1.0,
+                    n_exons=None):
+    """one protein x genomic-segment DP problem in the layout of tests/golden (arrays start at
+    at(-1)) with a synthetic SGPT6 table"""
+    g, q, _ = plant_protein_gene(rng, plen_range=plen_range, flank=flank, intron_scale=intron_scale,
+                                 n_exons=n_exons)
+    a = encode_protein(q)
+    b = nuc2tron(g)
+    sg = synthetic_sgpt6(g, b, rng)
+    lw, up = stripe31(0, len(a), 0, len(b), sh)
+    return {"a": np.concatenate([[0], a, [0]]).astype(np.uint8),
+            "b": np.concatenate([[_TRON_AMB], b, [_TRON_AMB]]).astype(np.uint8),
+            "sgpt6": sg, "blen": len(b), "a_left": 0, "a_right": len(a), "b_left": 0,
+            "b_right": len(b), "a_exgl": 1, "a_exgr": 1, "b_exgl": 1, "b_exgr": 1,
+            "lw": lw, "up": up, "genome": g, "query": q}

@@ -75,6 +75,7 @@ class Reference:
                                        C.c_void_p, C.c_void_p, C.c_int]
         L.ref_task_export_p.argtypes = [C.c_void_p] * 4
         L.ref_get_params_p.argtypes = [C.c_void_p, C.c_int]
+        L.ref_task_inject_p.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_task_kernel_p.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_void_p]
         L.ref_task_stripe31.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -177,6 +178,11 @@ class RefTask:
         self.lib.ref_task_export_p(self.h, a.ctypes.data, b.ctypes.data, g.ctypes.data)
         i.update(a=a, b=b, sgpt6=g)
         return i
+
+    def inject_p(self, sgpt6):
+        g = np.ascontiguousarray(sgpt6, np.int16)
+        assert g.shape == (self.info()["blen"] + 2, 8)
+        self.lib.ref_task_inject_p(self.h, g.ctypes.data)
 
     def stripe31(self, sh: int):
         b = np.zeros(3, np.int32)
