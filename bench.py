@@ -171,6 +171,151 @@ def reference_run(raw, steps, warmup, threads, lsp=False):
     return times, cells, out
 
 
+# ---------------------------------------------------------------------------
+# protein x genome leg (BASELINE.json configs[2] shape: proteins of 300-800 aa against their
+# genomic loci); secondary report next to the headline config-2 numbers
+# ---------------------------------------------------------------------------
+PROT_FIXTURE = "prot_A2_global"
+PROT_REF_OPTS = "-Q0 -A2 -yX0 -TDictyost"
+B_CELL_H = 3.0  # 2 B trace + 16 B band r/w + 16 B column record per (column x 16-row strip), DESIGN.md
+
+
+def make_protein_workload(n, seed):
+    from spaln_b200 import workload
+    rng = np.random.default_rng(seed)
+    return [workload.protein_problem(rng, plen_range=(300, 800), flank=(500, 5000), sh=100)
+            for _ in range(n)]
+
+
+def to_problems_h(raw):
+    from spaln_b200 import ProblemH
+    return [ProblemH.from_export(r, r["lw"], r["up"]) for r in raw]
+
+
+def protein_reference_child(nsample, seed, threads, out_path):
+    """runs in its own process (the reference keeps one option string per process): times
+    SimdAln2h1::forwardH1_wip on the first `nsample` problems of the protein workload"""
+    import ref_harness as R
+    if not R.available():
+        Path(out_path).write_text(json.dumps({"unavailable": "oracle/_ref not built"}))
+        return 0
+    import golden_io
+    import oracle_harness as O
+    raw_all = make_protein_workload(nsample, seed)
+    # fhlastH1 of the reference can return a start point right of b_right (its last-column scan
+    # moves mx but not maxr, src/fwd2h1_simd.h:764-788) and then walks outside its trace buffer
+    # (segfault).  Such problems are screened out of the CPU sample with the oracle, which stops
+    # there; the GPU arm keeps them (and reports the same lone corner).
+    prm, _ = golden_io.load_protein(PROT_FIXTURE)
+    keep = [i for i, r in enumerate(raw_all)
+            if O.forward_h1_wip(prm, r)["skl"][0][1] <= r["b_right"]]
+    raw = [raw_all[i] for i in keep]
+    nsample = len(raw)
+    ref = R.Reference(PROT_REF_OPTS, protein=True)
+    tasks = []
+    for r in raw:
+        t = ref.task(r["genome"], r["query"])
+        ex = t.export_p()
+        assert np.array_equal(ex["a"][1:-1], r["a"][1:-1]) and np.array_equal(ex["b"], r["b"])
+        t.inject_p(r["sgpt6"])
+        tasks.append(t)
+    out = [None] * nsample
+
+    def work(tid):
+        for i in range(tid, nsample, threads):
+            out[i] = tasks[i].kernel_p(raw[i]["lw"], raw[i]["up"], 0, cap=4096)
+
+    times = []
+    for s in range(2):
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+        [x.start() for x in th]
+        [x.join() for x in th]
+        times.append(time.perf_counter() - t0)
+    Path(out_path).write_text(json.dumps({
+        "seconds": times[-1], "index": keep, "scores": [int(o["score"]) for o in out],
+        "skl": [o["skl"].tolist() for o in out]}))
+    return 0
+
+
+def host_cells_h(raw):
+    import ctypes as C
+    from spaln_b200 import capi
+    lib = capi.load()
+    for r in raw:
+        t = capi.GspalnHTask()
+        t.a_left, t.a_right, t.b_left, t.b_right = r["a_left"], r["a_right"], r["b_left"], r["b_right"]
+        t.lw, t.up = r["lw"], r["up"]
+        r["cells"] = int(lib.gspaln_h_task_cells(C.byref(t)))
+
+
+def protein_leg(args, local_rank, rank, ncores, barrier, with_cpu):
+    from spaln_b200 import EngineH
+    import golden_io
+    prm, _ = golden_io.load_protein(PROT_FIXTURE)
+    seed = 20251017 + 104729 * rank
+    raw = make_protein_workload(args.protein_queries, seed)
+    host_cells_h(raw)
+    probs = to_problems_h(raw)
+    cells = sum(r["cells"] for r in raw)
+    eng = EngineH(prm, device=local_rank)
+    eng.upload(probs)
+    eng.run()
+    barrier()
+    ks = []
+    for _ in range(2):
+        eng.run()
+        ks.append(eng.timing().kernel_ms)
+    res = eng.download()
+    k_ms = float(np.mean(ks))
+    barrier()
+    t0 = time.perf_counter()
+    eng.submit(probs)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    tm = eng.timing()
+    peak, _ = measured_peak()
+    leg = {"note": "SimdAln2h1::forwardH1_wip semantics (score + corners), proteins 300-800 aa x genomic "
+                   "locus (+-0.5-5 kb), band = stripe31(sh=100), synthetic SGPT6 table; this rank",
+           "queries": args.protein_queries, "cells": cells, "kernel_ms": k_ms,
+           "gcups": cells / (k_ms * 1e-3) / 1e9, "queries_per_s": args.protein_queries / (k_ms * 1e-3),
+           "e2e_gcups": cells / e2e_s / 1e9, "e2e_ms": 1e3 * e2e_s,
+           "h2d_bytes": int(tm.h2d_bytes), "d2h_bytes": int(tm.d2h_bytes),
+           "status_nonzero": sum(1 for r in res if r.status != 0),
+           "roofline": {"bound": "hbm", "bytes_per_cell": B_CELL_H, "unit": "GB/s",
+                        "achieved": cells * B_CELL_H / (k_ms * 1e-3) / 1e9, "peak": peak,
+                        "frac": cells * B_CELL_H / (k_ms * 1e-3) / 1e9 / peak, "kernel": "dp_h1_kernel<true>"}}
+    if with_cpu:
+        nsample = min(args.cpu_sample, len(raw))
+        tmp = ROOT / "gpurun_out"
+        tmp.mkdir(exist_ok=True)
+        outp = tmp / f"_prot_ref_{os.getpid()}.json"
+        try:
+            subprocess.run([sys.executable, str(ROOT / "bench.py"), "--leg", "protein-cpu", "--cpu-sample",
+                            str(nsample), "--leg-seed", str(seed), "--leg-out", str(outp)],
+                           check=True, timeout=900)
+            r = json.loads(outp.read_text())
+            outp.unlink()
+        except Exception as e:      # the report line must still be printed
+            r = {"unavailable": repr(e)}
+        if "seconds" in r:
+            idx = r["index"]
+            sc = sum(raw[i]["cells"] for i in idx)
+            mism = sum(1 for k, i in enumerate(idx)
+                       if r["scores"][k] != res[i].score or
+                       not np.array_equal(np.array(r["skl"][k], np.int32).reshape(-1, 2), res[i].skl))
+            leg["cpu_baseline"] = {"value": sc / r["seconds"] / 1e9, "unit": "GCUPS", "cores": ncores,
+                                   "kind": "reference",
+                                   "sample": f"{len(idx)} of the first {nsample} problems ({sc / 1e6:.0f} Mcells; the rest "
+                                             "crash the reference: start point outside its trace buffer), "
+                                             f"SimdAln2h1::forwardH1_wip AVX2 build, {ncores} threads",
+                                   "parity_mismatches_on_sample": mism}
+        else:
+            leg["cpu_baseline"] = r
+    eng.close()
+    return leg
+
+
 def host_cells(raw):
     import ctypes as C
     from spaln_b200 import capi
@@ -191,7 +336,14 @@ def main():
     ap.add_argument("--queries", type=int, default=10000, help="queries per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=32, help="problems in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--protein-queries", type=int, default=3000,
+                    help="problems of the protein x genome leg per GPU (0 = skip the leg)")
+    ap.add_argument("--leg", default="", help=argparse.SUPPRESS)
+    ap.add_argument("--leg-seed", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--leg-out", default="", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.leg == "protein-cpu":
+        return protein_reference_child(args.cpu_sample, args.leg_seed, os.cpu_count() or 1, args.leg_out)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -299,6 +451,25 @@ def main():
     tm3 = eng.timing()
     lsp_bad = sum(1 for r in res3 if r.status != 0)
 
+    # ---- multi-GPU only: the final gather of the hit records (score + corners per query) to
+    # rank 0 -- the one collective of the query-sharded job, outside the DP timing
+    gather_ms = None
+    if world > 1:
+        from spaln_b200 import shard
+        barrier()
+        t0 = time.perf_counter()
+        hits = shard.gather_hits(np.arange(len(res)) * world + rank, [r.score for r in res],
+                                 [r.skl for r in res], dst=0, device=torch.device("cuda", local_rank))
+        barrier()
+        gather_ms = 1e3 * (time.perf_counter() - t0)
+        if rank == 0:
+            assert len(hits) == len(res) * world
+
+    prot = None
+    if args.protein_queries > 0:
+        prot = protein_leg(args, local_rank, rank, ncores, barrier,
+                           with_cpu=(n_gpus == 1 and not args.no_cpu_baseline))
+
     if world > 1:
         t = torch.tensor([dev_s, wall, e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -349,6 +520,10 @@ def main():
                          "kernel_ms": tm3.kernel_ms, "total_ms": 1e3 * lsp_s, "launches": tm3.launches,
                          "device_cells": tm3.cells, "status_nonzero": lsp_bad},
         }
+        if prot is not None:
+            line["protein_path"] = prot
+        if gather_ms is not None:
+            line["gather_hits_ms"] = gather_ms
         if n_gpus == 1 and not args.no_cpu_baseline:
             nsample = min(args.cpu_sample, len(raw))
             sample = raw[:nsample]

@@ -184,14 +184,22 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
         re.s5[2] = (s && (fl & 32u)) ? hi16(ci.z) : SIG_NONE;
         return re;
     };
+    // Bank-conflict-free ring: the four threads of a strip read slots 12 apart (3 columns x 4
+    // rows) = 384 B = the same banks; XOR-ing the low two slot bits with the next two spreads
+    // them over all four 32-byte bank groups, and odd strips store the two 16-byte halves
+    // swapped so that the 8 strips of the warp fill both halves of every group.
+    const int hswap = (sidx & 1) * 16;
+    auto ring_addr = [&](int c) -> char* {
+        const int sl = c & (RINGH - 1);
+        return reinterpret_cast<char*>(ring) + ((sl ^ ((sl >> 2) & 3)) * (int) sizeof(RingH));
+    };
     auto ring_store = [&](int c, const RingH& re) {
-        int4* dst = reinterpret_cast<int4*>(ring + (c & (RINGH - 1)));
-        dst[0] = make_int4(re.s3[0], re.s3[1], re.s3[2], re.prof);
-        dst[1] = make_int4(re.s5[0], re.s5[1], re.s5[2], re.cv);
+        char* dst = ring_addr(c);
+        *reinterpret_cast<int4*>(dst + hswap) = make_int4(re.s3[0], re.s3[1], re.s3[2], re.prof);
+        *reinterpret_cast<int4*>(dst + (16 - hswap)) = make_int4(re.s5[0], re.s5[1], re.s5[2], re.cv);
     };
 
     unsigned nxt_band = 0;
-    uint4 nxt_col = make_uint4(0u, 0u, 0u, (unsigned) ZROW << 16);
 
     for (int i = -1; i < niter; ++i) {
         const int j = i - off;
@@ -212,12 +220,17 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
                 ring_store(c, col_decode(col_fetch(c), false));
             }
             if (sub == 0) ring_store(g.n_start, col_decode(col_fetch(g.n_start), true));
-            nxt_col = col_fetch(g.n_start + 1);
         } else if (live && j >= 0 && j < nsteps) {
             const int n = g.n_start + j;
             const unsigned cur_band = nxt_band;
-            if (sub == 0 && j + 1 < nsteps) nxt_band = __ldcg(band + (n + 1 - band_bias));
-            const int slot = n & (RINGH - 1);
+            // both global loads of the iteration are issued here, a whole step ahead of their
+            // use: __syncwarp() at the bottom waits for outstanding loads
+            const bool feed = sub == 0 && j + 1 < nsteps;
+            uint4 nxt_col = make_uint4(0u, 0u, 0u, (unsigned) ZROW << 16);
+            if (feed) {
+                nxt_band = __ldcg(band + (n + 1 - band_bias));
+                nxt_col = col_fetch(n + 1);
+            }
             int u3, uf;
             if (sub == 0) { u3 = lo16(cur_band); uf = hi16(cur_band); }
             else { u3 = sh_h; uf = sh_f; }
@@ -226,7 +239,7 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
             int liftv = -32768;
             const int2* pen_base = sm.pen + (pen_cap + 1);
             if (SPJ) {
-                const int4 c0 = *reinterpret_cast<const int4*>(ring + slot);
+                const int4 c0 = *reinterpret_cast<const int4*>(ring_addr(n) + hswap);
                 const int has = max(max(c0.x, c0.y), c0.z) > SIG_NONE / 2 ? 1 : 0;
                 const int m = ((am0 << 1) | has) & 0xffff;
                 am0 = am1; am1 = am2; am2 = m;
@@ -237,9 +250,9 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
             int sv = INT_MIN, sk = 0;
 #pragma unroll
             for (int k = NRH - 1; k >= 0; --k) {
-                const int4* rp = reinterpret_cast<const int4*>(ring + ((slot - 3 * (row0 + k)) & (RINGH - 1)));
-                const int4 ra = rp[0];          // s3[0..2], prof
-                const int4 rb = rp[1];          // s5[0..2], cv
+                const char* rp = ring_addr(n - 3 * (row0 + k));
+                const int4 ra = *reinterpret_cast<const int4*>(rp + hswap);         // s3[0..2], prof
+                const int4 rb = *reinterpret_cast<const int4*>(rp + (16 - hswap));  // s5[0..2], cv
                 const int cv = rb.w;
                 const int U3 = k ? H[2][k ? k - 1 : 0] : u3;
                 const int U4 = k ? H[3][k ? k - 1 : 0] : up4;
@@ -342,10 +355,7 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
                     __stcg(band + (r0 - t.lw + 3), pack16(out_h, out_f));
             }
             // next column -> ring (read from the next iteration on)
-            if (sub == 0 && j + 1 < nsteps) {
-                ring_store(n + 1, col_decode(nxt_col, true));
-                nxt_col = col_fetch(n + 2);
-            }
+            if (feed) ring_store(n + 1, col_decode(nxt_col, true));
         }
         __syncwarp();
     }
@@ -475,7 +485,10 @@ __device__ __forceinline__ int gap_ext_pen3(const DevParamsH& P, int i) { return
 // persistent kernel: each warp pulls problems from a global ticket counter
 // ---------------------------------------------------------------------------
 template <bool TRACE, bool LOCAL, bool SPJ>
-__global__ void __launch_bounds__(CTA_THREADS, 2)
+#ifndef GSPALN_H1_MINB
+#define GSPALN_H1_MINB 3
+#endif
+__global__ void __launch_bounds__(CTA_THREADS, GSPALN_H1_MINB)
 dp_h1_kernel(const DevParamsH* __restrict__ gP, const int2* __restrict__ gpen,
              const DevTaskH* __restrict__ tasks, const int* __restrict__ order, int ntasks, int* ticket,
              const unsigned char* __restrict__ apool, const ColH* __restrict__ cpool,

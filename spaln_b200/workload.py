@@ -277,11 +277,16 @@ def encode_protein(q: str) -> np.ndarray:
 
 
 def nuc2tron(g: str) -> np.ndarray:
-    """tron code of at(i) = translation of the codon (i-1, i, i+1); the two ends are ambiguous"""
+    """tron code of at(i) = translation of the codon (i-1, i, i+1).  The ends follow
+    nuc2tron3 (src/utilseq.cc:204-224) as measured through oracle/_ref: at(0) has no first
+    nucleotide (most abundant residue for its middle one), at(len - 1) reads a NUL third
+    nucleotide (== A)."""
     v = np.array([_NT[c] for c in g], np.int64)
     out = np.full(len(g), _TRON_AMB, np.uint8)
     if len(g) >= 3:
         out[1:-1] = _TRON_TAB[v[:-2] * 16 + v[1:-1] * 4 + v[2:]]
+        out[0] = (14, 3, 10, 13)[v[0]]
+        out[-1] = _TRON_TAB[v[-2] * 16 + v[-1] * 4 + 0]
     return out
 
 
@@ -354,7 +359,7 @@ def protein_problem(rng, plen_range=(100, 400), flank=(100, 600), sh=100, intron
     sg = synthetic_sgpt6(g, b, rng)
     lw, up = stripe31(0, len(a), 0, len(b), sh)
     return {"a": np.concatenate([[0], a, [0]]).astype(np.uint8),
-            "b": np.concatenate([[_TRON_AMB], b, [_TRON_AMB]]).astype(np.uint8),
+            "b": np.concatenate([[0], b, [0]]).astype(np.uint8),
             "sgpt6": sg, "blen": len(b), "a_left": 0, "a_right": len(a), "b_left": 0,
             "b_right": len(b), "a_exgl": 1, "a_exgr": 1, "b_exgl": 1, "b_exgr": 1,
             "lw": lw, "up": up, "genome": g, "query": q}

@@ -1,0 +1,74 @@
+"""CPU, world_size 2 over gloo: the query-shard plumbing of the multi-GPU path
+(spaln_b200/shard.py) -- cell-balanced partition, genome broadcast, two-phase gather of
+variable-size hit records.  The DP itself needs a GPU; a deterministic stand-in produces the
+per-problem records here."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_hit(i):
+    rng = np.random.default_rng(i)
+    k = int(rng.integers(0, 9))
+    return int(rng.integers(-500, 5000)), rng.integers(0, 10000, size=(k, 2)).astype(np.int32)
+
+
+def _worker(rank, world, port, n, q):
+    import torch.distributed as dist
+    from spaln_b200 import shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    genome = np.arange(1000, dtype=np.uint8) if rank == 0 else np.zeros(0, np.uint8)
+    g = shard.broadcast_genome(genome)
+    cells = np.random.default_rng(7).integers(100, 100000, size=n)
+    mine = shard.lpt_partition(cells, world)[rank]
+    hits = [_fake_hit(int(i)) for i in mine]
+    out = shard.gather_hits(mine, [h[0] for h in hits], [h[1] for h in hits], dst=0)
+    if rank == 0:
+        ok = len(out) == n and all(out[i][0] == _fake_hit(i)[0] and
+                                   np.array_equal(out[i][1], _fake_hit(i)[1]) for i in range(n))
+        q.put((ok, bool(np.array_equal(g, np.arange(1000, dtype=np.uint8)))))
+    else:
+        assert out is None
+        q.put((True, bool(np.array_equal(g, np.arange(1000, dtype=np.uint8)))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_shard_gather_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 37, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=150) for _ in procs]
+    [p.join(30) for p in procs]
+    assert all(ok and g for ok, g in res)
+    assert all(p.exitcode == 0 for p in procs)
+
+
+def test_lpt_partition_balances_cells():
+    from spaln_b200 import shard
+    cells = np.random.default_rng(1).integers(1000, 10 ** 7, size=500)
+    parts = shard.lpt_partition(cells, 8)
+    assert sorted(np.concatenate(parts).tolist()) == list(range(500))
+    loads = [int(cells[p].sum()) for p in parts]
+    assert max(loads) - min(loads) <= int(cells.max())
+
+
+def test_gather_single_process_passthrough():
+    from spaln_b200 import shard
+    out = shard.gather_hits([3, 5], [10, 20], [np.zeros((2, 2), np.int32), np.zeros((0, 2), np.int32)])
+    assert out[3][0] == 10 and out[3][1].shape == (2, 2) and out[5][1].shape == (0, 2)
