@@ -64,7 +64,8 @@ enum {                          /* gspaln_result.status */
     GSPALN_ST_OK = 0,
     GSPALN_ST_SKL_OVERFLOW = 1, /* more corners than skl_cap: n_skl is the needed count */
     GSPALN_ST_BAD_TRACE = 2,    /* reference would have called fatal("Unexpected dir") */
-    GSPALN_ST_UNSUPPORTED = 3   /* needs a kernel that is not on the device yet */
+    GSPALN_ST_UNSUPPORTED = 3,  /* needs a kernel that is not on the device yet */
+    GSPALN_ST_INTERNAL = 4      /* device-side scheduling guard tripped (a bug: please report) */
 };
 
 /* frozen scoring parameters (reference globals -> one POD) */

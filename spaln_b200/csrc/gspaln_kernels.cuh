@@ -124,7 +124,7 @@ __device__ __forceinline__ StripGeom strip_geom(const DevTask& t, int ml)
     return g;
 }
 
-struct WarpMax { int val, mr, nr; };
+struct WarpMax { int val, mr, nr, err; };
 
 // shared-memory carve-up of one CTA
 struct SmemLayout {
@@ -209,9 +209,13 @@ __device__ __forceinline__ void strip_step(
 }
 
 // ---------------------------------------------------------------------------
-// one pass: strips ml0, ml0+16, ... (nstr <= SPP).  A strip is shared by TPS
-// neighbouring threads (NR rows each) that run in lock step; the lower thread
-// takes the (H, F) of the row above it from its neighbour by warp shuffle.
+// one segment: strips ml0, ml0+16, ... (nstr of them; a segment ends at a
+// re-basing check point or at the last query row).  The warp has SPP strip
+// slots (TPS neighbouring threads each, NR rows per thread, lock step; the
+// lower thread takes the (H, F) of the row above it from its neighbour by warp
+// shuffle).  Slot s runs strips s, s + SPP, s + 2 SPP, ... back to back: a slot
+// that finishes a strip starts its next one as soon as the strip above that one
+// is 15 + LAG steps ahead, so the systolic chain never drains inside a segment.
 // ---------------------------------------------------------------------------
 template <bool TRACE, bool LOCAL, bool SPJ>
 __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
@@ -220,50 +224,43 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
                          unsigned char* trace, int ml0, int nstr, bool localL_now,
                          bool localR, int accscr, WarpMax& wmax)
 {
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int sidx = lane / TPS;                // strip of this thread within the pass
+    const int slot = lane / TPS;                // strip slot of this thread
     const int sub = lane % TPS;                 // which NR-row slice of the strip
     const int row0 = sub * NR;                  // first strip row owned by this thread
-    const StripGeom g = strip_geom<TRACE>(t, ml0 + NELEM * sidx);
-    const int j8 = g.j9 - 1;
-    const int nsteps = g.n_last - g.n_start + 1;
-    const bool live = sidx < nstr && nsteps > 0;
+    const int pred_lane = ((slot + SPP - 1) % SPP) * TPS;
     const int width = t.up - t.lw + 3;
 
-    // Systolic schedule.  Strip s needs, at its step n, the band entry of
-    // column n, which strip s-1 (a full strip) produces at ITS step n + 15.
-    // With step j of strip s executed in iteration j + off_s this requires
-    //   off_s = off_{s-1} + (n_start_s - n_start_{s-1}) + 15 + LAG,
-    // which telescopes to the closed form below.
-    const int n_start0 = __shfl_sync(0xffffffffu, g.n_start, 0);
-    const int off = (g.n_start - n_start0) + (NELEM - 1 + LAG) * sidx;
-    int niter = live ? off + nsteps : 0;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) niter = max(niter, __shfl_xor_sync(0xffffffffu, niter, o));
-    if (niter == 0) return;
+    // current strip of this slot.  Step j of the strip runs in iteration j + off.
+    // Strip s needs, at its step n, the band entry of column n, which strip s-1
+    // (a full strip) produces at ITS step n + 15; hence
+    //   off_s >= off_{s-1} + (n_start_s - n_start_{s-1}) + 15 + LAG.
+    int sidx = slot;                            // strip index inside the segment
+    StripGeom g = strip_geom<TRACE>(t, ml0 + NELEM * min(sidx, nstr - 1));
+    int nsteps = g.n_last - g.n_start + 1;
+    int off = 0;
+    // state: 0 = waiting for the strip above to be scheduled, 1 = scheduled / running,
+    //        2 = no strip left, 3 = scheduled but empty (band outside the matrix)
+    int state = sidx < nstr ? (sidx == 0 ? (nsteps > 0 ? 1 : 3) : 0) : 2;
+    // schedule records of the two strips this slot scheduled last (index, off - n_start): the
+    // slot below needs the record of strip sidx - 1, and this slot can be at most one strip
+    // further by the time it asks
+    int rec_si = sidx == 0 ? 0 : -1000, rec_d = -g.n_start, old_si = -1000, old_d = 0;
 
     int HA[NR], HB[NR], F[NR], E[NR], V2[NR], NJ[NR], arow[NR];
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
-        HA[k] = NEV; HB[k] = NEV; F[k] = NEV; E[k] = NEV; V2[k] = NEV; NJ[k] = 0;
-        // rows beyond the last query residue score 0 (reference: pv_a stays 0)
-        arow[k] = (live && row0 + k < g.j9) ? 4 * (int) aseq[(g.ml - t.a_left) + row0 + k] : 4 * ZROW;
+        HA[k] = NEV; HB[k] = NEV; F[k] = NEV; E[k] = NEV; V2[k] = NEV; NJ[k] = 0; arow[k] = 4 * ZROW;
     }
     const int gn = P.gn, ge = P.ge;
     const int floorL = localL_now ? 0 : INT_MIN;
     int prev_uh = NEV;
-    int bval = INT_MIN, bstep = 0, bk = 0;      // best local-mode cell of this thread
+    int bval = INT_MIN, bstep = 0, bk = 0, bsi = 0;     // best local-mode cell of this thread
 
-    unsigned char* tr_base = TRACE
-        ? trace + ((long long) (sidx + (ml0 - t.a_left) / NELEM) * (width + TRACE_PAD)) * NELEM + row0
-        : nullptr;
-    const int band_bias = g.ml + t.lw - 1;      // band entry of column c (diagonal c - ml): c - band_bias
     RingEntry* ring = sm.ring + threadIdx.x;    // slot s at ring[s * CTA_THREADS]
     const char* mtx_bytes = reinterpret_cast<const char*>(sm.mtx);
     const int ipen = P.ipen;
-    // the thread that holds the strip's last row writes the band buffer
-    const bool owns_bottom = live && j8 >= row0 && j8 < row0 + NR;
-    const int kbot = j8 - row0;
 
     // Column inputs are prefetched RAW one iteration ahead (no dependent ALU
     // work behind the load) and decoded when the column is entered.
@@ -292,19 +289,57 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
     unsigned nxt_band = 0;
     uint2 nxt_col = make_uint2(0u, 0xffffffffu);
 
-    for (int i = -1; i < niter; ++i) {
+    // every strip run one after the other would need fewer iterations than this
+    const int max_iter = nstr * (width + 3 * NELEM + 8) + 64;
+    for (int i = -1; ; ++i) {
+        if (i > max_iter) { wmax.err = 1; break; }      // scheduling bug guard: never spin on the device
+        // scheduling: has the slot above scheduled strip sidx - 1 yet, and for when
+        {
+            const int p_rec_si = __shfl_sync(FULL, rec_si, pred_lane);
+            const int p_rec_d = __shfl_sync(FULL, rec_d, pred_lane);
+            const int p_old_si = __shfl_sync(FULL, old_si, pred_lane);
+            const int p_old_d = __shfl_sync(FULL, old_d, pred_lane);
+            if (state == 0 && (p_rec_si == sidx - 1 || p_old_si == sidx - 1)) {
+                const int pd = p_rec_si == sidx - 1 ? p_rec_d : p_old_d;
+                // the init iteration (j == -1) is this one at the earliest
+                off = max(i + 1, pd + g.n_start + (NELEM - 1 + LAG));
+                old_si = rec_si; old_d = rec_d;
+                rec_si = sidx; rec_d = off - g.n_start;
+                state = nsteps > 0 ? 1 : 3;
+            } else if (state == 3) {
+                // empty strip: nothing to run, this slot's next strip
+                sidx += SPP;
+                if (sidx < nstr) {
+                    g = strip_geom<TRACE>(t, ml0 + NELEM * sidx);
+                    nsteps = g.n_last - g.n_start + 1;
+                    state = 0;
+                } else
+                    state = 2;
+            }
+        }
+        if (!__any_sync(FULL, state != 2)) break;
+        const bool run = state == 1;
         const int j = i - off;
+        const int j8 = g.j9 - 1;
         // neighbour exchange inside a strip: bottom row of the thread above, as
         // of the previous step (every thread of the warp takes part)
         int sh_h = NEV, sh_f = NEV;
         if (TPS > 1) {
-            sh_h = __shfl_up_sync(0xffffffffu, (i & 1) ? HA[NR - 1] : HB[NR - 1], 1);
-            sh_f = __shfl_up_sync(0xffffffffu, F[NR - 1], 1);
+            sh_h = __shfl_up_sync(FULL, (i & 1) ? HA[NR - 1] : HB[NR - 1], 1);
+            sh_f = __shfl_up_sync(FULL, F[NR - 1], 1);
         }
-        if (live && j == -1) {
+        const int band_bias = g.ml + t.lw - 1;      // band entry of column c (diagonal c - ml): c - band_bias
+        if (run && j == -1) {
             // One iteration before the first step: the entries of columns
             // n_start - 1 and n_start are final by now (written >= LAG - 1
             // iterations ago by the strip above).
+#pragma unroll
+            for (int k = 0; k < NR; ++k) {
+                HA[k] = NEV; HB[k] = NEV; F[k] = NEV; E[k] = NEV; V2[k] = NEV; NJ[k] = 0;
+                // rows beyond the last query residue score 0 (reference: pv_a stays 0)
+                arow[k] = (row0 + k < g.j9) ? 4 * (int) aseq[(g.ml - t.a_left) + row0 + k] : 4 * ZROW;
+            }
+            prev_uh = NEV;
             if (sub == 0) {
                 nxt_band = __ldcg(band + (g.n_start - band_bias));
                 prev_uh = lo16(__ldcg(band + (g.n_start - 1 - band_bias)));
@@ -320,7 +355,7 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
                 ring[(c & 15) * CTA_THREADS] = re;
                 ring[((c & 15) + 16) * CTA_THREADS] = re;
             }
-        } else if (live && j >= 0 && j < nsteps) {
+        } else if (run && j >= 0) {
             const int n = g.n_start + j;
             const unsigned cur_band = nxt_band;
             const RingEntry cur_col = col_decode(nxt_col, n, n <= t.b_right);
@@ -328,10 +363,10 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
                 if (sub == 0) nxt_band = __ldcg(band + (n + 1 - band_bias));
                 nxt_col = col_fetch(n + 1);
             }
-            const int slot = n & 15;
-            ring[slot * CTA_THREADS] = cur_col;
-            ring[(slot + 16) * CTA_THREADS] = cur_col;
-            const char* ring_hi = reinterpret_cast<const char*>(ring + (slot + 16 - row0) * CTA_THREADS);
+            const int rslot = n & 15;
+            ring[rslot * CTA_THREADS] = cur_col;
+            ring[(rslot + 16) * CTA_THREADS] = cur_col;
+            const char* ring_hi = reinterpret_cast<const char*>(ring + (rslot + 16 - row0) * CTA_THREADS);
             int up_h, up_f, up_d;
             if (sub == 0) {
                 up_h = lo16(cur_band); up_f = hi16(cur_band);
@@ -359,18 +394,20 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
                         if (row0 + k < g.j9 && hv >= v) { v = hv; kk = k; }
                     }
                 }
-                if (v > bval) { bval = v; bstep = n; bk = row0 + kk; }
+                if (v > bval) { bval = v; bstep = n; bk = row0 + kk; bsi = sidx; }
             }
             if (TRACE) {
+                unsigned char* tr = trace + ((long long) (sidx + (ml0 - t.a_left) / NELEM) * (width + TRACE_PAD) + j) * NELEM + row0;
                 if (NR == 16)
-                    *reinterpret_cast<uint4*>(tr_base + (long long) j * NELEM) = make_uint4(tw[0], tw[1], tw[NR / 4 - 2], tw[NR / 4 - 1]);
+                    *reinterpret_cast<uint4*>(tr) = make_uint4(tw[0], tw[1], tw[NR / 4 - 2], tw[NR / 4 - 1]);
                 else if (NR == 8)
-                    *reinterpret_cast<uint2*>(tr_base + (long long) j * NELEM) = make_uint2(tw[0], tw[NR / 4 - 1]);
+                    *reinterpret_cast<uint2*>(tr) = make_uint2(tw[0], tw[NR / 4 - 1]);
                 else
-                    *reinterpret_cast<unsigned*>(tr_base + (long long) j * NELEM) = tw[0];
+                    *reinterpret_cast<unsigned*>(tr) = tw[0];
             }
             // bottom row of the strip -> band buffer (src/fwd2s1_wip_simd.h:438-442)
-            if (owns_bottom) {
+            if (j8 >= row0 && j8 < row0 + NR) {
+                const int kbot = j8 - row0;
                 int out_h = (i & 1) ? HB[NR - 1] : HA[NR - 1];
                 int out_f = F[NR - 1];
                 if (kbot != NR - 1) {
@@ -383,6 +420,16 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
                 if (cb > t.b_left && r0 >= t.lw && r0 <= t.up)
                     __stcg(band + (r0 - t.lw + 1), pack16(out_h, out_f));
             }
+            if (j == nsteps - 1) {
+                // strip finished: this slot's next strip
+                sidx += SPP;
+                if (sidx < nstr) {
+                    g = strip_geom<TRACE>(t, ml0 + NELEM * sidx);
+                    nsteps = g.n_last - g.n_start + 1;
+                    state = 0;
+                } else
+                    state = 2;
+            }
         } else if (TPS > 1) {
             prev_uh = NEV;      // (inactive) keep the exchange registers defined
         }
@@ -391,14 +438,14 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
 
     if (LOCAL && localR) {
         // reference order: strips ascending, then step, then lane (first max)
-        int bv = (live && bval > INT_MIN) ? bval : INT_MIN;
-        int bs = bstep, bkk = bk, bst = sidx;
+        int bv = bval;
+        int bs = bstep, bkk = bk, bst = bsi;
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
-            const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int os = __shfl_xor_sync(0xffffffffu, bs, o);
-            const int ok = __shfl_xor_sync(0xffffffffu, bkk, o);
-            const int ot = __shfl_xor_sync(0xffffffffu, bst, o);
+            const int ov = __shfl_xor_sync(FULL, bv, o);
+            const int os = __shfl_xor_sync(FULL, bs, o);
+            const int ok = __shfl_xor_sync(FULL, bkk, o);
+            const int ot = __shfl_xor_sync(FULL, bst, o);
             const bool take = ov > bv || (ov == bv && (ot < bst || (ot == bst && (os < bs || (os == bs && ok < bkk)))));
             if (take) { bv = ov; bs = os; bkk = ok; bst = ot; }
         }
@@ -558,14 +605,14 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
         __threadfence_block();
         __syncwarp();
 
-        // ---- strips in passes of <= 32, cut at re-basing check points
+        // ---- strips in segments cut at the re-basing check points
         int accscr = 0;
         const int md = checkpoint(P.avmch, 0);
         int mc = md + t.a_left;
         WarpMax wmax{NEV, t.a_right, t.b_right};
         int ml0 = t.a_left;
         while (ml0 < t.a_right) {
-            int nstr = min(SPP, (t.a_right - ml0 + NELEM - 1) / NELEM);
+            int nstr = (t.a_right - ml0 + NELEM - 1) / NELEM;
             if (mc >= ml0 && mc < ml0 + nstr * NELEM && ((mc - ml0) % NELEM) == 0)
                 nstr = (mc - ml0) / NELEM + 1;
             run_pass<TRACE, LOCAL, SPJ>(P, sm, t, aseq, cols, band, trace, ml0, nstr,
@@ -639,7 +686,7 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
         }
         if (lane == 0) {
             DevResult r;
-            r.score = wmax.val; r.status = status; r.n_skl = n_skl; r.pad = 0;
+            r.score = wmax.val; r.status = wmax.err ? 4 : status; r.n_skl = n_skl; r.pad = 0;
             results[ti] = r;
         }
         __syncwarp();
