@@ -107,7 +107,9 @@ struct SmemH {
 };
 
 // ---------------------------------------------------------------------------
-// one pass: strips ml0, ml0 + 16, ... (nstr <= SPPH)
+// one segment: strips ml0, ml0 + 16, ... (nstr of them, up to the next re-basing check
+// point).  The warp has SPPH strip slots; slot s runs strips s, s + SPPH, ... back to back and
+// starts its next strip as soon as the strip above that one is 45 + HLAG steps ahead.
 // ---------------------------------------------------------------------------
 template <bool TRACE, bool LOCAL, bool SPJ>
 __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH& t,
@@ -117,24 +119,24 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int sidx = lane / TPSH;
+    const int slot = lane / TPSH;
     const int sub = lane % TPSH;
     const int row0 = sub * NRH;
-    const StripGeomH g = strip_geom_h(t, ml0 + NELEM * sidx);
-    const int j8 = g.j9 - 1;
-    const int nsteps = g.n_last - g.n_start + 1;
-    const bool live = sidx < nstr && nsteps > 0;
+    const int pred_lane = ((slot + SPPH - 1) % SPPH) * TPSH;
     const int width = t.up - t.lw + 7;
 
-    // strip s needs, at its step n, the band entry the full strip above writes at ITS step
-    // n + 45: with step j of strip s run in iteration j + off_s,
-    //   off_s = off_{s-1} + (n_start_s - n_start_{s-1}) + 45 + HLAG
-    const int n_start0 = __shfl_sync(FULL, g.n_start, 0);
-    const int off = (g.n_start - n_start0) + (HSKEW + HLAG) * sidx;
-    int niter = live ? off + nsteps : 0;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) niter = max(niter, __shfl_xor_sync(FULL, niter, o));
-    if (niter == 0) return;
+    // Step j of the slot's current strip runs in iteration j + off.  Strip s needs, at its
+    // step n, the band entry the full strip above writes at ITS step n + 45; hence
+    //   off_s >= off_{s-1} + (n_start_s - n_start_{s-1}) + 45 + HLAG.
+    int sidx = slot;                            // strip index inside the segment
+    StripGeomH g = strip_geom_h(t, ml0 + NELEM * min(sidx, nstr - 1));
+    int nsteps = g.n_last - g.n_start + 1;
+    int off = 0;
+    // state: 0 = waiting for the strip above to be scheduled, 1 = scheduled / running,
+    //        2 = no strip left, 3 = scheduled but empty (band outside the matrix)
+    int state = sidx < nstr ? (sidx == 0 ? (nsteps > 0 ? 1 : 3) : 0) : 2;
+    // schedule records (strip index, off - n_start) of the two strips this slot scheduled last
+    int rec_si = sidx == 0 ? 0 : -1000, rec_d = -g.n_start, old_si = -1000, old_d = 0;
 
     int H[6][NRH], F[3][NRH], E[3][NRH], V[3][NRH], NJ[3][NRH], arow[NRH];
 #pragma unroll
@@ -143,25 +145,17 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
         for (int a = 0; a < 6; ++a) H[a][k] = NEV;
 #pragma unroll
         for (int a = 0; a < 3; ++a) { F[a][k] = NEV; E[a][k] = NEV; V[a][k] = NEV; NJ[a][k] = 0; }
-        arow[k] = (live && row0 + k < g.j9) ? 4 * (int) aseq[(g.ml - t.a_left) + row0 + k] : 4 * ZROW;
+        arow[k] = 4 * ZROW;
     }
     int up4 = NEV, up5 = NEV, up6 = NEV;        // H of the row above, 4 / 5 / 6 steps ago
     int am0 = 0, am1 = 0, am2 = 0;              // "any acceptor among the 16 lanes" shift masks by nt phase
     const int g1 = P.g1, g2 = P.g2, g3 = P.g3, ge = P.ge;
     const bool clampL = LOCAL && localL_now;
-    int bval = INT_MIN, bstep = 0, bk = 0;
+    int bval = INT_MIN, bstep = 0, bk = 0, bsi = 0;
 
-    unsigned short* tr_base = TRACE
-        ? trace + ((long long) (sidx + (ml0 - t.a_left) / NELEM) * (width + TRACE_PAD_H)) * NELEM + row0
-        : nullptr;
-    // band entry of diagonal d (hv[d]): index d - lw + 3; the top row at step n reads hv[r + 3],
-    // r = n - 3 (ml + 1), i.e. index n - band_bias
-    const int band_bias = 3 * g.ml + t.lw - 3;
-    RingH* ring = sm.ring + (size_t) ((threadIdx.x >> 5) * SPPH + sidx) * RINGH;
+    RingH* ring = sm.ring + (size_t) ((threadIdx.x >> 5) * SPPH + slot) * RINGH;
     const char* mtx_bytes = reinterpret_cast<const char*>(sm.mtx);
     const int pen_cap = P.pen_cap;
-    const bool owns_bottom = live && j8 >= row0 && j8 < row0 + NRH;
-    const int kbot = j8 - row0;
 
     auto col_fetch = [&](int c) -> uint4 {
         if (c >= t.b_left && c <= t.b_right + COL_TAIL_H)
@@ -188,7 +182,7 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
     // rows) = 384 B = the same banks; XOR-ing the low two slot bits with the next two spreads
     // them over all four 32-byte bank groups, and odd strips store the two 16-byte halves
     // swapped so that the 8 strips of the warp fill both halves of every group.
-    const int hswap = (sidx & 1) * 16;
+    const int hswap = (slot & 1) * 16;
     auto ring_addr = [&](int c) -> char* {
         const int sl = c & (RINGH - 1);
         return reinterpret_cast<char*>(ring) + ((sl ^ ((sl >> 2) & 3)) * (int) sizeof(RingH));
@@ -201,12 +195,53 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
 
     unsigned nxt_band = 0;
 
-    for (int i = -1; i < niter; ++i) {
+    // every strip run one after the other would need fewer iterations than this
+    const int max_iter = nstr * (width + TRACE_PAD_H + 8) + 64;
+    for (int i = -1; ; ++i) {
+        if (i > max_iter) { wmax.err = 1; break; }      // scheduling bug guard: never spin on the device
+        // scheduling: has the slot above scheduled strip sidx - 1 yet, and for when
+        {
+            const int p_rec_si = __shfl_sync(FULL, rec_si, pred_lane);
+            const int p_rec_d = __shfl_sync(FULL, rec_d, pred_lane);
+            const int p_old_si = __shfl_sync(FULL, old_si, pred_lane);
+            const int p_old_d = __shfl_sync(FULL, old_d, pred_lane);
+            if (state == 0 && (p_rec_si == sidx - 1 || p_old_si == sidx - 1)) {
+                const int pd = p_rec_si == sidx - 1 ? p_rec_d : p_old_d;
+                off = max(i + 1, pd + g.n_start + (HSKEW + HLAG));
+                old_si = rec_si; old_d = rec_d;
+                rec_si = sidx; rec_d = off - g.n_start;
+                state = nsteps > 0 ? 1 : 3;
+            } else if (state == 3) {
+                sidx += SPPH;
+                if (sidx < nstr) {
+                    g = strip_geom_h(t, ml0 + NELEM * sidx);
+                    nsteps = g.n_last - g.n_start + 1;
+                    state = 0;
+                } else
+                    state = 2;
+            }
+        }
+        if (!__any_sync(FULL, state != 2)) break;
+        const bool run = state == 1;
         const int j = i - off;
+        const int j8 = g.j9 - 1;
+        // band entry of diagonal d (hv[d]): index d - lw + 3; the top row at step n reads
+        // hv[r + 3], r = n - 3 (ml + 1), i.e. index n - band_bias
+        const int band_bias = 3 * g.ml + t.lw - 3;
         // neighbour exchange inside a strip: last row of the thread above, three steps ago
         const int sh_h = __shfl_up_sync(FULL, H[2][NRH - 1], 1);
         const int sh_f = __shfl_up_sync(FULL, F[2][NRH - 1], 1);
-        if (live && j == -1) {
+        if (run && j == -1) {
+#pragma unroll
+            for (int k = 0; k < NRH; ++k) {
+#pragma unroll
+                for (int a = 0; a < 6; ++a) H[a][k] = NEV;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { F[a][k] = NEV; E[a][k] = NEV; V[a][k] = NEV; NJ[a][k] = 0; }
+                arow[k] = (row0 + k < g.j9) ? 4 * (int) aseq[(g.ml - t.a_left) + row0 + k] : 4 * ZROW;
+            }
+            up4 = up5 = up6 = NEV;
+            am0 = am1 = am2 = 0;
             if (sub == 0) {
                 const int ix = g.n_start - band_bias;
                 nxt_band = __ldcg(band + ix);
@@ -220,7 +255,7 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
                 ring_store(c, col_decode(col_fetch(c), false));
             }
             if (sub == 0) ring_store(g.n_start, col_decode(col_fetch(g.n_start), true));
-        } else if (live && j >= 0 && j < nsteps) {
+        } else if (run && j >= 0) {
             const int n = g.n_start + j;
             const unsigned cur_band = nxt_band;
             // both global loads of the iteration are issued here, a whole step ahead of their
@@ -333,9 +368,10 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
                     for (int k = NRH - 1; k >= 0; --k)
                         if (row0 + k < g.j9 && H[0][k] >= v) { v = H[0][k]; kk = k; }
                 }
-                if (v > bval) { bval = v; bstep = n; bk = row0 + kk; }
+                if (v > bval) { bval = v; bstep = n; bk = row0 + kk; bsi = sidx; }
             }
             if (TRACE) {
+                unsigned short* tr_base = trace + ((long long) (sidx + (ml0 - t.a_left) / NELEM) * (width + TRACE_PAD_H)) * NELEM + row0;
                 if (NRH == 4)
                     *reinterpret_cast<uint2*>(tr_base + (long long) j * NELEM) =
                         make_uint2(tw[0] | (tw[1] << 16), tw[NRH - 2] | (tw[NRH - 1] << 16));
@@ -345,7 +381,8 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
                 }
             }
             // bottom row of the strip -> band buffer (wip.h:299-303)
-            if (owns_bottom) {
+            if (j8 >= row0 && j8 < row0 + NRH) {
+                const int kbot = j8 - row0;
                 int out_h = H[0][NRH - 1], out_f = F[0][NRH - 1];
 #pragma unroll
                 for (int k = 0; k < NRH - 1; ++k)
@@ -356,14 +393,24 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
             }
             // next column -> ring (read from the next iteration on)
             if (feed) ring_store(n + 1, col_decode(nxt_col, true));
+            if (j == nsteps - 1) {
+                // strip finished: this slot's next strip
+                sidx += SPPH;
+                if (sidx < nstr) {
+                    g = strip_geom_h(t, ml0 + NELEM * sidx);
+                    nsteps = g.n_last - g.n_start + 1;
+                    state = 0;
+                } else
+                    state = 2;
+            }
         }
         __syncwarp();
     }
 
     if (LOCAL && localR) {
         // reference order: strips ascending, then step, then lane (first maximum)
-        int bv = (live && bval > INT_MIN) ? bval : INT_MIN;
-        int bs = bstep, bkk = bk, bst = sidx;
+        int bv = bval;
+        int bs = bstep, bkk = bk, bst = bsi;
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             const int ov = __shfl_xor_sync(FULL, bv, o);
@@ -641,7 +688,7 @@ dp_h1_kernel(const DevParamsH* __restrict__ gP, const int2* __restrict__ gpen,
         WarpMax wmax{NEV, t.a_right, t.b_right};
         int ml0 = t.a_left;
         while (ml0 < t.a_right) {
-            int nstr = min(SPPH, (t.a_right - ml0 + NELEM - 1) / NELEM);
+            int nstr = (t.a_right - ml0 + NELEM - 1) / NELEM;
             if (mc >= ml0 && mc < ml0 + nstr * NELEM && ((mc - ml0) % NELEM) == 0)
                 nstr = (mc - ml0) / NELEM + 1;
             run_pass_h<TRACE, LOCAL, SPJ>(P, sm, t, aseq, cols, band, trace, ml0, nstr,
@@ -815,7 +862,7 @@ dp_h1_kernel(const DevParamsH* __restrict__ gP, const int2* __restrict__ gpen,
         }
         if (lane == 0) {
             DevResult r;
-            r.score = wmax.val; r.status = status; r.n_skl = n_skl; r.pad = 0;
+            r.score = wmax.val; r.status = wmax.err ? 4 : status; r.n_skl = n_skl; r.pad = 0;
             results[ti] = r;
         }
         __syncwarp();
