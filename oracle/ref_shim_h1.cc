@@ -34,4 +34,55 @@ int shim_h1_kernel(const Seq** seqs, const PwdB* pwd, int lw, int up, int kind,
 	return kind == 0? copy_out_h(mfd, (SKL*) skl_out, cap): 0;
 }
 
+// hirschbergH1_wip(cpos, n_imd) with the mode lspH_ng picks (src/fwd2h1.cc:2198-2207); cpos_out
+// receives (n_imd + 1) x 10 ints.  The call narrows seqs[0/1]->left/right (the caller reads them).
+int shim_h1_udh(const Seq** seqs, const PwdB* pwd, int lw, int up, int n_imd, int* score,
+	int* cpos_out, double* seconds)
+{
+	WINDOW wdw = {lw, up, up - lw + 7};
+	SpJunc spj(seqs[1], pwd);
+	Dim10* cpos = new Dim10[n_imd + 1];
+	for (int i = 0; i <= n_imd; ++i) vset(cpos[i], end_of_ulk, 10);
+	auto t0 = std::chrono::steady_clock::now();
+const	int mode = ((std::max(abs(wdw.lw), wdw.up) + wdw.width) < SHRT_MAX)? 2: 4;
+	SimdAln2h1 k(seqs, pwd, wdw, &spj, 0, mode);
+	*score = k.hirschbergH1_wip(cpos, n_imd);
+	auto t1 = std::chrono::steady_clock::now();
+	if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+	for (int i = 0; i <= n_imd; ++i)
+	    for (int j = 0; j < 10; ++j) cpos_out[10 * i + j] = cpos[i][j];
+	delete[] cpos;
+	return 0;
+}
+
+// the whole driver Aln2h1::lspH_ng (protected: reached through a derived class), returning the
+// raw Mfile corner list
+struct ShimAln2h1 : public Aln2h1 {
+	ShimAln2h1(const Seq** sqs, const PwdB* pwd) : Aln2h1(sqs, pwd) {}
+	VTYPE run_lsp(const WINDOW& w, SKL* out, int cap, int* n_out) {
+	    mfd = new Mfile(sizeof(SKL));
+	    VTYPE scr = lspH_ng(w);
+	    int n = (int) mfd->size();
+	    SKL* skl = (SKL*) mfd->flush();
+	    *n_out = n;
+	    for (int i = 0; i < n && i < cap; ++i) out[i] = skl[i];
+	    delete[] skl;
+	    delete mfd; mfd = 0;
+	    return scr;
+	}
+};
+
+int shim_h1_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up, int* score, int* skl_out,
+	int cap, double* seconds)
+{
+	WINDOW wdw = {lw, up, up - lw + 7};
+	int n = 0;
+	auto t0 = std::chrono::steady_clock::now();
+	ShimAln2h1 aln(seqs, pwd);
+	*score = aln.run_lsp(wdw, (SKL*) skl_out, cap, &n);
+	auto t1 = std::chrono::steady_clock::now();
+	if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+	return n;
+}
+
 }	// extern "C"

@@ -25,6 +25,10 @@ int shim_s1_kernel(const Seq** seqs, const PwdB* pwd, int lw, int up,
 int shim_s1_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up,
 	int* score, int* skl_out, int cap, double* seconds);
 int shim_s1_nelem();
+int shim_h1_udh(const Seq** seqs, const PwdB* pwd, int lw, int up, int n_imd, int* score,
+	int* cpos_out, double* seconds);
+int shim_h1_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up, int* score, int* skl_out,
+	int cap, double* seconds);
 int shim_h1_kernel(const Seq** seqs, const PwdB* pwd, int lw, int up, int kind,
 	int* score, int* skl_out, int cap, double* seconds);
 int shim_s1_adapter(const Seq** seqs, const PwdB* pwd, int lw, int up,
@@ -264,6 +268,18 @@ int ref_task_kernel_p(void* h, int lw, int up, int kind, int* score, int* skl_ou
 {
 	RefTask* t = (RefTask*) h;
 	return shim_h1_kernel((const Seq**) t->sqs, g_pwd, lw, up, kind, score, skl_out, cap, seconds);
+}
+
+int ref_task_udh_p(void* h, int lw, int up, int n_imd, int* score, int* cpos_out, double* seconds)
+{
+	RefTask* t = (RefTask*) h;
+	return shim_h1_udh((const Seq**) t->sqs, g_pwd, lw, up, n_imd, score, cpos_out, seconds);
+}
+
+int ref_task_lsp_p(void* h, int lw, int up, int* score, int* skl_out, int cap, double* seconds)
+{
+	RefTask* t = (RefTask*) h;
+	return shim_h1_lsp((const Seq**) t->sqs, g_pwd, lw, up, score, skl_out, cap, seconds);
 }
 
 void ref_task_stripe31(void* h, int sh, int* lwup)

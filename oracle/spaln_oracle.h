@@ -91,6 +91,8 @@ typedef struct {
     int32_t quant_len[SO_MAXQUANT], quant_pen[SO_MAXQUANT];
     int32_t avmch, local, lcl, spj, simdim;
     const int32_t* simmtx;  /* [aa code][tron code] */
+    int32_t lgop;           /* PwdB::LongGOP (GapPenalty beyond codonk1; driver only) */
+    int32_t gape1, gape2;   /* PwdB::GapE1, GapE2 (UnpPenalty3; driver only) */
 } so_params_h;
 
 typedef struct {
@@ -102,11 +104,21 @@ typedef struct {
     int32_t a_left, a_right, b_left, b_right;
     int32_t a_exgl, a_exgr, b_exgl, b_exgr;     /* INEX flags, values 0..3 */
     int32_t lw, up;         /* WINDOW from stripe31 (width = up - lw + 7) */
+    int32_t a_len;          /* Seq::len of the query (range check of mimd_postwork; driver only) */
 } so_task_h;
 
 /* returns number of corners (want_trace) or 0; -1 allocation failure, -2 bad trace code */
 int so_forward_h1_wip(const so_params_h* p, const so_task_h* t, int want_trace, int32_t* score,
                       int32_t* skl, int cap);
+
+/* SimdAln2h1::hirschbergH1_wip (src/fwd2h1_wip_simd.h:338-773); outputs as so_hirschberg_wip */
+int so_hirschberg_h1_wip(const so_params_h* p, const so_task_h* t, int n_im, int32_t* score,
+                         int32_t* cpos, int32_t* ranges);
+
+/* Aln2h1::lspH_ng driver (src/fwd2h1.cc:2134-2230) with trcbkalignH_ng (SIMD branch),
+ * diagonalH_ng, mimd_postwork, rcsv_postwork and stripe31 */
+int so_lsp_h(const so_params_h* p, const so_task_h* t, const so_lsp_opts* o, int32_t* score,
+             int32_t* skl, int cap, int* unsupported);
 
 #ifdef __cplusplus
 }

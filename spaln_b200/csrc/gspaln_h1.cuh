@@ -148,7 +148,6 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
         arow[k] = 4 * ZROW;
     }
     int up4 = NEV, up5 = NEV, up6 = NEV;        // H of the row above, 4 / 5 / 6 steps ago
-    int am0 = 0, am1 = 0, am2 = 0;              // "any acceptor among the 16 lanes" shift masks by nt phase
     const int g1 = P.g1, g2 = P.g2, g3 = P.g3, ge = P.ge;
     const bool clampL = LOCAL && localL_now;
     int bval = INT_MIN, bstep = 0, bk = 0, bsi = 0;
@@ -241,7 +240,6 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
                 arow[k] = (row0 + k < g.j9) ? 4 * (int) aseq[(g.ml - t.a_left) + row0 + k] : 4 * ZROW;
             }
             up4 = up5 = up6 = NEV;
-            am0 = am1 = am2 = 0;
             if (sub == 0) {
                 const int ix = g.n_start - band_bias;
                 nxt_band = __ldcg(band + ix);
@@ -270,17 +268,11 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
             if (sub == 0) { u3 = lo16(cur_band); uf = hi16(cur_band); }
             else { u3 = sh_h; uf = sh_f; }
 
-            // AllZero(ph_v) of the reference (wip.h:223): has any of the 16 lanes an acceptor?
-            int liftv = -32768;
-            const int2* pen_base = sm.pen + (pen_cap + 1);
-            if (SPJ) {
-                const int4 c0 = *reinterpret_cast<const int4*>(ring_addr(n) + hswap);
-                const int has = max(max(c0.x, c0.y), c0.z) > SIG_NONE / 2 ? 1 : 0;
-                const int m = ((am0 << 1) | has) & 0xffff;
-                am0 = am1; am1 = am2; am2 = m;
-                if (m) { liftv = NEV; pen_base = sm.pen; }
-            }
-
+            // `if (AllZero(ph_v)) continue;` (wip.h:223) never skips in the canonical AVX2 build
+            // (all_zero == _mm256_testnzc_si256(v, v) == 0, src/simd_functions.h:1057): a phase
+            // slot without an acceptor always contributes nevsel
+            const int liftv = NEV;
+            const int2* pen_base = sm.pen;
             unsigned tw[NRH];
             int sv = INT_MIN, sk = 0;
 #pragma unroll
@@ -322,9 +314,8 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
                 if (e > h) { h = e; pb = eb; }
                 bool ab = false;
                 if (SPJ) {
-                    // acceptors, one candidate per splice phase (wip.h:206-246).  A slot without
-                    // an acceptor in this column contributes nevsel when any lane of the vector
-                    // has one (liftv), nothing otherwise.
+                    // acceptors, one candidate per splice phase (wip.h:206-246); a slot without
+                    // an acceptor in this column contributes nevsel
                     const int h0 = h;
                     if (liftv > h) { h = liftv; pb = TH_ACCM; }
                     const int s3v[3] = {ra.x, ra.y, ra.z};

@@ -37,6 +37,10 @@ CONFIGS = {
     # protein query x genomic segment (SimdAln2h1::forwardH1_wip)
     "prot_A2_global": ("-Q0 -A2 -yX0 -TDictyost", 21),
     "prot_A2_local": ("-Q0 -A2 -yX0 -LS -TDictyost", 22),
+    # small -V: Aln2h1::lspH_ng takes the Hirschberg route (hirschbergH1_wip + post-work)
+    "prot_A2_udh": ("-Q0 -A2 -yX0 -V128K -TDictyost", 23),
+    "prot_A2_udh_local": ("-Q0 -A2 -yX0 -V128K -LS -TDictyost", 24),
+    "prot_A6_udh_recursive": ("-Q0 -A6 -yX0 -V96K -TDictyost", 25),
 }
 
 
@@ -52,6 +56,7 @@ def gen_protein(name: str):
     for k, v in p.items():
         out["prm_" + k] = np.asarray(v)
     n = 0
+    udh = "udh" in name
 
     def add(g, q, tag="", **setkw):
         nonlocal n
@@ -68,11 +73,24 @@ def gen_protein(name: str):
         out[pre + "sgpt6"] = ex["sgpt6"]
         out[pre + "geom"] = np.array([ex["a_left"], ex["a_right"], ex["b_left"], ex["b_right"],
                                       ex["a_exgl"], ex["a_exgr"], ex["b_exgl"], ex["b_exgr"],
-                                      lw, up, ex["blen"]], np.int32)
+                                      lw, up, ex["blen"], ex["alen"]], np.int32)
         out[pre + "score"] = np.int32(r["score"])
         out[pre + "skl"] = r["skl"].astype(np.int32)
         out[pre + "score_only"] = np.int32(r1["score"])
         out[pre + "tag"] = np.array(tag)
+        if udh:
+            # the whole driver (Aln2h1::lspH_ng) and the Hirschberg pass alone
+            rl = t.lsp_p(lw, up)
+            out[pre + "lsp_score"] = np.int32(rl["score"])
+            out[pre + "lsp_skl"] = rl["skl"].astype(np.int32)
+            m = ex["a_right"] - ex["a_left"]
+            if m >= 16:
+                n_im = max(1, min(3, m // 16))
+                rh = t.udh_p(lw, up, n_im)
+                out[pre + "udh_nim"] = np.int32(n_im)
+                out[pre + "udh_score"] = np.int32(rh["score"])
+                out[pre + "udh_cpos"] = rh["cpos"].astype(np.int32)
+                out[pre + "udh_ranges"] = np.array(rh["ranges"], np.int32)
         n += 1
         t.close()
 

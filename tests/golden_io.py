@@ -33,7 +33,8 @@ def load(name):
 
 
 PROTEIN_NAMES = ["prot_A2_global", "prot_A2_local"]
-GEOM_KEYS_P = GEOM_KEYS + ["blen"]
+PROTEIN_UDH_NAMES = ["prot_A2_udh", "prot_A2_udh_local", "prot_A6_udh_recursive"]
+GEOM_KEYS_P = GEOM_KEYS + ["blen", "alen"]
 
 
 def load_protein(name):
@@ -50,5 +51,10 @@ def load_protein(name):
              "score": int(z[pre + "score"]), "skl": z[pre + "skl"],
              "score_only": int(z[pre + "score_only"]), "tag": str(z[pre + "tag"])}
         d.update({k: int(v) for k, v in zip(GEOM_KEYS_P, z[pre + "geom"])})
+        d.setdefault("alen", len(d["a"]) - 2)
+        for k in ("lsp_score", "lsp_skl", "udh_nim", "udh_score", "udh_cpos", "udh_ranges"):
+            if pre + k in z.files:
+                v = z[pre + k]
+                d[k] = v if v.ndim else int(v)
         probs.append(d)
     return prm, probs

@@ -53,6 +53,8 @@ def lib():
         _lib.so_lsp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_void_p]
         _lib.so_forward_h1_wip.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        _lib.so_hirschberg_h1_wip.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.so_lsp_h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     return _lib
 
 
@@ -158,17 +160,18 @@ class SoParamsH(C.Structure):
                 ("ipen", C.c_int32), ("llmt", C.c_int32), ("nquant", C.c_int32),
                 ("quant_len", C.c_int32 * MAXQ), ("quant_pen", C.c_int32 * MAXQ),
                 ("avmch", C.c_int32), ("local", C.c_int32), ("lcl", C.c_int32), ("spj", C.c_int32),
-                ("simdim", C.c_int32), ("simmtx", C.c_void_p)]
+                ("simdim", C.c_int32), ("simmtx", C.c_void_p),
+                ("lgop", C.c_int32), ("gape1", C.c_int32), ("gape2", C.c_int32)]
 
 
 class SoTaskH(C.Structure):
     _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("sgpt6", C.c_void_p), ("b_len", C.c_int32),
                 ("a_left", C.c_int32), ("a_right", C.c_int32), ("b_left", C.c_int32), ("b_right", C.c_int32),
                 ("a_exgl", C.c_int32), ("a_exgr", C.c_int32), ("b_exgl", C.c_int32), ("b_exgr", C.c_int32),
-                ("lw", C.c_int32), ("up", C.c_int32)]
+                ("lw", C.c_int32), ("up", C.c_int32), ("a_len", C.c_int32)]
 
 
-def forward_h1_wip(p: dict, t: dict, want_trace=True, cap: int = 1 << 16):
+def _params_h(p: dict):
     sp = SoParamsH()
     sp.gop, sp.gep, sp.lgep, sp.codonk1 = p["BasicGOP"], p["BasicGEP"], p["LongGEP"], p["codonk1"]
     sp.gw1, sp.gw2, sp.gw3 = p["GapW1"], p["GapW2"], p["GapW3"]
@@ -183,14 +186,27 @@ def forward_h1_wip(p: dict, t: dict, want_trace=True, cap: int = 1 << 16):
     sp.simdim = p["simdim"]
     sim = np.ascontiguousarray(p["simmtx"], np.int32)
     sp.simmtx = sim.ctypes.data
+    sp.lgop, sp.gape1, sp.gape2 = int(p["LongGOP"]), int(p["GapE1"]), int(p["GapE2"])
+    sp._keep = sim
+    return sp
+
+
+def _task_h(t: dict):
     st = SoTaskH()
     a = np.ascontiguousarray(t["a"], np.uint8)
     b = np.ascontiguousarray(t["b"], np.uint8)
     g = np.ascontiguousarray(t["sgpt6"], np.int16)
     st.a, st.b, st.sgpt6 = a.ctypes.data + 1, b.ctypes.data + 1, g.ctypes.data
     st.b_len = int(t["blen"])
+    st.a_len = int(t.get("alen", len(a) - 2))
     for k in ("a_left", "a_right", "b_left", "b_right", "a_exgl", "a_exgr", "b_exgl", "b_exgr", "lw", "up"):
         setattr(st, k, int(t[k]))
+    st._keep = (a, b, g)
+    return st
+
+
+def forward_h1_wip(p: dict, t: dict, want_trace=True, cap: int = 1 << 16):
+    sp, st = _params_h(p), _task_h(t)
     score = C.c_int32(0)
     skl = np.zeros((cap, 2), np.int32)
     n = lib().so_forward_h1_wip(C.byref(sp), C.byref(st), int(want_trace), C.byref(score),
@@ -198,3 +214,28 @@ def forward_h1_wip(p: dict, t: dict, want_trace=True, cap: int = 1 << 16):
     if n < 0:
         raise RuntimeError(f"so_forward_h1_wip failed: {n}")
     return {"score": score.value, "skl": skl[:n].copy()}
+
+
+def hirschberg_h1_wip(p: dict, t: dict, n_im: int):
+    sp, st = _params_h(p), _task_h(t)
+    score = C.c_int32(0)
+    cpos = np.zeros((n_im + 1, 10), np.int32)
+    ranges = np.zeros(4, np.int32)
+    rc = lib().so_hirschberg_h1_wip(C.byref(sp), C.byref(st), n_im, C.byref(score),
+                                    cpos.ctypes.data, ranges.ctypes.data)
+    if rc < 0:
+        raise RuntimeError(f"so_hirschberg_h1_wip failed: {rc}")
+    return {"score": score.value, "cpos": cpos, "ranges": ranges.tolist()}
+
+
+def lsp_h(p: dict, t: dict, cap: int = 1 << 16, max_vmf_space=None):
+    """Aln2h1::lspH_ng restatement: score + corner list in Mfile order"""
+    sp, st = _params_h(p), _task_h(t)
+    o = SoLspOpts(int(max_vmf_space if max_vmf_space is not None else p["MaxVmfSpace"]),
+                  int(p["sh"]), int(p["ubh"]), int(p["alg"]))
+    score = C.c_int32(0)
+    unsup = C.c_int(0)
+    skl = np.zeros((cap, 2), np.int32)
+    n = lib().so_lsp_h(C.byref(sp), C.byref(st), C.byref(o), C.byref(score), skl.ctypes.data, cap,
+                       C.byref(unsup))
+    return {"score": score.value, "skl": skl[:min(n, cap)].copy(), "unsupported": bool(unsup.value)}

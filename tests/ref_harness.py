@@ -76,6 +76,8 @@ class Reference:
         L.ref_task_export_p.argtypes = [C.c_void_p] * 4
         L.ref_get_params_p.argtypes = [C.c_void_p, C.c_int]
         L.ref_task_inject_p.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_task_udh_p.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_task_lsp_p.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_task_kernel_p.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_void_p]
         L.ref_task_stripe31.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -195,6 +197,26 @@ class RefTask:
         skl = np.zeros((cap, 2), np.int32)
         n = self.lib.ref_task_kernel_p(self.h, lw, up, kind, C.byref(score), skl.ctypes.data, cap,
                                        C.byref(secs))
+        return {"score": score.value, "skl": skl[:n].copy(), "seconds": secs.value}
+
+    def udh_p(self, lw, up, n_imd):
+        """SimdAln2h1::hirschbergH1_wip; the narrowed ranges are reported, then restored"""
+        score = C.c_int(0)
+        secs = C.c_double(0)
+        cpos = np.zeros((n_imd + 1, 10), np.int32)
+        before = self.info()
+        self.lib.ref_task_udh_p(self.h, lw, up, n_imd, C.byref(score), cpos.ctypes.data, C.byref(secs))
+        after = self.info()
+        self.set(**before)
+        return {"score": score.value, "cpos": cpos, "seconds": secs.value,
+                "ranges": [after["a_left"], after["a_right"], after["b_left"], after["b_right"]]}
+
+    def lsp_p(self, lw, up, cap=1 << 16):
+        """Aln2h1::lspH_ng (trace-back vs Hirschberg dispatch + post-work), raw Mfile corners"""
+        score = C.c_int(0)
+        secs = C.c_double(0)
+        skl = np.zeros((cap, 2), np.int32)
+        n = self.lib.ref_task_lsp_p(self.h, lw, up, C.byref(score), skl.ctypes.data, cap, C.byref(secs))
         return {"score": score.value, "skl": skl[:n].copy(), "seconds": secs.value}
 
     def inject(self, sig5, sig3):

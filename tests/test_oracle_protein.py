@@ -18,3 +18,25 @@ def test_oracle_protein_matches_reference_golden(oracle, name):
         assert s["score"] == pb["score_only"], (name, i, pb["tag"])
     # exons of the planted genes are recovered (corner lists have several segments)
     assert max(len(pb["skl"]) for pb in probs) >= 6
+
+
+@pytest.mark.parametrize("name", golden_io.PROTEIN_UDH_NAMES)
+def test_oracle_protein_udh_and_driver_match_reference_golden(oracle, name):
+    """hirschbergH1_wip (crossing records, narrowed ranges) and the whole driver Aln2h1::lspH_ng
+    (trace-back vs Hirschberg dispatch + block re-alignment) against the reference's outputs"""
+    prm, probs = golden_io.load_protein(name)
+    n_udh = n_lsp = 0
+    for i, pb in enumerate(probs):
+        if "udh_nim" in pb:
+            o = oracle.hirschberg_h1_wip(prm, pb, pb["udh_nim"])
+            assert o["score"] == pb["udh_score"], (name, i, pb["tag"])
+            assert np.array_equal(o["cpos"][:, :8], pb["udh_cpos"][:, :8]), (name, i, pb["tag"])
+            assert o["ranges"] == pb["udh_ranges"].tolist(), (name, i, pb["tag"])
+            n_udh += 1
+        o = oracle.lsp_h(prm, pb)
+        if o["unsupported"]:
+            continue        # a block with < 8 query rows: the reference's scalar kernel
+        assert o["score"] == pb["lsp_score"], (name, i, pb["tag"])
+        assert np.array_equal(o["skl"], pb["lsp_skl"]), (name, i, pb["tag"])
+        n_lsp += 1
+    assert n_udh >= 10 and n_lsp >= 15
