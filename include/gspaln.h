@@ -210,6 +210,8 @@ typedef struct gspaln_h_params {
     int32_t spj;                /* Seq::inex.intr of the genomic sequence */
     int32_t simdim;             /* row stride of simmtx below */
     int32_t simmtx[GSPALN_MAXDIM * GSPALN_MAXDIM];  /* mtx[aa][tron] at [aa * simdim + tron] */
+    int32_t lgop;               /* PwdB::LongGOP          (driver: GapPenalty of an all-gap problem) */
+    int32_t gape1, gape2;       /* PwdB::GapE1, GapE2     (driver: UnpPenalty3) */
 } gspaln_h_params;
 
 typedef struct gspaln_h_task {
@@ -223,6 +225,7 @@ typedef struct gspaln_h_task {
     int32_t lw, up;             /* WINDOW from stripe31 (src/aln2.cc:178-199); width = up - lw + 7 */
     int32_t skl_cap;
     int32_t n_imd;              /* reserved (hirschbergH1_wip) */
+    int32_t a_len;              /* Seq::len of the query (driver: range check of mimd_postwork) */
 } gspaln_h_task;
 
 typedef struct gspaln_h_ctx gspaln_h_ctx;
@@ -235,6 +238,15 @@ int  gspaln_h_run(gspaln_h_ctx* ctx);
 int  gspaln_h_download(gspaln_h_ctx* ctx, gspaln_result* results);
 int  gspaln_h_get_timing(const gspaln_h_ctx* ctx, gspaln_timing* out);
 const char* gspaln_h_last_error(const gspaln_h_ctx* ctx);
+/* The protein driver: Aln2h1::lspH_ng (src/fwd2h1.cc:2134-2230) over a batch; each task is one
+ * lspH_ng call (task.kind is ignored).  Trivial problems, the single-diagonal case
+ * (diagonalH_ng, 1963-1995) and the trace-back dispatch (trcbkalignH_ng, 1997-2041, SIMD branch)
+ * are handled; problems whose rhombic volume 2 m (n + 3 m) reaches opts->max_vmf_space take the
+ * Hirschberg route in the reference (hirschbergH1_wip) -- that pass is restated in oracle/ but
+ * not on the device yet: such problems, and blocks with fewer than 8 query rows (scalar
+ * forwardH_ng), return GSPALN_ST_UNSUPPORTED. */
+int  gspaln_h_lsp(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, const gspaln_lsp_opts* opts,
+                  gspaln_result* results);
 /* amino acid x nucleotide band cells as the scalar reference counts them
  * (Aln2h1::forwardH_ng inner loop, src/fwd2h1.cc:326-331) */
 int64_t gspaln_h_task_cells(const gspaln_h_task* t);

@@ -30,6 +30,7 @@ EXPORTS = [
     "gspaln_version", "gspaln_task_cells", "gspaln_lsp",
     "gspaln_h_create", "gspaln_h_destroy", "gspaln_h_submit", "gspaln_h_upload", "gspaln_h_run",
     "gspaln_h_download", "gspaln_h_get_timing", "gspaln_h_last_error", "gspaln_h_task_cells",
+    "gspaln_h_lsp",
 ]
 
 
@@ -82,6 +83,7 @@ class GspalnHParams(C.Structure):
         ("quant_len", C.c_int32 * MAXQUANT), ("quant_pen", C.c_int32 * MAXQUANT),
         ("avmch", C.c_int32), ("lcl", C.c_int32), ("spj", C.c_int32), ("simdim", C.c_int32),
         ("simmtx", C.c_int32 * (MAXDIM * MAXDIM)),
+        ("lgop", C.c_int32), ("gape1", C.c_int32), ("gape2", C.c_int32),
     ]
 
 
@@ -93,6 +95,7 @@ class GspalnHTask(C.Structure):
         ("a_left", C.c_int32), ("a_right", C.c_int32), ("b_left", C.c_int32), ("b_right", C.c_int32),
         ("a_exgl", C.c_int32), ("a_exgr", C.c_int32), ("b_exgl", C.c_int32), ("b_exgr", C.c_int32),
         ("lw", C.c_int32), ("up", C.c_int32), ("skl_cap", C.c_int32), ("n_imd", C.c_int32),
+        ("a_len", C.c_int32),
     ]
 
 
@@ -151,6 +154,8 @@ def load():
     lib.gspaln_h_get_timing.argtypes = [C.c_void_p, C.POINTER(GspalnTiming)]
     lib.gspaln_h_last_error.argtypes = [C.c_void_p]
     lib.gspaln_h_last_error.restype = C.c_char_p
+    lib.gspaln_h_lsp.argtypes = [C.c_void_p, C.POINTER(GspalnHTask), C.c_int, C.POINTER(GspalnLspOpts),
+                                 C.POINTER(GspalnResult)]
     lib.gspaln_h_task_cells.argtypes = [C.POINTER(GspalnHTask)]
     lib.gspaln_h_task_cells.restype = C.c_int64
     _lib = lib
@@ -200,4 +205,6 @@ def make_h_params(p: dict) -> GspalnHParams:
     flat = np.asarray(p["simmtx"], np.int32).reshape(d, d).ravel()
     for i in range(d * d):
         gp.simmtx[i] = int(flat[i])
+    gp.lgop = int(p.get("LongGOP", 0))
+    gp.gape1, gp.gape2 = int(p.get("GapE1", 0)), int(p.get("GapE2", 0))
     return gp

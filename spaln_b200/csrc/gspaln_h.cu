@@ -8,6 +8,8 @@
 
 #include <algorithm>
 #include <climits>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -437,6 +439,79 @@ int gspaln_h_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gspaln
     if (rc == GSPALN_OK) rc = gspaln_h_run(ctx);
     if (rc == GSPALN_OK) rc = gspaln_h_download(ctx, results);
     return rc;
+}
+
+int gspaln_h_lsp(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, const gspaln_lsp_opts* opts,
+                 gspaln_result* results)
+{
+    if (!ctx || !opts || n < 0 || (n && (!tasks || !results))) return GSPALN_EINVAL;
+    const gspaln_h_params& P = ctx->prm;
+    const int NEVSEL = INT_MIN / 16 * 7;
+    const bool local = (P.lcl & 16) != 0;
+    auto gap_ext_pen = [&](int i) { return i > P.codonk1 ? P.lgep : P.gep; };
+    auto gap_penalty = [&](int i) { return i == 0 ? 0 : (i > P.codonk1 ? P.lgop + i * P.lgep : P.gop + i * P.gep); };
+    auto unp_penalty3 = [&](int i) {            // PwdB::UnpPenalty3 (src/aln.h:289-301), i <= codonk1
+        return (i / 3) * P.gep + (i % 3 == 1 ? P.gape1 : (i % 3 == 2 ? P.gape2 : 0));
+    };
+    std::vector<gspaln_h_task> batch;
+    std::vector<int> owner;
+    std::vector<gspaln_result> bres;
+    for (int i = 0; i < n; ++i) {
+        const gspaln_h_task& t = tasks[i];
+        gspaln_result& o = results[i];
+        o.score = 0; o.status = GSPALN_ST_OK; o.n_skl = 0; o.reserved = 0; o.cells = 0;
+        const int m = t.a_right - t.a_left, nn = t.b_right - t.b_left;
+        auto put = [&](int k, int mm, int nq) {
+            if (o.skl && k < t.skl_cap) { o.skl[2 * k] = mm; o.skl[2 * k + 1] = nq; }
+        };
+        if (!m && !nn) continue;
+        if (!m || !nn) {
+            put(0, t.a_left, t.b_left); put(1, t.a_right, t.b_right);
+            o.n_skl = 2;
+            if (t.skl_cap < 2) o.status = GSPALN_ST_SKL_OVERFLOW;
+            if (m) o.score = (t.a_exgl || t.a_exgr) ? gap_ext_pen(m) : gap_penalty(m);
+            else o.score = (t.b_exgl || t.b_exgr) ? gap_ext_pen(nn) : unp_penalty3(nn);
+            continue;
+        }
+        if (t.up == t.lw) {
+            // diagonalH_ng: one codon per residue along the only diagonal
+            const bool LocalL = local && t.a_exgl && t.b_exgl, LocalR = local && t.a_exgr && t.b_exgr;
+            int scr = 0, maxh = NEVSEL, mL = t.a_left, mR = t.a_right;
+            for (int mm = t.a_left, k = 0; mm < t.a_right; ++k) {
+                const int col = t.b_left + 1 + 3 * k;
+                scr += P.simmtx[(t.a[t.a_left + k] & 31) * P.simdim + (t.b[col] & 31)] + t.sg[col].sigE;
+                ++mm;
+                if (LocalL && scr < 0) { scr = 0; mL = mm; }
+                if (LocalR && scr > maxh) { maxh = scr; mR = mm; }
+            }
+            put(0, mL, 3 * (mL - t.a_left) + t.b_left); put(1, mR, 3 * (mR - t.a_left) + t.b_left);
+            o.n_skl = 2;
+            if (t.skl_cap < 2) o.status = GSPALN_ST_SKL_OVERFLOW;
+            o.score = LocalR ? maxh : scr;
+            continue;
+        }
+        bool trcbk = std::abs(nn - m) < NELEM || m == 1 || nn <= 3;
+        if (!trcbk) {
+            const float cvol = float(m) * (nn + 3 * m);         // rhombic volume, simd >= 2
+            trcbk = 2.f * cvol < (float) opts->max_vmf_space;
+        }
+        if (!trcbk) { o.status = GSPALN_ST_UNSUPPORTED; o.score = NEVSEL; continue; }   // Hirschberg route
+        if (t.up - t.lw + 7 < 0) { o.score = NEVSEL; continue; }
+        if (m < 8) { o.status = GSPALN_ST_UNSUPPORTED; o.score = NEVSEL; continue; }    // scalar forwardH_ng
+        gspaln_h_task b = t;
+        b.kind = GSPALN_FORWARD_WIP;
+        batch.push_back(b);
+        owner.push_back(i);
+        bres.push_back(o);
+    }
+    if (!batch.empty()) {
+        const int rc = gspaln_h_submit(ctx, batch.data(), (int) batch.size(), bres.data());
+        if (rc != GSPALN_OK) return rc;
+        for (size_t k = 0; k < batch.size(); ++k) results[owner[k]] = bres[k];
+    } else {
+        memset(&ctx->tim, 0, sizeof(ctx->tim));
+    }
+    return GSPALN_OK;
 }
 
 int gspaln_h_get_timing(const gspaln_h_ctx* ctx, gspaln_timing* out)

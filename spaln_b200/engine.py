@@ -268,6 +268,7 @@ class ProblemH:
     b_exgl: int = 1
     b_exgr: int = 1
     skl_cap: int = 0
+    a_len: int = 0          # Seq::len of the query (0: len(a) - 1, arrays carry one pad residue)
 
     @staticmethod
     def from_export(ex: dict, lw: int, up: int) -> "ProblemH":
@@ -278,7 +279,8 @@ class ProblemH:
                         a_left=ex["a_left"], a_right=ex["a_right"],
                         b_left=ex["b_left"], b_right=ex["b_right"], lw=lw, up=up,
                         a_exgl=ex["a_exgl"], a_exgr=ex["a_exgr"],
-                        b_exgl=ex["b_exgl"], b_exgr=ex["b_exgr"])
+                        b_exgl=ex["b_exgl"], b_exgr=ex["b_exgr"],
+                        a_len=int(ex.get("alen", len(ex["a"]) - 2)))
 
 
 class EngineH:
@@ -327,6 +329,7 @@ class EngineH:
             t.a_left, t.a_right, t.b_left, t.b_right = p.a_left, p.a_right, p.b_left, p.b_right
             t.a_exgl, t.a_exgr, t.b_exgl, t.b_exgr = p.a_exgl, p.a_exgr, p.b_exgl, p.b_exgr
             t.lw, t.up = p.lw, p.up
+            t.a_len = int(p.a_len or (len(a) - 1))
             cap = p.skl_cap or ((p.a_right - p.a_left) + (p.b_right - p.b_left) + 8)
             t.skl_cap = cap if kind == capi.FORWARD_WIP else 0
         return arr, keep
@@ -362,6 +365,17 @@ class EngineH:
     def forwardH1_wip(self, problems, trace=True):
         """trace=False == forwardH1_wip(0) as HomScoreH_ng calls it (score only)"""
         return self.submit(problems, capi.FORWARD_WIP if trace else capi.SCOREONLY_WIP)
+
+    def lspH_ng(self, problems, max_vmf_space=32 * 1024 * 1024, sh=100, ubh=0, alg=2):
+        """Aln2h1::lspH_ng over a batch (src/fwd2h1.cc:2134-2230).  Problems that take the
+        Hirschberg route in the reference come back with status GSPALN_ST_UNSUPPORTED (3)."""
+        arr, keep = self._pack(problems, capi.FORWARD_WIP)
+        n = len(problems)
+        res, bufs = self._results(n, arr)
+        o = capi.GspalnLspOpts(int(max_vmf_space), int(sh), int(ubh), int(alg))
+        self._check(self.lib.gspaln_h_lsp(self._h, arr, n, C.byref(o), res), "gspaln_h_lsp")
+        self._n = n
+        return self._collect(n, res, bufs, arr)
 
     def upload(self, problems, kind=capi.FORWARD_WIP):
         arr, keep = self._pack(problems, kind)

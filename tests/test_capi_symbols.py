@@ -38,6 +38,9 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(capi.GspalnParams) == 4 * (8 + 8 + 8 + 5) + 4 * 32 * 32
     assert ctypes.sizeof(capi.GspalnTask) == 8 + 4 * 8 + 4 * 12
     assert ctypes.sizeof(capi.GspalnResult) == 32 + 16 + 8
+    assert ctypes.sizeof(capi.GspalnHParams) == 4 * (10 + 8 + 8 + 4) + 4 * 32 * 32 + 4 * 3
+    assert ctypes.sizeof(capi.GspalnHTask) == 8 + 3 * 8 + 4 * 14
+    assert capi.SGPT6_DTYPE.itemsize == 14
 
 
 def test_no_cpu_fallback_without_device():

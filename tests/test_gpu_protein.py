@@ -84,3 +84,30 @@ def test_forwardH1_wip_matches_oracle_on_random_problems(oracle, case):
     # the planted genes are found: multi-exon corner lists exist
     assert max(len(r.skl) for r in res) >= 4
     eng.close()
+
+
+@pytest.mark.parametrize("name", golden_io.PROTEIN_NAMES + golden_io.PROTEIN_UDH_NAMES)
+def test_lspH_ng_driver_matches_reference_and_oracle(oracle, name):
+    """gspaln_h_lsp: the dispatch of Aln2h1::lspH_ng.  With the reference's default -V every golden
+    problem takes the trace-back route; with the fixture's own small -V the Hirschberg route is
+    reported as unsupported (not on the device yet) and everything else must equal the reference."""
+    from spaln_b200 import EngineH
+    prm, probs = golden_io.load_protein(name)
+    eng = EngineH(prm, device=0)
+    P = _problems(probs)
+    for vmf in (32 * 1024 * 1024, int(prm["MaxVmfSpace"])):
+        res = eng.lspH_ng(P, max_vmf_space=vmf, sh=int(prm["sh"]), alg=int(prm["alg"]))
+        n_ok = 0
+        for i, (pb, r) in enumerate(zip(probs, res)):
+            o = oracle.lsp_h(prm, pb, max_vmf_space=vmf)
+            if r.status == 3:
+                m, n = pb["a_right"] - pb["a_left"], pb["b_right"] - pb["b_left"]
+                assert o["unsupported"] or 2.0 * m * (n + 3 * m) >= vmf, (name, i, pb["tag"])
+                continue
+            assert r.status == 0 and not o["unsupported"], (name, i, pb["tag"], r.status)
+            assert r.score == o["score"] and np.array_equal(r.skl, o["skl"]), (name, i, pb["tag"])
+            if vmf == int(prm["MaxVmfSpace"]) and "lsp_skl" in pb:
+                assert r.score == pb["lsp_score"] and np.array_equal(r.skl, pb["lsp_skl"]), (name, i)
+            n_ok += 1
+        assert n_ok >= 3 if vmf < 1 << 20 else n_ok >= 15, (name, vmf, n_ok)
+    eng.close()
