@@ -215,7 +215,8 @@ typedef struct gspaln_h_params {
 } gspaln_h_params;
 
 typedef struct gspaln_h_task {
-    int32_t kind;               /* GSPALN_FORWARD_WIP or GSPALN_SCOREONLY_WIP */
+    int32_t kind;               /* GSPALN_FORWARD_WIP, GSPALN_SCOREONLY_WIP or GSPALN_HIRSCHBERG_WIP
+                                   (SimdAln2h1::hirschbergH1_wip, src/fwd2h1_wip_simd.h:338-773) */
     const uint8_t* a;           /* amino-acid codes; a[i] == *Seq::at(i) */
     const uint8_t* b;           /* tron codes (Seq::nuc2tron, src/seq.cc:774-798); b[i] == *Seq::at(i) */
     const gspaln_sgpt6* sg;     /* Exinon::data_p[n], n in [0, b_len + 1] */
@@ -224,7 +225,7 @@ typedef struct gspaln_h_task {
     int32_t a_exgl, a_exgr, b_exgl, b_exgr;     /* INEX values 0..3 */
     int32_t lw, up;             /* WINDOW from stripe31 (src/aln2.cc:178-199); width = up - lw + 7 */
     int32_t skl_cap;
-    int32_t n_imd;              /* reserved (hirschbergH1_wip) */
+    int32_t n_imd;              /* GSPALN_HIRSCHBERG_WIP: number of intermediate rows (>= 1) */
     int32_t a_len;              /* Seq::len of the query (driver: range check of mimd_postwork) */
 } gspaln_h_task;
 

@@ -4,6 +4,7 @@
 // CUDA-event timing.  No CPU implementation behind this API.
 #include "../../include/gspaln.h"
 #include "gspaln_h1.cuh"
+#include "gspaln_h1_udh.cuh"
 #include "gspaln_host.hpp"
 
 #include <algorithm>
@@ -39,6 +40,11 @@ struct gspaln_h_ctx {
     DevBuf<unsigned char> d_rows;
     DevBuf<int2> d_skl;
     DevBuf<DevResult> d_res;
+    DevBuf<int> d_ws;               // per-warp workspace of the Hirschberg pass
+    DevBuf<int> d_cpos;
+    DevBuf<DevUdhOutH> d_ures;
+    PinBuf<int> h_cpos;
+    PinBuf<DevUdhOutH> h_ures;
     PinBuf<DevTaskH> h_tasks;
     PinBuf<int> h_order;
     PinBuf<unsigned char> h_apool;
@@ -46,9 +52,11 @@ struct gspaln_h_ctx {
     PinBuf<ColEnd> h_epool;
     PinBuf<int2> h_skl;
     PinBuf<DevResult> h_res;
-    int n = 0, n_trace = 0, n_score = 0;
+    int n = 0, n_trace = 0, n_score = 0, n_udh = 0;
     size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, row_slab = 0, skl_elems = 0;
+    size_t ws_slab = 0, cpos_elems = 0;
     int grid_trace = 0, grid_score = 0, grid_run_trace = 0, grid_run_score = 0;
+    int grid_udh = 0, grid_run_udh = 0;
     std::vector<int64_t> cells;
     gspaln_timing tim;
     std::string err;
@@ -80,6 +88,17 @@ KernelH kernel_h(bool trace, bool local, bool spj)
         dp_h1_kernel<true, true, false>, dp_h1_kernel<true, true, true>,
     };
     return tab[(trace ? 4 : 0) | (local ? 2 : 0) | (spj ? 1 : 0)];
+}
+
+using KernelUdhH = void (*)(const DevParamsH*, const int2*, const DevTaskH*, const int*, int, int*,
+                            const unsigned char*, const ColH*, const ColEnd*, int*, long long, int*,
+                            DevUdhOutH*);
+
+KernelUdhH kernel_udh_h(bool local, bool spj)
+{
+    static const KernelUdhH tab[4] = {dp_h1_udh_kernel<false, false>, dp_h1_udh_kernel<true, false>,
+                                      dp_h1_udh_kernel<false, true>, dp_h1_udh_kernel<true, true>};
+    return tab[(local ? 2 : 0) | (spj ? 1 : 0)];
 }
 
 int64_t task_cells_h(const gspaln_h_task& t)
@@ -204,6 +223,12 @@ int gspaln_h_create(gspaln_h_ctx** out, const gspaln_h_params* prm, int device)
     ctx->grid_trace = std::max(1, occ) * ctx->sm_count;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ks, CTA_THREADS, ctx->smem_bytes);
     ctx->grid_score = std::max(1, occ) * ctx->sm_count;
+    {
+        const void* ku = reinterpret_cast<const void*>(kernel_udh_h(P.local, P.spj));
+        cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_bytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ku, CTA_THREADS, ctx->smem_bytes);
+        ctx->grid_udh = std::max(1, occ) * ctx->sm_count;
+    }
     if (cudaGetLastError() != cudaSuccess) { gspaln_h_destroy(ctx); return GSPALN_ECUDA; }
     *out = ctx;
     return GSPALN_OK;
@@ -216,7 +241,8 @@ void gspaln_h_destroy(gspaln_h_ctx* ctx)
     ctx->d_prm.release(); ctx->d_pen.release(); ctx->d_tasks.release(); ctx->d_order.release();
     ctx->d_ticket.release(); ctx->d_apool.release(); ctx->d_cpool.release(); ctx->d_epool.release();
     ctx->d_band.release(); ctx->d_trace.release(); ctx->d_rows.release(); ctx->d_skl.release();
-    ctx->d_res.release();
+    ctx->d_res.release(); ctx->d_ws.release(); ctx->d_cpos.release(); ctx->d_ures.release();
+    ctx->h_cpos.release(); ctx->h_ures.release();
     ctx->h_tasks.release(); ctx->h_order.release(); ctx->h_apool.release(); ctx->h_cpool.release();
     ctx->h_epool.release(); ctx->h_skl.release(); ctx->h_res.release();
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -230,13 +256,16 @@ int gspaln_h_upload(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n)
     CKH(cudaSetDevice(ctx->device));
     ctx->n = 0;
     size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, row_slab = 0, skl_elems = 0;
+    size_t ws_slab = 0, cpos_elems = 0;
     ctx->cells.assign(n, 0);
     std::vector<DevTaskH> dt(n);
-    int n_trace = 0, n_score = 0;
+    int n_trace = 0, n_score = 0, n_udh = 0;
     for (int i = 0; i < n; ++i) {
         const gspaln_h_task& t = tasks[i];
         if (t.a_right < t.a_left || t.b_right < t.b_left || t.up < t.lw || t.a_left < 0 || t.b_left < 0 ||
-            t.b_len < t.b_right || (t.kind != GSPALN_FORWARD_WIP && t.kind != GSPALN_SCOREONLY_WIP) ||
+            t.b_len < t.b_right ||
+            (t.kind != GSPALN_FORWARD_WIP && t.kind != GSPALN_SCOREONLY_WIP && t.kind != GSPALN_HIRSCHBERG_WIP) ||
+            (t.kind == GSPALN_HIRSCHBERG_WIP && (t.n_imd < 1 || t.a_right - t.a_left < 2)) ||
             !t.a || !t.b || !t.sg)
             return fail(ctx, GSPALN_EINVAL, "bad task");
         DevTaskH& d = dt[i];
@@ -259,6 +288,11 @@ int gspaln_h_upload(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n)
             trace_slab = std::max(trace_slab, align_up(nstrips * (size_t) (width + TRACE_PAD_H) * NELEM + 64, 128));
             skl_elems += (size_t) d.skl_cap;
             ++n_trace;
+        } else if (t.kind == GSPALN_HIRSCHBERG_WIP) {
+            d.pad1 = (long long) cpos_elems | ((long long) t.n_imd << 40);
+            cpos_elems += (size_t) 10 * (t.n_imd + 1);
+            ws_slab = std::max(ws_slab, align_up(4 * ((size_t) width + BAND_PAD_H) + (size_t) t.n_imd * 4 * width + 16, 64));
+            ++n_udh;
         } else
             ++n_score;
         ctx->cells[i] = task_cells_h(t);
@@ -266,12 +300,14 @@ int gspaln_h_upload(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n)
     if (ctx->h_tasks.reserve(n + 1) != cudaSuccess || ctx->h_order.reserve(n + 1) != cudaSuccess ||
         ctx->h_apool.reserve(a_bytes + 16) != cudaSuccess || ctx->h_cpool.reserve(c_elems + 4) != cudaSuccess ||
         ctx->h_epool.reserve(c_elems + 4) != cudaSuccess ||
-        ctx->h_res.reserve(n + 1) != cudaSuccess || ctx->h_skl.reserve(skl_elems + 1) != cudaSuccess)
+        ctx->h_res.reserve(n + 1) != cudaSuccess || ctx->h_skl.reserve(skl_elems + 1) != cudaSuccess ||
+        ctx->h_cpos.reserve(cpos_elems + 1) != cudaSuccess || ctx->h_ures.reserve(n + 1) != cudaSuccess)
         return fail(ctx, GSPALN_ENOMEM, "pinned host allocation");
     if (ctx->d_tasks.reserve(n + 1) != cudaSuccess || ctx->d_order.reserve(n + 1) != cudaSuccess ||
         ctx->d_apool.reserve(a_bytes + 16) != cudaSuccess || ctx->d_cpool.reserve(c_elems + 4) != cudaSuccess ||
         ctx->d_epool.reserve(c_elems + 4) != cudaSuccess ||
-        ctx->d_skl.reserve(skl_elems + 1) != cudaSuccess || ctx->d_res.reserve(n + 1) != cudaSuccess) {
+        ctx->d_skl.reserve(skl_elems + 1) != cudaSuccess || ctx->d_res.reserve(n + 1) != cudaSuccess ||
+        ctx->d_cpos.reserve(cpos_elems + 1) != cudaSuccess || ctx->d_ures.reserve(n + 1) != cudaSuccess) {
         cudaGetLastError();
         return fail(ctx, GSPALN_ENOMEM, "device allocation");
     }
@@ -295,6 +331,12 @@ int gspaln_h_upload(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n)
         }
         ctx->grid_run_trace = gt;
         ctx->grid_run_score = gs;
+        const int gu = n_udh ? ctas(ctx->grid_udh, n_udh) : 0;
+        if (ctx->d_ws.reserve((size_t) gu * WARPS_PER_CTA * ws_slab + 64) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, GSPALN_ENOMEM, "device UDH workspace allocation");
+        }
+        ctx->grid_run_udh = gu;
     }
     {
         auto pack_range = [&](int lo, int hi) {
@@ -353,7 +395,8 @@ int gspaln_h_upload(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n)
     ctx->tim.h2d_ms = ms;
     ctx->tim.h2d_bytes = (int64_t) (sizeof(DevTaskH) * n + sizeof(int) * n + a_bytes +
                                     (sizeof(ColH) + sizeof(ColEnd)) * c_elems);
-    ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score;
+    ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score; ctx->n_udh = n_udh;
+    ctx->ws_slab = ws_slab; ctx->cpos_elems = cpos_elems;
     ctx->a_bytes = a_bytes; ctx->c_elems = c_elems; ctx->band_slab = band_slab;
     ctx->trace_slab = trace_slab; ctx->row_slab = row_slab; ctx->skl_elems = skl_elems;
     int64_t cells = 0, tb = 0;
@@ -393,6 +436,14 @@ int gspaln_h_run(gspaln_h_ctx* ctx)
                 ctx->d_skl.p, ctx->d_res.p);
             ++launches;
         }
+        if (ctx->n_udh) {
+            CKH(cudaMemsetAsync(ctx->d_ticket.p + 2, 0, sizeof(int), ctx->stream));
+            kernel_udh_h(local, spj)<<<ctx->grid_run_udh, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+                ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p + 2,
+                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_epool.p, ctx->d_ws.p, (long long) ctx->ws_slab,
+                ctx->d_cpos.p, ctx->d_ures.p);
+            ++launches;
+        }
         CKH(cudaGetLastError());
     }
     CKH(cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -413,6 +464,10 @@ int gspaln_h_download(gspaln_h_ctx* ctx, gspaln_result* results)
     if (n) CKH(cudaMemcpyAsync(ctx->h_res.p, ctx->d_res.p, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (ctx->skl_elems)
         CKH(cudaMemcpyAsync(ctx->h_skl.p, ctx->d_skl.p, sizeof(int2) * ctx->skl_elems, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->n_udh) {
+        CKH(cudaMemcpyAsync(ctx->h_ures.p, ctx->d_ures.p, sizeof(DevUdhOutH) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        CKH(cudaMemcpyAsync(ctx->h_cpos.p, ctx->d_cpos.p, sizeof(int) * ctx->cpos_elems, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CKH(cudaEventRecord(ctx->ev[5], ctx->stream));
     CKH(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
@@ -425,6 +480,14 @@ int gspaln_h_download(gspaln_h_ctx* ctx, gspaln_result* results)
         o.score = r.score; o.status = r.status; o.n_skl = r.n_skl; o.reserved = 0;
         o.cells = ctx->cells[i];
         const DevTaskH& d = ctx->h_tasks.p[i];
+        if (d.kind == GSPALN_HIRSCHBERG_WIP) {
+            const DevUdhOutH& u = ctx->h_ures.p[i];
+            o.score = u.score; o.status = u.status; o.n_skl = 0;
+            o.ranges[0] = u.a_left; o.ranges[1] = u.a_right; o.ranges[2] = u.b_left; o.ranges[3] = u.b_right;
+            const int n_imd = (int) (d.pad1 >> 40);
+            if (o.cpos) memcpy(o.cpos, ctx->h_cpos.p + (d.pad1 & ((1ll << 40) - 1)), sizeof(int) * 10 * (size_t) (n_imd + 1));
+            continue;
+        }
         if (o.skl && d.skl_cap > 0) {
             const int cnt = std::min(r.n_skl, d.skl_cap);
             memcpy(o.skl, ctx->h_skl.p + d.skl_off, sizeof(int2) * (size_t) std::max(0, cnt));

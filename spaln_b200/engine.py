@@ -269,6 +269,7 @@ class ProblemH:
     b_exgr: int = 1
     skl_cap: int = 0
     a_len: int = 0          # Seq::len of the query (0: len(a) - 1, arrays carry one pad residue)
+    n_imd: int = 0          # hirschbergH1_wip only: number of intermediate rows
 
     @staticmethod
     def from_export(ex: dict, lw: int, up: int) -> "ProblemH":
@@ -332,6 +333,7 @@ class EngineH:
             t.a_len = int(p.a_len or (len(a) - 1))
             cap = p.skl_cap or ((p.a_right - p.a_left) + (p.b_right - p.b_left) + 8)
             t.skl_cap = cap if kind == capi.FORWARD_WIP else 0
+            t.n_imd = int(p.n_imd) if kind == capi.HIRSCHBERG_WIP else 0
         return arr, keep
 
     def _check(self, rc, what):
@@ -345,13 +347,16 @@ class EngineH:
         for i in range(n):
             cap = arr[i].skl_cap
             buf = np.zeros((max(cap, 1), 2), np.int32)
-            bufs.append(buf)
+            cp = np.zeros((arr[i].n_imd + 1, 10), np.int32) if arr[i].kind == capi.HIRSCHBERG_WIP else None
+            bufs.append((buf, cp))
             res[i].skl = buf.ctypes.data if cap > 0 else None
+            res[i].cpos = cp.ctypes.data if cp is not None else None
         return res, bufs
 
     def _collect(self, n, res, bufs, arr):
         return [Result(int(res[i].score), int(res[i].status),
-                       bufs[i][:max(min(res[i].n_skl, arr[i].skl_cap), 0)].copy(), int(res[i].cells))
+                       bufs[i][0][:max(min(res[i].n_skl, arr[i].skl_cap), 0)].copy(), int(res[i].cells),
+                       tuple(int(x) for x in res[i].ranges), bufs[i][1])
                 for i in range(n)]
 
     def submit(self, problems, kind=capi.FORWARD_WIP):
@@ -365,6 +370,10 @@ class EngineH:
     def forwardH1_wip(self, problems, trace=True):
         """trace=False == forwardH1_wip(0) as HomScoreH_ng calls it (score only)"""
         return self.submit(problems, capi.FORWARD_WIP if trace else capi.SCOREONLY_WIP)
+
+    def hirschbergH1_wip(self, problems):
+        """problems carry n_imd; results carry score, narrowed ranges and cpos (Dim10 records)"""
+        return self.submit(problems, capi.HIRSCHBERG_WIP)
 
     def lspH_ng(self, problems, max_vmf_space=32 * 1024 * 1024, sh=100, ubh=0, alg=2):
         """Aln2h1::lspH_ng over a batch (src/fwd2h1.cc:2134-2230).  Problems that take the

@@ -111,3 +111,45 @@ def test_lspH_ng_driver_matches_reference_and_oracle(oracle, name):
             n_ok += 1
         assert n_ok >= 3 if vmf < 1 << 20 else n_ok >= 15, (name, vmf, n_ok)
     eng.close()
+
+
+@pytest.mark.parametrize("name", golden_io.PROTEIN_UDH_NAMES)
+def test_hirschbergH1_wip_matches_reference_golden(name):
+    """the Hirschberg forward pass alone: score, crossing records, narrowed ranges"""
+    from spaln_b200 import EngineH
+    prm, probs = golden_io.load_protein(name)
+    sel = [pb for pb in probs if "udh_nim" in pb]
+    P = _problems(sel)
+    for pb, p in zip(sel, P):
+        p.n_imd = pb["udh_nim"]
+    eng = EngineH(prm, device=0)
+    res = eng.hirschbergH1_wip(P)
+    bad = []
+    for i, (pb, r) in enumerate(zip(sel, res)):
+        if r.status != 0 or r.score != pb["udh_score"] or list(r.ranges) != pb["udh_ranges"].tolist() or \
+                not np.array_equal(r.cpos[:, :8], pb["udh_cpos"][:, :8]):
+            bad.append((i, pb["tag"], r.status, r.score, pb["udh_score"], list(r.ranges), pb["udh_ranges"].tolist()))
+    assert not bad, (name, bad)
+    eng.close()
+
+
+@pytest.mark.parametrize("fixture,seed", [("prot_A2_udh", 71), ("prot_A2_udh_local", 72)])
+def test_hirschbergH1_wip_matches_oracle_on_random_problems(oracle, fixture, seed):
+    from spaln_b200 import EngineH
+    prm, _ = golden_io.load_protein(fixture)
+    rng = np.random.default_rng(seed)
+    probs = _synthetic_protein(prm, rng, 24, (40, 420), (30, 400))
+    P = _problems(probs)
+    for pb, p in zip(probs, P):
+        m = pb["a_right"] - pb["a_left"]
+        p.n_imd = int(rng.integers(1, max(2, min(8, m // 16))))
+    eng = EngineH(prm, device=0)
+    res = eng.hirschbergH1_wip(P)
+    bad = []
+    for i, (pb, p, r) in enumerate(zip(probs, P, res)):
+        o = oracle.hirschberg_h1_wip(prm, pb, p.n_imd)
+        if r.status != 0 or r.score != o["score"] or list(r.ranges) != o["ranges"] or \
+                not np.array_equal(r.cpos[:, :8], o["cpos"][:, :8]):
+            bad.append((i, p.n_imd, r.status, r.score, o["score"], list(r.ranges), o["ranges"]))
+    assert not bad, (fixture, bad)
+    eng.close()
