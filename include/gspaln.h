@@ -240,12 +240,12 @@ int  gspaln_h_download(gspaln_h_ctx* ctx, gspaln_result* results);
 int  gspaln_h_get_timing(const gspaln_h_ctx* ctx, gspaln_timing* out);
 const char* gspaln_h_last_error(const gspaln_h_ctx* ctx);
 /* The protein driver: Aln2h1::lspH_ng (src/fwd2h1.cc:2134-2230) over a batch; each task is one
- * lspH_ng call (task.kind is ignored).  Trivial problems, the single-diagonal case
- * (diagonalH_ng, 1963-1995) and the trace-back dispatch (trcbkalignH_ng, 1997-2041, SIMD branch)
- * are handled; problems whose rhombic volume 2 m (n + 3 m) reaches opts->max_vmf_space take the
- * Hirschberg route in the reference (hirschbergH1_wip) -- that pass is restated in oracle/ but
- * not on the device yet: such problems, and blocks with fewer than 8 query rows (scalar
- * forwardH_ng), return GSPALN_ST_UNSUPPORTED. */
+ * lspH_ng call (task.kind is ignored).  Same scheme as gspaln_lsp: trivial problems and the
+ * single-diagonal case (diagonalH_ng, 1963-1995) on the host, trace-back problems
+ * (trcbkalignH_ng, 1997-2041, SIMD branch), Hirschberg passes (hirschbergH1_wip) and the block
+ * re-alignments of mimd_postwork / rcsv_postwork (2045-2132, re-banded with stripe31) as device
+ * batches, one per recursion level.  Blocks with fewer than 8 query rows need the reference's
+ * scalar kernel forwardH_ng and set GSPALN_ST_UNSUPPORTED. */
 int  gspaln_h_lsp(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, const gspaln_lsp_opts* opts,
                   gspaln_result* results);
 /* amino acid x nucleotide band cells as the scalar reference counts them

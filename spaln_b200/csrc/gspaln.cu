@@ -520,3 +520,81 @@ int gspaln_get_timing(const gspaln_ctx* ctx, gspaln_timing* out)
 
 }   // extern "C"
 #include "gspaln_lsp.inl"
+
+namespace {
+
+// DNA x genome: Aln2s1::lspS_ng (src/fwd2s1.cc:1801-1897)
+struct LspTraitsS {
+    using Ctx = gspaln_ctx;
+    using Task = gspaln_task;
+    static constexpr int WPAD = 3;
+    static void stripe(LspGeo& g, int sh)       // stripe(), src/aln2.cc:156-176
+    {
+        if (sh < 0) {
+            const int shorter = std::min(g.a_right - g.a_left, g.b_right - g.b_left);
+            sh = -sh * shorter / 100;
+        }
+        int up = g.b_right - g.a_right;
+        int lw = g.b_left - g.a_left;
+        if (up < lw) std::swap(up, lw);
+        up += sh; lw -= sh;
+        int q;
+        if ((q = g.b_right - g.a_left) < up) up = q;
+        if ((q = g.b_left - g.a_right) > lw) lw = q;
+        g.up = up; g.lw = lw;
+    }
+    static bool small(int m, int nn) { return std::abs(nn - m) < 8 || m == 1 || nn == 1; }
+    static float cvol(int m, int nn) { return (float) m * (nn + m); }
+    static float coef_c(const gspaln_params& P) { return (float) ((P.noll + 1) * 4); }
+    static bool is_local(const gspaln_params& P) { return P.local != 0; }
+    static int trivial_score(const gspaln_params& P, const LspGeo& g, int m, int nn)
+    {
+        if (m) return (g.a_exgl || g.a_exgr) ? P.gep : (P.gop + m * P.gep);
+        return (g.b_exgl || g.b_exgr) ? P.gep : nn * P.gep;
+    }
+    static void diagonal(const gspaln_params& P, const gspaln_task& base, const LspGeo& g, int (&c4)[4], int& score)
+    {
+        // diagonalS_ng (src/fwd2s1.cc:1629-1665)
+        const int NEVSEL = INT_MIN / 16 * 7;
+        const int m = g.a_right - g.a_left, nn = g.b_right - g.b_left;
+        const bool LocalL = P.local && g.a_exgl && g.b_exgl, LocalR = P.local && g.a_exgr && g.b_exgr;
+        const int dlt = P.local ? 0 : (nn - m);
+        const uint8_t* as = dlt < 0 ? base.b : base.a;
+        const uint8_t* bs = dlt < 0 ? base.a : base.b;
+        const int al = dlt < 0 ? g.b_left : g.a_left, ar = dlt < 0 ? g.b_right : g.a_right;
+        const int bl = dlt < 0 ? g.a_left : g.b_left;
+        int mL = al, mR = ar, scr = 0, maxh = NEVSEL;
+        for (int mm = al, k = 0; mm++ < ar; ++k) {
+            const int x = as[al + k], y = bs[bl + k];
+            scr += dlt < 0 ? P.simmtx[y * P.simdim + x] : P.simmtx[x * P.simdim + y];
+            if (LocalL && scr < 0) { scr = 0; mL = mm; }
+            if (LocalR && scr > maxh) { maxh = scr; mR = mm; }
+        }
+        int r = bl - al;
+        if (dlt < 0) r -= dlt;
+        c4[0] = mL; c4[1] = mL + r; c4[2] = mR; c4[3] = mR + r;
+        score = LocalR ? maxh : scr;
+    }
+    static bool bad_range(const gspaln_task&, const LspGeo&) { return false; }
+    static gspaln_task make_task(const gspaln_task& base, const LspGeo& g, int kind, int n_imd)
+    {
+        gspaln_task t = base;
+        t.kind = kind;
+        t.a_left = g.a_left; t.a_right = g.a_right; t.b_left = g.b_left; t.b_right = g.b_right;
+        t.a_exgl = g.a_exgl; t.a_exgr = g.a_exgr; t.b_exgl = g.b_exgl; t.b_exgr = g.b_exgr;
+        t.lw = g.lw; t.up = g.up;
+        t.n_imd = n_imd;
+        t.skl_cap = kind == GSPALN_FORWARD_WIP ? (g.a_right - g.a_left) + (g.b_right - g.b_left) + 8 : 0;
+        return t;
+    }
+    static int submit(gspaln_ctx* ctx, const gspaln_task* t, int n, gspaln_result* r) { return gspaln_submit(ctx, t, n, r); }
+    static int64_t cells(const gspaln_task& t) { return task_cells(t); }
+};
+
+}   // namespace
+
+extern "C" int gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
+                          const gspaln_lsp_opts* opts, gspaln_result* results)
+{
+    return lsp_driver<LspTraitsS>(ctx, tasks, n, opts, results);
+}

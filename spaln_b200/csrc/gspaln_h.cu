@@ -504,79 +504,6 @@ int gspaln_h_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gspaln
     return rc;
 }
 
-int gspaln_h_lsp(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, const gspaln_lsp_opts* opts,
-                 gspaln_result* results)
-{
-    if (!ctx || !opts || n < 0 || (n && (!tasks || !results))) return GSPALN_EINVAL;
-    const gspaln_h_params& P = ctx->prm;
-    const int NEVSEL = INT_MIN / 16 * 7;
-    const bool local = (P.lcl & 16) != 0;
-    auto gap_ext_pen = [&](int i) { return i > P.codonk1 ? P.lgep : P.gep; };
-    auto gap_penalty = [&](int i) { return i == 0 ? 0 : (i > P.codonk1 ? P.lgop + i * P.lgep : P.gop + i * P.gep); };
-    auto unp_penalty3 = [&](int i) {            // PwdB::UnpPenalty3 (src/aln.h:289-301), i <= codonk1
-        return (i / 3) * P.gep + (i % 3 == 1 ? P.gape1 : (i % 3 == 2 ? P.gape2 : 0));
-    };
-    std::vector<gspaln_h_task> batch;
-    std::vector<int> owner;
-    std::vector<gspaln_result> bres;
-    for (int i = 0; i < n; ++i) {
-        const gspaln_h_task& t = tasks[i];
-        gspaln_result& o = results[i];
-        o.score = 0; o.status = GSPALN_ST_OK; o.n_skl = 0; o.reserved = 0; o.cells = 0;
-        const int m = t.a_right - t.a_left, nn = t.b_right - t.b_left;
-        auto put = [&](int k, int mm, int nq) {
-            if (o.skl && k < t.skl_cap) { o.skl[2 * k] = mm; o.skl[2 * k + 1] = nq; }
-        };
-        if (!m && !nn) continue;
-        if (!m || !nn) {
-            put(0, t.a_left, t.b_left); put(1, t.a_right, t.b_right);
-            o.n_skl = 2;
-            if (t.skl_cap < 2) o.status = GSPALN_ST_SKL_OVERFLOW;
-            if (m) o.score = (t.a_exgl || t.a_exgr) ? gap_ext_pen(m) : gap_penalty(m);
-            else o.score = (t.b_exgl || t.b_exgr) ? gap_ext_pen(nn) : unp_penalty3(nn);
-            continue;
-        }
-        if (t.up == t.lw) {
-            // diagonalH_ng: one codon per residue along the only diagonal
-            const bool LocalL = local && t.a_exgl && t.b_exgl, LocalR = local && t.a_exgr && t.b_exgr;
-            int scr = 0, maxh = NEVSEL, mL = t.a_left, mR = t.a_right;
-            for (int mm = t.a_left, k = 0; mm < t.a_right; ++k) {
-                const int col = t.b_left + 1 + 3 * k;
-                scr += P.simmtx[(t.a[t.a_left + k] & 31) * P.simdim + (t.b[col] & 31)] + t.sg[col].sigE;
-                ++mm;
-                if (LocalL && scr < 0) { scr = 0; mL = mm; }
-                if (LocalR && scr > maxh) { maxh = scr; mR = mm; }
-            }
-            put(0, mL, 3 * (mL - t.a_left) + t.b_left); put(1, mR, 3 * (mR - t.a_left) + t.b_left);
-            o.n_skl = 2;
-            if (t.skl_cap < 2) o.status = GSPALN_ST_SKL_OVERFLOW;
-            o.score = LocalR ? maxh : scr;
-            continue;
-        }
-        bool trcbk = std::abs(nn - m) < NELEM || m == 1 || nn <= 3;
-        if (!trcbk) {
-            const float cvol = float(m) * (nn + 3 * m);         // rhombic volume, simd >= 2
-            trcbk = 2.f * cvol < (float) opts->max_vmf_space;
-        }
-        if (!trcbk) { o.status = GSPALN_ST_UNSUPPORTED; o.score = NEVSEL; continue; }   // Hirschberg route
-        if (t.up - t.lw + 7 < 0) { o.score = NEVSEL; continue; }
-        if (m < 8) { o.status = GSPALN_ST_UNSUPPORTED; o.score = NEVSEL; continue; }    // scalar forwardH_ng
-        gspaln_h_task b = t;
-        b.kind = GSPALN_FORWARD_WIP;
-        batch.push_back(b);
-        owner.push_back(i);
-        bres.push_back(o);
-    }
-    if (!batch.empty()) {
-        const int rc = gspaln_h_submit(ctx, batch.data(), (int) batch.size(), bres.data());
-        if (rc != GSPALN_OK) return rc;
-        for (size_t k = 0; k < batch.size(); ++k) results[owner[k]] = bres[k];
-    } else {
-        memset(&ctx->tim, 0, sizeof(ctx->tim));
-    }
-    return GSPALN_OK;
-}
-
 int gspaln_h_get_timing(const gspaln_h_ctx* ctx, gspaln_timing* out)
 {
     if (!ctx || !out) return GSPALN_EINVAL;
@@ -585,3 +512,83 @@ int gspaln_h_get_timing(const gspaln_h_ctx* ctx, gspaln_timing* out)
 }
 
 }   // extern "C"
+#include "gspaln_lsp.inl"
+
+namespace {
+
+// protein x genome: Aln2h1::lspH_ng (src/fwd2h1.cc:2134-2230)
+struct LspTraitsH {
+    using Ctx = gspaln_h_ctx;
+    using Task = gspaln_h_task;
+    static constexpr int WPAD = 7;
+    static void stripe(LspGeo& g, int sh)       // stripe31(), src/aln2.cc:178-199
+    {
+        if (sh < 0) {
+            const int shorter = std::min(g.a_right - g.a_left, g.b_right - g.b_left);
+            sh = -sh * shorter / 100;
+        }
+        sh *= 3;
+        int up = g.b_right - 3 * g.a_right;
+        int lw = g.b_left - 3 * g.a_left;
+        if (up < lw) std::swap(up, lw);
+        up += sh; lw -= sh;
+        int q;
+        if ((q = g.b_right - 3 * g.a_left) < up) up = q;
+        if ((q = g.b_left - 3 * g.a_right) > lw) lw = q;
+        g.up = up; g.lw = lw;
+    }
+    static bool small(int m, int nn) { return std::abs(nn - m) < NELEM || m == 1 || nn <= 3; }
+    static float cvol(int m, int nn) { return (float) m * (nn + 3 * m); }
+    static float coef_c(const gspaln_h_params&) { return 12.f; }     // (Noll + 1) * sizeof(int), Noll == 2
+    static bool is_local(const gspaln_h_params& P) { return (P.lcl & 16) != 0; }
+    static int trivial_score(const gspaln_h_params& P, const LspGeo& g, int m, int nn)
+    {
+        auto ext = [&](int i) { return i > P.codonk1 ? P.lgep : P.gep; };
+        if (m) return (g.a_exgl || g.a_exgr) ? ext(m) : (m > P.codonk1 ? P.lgop + m * P.lgep : P.gop + m * P.gep);
+        // PwdB::UnpPenalty3 (src/aln.h:289-301), i <= codonk1
+        return (g.b_exgl || g.b_exgr) ? ext(nn)
+                                      : (nn / 3) * P.gep + (nn % 3 == 1 ? P.gape1 : (nn % 3 == 2 ? P.gape2 : 0));
+    }
+    static void diagonal(const gspaln_h_params& P, const gspaln_h_task& t, const LspGeo& g, int (&c4)[4], int& score)
+    {
+        // diagonalH_ng (src/fwd2h1.cc:1963-1995): one codon per residue along the only diagonal
+        const int NEVSEL = INT_MIN / 16 * 7;
+        const bool local = (P.lcl & 16) != 0;
+        const bool LocalL = local && g.a_exgl && g.b_exgl, LocalR = local && g.a_exgr && g.b_exgr;
+        int scr = 0, maxh = NEVSEL, mL = g.a_left, mR = g.a_right;
+        for (int mm = g.a_left, k = 0; mm < g.a_right; ++k) {
+            const int col = g.b_left + 1 + 3 * k;
+            scr += P.simmtx[(t.a[g.a_left + k] & 31) * P.simdim + (t.b[col] & 31)] + t.sg[col].sigE;
+            ++mm;
+            if (LocalL && scr < 0) { scr = 0; mL = mm; }
+            if (LocalR && scr > maxh) { maxh = scr; mR = mm; }
+        }
+        c4[0] = mL; c4[1] = 3 * (mL - g.a_left) + g.b_left; c4[2] = mR; c4[3] = 3 * (mR - g.a_left) + g.b_left;
+        score = LocalR ? maxh : scr;
+    }
+    static bool bad_range(const gspaln_h_task& t, const LspGeo& g)     // mimd_postwork, src/fwd2h1.cc:2060-2061
+    {
+        return g.a_right > t.a_len || g.b_right > t.b_len || g.a_left < 0 || g.b_left < 0;
+    }
+    static gspaln_h_task make_task(const gspaln_h_task& base, const LspGeo& g, int kind, int n_imd)
+    {
+        gspaln_h_task t = base;
+        t.kind = kind;
+        t.a_left = g.a_left; t.a_right = g.a_right; t.b_left = g.b_left; t.b_right = g.b_right;
+        t.a_exgl = g.a_exgl; t.a_exgr = g.a_exgr; t.b_exgl = g.b_exgl; t.b_exgr = g.b_exgr;
+        t.lw = g.lw; t.up = g.up;
+        t.n_imd = n_imd;
+        t.skl_cap = kind == GSPALN_FORWARD_WIP ? (g.a_right - g.a_left) + (g.b_right - g.b_left) + 8 : 0;
+        return t;
+    }
+    static int submit(gspaln_h_ctx* ctx, const gspaln_h_task* t, int n, gspaln_result* r) { return gspaln_h_submit(ctx, t, n, r); }
+    static int64_t cells(const gspaln_h_task& t) { return task_cells_h(t); }
+};
+
+}   // namespace
+
+extern "C" int gspaln_h_lsp(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n,
+                            const gspaln_lsp_opts* opts, gspaln_result* results)
+{
+    return lsp_driver<LspTraitsH>(ctx, tasks, n, opts, results);
+}

@@ -1,10 +1,14 @@
-// gspaln_lsp.inl -- host driver: Aln2s1::lspS_ng over a batch (included by gspaln.cu).
+// gspaln_lsp.inl -- host driver: Aln2s1::lspS_ng / Aln2h1::lspH_ng over a batch (included by
+// gspaln.cu and gspaln_h.cu, which supply the traits of their sequence type).
 //
 // Reference: lspS_ng src/fwd2s1.cc:1801-1897, trcbkalignS_ng 1667-1710 (SIMD branch),
 // mimd_postwork 1714-1756, rcsv_postwork 1758-1799, diagonalS_ng 1629-1665,
 // stripe src/aln2.cc:156-176.  The reference recurses problem by problem; here
 // every level of that recursion becomes one device batch (all Hirschberg passes
-// and all block re-alignments of a level run together).
+// and all block re-alignments of a level run together).  The protein driver
+// (src/fwd2h1.cc:1963-2230) differs only in what the traits carry: stripe31, the rhombic
+// volume m (n + 3 m), the lane count in the thresholds, the trivial-case penalties,
+// diagonalH_ng and the range check of its mimd_postwork.
 
 namespace {
 
@@ -36,41 +40,15 @@ struct LspFwd {                 // one trcbkalignS_ng call
     std::vector<int2> skl;
 };
 
-void lsp_stripe(LspGeo& g, int sh)
-{
-    if (sh < 0) {
-        const int shorter = std::min(g.a_right - g.a_left, g.b_right - g.b_left);
-        sh = -sh * shorter / 100;
-    }
-    int up = g.b_right - g.a_right;
-    int lw = g.b_left - g.a_left;
-    if (up < lw) std::swap(up, lw);
-    up += sh; lw -= sh;
-    int q;
-    if ((q = g.b_right - g.a_left) < up) up = q;
-    if ((q = g.b_left - g.a_right) > lw) lw = q;
-    g.up = up; g.lw = lw;
-}
-
-gspaln_task lsp_task(const gspaln_task& base, const LspGeo& g, int kind, int n_imd)
-{
-    gspaln_task t = base;
-    t.kind = kind;
-    t.a_left = g.a_left; t.a_right = g.a_right; t.b_left = g.b_left; t.b_right = g.b_right;
-    t.a_exgl = g.a_exgl; t.a_exgr = g.a_exgr; t.b_exgl = g.b_exgl; t.b_exgr = g.b_exgr;
-    t.lw = g.lw; t.up = g.up;
-    t.n_imd = n_imd;
-    t.skl_cap = kind == GSPALN_FORWARD_WIP ? (g.a_right - g.a_left) + (g.b_right - g.b_left) + 8 : 0;
-    return t;
-}
-
 }   // namespace
 
-extern "C" int gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
-                          const gspaln_lsp_opts* opts, gspaln_result* results)
+template <class TR>
+int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
+               const gspaln_lsp_opts* opts, gspaln_result* results)
 {
+    using Task = typename TR::Task;
     if (!ctx || !opts || n < 0 || (n && (!tasks || !results))) return GSPALN_EINVAL;
-    const gspaln_params& P = ctx->prm;
+    const auto& P = ctx->prm;
     const int NEVSEL = INT_MIN / 16 * 7;
     const int EOU = INT_MAX - 2;
     std::vector<LspItem> items;
@@ -79,7 +57,7 @@ extern "C" int gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
     std::vector<int> pending;
     items.reserve(2 * (size_t) n);
     for (int i = 0; i < n; ++i) {
-        const gspaln_task& t = tasks[i];
+        const Task& t = tasks[i];
         LspItem it;
         it.root = i;
         it.g = LspGeo{t.a_left, t.a_right, t.b_left, t.b_right, t.a_exgl, t.a_exgr, t.b_exgl, t.b_exgr, t.lw, t.up};
@@ -93,7 +71,7 @@ extern "C" int gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
     };
     // returns the index of the queued forward task or -1 (nothing to do / unsupported)
     auto queue_trcbk = [&](int item, const LspGeo& g) -> int {
-        if (g.up - g.lw + 3 < 0) return -1;
+        if (g.up - g.lw + TR::WPAD < 0) return -1;
         if (g.a_right - g.a_left < 8) { status[items[item].root] = GSPALN_ST_UNSUPPORTED; return -1; }
         LspFwd f; f.root = items[item].root; f.g = g;
         fwds.push_back(std::move(f));
@@ -115,41 +93,26 @@ extern "C" int gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
         for (int id : pending) {
             LspItem& it = items[id];
             const LspGeo& g = it.g;
-            const gspaln_task& base = tasks[it.root];
+            const Task& base = tasks[it.root];
             const int m = g.a_right - g.a_left, nn = g.b_right - g.b_left;
             if (!m && !nn) { it.score = 0; continue; }
             if (!m || !nn) {
                 lit2(it, g.a_left, g.b_left, g.a_right, g.b_right);
-                if (m) it.score = (g.a_exgl || g.a_exgr) ? P.gep : (P.gop + m * P.gep);
-                else it.score = (g.b_exgl || g.b_exgr) ? P.gep : nn * P.gep;
+                it.score = TR::trivial_score(P, g, m, nn);
                 continue;
             }
             if (g.up == g.lw) {
-                // diagonalS_ng (src/fwd2s1.cc:1629-1665)
-                const bool LocalL = P.local && g.a_exgl && g.b_exgl, LocalR = P.local && g.a_exgr && g.b_exgr;
-                const int dlt = P.local ? 0 : (nn - m);
-                const uint8_t* as = dlt < 0 ? base.b : base.a;
-                const uint8_t* bs = dlt < 0 ? base.a : base.b;
-                const int al = dlt < 0 ? g.b_left : g.a_left, ar = dlt < 0 ? g.b_right : g.a_right;
-                const int bl = dlt < 0 ? g.a_left : g.b_left;
-                int mL = al, mR = ar, scr = 0, maxh = NEVSEL;
-                for (int mm = al, k = 0; mm++ < ar; ++k) {
-                    const int x = as[al + k], y = bs[bl + k];
-                    scr += dlt < 0 ? P.simmtx[y * P.simdim + x] : P.simmtx[x * P.simdim + y];
-                    if (LocalL && scr < 0) { scr = 0; mL = mm; }
-                    if (LocalR && scr > maxh) { maxh = scr; mR = mm; }
-                }
-                int r = bl - al;
-                if (dlt < 0) r -= dlt;
-                lit2(it, mL, mL + r, mR, mR + r);
-                it.score = LocalR ? maxh : scr;
+                int c4[4], scr = 0;
+                TR::diagonal(P, base, g, c4, scr);
+                lit2(it, c4[0], c4[1], c4[2], c4[3]);
+                it.score = scr;
                 continue;
             }
-            bool trcbk = std::abs(nn - m) < 8 || m == 1 || nn == 1;
+            bool trcbk = TR::small(m, nn);
             int n_imd = 1;
             bool recursive = (opts->alg & 4) != 0;
-            const float coef_B = 2.f, coef_C = (float) ((P.noll + 1) * 4);
-            const float cvol = (float) m * (nn + m);            // rhombic (simd >= 2)
+            const float coef_B = 2.f, coef_C = TR::coef_c(P);
+            const float cvol = TR::cvol(m, nn);                 // rhombic (simd >= 2)
             if (!trcbk && coef_B * cvol < opts->max_vmf_space) trcbk = true;
             if (!trcbk && !recursive) {
                 const double z = 2. * m * coef_B / coef_C;
@@ -176,18 +139,18 @@ extern "C" int gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
         pending.clear();
 
         // ---- one device batch: all Hirschberg passes + all queued trace-back problems
-        std::vector<gspaln_task> batch;
+        std::vector<Task> batch;
         std::vector<gspaln_result> bres;
         std::vector<std::vector<int>> cposbuf(udh_items.size());
         for (size_t k = 0; k < udh_items.size(); ++k) {
             const LspItem& it = items[udh_items[k]];
-            batch.push_back(lsp_task(tasks[it.root], it.g, GSPALN_HIRSCHBERG_WIP, it.n_imd));
+            batch.push_back(TR::make_task(tasks[it.root], it.g, GSPALN_HIRSCHBERG_WIP, it.n_imd));
             cposbuf[k].assign(10 * (size_t) (it.n_imd + 1), 0);
         }
         const size_t fwd_first = fwd_done;
         std::vector<std::vector<int>> sklbuf(fwds.size() - fwd_first);
         for (size_t f = fwd_first; f < fwds.size(); ++f) {
-            batch.push_back(lsp_task(tasks[fwds[f].root], fwds[f].g, GSPALN_FORWARD_WIP, 0));
+            batch.push_back(TR::make_task(tasks[fwds[f].root], fwds[f].g, GSPALN_FORWARD_WIP, 0));
             sklbuf[f - fwd_first].assign(2 * (size_t) batch.back().skl_cap, 0);
         }
         bres.resize(batch.size());
@@ -197,7 +160,7 @@ extern "C" int gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
             bres[udh_items.size() + (f - fwd_first)].cpos = nullptr;
         }
         if (!batch.empty()) {
-            int rc = gspaln_submit(ctx, batch.data(), (int) batch.size(), bres.data());
+            int rc = TR::submit(ctx, batch.data(), (int) batch.size(), bres.data());
             if (rc != GSPALN_OK) return rc;
             kernel_ms += ctx->tim.kernel_ms; h2d_ms += ctx->tim.h2d_ms; d2h_ms += ctx->tim.d2h_ms;
             launches += ctx->tim.launches; h2d_bytes += ctx->tim.h2d_bytes; d2h_bytes += ctx->tim.d2h_bytes;
@@ -239,11 +202,11 @@ extern "C" int gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
                     const int aright = g.a_right, bright = g.b_right;
                     LspGeo g1 = g;
                     g1.a_right = cpos[0]; g1.b_right = cpos[c - 1];
-                    lsp_stripe(g1, opts->sh);
+                    TR::stripe(g1, opts->sh);
                     LspGeo g2 = g1;
                     g2.a_left = cpos[0]; g2.b_exgl = cpos[1]; g2.b_left = cpos[2];
                     g2.a_right = aright; g2.b_right = bright;
-                    lsp_stripe(g2, opts->sh);
+                    TR::stripe(g2, opts->sh);
                     for (const LspGeo& gg : {g1, g2}) {
                         LspItem child; child.root = items[id].root; child.g = gg;
                         items.push_back(child);
@@ -252,8 +215,8 @@ extern "C" int gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
                         items[id].pieces.push_back(std::move(cp));
                         pending.push_back(cid);
                     }
-                } else if (P.local) {
-                    lsp_stripe(g, opts->sh);
+                } else if (TR::is_local(P)) {
+                    TR::stripe(g, opts->sh);
                     queue_trcbk(id, g);
                 }
             } else {
@@ -267,19 +230,20 @@ extern "C" int gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
                     g.a_left = cpos[10 * i + c];
                     g.b_exgl = cpos[10 * i + (++c)];
                     g.b_left = cpos[10 * i + (++c)];
+                    if (TR::bad_range(tasks[items[id].root], g)) { i = -2; break; }    // mimd_postwork returns
                     if (g.b_left < 0 || g.b_left > g.b_right) break;
                     LspPiece p; p.kind = 0; p.ref = -1;
                     while (cpos[10 * i + (++c)] < EOU) p.lit.push_back(make_int2(g.a_left, cpos[10 * i + c]));
                     if (!p.lit.empty()) items[id].pieces.push_back(std::move(p));
-                    lsp_stripe(g, opts->sh);
+                    TR::stripe(g, opts->sh);
                     queue_trcbk(id, g);
                     g.a_right = g.a_left;
                     g.b_right = cpos[10 * i + c - 1];
                 }
-                if ((i < 0 && cpos[0] != EOU) || cpos[2] != EOU) {
+                if (i != -2 && ((i < 0 && cpos[0] != EOU) || cpos[2] != EOU)) {
                     g.a_left = aleft;
                     g.b_left = bleft;
-                    lsp_stripe(g, opts->sh);
+                    TR::stripe(g, opts->sh);
                     queue_trcbk(id, g);
                 }
             }
@@ -289,16 +253,16 @@ extern "C" int gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
         if (!pending.empty() && pending.back() == -1) {
             pending.pop_back();
             // a level with only forward tasks: loop once more with no items to classify
-            std::vector<gspaln_task> b2;
+            std::vector<Task> b2;
             std::vector<gspaln_result> r2;
             std::vector<std::vector<int>> s2(fwds.size() - fwd_done);
             for (size_t f = fwd_done; f < fwds.size(); ++f) {
-                b2.push_back(lsp_task(tasks[fwds[f].root], fwds[f].g, GSPALN_FORWARD_WIP, 0));
+                b2.push_back(TR::make_task(tasks[fwds[f].root], fwds[f].g, GSPALN_FORWARD_WIP, 0));
                 s2[f - fwd_done].assign(2 * (size_t) b2.back().skl_cap, 0);
             }
             r2.resize(b2.size());
             for (size_t f = 0; f < b2.size(); ++f) { r2[f].skl = s2[f].data(); r2[f].cpos = nullptr; }
-            int rc = gspaln_submit(ctx, b2.data(), (int) b2.size(), r2.data());
+            int rc = TR::submit(ctx, b2.data(), (int) b2.size(), r2.data());
             if (rc != GSPALN_OK) return rc;
             kernel_ms += ctx->tim.kernel_ms; h2d_ms += ctx->tim.h2d_ms; d2h_ms += ctx->tim.d2h_ms;
             launches += ctx->tim.launches; h2d_bytes += ctx->tim.h2d_bytes; d2h_bytes += ctx->tim.d2h_bytes;
@@ -334,7 +298,7 @@ extern "C" int gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
         o.status = status[i];
         o.n_skl = (int) out.size();
         o.reserved = 0;
-        o.cells = task_cells(tasks[i]);
+        o.cells = TR::cells(tasks[i]);
         const int cap = tasks[i].skl_cap;
         if (o.status == GSPALN_ST_OK && o.n_skl > cap) o.status = GSPALN_ST_SKL_OVERFLOW;
         if (o.skl)
