@@ -28,6 +28,9 @@ struct gspaln_ctx {
     int sm_count = 0;
     gspaln_params prm;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;    // H2D of the chunks that follow the first one
+    cudaEvent_t ev_sync[2] = {nullptr, nullptr};
+    PinBuf<int> h_marks;                    // watermark values, one per chunk
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf<DevParams> d_prm;
     DevBuf<int2> d_pen;
@@ -82,7 +85,7 @@ int fail(gspaln_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
 
 using KernelFn = void (*)(const DevParams*, const int2*, const DevTask*, const int*, int, int*,
                           const unsigned char*, const ColInfo*, unsigned*, long long,
-                          unsigned char*, long long, int2*, DevResult*);
+                          unsigned char*, long long, int2*, DevResult*, const int*);
 
 KernelFn kernel_fn(bool trace, bool local, bool spj)
 {
@@ -102,7 +105,7 @@ const void* kernel_ptr(bool trace, bool local, bool spj)
 
 using UdhKernelFn = void (*)(const DevParams*, const int2*, const DevTask*, const int*, int, int*,
                              const unsigned char*, const ColInfo*, unsigned*, long long, int*,
-                             long long, int*, DevUdhOut*);
+                             long long, int*, DevUdhOut*, const int*);
 
 UdhKernelFn udh_kernel_fn(bool spj, bool local)
 {
@@ -161,6 +164,8 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
     memset(&ctx->tim, 0, sizeof(ctx->tim));
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_sync[i], cudaEventDisableTiming);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
@@ -215,7 +220,7 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
         gspaln_destroy(ctx);
         return GSPALN_EINVAL;
     }
-    if (ctx->d_prm.reserve(1) != cudaSuccess || ctx->d_ticket.reserve(4) != cudaSuccess ||
+    if (ctx->d_prm.reserve(1) != cudaSuccess || ctx->d_ticket.reserve(64) != cudaSuccess ||
         ctx->d_pen.reserve(cap + 1) != cudaSuccess ||
         cudaMemcpy(ctx->d_pen.p, pen.data(), sizeof(int2) * (cap + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(ctx->d_prm.p, &P, sizeof(P), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -252,23 +257,21 @@ void gspaln_destroy(gspaln_ctx* ctx)
     ctx->h_tasks.release(); ctx->h_order.release(); ctx->h_apool.release(); ctx->h_cpool.release();
     ctx->h_skl.release(); ctx->h_res.release(); ctx->h_cpos.release(); ctx->h_ures.release();
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->ev_sync) if (e) cudaEventDestroy(e);
+    ctx->h_marks.release();
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
-int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
+// ---- planning: validation, longest-first order, pool offsets (assigned along that order so
+// that any contiguous range of the order is contiguous in every pool), workspaces, grids
+static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
 {
-    if (!ctx || !tasks || n < 0) return GSPALN_EINVAL;
     CK(cudaSetDevice(ctx->device));
     ctx->n = 0;
-    // ---- layout
-    size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, skl_elems = 0;
-    size_t udh_slab = 0, cpos_elems = 0;
-    int n_udh = 0;
     ctx->cells.assign(n, 0);
     ctx->skl_cap.assign(n, 0);
-    std::vector<DevTask> dt(n);
-    int n_trace = 0, n_score = 0;
     for (int i = 0; i < n; ++i) {
         const gspaln_task& t = tasks[i];
         if (t.a_right < t.a_left || t.b_right < t.b_left || t.up < t.lw ||
@@ -276,7 +279,21 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             (t.kind == GSPALN_HIRSCHBERG_WIP && (t.n_imd < 1 || t.a_right - t.a_left < 2)) ||
             !t.a || !t.b || (ctx->prm.spj && (!t.sig5 || !t.sig3)))
             return fail(ctx, GSPALN_EINVAL, "bad task");
-        DevTask& d = dt[i];
+        ctx->cells[i] = task_cells(t);
+    }
+    if (ctx->h_tasks.reserve(n + 1) != cudaSuccess || ctx->h_order.reserve(n + 1) != cudaSuccess)
+        return fail(ctx, GSPALN_ENOMEM, "pinned host allocation");
+    // largest problems first (longest-processing-time order for the ticket queue)
+    std::iota(ctx->h_order.p, ctx->h_order.p + n, 0);
+    std::stable_sort(ctx->h_order.p, ctx->h_order.p + n,
+                     [&](int x, int y) { return ctx->cells[x] > ctx->cells[y]; });
+    size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, skl_elems = 0;
+    size_t udh_slab = 0, cpos_elems = 0;
+    int n_trace = 0, n_score = 0, n_udh = 0;
+    for (int k = 0; k < n; ++k) {
+        const int i = ctx->h_order.p[k];
+        const gspaln_task& t = tasks[i];
+        DevTask& d = ctx->h_tasks.p[i];
         d.kind = t.kind;
         d.a_left = t.a_left; d.a_right = t.a_right; d.b_left = t.b_left; d.b_right = t.b_right;
         d.lw = t.lw; d.up = t.up;
@@ -285,8 +302,10 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         d.pad0 = 0;
         const int mw = t.a_right - t.a_left, nw = t.b_right - t.b_left;
         const int width = t.up - t.lw + 3;
-        d.a_off = (long long) a_bytes;      a_bytes += align_up((size_t) mw + 1, 16);
-        d.col_off = (long long) c_elems;    c_elems += align_up((size_t) nw + 2, 4);
+        // 128-byte granules: a problem whose inputs arrive later never shares a cache line with
+        // one that is already being read (one-shot submits stream the batch in)
+        d.a_off = (long long) a_bytes;      a_bytes += align_up((size_t) mw + 1, 128);
+        d.col_off = (long long) c_elems;    c_elems += align_up((size_t) nw + 2, 16);
         band_slab = std::max(band_slab, align_up((size_t) width + 2 * NELEM, 32));
         d.skl_off = (long long) skl_elems;
         d.pad1 = 0;
@@ -304,11 +323,9 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             ++n_udh;
         } else
             ++n_score;
-        ctx->cells[i] = task_cells(t);
         ctx->skl_cap[i] = d.skl_cap;
     }
-    if (ctx->h_tasks.reserve(n + 1) != cudaSuccess || ctx->h_order.reserve(n + 1) != cudaSuccess ||
-        ctx->h_apool.reserve(a_bytes + 16) != cudaSuccess || ctx->h_cpool.reserve(c_elems + 4) != cudaSuccess ||
+    if (ctx->h_apool.reserve(a_bytes + 16) != cudaSuccess || ctx->h_cpool.reserve(c_elems + 4) != cudaSuccess ||
         ctx->h_res.reserve(n + 1) != cudaSuccess || ctx->h_skl.reserve(skl_elems + 1) != cudaSuccess ||
         ctx->h_cpos.reserve(cpos_elems + 1) != cudaSuccess || ctx->h_ures.reserve(n + 1) != cudaSuccess)
         return fail(ctx, GSPALN_ENOMEM, "pinned host allocation");
@@ -346,64 +363,6 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         ctx->grid_run_trace = gt;
         ctx->grid_run_score = gs;
     }
-    // ---- pack (host work is part of the end-to-end path): problems are dealt to a
-    // few host threads; every problem writes a disjoint slice of the pinned pools
-    {
-        auto pack_range = [&](int lo, int hi) {
-            for (int i = lo; i < hi; ++i) {
-                const gspaln_task& t = tasks[i];
-                const DevTask& d = dt[i];
-                const int mw = t.a_right - t.a_left, nw = t.b_right - t.b_left;
-                unsigned char* ap = ctx->h_apool.p + d.a_off;
-                for (int j = 0; j < mw; ++j) ap[j] = ctx->perm[t.a[t.a_left + j] & 31];
-                ColInfo* col = ctx->h_cpool.p + d.col_off;
-                const bool spj = ctx->prm.spj != 0;
-                for (int j = 0; j <= nw; ++j) {
-                    const int c = t.b_left + j;     // column c pairs genome residue at(c - 1)
-                    ColInfo ci;
-                    ci.sig5 = spj ? t.sig5[c] : 0;
-                    ci.sig3 = spj ? t.sig3[c] : 0;
-                    ci.code = j > 0 ? ctx->perm[t.b[c - 1] & 31] : 0;
-                    ci.pad[0] = ci.pad[1] = ci.pad[2] = 0;
-                    col[j] = ci;
-                }
-                ctx->h_tasks.p[i] = d;
-            }
-        };
-        const size_t work = c_elems + a_bytes;
-        int nthr = (int) std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
-        if (work < (1u << 20) || n < 2 * nthr) nthr = 1;
-        if (nthr == 1) pack_range(0, n);
-        else {
-            // contiguous ranges balanced by column count
-            std::vector<std::thread> pool;
-            size_t acc = 0, per = (work + nthr - 1) / nthr;
-            int lo = 0;
-            for (int i = 0; i < n; ++i) {
-                acc += (size_t) (tasks[i].b_right - tasks[i].b_left) + (tasks[i].a_right - tasks[i].a_left);
-                if (acc >= per || i == n - 1) {
-                    pool.emplace_back(pack_range, lo, i + 1);
-                    lo = i + 1; acc = 0;
-                }
-            }
-            for (auto& th : pool) th.join();
-        }
-    }
-    // largest problems first (longest-processing-time order for the ticket queue)
-    std::iota(ctx->h_order.p, ctx->h_order.p + n, 0);
-    std::stable_sort(ctx->h_order.p, ctx->h_order.p + n,
-                     [&](int x, int y) { return ctx->cells[x] > ctx->cells[y]; });
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_tasks.p, ctx->h_tasks.p, sizeof(DevTask) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.p, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_apool.p, ctx->h_apool.p, a_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_cpool.p, ctx->h_cpool.p, sizeof(ColInfo) * c_elems, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    ctx->tim.h2d_ms = ms;
-    ctx->tim.h2d_bytes = (int64_t) (sizeof(DevTask) * n + sizeof(int) * n + a_bytes + sizeof(ColInfo) * c_elems);
     ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score; ctx->n_udh = n_udh;
     ctx->udh_slab = udh_slab; ctx->cpos_elems = cpos_elems;
     ctx->a_bytes = a_bytes; ctx->c_elems = c_elems; ctx->band_slab = band_slab;
@@ -418,6 +377,119 @@ int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
     return GSPALN_OK;
 }
 
+// ---- packing of the problems order[lo .. hi) into the pinned pools (host work is part of the
+// end-to-end path): dealt to a few host threads, every problem writes a disjoint slice
+static void pack_range(gspaln_ctx* ctx, const gspaln_task* tasks, int lo, int hi)
+{
+    auto pack_some = [&](int klo, int khi) {
+        for (int k = klo; k < khi; ++k) {
+            const int i = ctx->h_order.p[k];
+            const gspaln_task& t = tasks[i];
+            const DevTask& d = ctx->h_tasks.p[i];
+            const int mw = t.a_right - t.a_left, nw = t.b_right - t.b_left;
+            unsigned char* ap = ctx->h_apool.p + d.a_off;
+            for (int j = 0; j < mw; ++j) ap[j] = ctx->perm[t.a[t.a_left + j] & 31];
+            ColInfo* col = ctx->h_cpool.p + d.col_off;
+            const bool spj = ctx->prm.spj != 0;
+            for (int j = 0; j <= nw; ++j) {
+                const int c = t.b_left + j;     // column c pairs genome residue at(c - 1)
+                ColInfo ci;
+                ci.sig5 = spj ? t.sig5[c] : 0;
+                ci.sig3 = spj ? t.sig3[c] : 0;
+                ci.code = j > 0 ? ctx->perm[t.b[c - 1] & 31] : 0;
+                ci.pad[0] = ci.pad[1] = ci.pad[2] = 0;
+                col[j] = ci;
+            }
+        }
+    };
+    size_t work = 0;
+    for (int k = lo; k < hi; ++k) {
+        const gspaln_task& t = tasks[ctx->h_order.p[k]];
+        work += (size_t) (t.b_right - t.b_left) + (t.a_right - t.a_left);
+    }
+    int nthr = (int) std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    if (work < (1u << 20) || hi - lo < 2 * nthr) nthr = 1;
+    if (nthr == 1) { pack_some(lo, hi); return; }
+    std::vector<std::thread> pool;
+    size_t acc = 0, per = (work + nthr - 1) / nthr;
+    int from = lo;
+    for (int k = lo; k < hi; ++k) {
+        const gspaln_task& t = tasks[ctx->h_order.p[k]];
+        acc += (size_t) (t.b_right - t.b_left) + (t.a_right - t.a_left);
+        if (acc >= per || k == hi - 1) {
+            pool.emplace_back(pack_some, from, k + 1);
+            from = k + 1; acc = 0;
+        }
+    }
+    for (auto& th : pool) th.join();
+}
+
+// pool ranges [begin, end) covered by order[lo .. hi)
+static void pool_span(const gspaln_ctx* ctx, const gspaln_task* tasks, int lo, int hi, size_t& a0, size_t& a1,
+                      size_t& c0, size_t& c1)
+{
+    const DevTask& f = ctx->h_tasks.p[ctx->h_order.p[lo]];
+    const int li = ctx->h_order.p[hi - 1];
+    const DevTask& l = ctx->h_tasks.p[li];
+    a0 = (size_t) f.a_off; c0 = (size_t) f.col_off;
+    a1 = (size_t) l.a_off + align_up((size_t) (tasks[li].a_right - tasks[li].a_left) + 1, 128);
+    c1 = (size_t) l.col_off + align_up((size_t) (tasks[li].b_right - tasks[li].b_left) + 2, 16);
+}
+
+// launches the kernels for order[lo .. hi) with ticket slot `slot` (3 counters per slot)
+static int launch_range(gspaln_ctx* ctx, int lo, int hi, int slot, int& launches, const int* ready = nullptr)
+{
+    const bool local = ctx->prm.local != 0, spj = ctx->prm.spj != 0;
+    int* tick = ctx->d_ticket.p + 3 * slot;
+    const int cnt = hi - lo;
+    if (ctx->n_trace) {
+        kernel_fn(true, local, spj)<<<ctx->grid_run_trace, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+            ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick,
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
+            ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p, ready);
+        ++launches;
+    }
+    if (ctx->n_score) {
+        kernel_fn(false, local, spj)<<<ctx->grid_run_score, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+            ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 1,
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
+            ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p, ready);
+        ++launches;
+    }
+    if (ctx->n_udh) {
+        auto ku = udh_kernel_fn(spj, local);
+        ku<<<ctx->grid_run_udh, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+            ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 2,
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
+            ctx->d_udh.p, (long long) ctx->udh_slab, ctx->d_cpos.p, ctx->d_ures.p, ready);
+        ++launches;
+    }
+    CK(cudaGetLastError());
+    return GSPALN_OK;
+}
+
+constexpr int MAX_CHUNKS = 16;
+
+int gspaln_upload(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
+{
+    if (!ctx || !tasks || n < 0) return GSPALN_EINVAL;
+    int rc = plan_batch(ctx, tasks, n);
+    if (rc != GSPALN_OK) return rc;
+    if (n) pack_range(ctx, tasks, 0, n);
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_tasks.p, ctx->h_tasks.p, sizeof(DevTask) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.p, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_apool.p, ctx->h_apool.p, ctx->a_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_cpool.p, ctx->h_cpool.p, sizeof(ColInfo) * ctx->c_elems, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->tim.h2d_ms = ms;
+    ctx->tim.h2d_bytes = (int64_t) (sizeof(DevTask) * n + sizeof(int) * n + ctx->a_bytes + sizeof(ColInfo) * ctx->c_elems);
+    return GSPALN_OK;
+}
+
 int gspaln_run(gspaln_ctx* ctx)
 {
     if (!ctx) return GSPALN_EINVAL;
@@ -426,33 +498,9 @@ int gspaln_run(gspaln_ctx* ctx)
     int launches = 0;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (n > 0) {
-        const bool local = ctx->prm.local != 0, spj = ctx->prm.spj != 0;
-        if (ctx->n_trace) {
-            CK(cudaMemsetAsync(ctx->d_ticket.p, 0, sizeof(int), ctx->stream));
-            kernel_fn(true, local, spj)<<<ctx->grid_run_trace, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
-                ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p,
-                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
-                ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p);
-            ++launches;
-        }
-        if (ctx->n_score) {
-            CK(cudaMemsetAsync(ctx->d_ticket.p + 1, 0, sizeof(int), ctx->stream));
-            kernel_fn(false, local, spj)<<<ctx->grid_run_score, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
-                ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p + 1,
-                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
-                ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p);
-            ++launches;
-        }
-        if (ctx->n_udh) {
-            CK(cudaMemsetAsync(ctx->d_ticket.p + 2, 0, sizeof(int), ctx->stream));
-            auto ku = udh_kernel_fn(spj, local);
-            ku<<<ctx->grid_run_udh, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
-                ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p + 2,
-                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
-                ctx->d_udh.p, (long long) ctx->udh_slab, ctx->d_cpos.p, ctx->d_ures.p);
-            ++launches;
-        }
-        CK(cudaGetLastError());
+        CK(cudaMemsetAsync(ctx->d_ticket.p, 0, 3 * sizeof(int), ctx->stream));
+        int rc = launch_range(ctx, 0, n, 0, launches);
+        if (rc != GSPALN_OK) return rc;
     }
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -503,12 +551,77 @@ int gspaln_download(gspaln_ctx* ctx, gspaln_result* results)
     return GSPALN_OK;
 }
 
+// One-shot path.  The persistent kernels consume the problems in longest-first ticket order, so
+// a large batch is streamed in along that order: the first chunk is packed and copied, the
+// kernels start, and while they run the host threads pack the following chunks into pinned
+// memory and a second stream copies them and advances a watermark the kernels wait on.
+// Packing and H2D of everything but the first chunk hide behind the DP.
 int gspaln_submit(gspaln_ctx* ctx, const gspaln_task* tasks, int n, gspaln_result* results)
 {
-    int rc = gspaln_upload(ctx, tasks, n);
-    if (rc == GSPALN_OK) rc = gspaln_run(ctx);
-    if (rc == GSPALN_OK) rc = gspaln_download(ctx, results);
-    return rc;
+    if (!ctx || !tasks || n < 0) return GSPALN_EINVAL;
+    int rc = plan_batch(ctx, tasks, n);
+    if (rc != GSPALN_OK) return rc;
+    int bounds[MAX_CHUNKS + 1];
+    int nchunks = 1;
+    bounds[0] = 0; bounds[1] = n;
+    const size_t total = ctx->c_elems;
+    if (n >= 256 && total >= (4u << 20)) {
+        // boundaries by cumulative columns (what packing and H2D cost); small first chunk
+        nchunks = 0;
+        size_t acc = 0;
+        const int want = (int) std::min<size_t>(MAX_CHUNKS, 2 + total / (6u << 20));
+        size_t next = total / (2 * (size_t) want);
+        for (int k = 0; k < n; ++k) {
+            const gspaln_task& t = tasks[ctx->h_order.p[k]];
+            acc += (size_t) (t.b_right - t.b_left) + 2;
+            if (acc >= next && nchunks + 1 < want && k + 1 < n) {
+                bounds[++nchunks] = k + 1;
+                next = acc + (total - acc) / (size_t) (want - nchunks);
+            }
+        }
+        bounds[++nchunks] = n;
+    }
+    if (ctx->h_marks.reserve(MAX_CHUNKS + 1) != cudaSuccess) return fail(ctx, GSPALN_ENOMEM, "pinned host allocation");
+    int* d_ready = ctx->d_ticket.p + 32;
+    CK(cudaMemsetAsync(ctx->d_ticket.p, 0, 40 * sizeof(int), ctx->stream));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_tasks.p, ctx->h_tasks.p, sizeof(DevTask) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.p, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    int launches = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int lo = bounds[c], hi = bounds[c + 1];
+        if (hi <= lo) continue;
+        pack_range(ctx, tasks, lo, hi);
+        size_t a0, a1, c0, c1;
+        pool_span(ctx, tasks, lo, hi, a0, a1, c0, c1);
+        cudaStream_t st = c == 0 ? ctx->stream : ctx->copy_stream;
+        CK(cudaMemcpyAsync(ctx->d_apool.p + a0, ctx->h_apool.p + a0, a1 - a0, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_cpool.p + c0, ctx->h_cpool.p + c0, sizeof(ColInfo) * (c1 - c0), cudaMemcpyHostToDevice, st));
+        ctx->h_marks.p[c] = hi;
+        CK(cudaMemcpyAsync(d_ready, ctx->h_marks.p + c, sizeof(int), cudaMemcpyHostToDevice, st));
+        if (c == 0) {
+            // the kernels start once the first chunk (and the watermark reset) is in place; the
+            // copy stream must not advance the watermark before that reset either
+            CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+            CK(cudaEventRecord(ctx->ev_sync[0], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_sync[0], 0));
+            CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+            rc = launch_range(ctx, 0, n, 0, launches, nchunks > 1 ? d_ready : nullptr);
+            if (rc != GSPALN_OK) return rc;
+        }
+    }
+    if (n == 0) { CK(cudaEventRecord(ctx->ev[1], ctx->stream)); CK(cudaEventRecord(ctx->ev[2], ctx->stream)); }
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->tim.h2d_ms = ms;           // first chunk only: the rest overlaps the kernels
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+    ctx->tim.kernel_ms = ms;
+    ctx->tim.launches = launches;
+    ctx->tim.h2d_bytes = (int64_t) (sizeof(DevTask) * n + sizeof(int) * n + ctx->a_bytes + sizeof(ColInfo) * ctx->c_elems);
+    return gspaln_download(ctx, results);
 }
 
 int gspaln_get_timing(const gspaln_ctx* ctx, gspaln_timing* out)

@@ -126,6 +126,26 @@ __device__ __forceinline__ StripGeom strip_geom(const DevTask& t, int ml)
 
 struct WarpMax { int val, mr, nr, err; };
 
+// One-shot submits stream the batch in while the persistent kernel runs: `ready` counts the
+// problems (in ticket order) whose inputs have arrived in HBM.  Returns false on time-out
+// (~4 s: the host died or a copy failed) so that the kernel never spins forever.
+__device__ __forceinline__ bool wait_inputs(const int* ready, int tk)
+{
+    if (!ready) return true;
+    int ok = 1;
+    if ((threadIdx.x & 31) == 0) {
+        const volatile int* r = ready;
+        const long long t0 = clock64();
+        while (*r <= tk) {
+            __nanosleep(256);
+            if (clock64() - t0 > (1ll << 33)) { ok = 0; break; }
+        }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    __syncwarp();
+    return ok != 0;
+}
+
 // shared-memory carve-up of one CTA
 struct SmemLayout {
     RingEntry* ring;            // [RING][CTA_THREADS]
@@ -533,7 +553,7 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
               const int* __restrict__ order, int ntasks, int* ticket,
               const unsigned char* __restrict__ apool, const ColInfo* __restrict__ cpool,
               unsigned* bandpool, long long band_slab, unsigned char* tracepool,
-              long long trace_slab, int2* sklpool, DevResult* results)
+              long long trace_slab, int2* sklpool, DevResult* results, const int* ready)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ DevParams sP;
@@ -567,6 +587,10 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
         const int ti = order[tk];
         const DevTask t = tasks[ti];
         if ((t.kind == 0) != TRACE) continue;       // handled by the other instantiation
+        if (!wait_inputs(ready, tk)) {
+            if (lane == 0) { DevResult r; r.score = 0; r.status = 4; r.n_skl = 0; r.pad = 0; results[ti] = r; }
+            continue;
+        }
         const unsigned char* aseq = apool + t.a_off;
         const ColInfo* cols = cpool + t.col_off;
         const int width = t.up - t.lw + 3;

@@ -403,7 +403,7 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
               const DevTask* __restrict__ tasks, const int* __restrict__ order, int ntasks, int* ticket,
               const unsigned char* __restrict__ apool, const ColInfo* __restrict__ cpool,
               unsigned* bandpool, long long band_slab, int* udhpool, long long udh_slab,
-              int* cpospool, DevUdhOut* results)
+              int* cpospool, DevUdhOut* results, const int* ready)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ DevParams sP;
@@ -435,6 +435,10 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
         const int ti = order[tk];
         const DevTask t = tasks[ti];
         if (t.kind != 2) continue;
+        if (!wait_inputs(ready, tk)) {
+            if (lane == 0) { DevUdhOut r; memset(&r, 0, sizeof(r)); r.status = 4; results[ti] = r; }
+            continue;
+        }
         const unsigned char* aseq = apool + t.a_off;
         const ColInfo* cols = cpool + t.col_off;
         const int width = t.up - t.lw + 3;
