@@ -122,13 +122,7 @@ const void* udh_kernel_ptr(bool spj, bool local)
 int64_t task_cells(const gspaln_task& t)
 {
     // rows m in (a_left, a_right], columns max(m + lw, b_left) < n <= min(m + up + 1, b_right)
-    int64_t cells = 0;
-    for (int m = t.a_left + 1; m <= t.a_right; ++m) {
-        int lo = std::max(m + t.lw, t.b_left);
-        int hi = std::min(m + t.up + 1, t.b_right);
-        if (hi > lo) cells += hi - lo;
-    }
-    return cells;
+    return band_cells(t.a_left, t.a_right, 1, t.lw, t.b_left, t.up + 1, t.b_right);
 }
 
 }   // namespace

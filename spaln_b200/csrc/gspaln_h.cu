@@ -24,6 +24,9 @@ struct gspaln_h_ctx {
     int sm_count = 0;
     gspaln_h_params prm;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;    // H2D of the chunks that follow the first one
+    cudaEvent_t ev_sync[2] = {nullptr, nullptr};
+    PinBuf<int> h_marks;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf<DevParamsH> d_prm;
     DevBuf<int2> d_pen;
@@ -77,7 +80,7 @@ int fail(gspaln_h_ctx* c, int code, const char* what, cudaError_t e = cudaSucces
 
 using KernelH = void (*)(const DevParamsH*, const int2*, const DevTaskH*, const int*, int, int*,
                          const unsigned char*, const ColH*, const ColEnd*, unsigned*, long long,
-                         unsigned short*, long long, unsigned char*, long long, int2*, DevResult*);
+                         unsigned short*, long long, unsigned char*, long long, int2*, DevResult*, const int*);
 
 KernelH kernel_h(bool trace, bool local, bool spj)
 {
@@ -92,7 +95,7 @@ KernelH kernel_h(bool trace, bool local, bool spj)
 
 using KernelUdhH = void (*)(const DevParamsH*, const int2*, const DevTaskH*, const int*, int, int*,
                             const unsigned char*, const ColH*, const ColEnd*, int*, long long, int*,
-                            DevUdhOutH*);
+                            DevUdhOutH*, const int*);
 
 KernelUdhH kernel_udh_h(bool local, bool spj)
 {
@@ -104,47 +107,7 @@ KernelUdhH kernel_udh_h(bool local, bool spj)
 int64_t task_cells_h(const gspaln_h_task& t)
 {
     // rows m in (a_left, a_right], columns max(3m + lw - 1, b_left) < n <= min(3m + up, b_right)
-    int64_t cells = 0;
-    for (int m = t.a_left + 1; m <= t.a_right; ++m) {
-        const int lo = std::max(3 * m + t.lw - 1, t.b_left);
-        const int hi = std::min(3 * m + t.up, t.b_right);
-        if (hi > lo) cells += hi - lo;
-    }
-    return cells;
-}
-
-// the column record of genome column c (what enters lane 0 of the reference's shift registers
-// at step n == c: src/fwd2h1_wip_simd.h:115-117 (cv), 189-192 (profile), 208-222 / 270-283 (signals))
-ColH derive_col(const gspaln_h_task& t, const gspaln_h_params& prm, int c)
-{
-    ColH o;
-    memset(&o, 0, sizeof(o));
-    unsigned flags = 0;
-    auto sg = [&](int i) -> const gspaln_sgpt6* { return (i >= 0 && i <= t.b_len + 1) ? t.sg + i : nullptr; };
-    if (prm.spj && c < t.b_right) {
-        const gspaln_sgpt6* s = sg(c);
-        const int ipen = prm.ipen;
-        if (s) {
-            auto put3 = [&](int phase) {
-                const gspaln_sgpt6* q = sg(c - phase);
-                o.s3[phase + 1] = q ? q->sig3 : 0;
-                flags |= 1u << (phase + 1);
-            };
-            auto put5 = [&](int phase) {
-                const gspaln_sgpt6* q = sg(c - phase);
-                o.s5[phase + 1] = (short) ((q ? q->sig5 : 0) + ipen);
-                flags |= 8u << (phase + 1);
-            };
-            if (s->phs3 == 2) { put3(-1); put3(1); }
-            else if (s->phs3 > -2) put3(s->phs3);
-            if (s->phs5 == 2) { put5(-1); put5(1); }
-            else if (s->phs5 > -2) put5(s->phs5);
-        }
-    }
-    if (c - 2 >= 0 && c - 2 < t.b_len) o.cv = t.sg[c - 2].sigE;
-    o.prof = (c >= t.b_left + 3 && c <= t.b_right + 2) ? (unsigned char) (t.b[c - 2] & 31) : (unsigned char) ZROW;
-    o.flags = (unsigned char) flags;
-    return o;
+    return band_cells(t.a_left, t.a_right, 3, (long long) t.lw - 1, t.b_left, t.up, t.b_right);
 }
 
 }   // namespace
@@ -173,6 +136,8 @@ int gspaln_h_create(gspaln_h_ctx** out, const gspaln_h_params* prm, int device)
     memset(&ctx->tim, 0, sizeof(ctx->tim));
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_sync[i], cudaEventDisableTiming);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
@@ -207,7 +172,7 @@ int gspaln_h_create(gspaln_h_ctx** out, const gspaln_h_params* prm, int device)
     ctx->pen_cap = cap;
     ctx->smem_bytes = sizeof(RingH) * RINGH * SPPH * WARPS_PER_CTA + sizeof(int2) * pen.size();
     if (ctx->smem_bytes > 100 * 1024) { gspaln_h_destroy(ctx); return GSPALN_EINVAL; }
-    if (ctx->d_prm.reserve(1) != cudaSuccess || ctx->d_ticket.reserve(4) != cudaSuccess ||
+    if (ctx->d_prm.reserve(1) != cudaSuccess || ctx->d_ticket.reserve(64) != cudaSuccess ||
         ctx->d_pen.reserve(pen.size()) != cudaSuccess ||
         cudaMemcpy(ctx->d_pen.p, pen.data(), sizeof(int2) * pen.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(ctx->d_prm.p, &P, sizeof(P), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -246,20 +211,19 @@ void gspaln_h_destroy(gspaln_h_ctx* ctx)
     ctx->h_tasks.release(); ctx->h_order.release(); ctx->h_apool.release(); ctx->h_cpool.release();
     ctx->h_epool.release(); ctx->h_skl.release(); ctx->h_res.release();
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->ev_sync) if (e) cudaEventDestroy(e);
+    ctx->h_marks.release();
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
-int gspaln_h_upload(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n)
+// ---- planning: validation, longest-first order, pool offsets along that order, workspaces, grids
+static int plan_batch_h(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n)
 {
-    if (!ctx || !tasks || n < 0) return GSPALN_EINVAL;
     CKH(cudaSetDevice(ctx->device));
     ctx->n = 0;
-    size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, row_slab = 0, skl_elems = 0;
-    size_t ws_slab = 0, cpos_elems = 0;
     ctx->cells.assign(n, 0);
-    std::vector<DevTaskH> dt(n);
-    int n_trace = 0, n_score = 0, n_udh = 0;
     for (int i = 0; i < n; ++i) {
         const gspaln_h_task& t = tasks[i];
         if (t.a_right < t.a_left || t.b_right < t.b_left || t.up < t.lw || t.a_left < 0 || t.b_left < 0 ||
@@ -268,7 +232,20 @@ int gspaln_h_upload(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n)
             (t.kind == GSPALN_HIRSCHBERG_WIP && (t.n_imd < 1 || t.a_right - t.a_left < 2)) ||
             !t.a || !t.b || !t.sg)
             return fail(ctx, GSPALN_EINVAL, "bad task");
-        DevTaskH& d = dt[i];
+        ctx->cells[i] = task_cells_h(t);
+    }
+    if (ctx->h_tasks.reserve(n + 1) != cudaSuccess || ctx->h_order.reserve(n + 1) != cudaSuccess)
+        return fail(ctx, GSPALN_ENOMEM, "pinned host allocation");
+    std::iota(ctx->h_order.p, ctx->h_order.p + n, 0);
+    std::stable_sort(ctx->h_order.p, ctx->h_order.p + n,
+                     [&](int x, int y) { return ctx->cells[x] > ctx->cells[y]; });
+    size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, row_slab = 0, skl_elems = 0;
+    size_t ws_slab = 0, cpos_elems = 0;
+    int n_trace = 0, n_score = 0, n_udh = 0;
+    for (int k = 0; k < n; ++k) {
+        const int i = ctx->h_order.p[k];
+        const gspaln_h_task& t = tasks[i];
+        DevTaskH& d = ctx->h_tasks.p[i];
         d.kind = t.kind;
         d.a_left = t.a_left; d.a_right = t.a_right; d.b_left = t.b_left; d.b_right = t.b_right;
         d.lw = t.lw; d.up = t.up;
@@ -277,8 +254,9 @@ int gspaln_h_upload(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n)
         d.b_len = t.b_len;
         const int mw = t.a_right - t.a_left, nw = t.b_right - t.b_left;
         const int width = t.up - t.lw + 7;
-        d.a_off = (long long) a_bytes;      a_bytes += align_up((size_t) mw + 1, 16);
-        d.col_off = (long long) c_elems;    c_elems += align_up((size_t) nw + COL_TAIL_H + 2, 4);
+        // 128-byte granules in every pool (inputs of later problems arrive while earlier ones are read)
+        d.a_off = (long long) a_bytes;      a_bytes += align_up((size_t) mw + 1, 128);
+        d.col_off = (long long) c_elems;    c_elems += align_up((size_t) nw + COL_TAIL_H + 2, 16);
         band_slab = std::max(band_slab, align_up((size_t) width + BAND_PAD_H + 8, 32));
         row_slab = std::max(row_slab, 2 * align_up((size_t) width + 16, 64));
         d.skl_off = (long long) skl_elems;
@@ -295,10 +273,8 @@ int gspaln_h_upload(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n)
             ++n_udh;
         } else
             ++n_score;
-        ctx->cells[i] = task_cells_h(t);
     }
-    if (ctx->h_tasks.reserve(n + 1) != cudaSuccess || ctx->h_order.reserve(n + 1) != cudaSuccess ||
-        ctx->h_apool.reserve(a_bytes + 16) != cudaSuccess || ctx->h_cpool.reserve(c_elems + 4) != cudaSuccess ||
+    if (ctx->h_apool.reserve(a_bytes + 16) != cudaSuccess || ctx->h_cpool.reserve(c_elems + 4) != cudaSuccess ||
         ctx->h_epool.reserve(c_elems + 4) != cudaSuccess ||
         ctx->h_res.reserve(n + 1) != cudaSuccess || ctx->h_skl.reserve(skl_elems + 1) != cudaSuccess ||
         ctx->h_cpos.reserve(cpos_elems + 1) != cudaSuccess || ctx->h_ures.reserve(n + 1) != cudaSuccess)
@@ -338,63 +314,6 @@ int gspaln_h_upload(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n)
         }
         ctx->grid_run_udh = gu;
     }
-    {
-        auto pack_range = [&](int lo, int hi) {
-            for (int i = lo; i < hi; ++i) {
-                const gspaln_h_task& t = tasks[i];
-                const DevTaskH& d = dt[i];
-                const int mw = t.a_right - t.a_left, nw = t.b_right - t.b_left;
-                unsigned char* ap = ctx->h_apool.p + d.a_off;
-                for (int j = 0; j < mw; ++j) ap[j] = (unsigned char) (t.a[t.a_left + j] & 31);
-                ColH* col = ctx->h_cpool.p + d.col_off;
-                ColEnd* ce = ctx->h_epool.p + d.col_off;
-                for (int j = 0; j <= nw + COL_TAIL_H; ++j) {
-                    const int c = t.b_left + j;
-                    col[j] = derive_col(t, ctx->prm, c);
-                    ColEnd e = {0, 0, 0, 0};
-                    if (c <= t.b_len + 1) {
-                        const gspaln_sgpt6& s = t.sg[c];
-                        e.sigS = s.sigS; e.sigT = s.sigT; e.sigE = s.sigE; e.sig5 = s.sig5;
-                    }
-                    ce[j] = e;
-                }
-                ctx->h_tasks.p[i] = d;
-            }
-        };
-        const size_t work = c_elems + a_bytes;
-        int nthr = (int) std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
-        if (work < (1u << 19) || n < 2 * nthr) nthr = 1;
-        if (nthr == 1) pack_range(0, n);
-        else {
-            std::vector<std::thread> pool;
-            size_t acc = 0, per = (work + nthr - 1) / nthr;
-            int lo = 0;
-            for (int i = 0; i < n; ++i) {
-                acc += (size_t) (tasks[i].b_right - tasks[i].b_left) + (tasks[i].a_right - tasks[i].a_left);
-                if (acc >= per || i == n - 1) {
-                    pool.emplace_back(pack_range, lo, i + 1);
-                    lo = i + 1; acc = 0;
-                }
-            }
-            for (auto& th : pool) th.join();
-        }
-    }
-    std::iota(ctx->h_order.p, ctx->h_order.p + n, 0);
-    std::stable_sort(ctx->h_order.p, ctx->h_order.p + n,
-                     [&](int x, int y) { return ctx->cells[x] > ctx->cells[y]; });
-    CKH(cudaEventRecord(ctx->ev[0], ctx->stream));
-    CKH(cudaMemcpyAsync(ctx->d_tasks.p, ctx->h_tasks.p, sizeof(DevTaskH) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CKH(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.p, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CKH(cudaMemcpyAsync(ctx->d_apool.p, ctx->h_apool.p, a_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CKH(cudaMemcpyAsync(ctx->d_cpool.p, ctx->h_cpool.p, sizeof(ColH) * c_elems, cudaMemcpyHostToDevice, ctx->stream));
-    CKH(cudaMemcpyAsync(ctx->d_epool.p, ctx->h_epool.p, sizeof(ColEnd) * c_elems, cudaMemcpyHostToDevice, ctx->stream));
-    CKH(cudaEventRecord(ctx->ev[1], ctx->stream));
-    CKH(cudaStreamSynchronize(ctx->stream));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    ctx->tim.h2d_ms = ms;
-    ctx->tim.h2d_bytes = (int64_t) (sizeof(DevTaskH) * n + sizeof(int) * n + a_bytes +
-                                    (sizeof(ColH) + sizeof(ColEnd)) * c_elems);
     ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score; ctx->n_udh = n_udh;
     ctx->ws_slab = ws_slab; ctx->cpos_elems = cpos_elems;
     ctx->a_bytes = a_bytes; ctx->c_elems = c_elems; ctx->band_slab = band_slab;
@@ -409,42 +328,158 @@ int gspaln_h_upload(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n)
     return GSPALN_OK;
 }
 
+// ---- packing of order[lo .. hi): the per-column records are derived here from SGPT6
+static void pack_range_h(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int lo, int hi)
+{
+    auto pack_some = [&](int klo, int khi) {
+        for (int k = klo; k < khi; ++k) {
+            const int i = ctx->h_order.p[k];
+            const gspaln_h_task& t = tasks[i];
+            const DevTaskH& d = ctx->h_tasks.p[i];
+            const int mw = t.a_right - t.a_left, nw = t.b_right - t.b_left;
+            unsigned char* ap = ctx->h_apool.p + d.a_off;
+            for (int j = 0; j < mw; ++j) ap[j] = (unsigned char) (t.a[t.a_left + j] & 31);
+            ColH* col = ctx->h_cpool.p + d.col_off;
+            ColEnd* ce = ctx->h_epool.p + d.col_off;
+            const gspaln_sgpt6* sg = t.sg;
+            const bool spj = ctx->prm.spj != 0;
+            const int ipen = ctx->prm.ipen;
+            const int c_sig_end = spj ? t.b_right : t.b_left;      // signals for c < b_right only
+            for (int j = 0; j <= nw + COL_TAIL_H; ++j) {
+                const int c = t.b_left + j;
+                // the record of genome column c = what enters lane 0 of the reference's shift
+                // registers at step n == c: src/fwd2h1_wip_simd.h:115-117 (cv), 189-192 (profile),
+                // 208-222 / 270-283 (signals by splice phase; phs == 2 means both -1 and +1)
+                ColH o;
+                o.s3[0] = o.s3[1] = o.s3[2] = o.s5[0] = o.s5[1] = o.s5[2] = 0;
+                unsigned flags = 0;
+                if (c < c_sig_end) {
+                    const gspaln_sgpt6& s0 = sg[c];
+                    const int p3 = s0.phs3, p5 = s0.phs5;
+                    if (p3 > -2 || p5 > -2) {
+                        const short m3 = sg[c + 1].sig3, z3 = s0.sig3, q3 = c > 0 ? sg[c - 1].sig3 : (short) 0;
+                        const short m5 = sg[c + 1].sig5, z5 = s0.sig5, q5 = c > 0 ? sg[c - 1].sig5 : (short) 0;
+                        if (p3 == 2) { o.s3[0] = m3; o.s3[2] = q3; flags |= 5u; }
+                        else if (p3 == -1) { o.s3[0] = m3; flags |= 1u; }
+                        else if (p3 == 0) { o.s3[1] = z3; flags |= 2u; }
+                        else if (p3 == 1) { o.s3[2] = q3; flags |= 4u; }
+                        if (p5 == 2) { o.s5[0] = (short) (m5 + ipen); o.s5[2] = (short) (q5 + ipen); flags |= 40u; }
+                        else if (p5 == -1) { o.s5[0] = (short) (m5 + ipen); flags |= 8u; }
+                        else if (p5 == 0) { o.s5[1] = (short) (z5 + ipen); flags |= 16u; }
+                        else if (p5 == 1) { o.s5[2] = (short) (q5 + ipen); flags |= 32u; }
+                    }
+                }
+                o.cv = (c >= 2 && c - 2 < t.b_len) ? sg[c - 2].sigE : (short) 0;
+                o.prof = (c >= t.b_left + 3 && c <= t.b_right + 2) ? (unsigned char) (t.b[c - 2] & 31) : (unsigned char) ZROW;
+                o.flags = (unsigned char) flags;
+                col[j] = o;
+                ColEnd e = {0, 0, 0, 0};
+                if (c <= t.b_len + 1) {
+                    const gspaln_sgpt6& s = sg[c];
+                    e.sigS = s.sigS; e.sigT = s.sigT; e.sigE = s.sigE; e.sig5 = s.sig5;
+                }
+                ce[j] = e;
+            }
+        }
+    };
+    size_t work = 0;
+    for (int k = lo; k < hi; ++k) {
+        const gspaln_h_task& t = tasks[ctx->h_order.p[k]];
+        work += (size_t) (t.b_right - t.b_left) + (t.a_right - t.a_left);
+    }
+    int nthr = (int) std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    if (work < (1u << 19) || hi - lo < 2 * nthr) nthr = 1;
+    if (nthr == 1) { pack_some(lo, hi); return; }
+    std::vector<std::thread> pool;
+    size_t acc = 0, per = (work + nthr - 1) / nthr;
+    int from = lo;
+    for (int k = lo; k < hi; ++k) {
+        const gspaln_h_task& t = tasks[ctx->h_order.p[k]];
+        acc += (size_t) (t.b_right - t.b_left) + (t.a_right - t.a_left);
+        if (acc >= per || k == hi - 1) {
+            pool.emplace_back(pack_some, from, k + 1);
+            from = k + 1; acc = 0;
+        }
+    }
+    for (auto& th : pool) th.join();
+}
+
+static void pool_span_h(const gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int lo, int hi, size_t& a0, size_t& a1,
+                        size_t& c0, size_t& c1)
+{
+    const DevTaskH& f = ctx->h_tasks.p[ctx->h_order.p[lo]];
+    const int li = ctx->h_order.p[hi - 1];
+    const DevTaskH& l = ctx->h_tasks.p[li];
+    a0 = (size_t) f.a_off; c0 = (size_t) f.col_off;
+    a1 = (size_t) l.a_off + align_up((size_t) (tasks[li].a_right - tasks[li].a_left) + 1, 128);
+    c1 = (size_t) l.col_off + align_up((size_t) (tasks[li].b_right - tasks[li].b_left) + COL_TAIL_H + 2, 16);
+}
+
+static int launch_all_h(gspaln_h_ctx* ctx, int& launches, const int* ready)
+{
+    const int n = ctx->n;
+    const bool local = (ctx->prm.lcl & 16) != 0, spj = ctx->prm.spj != 0;
+    if (ctx->n_trace) {
+        kernel_h(true, local, spj)<<<ctx->grid_run_trace, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+            ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p,
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_epool.p, ctx->d_band.p, (long long) ctx->band_slab,
+            ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_rows.p, (long long) ctx->row_slab,
+            ctx->d_skl.p, ctx->d_res.p, ready);
+        ++launches;
+    }
+    if (ctx->n_score) {
+        kernel_h(false, local, spj)<<<ctx->grid_run_score, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+            ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p + 1,
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_epool.p, ctx->d_band.p, (long long) ctx->band_slab,
+            ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_rows.p, (long long) ctx->row_slab,
+            ctx->d_skl.p, ctx->d_res.p, ready);
+        ++launches;
+    }
+    if (ctx->n_udh) {
+        kernel_udh_h(local, spj)<<<ctx->grid_run_udh, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+            ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p + 2,
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_epool.p, ctx->d_ws.p, (long long) ctx->ws_slab,
+            ctx->d_cpos.p, ctx->d_ures.p, ready);
+        ++launches;
+    }
+    CKH(cudaGetLastError());
+    return GSPALN_OK;
+}
+
+constexpr int MAX_CHUNKS_H = 16;
+
+int gspaln_h_upload(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n)
+{
+    if (!ctx || !tasks || n < 0) return GSPALN_EINVAL;
+    int rc = plan_batch_h(ctx, tasks, n);
+    if (rc != GSPALN_OK) return rc;
+    if (n) pack_range_h(ctx, tasks, 0, n);
+    CKH(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CKH(cudaMemcpyAsync(ctx->d_tasks.p, ctx->h_tasks.p, sizeof(DevTaskH) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CKH(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.p, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CKH(cudaMemcpyAsync(ctx->d_apool.p, ctx->h_apool.p, ctx->a_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CKH(cudaMemcpyAsync(ctx->d_cpool.p, ctx->h_cpool.p, sizeof(ColH) * ctx->c_elems, cudaMemcpyHostToDevice, ctx->stream));
+    CKH(cudaMemcpyAsync(ctx->d_epool.p, ctx->h_epool.p, sizeof(ColEnd) * ctx->c_elems, cudaMemcpyHostToDevice, ctx->stream));
+    CKH(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CKH(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->tim.h2d_ms = ms;
+    ctx->tim.h2d_bytes = (int64_t) (sizeof(DevTaskH) * n + sizeof(int) * n + ctx->a_bytes +
+                                    (sizeof(ColH) + sizeof(ColEnd)) * ctx->c_elems);
+    return GSPALN_OK;
+}
+
 int gspaln_h_run(gspaln_h_ctx* ctx)
 {
     if (!ctx) return GSPALN_EINVAL;
     CKH(cudaSetDevice(ctx->device));
-    const int n = ctx->n;
     int launches = 0;
     CKH(cudaEventRecord(ctx->ev[2], ctx->stream));
-    if (n > 0) {
-        const bool local = (ctx->prm.lcl & 16) != 0, spj = ctx->prm.spj != 0;
-        if (ctx->n_trace) {
-            CKH(cudaMemsetAsync(ctx->d_ticket.p, 0, sizeof(int), ctx->stream));
-            kernel_h(true, local, spj)<<<ctx->grid_run_trace, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
-                ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p,
-                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_epool.p, ctx->d_band.p, (long long) ctx->band_slab,
-                ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_rows.p, (long long) ctx->row_slab,
-                ctx->d_skl.p, ctx->d_res.p);
-            ++launches;
-        }
-        if (ctx->n_score) {
-            CKH(cudaMemsetAsync(ctx->d_ticket.p + 1, 0, sizeof(int), ctx->stream));
-            kernel_h(false, local, spj)<<<ctx->grid_run_score, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
-                ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p + 1,
-                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_epool.p, ctx->d_band.p, (long long) ctx->band_slab,
-                ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_rows.p, (long long) ctx->row_slab,
-                ctx->d_skl.p, ctx->d_res.p);
-            ++launches;
-        }
-        if (ctx->n_udh) {
-            CKH(cudaMemsetAsync(ctx->d_ticket.p + 2, 0, sizeof(int), ctx->stream));
-            kernel_udh_h(local, spj)<<<ctx->grid_run_udh, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
-                ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p, n, ctx->d_ticket.p + 2,
-                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_epool.p, ctx->d_ws.p, (long long) ctx->ws_slab,
-                ctx->d_cpos.p, ctx->d_ures.p);
-            ++launches;
-        }
-        CKH(cudaGetLastError());
+    if (ctx->n > 0) {
+        CKH(cudaMemsetAsync(ctx->d_ticket.p, 0, 3 * sizeof(int), ctx->stream));
+        int rc = launch_all_h(ctx, launches, nullptr);
+        if (rc != GSPALN_OK) return rc;
     }
     CKH(cudaEventRecord(ctx->ev[3], ctx->stream));
     CKH(cudaStreamSynchronize(ctx->stream));
@@ -496,12 +531,72 @@ int gspaln_h_download(gspaln_h_ctx* ctx, gspaln_result* results)
     return GSPALN_OK;
 }
 
+// One-shot path: the batch is streamed in behind the persistent kernels (see gspaln_submit)
 int gspaln_h_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gspaln_result* results)
 {
-    int rc = gspaln_h_upload(ctx, tasks, n);
-    if (rc == GSPALN_OK) rc = gspaln_h_run(ctx);
-    if (rc == GSPALN_OK) rc = gspaln_h_download(ctx, results);
-    return rc;
+    if (!ctx || !tasks || n < 0) return GSPALN_EINVAL;
+    int rc = plan_batch_h(ctx, tasks, n);
+    if (rc != GSPALN_OK) return rc;
+    int bounds[MAX_CHUNKS_H + 1];
+    int nchunks = 1;
+    bounds[0] = 0; bounds[1] = n;
+    const size_t total = ctx->c_elems;
+    if (n >= 256 && total >= (2u << 20)) {
+        nchunks = 0;
+        size_t acc = 0;
+        const int want = (int) std::min<size_t>(MAX_CHUNKS_H, 2 + total / (2u << 20));
+        size_t next = total / (2 * (size_t) want);
+        for (int k = 0; k < n; ++k) {
+            const gspaln_h_task& t = tasks[ctx->h_order.p[k]];
+            acc += (size_t) (t.b_right - t.b_left) + COL_TAIL_H + 2;
+            if (acc >= next && nchunks + 1 < want && k + 1 < n) {
+                bounds[++nchunks] = k + 1;
+                next = acc + (total - acc) / (size_t) (want - nchunks);
+            }
+        }
+        bounds[++nchunks] = n;
+    }
+    if (ctx->h_marks.reserve(MAX_CHUNKS_H + 1) != cudaSuccess) return fail(ctx, GSPALN_ENOMEM, "pinned host allocation");
+    int* d_ready = ctx->d_ticket.p + 32;
+    CKH(cudaMemsetAsync(ctx->d_ticket.p, 0, 40 * sizeof(int), ctx->stream));
+    CKH(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CKH(cudaMemcpyAsync(ctx->d_tasks.p, ctx->h_tasks.p, sizeof(DevTaskH) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CKH(cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.p, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    int launches = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int lo = bounds[c], hi = bounds[c + 1];
+        if (hi <= lo) continue;
+        pack_range_h(ctx, tasks, lo, hi);
+        size_t a0, a1, c0, c1;
+        pool_span_h(ctx, tasks, lo, hi, a0, a1, c0, c1);
+        cudaStream_t st = c == 0 ? ctx->stream : ctx->copy_stream;
+        CKH(cudaMemcpyAsync(ctx->d_apool.p + a0, ctx->h_apool.p + a0, a1 - a0, cudaMemcpyHostToDevice, st));
+        CKH(cudaMemcpyAsync(ctx->d_cpool.p + c0, ctx->h_cpool.p + c0, sizeof(ColH) * (c1 - c0), cudaMemcpyHostToDevice, st));
+        CKH(cudaMemcpyAsync(ctx->d_epool.p + c0, ctx->h_epool.p + c0, sizeof(ColEnd) * (c1 - c0), cudaMemcpyHostToDevice, st));
+        ctx->h_marks.p[c] = hi;
+        CKH(cudaMemcpyAsync(d_ready, ctx->h_marks.p + c, sizeof(int), cudaMemcpyHostToDevice, st));
+        if (c == 0) {
+            CKH(cudaEventRecord(ctx->ev[1], ctx->stream));
+            CKH(cudaEventRecord(ctx->ev_sync[0], ctx->stream));
+            CKH(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_sync[0], 0));
+            CKH(cudaEventRecord(ctx->ev[2], ctx->stream));
+            rc = launch_all_h(ctx, launches, nchunks > 1 ? d_ready : nullptr);
+            if (rc != GSPALN_OK) return rc;
+        }
+    }
+    if (n == 0) { CKH(cudaEventRecord(ctx->ev[1], ctx->stream)); CKH(cudaEventRecord(ctx->ev[2], ctx->stream)); }
+    CKH(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CKH(cudaStreamSynchronize(ctx->copy_stream));
+    CKH(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->tim.h2d_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+    ctx->tim.kernel_ms = ms;
+    ctx->tim.launches = launches;
+    ctx->tim.h2d_bytes = (int64_t) (sizeof(DevTaskH) * n + sizeof(int) * n + ctx->a_bytes +
+                                    (sizeof(ColH) + sizeof(ColEnd)) * ctx->c_elems);
+    return gspaln_h_download(ctx, results);
 }
 
 int gspaln_h_get_timing(const gspaln_h_ctx* ctx, gspaln_timing* out)

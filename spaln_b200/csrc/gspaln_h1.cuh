@@ -532,7 +532,7 @@ dp_h1_kernel(const DevParamsH* __restrict__ gP, const int2* __restrict__ gpen,
              const unsigned char* __restrict__ apool, const ColH* __restrict__ cpool,
              const ColEnd* __restrict__ epool, unsigned* bandpool, long long band_slab,
              unsigned short* tracepool, long long trace_slab, unsigned char* rowpool, long long row_slab,
-             int2* sklpool, DevResult* results)
+             int2* sklpool, DevResult* results, const int* ready)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ DevParamsH sP;
@@ -565,7 +565,11 @@ dp_h1_kernel(const DevParamsH* __restrict__ gP, const int2* __restrict__ gpen,
         if (tk >= ntasks) break;
         const int ti = order[tk];
         const DevTaskH t = tasks[ti];
-        if ((t.kind == 0) != TRACE) continue;
+        if (t.kind > 1 || (t.kind == 0) != TRACE) continue;
+        if (!wait_inputs(ready, tk)) {
+            if (lane == 0) { DevResult r; r.score = 0; r.status = 4; r.n_skl = 0; r.pad = 0; results[ti] = r; }
+            continue;
+        }
         const unsigned char* aseq = apool + t.a_off;
         const ColH* cols = cpool + t.col_off;
         const ColEnd* ce = epool + t.col_off;       // ce[c - b_left]

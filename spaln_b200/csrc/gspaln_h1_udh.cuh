@@ -39,7 +39,7 @@ dp_h1_udh_kernel(const DevParamsH* __restrict__ gP, const int2* __restrict__ gpe
                  const DevTaskH* __restrict__ tasks, const int* __restrict__ order, int ntasks, int* ticket,
                  const unsigned char* __restrict__ apool, const ColH* __restrict__ cpool,
                  const ColEnd* __restrict__ epool, int* wspool, long long ws_slab,
-                 int* cpospool, DevUdhOutH* results)
+                 int* cpospool, DevUdhOutH* results, const int* ready)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ DevParamsH sP;
@@ -72,6 +72,10 @@ dp_h1_udh_kernel(const DevParamsH* __restrict__ gP, const int2* __restrict__ gpe
         const int ti = order[tk];
         const DevTaskH t = tasks[ti];
         if (t.kind != 2) continue;
+        if (!wait_inputs(ready, tk)) {
+            if (lane == 0) { DevUdhOutH r; memset(&r, 0, sizeof(r)); r.status = 4; results[ti] = r; }
+            continue;
+        }
         const int n_im = (int) (t.pad1 >> 40);
         int* cpos = cpospool + (t.pad1 & ((1ll << 40) - 1));
         const unsigned char* aseq = apool + t.a_off;

@@ -586,7 +586,7 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
         if (tk >= ntasks) break;
         const int ti = order[tk];
         const DevTask t = tasks[ti];
-        if ((t.kind == 0) != TRACE) continue;       // handled by the other instantiation
+        if (t.kind > 1 || (t.kind == 0) != TRACE) continue;    // handled by another kernel
         if (!wait_inputs(ready, tk)) {
             if (lane == 0) { DevResult r; r.score = 0; r.status = 4; r.n_skl = 0; r.pad = 0; results[ti] = r; }
             continue;

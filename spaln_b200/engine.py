@@ -371,6 +371,16 @@ class EngineH:
         """trace=False == forwardH1_wip(0) as HomScoreH_ng calls it (score only)"""
         return self.submit(problems, capi.FORWARD_WIP if trace else capi.SCOREONLY_WIP)
 
+    def pack(self, problems, kind=capi.FORWARD_WIP) -> PackedBatch:
+        arr, keep = self._pack(problems, kind)
+        return PackedBatch(arr, keep, len(problems))
+
+    def submit_packed(self, batch: PackedBatch) -> PackedBatch:
+        """host buffers in, host results out (scores / status / corners in `batch`)"""
+        res = batch.res.ctypes.data_as(C.POINTER(capi.GspalnResult))
+        self._check(self.lib.gspaln_h_submit(self._h, batch.arr, batch.n, res), "gspaln_h_submit")
+        return batch
+
     def hirschbergH1_wip(self, problems):
         """problems carry n_imd; results carry score, narrowed ranges and cpos (Dim10 records)"""
         return self.submit(problems, capi.HIRSCHBERG_WIP)
