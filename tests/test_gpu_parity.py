@@ -259,3 +259,29 @@ def test_packed_batch_api_equals_object_api():
         assert b.scores[i] == w.score and b.status[i] == w.status
         assert np.array_equal(b.corners(i), w.skl)
     eng.close()
+
+
+def test_streamed_submit_equals_resident_path():
+    """A batch large enough for the one-shot submit to stream it in behind the running kernel
+    (chunks on a second stream + watermark) must give exactly what upload / run / download of the
+    resident batch gives; a few problems are also checked against the oracle by the caller tests."""
+    prm, _ = golden_io.load("dna_A2_global")
+    rng = np.random.default_rng(77)
+    probs = _synthetic(prm, rng, 700, (800, 2000), (500, 4000))
+    assert sum(pb["b_right"] - pb["b_left"] for pb in probs) > (4 << 20)    # above the chunking threshold
+    P = _problems(probs)
+    eng = _engine(prm)
+    eng.upload(P)
+    eng.run()
+    want = eng.download()
+    for rep in range(2):
+        got = eng.forwardS1_wip(P)
+        for i, (w, g) in enumerate(zip(want, got)):
+            assert g.status == 0 and w.status == 0, (rep, i, g.status)
+            assert g.score == w.score and np.array_equal(g.skl, w.skl), (rep, i)
+    so = eng.scoreonlyS1_wip(P)
+    eng.upload(P, kind=1)
+    eng.run()
+    for w, g in zip(eng.download(), so):
+        assert w.score == g.score
+    eng.close()

@@ -156,3 +156,37 @@ def test_hirschbergH1_wip_matches_oracle_on_random_problems(oracle, fixture, see
             bad.append((i, p.n_imd, r.status, r.score, o["score"], list(r.ranges), o["ranges"]))
     assert not bad, (fixture, bad)
     eng.close()
+
+
+def test_protein_batch_properties_full_size_and_streamed_submit():
+    """BASELINE config-3 shaped problems (proteins of 300-800 aa against loci with 0.5-5 kb
+    flanks): properties that do not need the oracle -- the streamed one-shot submit equals the
+    resident path, batch order does not matter, the score-only call returns the same score,
+    corner lists are monotone walks that start inside the matrix."""
+    from spaln_b200 import EngineH
+    import bench
+    prm, _ = golden_io.load_protein("prot_A2_local")
+    raw = bench.make_protein_workload(420, 4242)
+    assert sum(r["b_right"] + 52 for r in raw) > (2 << 20)      # above the chunking threshold
+    P = bench.to_problems_h(raw)
+    eng = EngineH(prm, device=0)
+    eng.upload(P)
+    eng.run()
+    want = eng.download()
+    got = eng.forwardH1_wip(P)
+    rev = eng.forwardH1_wip(P[::-1])[::-1]
+    so = eng.forwardH1_wip(P, trace=False)
+    n_multi = 0
+    for i, (pb, w, g, r, s) in enumerate(zip(raw, want, got, rev, so)):
+        assert w.status == 0 and g.status == 0, (i, w.status, g.status)
+        assert g.score == w.score == r.score == s.score, (i, g.score, w.score, r.score, s.score)
+        assert np.array_equal(g.skl, w.skl) and np.array_equal(g.skl, r.skl), i
+        skl = g.skl
+        assert len(skl) >= 1
+        assert skl[0, 0] <= pb["a_right"] and skl[:, 0].min() >= pb["a_left"]
+        assert skl[:, 1].min() >= pb["b_left"]
+        assert np.all(np.diff(skl[:, 0]) <= 0)
+        n_multi += len(skl) >= 4
+    assert n_multi > len(raw) // 2          # the planted multi-exon genes are found
+    assert np.median([g.score for g in got]) > 5000
+    eng.close()
