@@ -450,6 +450,7 @@ def main():
 
     # ---- the driver path (lspS_ng dispatch at the reference's default -V = 32 MiB):
     # Hirschberg passes + block re-alignments for the larger problems, host in the loop
+    eng.lspS_ng(problems, max_vmf_space=32 * 1024 * 1024, sh=int(prm["sh"]), alg=2)   # warm-up: pools of this path
     barrier()
     t0 = time.perf_counter()
     res3 = eng.lspS_ng(problems, max_vmf_space=32 * 1024 * 1024, sh=int(prm["sh"]), alg=2)

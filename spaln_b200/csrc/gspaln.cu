@@ -11,6 +11,7 @@
 #include "gspaln_host.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdio>

@@ -8,7 +8,9 @@
 #include "gspaln_host.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>

@@ -81,11 +81,19 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
     };
     size_t fwd_done = 0;
     int64_t cells_total = 0;
+    const bool dbg = getenv("GSPALN_LSP_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto msec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    double t_classify = 0, t_submit = 0, t_post = 0;
+    auto t_all = now();
     float kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
     int launches = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
 
     while (!pending.empty()) {
+        auto t0 = now();
         // ---- classify (lspS_ng head) and build this level's batch
         std::vector<int> udh_items;         // items waiting for a Hirschberg pass
         std::vector<int> score_from_fwd;    // (item, fwd) pairs: item score = forward score
@@ -159,9 +167,12 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
             bres[udh_items.size() + (f - fwd_first)].skl = sklbuf[f - fwd_first].data();
             bres[udh_items.size() + (f - fwd_first)].cpos = nullptr;
         }
+        auto t1 = now();
+        t_classify += msec(t0, t1);
         if (!batch.empty()) {
             int rc = TR::submit(ctx, batch.data(), (int) batch.size(), bres.data());
             if (rc != GSPALN_OK) return rc;
+            t_submit += msec(t1, now());
             kernel_ms += ctx->tim.kernel_ms; h2d_ms += ctx->tim.h2d_ms; d2h_ms += ctx->tim.d2h_ms;
             launches += ctx->tim.launches; h2d_bytes += ctx->tim.h2d_bytes; d2h_bytes += ctx->tim.d2h_bytes;
             cells_total += ctx->tim.cells;
@@ -179,6 +190,7 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
         fwd_done = fwds.size();
         for (auto& pr : item_fwd) items[pr.first].score = fwds[pr.second].score;
 
+        auto t2 = now();
         // ---- post-work of the Hirschberg passes: next level
         for (size_t k = 0; k < udh_items.size(); ++k) {
             const int id = udh_items[k];
@@ -248,6 +260,7 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
                 }
             }
         }
+        t_post += msec(t2, now());
         // block re-alignments queued by the post-work run with the next level
         if (pending.empty() && fwd_done < fwds.size()) pending.push_back(-1);
         if (!pending.empty() && pending.back() == -1) {
@@ -262,8 +275,10 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
             }
             r2.resize(b2.size());
             for (size_t f = 0; f < b2.size(); ++f) { r2[f].skl = s2[f].data(); r2[f].cpos = nullptr; }
+            auto t3 = now();
             int rc = TR::submit(ctx, b2.data(), (int) b2.size(), r2.data());
             if (rc != GSPALN_OK) return rc;
+            t_submit += msec(t3, now());
             kernel_ms += ctx->tim.kernel_ms; h2d_ms += ctx->tim.h2d_ms; d2h_ms += ctx->tim.d2h_ms;
             launches += ctx->tim.launches; h2d_bytes += ctx->tim.h2d_bytes; d2h_bytes += ctx->tim.d2h_bytes;
             cells_total += ctx->tim.cells;
@@ -304,6 +319,10 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
         if (o.skl)
             for (int k = 0; k < std::min(o.n_skl, cap); ++k) { o.skl[2 * k] = out[k].x; o.skl[2 * k + 1] = out[k].y; }
     }
+    if (dbg)
+        fprintf(stderr, "gspaln lsp: %d problems, %zu forward tasks; classify %.1f ms, submits %.1f ms "
+                "(kernels %.1f), post-work %.1f ms, total %.1f ms\n", n, fwds.size(), t_classify, t_submit,
+                kernel_ms, t_post, msec(t_all, now()));
     ctx->tim.kernel_ms = kernel_ms; ctx->tim.h2d_ms = h2d_ms; ctx->tim.d2h_ms = d2h_ms;
     ctx->tim.launches = launches; ctx->tim.h2d_bytes = h2d_bytes; ctx->tim.d2h_bytes = d2h_bytes;
     ctx->tim.cells = cells_total;
