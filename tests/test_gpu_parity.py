@@ -285,3 +285,68 @@ def test_streamed_submit_equals_resident_path():
     for w, g in zip(eng.download(), so):
         assert w.score == g.score
     eng.close()
+
+
+def _config5_problem(rng, m, W):
+    """query of m nt; genome = the query with 0 / 1 / 2 inserted GT..AG introns and short flanks,
+    d = n - m extra nucleotides in total; band = stripe() with the shoulder that makes the band
+    W diagonals wide"""
+    from spaln_b200 import workload
+    d = int(rng.integers(0, max(1, W // 2)))
+    q = workload.random_dna(rng, m)
+    nin = int(rng.integers(0, 3)) if d >= 60 and m >= 40 else 0
+    lens = []
+    rest = d
+    for _ in range(nin):
+        il = int(rng.integers(25, max(26, rest // (nin + 1) + 26)))
+        il = min(il, rest)
+        if il >= 25:
+            lens.append(il)
+            rest -= il
+    fl = rest // 2
+    parts = [workload.random_dna(rng, fl)]
+    cuts = sorted(int(x) for x in rng.choice(np.arange(10, m - 10), size=len(lens), replace=False)) if lens else []
+    prev = 0
+    for c, il in zip(cuts, lens):
+        parts.append(q[prev:c])
+        it = workload.random_dna(rng, il)
+        it[:2] = np.frombuffer(b"GT", np.uint8)
+        it[-2:] = np.frombuffer(b"AG", np.uint8)
+        parts.append(it)
+        prev = c
+    parts.append(q[prev:])
+    parts.append(workload.random_dna(rng, rest - fl))
+    g = np.concatenate(parts)
+    a, b = workload.encode_dna(q.tobytes().decode()), workload.encode_dna(g.tobytes().decode())
+    s5, s3 = workload.synthetic_signals(b, rng)
+    sh = max(1, (W - 3 - (len(b) - len(a))) // 2)
+    lw, up = workload.stripe(0, len(a), 0, len(b), sh)
+    return {"a": np.concatenate([[0], a, [0]]).astype(np.uint8),
+            "b": np.concatenate([[0], b, [0]]).astype(np.uint8),
+            "sig5": s5, "sig3": s3, "a_left": 0, "a_right": len(a), "b_left": 0,
+            "b_right": len(b), "a_exgl": 1, "a_exgr": 1, "b_exgl": 1, "b_exgr": 1, "lw": lw, "up": up}
+
+
+def test_config5_sweep_matches_oracle(oracle):
+    """BASELINE config 5 shapes: band width W in {16 .. 1024} x query length m in {16 .. 4096}
+    with m * W in [256, 65536] cells, 0 / 1 / 2 planted introns: trace-back and score-only
+    against the oracle, global and local parameter sets."""
+    for fixture in ("dna_A2_global", "dna_A2_local"):
+        prm, _ = golden_io.load(fixture)
+        rng = np.random.default_rng(55555)
+        probs = []
+        for W in (16, 32, 64, 128, 256, 512, 1024):
+            for m in (16, 33, 64, 250, 1024, 4096):
+                if 256 <= m * W <= 65536:
+                    probs += [_config5_problem(rng, m, W) for _ in range(2)]
+        assert len(probs) >= 40
+        eng = _engine(prm)
+        res = eng.forwardS1_wip(_problems(probs))
+        sco = eng.scoreonlyS1_wip(_problems(probs))
+        for i, (pb, r, s) in enumerate(zip(probs, res, sco)):
+            o = oracle.forward_wip(prm, pb)
+            assert r.status == 0, (fixture, i)
+            assert r.score == o["score"], (fixture, i, pb["lw"], pb["up"], r.score, o["score"])
+            assert np.array_equal(r.skl, o["skl"]), (fixture, i)
+            assert s.score == oracle.scoreonly_wip(prm, pb)["score"], (fixture, i)
+        eng.close()
