@@ -334,6 +334,28 @@ def host_cells(raw):
         r["cells"] = int(lib.gspaln_task_cells(C.byref(t)))
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL: "NCCL version ...") write to fd 1; the contract is ONE JSON line on
+    stdout, so everything else is sent to stderr and the line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -351,6 +373,7 @@ def main():
     args = ap.parse_args()
     if args.leg == "protein-cpu":
         return protein_reference_child(args.cpu_sample, args.leg_seed, os.cpu_count() or 1, args.leg_out)
+    _quiet_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -370,7 +393,7 @@ def main():
         host_cells(raw)
         r = reference_run(raw, args.steps, max(1, args.warmup), ncores)
         if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref not built"})
             return 0
         times, cells, _ = r
         ms = 1e3 * float(np.mean(times))
@@ -387,7 +410,7 @@ def main():
             "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm
@@ -559,7 +582,7 @@ def main():
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": ncores, "kind": "reference",
                                         "sample": "oracle/_ref not available"}
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

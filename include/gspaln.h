@@ -165,6 +165,18 @@ typedef struct gspaln_lsp_opts {
 int  gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n, const gspaln_lsp_opts* opts,
                 gspaln_result* results);
 
+/* Coalescing queue for the literal drop-in: Spaln issues its DP problems one at a time from each
+ * pthread worker (src/spaln.cc:1363-1468).  Workers call gspaln_queue_submit() with ONE task and
+ * block until its result is there; a dispatcher thread owned by the queue collects what the
+ * workers have queued (up to max_batch tasks, waiting at most max_wait_us for stragglers once
+ * the first task has arrived) and runs it as one gspaln_submit() batch.  Thread-safe; the
+ * context must not be used directly while a queue is attached to it. */
+typedef struct gspaln_queue gspaln_queue;
+int  gspaln_queue_create(gspaln_queue** out, gspaln_ctx* ctx, int max_batch, int max_wait_us);
+int  gspaln_queue_submit(gspaln_queue* q, const gspaln_task* task, gspaln_result* result);
+int  gspaln_queue_stats(const gspaln_queue* q, int64_t* tasks, int64_t* batches);
+void gspaln_queue_destroy(gspaln_queue* q);
+
 int  gspaln_get_timing(const gspaln_ctx* ctx, gspaln_timing* out);
 const char* gspaln_last_error(const gspaln_ctx* ctx);
 int  gspaln_device_count(void);

@@ -31,6 +31,7 @@ EXPORTS = [
     "gspaln_h_create", "gspaln_h_destroy", "gspaln_h_submit", "gspaln_h_upload", "gspaln_h_run",
     "gspaln_h_download", "gspaln_h_get_timing", "gspaln_h_last_error", "gspaln_h_task_cells",
     "gspaln_h_lsp",
+    "gspaln_queue_create", "gspaln_queue_submit", "gspaln_queue_stats", "gspaln_queue_destroy",
 ]
 
 
@@ -144,6 +145,11 @@ def load():
     lib.gspaln_version.restype = C.c_char_p
     lib.gspaln_task_cells.argtypes = [C.POINTER(GspalnTask)]
     lib.gspaln_task_cells.restype = C.c_int64
+    lib.gspaln_queue_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int]
+    lib.gspaln_queue_submit.argtypes = [C.c_void_p, C.POINTER(GspalnTask), C.POINTER(GspalnResult)]
+    lib.gspaln_queue_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.gspaln_queue_destroy.argtypes = [C.c_void_p]
+    lib.gspaln_queue_destroy.restype = None
     lib.gspaln_h_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(GspalnHParams), C.c_int]
     lib.gspaln_h_destroy.argtypes = [C.c_void_p]
     lib.gspaln_h_destroy.restype = None

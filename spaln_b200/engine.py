@@ -226,6 +226,12 @@ class Engine:
         self._n = n
         return self._collect(n, res, bufs, arr)
 
+    # ---- coalescing queue: the shape of the literal drop-in ---------------
+    def queue(self, max_batch=256, max_wait_us=200) -> "SubmitQueue":
+        """Thread-safe single-problem submits, coalesced into batches by a dispatcher thread
+        (what Spaln's pthread workers would call, one problem at a time)."""
+        return SubmitQueue(self, max_batch, max_wait_us)
+
     # ---- split form (batch resident in HBM) -----------------------------
     def upload(self, problems, kind=capi.FORWARD_WIP):
         arr, keep = self._pack(problems, kind)
@@ -246,6 +252,38 @@ class Engine:
         self.lib.gspaln_get_timing(self._h, C.byref(t))
         return Timing(t.h2d_ms, t.kernel_ms, t.d2h_ms, t.launches, t.h2d_bytes, t.d2h_bytes,
                       t.trace_bytes, t.cells)
+
+
+class SubmitQueue:
+    """gspaln_queue_*: `forwardS1_wip(problem)` may be called from many threads at once"""
+
+    def __init__(self, engine: Engine, max_batch: int, max_wait_us: int):
+        self.eng = engine
+        self._q = C.c_void_p()
+        rc = engine.lib.gspaln_queue_create(C.byref(self._q), engine._h, max_batch, max_wait_us)
+        if rc != 0:
+            raise EngineError(f"gspaln_queue_create failed ({rc})")
+
+    def submit(self, problem: Problem, kind=capi.FORWARD_WIP) -> Result:
+        arr, keep = self.eng._pack([problem], kind)
+        res, bufs = self.eng._results(1, arr)
+        rc = self.eng.lib.gspaln_queue_submit(self._q, arr, res)      # ctypes releases the GIL
+        if rc != 0:
+            raise EngineError(f"gspaln_queue_submit failed ({rc})")
+        return self.eng._collect(1, res, bufs, arr)[0]
+
+    def forwardS1_wip(self, problem: Problem) -> Result:
+        return self.submit(problem, capi.FORWARD_WIP)
+
+    def stats(self):
+        t, b = C.c_int64(0), C.c_int64(0)
+        self.eng.lib.gspaln_queue_stats(self._q, C.byref(t), C.byref(b))
+        return t.value, b.value
+
+    def close(self):
+        if self._q and self._q.value:
+            self.eng.lib.gspaln_queue_destroy(self._q)
+            self._q = C.c_void_p()
 
 
 # ---------------------------------------------------------------------------

@@ -350,3 +350,33 @@ def test_config5_sweep_matches_oracle(oracle):
             assert np.array_equal(r.skl, o["skl"]), (fixture, i)
             assert s.score == oracle.scoreonly_wip(prm, pb)["score"], (fixture, i)
         eng.close()
+
+
+def test_coalescing_queue_from_many_threads():
+    """the literal drop-in shape: 16 host threads submit one problem at a time through
+    gspaln_queue_*; the dispatcher coalesces them into batches; results equal the batch API"""
+    import threading
+    prm, probs = golden_io.load("dna_A2_global")
+    rng = np.random.default_rng(9)
+    probs = probs + _synthetic(prm, rng, 40, (100, 600), (50, 400))
+    P = _problems(probs)
+    eng = _engine(prm)
+    want = eng.forwardS1_wip(P)
+    q = eng.queue(max_batch=64, max_wait_us=500)
+    got = [None] * len(P)
+    nthr = 16
+
+    def work(tid):
+        for i in range(tid, len(P), nthr):
+            got[i] = q.forwardS1_wip(P[i])
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(nthr)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    tasks, batches = q.stats()
+    q.close()
+    assert tasks == len(P) and batches < tasks          # something was coalesced
+    for i, (w, g) in enumerate(zip(want, got)):
+        assert g is not None and g.status == w.status and g.score == w.score, i
+        assert np.array_equal(g.skl, w.skl), i
+    eng.close()
