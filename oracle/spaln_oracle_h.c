@@ -1041,7 +1041,8 @@ static int drvh_trcbk(so_drvh* d, const so_task_h* t)
     const int width = t->up - t->lw + 7;
     if (width < 0) return NEVSEL32_H;
     const int m = t->a_right - t->a_left;
-    if (m < 8) { d->unsupported = 1; return NEVSEL32_H; }
+    if (m < 8 || t->b_right < t->b_left || t->a_left < 0 || t->b_left < 0 || t->b_right > t->b_len ||
+        t->a_right > t->a_len) { d->unsupported = 1; return NEVSEL32_H; }
     int32_t score = 0;
     int room = d->cap > d->n ? d->cap - d->n : 0;
     int cnt = so_forward_h1_wip(d->p, t, 1, &score, d->skl + 2 * (d->n < d->cap ? d->n : d->cap), room);
@@ -1127,6 +1128,12 @@ static int drvh_lsp(so_drvh* d, so_task_h* t)
     const so_params_h* p = d->p;
     const int m = t->a_right - t->a_left;
     const int n = t->b_right - t->b_left;
+    if (m < 0 || n < 0 || t->a_left < 0 || t->b_left < 0 || t->b_right > t->b_len || t->a_right > t->a_len) {
+        /* a range a Hirschberg pass narrowed to outside the sequences (fhlastH1's start point
+         * right of b_right): the reference reads foreign memory from here on */
+        d->unsupported = 1;
+        return NEVSEL32_H;
+    }
     if (!m && !n) return 0;
     const int aexgl = t->a_exgl, aexgr = t->a_exgr, bexgl = t->b_exgl, bexgr = t->b_exgr;
     if (!m || !n) {

@@ -272,11 +272,15 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
     ctx->skl_cap.assign(n, 0);
     for (int i = 0; i < n; ++i) {
         const gspaln_task& t = tasks[i];
-        if (t.a_right < t.a_left || t.b_right < t.b_left || t.up < t.lw ||
+        if (t.a_right < t.a_left || t.b_right < t.b_left || t.up - t.lw + 3 < 0 ||
             (t.kind != GSPALN_FORWARD_WIP && t.kind != GSPALN_SCOREONLY_WIP && t.kind != GSPALN_HIRSCHBERG_WIP) ||
             (t.kind == GSPALN_HIRSCHBERG_WIP && (t.n_imd < 1 || t.a_right - t.a_left < 2)) ||
-            !t.a || !t.b || (ctx->prm.spj && (!t.sig5 || !t.sig3)))
-            return fail(ctx, GSPALN_EINVAL, "bad task");
+            !t.a || !t.b || (ctx->prm.spj && (!t.sig5 || !t.sig3))) {
+            char msg[256];
+            snprintf(msg, sizeof(msg), "bad task %d: kind %d a (%d, %d] b (%d, %d] band [%d, %d] n_imd %d",
+                     i, t.kind, t.a_left, t.a_right, t.b_left, t.b_right, t.lw, t.up, t.n_imd);
+            return fail(ctx, GSPALN_EINVAL, msg);
+        }
         ctx->cells[i] = task_cells(t);
     }
     if (ctx->h_tasks.reserve(n + 1) != cudaSuccess || ctx->h_order.reserve(n + 1) != cudaSuccess)
@@ -687,6 +691,7 @@ struct LspTraitsS {
         score = LocalR ? maxh : scr;
     }
     static bool bad_range(const gspaln_task&, const LspGeo&) { return false; }
+    static bool beyond(const gspaln_task&, const LspGeo&) { return false; }     // lengths are not part of the DNA task
     static gspaln_task make_task(const gspaln_task& base, const LspGeo& g, int kind, int n_imd)
     {
         gspaln_task t = base;

@@ -228,12 +228,16 @@ static int plan_batch_h(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n)
     ctx->cells.assign(n, 0);
     for (int i = 0; i < n; ++i) {
         const gspaln_h_task& t = tasks[i];
-        if (t.a_right < t.a_left || t.b_right < t.b_left || t.up < t.lw || t.a_left < 0 || t.b_left < 0 ||
+        if (t.a_right < t.a_left || t.b_right < t.b_left || t.up - t.lw + 7 < 0 || t.a_left < 0 || t.b_left < 0 ||
             t.b_len < t.b_right ||
             (t.kind != GSPALN_FORWARD_WIP && t.kind != GSPALN_SCOREONLY_WIP && t.kind != GSPALN_HIRSCHBERG_WIP) ||
             (t.kind == GSPALN_HIRSCHBERG_WIP && (t.n_imd < 1 || t.a_right - t.a_left < 2)) ||
-            !t.a || !t.b || !t.sg)
-            return fail(ctx, GSPALN_EINVAL, "bad task");
+            !t.a || !t.b || !t.sg) {
+            char msg[256];
+            snprintf(msg, sizeof(msg), "bad task %d: kind %d a (%d, %d] b (%d, %d] of %d band [%d, %d] n_imd %d",
+                     i, t.kind, t.a_left, t.a_right, t.b_left, t.b_right, t.b_len, t.lw, t.up, t.n_imd);
+            return fail(ctx, GSPALN_EINVAL, msg);
+        }
         ctx->cells[i] = task_cells_h(t);
     }
     if (ctx->h_tasks.reserve(n + 1) != cudaSuccess || ctx->h_order.reserve(n + 1) != cudaSuccess)
@@ -667,6 +671,7 @@ struct LspTraitsH {
     {
         return g.a_right > t.a_len || g.b_right > t.b_len || g.a_left < 0 || g.b_left < 0;
     }
+    static bool beyond(const gspaln_h_task& t, const LspGeo& g) { return g.b_right > t.b_len || g.a_right > t.a_len; }
     static gspaln_h_task make_task(const gspaln_h_task& base, const LspGeo& g, int kind, int n_imd)
     {
         gspaln_h_task t = base;

@@ -72,7 +72,11 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
     // returns the index of the queued forward task or -1 (nothing to do / unsupported)
     auto queue_trcbk = [&](int item, const LspGeo& g) -> int {
         if (g.up - g.lw + TR::WPAD < 0) return -1;
-        if (g.a_right - g.a_left < 8) { status[items[item].root] = GSPALN_ST_UNSUPPORTED; return -1; }
+        if (g.a_right - g.a_left < 8 || g.b_right < g.b_left || g.a_left < 0 || g.b_left < 0 ||
+            TR::beyond(tasks[items[item].root], g)) {
+            status[items[item].root] = GSPALN_ST_UNSUPPORTED;
+            return -1;
+        }
         LspFwd f; f.root = items[item].root; f.g = g;
         fwds.push_back(std::move(f));
         LspPiece p; p.kind = 1; p.ref = (int) fwds.size() - 1;
@@ -103,6 +107,13 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
             const LspGeo& g = it.g;
             const Task& base = tasks[it.root];
             const int m = g.a_right - g.a_left, nn = g.b_right - g.b_left;
+            if (m < 0 || nn < 0 || g.a_left < 0 || g.b_left < 0 || TR::beyond(base, g)) {
+                // a range a Hirschberg pass narrowed to outside the sequences (the reference reads
+                // foreign memory from here on, e.g. fhlastH1's start point right of b_right)
+                status[it.root] = GSPALN_ST_UNSUPPORTED;
+                it.score = NEVSEL;
+                continue;
+            }
             if (!m && !nn) { it.score = 0; continue; }
             if (!m || !nn) {
                 lit2(it, g.a_left, g.b_left, g.a_right, g.b_right);
