@@ -567,7 +567,10 @@ int gspaln_submit(gspaln_ctx* ctx, const gspaln_task* tasks, int n, gspaln_resul
     int nchunks = 1;
     bounds[0] = 0; bounds[1] = n;
     const size_t total = ctx->c_elems;
-    if (n >= 256 && total >= (4u << 20)) {
+    // GSPALN_NO_STREAM=1: one chunk (profilers serialise the copy stream behind the running kernel,
+    // which would leave the kernel waiting for its watermark until the in-kernel time-out)
+    static const bool no_stream = getenv("GSPALN_NO_STREAM") != nullptr;
+    if (!no_stream && n >= 256 && total >= (4u << 20)) {
         // boundaries by cumulative columns (what packing and H2D cost); small first chunk
         nchunks = 0;
         size_t acc = 0;

@@ -547,7 +547,10 @@ int gspaln_h_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gspaln
     int nchunks = 1;
     bounds[0] = 0; bounds[1] = n;
     const size_t total = ctx->c_elems;
-    if (n >= 256 && total >= (2u << 20)) {
+    // GSPALN_NO_STREAM=1: one chunk (profilers serialise the copy stream behind the running kernel,
+    // which would leave the kernel waiting for its watermark until the in-kernel time-out)
+    static const bool no_stream = getenv("GSPALN_NO_STREAM") != nullptr;
+    if (!no_stream && n >= 256 && total >= (2u << 20)) {
         nchunks = 0;
         size_t acc = 0;
         const int want = (int) std::min<size_t>(MAX_CHUNKS_H, 2 + total / (2u << 20));
