@@ -81,13 +81,9 @@ struct DevTaskH {
 };
 
 struct __align__(16) RingH {    // expanded column record (32 B = two 16-byte halves)
-    // A column carries at most two acceptor (donor) candidates: one of phase -1 / 0 / +1, and a
-    // second one of phase +1 when its phs field is 2 ("both -1 and +1", e.g. AGAG / GTGT).
-    int s3a, s3b;               // acceptor signals of candidate A / B (SIG_NONE: no such candidate)
-    int meta;                   // phase slot of A: acceptor bits 0-1, donor bits 4-5; B present: bit 2 / bit 6
+    int s3[3];
     int prof;                   // byte offset of the substitution-table row
-    int s5a, s5b;               // donor signals + mean intron penalty
-    int pad;
+    int s5[3];
     int cv;
 };
 
@@ -173,17 +169,12 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
         re.prof = (int) ((ci.w >> 16) & 0xffu) * (MTX_LD * 4);
         re.cv = with_sig ? lo16(ci.w) : 0;
         const bool s = SPJ && with_sig;
-        const unsigned f3 = s ? (fl & 7u) : 0u, f5 = s ? ((fl >> 3) & 7u) : 0u;
-        const int s3[3] = {lo16(ci.x), hi16(ci.x), lo16(ci.y)};
-        const int s5[3] = {hi16(ci.y), lo16(ci.z), hi16(ci.z)};
-        const int a3 = (f3 & 1u) ? 0 : ((f3 & 2u) ? 1 : 2), a5 = (f5 & 1u) ? 0 : ((f5 & 2u) ? 1 : 2);
-        const bool two3 = (f3 & 5u) == 5u, two5 = (f5 & 5u) == 5u;
-        re.s3a = f3 ? (a3 == 0 ? s3[0] : (a3 == 1 ? s3[1] : s3[2])) : SIG_NONE;
-        re.s3b = two3 ? s3[2] : SIG_NONE;
-        re.s5a = f5 ? (a5 == 0 ? s5[0] : (a5 == 1 ? s5[1] : s5[2])) : SIG_NONE;
-        re.s5b = two5 ? s5[2] : SIG_NONE;
-        re.meta = a3 | (two3 ? 4 : 0) | (a5 << 4) | (two5 ? 64 : 0);
-        re.pad = 0;
+        re.s3[0] = (s && (fl & 1u)) ? lo16(ci.x) : SIG_NONE;
+        re.s3[1] = (s && (fl & 2u)) ? hi16(ci.x) : SIG_NONE;
+        re.s3[2] = (s && (fl & 4u)) ? lo16(ci.y) : SIG_NONE;
+        re.s5[0] = (s && (fl & 8u)) ? hi16(ci.y) : SIG_NONE;
+        re.s5[1] = (s && (fl & 16u)) ? lo16(ci.z) : SIG_NONE;
+        re.s5[2] = (s && (fl & 32u)) ? hi16(ci.z) : SIG_NONE;
         return re;
     };
     // Bank-conflict-free ring: the four threads of a strip read slots 12 apart (3 columns x 4
@@ -197,8 +188,8 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
     };
     auto ring_store = [&](int c, const RingH& re) {
         char* dst = ring_addr(c);
-        *reinterpret_cast<int4*>(dst + hswap) = make_int4(re.s3a, re.s3b, re.meta, re.prof);
-        *reinterpret_cast<int4*>(dst + (16 - hswap)) = make_int4(re.s5a, re.s5b, re.pad, re.cv);
+        *reinterpret_cast<int4*>(dst + hswap) = make_int4(re.s3[0], re.s3[1], re.s3[2], re.prof);
+        *reinterpret_cast<int4*>(dst + (16 - hswap)) = make_int4(re.s5[0], re.s5[1], re.s5[2], re.cv);
     };
 
     unsigned nxt_band = 0;
@@ -287,8 +278,8 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
 #pragma unroll
             for (int k = NRH - 1; k >= 0; --k) {
                 const char* rp = ring_addr(n - 3 * (row0 + k));
-                const int4 ra = *reinterpret_cast<const int4*>(rp + hswap);         // s3a, s3b, meta, prof
-                const int4 rb = *reinterpret_cast<const int4*>(rp + (16 - hswap));  // s5a, s5b, -, cv
+                const int4 ra = *reinterpret_cast<const int4*>(rp + hswap);         // s3[0..2], prof
+                const int4 rb = *reinterpret_cast<const int4*>(rp + (16 - hswap));  // s5[0..2], cv
                 const int cv = rb.w;
                 const int U3 = k ? H[2][k ? k - 1 : 0] : u3;
                 const int U4 = k ? H[3][k ? k - 1 : 0] : up4;
@@ -323,49 +314,31 @@ __device__ void run_pass_h(const DevParamsH& P, const SmemH& sm, const DevTaskH&
                 if (e > h) { h = e; pb = eb; }
                 bool ab = false;
                 if (SPJ) {
-                    // acceptors (wip.h:206-246).  The reference tries the phases -1, 0, +1 in turn;
-                    // a phase without an acceptor in this column contributes nevsel (liftv), so
-                    // only the one or two real candidates of the column need evaluating.
+                    // acceptors, one candidate per splice phase (wip.h:206-246); a slot without
+                    // an acceptor in this column contributes nevsel
                     const int h0 = h;
                     if (liftv > h) { h = liftv; pb = TH_ACCM; }
-                    const int meta = ra.z;
-                    {
-                        const int fz = meta & 3;
-                        const int Vs = fz == 0 ? V[0][k] : (fz == 1 ? V[1][k] : V[2][k]);
-                        const int Ns = fz == 0 ? NJ[0][k] : (fz == 1 ? NJ[1][k] : NJ[2][k]);
-                        const int q0 = sat16(Vs + ra.x);
-                        const int2 pq = pen_base[min(j + Ns, pen_cap)];
+                    const int s3v[3] = {ra.x, ra.y, ra.z};
+#pragma unroll
+                    for (int fz = 0; fz < 3; ++fz) {
+                        const int q0 = sat16(V[fz][k] + s3v[fz]);
+                        const int2 pq = pen_base[min(j + NJ[fz][k], pen_cap)];
                         const int q = min(max(q0 + pq.x, pq.y), 32767);
                         if (q > h) { h = q; pb = TH_ACCM + fz; }
                     }
-                    if (meta & 4) {                             // phs3 == 2: a second candidate of phase +1
-                        const int q0 = sat16(V[2][k] + ra.y);
-                        const int2 pq = pen_base[min(j + NJ[2][k], pen_cap)];
-                        const int q = min(max(q0 + pq.x, pq.y), 32767);
-                        if (q > h) { h = q; pb = TH_ACCP; }
-                    }
-                    ab = h > h0 && ra.x > SIG_NONE / 2;
+                    ab = h > h0 && max(max(ra.x, ra.y), ra.z) > SIG_NONE / 2;
                 }
                 if (clampL) { if (h < 0) { h = 0; hb = 0; } }
                 if (SPJ) {
                     // donors (wip.h:268-296): phase +1 leaves from the diagonal predecessor
-                    const int meta = ra.z;
-                    const int fz = (meta >> 4) & 3;
-                    {
-                        const int q = sat16((fz == 2 ? DV : h) + rb.x);
-                        const int Vs = fz == 0 ? V[0][k] : (fz == 1 ? V[1][k] : V[2][k]);
-                        const bool don = !ab && q > Vs;         // no candidate: q == -32768
-                        const bool d0 = don && fz == 0, d1 = don && fz == 1, d2 = don && fz == 2;
-                        V[0][k] = d0 ? q : V[0][k]; V[1][k] = d1 ? q : V[1][k]; V[2][k] = d2 ? q : V[2][k];
-                        NJ[0][k] = d0 ? -j : NJ[0][k]; NJ[1][k] = d1 ? -j : NJ[1][k]; NJ[2][k] = d2 ? -j : NJ[2][k];
+                    const int s5v[3] = {rb.x, rb.y, rb.z};
+#pragma unroll
+                    for (int fz = 0; fz < 3; ++fz) {
+                        const int q = sat16((fz == 2 ? DV : h) + s5v[fz]);
+                        const bool don = !ab && q > V[fz][k];
+                        V[fz][k] = don ? q : V[fz][k];
+                        NJ[fz][k] = don ? -j : NJ[fz][k];
                         if (TRACE && don) hb |= TH_DONM << fz;
-                    }
-                    if (meta & 64) {                            // phs5 == 2: a second donor of phase +1
-                        const int q = sat16(DV + rb.y);
-                        const bool don = !ab && q > V[2][k];
-                        V[2][k] = don ? q : V[2][k];
-                        NJ[2][k] = don ? -j : NJ[2][k];
-                        if (TRACE && don) hb |= TH_DONP;
                     }
                 }
                 if (LOCAL) {
