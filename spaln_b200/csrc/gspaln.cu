@@ -91,20 +91,24 @@ using KernelFn = void (*)(const DevParams*, const int2*, const DevTask*, const i
                           const unsigned char*, const ColInfo*, unsigned*, long long,
                           unsigned char*, long long, int2*, DevResult*, const int*);
 
-KernelFn kernel_fn(bool trace, bool local, bool spj)
+KernelFn kernel_fn(bool trace, bool local, bool spj, bool dagp = false)
 {
-    static const KernelFn tab[8] = {
-        dp_wip_kernel<false, false, false>, dp_wip_kernel<false, false, true>,
-        dp_wip_kernel<false, true, false>, dp_wip_kernel<false, true, true>,
-        dp_wip_kernel<true, false, false>, dp_wip_kernel<true, false, true>,
-        dp_wip_kernel<true, true, false>, dp_wip_kernel<true, true, true>,
+    static const KernelFn tab[16] = {
+        dp_wip_kernel<false, false, false, false>, dp_wip_kernel<false, false, true, false>,
+        dp_wip_kernel<false, true, false, false>, dp_wip_kernel<false, true, true, false>,
+        dp_wip_kernel<true, false, false, false>, dp_wip_kernel<true, false, true, false>,
+        dp_wip_kernel<true, true, false, false>, dp_wip_kernel<true, true, true, false>,
+        dp_wip_kernel<false, false, false, true>, dp_wip_kernel<false, false, true, true>,
+        dp_wip_kernel<false, true, false, true>, dp_wip_kernel<false, true, true, true>,
+        dp_wip_kernel<true, false, false, true>, dp_wip_kernel<true, false, true, true>,
+        dp_wip_kernel<true, true, false, true>, dp_wip_kernel<true, true, true, true>,
     };
-    return tab[(trace ? 4 : 0) | (local ? 2 : 0) | (spj ? 1 : 0)];
+    return tab[(dagp ? 8 : 0) | (trace ? 4 : 0) | (local ? 2 : 0) | (spj ? 1 : 0)];
 }
 
-const void* kernel_ptr(bool trace, bool local, bool spj)
+const void* kernel_ptr(bool trace, bool local, bool spj, bool dagp = false)
 {
-    return reinterpret_cast<const void*>(kernel_fn(trace, local, spj));
+    return reinterpret_cast<const void*>(kernel_fn(trace, local, spj, dagp));
 }
 
 using UdhKernelFn = void (*)(const DevParams*, const int2*, const DevTask*, const int*, int, int*,
@@ -150,7 +154,8 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
 {
     if (!out || !prm) return GSPALN_EINVAL;
     *out = nullptr;
-    if (prm->noll != 2 || prm->simdim <= 0 || prm->simdim >= ZROW ||
+    if ((prm->noll != 2 && prm->noll != 3) || prm->simdim <= 0 || prm->simdim >= ZROW ||
+        (prm->noll == 3 && ((short) prm->lgep > 0 || (short) (prm->lgep + prm->lgop) > 0)) ||
         prm->nquant < 1 || prm->nquant > GSPALN_MAXQUANT || prm->avmch <= 0 ||
         (short) prm->gep > 0 || (short) (prm->gep + prm->gop) > 0)     // kernels clamp gap terms on the low side only
         return GSPALN_EINVAL;
@@ -174,6 +179,8 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
     memset(&P, 0, sizeof(P));
     P.ge = (short) prm->gep;                        // Splat() narrows to short
     P.gn = (short) (prm->gep + prm->gop);
+    P.ge2 = (short) prm->lgep;                      // double affine (Noll == 3)
+    P.gn2 = (short) (prm->lgep + prm->lgop);
     P.ipen = (short) (prm->spj ? prm->ipen : NEV);
     P.mil = (short) prm->llmt;
     P.nquant = prm->nquant;
@@ -225,8 +232,9 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
         gspaln_destroy(ctx);
         return GSPALN_ENOMEM;
     }
-    const void* kt = kernel_ptr(true, P.local, P.spj);
-    const void* ks = kernel_ptr(false, P.local, P.spj);
+    const bool dagp = prm->noll == 3;
+    const void* kt = kernel_ptr(true, P.local, P.spj, dagp);
+    const void* ks = kernel_ptr(false, P.local, P.spj, dagp);
     cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_bytes);
     cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_bytes);
     int occ = 0;
@@ -274,7 +282,7 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         const gspaln_task& t = tasks[i];
         if (t.a_right < t.a_left || t.b_right < t.b_left || t.up - t.lw + 3 < 0 ||
             (t.kind != GSPALN_FORWARD_WIP && t.kind != GSPALN_SCOREONLY_WIP && t.kind != GSPALN_HIRSCHBERG_WIP) ||
-            (t.kind == GSPALN_HIRSCHBERG_WIP && (t.n_imd < 1 || t.a_right - t.a_left < 2)) ||
+            (t.kind == GSPALN_HIRSCHBERG_WIP && (t.n_imd < 1 || t.a_right - t.a_left < 2 || ctx->prm.noll != 2)) ||
             !t.a || !t.b || (ctx->prm.spj && (!t.sig5 || !t.sig3))) {
             char msg[256];
             snprintf(msg, sizeof(msg), "bad task %d: kind %d a (%d, %d] b (%d, %d] band [%d, %d] n_imd %d",
@@ -349,7 +357,7 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         cudaMemGetInfo(&free_b, &total_b);
         free_b += ctx->d_trace.cap + ctx->d_band.cap * sizeof(unsigned);
         const size_t budget = (size_t) (0.85 * (double) free_b);
-        while (gt > 1 && (size_t) gt * WARPS_PER_CTA * (trace_slab + band_slab * 4) > budget) gt = gt * 3 / 4;
+        while (gt > 1 && (size_t) gt * WARPS_PER_CTA * (trace_slab + band_slab * 8) > budget) gt = gt * 3 / 4;
         int gu = n_udh ? ctas(ctx->grid_udh, n_udh) : 0;
         const size_t warps = (size_t) std::max(std::max(gt, gs), gu) * WARPS_PER_CTA;
         if (ctx->d_udh.reserve((size_t) gu * WARPS_PER_CTA * udh_slab + 64) != cudaSuccess) {
@@ -357,7 +365,7 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             return fail(ctx, GSPALN_ENOMEM, "device UDH workspace allocation");
         }
         ctx->grid_run_udh = gu;
-        if (ctx->d_band.reserve(warps * band_slab + 32) != cudaSuccess ||
+        if (ctx->d_band.reserve(warps * band_slab * (ctx->prm.noll == 3 ? 2 : 1) + 32) != cudaSuccess ||
             ctx->d_trace.reserve((size_t) gt * WARPS_PER_CTA * trace_slab + 256) != cudaSuccess) {
             cudaGetLastError();
             return fail(ctx, GSPALN_ENOMEM, "device workspace allocation");
@@ -441,18 +449,18 @@ static void pool_span(const gspaln_ctx* ctx, const gspaln_task* tasks, int lo, i
 // launches the kernels for order[lo .. hi) with ticket slot `slot` (3 counters per slot)
 static int launch_range(gspaln_ctx* ctx, int lo, int hi, int slot, int& launches, const int* ready = nullptr)
 {
-    const bool local = ctx->prm.local != 0, spj = ctx->prm.spj != 0;
+    const bool local = ctx->prm.local != 0, spj = ctx->prm.spj != 0, dagp = ctx->prm.noll == 3;
     int* tick = ctx->d_ticket.p + 3 * slot;
     const int cnt = hi - lo;
     if (ctx->n_trace) {
-        kernel_fn(true, local, spj)<<<ctx->grid_run_trace, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+        kernel_fn(true, local, spj, dagp)<<<ctx->grid_run_trace, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
             ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick,
             ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
             ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p, ready);
         ++launches;
     }
     if (ctx->n_score) {
-        kernel_fn(false, local, spj)<<<ctx->grid_run_score, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+        kernel_fn(false, local, spj, dagp)<<<ctx->grid_run_score, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
             ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 1,
             ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
             ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p, ready);
@@ -665,6 +673,7 @@ struct LspTraitsS {
     static float cvol(int m, int nn) { return (float) m * (nn + m); }
     static float coef_c(const gspaln_params& P) { return (float) ((P.noll + 1) * 4); }
     static bool is_local(const gspaln_params& P) { return P.local != 0; }
+    static bool udh_ok(const gspaln_params& P) { return P.noll == 2; }   // no double-affine Hirschberg pass yet
     static int trivial_score(const gspaln_params& P, const LspGeo& g, int m, int nn)
     {
         if (m) return (g.a_exgl || g.a_exgr) ? P.gep : (P.gop + m * P.gep);

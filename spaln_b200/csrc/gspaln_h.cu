@@ -645,6 +645,7 @@ struct LspTraitsH {
     static float cvol(int m, int nn) { return (float) m * (nn + 3 * m); }
     static float coef_c(const gspaln_h_params&) { return 12.f; }     // (Noll + 1) * sizeof(int), Noll == 2
     static bool is_local(const gspaln_h_params& P) { return (P.lcl & 16) != 0; }
+    static bool udh_ok(const gspaln_h_params&) { return true; }
     static int trivial_score(const gspaln_h_params& P, const LspGeo& g, int m, int nn)
     {
         auto ext = [&](int i) { return i > P.codonk1 ? P.lgep : P.gep; };

@@ -49,11 +49,12 @@ constexpr int RING = 32;                // doubled 16-entry ring of per-column i
 constexpr int PEN_INVALID = -200000;    // added to an int16: always far below the int16 range
 
 // TraceBackCode, src/rhomb_coord.h:36-61
-enum : unsigned { TB_DIAG = 1, TB_HORI = 2, TB_VERT = 8, TB_ACCR = 14,
-                  TB_NHOR = 16, TB_NVER = 32, TB_DONR = 128 };
+enum : unsigned { TB_DIAG = 1, TB_HORI = 2, TB_HORL = 3, TB_VERT = 8, TB_VERL = 9, TB_ACCR = 14,
+                  TB_NHOR = 16, TB_NVER = 32, TB_NHOL = 64, TB_NVEL = 128, TB_DONR = 128 };
 
 struct DevParams {
     int gn, ge;                 // (short)(gep + gop), (short) gep
+    int gn2, ge2;               // double affine (Noll == 3): (short)(lgep + lgop), (short) lgep
     int ipen, mil, nquant;
     int quant[MAXQ], mean[MAXQ];
     int avmch, local, spj, simdim, gappen1, gop, gep;
@@ -162,9 +163,10 @@ struct SmemLayout {
 //       last reset (counter value == step + NJ; saturation is implied by the
 //       clamp to the table size).
 // ---------------------------------------------------------------------------
-template <bool TRACE, bool LOCAL, bool SPJ>
+template <bool TRACE, bool LOCAL, bool SPJ, bool DAGP>
 __device__ __forceinline__ void strip_step(
     int (&HO)[NR], const int (&HN)[NR], int (&F)[NR], int (&E)[NR],
+    int (&F2)[NR], int (&E2)[NR], int up_f2, int gn2, int ge2,
     int (&V2)[NR], int (&NJ)[NR], const int (&arow)[NR],
     const char* __restrict__ ring_hi, const char* __restrict__ mtx_bytes,
     const int2* __restrict__ pen_tab, int pen_cap, int step,
@@ -190,17 +192,38 @@ __device__ __forceinline__ void strip_step(
         int e = satlo(E[k] + ge);
         if (!(e > x)) { e = x; hb = TB_NHOR; }
         E[k] = e;
+        int e2 = NEV, f2 = NEV;
+        if (DAGP) {
+            // second (long) gap state, src/fwd2s1_wip_simd.h:99-109, 312-321
+            const int x2 = satlo(left + gn2);
+            e2 = satlo(E2[k] + ge2);
+            if (!(e2 > x2)) { e2 = x2; hb |= TB_NHOL; }
+            E2[k] = e2;
+            if (!TRACE && e2 > e) { e = e2; E[k] = e; }     // score only: the two states are merged
+        }
         // vertical: query residue against a gap
         int f = satlo(uf + ge);
         x = satlo(uh + gn);
         if (!(f > x)) { f = x; hb |= TB_NVER; }
+        if (DAGP) {
+            const int uf2 = k ? F2[k ? k - 1 : 0] : up_f2;
+            f2 = satlo(uf2 + ge2);
+            // forwardS1_wip re-uses a register that by then holds the NVER flag (0 | 32): its long
+            // vertical gap opens from that value, not from H (wip.h:333,339); score only is sound
+            x = TRACE ? satlo((int) (hb & TB_NVER) + gn2) : satlo(uh + gn2);
+            if (!(f2 > x)) { f2 = x; hb |= TB_NVEL; }
+            F2[k] = f2;
+            if (!TRACE && f2 > f) f = f2;
+        }
         F[k] = f;
         // diagonal
         const int pv = *reinterpret_cast<const int*>(mtx_bytes + re.prof + arow[k]);
         int h = sat16(pv + dg);
         unsigned pb = TB_DIAG;
         if (f > h) { h = f; pb = TB_VERT; }
+        if (TRACE && DAGP && f2 > h) { h = f2; pb = TB_VERL; }
         if (e > h) { h = e; pb = TB_HORI; }
+        if (TRACE && DAGP && e2 > h) { h = e2; pb = TB_HORL; }
         bool acc = false;
         if (SPJ) {
             // acceptor: best donor of this row + 3' signal + binned length penalty,
@@ -224,7 +247,7 @@ __device__ __forceinline__ void strip_step(
             if (h >= best_v) { best_v = h; best_k = k; }    // descending k: ties end at the lowest row
         }
         HO[k] = h;
-        if (TRACE) tw[k >> 2] |= (hb | pb) << (8 * (k & 3));
+        if (TRACE) tw[k >> 2] |= ((hb | pb) & 0xffu) << (8 * (k & 3));
     }
 }
 
@@ -237,10 +260,10 @@ __device__ __forceinline__ void strip_step(
 // that finishes a strip starts its next one as soon as the strip above that one
 // is 15 + LAG steps ahead, so the systolic chain never drains inside a segment.
 // ---------------------------------------------------------------------------
-template <bool TRACE, bool LOCAL, bool SPJ>
+template <bool TRACE, bool LOCAL, bool SPJ, bool DAGP>
 __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
                          const DevTask& t, const unsigned char* __restrict__ aseq,
-                         const ColInfo* __restrict__ cols, unsigned* band,
+                         const ColInfo* __restrict__ cols, unsigned* band, int* band2,
                          unsigned char* trace, int ml0, int nstr, bool localL_now,
                          bool localR, int accscr, WarpMax& wmax)
 {
@@ -269,11 +292,14 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
     int rec_si = sidx == 0 ? 0 : -1000, rec_d = -g.n_start, old_si = -1000, old_d = 0;
 
     int HA[NR], HB[NR], F[NR], E[NR], V2[NR], NJ[NR], arow[NR];
+    int F2[NR], E2[NR];     // dead (and eliminated) unless DAGP
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
         HA[k] = NEV; HB[k] = NEV; F[k] = NEV; E[k] = NEV; V2[k] = NEV; NJ[k] = 0; arow[k] = 4 * ZROW;
+        if (DAGP) { F2[k] = NEV; E2[k] = NEV; }
     }
-    const int gn = P.gn, ge = P.ge;
+    const int gn = P.gn, ge = P.ge, gn2 = P.gn2, ge2 = P.ge2;
+    int nxt_f2 = NEV;
     const int floorL = localL_now ? 0 : INT_MIN;
     int prev_uh = NEV;
     int bval = INT_MIN, bstep = 0, bk = 0, bsi = 0;     // best local-mode cell of this thread
@@ -343,10 +369,11 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
         const int j8 = g.j9 - 1;
         // neighbour exchange inside a strip: bottom row of the thread above, as
         // of the previous step (every thread of the warp takes part)
-        int sh_h = NEV, sh_f = NEV;
+        int sh_h = NEV, sh_f = NEV, sh_f2 = NEV;
         if (TPS > 1) {
             sh_h = __shfl_up_sync(FULL, (i & 1) ? HA[NR - 1] : HB[NR - 1], 1);
             sh_f = __shfl_up_sync(FULL, F[NR - 1], 1);
+            if (DAGP) sh_f2 = __shfl_up_sync(FULL, F2[NR - 1], 1);
         }
         const int band_bias = g.ml + t.lw - 1;      // band entry of column c (diagonal c - ml): c - band_bias
         if (run && j == -1) {
@@ -356,12 +383,14 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
 #pragma unroll
             for (int k = 0; k < NR; ++k) {
                 HA[k] = NEV; HB[k] = NEV; F[k] = NEV; E[k] = NEV; V2[k] = NEV; NJ[k] = 0;
+                if (DAGP) { F2[k] = NEV; E2[k] = NEV; }
                 // rows beyond the last query residue score 0 (reference: pv_a stays 0)
                 arow[k] = (row0 + k < g.j9) ? 4 * (int) aseq[(g.ml - t.a_left) + row0 + k] : 4 * ZROW;
             }
             prev_uh = NEV;
             if (sub == 0) {
                 nxt_band = __ldcg(band + (g.n_start - band_bias));
+                if (DAGP) nxt_f2 = __ldcg(band2 + (g.n_start - band_bias));
                 prev_uh = lo16(__ldcg(band + (g.n_start - 1 - band_bias)));
             }
             nxt_col = col_fetch(g.n_start);
@@ -378,31 +407,37 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
         } else if (run && j >= 0) {
             const int n = g.n_start + j;
             const unsigned cur_band = nxt_band;
+            const int cur_f2 = nxt_f2;
             const RingEntry cur_col = col_decode(nxt_col, n, n <= t.b_right);
             if (j + 1 < nsteps) {
-                if (sub == 0) nxt_band = __ldcg(band + (n + 1 - band_bias));
+                if (sub == 0) {
+                    nxt_band = __ldcg(band + (n + 1 - band_bias));
+                    if (DAGP) nxt_f2 = __ldcg(band2 + (n + 1 - band_bias));
+                }
                 nxt_col = col_fetch(n + 1);
             }
             const int rslot = n & 15;
             ring[rslot * CTA_THREADS] = cur_col;
             ring[(rslot + 16) * CTA_THREADS] = cur_col;
             const char* ring_hi = reinterpret_cast<const char*>(ring + (rslot + 16 - row0) * CTA_THREADS);
-            int up_h, up_f, up_d;
+            int up_h, up_f, up_d, up_f2;
             if (sub == 0) {
-                up_h = lo16(cur_band); up_f = hi16(cur_band);
+                up_h = lo16(cur_band); up_f = hi16(cur_band); up_f2 = cur_f2;
             } else {
-                up_h = sh_h; up_f = sh_f;
+                up_h = sh_h; up_f = sh_f; up_f2 = sh_f2;
             }
             up_d = prev_uh;
             prev_uh = up_h;
             unsigned tw[NR / 4];
             int sv = INT_MIN, sk = 0;
             if (i & 1)      // warp-uniform ping-pong (every thread steps once per iteration)
-                strip_step<TRACE, LOCAL, SPJ>(HB, HA, F, E, V2, NJ, arow, ring_hi, mtx_bytes, sm.pen,
-                                              P.pen_cap, j, up_h, up_f, up_d, gn, ge, floorL, tw, sv, sk);
+                strip_step<TRACE, LOCAL, SPJ, DAGP>(HB, HA, F, E, F2, E2, up_f2, gn2, ge2, V2, NJ, arow, ring_hi,
+                                                    mtx_bytes, sm.pen, P.pen_cap, j, up_h, up_f, up_d, gn, ge,
+                                                    floorL, tw, sv, sk);
             else
-                strip_step<TRACE, LOCAL, SPJ>(HA, HB, F, E, V2, NJ, arow, ring_hi, mtx_bytes, sm.pen,
-                                              P.pen_cap, j, up_h, up_f, up_d, gn, ge, floorL, tw, sv, sk);
+                strip_step<TRACE, LOCAL, SPJ, DAGP>(HA, HB, F, E, F2, E2, up_f2, gn2, ge2, V2, NJ, arow, ring_hi,
+                                                    mtx_bytes, sm.pen, P.pen_cap, j, up_h, up_f, up_d, gn, ge,
+                                                    floorL, tw, sv, sk);
             if (LOCAL && localR) {
                 // vmax over the real rows of this step; strictly greater wins (earlier steps keep ties)
                 int v = INT_MIN, kk = 0;
@@ -430,15 +465,18 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
                 const int kbot = j8 - row0;
                 int out_h = (i & 1) ? HB[NR - 1] : HA[NR - 1];
                 int out_f = F[NR - 1];
+                int out_f2 = DAGP ? F2[NR - 1] : 0;
                 if (kbot != NR - 1) {
 #pragma unroll
                     for (int k = 0; k < NR - 1; ++k)
-                        if (k == kbot) { out_h = (i & 1) ? HB[k] : HA[k]; out_f = F[k]; }
+                        if (k == kbot) { out_h = (i & 1) ? HB[k] : HA[k]; out_f = F[k]; if (DAGP) out_f2 = F2[k]; }
                 }
                 const int cb = n - j8;                  // column of the bottom row
                 const int r0 = cb - (g.ml + g.j9);
-                if (cb > t.b_left && r0 >= t.lw && r0 <= t.up)
+                if (cb > t.b_left && r0 >= t.lw && r0 <= t.up) {
                     __stcg(band + (r0 - t.lw + 1), pack16(out_h, out_f));
+                    if (DAGP) __stcg(band2 + (r0 - t.lw + 1), out_f2);
+                }
             }
             if (j == nsteps - 1) {
                 // strip finished: this slot's next strip
@@ -531,6 +569,14 @@ static __device__ int walk_trace(const DevTask& t, const unsigned char* trace, i
             bool stop = false;
             while (!(code & TB_NVER)) { code = to_upper(0); if (!code) { stop = true; break; } }
             if (!stop) code = to_upper(0);
+        } else if (dir == TB_HORL) {
+            bool stop = false;
+            while (!(code & TB_NHOL)) { code = to_left(1); if (!code) { stop = true; break; } }
+            if (!stop) code = to_left(1);
+        } else if (dir == TB_VERL) {
+            bool stop = false;
+            while (!(code & TB_NVEL)) { code = to_upper(0); if (!code) { stop = true; break; } }
+            if (!stop) code = to_upper(0);
         } else if (dir == TB_ACCR) {
             do { code = to_left(1); } while (code && !(code & TB_DONR));
         } else {
@@ -546,7 +592,7 @@ static __device__ int walk_trace(const DevTask& t, const unsigned char* trace, i
 // ---------------------------------------------------------------------------
 // persistent kernel: each warp pulls problems from a global ticket counter
 // ---------------------------------------------------------------------------
-template <bool TRACE, bool LOCAL, bool SPJ>
+template <bool TRACE, bool LOCAL, bool SPJ, bool DAGP>
 __global__ void __launch_bounds__(CTA_THREADS, 3)
 dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
               const DevTask* __restrict__ tasks,
@@ -576,7 +622,9 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
     // per-warp workspace: band rows and trace matrix are reused by every
     // problem this warp picks up (the walk runs before the next forward pass)
     const long long wslot = (long long) blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-    unsigned* band = bandpool + wslot * band_slab;
+    // double affine: the slab holds the {H | F} words, then as many F2 words
+    unsigned* band = bandpool + wslot * band_slab * (DAGP ? 2 : 1);
+    int* band2 = DAGP ? reinterpret_cast<int*>(band + band_slab) : nullptr;
     unsigned char* trace = TRACE ? tracepool + wslot * trace_slab : nullptr;
 
     for (;;) {
@@ -600,7 +648,7 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
         const bool LocalR = LOCAL && a_exgr && b_exgr;
 
         // ---- fhinitS1 (src/fwd2s1_simd.cc:163-184); entry i <-> diagonal lw - 1 + i
-        for (int i = lane; i < buf_size; i += 32) band[i] = pack16(NEV, NEV);
+        for (int i = lane; i < buf_size; i += 32) { band[i] = pack16(NEV, NEV); if (DAGP) band2[i] = NEV; }
         __syncwarp();
         {
             const int rl = t.b_left - t.a_left;
@@ -639,8 +687,8 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
             int nstr = (t.a_right - ml0 + NELEM - 1) / NELEM;
             if (mc >= ml0 && mc < ml0 + nstr * NELEM && ((mc - ml0) % NELEM) == 0)
                 nstr = (mc - ml0) / NELEM + 1;
-            run_pass<TRACE, LOCAL, SPJ>(P, sm, t, aseq, cols, band, trace, ml0, nstr,
-                                        LocalL && !accscr, LocalR, accscr, wmax);
+            run_pass<TRACE, LOCAL, SPJ, DAGP>(P, sm, t, aseq, cols, band, band2, trace, ml0, nstr,
+                                              LocalL && !accscr, LocalR, accscr, wmax);
             const int last_ml = ml0 + (nstr - 1) * NELEM;
             if (last_ml == mc) {
                 // src/fwd2s1_wip_simd.h:454-465
@@ -658,6 +706,11 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
                         if (i < nn) { h = sat16(h); f = sat16(f); }
                         else { h = (short) h; f = (short) f; }
                         __stcg(band + i, pack16(h, f));
+                        if (DAGP) {
+                            int f2 = __ldcg(band2 + i) - cm;
+                            f2 = i < nn ? sat16(f2) : (int) (short) f2;
+                            __stcg(band2 + i, f2);
+                        }
                     }
                     accscr += cm;
                     mc += md;

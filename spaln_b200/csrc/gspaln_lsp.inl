@@ -151,6 +151,11 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
                 if (f >= 0) item_fwd.push_back({id, f}); else it.score = NEVSEL;
                 continue;
             }
+            if (!TR::udh_ok(P)) {       // the Hirschberg route needs a pass that is not on the device
+                status[it.root] = GSPALN_ST_UNSUPPORTED;
+                it.score = NEVSEL;
+                continue;
+            }
             it.recursive = recursive;
             it.n_imd = n_imd;
             udh_items.push_back(id);

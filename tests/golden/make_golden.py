@@ -30,6 +30,8 @@ CONFIGS = {
     "dna_A2_local": ("-Q0 -A2 -S1 -yX0 -LS -TDictyost", 12),
     "dna_A3_global": ("-Q0 -A3 -S1 -yX0 -TDictyost", 13),
     "dna_A2_tetrapod": ("-Q0 -A2 -S1 -TTetrapod", 14),
+    # double affine gap penalty (alprm.ls = 3 -> PwdB::Noll == 3)
+    "dna_A2_dagp": ("-Q0 -A2 -S1 -yX0 -yl3 -TDictyost", 18),
     # small -V forces the unidirectional-Hirschberg path on small inputs (SURVEY section 4 pin d)
     "dna_A2_udh": ("-Q0 -A2 -S1 -yX0 -V256K -TDictyost", 15),
     "dna_A2_udh_local": ("-Q0 -A2 -S1 -yX0 -V256K -LS -TDictyost", 16),

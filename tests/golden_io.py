@@ -5,6 +5,7 @@ import numpy as np
 
 GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
 GOLDEN_NAMES = ["dna_A2_global", "dna_A2_local", "dna_A3_global", "dna_A2_tetrapod"]
+DAGP_NAMES = ["dna_A2_dagp"]        # double affine gaps (-yl3)
 UDH_NAMES = ["dna_A2_udh", "dna_A2_udh_local", "dna_A6_udh_recursive"]
 GEOM_KEYS = ["a_left", "a_right", "b_left", "b_right", "a_exgl", "a_exgr", "b_exgl", "b_exgr",
              "lw", "up"]

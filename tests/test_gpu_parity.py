@@ -19,7 +19,7 @@ def _problems(probs):
     return [Problem.from_export(pb, pb["lw"], pb["up"]) for pb in probs]
 
 
-@pytest.mark.parametrize("name", golden_io.GOLDEN_NAMES)
+@pytest.mark.parametrize("name", golden_io.GOLDEN_NAMES + golden_io.DAGP_NAMES)
 def test_forward_wip_matches_reference_golden(name):
     prm, probs = golden_io.load(name)
     eng = _engine(prm)
@@ -31,7 +31,7 @@ def test_forward_wip_matches_reference_golden(name):
     eng.close()
 
 
-@pytest.mark.parametrize("name", golden_io.GOLDEN_NAMES)
+@pytest.mark.parametrize("name", golden_io.GOLDEN_NAMES + golden_io.DAGP_NAMES)
 def test_scoreonly_wip_matches_reference_golden(name):
     prm, probs = golden_io.load(name)
     eng = _engine(prm)
@@ -68,6 +68,9 @@ def _synthetic(prm, rng, n, qlen, flank, intron_scale=1.0, flags=None, sub=None)
     ("dna_A2_global", (1, 0, 0, 1), (7, 3, 11, 5)),
     ("dna_A2_local", None, None),
     ("dna_A3_global", None, None),
+    ("dna_A2_dagp", None, None),
+    ("dna_A2_dagp", (0, 0, 0, 0), None),
+    ("dna_A2_dagp", (1, 0, 0, 1), (7, 3, 11, 5)),
 ])
 def test_forward_wip_matches_oracle_seeded(oracle, name, flags, sub):
     prm, _ = golden_io.load(name)

@@ -6,7 +6,7 @@ import pytest
 import golden_io
 
 
-@pytest.mark.parametrize("name", golden_io.GOLDEN_NAMES)
+@pytest.mark.parametrize("name", golden_io.GOLDEN_NAMES + golden_io.DAGP_NAMES)
 def test_oracle_matches_reference_golden(oracle, name):
     prm, probs = golden_io.load(name)
     assert len(probs) >= 25

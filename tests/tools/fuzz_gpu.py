@@ -62,7 +62,7 @@ def report(name, bad, n):
 
 
 ONLY = sys.argv[3] if len(sys.argv) > 3 else ""
-for fixture in ("dna_A2_global", "dna_A2_local", "dna_A3_global") if ONLY in ("", "dna") else ():
+for fixture in ("dna_A2_global", "dna_A2_local", "dna_A3_global", "dna_A2_dagp") if ONLY in ("", "dna") else ():
     prm, _ = golden_io.load(fixture)
     rng = np.random.default_rng(SEED * 1000 + hash(fixture) % 997)
     probs = [dna_problem(prm, rng, i) for i in range(N)]
@@ -76,6 +76,19 @@ for fixture in ("dna_A2_global", "dna_A2_local", "dna_A3_global") if ONLY in (""
                 s.score != O.scoreonly_wip(prm, pb)["score"]:
             bad.append(i)
     report(f"{fixture} forward / score-only", bad, N)
+    if int(prm["Noll"]) == 3:       # double affine: no Hirschberg pass on the device (nor in the oracle)
+        rl = eng.lspS_ng(P, max_vmf_space=1 << 25, sh=int(prm["sh"]), alg=2)
+        bad = []
+        for i, (pb, r) in enumerate(zip(probs, rl)):
+            o = O.lsp(prm, pb, cap=1 << 17, max_vmf_space=1 << 25)
+            if o["unsupported"]:
+                if r.status != 3:
+                    bad.append(i)
+            elif r.status or r.score != o["score"] or not np.array_equal(r.skl, o["skl"]):
+                bad.append(i)
+        report(f"{fixture} lspS_ng -V32M", bad, N)
+        eng.close()
+        continue
     # Hirschberg pass + driver at small -V
     sel = [i for i, pb in enumerate(probs) if pb["a_right"] - pb["a_left"] >= 32]
     PU = [Problem.from_export(probs[i], probs[i]["lw"], probs[i]["up"]) for i in sel]
