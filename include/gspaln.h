@@ -74,7 +74,7 @@ typedef struct gspaln_params {
     int32_t gep;                /* PwdB::BasicGEP  (< 0) */
     int32_t lgop;               /* PwdB::LongGOP */
     int32_t lgep;               /* PwdB::LongGEP */
-    int32_t noll;               /* PwdB::Noll: 2 = affine (3 = double affine: not yet on device) */
+    int32_t noll;               /* PwdB::Noll: 2 = affine, 3 = double affine (forward / score-only kernels) */
     int32_t ipen;               /* IntronPenalty::Penalty() == GapWI */
     int32_t llmt;               /* IntronPrm.llmt */
     int32_t nquant;             /* IntronPrm.nquant (1 for -A3) */
