@@ -18,6 +18,19 @@
 #include "spaln.cc"
 #undef main
 
+// Exinon keeps its INT53 array and sig53tab private (src/codepot.h:72-80); the harness exports
+// them as inputs of the scalar kernel.  Explicit instantiation may name private members, which
+// gives access without touching the reference headers.
+namespace {
+template <typename Tag, typename Tag::type M> struct Rob {
+	friend typename Tag::type get(Tag) { return M; }
+};
+struct ExinonInt53 { typedef INT53* Exinon::*type; friend type get(ExinonInt53); };
+struct ExinonTab { typedef STYPE** Exinon::*type; friend type get(ExinonTab); };
+template struct Rob<ExinonInt53, &Exinon::int53>;
+template struct Rob<ExinonTab, &Exinon::sig53tab>;
+}
+
 extern "C" {
 int shim_s1_kernel(const Seq** seqs, const PwdB* pwd, int lw, int up,
 	int kind, int n_imd, int mode, int* score, int* skl_out, int cap,
@@ -25,6 +38,8 @@ int shim_s1_kernel(const Seq** seqs, const PwdB* pwd, int lw, int up,
 int shim_s1_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up,
 	int* score, int* skl_out, int cap, double* seconds);
 int shim_s1_nelem();
+int shim_s1_scalar(const Seq** seqs, const PwdB* pwd, int lw, int up,
+	int* score, int* skl_out, int cap, double* seconds);
 int shim_h1_udh(const Seq** seqs, const PwdB* pwd, int lw, int up, int n_imd, int* score,
 	int* cpos_out, double* seconds);
 int shim_h1_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up, int* score, int* skl_out,
@@ -313,6 +328,39 @@ int ref_task_adapter(void* h, int lw, int up, int kind, int device,
 	RefTask* t = (RefTask*) h;
 	return shim_s1_adapter((const Seq**) t->sqs, g_pwd, lw, up, kind, device,
 	    score, skl_out, cap);
+}
+
+// inputs of the exact intron scoring (Aln2s1::forwardS_ng): per column n = 0 .. b.len + 1 the
+// INT53 nibbles (dinc5 | dinc3 << 4 | cano5 << 8 | cano3 << 12, src/codepot.h:49-54)
+void ref_task_export_int53(void* h, unsigned short* out)
+{
+	RefTask* t = (RefTask*) h;
+	const Seq* b = t->sqs[1];
+	for (int n = 0; n <= b->len + 1; ++n) {
+	    const INT53& w = (b->exin->*get(ExinonInt53()))[n];
+	    out[n] = (unsigned short) (w.dinc5 | (w.dinc3 << 4) | (w.cano5 << 8) | (w.cano3 << 12));
+	}
+}
+
+// sig53tab (544 shorts, src/codepot.cc:281-285) of this task's Exinon and
+// IntronPenalty::Penalty(n) for n in [0, n_pen); misc[0] = alprm2.Z > 0
+int ref_task_export_ng_tables(void* h, short* sig53tab, short* penalty, int n_pen, int* misc)
+{
+	RefTask* t = (RefTask*) h;
+	const Seq* b = t->sqs[1];
+	if (!b->exin || !g_pwd->IntPen) return -1;
+	STYPE** tab = b->exin->*get(ExinonTab());
+	if (!tab) return -1;
+	for (int i = 0; i < 544; ++i) sig53tab[i] = tab[0][i];
+	for (int n = 0; n < n_pen; ++n) penalty[n] = g_pwd->IntPen->Penalty(n);
+	misc[0] = alprm2.Z > 0;
+	return 0;
+}
+
+int ref_task_scalar(void* h, int lw, int up, int* score, int* skl_out, int cap, double* seconds)
+{
+	RefTask* t = (RefTask*) h;
+	return shim_s1_scalar((const Seq**) t->sqs, g_pwd, lw, up, score, skl_out, cap, seconds);
 }
 
 int ref_task_lsp(void* h, int lw, int up, int* score, int* skl_out, int cap,

@@ -36,6 +36,21 @@ struct ShimAln2s1 : public Aln2s1 {
 	    delete mfd; mfd = 0;
 	    return scr;
 	}
+	// Aln2s1::trcbkalignS_ng (src/fwd2s1.cc:1667-1710) with the SIMD level forced to 0, so that
+	// its scalar branch (forwardS_ng + Vmf::traceback + end adjustment) runs for any number of
+	// query rows -- the branch the stock code takes for blocks with fewer than 8 rows.
+	VTYPE	run_scalar(const WINDOW& wdw, SKL* out, int cap, int* n_out) {
+	    *const_cast<int*>(&simd) = 0;
+	    mfd = new Mfile(sizeof(SKL));
+	    VTYPE scr = trcbkalignS_ng(wdw);
+	    int n = (int) mfd->size();
+	    SKL* skl = (SKL*) mfd->flush();
+	    *n_out = n;
+	    for (int i = 0; i < n && i < cap; ++i) out[i] = skl[i];
+	    delete[] skl;
+	    delete mfd; mfd = 0;
+	    return scr;
+	}
 };
 
 int copy_out(Mfile& mfd, SKL* out, int cap)
@@ -103,6 +118,20 @@ int shim_s1_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up,
 }
 
 int shim_s1_nelem() { return Simd_functions<short>::Nelem; }
+
+// the scalar trace-back kernel (Aln2s1::forwardS_ng through trcbkalignS_ng) on the current ranges
+int shim_s1_scalar(const Seq** seqs, const PwdB* pwd, int lw, int up,
+	int* score, int* skl_out, int cap, double* seconds)
+{
+	WINDOW wdw = {lw, up, up - lw + 3};
+	ShimAln2s1 alnv(seqs, pwd);
+	int n = 0;
+	auto t0 = std::chrono::steady_clock::now();
+	*score = alnv.run_scalar(wdw, (SKL*) skl_out, cap, &n);
+	auto t1 = std::chrono::steady_clock::now();
+	if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+	return n;
+}
 
 // same call as shim_s1_kernel(kind 0 | 1) but through the gspaln adapter (GPU)
 int shim_s1_adapter(const Seq** seqs, const PwdB* pwd, int lw, int up,

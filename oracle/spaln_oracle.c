@@ -874,8 +874,9 @@ int so_hirschberg_wip(const so_params* p, const so_task* t, int n_im,
  * rcsv_postwork (1758-1799), diagonalS_ng (1629-1665) and stripe
  * (src/aln2.cc:156-176), for simd = 2 | 3 (-A2 / -A3) and single affine gaps.
  * Problems with fewer than 8 query rows go to the scalar exact-ILD kernel in
- * the reference (src/fwd2s1.cc:1676); that kernel is not restated here, so
- * such calls set `unsupported`.
+ * the reference (src/fwd2s1.cc:1676), restated in spaln_oracle_ng.c; without
+ * its tables (so_params.penalty / sig53tab, so_task.int53) such calls set
+ * `unsupported`.
  * ========================================================================= */
 #include <math.h>
 
@@ -919,9 +920,15 @@ static int drv_trcbk(so_drv* d, const so_task* t)
     const int width = t->up - t->lw + 3;
     if (width < 0) return NEVSEL32;
     const int m = t->a_right - t->a_left;
-    if (m < 8) { d->unsupported = 1; return NEVSEL32; }
     int32_t score = 0;
     int room = d->cap > d->n ? d->cap - d->n : 0;
+    if (m < 8) {
+        /* scalar exact-ILD kernel (src/fwd2s1.cc:1676): needs the intron tables */
+        int c = so_trcbk_ng(d->p, t, &score, d->skl + 2 * (d->n < d->cap ? d->n : d->cap), room);
+        if (c < 0) { d->unsupported = 1; return NEVSEL32; }
+        d->n += c;
+        return score;
+    }
     int cnt = so_forward_wip(d->p, t, &score, d->skl + 2 * (d->n < d->cap ? d->n : d->cap), room, 0);
     if (cnt < 0) { d->unsupported = 1; return NEVSEL32; }
     d->n += cnt;

@@ -43,6 +43,11 @@ typedef struct {
     int32_t simdim;     /* Simmtx::dim */
     const int32_t* simmtx;  /* dim x dim, row = query code, col = genome code */
     int32_t gappen1;    /* PwdB::GapPenalty(1) */
+    /* inputs of the scalar exact-ILD kernel only (so_trcbk_ng); may be 0 / NULL otherwise */
+    int32_t codonk1;        /* PwdB::codonk1 (GapExtPen: LongGEP beyond it) */
+    int32_t n_penalty;      /* entries of penalty[] */
+    const int16_t* penalty; /* IntronPenalty::Penalty(n), n in [0, n_penalty)  src/codepot.h:243-248 */
+    const int16_t* sig53tab;/* Exinon::sig53tab[0][0..543]                      src/codepot.cc:281-285 */
 } so_params;
 
 typedef struct {
@@ -53,6 +58,8 @@ typedef struct {
     int32_t a_left, a_right, b_left, b_right;   /* Seq::left / right */
     int32_t a_exgl, a_exgr, b_exgl, b_exgr;     /* INEX end-gap flags */
     int32_t lw, up;         /* WINDOW (width = up - lw + 3) */
+    const uint16_t* int53;  /* scalar kernel only: INT53 nibbles by column n in [0, blen + 1]:
+                               dinc5 | dinc3 << 4 | cano5 << 8 | cano3 << 12 (src/codepot.h:49-54) */
 } so_task;
 
 /* forwardS1_wip: returns number of SKL corners written to skl[2*i], skl[2*i+1]
@@ -69,6 +76,13 @@ int so_scoreonly_wip(const so_params* p, const so_task* t, int32_t* score);
  * b_right as the reference leaves them in the Seq objects. */
 int so_hirschberg_wip(const so_params* p, const so_task* t, int n_im,
                       int32_t* score, int32_t* cpos, int32_t* ranges);
+
+/* Aln2s1::trcbkalignS_ng on its scalar branch (src/fwd2s1.cc:1667-1710): forwardS_ng
+ * (217-444) with initS_ng / lastS_ng (141-215), Vmf::traceback (src/vmf.cc:125-140) and the
+ * end-point adjustment; exact intron scoring SpJunc::spjscr (src/codepot.cc:74-77).  This is
+ * what the reference runs for blocks with fewer than 8 query rows.  Returns the number of
+ * corners, -1 allocation failure, -3 missing tables. */
+int so_trcbk_ng(const so_params* p, const so_task* t, int32_t* score, int32_t* skl, int cap);
 
 /* Aln2s1::lspS_ng driver (trace-back vs multi-intermediate Hirschberg dispatch,
  * src/fwd2s1.cc:1801-1897) */

@@ -129,6 +129,7 @@ def gen(name: str):
         out["prm_" + k] = np.asarray(v)
     probs = []
     udh = "udh" in name
+    ng_tables = None
 
     def add(g, q, comrev=False, tag="", **setkw):
         t = ref.task(g, q, comrev)
@@ -151,6 +152,14 @@ def gen(name: str):
         out[pre + "skl"] = r["skl"].astype(np.int32)
         out[pre + "score_only"] = np.int32(r1["score"])
         out[pre + "tag"] = np.array(tag)
+        # scalar exact-ILD kernel (Aln2s1::trcbkalignS_ng, scalar branch) and its extra inputs
+        rn = t.scalar(lw, up)
+        out[pre + "int53"] = t.export_int53()
+        out[pre + "ng_score"] = np.int32(rn["score"])
+        out[pre + "ng_skl"] = rn["skl"].astype(np.int32)
+        nonlocal ng_tables
+        if ng_tables is None or len(ng_tables["penalty"]) < ex["blen"] + 2:
+            ng_tables = t.export_ng_tables(max(4096, ex["blen"] + 2))
         if udh:
             # the whole driver (Aln2s1::lspS_ng) and the Hirschberg pass alone
             rl = t.lsp(lw, up)
@@ -192,6 +201,10 @@ def gen(name: str):
     g, q, _ = synth.plant_gene(rng, qlen_range=(1700, 1900), n_exons=3, flank=(40, 80))
     add(g, q, tag="rebase")
     out["n"] = np.int32(len(probs))
+    # IntronPenalty::Penalty(n) table, Exinon::sig53tab, alprm2.Z > 0 (inputs of the scalar kernel)
+    out["prm_penalty"] = ng_tables["penalty"]
+    out["prm_sig53tab"] = ng_tables["sig53tab"]
+    out["prm_intpot"] = np.int32(ng_tables["intpot"])
     path = HERE / f"{name}.npz"
     np.savez_compressed(path, **out)
     print(name, "problems:", len(probs), "->", path, f"{path.stat().st_size / 1024:.0f} KiB")

@@ -20,6 +20,8 @@ class SoParams(C.Structure):
         ("quant_len", C.c_int32 * MAXQ), ("quant_pen", C.c_int32 * MAXQ),
         ("avmch", C.c_int32), ("local", C.c_int32), ("spj", C.c_int32),
         ("simdim", C.c_int32), ("simmtx", C.c_void_p), ("gappen1", C.c_int32),
+        ("codonk1", C.c_int32), ("n_penalty", C.c_int32), ("penalty", C.c_void_p),
+        ("sig53tab", C.c_void_p),
     ]
 
 
@@ -28,7 +30,7 @@ class SoTask(C.Structure):
         ("a", C.c_void_p), ("b", C.c_void_p), ("sig5", C.c_void_p), ("sig3", C.c_void_p),
         ("a_left", C.c_int32), ("a_right", C.c_int32), ("b_left", C.c_int32), ("b_right", C.c_int32),
         ("a_exgl", C.c_int32), ("a_exgr", C.c_int32), ("b_exgl", C.c_int32), ("b_exgr", C.c_int32),
-        ("lw", C.c_int32), ("up", C.c_int32),
+        ("lw", C.c_int32), ("up", C.c_int32), ("int53", C.c_void_p),
     ]
 
 
@@ -52,6 +54,7 @@ def lib():
                                            C.c_void_p, C.c_void_p]
         _lib.so_lsp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_void_p]
+        _lib.so_trcbk_ng.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _lib.so_forward_h1_wip.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         _lib.so_hirschberg_h1_wip.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.so_lsp_h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -68,7 +71,7 @@ def make_params(p: dict):
     sp.ipen = p["GapWI"]
     sp.llmt = p["llmt"]
     sp.nquant = p["nquant"]
-    for j in range(p["nquant"]):
+    for j in range(min(p["nquant"], len(p["quant_len"]))):
         sp.quant_len[j] = int(p["quant_len"][j])
         sp.quant_pen[j] = int(p["quant_pen"][j])
     sp.avmch = p["avmch"]
@@ -78,7 +81,14 @@ def make_params(p: dict):
     sim = np.ascontiguousarray(p["simmtx"], np.int32)
     sp.simmtx = sim.ctypes.data
     sp.gappen1 = p["GapPenalty1"]
-    sp._keep = sim
+    sp._keep = [sim]
+    # inputs of the scalar exact-ILD kernel (present in fixtures that carry them)
+    sp.codonk1 = int(p.get("codonk1", 2 ** 31 - 1))
+    if "penalty" in p and "sig53tab" in p:
+        pen = np.ascontiguousarray(p["penalty"], np.int16)
+        tab = np.ascontiguousarray(p["sig53tab"], np.int16)
+        sp.n_penalty, sp.penalty, sp.sig53tab = len(pen), pen.ctypes.data, tab.ctypes.data
+        sp._keep += [pen, tab]
     return sp
 
 
@@ -97,7 +107,11 @@ def make_task(t: dict):
     for k in ("a_left", "a_right", "b_left", "b_right", "a_exgl", "a_exgr",
               "b_exgl", "b_exgr", "lw", "up"):
         setattr(st, k, int(t[k]))
-    st._keep = (a, b, s5, s3)
+    st._keep = [a, b, s5, s3]
+    if t.get("int53") is not None:
+        i53 = np.ascontiguousarray(t["int53"], np.uint16)
+        st.int53 = i53.ctypes.data
+        st._keep.append(i53)
     return st
 
 
@@ -111,6 +125,17 @@ def forward_wip(p: dict, t: dict, cap: int = 1 << 16):
     if n < 0:
         raise RuntimeError(f"so_forward_wip failed: {n}")
     return {"score": score.value, "skl": skl[:n].copy(), "cells": cells.value}
+
+
+def trcbk_ng(p: dict, t: dict, cap: int = 1 << 16):
+    """scalar kernel (Aln2s1::trcbkalignS_ng's scalar branch): score + corners"""
+    sp, st = make_params(p), make_task(t)
+    score = C.c_int32(0)
+    skl = np.zeros((cap, 2), np.int32)
+    n = lib().so_trcbk_ng(C.byref(sp), C.byref(st), C.byref(score), skl.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError(f"so_trcbk_ng failed: {n}")
+    return {"score": score.value, "skl": skl[:n].copy()}
 
 
 def scoreonly_wip(p: dict, t: dict):

@@ -82,6 +82,9 @@ class Reference:
                                         C.c_int, C.c_void_p]
         L.ref_task_stripe31.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ref_get_params.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.ref_task_export_int53.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_task_export_ng_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_task_scalar.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         self.tmp = tempfile.TemporaryDirectory(prefix="spaln_ref_")
         g = os.path.join(self.tmp.name, "g0.fa")
         q = os.path.join(self.tmp.name, "q0.fa")
@@ -217,6 +220,31 @@ class RefTask:
         secs = C.c_double(0)
         skl = np.zeros((cap, 2), np.int32)
         n = self.lib.ref_task_lsp_p(self.h, lw, up, C.byref(score), skl.ctypes.data, cap, C.byref(secs))
+        return {"score": score.value, "skl": skl[:n].copy(), "seconds": secs.value}
+
+    def export_int53(self):
+        """INT53 nibbles per column (dinc5 | dinc3 << 4 | cano5 << 8 | cano3 << 12)"""
+        out = np.zeros(self.info()["blen"] + 2, np.uint16)
+        self.lib.ref_task_export_int53(self.h, out.ctypes.data)
+        return out
+
+    def export_ng_tables(self, n_pen: int):
+        """sig53tab (544 shorts) and IntronPenalty::Penalty(0 .. n_pen - 1)"""
+        tab = np.zeros(544, np.int16)
+        pen = np.zeros(n_pen, np.int16)
+        misc = np.zeros(4, np.int32)
+        rc = self.lib.ref_task_export_ng_tables(self.h, tab.ctypes.data, pen.ctypes.data, n_pen,
+                                                misc.ctypes.data)
+        if rc:
+            raise RuntimeError("no intron tables in this set-up")
+        return {"sig53tab": tab, "penalty": pen, "intpot": int(misc[0])}
+
+    def scalar(self, lw, up, cap=1 << 16):
+        """Aln2s1::trcbkalignS_ng forced onto its scalar branch (forwardS_ng + Vmf), raw Mfile corners"""
+        score = C.c_int(0)
+        secs = C.c_double(0)
+        skl = np.zeros((cap, 2), np.int32)
+        n = self.lib.ref_task_scalar(self.h, lw, up, C.byref(score), skl.ctypes.data, cap, C.byref(secs))
         return {"score": score.value, "skl": skl[:n].copy(), "seconds": secs.value}
 
     def inject(self, sig5, sig3):

@@ -18,6 +18,18 @@ def test_oracle_matches_reference_golden(oracle, name):
         assert s["score"] == pb["score_only"], (name, i, pb["tag"])
 
 
+@pytest.mark.parametrize("name", golden_io.GOLDEN_NAMES + golden_io.DAGP_NAMES + golden_io.UDH_NAMES)
+def test_oracle_scalar_kernel_matches_reference_golden(oracle, name):
+    """Aln2s1::trcbkalignS_ng on its scalar branch (forwardS_ng + Vmf, exact intron scoring):
+    the kernel the reference uses for blocks with fewer than 8 query rows"""
+    prm, probs = golden_io.load(name)
+    assert "penalty" in prm and "sig53tab" in prm and int(prm["intpot"]) == 0
+    for i, pb in enumerate(probs):
+        o = oracle.trcbk_ng(prm, pb)
+        assert o["score"] == pb["ng_score"], (name, i, pb["tag"])
+        assert np.array_equal(o["skl"], pb["ng_skl"]), (name, i, pb["tag"])
+
+
 def test_golden_covers_edge_cases():
     prm, probs = golden_io.load("dna_A2_global")
     tags = {p["tag"] for p in probs}
@@ -60,9 +72,8 @@ def test_oracle_udh_matches_reference_golden(oracle, name):
             assert cpos_equal(o["cpos"], pb["udh_cpos"]), (name, i, pb["tag"])
             n_udh += 1
         o = oracle.lsp(prm, pb)
-        if o["unsupported"]:        # < 8 query rows: scalar kernel of the reference, not restated
-            continue
+        assert not o["unsupported"], (name, i, pb["tag"])   # blocks with < 8 rows: scalar kernel
         assert o["score"] == pb["lsp_score"], (name, i, pb["tag"])
         assert np.array_equal(o["skl"], pb["lsp_skl"]), (name, i, pb["tag"])
         n_lsp += 1
-    assert n_udh >= 20 and n_lsp >= 20
+    assert n_udh >= 20 and n_lsp == len(probs)
