@@ -55,9 +55,14 @@ enum {
 enum {                          /* gspaln_task.kind */
     GSPALN_FORWARD_WIP = 0,     /* score + trace-back corners */
     GSPALN_SCOREONLY_WIP = 1,   /* score only */
-    GSPALN_HIRSCHBERG_WIP = 2   /* SimdAln2s1::hirschbergS1_wip(Dim10* cpos, n_imd)
+    GSPALN_HIRSCHBERG_WIP = 2,  /* SimdAln2s1::hirschbergS1_wip(Dim10* cpos, n_imd)
                                    (src/fwd2s1_wip_simd.h:476-864): score, crossing records
                                    and the narrowed sequence ranges; global / semi-global only */
+    GSPALN_FORWARD_NG = 3       /* Aln2s1::trcbkalignS_ng on its scalar branch: forwardS_ng
+                                   (src/fwd2s1.cc:217-444) + Vmf::traceback + end adjustment
+                                   (1667-1710), exact intron scoring.  The reference runs it for
+                                   blocks with fewer than 8 query rows.  Needs
+                                   gspaln_set_ng_tables() and gspaln_task.int53. */
 };
 
 enum {                          /* gspaln_result.status */
@@ -65,7 +70,9 @@ enum {                          /* gspaln_result.status */
     GSPALN_ST_SKL_OVERFLOW = 1, /* more corners than skl_cap: n_skl is the needed count */
     GSPALN_ST_BAD_TRACE = 2,    /* reference would have called fatal("Unexpected dir") */
     GSPALN_ST_UNSUPPORTED = 3,  /* needs a kernel that is not on the device yet */
-    GSPALN_ST_INTERNAL = 4      /* device-side scheduling guard tripped (a bug: please report) */
+    GSPALN_ST_INTERNAL = 4,     /* device-side scheduling guard tripped (a bug: please report) */
+    GSPALN_ST_VMF_OVERFLOW = 5  /* GSPALN_FORWARD_NG: more path records than the workspace holds
+                                   (the reference's fatal("Too many Vmf records")) */
 };
 
 /* frozen scoring parameters (reference globals -> one POD) */
@@ -102,6 +109,9 @@ typedef struct gspaln_task {
     int32_t lw, up;             /* WINDOW (src/cmn.h:133); width = up - lw + 3 */
     int32_t skl_cap;            /* capacity of result.skl in corners */
     int32_t n_imd;              /* GSPALN_HIRSCHBERG_WIP: number of intermediate rows (>= 1) */
+    const uint16_t* int53;      /* GSPALN_FORWARD_NG (and gspaln_lsp blocks with < 8 rows), else may be
+                                   NULL: Exinon::int53[n] by column n (src/codepot.h:49-54) as
+                                   dinc5 | dinc3 << 4 | cano5 << 8 | cano3 << 12 */
 } gspaln_task;
 
 typedef struct gspaln_result {
@@ -133,6 +143,15 @@ typedef struct gspaln_timing {
 int  gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device);
 void gspaln_destroy(gspaln_ctx* ctx);
 
+/* Tables of the exact intron scoring (SpJunc::spjscr, src/codepot.cc:74-77) used by
+ * GSPALN_FORWARD_NG: sig53tab = Exinon::sig53tab[0][0 .. 543] (src/codepot.cc:281-285),
+ * penalty[len] = IntronPenalty::Penalty(len) for len in [0, n_penalty) (src/codepot.h:243-248;
+ * evaluated by the caller so that the float tail of the distribution is the reference's own
+ * libm result), codonk1 = PwdB::codonk1 (GapExtPen).  alprm2.Z must be 0 (no intron potential).
+ * Problems whose genomic range is n_penalty or longer are refused. */
+int  gspaln_set_ng_tables(gspaln_ctx* ctx, const int16_t* sig53tab, const int16_t* penalty,
+                          int32_t n_penalty, int32_t codonk1);
+
 /* blocking: pack + H2D + kernels + D2H.  results[i].skl must point to
  * tasks[i].skl_cap * 2 int32 (may be NULL for score-only tasks). */
 int  gspaln_submit(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
@@ -152,9 +171,9 @@ int  gspaln_download(gspaln_ctx* ctx, gspaln_result* results);
  * Hirschberg method with the reference's own space estimate, runs the Hirschberg passes and
  * the block re-alignments of mimd_postwork / rcsv_postwork (src/fwd2s1.cc:1714-1799) as
  * further device batches, and returns the corner list in the order the reference writes
- * it to its Mfile.  Pieces that need a kernel which is not on the device yet (fewer than 8
- * query rows -> the reference's scalar kernel; local-mode Hirschberg) set
- * GSPALN_ST_UNSUPPORTED on that problem. */
+ * it to its Mfile.  Blocks with fewer than 8 query rows go to the scalar kernel
+ * (GSPALN_FORWARD_NG) like in the reference; without gspaln_set_ng_tables() / task.int53 they
+ * set GSPALN_ST_UNSUPPORTED on that problem, as does the double-affine Hirschberg route. */
 typedef struct gspaln_lsp_opts {
     int32_t max_vmf_space;      /* MaxVmfSpace (-V; default 32 MiB, src/vmf.h:26) */
     int32_t sh;                 /* alprm.sh: band shoulder for the block re-alignments */

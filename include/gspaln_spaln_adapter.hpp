@@ -33,6 +33,7 @@ class SpalnEngine {
         const Seq* a = seqs[0];
         const Seq* b = seqs[1];
         t.kind = kind;
+        t.int53 = 0;    // only the scalar kernel (GSPALN_FORWARD_NG) reads the INT53 array
         t.a = a->at(0);
         t.b = b->at(0);
         t.a_left = a->left; t.a_right = a->right;

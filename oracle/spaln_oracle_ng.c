@@ -55,7 +55,8 @@ int so_trcbk_ng(const so_params* p, const so_task* t, int32_t* score, int32_t* s
     const int width = t->up - t->lw + 3;
     *score = NEVSEL32;
     if (width < 0) return 0;
-    if (p->spj && (!p->penalty || !p->sig53tab || !t->int53 || p->n_penalty < 1)) return -3;
+    if (p->spj && (!p->penalty || !p->sig53tab || !t->int53 || t->b_right - t->b_left >= p->n_penalty))
+        return -3;          /* no tables, or an intron could be longer than the penalty table */
     const int dagp = p->noll == 3, spj = p->spj;
     const int nod = 2 * p->noll - 1;
     const int gop_k[3] = { 0, p->gop, p->lgop };            /* PwdB::GOP, src/aln2.cc:111 */

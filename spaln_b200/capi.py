@@ -22,12 +22,13 @@ MAXDIM = 32
 FORWARD_WIP = 0
 SCOREONLY_WIP = 1
 HIRSCHBERG_WIP = 2
+FORWARD_NG = 3          # scalar exact-ILD kernel (Aln2s1::forwardS_ng + Vmf trace-back)
 END_OF_ULK = 2 ** 31 - 1 - 2
 
 EXPORTS = [
     "gspaln_create", "gspaln_destroy", "gspaln_submit", "gspaln_upload", "gspaln_run",
     "gspaln_download", "gspaln_get_timing", "gspaln_last_error", "gspaln_device_count",
-    "gspaln_version", "gspaln_task_cells", "gspaln_lsp",
+    "gspaln_version", "gspaln_task_cells", "gspaln_lsp", "gspaln_set_ng_tables",
     "gspaln_h_create", "gspaln_h_destroy", "gspaln_h_submit", "gspaln_h_upload", "gspaln_h_run",
     "gspaln_h_download", "gspaln_h_get_timing", "gspaln_h_last_error", "gspaln_h_task_cells",
     "gspaln_h_lsp",
@@ -53,6 +54,7 @@ class GspalnTask(C.Structure):
         ("a_left", C.c_int32), ("a_right", C.c_int32), ("b_left", C.c_int32), ("b_right", C.c_int32),
         ("a_exgl", C.c_int32), ("a_exgr", C.c_int32), ("b_exgl", C.c_int32), ("b_exgr", C.c_int32),
         ("lw", C.c_int32), ("up", C.c_int32), ("skl_cap", C.c_int32), ("n_imd", C.c_int32),
+        ("int53", C.c_void_p),
     ]
 
 
@@ -132,6 +134,7 @@ def load():
     lib.gspaln_create.restype = C.c_int
     lib.gspaln_destroy.argtypes = [C.c_void_p]
     lib.gspaln_destroy.restype = None
+    lib.gspaln_set_ng_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
     lib.gspaln_submit.argtypes = [C.c_void_p, C.POINTER(GspalnTask), C.c_int, C.POINTER(GspalnResult)]
     lib.gspaln_upload.argtypes = [C.c_void_p, C.POINTER(GspalnTask), C.c_int]
     lib.gspaln_run.argtypes = [C.c_void_p]

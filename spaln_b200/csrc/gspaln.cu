@@ -8,6 +8,7 @@
 #include "../../include/gspaln.h"
 #include "gspaln_kernels.cuh"
 #include "gspaln_udh.cuh"
+#include "gspaln_ng.cuh"
 #include "gspaln_host.hpp"
 
 #include <algorithm>
@@ -53,6 +54,14 @@ struct gspaln_ctx {
     DevBuf<int> d_udh;              // per-warp UDH workspace (link band + intermediates)
     DevBuf<int> d_cpos;
     DevBuf<DevUdhOut> d_ures;
+    // scalar exact-ILD kernel (GSPALN_FORWARD_NG)
+    DevParams hP;                   // host copy of the device parameter block
+    DevBuf<short> d_ngtab;          // sig53tab[544] | Penalty(0 .. n_pen - 1)
+    DevBuf<unsigned char> d_ngwork; // per-thread workspaces
+    int n_pen = 0;
+    bool ng_ready = false;
+    int n_ng = 0, grid_run_ng = 0, ng_rec_cap = 0;
+    size_t ng_slab = 0, ng_width = 0;
     PinBuf<DevTask> h_tasks;
     PinBuf<int> h_order;
     PinBuf<unsigned char> h_apool;
@@ -189,6 +198,8 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
         P.mean[j] = (short) prm->quant_pen[j];
     }
     P.avmch = prm->avmch; P.local = prm->local ? 1 : 0; P.spj = prm->spj ? 1 : 0;
+    P.lgop = prm->lgop; P.lgep = prm->lgep; P.noll = prm->noll; P.llmt = prm->llmt;
+    P.codonk1 = INT_MAX;            // set by gspaln_set_ng_tables
     P.simdim = prm->simdim; P.gappen1 = prm->gappen1; P.gop = prm->gop; P.gep = prm->gep;
     // residue code -> table index.  The four unambiguous nucleotides of the
     // reference's DNA alphabet (A=2, C=3, G=5, T=9) go first so that their 16
@@ -220,6 +231,7 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
     }
     P.pen_cap = cap;
     ctx->pen_cap = cap;
+    ctx->hP = P;
     ctx->smem_bytes = sizeof(RingEntry) * RING * CTA_THREADS + sizeof(int2) * (size_t) (cap + 1);
     if (ctx->smem_bytes > 108 * 1024) {     // two CTAs per SM must fit
         gspaln_destroy(ctx);
@@ -270,6 +282,24 @@ void gspaln_destroy(gspaln_ctx* ctx)
     delete ctx;
 }
 
+int gspaln_set_ng_tables(gspaln_ctx* ctx, const int16_t* sig53tab, const int16_t* penalty,
+                         int32_t n_penalty, int32_t codonk1)
+{
+    if (!ctx || !sig53tab || !penalty || n_penalty < 1) return GSPALN_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->d_ngtab.reserve(544 + (size_t) n_penalty) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, GSPALN_ENOMEM, "device allocation");
+    }
+    CK(cudaMemcpy(ctx->d_ngtab.p, sig53tab, 544 * sizeof(short), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_ngtab.p + 544, penalty, (size_t) n_penalty * sizeof(short), cudaMemcpyHostToDevice));
+    ctx->hP.codonk1 = codonk1;
+    CK(cudaMemcpy(ctx->d_prm.p, &ctx->hP, sizeof(DevParams), cudaMemcpyHostToDevice));
+    ctx->n_pen = n_penalty;
+    ctx->ng_ready = true;
+    return GSPALN_OK;
+}
+
 // ---- planning: validation, longest-first order, pool offsets (assigned along that order so
 // that any contiguous range of the order is contiguous in every pool), workspaces, grids
 static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
@@ -281,8 +311,11 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
     for (int i = 0; i < n; ++i) {
         const gspaln_task& t = tasks[i];
         if (t.a_right < t.a_left || t.b_right < t.b_left || t.up - t.lw + 3 < 0 ||
-            (t.kind != GSPALN_FORWARD_WIP && t.kind != GSPALN_SCOREONLY_WIP && t.kind != GSPALN_HIRSCHBERG_WIP) ||
+            (t.kind != GSPALN_FORWARD_WIP && t.kind != GSPALN_SCOREONLY_WIP && t.kind != GSPALN_HIRSCHBERG_WIP &&
+             t.kind != GSPALN_FORWARD_NG) ||
             (t.kind == GSPALN_HIRSCHBERG_WIP && (t.n_imd < 1 || t.a_right - t.a_left < 2 || ctx->prm.noll != 2)) ||
+            (t.kind == GSPALN_FORWARD_NG && ctx->prm.spj &&
+             (!ctx->ng_ready || !t.int53 || t.b_right - t.b_left >= ctx->n_pen)) ||
             !t.a || !t.b || (ctx->prm.spj && (!t.sig5 || !t.sig3))) {
             char msg[256];
             snprintf(msg, sizeof(msg), "bad task %d: kind %d a (%d, %d] b (%d, %d] band [%d, %d] n_imd %d",
@@ -299,7 +332,8 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
                      [&](int x, int y) { return ctx->cells[x] > ctx->cells[y]; });
     size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, skl_elems = 0;
     size_t udh_slab = 0, cpos_elems = 0;
-    int n_trace = 0, n_score = 0, n_udh = 0;
+    int n_trace = 0, n_score = 0, n_udh = 0, n_ng = 0;
+    size_t ng_width = 0, ng_rec = 0;
     for (int k = 0; k < n; ++k) {
         const int i = ctx->h_order.p[k];
         const gspaln_task& t = tasks[i];
@@ -308,7 +342,7 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         d.a_left = t.a_left; d.a_right = t.a_right; d.b_left = t.b_left; d.b_right = t.b_right;
         d.lw = t.lw; d.up = t.up;
         d.flags = (t.a_exgl ? 1 : 0) | (t.a_exgr ? 2 : 0) | (t.b_exgl ? 4 : 0) | (t.b_exgr ? 8 : 0);
-        d.skl_cap = t.kind == GSPALN_FORWARD_WIP ? std::max(0, t.skl_cap) : 0;
+        d.skl_cap = (t.kind == GSPALN_FORWARD_WIP || t.kind == GSPALN_FORWARD_NG) ? std::max(0, t.skl_cap) : 0;
         d.pad0 = 0;
         const int mw = t.a_right - t.a_left, nw = t.b_right - t.b_left;
         const int width = t.up - t.lw + 3;
@@ -324,6 +358,12 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             trace_slab = std::max(trace_slab, align_up(nstrips * (size_t) (width + TRACE_PAD) * NELEM + 64, 256));
             skl_elems += (size_t) d.skl_cap;
             ++n_trace;
+        } else if (t.kind == GSPALN_FORWARD_NG) {
+            // path records: at most one per cell plus two per gap state at acceptor columns
+            ng_width = std::max(ng_width, (size_t) width);
+            ng_rec = std::max(ng_rec, (size_t) std::min<int64_t>(3 * ctx->cells[i] + 2 * width + 64, INT_MAX / 4));
+            skl_elems += (size_t) d.skl_cap;
+            ++n_ng;
         } else if (t.kind == GSPALN_HIRSCHBERG_WIP) {
             d.pad0 = t.n_imd;
             d.pad1 = (long long) cpos_elems;
@@ -372,8 +412,23 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         }
         ctx->grid_run_trace = gt;
         ctx->grid_run_score = gs;
+        // scalar kernel: one thread per problem, workspace = band rows + direction bytes + records
+        ctx->grid_run_ng = 0;
+        if (n_ng) {
+            const size_t slab = align_up(3 * ng_width * sizeof(NgRvp) + align_up(ng_width, 16) + 12 * ng_rec, 16);
+            int g = std::min((n_ng + NG_THREADS - 1) / NG_THREADS, 4 * ctx->sm_count);
+            cudaMemGetInfo(&free_b, &total_b);
+            const size_t room = (size_t) (0.5 * (double) (free_b + ctx->d_ngwork.cap));
+            while (g > 1 && (size_t) g * NG_THREADS * slab > room) g = g * 3 / 4;
+            if (ctx->d_ngwork.reserve((size_t) g * NG_THREADS * slab + 64) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(ctx, GSPALN_ENOMEM, "device scalar-kernel workspace allocation");
+            }
+            ctx->grid_run_ng = g;
+            ctx->ng_slab = slab; ctx->ng_width = ng_width; ctx->ng_rec_cap = (int) ng_rec;
+        }
     }
-    ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score; ctx->n_udh = n_udh;
+    ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score; ctx->n_udh = n_udh; ctx->n_ng = n_ng;
     ctx->udh_slab = udh_slab; ctx->cpos_elems = cpos_elems;
     ctx->a_bytes = a_bytes; ctx->c_elems = c_elems; ctx->band_slab = band_slab;
     ctx->trace_slab = trace_slab; ctx->skl_elems = skl_elems;
@@ -407,7 +462,11 @@ static void pack_range(gspaln_ctx* ctx, const gspaln_task* tasks, int lo, int hi
                 ci.sig5 = spj ? t.sig5[c] : 0;
                 ci.sig3 = spj ? t.sig3[c] : 0;
                 ci.code = j > 0 ? ctx->perm[t.b[c - 1] & 31] : 0;
-                ci.pad[0] = ci.pad[1] = ci.pad[2] = 0;
+                // INT53 nibbles ride in the padding: [0] dinc5 | dinc3 << 4, [1] cano5 | cano3 << 4
+                const unsigned i53 = t.int53 ? t.int53[c] : 0u;
+                ci.pad[0] = (unsigned char) (i53 & 0xffu);
+                ci.pad[1] = (unsigned char) (i53 >> 8);
+                ci.pad[2] = 0;
                 col[j] = ci;
             }
         }
@@ -474,6 +533,13 @@ static int launch_range(gspaln_ctx* ctx, int lo, int hi, int slot, int& launches
             ctx->d_udh.p, (long long) ctx->udh_slab, ctx->d_cpos.p, ctx->d_ures.p, ready);
         ++launches;
     }
+    if (ctx->n_ng) {
+        dp_ng_kernel<<<ctx->grid_run_ng, NG_THREADS, 0, ctx->stream>>>(
+            ctx->d_prm.p, ctx->d_ngtab.p, ctx->n_pen, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 8,
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_ngwork.p, (long long) ctx->ng_slab,
+            (long long) ctx->ng_width, ctx->ng_rec_cap, ctx->d_skl.p, ctx->d_res.p, ready);
+        ++launches;
+    }
     CK(cudaGetLastError());
     return GSPALN_OK;
 }
@@ -508,7 +574,7 @@ int gspaln_run(gspaln_ctx* ctx)
     int launches = 0;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (n > 0) {
-        CK(cudaMemsetAsync(ctx->d_ticket.p, 0, 3 * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_ticket.p, 0, 16 * sizeof(int), ctx->stream));
         int rc = launch_range(ctx, 0, n, 0, launches);
         if (rc != GSPALN_OK) return rc;
     }
@@ -674,6 +740,11 @@ struct LspTraitsS {
     static float coef_c(const gspaln_params& P) { return (float) ((P.noll + 1) * 4); }
     static bool is_local(const gspaln_params& P) { return P.local != 0; }
     static bool udh_ok(const gspaln_params& P) { return P.noll == 2; }   // no double-affine Hirschberg pass yet
+    // blocks with fewer than 8 query rows: the scalar kernel, if its tables are there
+    static bool scalar_ok(const gspaln_ctx* ctx, const gspaln_task& base, const LspGeo& g)
+    {
+        return !ctx->prm.spj || (ctx->ng_ready && base.int53 && g.b_right - g.b_left < ctx->n_pen);
+    }
     static int trivial_score(const gspaln_params& P, const LspGeo& g, int m, int nn)
     {
         if (m) return (g.a_exgl || g.a_exgr) ? P.gep : (P.gop + m * P.gep);
@@ -712,7 +783,8 @@ struct LspTraitsS {
         t.a_exgl = g.a_exgl; t.a_exgr = g.a_exgr; t.b_exgl = g.b_exgl; t.b_exgr = g.b_exgr;
         t.lw = g.lw; t.up = g.up;
         t.n_imd = n_imd;
-        t.skl_cap = kind == GSPALN_FORWARD_WIP ? (g.a_right - g.a_left) + (g.b_right - g.b_left) + 8 : 0;
+        t.skl_cap = (kind == GSPALN_FORWARD_WIP || kind == GSPALN_FORWARD_NG)
+                        ? (g.a_right - g.a_left) + (g.b_right - g.b_left) + 8 : 0;
         return t;
     }
     static int submit(gspaln_ctx* ctx, const gspaln_task* t, int n, gspaln_result* r) { return gspaln_submit(ctx, t, n, r); }

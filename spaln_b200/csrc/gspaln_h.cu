@@ -646,6 +646,8 @@ struct LspTraitsH {
     static float coef_c(const gspaln_h_params&) { return 12.f; }     // (Noll + 1) * sizeof(int), Noll == 2
     static bool is_local(const gspaln_h_params& P) { return (P.lcl & 16) != 0; }
     static bool udh_ok(const gspaln_h_params&) { return true; }
+    // no scalar forwardH_ng on the device: blocks with fewer than 8 rows stay unsupported
+    static bool scalar_ok(const gspaln_h_ctx*, const gspaln_h_task&, const LspGeo&) { return false; }
     static int trivial_score(const gspaln_h_params& P, const LspGeo& g, int m, int nn)
     {
         auto ext = [&](int i) { return i > P.codonk1 ? P.lgep : P.gep; };

@@ -59,6 +59,7 @@ struct DevParams {
     int quant[MAXQ], mean[MAXQ];
     int avmch, local, spj, simdim, gappen1, gop, gep;
     int pen_cap;                // pen table has pen_cap + 1 entries
+    int lgop, lgep, noll, llmt, codonk1;    // raw values for the scalar kernel (gspaln_ng.cuh)
     int mtxT[32 * MTX_LD];      // [genome index][query index] (remapped codes); row/col ZROW == 0
     unsigned char perm[32];     // residue code -> table index
 };

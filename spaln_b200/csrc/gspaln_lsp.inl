@@ -35,6 +35,7 @@ struct LspItem {
 
 struct LspFwd {                 // one trcbkalignS_ng call
     int root;
+    int kind = GSPALN_FORWARD_WIP;  // GSPALN_FORWARD_NG for blocks with fewer than 8 query rows
     LspGeo g;
     int score = 0;
     std::vector<int2> skl;
@@ -72,12 +73,14 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
     // returns the index of the queued forward task or -1 (nothing to do / unsupported)
     auto queue_trcbk = [&](int item, const LspGeo& g) -> int {
         if (g.up - g.lw + TR::WPAD < 0) return -1;
-        if (g.a_right - g.a_left < 8 || g.b_right < g.b_left || g.a_left < 0 || g.b_left < 0 ||
-            TR::beyond(tasks[items[item].root], g)) {
+        const bool scalar = g.a_right - g.a_left < 8;     // src/fwd2s1.cc:1676, src/fwd2h1.cc:2007
+        if ((scalar && !TR::scalar_ok(ctx, tasks[items[item].root], g)) || g.b_right < g.b_left ||
+            g.a_left < 0 || g.b_left < 0 || TR::beyond(tasks[items[item].root], g)) {
             status[items[item].root] = GSPALN_ST_UNSUPPORTED;
             return -1;
         }
         LspFwd f; f.root = items[item].root; f.g = g;
+        if (scalar) f.kind = GSPALN_FORWARD_NG;
         fwds.push_back(std::move(f));
         LspPiece p; p.kind = 1; p.ref = (int) fwds.size() - 1;
         items[item].pieces.push_back(std::move(p));
@@ -174,7 +177,7 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
         const size_t fwd_first = fwd_done;
         std::vector<std::vector<int>> sklbuf(fwds.size() - fwd_first);
         for (size_t f = fwd_first; f < fwds.size(); ++f) {
-            batch.push_back(TR::make_task(tasks[fwds[f].root], fwds[f].g, GSPALN_FORWARD_WIP, 0));
+            batch.push_back(TR::make_task(tasks[fwds[f].root], fwds[f].g, fwds[f].kind, 0));
             sklbuf[f - fwd_first].assign(2 * (size_t) batch.back().skl_cap, 0);
         }
         bres.resize(batch.size());
@@ -286,7 +289,7 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
             std::vector<gspaln_result> r2;
             std::vector<std::vector<int>> s2(fwds.size() - fwd_done);
             for (size_t f = fwd_done; f < fwds.size(); ++f) {
-                b2.push_back(TR::make_task(tasks[fwds[f].root], fwds[f].g, GSPALN_FORWARD_WIP, 0));
+                b2.push_back(TR::make_task(tasks[fwds[f].root], fwds[f].g, fwds[f].kind, 0));
                 s2[f - fwd_done].assign(2 * (size_t) b2.back().skl_cap, 0);
             }
             r2.resize(b2.size());

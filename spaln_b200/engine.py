@@ -37,11 +37,14 @@ class Problem:
     b_exgr: int = 1
     skl_cap: int = 0        # 0: a_len + b_len + 8
     n_imd: int = 0          # hirschbergS1_wip only: number of intermediate rows
+    int53: np.ndarray = None    # uint16 Exinon::int53[n] nibbles by column (scalar kernel only)
 
     @staticmethod
     def from_export(ex: dict, lw: int, up: int) -> "Problem":
         """ex: tests/ref_harness.py::RefTask.export() layout (arrays start at at(-1))."""
-        return Problem(a=np.ascontiguousarray(ex["a"][1:], np.uint8),
+        return Problem(int53=(np.ascontiguousarray(ex["int53"], np.uint16)
+                              if ex.get("int53") is not None else None),
+                       a=np.ascontiguousarray(ex["a"][1:], np.uint8),
                        b=np.ascontiguousarray(ex["b"][1:], np.uint8),
                        sig5=np.ascontiguousarray(ex["sig5"], np.int16),
                        sig3=np.ascontiguousarray(ex["sig3"], np.int16),
@@ -123,6 +126,18 @@ class Engine:
         self._tasks = None
         self._keep = None
         self._n = 0
+        # tables of the exact intron scoring (scalar kernel), when the parameter set carries them
+        if params.get("penalty") is not None and params.get("sig53tab") is not None:
+            self.set_ng_tables(params["sig53tab"], params["penalty"], int(params.get("codonk1", 2 ** 31 - 1)))
+
+    def set_ng_tables(self, sig53tab, penalty, codonk1):
+        """Exinon::sig53tab (544 shorts), IntronPenalty::Penalty(0 .. n - 1), PwdB::codonk1"""
+        tab = np.ascontiguousarray(sig53tab, np.int16)
+        pen = np.ascontiguousarray(penalty, np.int16)
+        if tab.size != 544:
+            raise ValueError("sig53tab must hold 544 entries")
+        self._check(self.lib.gspaln_set_ng_tables(self._h, tab.ctypes.data, pen.ctypes.data, pen.size,
+                                                  int(codonk1)), "gspaln_set_ng_tables")
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -147,16 +162,22 @@ class Engine:
             s3 = np.ascontiguousarray(p.sig3, np.int16)
             if len(a) < p.a_right or len(b) < p.b_right or len(s5) <= p.b_right or len(s3) <= p.b_right:
                 raise ValueError("problem arrays shorter than the stated ranges")
-            keep.append((a, b, s5, s3))
+            i53 = None
+            if p.int53 is not None:
+                i53 = np.ascontiguousarray(p.int53, np.uint16)
+                if len(i53) <= p.b_right:
+                    raise ValueError("int53 shorter than the stated range")
+            keep.append((a, b, s5, s3, i53))
             t = arr[i]
             t.kind = kind
             t.a, t.b = a.ctypes.data, b.ctypes.data
             t.sig5, t.sig3 = s5.ctypes.data, s3.ctypes.data
+            t.int53 = i53.ctypes.data if i53 is not None else None
             t.a_left, t.a_right, t.b_left, t.b_right = p.a_left, p.a_right, p.b_left, p.b_right
             t.a_exgl, t.a_exgr, t.b_exgl, t.b_exgr = p.a_exgl, p.a_exgr, p.b_exgl, p.b_exgr
             t.lw, t.up = p.lw, p.up
             cap = p.skl_cap or ((p.a_right - p.a_left) + (p.b_right - p.b_left) + 8)
-            t.skl_cap = cap if kind == capi.FORWARD_WIP else 0
+            t.skl_cap = cap if kind in (capi.FORWARD_WIP, capi.FORWARD_NG) else 0
             t.n_imd = int(p.n_imd) if kind == capi.HIRSCHBERG_WIP else 0
         return arr, keep
 
@@ -209,6 +230,11 @@ class Engine:
 
     def scoreonlyS1_wip(self, problems):
         return self.submit(problems, capi.SCOREONLY_WIP)
+
+    def forwardS_ng(self, problems):
+        """Aln2s1::trcbkalignS_ng on its scalar branch (forwardS_ng + Vmf trace-back, exact intron
+        scoring; src/fwd2s1.cc:217-444, 1667-1710): score + corners.  Problems carry int53."""
+        return self.submit(problems, capi.FORWARD_NG)
 
     def hirschbergS1_wip(self, problems):
         """problems carry n_imd; results carry score, ranges and cpos (Dim10 records)"""

@@ -120,6 +120,30 @@ def synthetic_signals(bcodes: np.ndarray, rng, scale: float = 1.0):
     return s5.astype(np.int16), s3.astype(np.int16)
 
 
+def synthetic_int53(bcodes: np.ndarray) -> np.ndarray:
+    """Exinon::int53 as Exinon::intron53_c fills it (src/codepot.cc:437-477) for algmode.any == 0
+    and one orientation: per column n the rolling dinucleotide codes dinc5 = (at(n), at(n+1)),
+    dinc3 = (at(n-2), at(n-1)) (A, C, G, T = 0..3, anything else counts as C, the residue before
+    the sequence too) and the site classes cano5 (GT, GC: 3; AT: 2) and cano3 (AG: 3; AC: 2).
+    Returns uint16 dinc5 | dinc3 << 4 | cano5 << 8 | cano3 << 12 for n in [0, len + 1]
+    (entries the reference leaves unwritten are 0)."""
+    L = len(bcodes)
+    red = np.full(256, 1, np.int64)
+    for code, v in ((2, 0), (3, 1), (5, 2), (9, 3)):
+        red[code] = v
+    c = red[np.asarray(bcodes, np.uint8)]
+    prev = np.concatenate([[1], c[:-1]]) if L else c
+    dinc = ((prev << 2) | c) & 15                   # dinc[i]: residues at(i - 1), at(i)
+    out = np.zeros(L + 2, np.int64)
+    c5 = np.zeros(16, np.int64); c5[[11, 9]] = 3; c5[3] = 2     # GT, GC, AT
+    c3 = np.zeros(16, np.int64); c3[2] = 3; c3[1] = 2           # AG, AC
+    n5 = np.arange(0, L - 1)                        # dinc5[n] = dinc[n + 1]
+    out[n5] |= dinc[n5 + 1] | (c5[dinc[n5 + 1]] << 8)
+    n3 = np.arange(1, L + 1)                        # dinc3[n] = dinc[n - 1]
+    out[n3] |= (dinc[n3 - 1] << 4) | (c3[dinc[n3 - 1]] << 12)
+    return out.astype(np.uint16)
+
+
 def stripe(a_left, a_right, b_left, b_right, sh=100):
     """band window exactly as `stripe()` (src/aln2.cc:156-176), cmode 0"""
     up = b_right - a_right

@@ -159,7 +159,7 @@ def gen(name: str):
         out[pre + "ng_skl"] = rn["skl"].astype(np.int32)
         nonlocal ng_tables
         if ng_tables is None or len(ng_tables["penalty"]) < ex["blen"] + 2:
-            ng_tables = t.export_ng_tables(max(4096, ex["blen"] + 2))
+            ng_tables = t.export_ng_tables(max(16384, ex["blen"] + 2))
         if udh:
             # the whole driver (Aln2s1::lspS_ng) and the Hirschberg pass alone
             rl = t.lsp(lw, up)

@@ -56,7 +56,7 @@ def _synthetic(prm, rng, n, qlen, flank, intron_scale=1.0, flags=None, sub=None)
         f = flags or (1, 1, 1, 1)
         out.append({"a": np.concatenate([[0], a, [0]]).astype(np.uint8),
                     "b": np.concatenate([[0], b, [0]]).astype(np.uint8),
-                    "sig5": s5, "sig3": s3, "a_left": al, "a_right": ar, "b_left": bl,
+                    "sig5": s5, "sig3": s3, "int53": workload.synthetic_int53(b), "a_left": al, "a_right": ar, "b_left": bl,
                     "b_right": br, "a_exgl": f[0], "a_exgr": f[1], "b_exgl": f[2], "b_exgr": f[3],
                     "lw": lw, "up": up})
     return out
@@ -203,6 +203,63 @@ def test_hirschberg_wip_matches_oracle_seeded(oracle, flags, fixture):
 
 
 # ---------------------------------------------------------------------------
+# scalar exact-ILD kernel: Aln2s1::trcbkalignS_ng's scalar branch (forwardS_ng + Vmf)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_io.GOLDEN_NAMES + golden_io.DAGP_NAMES + golden_io.UDH_NAMES)
+def test_scalar_kernel_matches_reference_golden(name):
+    prm, probs = golden_io.load(name)
+    eng = _engine(prm)
+    res = eng.forwardS_ng(_problems(probs))
+    for i, (pb, r) in enumerate(zip(probs, res)):
+        assert r.status == 0, (name, i, pb["tag"], r.status)
+        assert r.score == pb["ng_score"], (name, i, pb["tag"], r.score, pb["ng_score"])
+        assert np.array_equal(r.skl, pb["ng_skl"]), (name, i, pb["tag"])
+    eng.close()
+
+
+@pytest.mark.parametrize("name,flags,sub", [
+    ("dna_A2_global", None, None),
+    ("dna_A2_global", (0, 0, 0, 0), None),
+    ("dna_A2_global", (1, 0, 0, 1), (2, 1, 11, 5)),
+    ("dna_A2_local", None, None),
+    ("dna_A2_local", (1, 1, 0, 0), None),
+    ("dna_A2_dagp", None, None),
+    ("dna_A2_dagp", (0, 0, 0, 0), None),
+    ("dna_A2_tetrapod", None, None),
+])
+def test_scalar_kernel_matches_oracle_seeded(oracle, name, flags, sub):
+    prm, _ = golden_io.load(name)
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(repr(("ng", name, flags, sub)).encode()))
+    probs = _synthetic(prm, rng, 40, (4, 8), (20, 2500), flags=flags, sub=sub)       # what the driver sends
+    probs += _synthetic(prm, rng, 12, (30, 300), (30, 400), flags=flags, sub=sub)    # any size works
+    eng = _engine(prm)
+    res = eng.forwardS_ng(_problems(probs))
+    for i, (pb, r) in enumerate(zip(probs, res)):
+        o = oracle.trcbk_ng(prm, pb)
+        assert r.status == 0, (i, r.status)
+        assert r.score == o["score"], (i, r.score, o["score"])
+        assert np.array_equal(r.skl, o["skl"]), i
+    eng.close()
+
+
+def test_scalar_kernel_needs_its_tables():
+    """without gspaln_set_ng_tables / int53 the kind is refused, and the driver reports
+    GSPALN_ST_UNSUPPORTED for blocks with fewer than 8 query rows"""
+    from spaln_b200 import EngineError
+    prm, probs = golden_io.load("dna_A2_udh")
+    bare = {k: v for k, v in prm.items() if k not in ("penalty", "sig53tab")}
+    eng = _engine(bare)
+    with pytest.raises(EngineError):
+        eng.forwardS_ng(_problems(probs[:2]))
+    tiny = [pb for pb in probs if pb["a_right"] - pb["a_left"] < 8]
+    assert tiny
+    res = eng.lspS_ng(_problems(tiny), max_vmf_space=int(prm["MaxVmfSpace"]), sh=int(prm["sh"]))
+    assert all(r.status == 3 for r in res)
+    eng.close()
+
+
+# ---------------------------------------------------------------------------
 # the whole driver: lspS_ng (trace-back vs UDH dispatch + block re-alignment)
 # ---------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["dna_A2_udh", "dna_A6_udh_recursive", "dna_A2_global", "dna_A2_udh_local"])
@@ -213,18 +270,18 @@ def test_lsp_driver_matches_reference_golden(oracle, name):
                       ubh=int(prm["ubh"]), alg=int(prm["alg"]))
     n_ok = 0
     for i, (pb, r) in enumerate(zip(probs, res)):
-        if r.status == 3:           # a block with < 8 query rows (scalar kernel of the reference)
-            assert oracle.lsp(prm, pb)["unsupported"]
-            continue
+        # blocks with < 8 query rows run on the scalar kernel, like in the reference
         assert r.status == 0, (name, i, pb["tag"])
-        want_score = pb.get("lsp_score", pb["score"])
-        want_skl = pb.get("lsp_skl", pb["skl"])
-        if "lsp_score" not in pb and (pb["a_right"] - pb["a_left"]) < 8:
-            continue
+        if "lsp_score" in pb:
+            want_score, want_skl = pb["lsp_score"], pb["lsp_skl"]
+        elif pb["a_right"] - pb["a_left"] < 8:
+            want_score, want_skl = pb["ng_score"], pb["ng_skl"]
+        else:
+            want_score, want_skl = pb["score"], pb["skl"]
         assert r.score == want_score, (name, i, pb["tag"], r.score, want_score)
         assert np.array_equal(r.skl, want_skl), (name, i, pb["tag"])
         n_ok += 1
-    assert n_ok >= 20
+    assert n_ok == len(probs)
     eng.close()
 
 
@@ -240,9 +297,7 @@ def test_lsp_driver_matches_oracle_seeded(oracle):
         n_udh = 0
         for i, (pb, r) in enumerate(zip(probs, res)):
             o = oracle.lsp(prm, pb, cap=1 << 16, max_vmf_space=vmf)
-            if o["unsupported"]:
-                assert r.status == 3
-                continue
+            assert not o["unsupported"]
             m, n = pb["a_right"] - pb["a_left"], pb["b_right"] - pb["b_left"]
             n_udh += 2.0 * m * (n + m) >= vmf
             assert r.status == 0

@@ -34,7 +34,8 @@ def dna_problem(prm, rng, i):
     lw, up = workload.stripe(al, ar, bl, br, sh)
     f = FLAGS[int(rng.integers(0, len(FLAGS)))] if i % 3 == 0 else (1, 1, 1, 1)
     return {"a": np.concatenate([[0], a, [0]]).astype(np.uint8), "b": np.concatenate([[0], b, [0]]).astype(np.uint8),
-            "sig5": s5, "sig3": s3, "a_left": al, "a_right": ar, "b_left": bl, "b_right": br,
+            "sig5": s5, "sig3": s3, "int53": workload.synthetic_int53(b),
+            "a_left": al, "a_right": ar, "b_left": bl, "b_right": br,
             "a_exgl": f[0], "a_exgr": f[1], "b_exgl": f[2], "b_exgr": f[3], "lw": lw, "up": up}
 
 
@@ -76,6 +77,15 @@ for fixture in ("dna_A2_global", "dna_A2_local", "dna_A3_global", "dna_A2_dagp")
                 s.score != O.scoreonly_wip(prm, pb)["score"]:
             bad.append(i)
     report(f"{fixture} forward / score-only", bad, N)
+    # scalar exact-ILD kernel (what the driver uses for blocks with < 8 rows), on the smaller problems
+    sel = [i for i, pb in enumerate(probs) if (pb["a_right"] - pb["a_left"]) * (pb["up"] - pb["lw"]) < 400000]
+    rn = eng.forwardS_ng([P[i] for i in sel])
+    bad = []
+    for i, r in zip(sel, rn):
+        o = O.trcbk_ng(prm, probs[i], cap=1 << 17)
+        if r.status or r.score != o["score"] or not np.array_equal(r.skl, o["skl"]):
+            bad.append(i)
+    report(f"{fixture} forwardS_ng (scalar)", bad, len(sel))
     if int(prm["Noll"]) == 3:       # double affine: no Hirschberg pass on the device (nor in the oracle)
         rl = eng.lspS_ng(P, max_vmf_space=1 << 25, sh=int(prm["sh"]), alg=2)
         bad = []
