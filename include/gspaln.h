@@ -206,6 +206,45 @@ const char* gspaln_version(void);
 int64_t gspaln_task_cells(const gspaln_task* t);
 
 /* ======================================================================================
+ * Splice-signal scan of a genomic DNA segment: what the Exinon
+ * constructor computes per (segment, strand) before any DP runs --
+ *   Exinon::intron53_c  (src/codepot.cc:437-477)  INT53: dinucleotide codes + site classes
+ *   Exinon::intron53_n  (src/codepot.cc:479-523)  SGPT2 sig5 / sig3 from the two splice PSSMs
+ *   PatMat::calcPatMat  (src/utilseq.cc:905-1002) Markov order <= 2, Seq::many == 1
+ * One thread per genome position; same fp32 operation order as the reference, so the shorts
+ * are bit-identical.  Outputs are indexed by column n in [0, len + 1] like Exinon::data_n
+ * built over [0, len); sig3[0] and sig5[len - 1] are undefined in the reference
+ * (uninitialised INT53 entries) and use dinucleotide code 0 here.
+ * ====================================================================================== */
+typedef struct gspaln_patmat {      /* PatMat, src/utilseq.h:62-90 */
+    int32_t rows, cols, offset, nalpha, morder;
+    float tonic, min_elem;
+    const float* mtx;               /* cols blocks of rows floats */
+} gspaln_patmat;
+
+typedef struct gspaln_scan_params {
+    gspaln_patmat pat5, pat3;       /* EijPat::pattern5 / pattern3 (mtx may be NULL: no PSSM) */
+    float fS, sss;                  /* Exinon::fS, alprm2.sss */
+    int32_t any;                    /* algmode.any */
+    int16_t sig53tab[32];           /* Exinon::sig53tab[0][0..15] (5') and [1][0..15] (3') */
+} gspaln_scan_params;
+
+typedef struct gspaln_scan gspaln_scan;
+
+int  gspaln_scan_create(gspaln_scan** out, const gspaln_scan_params* prm, int device);
+void gspaln_scan_destroy(gspaln_scan* sc);
+/* blocking, host buffers: codes[i] == *Seq::at(i), i in [0, len); outputs hold len + 2 entries */
+int  gspaln_exinon_scan(gspaln_scan* sc, const uint8_t* codes, int64_t len,
+                        int16_t* sig5, int16_t* sig3, uint16_t* int53);
+/* split form (segment resident in HBM; gspaln_scan_run may be repeated) */
+int  gspaln_scan_upload(gspaln_scan* sc, const uint8_t* codes, int64_t len);
+int  gspaln_scan_run(gspaln_scan* sc);
+int  gspaln_scan_download(gspaln_scan* sc, int16_t* sig5, int16_t* sig3, uint16_t* int53);
+/* ms of the last upload / run / download (CUDA events on the engine's stream) */
+int  gspaln_scan_get_timing(const gspaln_scan* sc, float* h2d_ms, float* kernel_ms, float* d2h_ms);
+const char* gspaln_scan_last_error(const gspaln_scan* sc);
+
+/* ======================================================================================
  * Protein query x genomic segment: SimdAln2h1 (src/fwd2h1_simd.h:69-382).
  *
  *   gspaln_h_create      freezes what SimdAln2h1::forwardH1_wip / fhinitH1 / fhlastH1 read from

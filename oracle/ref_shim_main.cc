@@ -357,6 +357,35 @@ int ref_task_export_ng_tables(void* h, short* sig53tab, short* penalty, int n_pe
 	return 0;
 }
 
+// splice-site PSSMs (EijPat::pattern5 / pattern3, src/utilseq.h:169-180) and the factors
+// Exinon::intron53_n applies to them (src/codepot.cc:479-523): inputs of the signal scan.
+// which: 0 = pattern5, 1 = pattern3.  meta = rows, cols, offset, nalpha, morder;
+// fmeta = tonic, min_elem.  Returns the number of matrix floats (rows * cols), 0 if absent.
+int ref_get_patmat(int which, int* meta, float* fmeta, float* mtx, int cap)
+{
+	if (!g_pwd || !g_pwd->eijpat) return -1;
+	const PatMat* pm = which == 0? g_pwd->eijpat->pattern5: g_pwd->eijpat->pattern3;
+	if (!pm) return 0;
+	meta[0] = pm->rows; meta[1] = pm->cols; meta[2] = pm->offset;
+	meta[3] = pm->nalpha; meta[4] = pm->order();
+	fmeta[0] = pm->tonic; fmeta[1] = pm->min_elem;
+	int n = pm->rows * pm->cols;
+	for (int i = 0; i < n && i < cap; ++i) mtx[i] = pm->mtx[i];
+	return n;
+}
+
+// fvals = Exinon::fS of this task, alprm2.sss, EijPat::tonic5, tonic3; ivals = algmode.any
+void ref_task_scan_factors(void* h, float* fvals, int* ivals)
+{
+	RefTask* t = (RefTask*) h;
+	const Seq* b = t->sqs[1];
+	fvals[0] = b->exin->fS; fvals[1] = alprm2.sss;
+	fvals[2] = g_pwd->eijpat->tonic5; fvals[3] = g_pwd->eijpat->tonic3;
+	ivals[0] = algmode.any;
+	ivals[1] = b->inex.cmpc;
+	ivals[2] = b->many;
+}
+
 int ref_task_scalar(void* h, int lw, int up, int* score, int* skl_out, int cap, double* seconds)
 {
 	RefTask* t = (RefTask*) h;

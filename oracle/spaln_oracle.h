@@ -84,6 +84,26 @@ int so_hirschberg_wip(const so_params* p, const so_task* t, int n_im,
  * corners, -1 allocation failure, -3 missing tables. */
 int so_trcbk_ng(const so_params* p, const so_task* t, int32_t* score, int32_t* skl, int cap);
 
+/* ---- splice-signal scan of a genomic DNA segment ---- */
+typedef struct {
+    int32_t rows, cols, offset, nalpha, morder;     /* PatMat, src/utilseq.h:62-90 */
+    float tonic, min_elem;
+    const float* mtx;                               /* rows x cols, column major (cols blocks of rows) */
+} so_patmat;
+
+typedef struct {
+    so_patmat pat5, pat3;       /* EijPat::pattern5 / pattern3 */
+    float fS, sss;              /* Exinon::fS, alprm2.sss */
+    int32_t any;                /* algmode.any */
+    const int16_t* sig53tab;    /* Exinon::sig53tab[0][0..543] */
+} so_scan_params;
+
+/* Exinon::intron53_c + intron53_n (src/codepot.cc:437-523) with PatMat::calcPatMat
+ * (src/utilseq.cc:905-1002) for a sequence whose Exinon is built over [0, len):
+ * codes[i] == *Seq::at(i); outputs indexed by column n in [0, len + 1]. */
+void so_exinon_scan_n(const so_scan_params* sp, const uint8_t* codes, int len,
+                      int16_t* sig5, int16_t* sig3, uint16_t* int53);
+
 /* Aln2s1::lspS_ng driver (trace-back vs multi-intermediate Hirschberg dispatch,
  * src/fwd2s1.cc:1801-1897) */
 typedef struct {

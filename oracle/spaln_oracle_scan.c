@@ -1,0 +1,103 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement (plain C) of the splice-signal scan that fills
+ * the Exinon tables of a genomic DNA segment:
+ *   src/codepot.cc:437-477   Exinon::intron53_c   (INT53: dinucleotide codes, site classes)
+ *   src/codepot.cc:479-523   Exinon::intron53_n   (SGPT2: sig5 / sig3 from the two PSSMs)
+ *   src/utilseq.cc:905-1002  PatMat::calcPatMat, Markov order <= 2, Seq::many == 1
+ * Float arithmetic is the reference's: sequential fp32 adds of table entries, one fp32 multiply,
+ * truncation to short.  Pinned against the SGPT2 / INT53 arrays of the unmodified reference
+ * (tests/golden/, tests/test_oracle_scan.py).
+ */
+#include <string.h>
+#include "spaln_oracle.h"
+
+/* ncredctab, src/seq.cc:31 (A, C, G, T -> 0..3; everything else >= 4) */
+static const unsigned char so_ncred[17] = { 15, 15, 0, 1, 4, 2, 5, 6, 10, 3, 7, 8, 10, 9, 12, 13, 14 };
+
+static int red(unsigned c) { return c < 17 ? so_ncred[c] : 15; }
+
+/* one PSSM value: PatMat::calcPatMat for the window that starts at position n
+ * (codes[i] == *sd->at(i), i in [0, len)) */
+static float patmat_at(const so_patmat* pm, const uint8_t* codes, int len, int n)
+{
+    const int rows = pm->rows, cols = pm->cols, na = pm->nalpha, order = pm->morder;
+    int s = n, e = n + cols;
+    if (e > len - order) e = len - order;           /* tt = min(at(n + cols), zz) */
+    const float* ptn = pm->mtx;
+    if (n < 0) { ptn -= (long) n * rows; s = 0; }
+    int q = n + cols >= len;                        /* bad characters */
+    float fit = 0;
+    if (order <= 1) {
+        for (int m = 0; s < e; ptn += rows, ++m, ++s) {
+            int k = red(codes[s]);
+            if (k < 0 || k >= na) ++q;
+            if (order && !q) {
+                if (m == 0) fit += ptn[k];
+                int j = red(codes[s + 1]);
+                if (j < 0 || j >= na) ++q;
+                k = na * k + j + na;
+            }
+            fit += q ? 0.f : ptn[k];
+        }
+        return fit + pm->tonic;
+    }
+    for (int m = 0; s < e; ptn += rows, ++m, ++s) {
+        int i = red(codes[s]);
+        int k = i;
+        if (i > 3) ++q;
+        if (m == 0 && q == 0) fit += ptn[k];
+        i = red(codes[s + 1]);
+        if (i > 3) ++q;
+        else if (q == 0) { k = na * k + i; if (m == 0) fit += ptn[k + na]; }
+        i = red(codes[s + 2]);
+        if (i > 3) ++q;
+        else if (q == 0) { k = na * k + i; fit += ptn[k + 20]; }
+    }
+    if (q) fit = (float) cols * pm->min_elem;
+    return fit + pm->tonic;
+}
+
+void so_exinon_scan_n(const so_scan_params* sp, const uint8_t* codes, int len,
+                      int16_t* sig5, int16_t* sig3, uint16_t* int53)
+{
+    static const unsigned jlevelac[4] = { 0, 2, 3, 1 }, jlevelgt[4] = { 0, 0, 3, 1 };
+    const unsigned any = (unsigned) sp->any & 3;
+    memset(sig5, 0, sizeof(int16_t) * (size_t) (len + 2));
+    memset(sig3, 0, sizeof(int16_t) * (size_t) (len + 2));
+    memset(int53, 0, sizeof(uint16_t) * (size_t) (len + 2));
+    /* intron53_c: residue i closes the dinucleotide (i - 1, i); it is the 5' code of column
+     * i - 1 and the 3' code of column i + 1 */
+    unsigned nc = 1;
+    for (int i = 0; i < len; ++i) {
+        unsigned c = (unsigned) red(codes[i]);
+        if (c >= 4) c = 1;
+        nc = ((nc << 2) + c) & 15;
+        unsigned c5 = any == 3, c3 = any == 3;
+        switch (nc) {
+          case 0: c3 = jlevelac[any]; break;                    /* AA */
+          case 1: c3 = 2; break;                                /* AC */
+          case 2: c3 = 3; break;                                /* AG */
+          case 3: c5 = 2; c3 = jlevelac[any]; break;            /* AT */
+          case 6: c3 = jlevelgt[any]; break;                    /* CG */
+          case 7: c5 = jlevelgt[any]; break;                    /* CT */
+          case 8: c5 = jlevelgt[any]; break;                    /* GA */
+          case 9: c5 = 3; break;                                /* GC */
+          case 10: c5 = jlevelgt[any]; c3 = jlevelgt[any]; break;   /* GG */
+          case 11: c5 = 3; break;                               /* GT */
+          case 14: c3 = jlevelgt[any]; break;                   /* TG */
+          case 15: c5 = jlevelgt[any]; break;                   /* TT */
+          default: break;
+        }
+        if (i - 1 >= 0) int53[i - 1] |= (uint16_t) (nc | (c5 << 8));
+        int53[i + 1] |= (uint16_t) ((nc << 4) | (c3 << 12));
+    }
+    /* intron53_n: columns 0 .. len - 1 */
+    const float fs = sp->fS * sp->sss;
+    for (int n = 0; n < len; ++n) {
+        int16_t s5 = sp->pat5.mtx ? (int16_t) (fs * patmat_at(&sp->pat5, codes, len, n - sp->pat5.offset)) : 0;
+        int16_t s3 = sp->pat3.mtx ? (int16_t) (fs * patmat_at(&sp->pat3, codes, len, n - sp->pat3.offset)) : 0;
+        s5 = (int16_t) (s5 + sp->sig53tab[int53[n] & 15]);
+        s3 = (int16_t) (s3 + sp->sig53tab[16 + ((int53[n] >> 4) & 15)]);
+        sig5[n] = s5;
+        sig3[n] = s3;
+    }
+}

@@ -33,6 +33,8 @@ EXPORTS = [
     "gspaln_h_download", "gspaln_h_get_timing", "gspaln_h_last_error", "gspaln_h_task_cells",
     "gspaln_h_lsp",
     "gspaln_queue_create", "gspaln_queue_submit", "gspaln_queue_stats", "gspaln_queue_destroy",
+    "gspaln_scan_create", "gspaln_scan_destroy", "gspaln_exinon_scan", "gspaln_scan_upload",
+    "gspaln_scan_run", "gspaln_scan_download", "gspaln_scan_get_timing", "gspaln_scan_last_error",
 ]
 
 
@@ -76,6 +78,16 @@ class GspalnTiming(C.Structure):
         ("launches", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("trace_bytes", C.c_int64), ("cells", C.c_int64),
     ]
+
+
+class GspalnPatMat(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("offset", C.c_int32), ("nalpha", C.c_int32),
+                ("morder", C.c_int32), ("tonic", C.c_float), ("min_elem", C.c_float), ("mtx", C.c_void_p)]
+
+
+class GspalnScanParams(C.Structure):
+    _fields_ = [("pat5", GspalnPatMat), ("pat3", GspalnPatMat), ("fS", C.c_float), ("sss", C.c_float),
+                ("any", C.c_int32), ("sig53tab", C.c_int16 * 32)]
 
 
 class GspalnHParams(C.Structure):
@@ -153,6 +165,17 @@ def load():
     lib.gspaln_queue_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.gspaln_queue_destroy.argtypes = [C.c_void_p]
     lib.gspaln_queue_destroy.restype = None
+    lib.gspaln_scan_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(GspalnScanParams), C.c_int]
+    lib.gspaln_scan_destroy.argtypes = [C.c_void_p]
+    lib.gspaln_scan_destroy.restype = None
+    lib.gspaln_exinon_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gspaln_scan_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    lib.gspaln_scan_run.argtypes = [C.c_void_p]
+    lib.gspaln_scan_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gspaln_scan_get_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                           C.POINTER(C.c_float)]
+    lib.gspaln_scan_last_error.argtypes = [C.c_void_p]
+    lib.gspaln_scan_last_error.restype = C.c_char_p
     lib.gspaln_h_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(GspalnHParams), C.c_int]
     lib.gspaln_h_destroy.argtypes = [C.c_void_p]
     lib.gspaln_h_destroy.restype = None
@@ -194,6 +217,31 @@ def make_params(p: dict) -> GspalnParams:
     for i in range(d * d):
         gp.simmtx[i] = int(flat[i])
     return gp
+
+
+def make_scan_params(p: dict):
+    """splice-signal scan parameters: PSSMs pat5_* / pat3_* (meta = rows, cols, offset, nalpha,
+    morder; f = tonic, min_elem; mtx), scan_f = (Exinon::fS, alprm2.sss), any, sig53tab.
+    Returns (struct, arrays to keep alive)."""
+    sp = GspalnScanParams()
+    keep = []
+    for name, pm in (("pat5", sp.pat5), ("pat3", sp.pat3)):
+        if p.get(name + "_mtx") is None:
+            continue
+        meta = [int(x) for x in p[name + "_meta"]]
+        f = np.asarray(p[name + "_f"], np.float32)
+        mtx = np.ascontiguousarray(p[name + "_mtx"], np.float32)
+        pm.rows, pm.cols, pm.offset, pm.nalpha, pm.morder = meta
+        pm.tonic, pm.min_elem = float(f[0]), float(f[1])
+        pm.mtx = mtx.ctypes.data
+        keep.append(mtx)
+    sf = np.asarray(p["scan_f"], np.float32)
+    sp.fS, sp.sss = float(sf[0]), float(sf[1])
+    sp.any = int(p["any"])
+    tab = np.asarray(p["sig53tab"], np.int16)
+    for i in range(32):
+        sp.sig53tab[i] = int(tab[i])
+    return sp, keep
 
 
 def make_h_params(p: dict) -> GspalnHParams:

@@ -1,0 +1,314 @@
+// gspaln_scan.cu -- splice-signal scan of a genomic DNA segment on the device (include/gspaln.h,
+// SURVEY section 8 row N1): Exinon::intron53_c + intron53_n (src/codepot.cc:437-523) with
+// PatMat::calcPatMat (src/utilseq.cc:905-1002, Markov order <= 2, Seq::many == 1).
+//
+// A streaming kernel: 1 byte in, 6 bytes out per genome position (sig5, sig3, INT53), one
+// thread per position.  A CTA stages the reduced codes of its tile (+ the PSSM windows on both
+// sides) and both PSSMs in shared memory; every thread then walks its two windows with the
+// reference's own fp32 operation order (sequential adds, one multiply, truncation to short), so
+// the results are bit-identical.  HBM-bound by design (7 B per position); see DESIGN.md.
+#include "../../include/gspaln.h"
+#include "gspaln_host.hpp"
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace gspaln;
+
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_PER_THREAD = 4;                  // positions per thread
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+constexpr int SCAN_MAXCOLS = 32;                    // PSSM columns handled
+constexpr int SCAN_MAXTAB = 4096;                   // floats per PSSM handled
+
+struct DevPat { int rows, cols, offset, nalpha, morder, present; float tonic, min_elem; };
+struct DevScanParams {
+    DevPat p5, p3;
+    float fs;               // fS * sss (fp32 product, as the reference forms it)
+    int any;
+    short tab[32];
+};
+
+// ncredctab, src/seq.cc:31
+__constant__ unsigned char c_ncred[17] = {15, 15, 0, 1, 4, 2, 5, 6, 10, 3, 7, 8, 10, 9, 12, 13, 14};
+
+// PatMat::calcPatMat for the window that starts at position n.  rc: reduced codes of the tile,
+// rc[i - base] for position i (0..3 = A, C, G, T; >= 4 anything else).
+__device__ __forceinline__ float patmat_at(const DevPat& pm, const float* __restrict__ mtx,
+                                           const unsigned char* __restrict__ rc, long long base,
+                                           long long len, long long n)
+{
+    const int rows = pm.rows, na = pm.nalpha, order = pm.morder;
+    long long s = n, e = n + pm.cols;
+    if (e > len - order) e = len - order;
+    const float* ptn = mtx;
+    if (n < 0) { ptn -= n * rows; s = 0; }
+    int q = n + pm.cols >= len;
+    float fit = 0.f;
+    if (order <= 1) {
+        for (int m = 0; s < e; ptn += rows, ++m, ++s) {
+            int k = rc[s - base];
+            if (k >= na) ++q;
+            if (order && !q) {
+                if (m == 0) fit = __fadd_rn(fit, ptn[k]);
+                const int j = rc[s + 1 - base];
+                if (j >= na) ++q;
+                k = na * k + j + na;
+            }
+            fit = __fadd_rn(fit, q ? 0.f : ptn[k]);
+        }
+        return __fadd_rn(fit, pm.tonic);
+    }
+    for (int m = 0; s < e; ptn += rows, ++m, ++s) {
+        int i = rc[s - base];
+        int k = i;
+        if (i > 3) ++q;
+        if (m == 0 && q == 0) fit = __fadd_rn(fit, ptn[k]);
+        i = rc[s + 1 - base];
+        if (i > 3) ++q;
+        else if (q == 0) { k = na * k + i; if (m == 0) fit = __fadd_rn(fit, ptn[k + na]); }
+        i = rc[s + 2 - base];
+        if (i > 3) ++q;
+        else if (q == 0) { k = na * k + i; fit = __fadd_rn(fit, ptn[k + 20]); }
+    }
+    if (q) fit = __fmul_rn((float) pm.cols, pm.min_elem);
+    return __fadd_rn(fit, pm.tonic);
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+exinon_scan_kernel(const DevScanParams* __restrict__ gP, const float* __restrict__ gmtx5,
+                   const float* __restrict__ gmtx3, const unsigned char* __restrict__ codes,
+                   long long len, short* __restrict__ sig5, short* __restrict__ sig3,
+                   unsigned short* __restrict__ int53)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ DevScanParams P;
+    if (threadIdx.x < sizeof(DevScanParams) / 4)
+        reinterpret_cast<int*>(&P)[threadIdx.x] = reinterpret_cast<const int*>(gP)[threadIdx.x];
+    __syncthreads();
+    const int n5 = P.p5.present ? P.p5.rows * P.p5.cols : 0, n3 = P.p3.present ? P.p3.rows * P.p3.cols : 0;
+    float* mtx5 = reinterpret_cast<float*>(smem);
+    float* mtx3 = mtx5 + n5;
+    unsigned char* rc = reinterpret_cast<unsigned char*>(mtx3 + n3);
+    for (int i = threadIdx.x; i < n5; i += SCAN_THREADS) mtx5[i] = gmtx5[i];
+    for (int i = threadIdx.x; i < n3; i += SCAN_THREADS) mtx3[i] = gmtx3[i];
+    // tile of positions [t0, t0 + SCAN_TILE) needs codes [t0 - back, t0 + SCAN_TILE + fwd)
+    const int back = max(max(P.p5.offset, P.p3.offset), 2);
+    const int fwd = SCAN_MAXCOLS + 4;
+    const long long t0 = (long long) blockIdx.x * SCAN_TILE;
+    const long long base = t0 - back;
+    const int span = back + SCAN_TILE + fwd;
+    for (int i = threadIdx.x; i < span; i += SCAN_THREADS) {
+        const long long pos = base + i;
+        unsigned c = 15;
+        if (pos >= 0 && pos < len) { const unsigned v = codes[pos]; c = v < 17 ? c_ncred[v] : 15; }
+        rc[i] = (unsigned char) c;
+    }
+    __syncthreads();
+    const unsigned any = (unsigned) P.any & 3;
+    const unsigned jac = (0x1320u >> (4 * any)) & 15, jgt = (0x1300u >> (4 * any)) & 15;    // jlevelac / jlevelgt
+#pragma unroll
+    for (int u = 0; u < SCAN_PER_THREAD; ++u) {
+        const long long n = t0 + u * SCAN_THREADS + threadIdx.x;       // column index
+        if (n > len + 1) continue;
+        // INT53 (intron53_c): dinc5 = (at(n), at(n + 1)) for n <= len - 2, dinc3 = (at(n - 2), at(n - 1))
+        // for 1 <= n <= len; the residue before the sequence and every ambiguous one count as C
+        auto code2 = [&](long long i) -> unsigned {
+            if (i < 0) return 1u;
+            const unsigned c = rc[i - base];
+            return c >= 4 ? 1u : c;
+        };
+        unsigned w = 0, d5 = 0, d3 = 0;
+        if (n <= len - 2) {
+            d5 = (code2(n) << 2) | code2(n + 1);
+            unsigned c5 = any == 3;
+            if (d5 == 3) c5 = 2;
+            else if (d5 == 9 || d5 == 11) c5 = 3;
+            else if (d5 == 7 || d5 == 8 || d5 == 10 || d5 == 15) c5 = jgt;
+            w |= d5 | (c5 << 8);
+        }
+        if (n >= 1 && n <= len) {
+            d3 = (code2(n - 2) << 2) | code2(n - 1);
+            unsigned c3 = any == 3;
+            if (d3 == 1) c3 = 2;
+            else if (d3 == 2) c3 = 3;
+            else if (d3 == 0 || d3 == 3) c3 = jac;
+            else if (d3 == 6 || d3 == 10 || d3 == 14) c3 = jgt;
+            w |= (d3 << 4) | (c3 << 12);
+        }
+        int53[n] = (unsigned short) w;
+        short s5 = 0, s3 = 0;
+        if (n < len) {
+            // intron53_n: (STYPE) (fs * pwm) + the dinucleotide term, both in short arithmetic
+            if (P.p5.present)
+                s5 = (short) __fmul_rn(P.fs, patmat_at(P.p5, mtx5, rc, base, len, n - P.p5.offset));
+            if (P.p3.present)
+                s3 = (short) __fmul_rn(P.fs, patmat_at(P.p3, mtx3, rc, base, len, n - P.p3.offset));
+            s5 = (short) (s5 + P.tab[d5]);
+            s3 = (short) (s3 + P.tab[16 + d3]);
+        }
+        sig5[n] = s5;
+        sig3[n] = s3;
+    }
+}
+
+}   // namespace
+
+struct gspaln_scan {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DevBuf<DevScanParams> d_prm;
+    DevBuf<float> d_mtx5, d_mtx3;
+    DevBuf<unsigned char> d_codes;
+    DevBuf<short> d_sig5, d_sig3;
+    DevBuf<unsigned short> d_int53;
+    DevScanParams hP;
+    size_t smem = 0;
+    long long len = 0;
+    float h2d_ms = 0, kernel_ms = 0, d2h_ms = 0;
+    std::string err;
+};
+
+namespace {
+int sfail(gspaln_scan* c, int code, const char* what, cudaError_t e = cudaSuccess)
+{
+    if (c) { c->err = what; if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); } }
+    return code;
+}
+#define SCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return sfail(sc, GSPALN_ECUDA, #call, e_); } while (0)
+
+bool pat_ok(const gspaln_patmat& p)
+{
+    if (!p.mtx) return true;
+    return p.rows > 0 && p.cols > 0 && p.cols <= SCAN_MAXCOLS && p.rows * p.cols <= SCAN_MAXTAB &&
+           p.morder >= 0 && p.morder <= 2 && p.nalpha == 4 && p.offset >= 0 && p.offset <= 64 &&
+           p.rows >= (p.morder == 2 ? 84 : p.morder == 1 ? 20 : 4);
+}
+}   // namespace
+
+extern "C" {
+
+const char* gspaln_scan_last_error(const gspaln_scan* sc) { return sc ? sc->err.c_str() : "null scan context"; }
+
+void gspaln_scan_destroy(gspaln_scan* sc)
+{
+    if (!sc) return;
+    cudaSetDevice(sc->device);
+    sc->d_prm.release(); sc->d_mtx5.release(); sc->d_mtx3.release(); sc->d_codes.release();
+    sc->d_sig5.release(); sc->d_sig3.release(); sc->d_int53.release();
+    for (auto& e : sc->ev) if (e) cudaEventDestroy(e);
+    if (sc->stream) cudaStreamDestroy(sc->stream);
+    delete sc;
+}
+
+int gspaln_scan_create(gspaln_scan** out, const gspaln_scan_params* prm, int device)
+{
+    if (!out || !prm) return GSPALN_EINVAL;
+    *out = nullptr;
+    if (!pat_ok(prm->pat5) || !pat_ok(prm->pat3)) return GSPALN_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return GSPALN_ENODEV; }
+    if (ndev <= 0 || device < 0 || device >= ndev) return GSPALN_ENODEV;    // there is no CPU fallback
+    gspaln_scan* sc = new gspaln_scan;
+    sc->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&sc->ev[i]);
+    DevScanParams& P = sc->hP;
+    memset(&P, 0, sizeof(P));
+    auto cp = [](DevPat& d, const gspaln_patmat& s) {
+        d.present = s.mtx != nullptr;
+        d.rows = s.rows; d.cols = s.cols; d.offset = s.offset; d.nalpha = s.nalpha; d.morder = s.morder;
+        d.tonic = s.tonic; d.min_elem = s.min_elem;
+    };
+    cp(P.p5, prm->pat5); cp(P.p3, prm->pat3);
+    P.fs = prm->fS * prm->sss;
+    P.any = prm->any;
+    memcpy(P.tab, prm->sig53tab, sizeof(P.tab));
+    const size_t n5 = P.p5.present ? (size_t) P.p5.rows * P.p5.cols : 0, n3 = P.p3.present ? (size_t) P.p3.rows * P.p3.cols : 0;
+    if (e == cudaSuccess) e = sc->d_prm.reserve(1);
+    if (e == cudaSuccess) e = sc->d_mtx5.reserve(n5 + 1);
+    if (e == cudaSuccess) e = sc->d_mtx3.reserve(n3 + 1);
+    if (e == cudaSuccess) e = cudaMemcpy(sc->d_prm.p, &P, sizeof(P), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n5) e = cudaMemcpy(sc->d_mtx5.p, prm->pat5.mtx, n5 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n3) e = cudaMemcpy(sc->d_mtx3.p, prm->pat3.mtx, n3 * sizeof(float), cudaMemcpyHostToDevice);
+    sc->smem = (n5 + n3) * sizeof(float) + 64 + 2 + SCAN_TILE + SCAN_MAXCOLS + 4 + 16;
+    if (e == cudaSuccess && sc->smem > 48 * 1024)
+        e = cudaFuncSetAttribute(exinon_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sc->smem);
+    if (e != cudaSuccess) { cudaGetLastError(); gspaln_scan_destroy(sc); return GSPALN_ECUDA; }
+    *out = sc;
+    return GSPALN_OK;
+}
+
+int gspaln_scan_upload(gspaln_scan* sc, const uint8_t* codes, int64_t len)
+{
+    if (!sc || len < 0 || (len && !codes)) return GSPALN_EINVAL;
+    SCK(cudaSetDevice(sc->device));
+    if (sc->d_codes.reserve((size_t) len + 16) != cudaSuccess || sc->d_sig5.reserve((size_t) len + 2) != cudaSuccess ||
+        sc->d_sig3.reserve((size_t) len + 2) != cudaSuccess || sc->d_int53.reserve((size_t) len + 2) != cudaSuccess) {
+        cudaGetLastError();
+        return sfail(sc, GSPALN_ENOMEM, "device allocation");
+    }
+    SCK(cudaEventRecord(sc->ev[0], sc->stream));
+    if (len) SCK(cudaMemcpyAsync(sc->d_codes.p, codes, (size_t) len, cudaMemcpyHostToDevice, sc->stream));
+    SCK(cudaEventRecord(sc->ev[1], sc->stream));
+    SCK(cudaStreamSynchronize(sc->stream));
+    cudaEventElapsedTime(&sc->h2d_ms, sc->ev[0], sc->ev[1]);
+    sc->len = len;
+    return GSPALN_OK;
+}
+
+int gspaln_scan_run(gspaln_scan* sc)
+{
+    if (!sc) return GSPALN_EINVAL;
+    SCK(cudaSetDevice(sc->device));
+    const long long cols = sc->len + 2;
+    const unsigned grid = (unsigned) ((cols + SCAN_TILE - 1) / SCAN_TILE);
+    SCK(cudaEventRecord(sc->ev[2], sc->stream));
+    exinon_scan_kernel<<<grid, SCAN_THREADS, sc->smem, sc->stream>>>(
+        sc->d_prm.p, sc->d_mtx5.p, sc->d_mtx3.p, sc->d_codes.p, sc->len, sc->d_sig5.p, sc->d_sig3.p, sc->d_int53.p);
+    SCK(cudaGetLastError());
+    SCK(cudaEventRecord(sc->ev[3], sc->stream));
+    SCK(cudaStreamSynchronize(sc->stream));
+    cudaEventElapsedTime(&sc->kernel_ms, sc->ev[2], sc->ev[3]);
+    return GSPALN_OK;
+}
+
+int gspaln_scan_download(gspaln_scan* sc, int16_t* sig5, int16_t* sig3, uint16_t* int53)
+{
+    if (!sc || !sig5 || !sig3 || !int53) return GSPALN_EINVAL;
+    SCK(cudaSetDevice(sc->device));
+    const size_t n = (size_t) sc->len + 2;
+    SCK(cudaEventRecord(sc->ev[4], sc->stream));
+    SCK(cudaMemcpyAsync(sig5, sc->d_sig5.p, n * sizeof(short), cudaMemcpyDeviceToHost, sc->stream));
+    SCK(cudaMemcpyAsync(sig3, sc->d_sig3.p, n * sizeof(short), cudaMemcpyDeviceToHost, sc->stream));
+    SCK(cudaMemcpyAsync(int53, sc->d_int53.p, n * sizeof(unsigned short), cudaMemcpyDeviceToHost, sc->stream));
+    SCK(cudaEventRecord(sc->ev[5], sc->stream));
+    SCK(cudaStreamSynchronize(sc->stream));
+    cudaEventElapsedTime(&sc->d2h_ms, sc->ev[4], sc->ev[5]);
+    return GSPALN_OK;
+}
+
+int gspaln_exinon_scan(gspaln_scan* sc, const uint8_t* codes, int64_t len,
+                       int16_t* sig5, int16_t* sig3, uint16_t* int53)
+{
+    int rc = gspaln_scan_upload(sc, codes, len);
+    if (rc == GSPALN_OK) rc = gspaln_scan_run(sc);
+    if (rc == GSPALN_OK) rc = gspaln_scan_download(sc, sig5, sig3, int53);
+    return rc;
+}
+
+int gspaln_scan_get_timing(const gspaln_scan* sc, float* h2d_ms, float* kernel_ms, float* d2h_ms)
+{
+    if (!sc) return GSPALN_EINVAL;
+    if (h2d_ms) *h2d_ms = sc->h2d_ms;
+    if (kernel_ms) *kernel_ms = sc->kernel_ms;
+    if (d2h_ms) *d2h_ms = sc->d2h_ms;
+    return GSPALN_OK;
+}
+
+}   // extern "C"

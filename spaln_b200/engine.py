@@ -479,3 +479,69 @@ class EngineH:
         self.lib.gspaln_h_get_timing(self._h, C.byref(t))
         return Timing(t.h2d_ms, t.kernel_ms, t.d2h_ms, t.launches, t.h2d_bytes, t.d2h_bytes,
                       t.trace_bytes, t.cells)
+
+
+# ---------------------------------------------------------------------------
+# splice-signal scan of a genomic DNA segment (Exinon::intron53_c / intron53_n)
+# ---------------------------------------------------------------------------
+class ExinonScan:
+    """Device mirror of what the reference's `Exinon` constructor computes for a DNA segment
+    (src/codepot.cc:357-399, 437-523): per column the 5' / 3' splice signals (SGPT2 sig5, sig3)
+    and the INT53 record.  `params` carries the two PSSMs and factors (see capi.make_scan_params)."""
+
+    def __init__(self, params: dict, device: int = 0):
+        self.lib = capi.load()
+        self._sp, self._keep = capi.make_scan_params(params)
+        self._h = C.c_void_p()
+        rc = self.lib.gspaln_scan_create(C.byref(self._h), C.byref(self._sp), device)
+        if rc != 0:
+            raise EngineError(f"gspaln_scan_create failed ({rc}): no usable CUDA device or bad "
+                              "parameters; the scan has no CPU fallback")
+        self._len = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.gspaln_scan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.gspaln_scan_last_error(self._h)
+            raise EngineError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def _out(self, n):
+        return np.zeros(n + 2, np.int16), np.zeros(n + 2, np.int16), np.zeros(n + 2, np.uint16)
+
+    def scan(self, codes):
+        """codes[i] == *Seq::at(i); returns sig5, sig3 (int16), int53 (uint16) by column 0 .. len + 1"""
+        c = np.ascontiguousarray(codes, np.uint8)
+        s5, s3, i53 = self._out(len(c))
+        self._check(self.lib.gspaln_exinon_scan(self._h, c.ctypes.data, len(c), s5.ctypes.data,
+                                                s3.ctypes.data, i53.ctypes.data), "gspaln_exinon_scan")
+        self._len = len(c)
+        return s5, s3, i53
+
+    def upload(self, codes):
+        c = np.ascontiguousarray(codes, np.uint8)
+        self._check(self.lib.gspaln_scan_upload(self._h, c.ctypes.data, len(c)), "gspaln_scan_upload")
+        self._len = len(c)
+
+    def run(self):
+        self._check(self.lib.gspaln_scan_run(self._h), "gspaln_scan_run")
+
+    def download(self):
+        s5, s3, i53 = self._out(self._len)
+        self._check(self.lib.gspaln_scan_download(self._h, s5.ctypes.data, s3.ctypes.data, i53.ctypes.data),
+                    "gspaln_scan_download")
+        return s5, s3, i53
+
+    def timing(self):
+        a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
+        self.lib.gspaln_scan_get_timing(self._h, C.byref(a), C.byref(b), C.byref(c))
+        return {"h2d_ms": a.value, "kernel_ms": b.value, "d2h_ms": c.value}

@@ -130,6 +130,7 @@ def gen(name: str):
     probs = []
     udh = "udh" in name
     ng_tables = None
+    scan_f = None
 
     def add(g, q, comrev=False, tag="", **setkw):
         t = ref.task(g, q, comrev)
@@ -157,7 +158,8 @@ def gen(name: str):
         out[pre + "int53"] = t.export_int53()
         out[pre + "ng_score"] = np.int32(rn["score"])
         out[pre + "ng_skl"] = rn["skl"].astype(np.int32)
-        nonlocal ng_tables
+        nonlocal ng_tables, scan_f
+        scan_f = t.scan_factors()
         if ng_tables is None or len(ng_tables["penalty"]) < ex["blen"] + 2:
             ng_tables = t.export_ng_tables(max(16384, ex["blen"] + 2))
         if udh:
@@ -205,6 +207,15 @@ def gen(name: str):
     out["prm_penalty"] = ng_tables["penalty"]
     out["prm_sig53tab"] = ng_tables["sig53tab"]
     out["prm_intpot"] = np.int32(ng_tables["intpot"])
+    # splice PSSMs + factors of the signal scan (Exinon::intron53_n): the fixtures' sig5 / sig3
+    # arrays are the reference's output for the fixtures' genome codes
+    for w, nm in ((0, "pat5"), (1, "pat3")):
+        pm = ref.patmat(w)
+        if pm is not None:
+            out[f"prm_{nm}_meta"] = np.array([pm["rows"], pm["cols"], pm["offset"], pm["nalpha"], pm["morder"]], np.int32)
+            out[f"prm_{nm}_f"] = np.array([pm["tonic"], pm["min_elem"]], np.float32)
+            out[f"prm_{nm}_mtx"] = pm["mtx"]
+    out["prm_scan_f"] = np.array([scan_f["fS"], scan_f["sss"]], np.float32)
     path = HERE / f"{name}.npz"
     np.savez_compressed(path, **out)
     print(name, "problems:", len(probs), "->", path, f"{path.stat().st_size / 1024:.0f} KiB")

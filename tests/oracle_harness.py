@@ -54,6 +54,8 @@ def lib():
                                            C.c_void_p, C.c_void_p]
         _lib.so_lsp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_void_p]
+        _lib.so_exinon_scan_n.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.so_exinon_scan_n.restype = None
         _lib.so_trcbk_ng.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _lib.so_forward_h1_wip.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         _lib.so_hirschberg_h1_wip.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -157,6 +159,52 @@ def hirschberg_wip(p: dict, t: dict, n_im: int):
     if rc < 0:
         raise RuntimeError(f"so_hirschberg_wip failed: {rc}")
     return {"score": score.value, "cpos": cpos, "ranges": ranges.tolist()}
+
+
+class SoPatMat(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("offset", C.c_int32), ("nalpha", C.c_int32),
+                ("morder", C.c_int32), ("tonic", C.c_float), ("min_elem", C.c_float), ("mtx", C.c_void_p)]
+
+
+class SoScanParams(C.Structure):
+    _fields_ = [("pat5", SoPatMat), ("pat3", SoPatMat), ("fS", C.c_float), ("sss", C.c_float),
+                ("any", C.c_int32), ("sig53tab", C.c_void_p)]
+
+
+def make_scan_params(p: dict):
+    """p: fixture parameters with the splice PSSMs (pat5_* / pat3_*), scan_f = (fS, sss), sig53tab"""
+    sp = SoScanParams()
+    keep = []
+    for name, pm in (("pat5", sp.pat5), ("pat3", sp.pat3)):
+        meta = [int(x) for x in p[name + "_meta"]]
+        f = np.asarray(p[name + "_f"], np.float32)
+        mtx = np.ascontiguousarray(p[name + "_mtx"], np.float32)
+        pm.rows, pm.cols, pm.offset, pm.nalpha, pm.morder = meta
+        pm.tonic, pm.min_elem = float(f[0]), float(f[1])
+        pm.mtx = mtx.ctypes.data
+        keep.append(mtx)
+    sf = np.asarray(p["scan_f"], np.float32)
+    sp.fS, sp.sss = float(sf[0]), float(sf[1])
+    sp.any = int(p["any"])
+    tab = np.ascontiguousarray(p["sig53tab"], np.int16)
+    sp.sig53tab = tab.ctypes.data
+    keep.append(tab)
+    sp._keep = keep
+    return sp
+
+
+def exinon_scan(p: dict, codes):
+    """Exinon::intron53_c + intron53_n over a whole segment: codes[i] == *Seq::at(i).
+    Returns sig5, sig3 (int16) and int53 (uint16) by column n in [0, len + 1]."""
+    sp = make_scan_params(p)
+    c = np.ascontiguousarray(codes, np.uint8)
+    n = len(c)
+    buf = np.concatenate([c, np.zeros(4, np.uint8)])       # the kernel never reads past len - 1
+    s5 = np.zeros(n + 2, np.int16)
+    s3 = np.zeros(n + 2, np.int16)
+    i53 = np.zeros(n + 2, np.uint16)
+    lib().so_exinon_scan_n(C.byref(sp), buf.ctypes.data, n, s5.ctypes.data, s3.ctypes.data, i53.ctypes.data)
+    return {"sig5": s5, "sig3": s3, "int53": i53}
 
 
 class SoLspOpts(C.Structure):

@@ -84,6 +84,8 @@ class Reference:
         L.ref_get_params.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.ref_task_export_int53.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_task_export_ng_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_get_patmat.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_task_scan_factors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_task_scalar.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         self.tmp = tempfile.TemporaryDirectory(prefix="spaln_ref_")
         g = os.path.join(self.tmp.name, "g0.fa")
@@ -117,6 +119,18 @@ class Reference:
                                       "codonk1", "termk1", "sim_rows", "sim_cols"]):
                 p[name] = int(pb[i])
         return p
+
+    def patmat(self, which: int):
+        """EijPat::pattern5 (0) / pattern3 (1): the splice-site PSSM the signal scan applies"""
+        meta = np.zeros(8, np.int32)
+        fmeta = np.zeros(4, np.float32)
+        mtx = np.zeros(1 << 16, np.float32)
+        n = self.lib.ref_get_patmat(which, meta.ctypes.data, fmeta.ctypes.data, mtx.ctypes.data, mtx.size)
+        if n <= 0:
+            return None
+        return {"rows": int(meta[0]), "cols": int(meta[1]), "offset": int(meta[2]), "nalpha": int(meta[3]),
+                "morder": int(meta[4]), "tonic": np.float32(fmeta[0]), "min_elem": np.float32(fmeta[1]),
+                "mtx": mtx[:n].copy()}
 
     def task(self, genome: str, query: str, comrev_query: bool = False) -> "RefTask":
         self._n += 1
@@ -238,6 +252,13 @@ class RefTask:
         if rc:
             raise RuntimeError("no intron tables in this set-up")
         return {"sig53tab": tab, "penalty": pen, "intpot": int(misc[0])}
+
+    def scan_factors(self):
+        f = np.zeros(4, np.float32)
+        i = np.zeros(4, np.int32)
+        self.lib.ref_task_scan_factors(self.h, f.ctypes.data, i.ctypes.data)
+        return {"fS": np.float32(f[0]), "sss": np.float32(f[1]), "tonic5": np.float32(f[2]),
+                "tonic3": np.float32(f[3]), "any": int(i[0]), "cmpc": int(i[1]), "many": int(i[2])}
 
     def scalar(self, lw, up, cap=1 << 16):
         """Aln2s1::trcbkalignS_ng forced onto its scalar branch (forwardS_ng + Vmf), raw Mfile corners"""

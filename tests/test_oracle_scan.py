@@ -1,0 +1,34 @@
+"""CPU: the splice-signal scan restatement (oracle/spaln_oracle_scan.c: Exinon::intron53_c /
+intron53_n + PatMat::calcPatMat) against the Exinon tables of the unmodified reference that the
+golden fixtures carry (sig5, sig3, int53 of every fixture problem)."""
+import numpy as np
+import pytest
+
+import golden_io
+
+
+def scan_equal(got, pb):
+    """got: dict sig5 / sig3 / int53 by column; pb: fixture problem.  sig3[0], sig5[len - 1] and the
+    INT53 halves the reference never writes are not reproducible (uninitialised memory there)."""
+    L = len(pb["b"]) - 2
+    ok = np.array_equal(got["sig5"][:L - 1], pb["sig5"][:L - 1]) and np.array_equal(got["sig3"][1:L], pb["sig3"][1:L])
+    ok = ok and np.array_equal(got["int53"][0:L - 1] & 0x0f0f, pb["int53"][0:L - 1] & 0x0f0f)
+    return ok and np.array_equal(got["int53"][1:L + 1] & 0xf0f0, pb["int53"][1:L + 1] & 0xf0f0)
+
+
+@pytest.mark.parametrize("name", ["dna_A2_global", "dna_A2_tetrapod", "dna_A2_udh"])
+def test_oracle_scan_matches_reference_tables(oracle, name):
+    prm, probs = golden_io.load(name)
+    assert int(prm["pat5_meta"][4]) == 2 and int(prm["pat3_meta"][4]) == 2     # Markov order 2 PSSMs
+    for i, pb in enumerate(probs):
+        got = oracle.exinon_scan(prm, pb["b"][1:-1])
+        assert scan_equal(got, pb), (name, i, pb["tag"])
+
+
+def test_oracle_scan_handles_ambiguity_and_short_segments(oracle):
+    prm, _ = golden_io.load("dna_A2_global")
+    from spaln_b200 import workload
+    for s in ("A", "ACG", "ACGTNNACGT" * 3, "GTAAGT" + "N" * 30 + "TTTCAG"):
+        got = oracle.exinon_scan(prm, workload.encode_dna(s))
+        assert np.array_equal(got["int53"], workload.synthetic_int53(workload.encode_dna(s)))
+        assert got["sig5"][len(s)] == 0 and got["sig5"][len(s) + 1] == 0
