@@ -10,6 +10,8 @@
 #include "../../include/gspaln.h"
 #include "gspaln_host.hpp"
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -155,6 +157,226 @@ exinon_scan_kernel(const DevScanParams* __restrict__ gP, const float* __restrict
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Fast path for the shape every parameter set of the reference ships: two Markov-order-2
+// PSSMs over 4 letters (84 rows).  The cost of a position is its 2 + cols5 + cols3 table
+// look-ups with data-dependent indices, so the kernel is built around shared-memory banks:
+//   * persistent CTAs (one per SM, 1024 threads); each keeps BOTH PSSMs in shared memory
+//     REPLICATED 32 TIMES, entry (column, k) of lane l at word (column * 64 + k) * 32 + l, so
+//     that every lane reads its own bank whatever its index is (no bank conflicts);
+//   * the tile's residues are staged as 2-bit codes (16 per word) plus one "ambiguous" bit per
+//     residue; a thread pulls the 32 residues around its position into one 64-bit register with
+//     two funnel shifts, and every table index is a 6-bit field of that register (the tables are
+//     stored with the k-mer digits reversed for that);
+//   * windows that touch an ambiguity code or an end of the segment (rare) take the generic
+//     routine above on global memory.
+// The fp32 additions run in the reference's order, so the shorts are bit-identical.
+// ---------------------------------------------------------------------------
+constexpr int FAST_THREADS = 1024;
+constexpr int FAST_PER = 4;
+constexpr int FAST_TILE = FAST_THREADS * FAST_PER;      // positions per tile
+constexpr int FAST_BACK = 32, FAST_FWD = 32;            // staged residues before / after the tile
+constexpr int FAST_WORDS = (FAST_BACK + FAST_TILE + FAST_FWD) / 16;
+
+// generic PSSM value straight from global memory (slow path of the fast kernel)
+__device__ __noinline__ float patmat_at_global(const DevPat& pm, const float* __restrict__ mtx,
+                                               const unsigned char* __restrict__ codes, long long len, long long n)
+{
+    const int rows = pm.rows, na = pm.nalpha;
+    auto rcode = [&](long long i) -> int { const unsigned v = codes[i]; return v < 17 ? c_ncred[v] : 15; };
+    long long s = n, e = n + pm.cols;
+    if (e > len - 2) e = len - 2;
+    const float* ptn = mtx;
+    if (n < 0) { ptn -= n * rows; s = 0; }
+    int q = n + pm.cols >= len;
+    float fit = 0.f;
+    for (int m = 0; s < e; ptn += rows, ++m, ++s) {
+        int i = rcode(s);
+        int k = i;
+        if (i > 3) ++q;
+        if (m == 0 && q == 0) fit = __fadd_rn(fit, ptn[k]);
+        i = rcode(s + 1);
+        if (i > 3) ++q;
+        else if (q == 0) { k = na * k + i; if (m == 0) fit = __fadd_rn(fit, ptn[k + na]); }
+        i = rcode(s + 2);
+        if (i > 3) ++q;
+        else if (q == 0) { k = na * k + i; fit = __fadd_rn(fit, ptn[k + 20]); }
+    }
+    if (q) fit = __fmul_rn((float) pm.cols, pm.min_elem);
+    return __fadd_rn(fit, pm.tonic);
+}
+
+template <int C>
+__device__ __forceinline__ float fast_sum(const float* __restrict__ T, const float* __restrict__ P, unsigned long long w)
+{
+    // T: replicated order-2 columns of this PSSM (already offset by the lane), P: order-0 / order-1
+    // terms of column 0 (4 + 16 entries, replicated); w: residues of the window from bit 0.
+    // Entry k of a column sits k * 128 bytes into it: the byte offset is a masked funnel shift.
+    const char* Tb = reinterpret_cast<const char*>(T);
+    const char* Pb = reinterpret_cast<const char*>(P);
+    const unsigned lo = (unsigned) w;
+    const unsigned long long w7 = w << 7;
+    float fit = __fadd_rn(0.f, *reinterpret_cast<const float*>(Pb + ((lo & 3u) << 7)));
+    fit = __fadd_rn(fit, *reinterpret_cast<const float*>(Pb + 512 + ((lo & 15u) << 7)));
+#pragma unroll
+    for (int m = 0; m < C; ++m) {
+        const unsigned off = (unsigned) (w7 >> (2 * m)) & 0x1f80u;
+        fit = __fadd_rn(fit, *reinterpret_cast<const float*>(Tb + m * 8192 + off));
+    }
+    return fit;
+}
+
+template <int C5, int C3>
+__global__ void __launch_bounds__(FAST_THREADS, 1)
+exinon_scan_fast_kernel(const DevScanParams* __restrict__ gP, const float* __restrict__ gmtx5,
+                        const float* __restrict__ gmtx3, const unsigned char* __restrict__ codes,
+                        long long len, short* __restrict__ sig5, short* __restrict__ sig3,
+                        unsigned short* __restrict__ int53)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ DevScanParams P;
+    if (threadIdx.x < sizeof(DevScanParams) / 4)
+        reinterpret_cast<int*>(&P)[threadIdx.x] = reinterpret_cast<const int*>(gP)[threadIdx.x];
+    __syncthreads();
+    float* T5 = reinterpret_cast<float*>(smem);                 // [C5 * 64][32]
+    float* T3 = T5 + C5 * 64 * 32;                              // [C3 * 64][32]
+    float* P5 = T3 + C3 * 64 * 32;                              // [20][32]
+    float* P3 = P5 + 20 * 32;
+    unsigned* pk = reinterpret_cast<unsigned*>(P3 + 20 * 32);   // 2-bit residues, 16 per word
+    unsigned short* bm = reinterpret_cast<unsigned short*>(pk + FAST_WORDS + 2);    // ambiguity bits
+    // tables, k-mer digits reversed: index c0 + 4 c1 + 16 c2 <-> reference index 16 c0 + 4 c1 + c2
+    for (int i = threadIdx.x; i < (C5 + C3) * 64 * 32; i += FAST_THREADS) {
+        const int lane = i & 31, e = i >> 5;
+        const bool five = e < C5 * 64;
+        const int ee = five ? e : e - C5 * 64;
+        const int m = ee >> 6, kp = ee & 63;
+        const int k = ((kp & 3) << 4) | (kp & 12) | (kp >> 4);
+        (five ? T5 : T3)[(ee << 5) + lane] = (five ? gmtx5 : gmtx3)[m * 84 + 20 + k];
+    }
+    for (int i = threadIdx.x; i < 2 * 20 * 32; i += FAST_THREADS) {
+        const int lane = i & 31, e = (i >> 5) % 20;
+        const bool five = (i >> 5) < 20;
+        int src = e;                                            // order 0: column-0 entry c0
+        if (e >= 4) { const int kp = e - 4; src = 4 + (((kp & 3) << 2) | (kp >> 2)); }
+        (five ? P5 : P3)[(e << 5) + lane] = (five ? gmtx5 : gmtx3)[src];
+    }
+    const int lane = threadIdx.x & 31;
+    const float* t5 = T5 + lane; const float* t3 = T3 + lane;
+    const float* p5 = P5 + lane; const float* p3 = P3 + lane;
+    const int o5 = P.p5.offset, o3 = P.p3.offset;
+    const unsigned any = (unsigned) P.any & 3;
+    const unsigned jac = (0x1320u >> (4 * any)) & 15, jgt = (0x1300u >> (4 * any)) & 15;
+    // site classes of the 16 dinucleotides, two bits each (intron53_c's switch)
+    unsigned lut5 = 0, lut3 = 0;
+    for (unsigned d = 0; d < 16; ++d) {
+        unsigned c5 = any == 3, c3 = any == 3;
+        if (d == 3) c5 = 2;
+        else if (d == 9 || d == 11) c5 = 3;
+        else if (d == 7 || d == 8 || d == 10 || d == 15) c5 = jgt;
+        if (d == 1) c3 = 2;
+        else if (d == 2) c3 = 3;
+        else if (d == 0 || d == 3) c3 = jac;
+        else if (d == 6 || d == 10 || d == 14) c3 = jgt;
+        lut5 |= c5 << (2 * d);
+        lut3 |= c3 << (2 * d);
+    }
+    const long long ntiles = (len + 2 + FAST_TILE - 1) / FAST_TILE;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long t0 = tile * FAST_TILE;
+        const long long base = t0 - FAST_BACK;
+        // 32-bit views of the tile's place in the segment (clamped: only small distances matter)
+        const int rem = (int) min(len - t0, (long long) (1 << 30));     // len - t0
+        const int pre = (int) min(t0, (long long) (1 << 30));           // residues before the tile
+        __syncthreads();                                        // previous tile fully consumed
+        for (int wi = threadIdx.x; wi < FAST_WORDS; wi += FAST_THREADS) {
+            const long long p0 = base + 16ll * wi;
+            unsigned word = 0, bad = 0;
+            if (p0 >= 0 && p0 + 16 <= len) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(codes + p0));
+                const unsigned vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const unsigned c = (vv[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                    const unsigned r = c < 17 ? c_ncred[c] : 15u;
+                    word |= (r > 3 ? 1u : r) << (2 * j);
+                    bad |= (r > 3 ? 1u : 0u) << j;
+                }
+            } else {
+                for (int j = 0; j < 16; ++j) {
+                    const long long pos = p0 + j;
+                    unsigned r = 1u;                            // outside the segment counts as C
+                    bool b = true;
+                    if (pos >= 0 && pos < len) {
+                        const unsigned c = codes[pos];
+                        r = c < 17 ? c_ncred[c] : 15u;
+                        b = r > 3;
+                        if (b) r = 1u;
+                    }
+                    word |= r << (2 * j);
+                    bad |= (b ? 1u : 0u) << j;
+                }
+            }
+            pk[wi] = word;
+            bm[wi] = (unsigned short) bad;
+        }
+        if (threadIdx.x < 2) { pk[FAST_WORDS + threadIdx.x] = 0x55555555u; bm[FAST_WORDS + threadIdx.x] = 0xffffu; }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < FAST_PER; ++u) {
+            const int local = u * FAST_THREADS + threadIdx.x;
+            const long long n = t0 + local;
+            if (local > rem + 1) continue;                      // n > len + 1
+            // residues n - 18 .. n + 13 -> 64-bit window (residue n - 18 + i at bits 2 i)
+            const int a = local + FAST_BACK - 18;
+            const int wj = a >> 4, sh = 2 * (a & 15);
+            const unsigned w0 = pk[wj], w1 = pk[wj + 1], w2 = pk[wj + 2];
+            const unsigned long long W = (unsigned long long) __funnelshift_r(w0, w1, sh) |
+                                         ((unsigned long long) __funnelshift_r(w1, w2, sh) << 32);
+            const unsigned b0 = bm[wj] | ((unsigned) bm[wj + 1] << 16), b1 = bm[wj + 2];
+            const unsigned B = __funnelshift_r(b0, b1, a & 15);       // ambiguity bits of the same residues
+            // INT53: dinc3 = residues n - 2, n - 1 (i = 16, 17); dinc5 = residues n, n + 1 (i = 18, 19)
+            unsigned wv = 0, d5 = 0, d3 = 0;
+            const unsigned hi = (unsigned) (W >> 32);           // residues n - 2 .. n + 13
+            if (local <= rem - 2) {                             // n <= len - 2
+                d5 = ((hi >> 4) & 3u) << 2 | ((hi >> 6) & 3u);
+                wv = d5 | (((lut5 >> (2 * d5)) & 3u) << 8);
+            }
+            if (local + pre >= 1 && local <= rem) {             // 1 <= n <= len
+                d3 = (hi & 3u) << 2 | ((hi >> 2) & 3u);
+                wv |= (d3 << 4) | (((lut3 >> (2 * d3)) & 3u) << 12);
+            }
+            int53[n] = (unsigned short) wv;
+            short s5 = 0, s3 = 0;
+            if (local < rem) {                                  // n < len
+                // window of the 5' PSSM: residues n - o5 .. n - o5 + C5 + 1; of the 3' PSSM likewise
+                const int i5 = 18 - o5, i3 = 18 - o3;
+                const bool ok5 = local + pre >= o5 && local - o5 + C5 <= rem - 2 &&
+                                 ((B >> i5) & ((1u << (C5 + 2)) - 1u)) == 0;
+                const bool ok3 = local + pre >= o3 && local - o3 + C3 <= rem - 2 &&
+                                 ((B >> i3) & ((1u << (C3 + 2)) - 1u)) == 0;
+                float f5, f3;
+                if (ok5) f5 = __fadd_rn(fast_sum<C5>(t5, p5, W >> (2 * i5)), P.p5.tonic);
+                else f5 = patmat_at_global(P.p5, gmtx5, codes, len, n - o5);
+                if (ok3) f3 = __fadd_rn(fast_sum<C3>(t3, p3, W >> (2 * i3)), P.p3.tonic);
+                else f3 = patmat_at_global(P.p3, gmtx3, codes, len, n - o3);
+                s5 = (short) __fmul_rn(P.fs, f5);
+                s3 = (short) __fmul_rn(P.fs, f3);
+                s5 = (short) (s5 + P.tab[d5]);
+                s3 = (short) (s3 + P.tab[16 + d3]);
+            }
+            sig5[n] = s5;
+            sig3[n] = s3;
+        }
+    }
+}
+
+constexpr size_t fast_smem(int c5, int c3)
+{
+    return ((size_t) (c5 + c3) * 64 * 32 + 2 * 20 * 32) * sizeof(float) + (FAST_WORDS + 2) * sizeof(unsigned) +
+           (FAST_WORDS + 4) * sizeof(unsigned short) + 16;
+}
+
 }   // namespace
 
 struct gspaln_scan {
@@ -168,6 +390,8 @@ struct gspaln_scan {
     DevBuf<unsigned short> d_int53;
     DevScanParams hP;
     size_t smem = 0;
+    bool fast = false;              // both PSSMs have the stock shape: bank-replicated kernel
+    int sm_count = 0;
     long long len = 0;
     float h2d_ms = 0, kernel_ms = 0, d2h_ms = 0;
     std::string err;
@@ -239,6 +463,20 @@ int gspaln_scan_create(gspaln_scan** out, const gspaln_scan_params* prm, int dev
     sc->smem = (n5 + n3) * sizeof(float) + 64 + 2 + SCAN_TILE + SCAN_MAXCOLS + 4 + 16;
     if (e == cudaSuccess && sc->smem > 48 * 1024)
         e = cudaFuncSetAttribute(exinon_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sc->smem);
+    // the stock shape (Markov order 2 over 4 letters, 8 + 18 columns, offsets that keep both
+    // windows inside residues n - 18 .. n + 13) runs on the bank-replicated kernel
+    if (e == cudaSuccess && !getenv("GSPALN_SCAN_GENERIC") && P.p5.present && P.p3.present &&
+        P.p5.morder == 2 && P.p3.morder == 2 && P.p5.rows == 84 && P.p3.rows == 84 && P.p5.cols == 8 && P.p3.cols == 18 &&
+        P.p5.offset <= 18 && P.p3.offset <= 18 && (18 - P.p5.offset) + 8 + 2 <= 32 && (18 - P.p3.offset) + 18 + 2 <= 32) {
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, device);
+        if (e == cudaSuccess && fast_smem(8, 18) <= (size_t) prop.sharedMemPerBlockOptin) {
+            e = cudaFuncSetAttribute(exinon_scan_fast_kernel<8, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int) fast_smem(8, 18));
+            sc->fast = e == cudaSuccess;
+            sc->sm_count = prop.multiProcessorCount;
+        }
+    }
     if (e != cudaSuccess) { cudaGetLastError(); gspaln_scan_destroy(sc); return GSPALN_ECUDA; }
     *out = sc;
     return GSPALN_OK;
@@ -269,8 +507,14 @@ int gspaln_scan_run(gspaln_scan* sc)
     const long long cols = sc->len + 2;
     const unsigned grid = (unsigned) ((cols + SCAN_TILE - 1) / SCAN_TILE);
     SCK(cudaEventRecord(sc->ev[2], sc->stream));
-    exinon_scan_kernel<<<grid, SCAN_THREADS, sc->smem, sc->stream>>>(
-        sc->d_prm.p, sc->d_mtx5.p, sc->d_mtx3.p, sc->d_codes.p, sc->len, sc->d_sig5.p, sc->d_sig3.p, sc->d_int53.p);
+    if (sc->fast) {
+        const long long ntiles = (cols + FAST_TILE - 1) / FAST_TILE;
+        const unsigned g = (unsigned) std::min<long long>(ntiles, sc->sm_count);
+        exinon_scan_fast_kernel<8, 18><<<g, FAST_THREADS, fast_smem(8, 18), sc->stream>>>(
+            sc->d_prm.p, sc->d_mtx5.p, sc->d_mtx3.p, sc->d_codes.p, sc->len, sc->d_sig5.p, sc->d_sig3.p, sc->d_int53.p);
+    } else
+        exinon_scan_kernel<<<grid, SCAN_THREADS, sc->smem, sc->stream>>>(
+            sc->d_prm.p, sc->d_mtx5.p, sc->d_mtx3.p, sc->d_codes.p, sc->len, sc->d_sig5.p, sc->d_sig3.p, sc->d_int53.p);
     SCK(cudaGetLastError());
     SCK(cudaEventRecord(sc->ev[3], sc->stream));
     SCK(cudaStreamSynchronize(sc->stream));
