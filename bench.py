@@ -371,6 +371,93 @@ def scan_leg(prm, with_cpu):
     return out
 
 
+def config4_leg(args, ncores, with_cpu):
+    """BASELINE config 4 shape on one GPU: mRNA of ~2.5 kb against loci with 20x longer introns
+    (tens of kb), local mode (-LS), through the driver (Aln2s1::lspS_ng) at the default -V: every
+    problem takes the multi-intermediate Hirschberg route + block re-alignments."""
+    import golden_io
+    from spaln_b200 import Engine, Problem, workload
+    prm, _ = golden_io.load("dna_A2_local")
+    rng = np.random.default_rng(20251017 + 4)
+    nq = max(16, args.queries // 5)
+    raw = [workload.config2_problem(rng, qlen_range=(1500, 3500), intron_scale=20.0) for _ in range(nq)]
+    problems = to_problems(raw)
+    host_cells(raw)
+    cells = sum(r["cells"] for r in raw)
+    eng = Engine(prm, device=0)
+    opts = dict(max_vmf_space=32 * 1024 * 1024, sh=int(prm["sh"]), alg=2)
+    eng.lspS_ng(problems[: max(8, nq // 10)], **opts)       # pools
+    t0 = time.perf_counter()
+    res = eng.lspS_ng(problems, **opts)
+    dt = time.perf_counter() - t0
+    tm = eng.timing()
+    out = {"note": "config-4 shaped problems (mRNA 1.5-3.5 kb, introns x20: loci of tens of kb), -LS, "
+                   "Aln2s1::lspS_ng at -V 32 MiB (Hirschberg route), wall clock with host buffers",
+           "queries": nq, "root_cells": cells, "queries_per_s": nq / dt, "gcups_root_cells": cells / dt / 1e9,
+           "kernel_ms": tm.kernel_ms, "total_ms": 1e3 * dt, "launches": tm.launches,
+           "device_cells": tm.cells, "status_nonzero": sum(1 for r in res if r.status != 0),
+           "mean_locus_nt": float(np.mean([r["b_right"] for r in raw]))}
+    eng.close()
+    if with_cpu:
+        import ref_harness
+        k = min(8, nq)
+        child = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--leg", "config4-ref", "--leg-seed", str(k),
+                                "--queries", str(args.queries)], capture_output=True, text=True)
+        try:
+            c = json.loads(child.stdout.strip().splitlines()[-1])
+            mism = sum(1 for i in range(k) if c["scores"][i] != res[i].score or c["nskl"][i] != len(res[i].skl))
+            out["cpu_baseline"] = {"queries_per_s": c["queries_per_s"], "gcups_root_cells": c["gcups"],
+                                   "cores": c["cores"], "kind": "reference",
+                                   "sample": f"first {k} problems, Aln2s1::lspS_ng of the AVX2 build, -LS, "
+                                             f"{c['cores']} threads (own process: the reference keeps one option "
+                                             "string per process)",
+                                   "parity_mismatches_on_sample": mism}
+        except Exception as e:      # the reference arm is a reported baseline, never the product
+            out["cpu_baseline"] = {"value": None, "error": f"{type(e).__name__}: {child.stderr[-200:]}"}
+    return out
+
+
+def config4_reference_child(args):
+    """child process: the reference's own lspS_ng (-LS) on the first k config-4 problems"""
+    import threading
+    import ref_harness
+    from spaln_b200 import workload
+    k = args.leg_seed
+    rng = np.random.default_rng(20251017 + 4)
+    nq = max(16, args.queries // 5)
+    raw = [workload.config2_problem(rng, qlen_range=(1500, 3500), intron_scale=20.0) for _ in range(nq)][:k]
+    ref = ref_harness.Reference("-Q0 -A2 -S1 -yX0 -LS -TDictyost")
+    tasks = []
+    for r in raw:
+        t = ref.task(r["genome_str"], r["query_str"])
+        t.inject(r["sig5"], r["sig3"])
+        tasks.append(t)
+    ncores = os.cpu_count() or 1
+    outs = [None] * k
+    nxt = [0]
+    lock = threading.Lock()
+
+    def work():
+        while True:
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+            if i >= k:
+                return
+            outs[i] = tasks[i].lsp(raw[i]["lw"], raw[i]["up"], cap=1 << 17)
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work) for _ in range(min(ncores, k))]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    dt = time.perf_counter() - t0
+    host_cells(raw)
+    cells = sum(r["cells"] for r in raw)
+    print(json.dumps({"queries_per_s": k / dt, "gcups": cells / dt / 1e9, "cores": min(ncores, k),
+                      "scores": [o["score"] for o in outs], "nskl": [len(o["skl"]) for o in outs]}))
+    return 0
+
+
 def host_cells(raw):
     import ctypes as C
     from spaln_b200 import capi
@@ -421,6 +508,8 @@ def main():
     args = ap.parse_args()
     if args.leg == "protein-cpu":
         return protein_reference_child(args.cpu_sample, args.leg_seed, os.cpu_count() or 1, args.leg_out)
+    if args.leg == "config4-ref":
+        return config4_reference_child(args)
     _quiet_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -603,6 +692,7 @@ def main():
             line["protein_path"] = prot
         if n_gpus == 1:
             line["scan_path"] = scan_leg(prm, with_cpu=not args.no_cpu_baseline)
+            line["config4_path"] = config4_leg(args, ncores, with_cpu=not args.no_cpu_baseline)
         if gather_ms is not None:
             line["gather_hits_ms"] = gather_ms
         if n_gpus == 1 and not args.no_cpu_baseline:

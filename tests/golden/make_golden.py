@@ -161,7 +161,7 @@ def gen(name: str):
         nonlocal ng_tables, scan_f
         scan_f = t.scan_factors()
         if ng_tables is None or len(ng_tables["penalty"]) < ex["blen"] + 2:
-            ng_tables = t.export_ng_tables(max(16384, ex["blen"] + 2))
+            ng_tables = t.export_ng_tables(max(1 << 19, ex["blen"] + 2))
         if udh:
             # the whole driver (Aln2s1::lspS_ng) and the Hirschberg pass alone
             rl = t.lsp(lw, up)

@@ -307,6 +307,36 @@ def test_lsp_driver_matches_oracle_seeded(oracle):
     eng.close()
 
 
+def test_lsp_driver_config4_shape_local(oracle):
+    """BASELINE config 4 shape: mRNA of ~2.5 kb against a locus with 20x longer introns (tens of kb),
+    local mode (-LS), default -V: every problem takes the multi-intermediate Hirschberg route and
+    its block re-alignments (some with fewer than 8 rows -> scalar kernel)"""
+    from spaln_b200 import workload
+    prm, _ = golden_io.load("dna_A2_local")
+    rng = np.random.default_rng(404)
+    probs = []
+    for _ in range(4):
+        r = workload.config2_problem(rng, qlen_range=(1500, 3500), intron_scale=20.0, flank=(500, 3000))
+        b = r["b"]
+        probs.append({"a": np.concatenate([[0], r["a"], [0]]).astype(np.uint8),
+                      "b": np.concatenate([[0], b, [0]]).astype(np.uint8),
+                      "sig5": r["sig5"], "sig3": r["sig3"], "int53": workload.synthetic_int53(b),
+                      "a_left": 0, "a_right": len(r["a"]), "b_left": 0, "b_right": len(b),
+                      "a_exgl": 1, "a_exgr": 1, "b_exgl": 1, "b_exgr": 1, "lw": r["lw"], "up": r["up"]})
+    assert min(len(pb["b"]) for pb in probs) > 10000
+    eng = _engine(prm)
+    vmf = int(prm["MaxVmfSpace"])
+    res = eng.lspS_ng(_problems(probs), max_vmf_space=vmf, sh=int(prm["sh"]), alg=2)
+    for i, (pb, r) in enumerate(zip(probs, res)):
+        o = oracle.lsp(prm, pb, cap=1 << 17, max_vmf_space=vmf)
+        assert not o["unsupported"] and r.status == 0, (i, r.status)
+        assert 2.0 * pb["a_right"] * (pb["b_right"] + pb["a_right"]) >= vmf         # Hirschberg route
+        assert r.score == o["score"], (i, r.score, o["score"])
+        assert np.array_equal(r.skl, o["skl"]), i
+        assert r.score > 5000               # the planted gene is found across the long introns
+    eng.close()
+
+
 def test_packed_batch_api_equals_object_api():
     prm, probs = golden_io.load("dna_A2_global")
     eng = _engine(prm)
