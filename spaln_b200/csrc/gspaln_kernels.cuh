@@ -37,7 +37,12 @@ constexpr int TPS = NELEM / NR;         // threads per strip (run in lock step)
 constexpr int SPP = 32 / TPS;           // strips per pass of one warp
 constexpr int NEV = -32768 + 1024;      // nevsel, src/fwd2s1_simd.h:47,202
 constexpr int CHECK_SCR = 29490;        // int(0.9 * SHRT_MAX), src/fwd2s1_simd.h:44
-constexpr int LAG = 2;                  // extra systolic lag (iterations) hiding the band-load latency
+constexpr int PF = 1;                   // band entries are loaded PF steps before their use
+constexpr int LAG = PF + 1;             // extra systolic lag (iterations): the entry of column n + PF
+                                        // must be final while column n is evaluated.  Measured on B200:
+                                        // PF = 3 changes nothing (364 GCUPS on config 2; a warp that
+                                        // runs alone does 0.35 GCUPS either way: it is bound by its own
+                                        // dependent-issue latency, not by the band loads)
 constexpr int TRACE_PAD = 36;           // trace steps per strip <= width + 31; slab stride width + TRACE_PAD
 constexpr int MAXQ = 8;
 constexpr int MTX_LD = 36;              // row stride (words) of the substitution table: with the four
@@ -300,7 +305,9 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
         if (DAGP) { F2[k] = NEV; E2[k] = NEV; }
     }
     const int gn = P.gn, ge = P.ge, gn2 = P.gn2, ge2 = P.ge2;
-    int nxt_f2 = NEV;
+    int pf_f2[PF];                      // prefetched F2 band words (DAGP only)
+#pragma unroll
+    for (int d = 0; d < PF; ++d) pf_f2[d] = NEV;
     const int floorL = localL_now ? 0 : INT_MIN;
     int prev_uh = NEV;
     int bval = INT_MIN, bstep = 0, bk = 0, bsi = 0;     // best local-mode cell of this thread
@@ -333,7 +340,9 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
         return re;
     };
 
-    unsigned nxt_band = 0;
+    unsigned pf_band[PF];               // prefetched {H | F} band words of columns n .. n + PF - 1
+#pragma unroll
+    for (int d = 0; d < PF; ++d) pf_band[d] = 0;
     uint2 nxt_col = make_uint2(0u, 0xffffffffu);
 
     // every strip run one after the other would need fewer iterations than this
@@ -379,8 +388,8 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
         const int band_bias = g.ml + t.lw - 1;      // band entry of column c (diagonal c - ml): c - band_bias
         if (run && j == -1) {
             // One iteration before the first step: the entries of columns
-            // n_start - 1 and n_start are final by now (written >= LAG - 1
-            // iterations ago by the strip above).
+            // n_start - 1 .. n_start + PF - 1 are final by now (the strip above
+            // is LAG = PF + 1 iterations ahead of the write of column n_start - 1).
 #pragma unroll
             for (int k = 0; k < NR; ++k) {
                 HA[k] = NEV; HB[k] = NEV; F[k] = NEV; E[k] = NEV; V2[k] = NEV; NJ[k] = 0;
@@ -390,8 +399,13 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
             }
             prev_uh = NEV;
             if (sub == 0) {
-                nxt_band = __ldcg(band + (g.n_start - band_bias));
-                if (DAGP) nxt_f2 = __ldcg(band2 + (g.n_start - band_bias));
+#pragma unroll
+                for (int d = 0; d < PF; ++d) {
+                    if (d < nsteps) {
+                        pf_band[d] = __ldcg(band + (g.n_start + d - band_bias));
+                        if (DAGP) pf_f2[d] = __ldcg(band2 + (g.n_start + d - band_bias));
+                    }
+                }
                 prev_uh = lo16(__ldcg(band + (g.n_start - 1 - band_bias)));
             }
             nxt_col = col_fetch(g.n_start);
@@ -407,16 +421,16 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
             }
         } else if (run && j >= 0) {
             const int n = g.n_start + j;
-            const unsigned cur_band = nxt_band;
-            const int cur_f2 = nxt_f2;
+            const unsigned cur_band = pf_band[0];
+            const int cur_f2 = pf_f2[0];
+#pragma unroll
+            for (int d = 0; d + 1 < PF; ++d) { pf_band[d] = pf_band[d + 1]; if (DAGP) pf_f2[d] = pf_f2[d + 1]; }
             const RingEntry cur_col = col_decode(nxt_col, n, n <= t.b_right);
-            if (j + 1 < nsteps) {
-                if (sub == 0) {
-                    nxt_band = __ldcg(band + (n + 1 - band_bias));
-                    if (DAGP) nxt_f2 = __ldcg(band2 + (n + 1 - band_bias));
-                }
-                nxt_col = col_fetch(n + 1);
+            if (sub == 0 && j + PF < nsteps) {
+                pf_band[PF - 1] = __ldcg(band + (n + PF - band_bias));
+                if (DAGP) pf_f2[PF - 1] = __ldcg(band2 + (n + PF - band_bias));
             }
+            if (j + 1 < nsteps) nxt_col = col_fetch(n + 1);
             const int rslot = n & 15;
             ring[rslot * CTA_THREADS] = cur_col;
             ring[(rslot + 16) * CTA_THREADS] = cur_col;

@@ -29,6 +29,14 @@ for name in ("dna_A2_global", "dna_A2_local"):
     eng.run(); eng.run()
     t = eng.timing()
     print(f"{name}: forwardS1_wip kernel {t.kernel_ms:.1f} ms -> {cells.sum() / t.kernel_ms / 1e6:.1f} GCUPS", flush=True)
+    # the largest problem alone: what one warp does when it has an SM to itself
+    big = int(np.argmax(cells))
+    eng.upload([P[big]]); eng.run(); eng.run()
+    t = eng.timing()
+    print(f"{name}: largest problem alone ({cells[big]:.3e} cells) {t.kernel_ms:.1f} ms -> "
+          f"{cells[big] / t.kernel_ms / 1e6:.3f} GCUPS per warp", flush=True)
+    eng.close()
+    eng = Engine(prm, 0)
     for p in P:
         m = p.a_right - p.a_left
         p.n_imd = max(1, min(int(round((2.0 * m * 2 / 12) ** (1 / 3))) - 1, m // 16))
