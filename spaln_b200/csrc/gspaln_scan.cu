@@ -207,24 +207,41 @@ __device__ __noinline__ float patmat_at_global(const DevPat& pm, const float* __
     return __fadd_rn(fit, pm.tonic);
 }
 
-template <int C>
-__device__ __forceinline__ float fast_sum(const float* __restrict__ T, const float* __restrict__ P, unsigned long long w)
+// One look-up-and-add step: the table entry at shared address (a + IMM).  The tables start on an
+// 8 KB boundary, so the data-dependent part of the address (bits 7..12) is OR-ed into the lane's
+// base with the same LOP3 that masks it, and the column offset rides in the LDS immediate.
+template <int IMM>
+__device__ __forceinline__ float lds_at(unsigned a)
 {
-    // T: replicated order-2 columns of this PSSM (already offset by the lane), P: order-0 / order-1
-    // terms of column 0 (4 + 16 entries, replicated); w: residues of the window from bit 0.
-    // Entry k of a column sits k * 128 bytes into it: the byte offset is a masked funnel shift.
-    const char* Tb = reinterpret_cast<const char*>(T);
-    const char* Pb = reinterpret_cast<const char*>(P);
-    const unsigned lo = (unsigned) w;
-    const unsigned long long w7 = w << 7;
-    float fit = __fadd_rn(0.f, *reinterpret_cast<const float*>(Pb + ((lo & 3u) << 7)));
-    fit = __fadd_rn(fit, *reinterpret_cast<const float*>(Pb + 512 + ((lo & 15u) << 7)));
-#pragma unroll
-    for (int m = 0; m < C; ++m) {
-        const unsigned off = (unsigned) (w7 >> (2 * m)) & 0x1f80u;
-        fit = __fadd_rn(fit, *reinterpret_cast<const float*>(Tb + m * 8192 + off));
+    float v;
+    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(IMM));
+    return v;
+}
+
+template <int M, int C>
+struct FastCols {       // columns M .. C - 1 of an order-2 PSSM, in order
+    static __device__ __forceinline__ float run(float fit, unsigned t_addr, unsigned long long w7)
+    {
+        const unsigned a = ((unsigned) (w7 >> (2 * M)) & 0x1f80u) | t_addr;
+        fit = __fadd_rn(fit, lds_at<M * 8192>(a));
+        return FastCols<M + 1, C>::run(fit, t_addr, w7);
     }
-    return fit;
+};
+template <int C>
+struct FastCols<C, C> {
+    static __device__ __forceinline__ float run(float fit, unsigned, unsigned long long) { return fit; }
+};
+
+template <int C>
+__device__ __forceinline__ float fast_sum(unsigned t_addr, unsigned p_addr, unsigned long long w)
+{
+    // t_addr / p_addr: shared addresses of this lane's copy of the order-2 columns / of the order-0
+    // and order-1 terms of column 0 (4 + 16 entries); w: residues of the window from bit 0.
+    // Entry k of a column sits k * 128 bytes into it.
+    const unsigned lo = (unsigned) w;
+    float fit = __fadd_rn(0.f, lds_at<0>(((lo & 3u) << 7) | p_addr));
+    fit = __fadd_rn(fit, lds_at<512>(((lo & 15u) << 7) | p_addr));
+    return FastCols<0, C>::run(fit, t_addr, w << 7);
 }
 
 template <int C5, int C3>
@@ -239,10 +256,12 @@ exinon_scan_fast_kernel(const DevScanParams* __restrict__ gP, const float* __res
     if (threadIdx.x < sizeof(DevScanParams) / 4)
         reinterpret_cast<int*>(&P)[threadIdx.x] = reinterpret_cast<const int*>(gP)[threadIdx.x];
     __syncthreads();
-    float* T5 = reinterpret_cast<float*>(smem);                 // [C5 * 64][32]
+    // tables on an 8 KB boundary of the shared window (see lds_at)
+    const unsigned sh0 = (unsigned) __cvta_generic_to_shared(smem);
+    float* T5 = reinterpret_cast<float*>(smem + ((8192u - (sh0 & 8191u)) & 8191u));     // [C5 * 64][32]
     float* T3 = T5 + C5 * 64 * 32;                              // [C3 * 64][32]
     float* P5 = T3 + C3 * 64 * 32;                              // [20][32]
-    float* P3 = P5 + 20 * 32;
+    float* P3 = P5 + 1024;                                      // [20][32], 4 KB further
     unsigned* pk = reinterpret_cast<unsigned*>(P3 + 20 * 32);   // 2-bit residues, 16 per word
     unsigned short* bm = reinterpret_cast<unsigned short*>(pk + FAST_WORDS + 2);    // ambiguity bits
     // tables, k-mer digits reversed: index c0 + 4 c1 + 16 c2 <-> reference index 16 c0 + 4 c1 + c2
@@ -262,8 +281,8 @@ exinon_scan_fast_kernel(const DevScanParams* __restrict__ gP, const float* __res
         (five ? P5 : P3)[(e << 5) + lane] = (five ? gmtx5 : gmtx3)[src];
     }
     const int lane = threadIdx.x & 31;
-    const float* t5 = T5 + lane; const float* t3 = T3 + lane;
-    const float* p5 = P5 + lane; const float* p3 = P3 + lane;
+    const unsigned t5 = (unsigned) __cvta_generic_to_shared(T5 + lane), t3 = (unsigned) __cvta_generic_to_shared(T3 + lane);
+    const unsigned p5 = (unsigned) __cvta_generic_to_shared(P5 + lane), p3 = (unsigned) __cvta_generic_to_shared(P3 + lane);
     const int o5 = P.p5.offset, o3 = P.p3.offset;
     const unsigned any = (unsigned) P.any & 3;
     const unsigned jac = (0x1320u >> (4 * any)) & 15, jgt = (0x1300u >> (4 * any)) & 15;
@@ -373,8 +392,8 @@ exinon_scan_fast_kernel(const DevScanParams* __restrict__ gP, const float* __res
 
 constexpr size_t fast_smem(int c5, int c3)
 {
-    return ((size_t) (c5 + c3) * 64 * 32 + 2 * 20 * 32) * sizeof(float) + (FAST_WORDS + 2) * sizeof(unsigned) +
-           (FAST_WORDS + 4) * sizeof(unsigned short) + 16;
+    return 8192 + ((size_t) (c5 + c3) * 64 * 32 + 1024 + 20 * 32) * sizeof(float) +
+           (FAST_WORDS + 2) * sizeof(unsigned) + (FAST_WORDS + 4) * sizeof(unsigned short) + 16;
 }
 
 }   // namespace
