@@ -356,9 +356,25 @@ def scan_leg(prm, with_cpu):
                         "kernel": "exinon_scan_fast_kernel<8, 18>",
                         "note": "issue-slot bound: 2 + 8 + 18 dependent fp32 table look-ups per position "
                                 "(reference operation order), see DESIGN.md"}}
+    # the protein-side preparation of the same genome: Seq::nuc2tron (1 B in, 1 B out per position)
+    from spaln_b200 import nuc2tron
+    z = np.load(ROOT / "tests" / "golden" / "nuc2tron.npz")
+    ends = np.concatenate([[0], codes, [0]]).astype(np.uint8)
+    tron, t_ms = nuc2tron(z["gencode"], ends)
+    out["nuc2tron"] = {"note": "Seq::nuc2tron over the same 100 Mb, kernel time with the segment resident",
+                       "kernel_ms": t_ms, "gnt_per_s": n / t_ms / 1e6,
+                       "roofline": {"bound": "hbm", "bytes_per_position": 2.0, "achieved": 2.0 * n / t_ms / 1e6,
+                                    "peak": peak, "unit": "GB/s", "frac": 2.0 * n / t_ms / 1e6 / peak,
+                                    "kernel": "nuc2tron_kernel"}}
     if with_cpu:
         sys.path.insert(0, str(ROOT / "tests"))
         import oracle_harness
+        kk = 20_000_000
+        t0 = time.perf_counter()
+        ot = oracle_harness.nuc2tron(z["gencode"], ends[: kk + 2])
+        out["nuc2tron"]["cpu_baseline"] = {"value": kk / (time.perf_counter() - t0) / 1e9, "unit": "Gnt/s",
+                                           "cores": 1, "kind": "port", "sample": "first 20 Mb",
+                                           "parity_on_sample": bool(np.array_equal(ot[:-1], tron[: kk - 1]))}
         k = 10_000_000
         t0 = time.perf_counter()
         o = oracle_harness.exinon_scan(prm, codes[:k])

@@ -244,6 +244,15 @@ int  gspaln_scan_download(gspaln_scan* sc, int16_t* sig5, int16_t* sig3, uint16_
 int  gspaln_scan_get_timing(const gspaln_scan* sc, float* h2d_ms, float* kernel_ms, float* d2h_ms);
 const char* gspaln_scan_last_error(const gspaln_scan* sc);
 
+/* Seq::nuc2tron (src/seq.cc:774-798, nuc2tron3 src/utilseq.cc:205-224; Seq::many == 1): the "tron"
+ * residues a protein query is aligned against -- position i becomes the translation of the codon
+ * (i - 1, i, i + 1) with the genetic code table `gencode` (src/utilseq.cc:38).  codes holds
+ * at(-1 .. len), i.e. len + 2 bytes with the two terminal residues; tron receives at(0 .. len - 1).
+ * Blocking, host buffers; *kernel_ms (may be NULL) receives the CUDA-event time of one kernel run
+ * with the segment resident.  There is no CPU fallback (GSPALN_ENODEV without a device). */
+int  gspaln_nuc2tron(int device, const uint8_t* gencode, const uint8_t* codes, int64_t len,
+                     uint8_t* tron, float* kernel_ms);
+
 /* ======================================================================================
  * Protein query x genomic segment: SimdAln2h1 (src/fwd2h1_simd.h:69-382).
  *

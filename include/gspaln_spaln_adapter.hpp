@@ -6,6 +6,8 @@
 // Replaces (all paths relative to the reference tree):
 //   SimdAln2s1 ctor + forwardS1_wip(Mfile*)   src/fwd2s1_simd.h:191-333, src/fwd2s1_wip_simd.h:233-474
 //   SimdAln2s1 ctor + scoreonlyS1_wip()       src/fwd2s1_wip_simd.h:42-231
+//   Aln2s1::lspS_ng(wdw) as a whole           src/fwd2s1.cc:1801-1897 (driver: trace-back vs
+//                                             Hirschberg dispatch, post-work, scalar small blocks)
 // See INTEGRATION.md for the three-line patch of src/fwd2s1.cc.
 #ifndef GSPALN_SPALN_ADAPTER_HPP
 #define GSPALN_SPALN_ADAPTER_HPP
@@ -20,6 +22,7 @@ namespace gspaln {
 class SpalnEngine {
     gspaln_ctx* ctx_ = nullptr;
     std::vector<short> sig5_, sig3_;
+    std::vector<unsigned short> int53_;
     std::vector<int> skl_;
 
     static void die(const char* what, int rc, const gspaln_ctx* c)
@@ -106,6 +109,59 @@ public:
             mfd->write((UPTR) &wsk);
         }
         return (VTYPE) r.score;
+    }
+
+    // Tables of the scalar exact-ILD kernel (the reference runs Aln2s1::forwardS_ng for blocks with
+    // fewer than 8 query rows, src/fwd2s1.cc:1676): sig53tab = Exinon::sig53tab[0] (544 shorts),
+    // the length penalty is evaluated here with the reference's own IntronPenalty::Penalty().
+    void enable_scalar(const PwdB* pwd, const STYPE* sig53tab, int max_segment)
+    {
+        std::vector<short> pen((size_t) max_segment + 1);
+        for (int n = 0; n <= max_segment; ++n) pen[n] = pwd->IntPen->Penalty(n);
+        std::vector<short> tab(sig53tab, sig53tab + 544);
+        int rc = gspaln_set_ng_tables(ctx_, tab.data(), pen.data(), (int) pen.size(), pwd->codonk1);
+        if (rc != GSPALN_OK) die("gspaln_set_ng_tables", rc, ctx_);
+    }
+
+    // == Aln2s1::lspS_ng(wdw) with the corners appended to mfd (src/fwd2s1.cc:1801-1897).
+    // int53: the INT53 array of seqs[1]->exin indexed by column (may be 0: blocks with fewer than
+    // 8 rows are then reported as unsupported).  Returns false if the problem needs a kernel that
+    // is not on the device (the caller falls back to the stock lspS_ng); *scr receives the score.
+    bool lspS_ng(const Seq** seqs, const WINDOW& wdw, Mfile* mfd, const INT53* int53, VTYPE* scr)
+    {
+        gspaln_task t;
+        gspaln_result r;
+        fill(t, seqs, wdw, GSPALN_FORWARD_WIP);
+        const Seq* b = seqs[1];
+        if (int53) {
+            // INT53 is four 4-bit fields in one INT (src/codepot.h:49-54): the low 16 bits are the
+            // dinc5 | dinc3 << 4 | cano5 << 8 | cano3 << 12 word of gspaln_task.int53
+            int53_.assign((size_t) b->right + 2, 0);
+            for (int i = b->left; i <= b->right; ++i)
+                int53_[i] = (unsigned short) (int53[i].dinc5 | (int53[i].dinc3 << 4) |
+                                              (int53[i].cano5 << 8) | (int53[i].cano3 << 12));
+            t.int53 = int53_.data();
+        }
+        gspaln_lsp_opts o = {MaxVmfSpace, (int) alprm.sh, (int) alprm.ubh, (int) algmode.alg};
+        int cap = (t.a_right - t.a_left) + (t.b_right - t.b_left) + 8;
+        for (;;) {
+            skl_.assign(2 * (size_t) cap, 0);
+            t.skl_cap = cap;
+            r.skl = skl_.data();
+            r.cpos = 0;
+            int rc = gspaln_lsp(ctx_, &t, 1, &o, &r);
+            if (rc != GSPALN_OK) die("gspaln_lsp", rc, ctx_);
+            if (r.status != GSPALN_ST_SKL_OVERFLOW) break;
+            cap = r.n_skl + 8;
+        }
+        if (r.status == GSPALN_ST_UNSUPPORTED) return false;
+        if (r.status == GSPALN_ST_BAD_TRACE) fatal("Unexpected dir\n");
+        for (int i = 0; i < r.n_skl; ++i) {
+            SKL wsk = {skl_[2 * i], skl_[2 * i + 1]};
+            mfd->write((UPTR) &wsk);
+        }
+        *scr = (VTYPE) r.score;
+        return true;
     }
 
     // == SimdAln2s1(seqs, pwd, wdw, spjcs, cip, 1).scoreonlyS1_wip()

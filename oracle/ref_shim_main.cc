@@ -48,6 +48,8 @@ int shim_h1_kernel(const Seq** seqs, const PwdB* pwd, int lw, int up, int kind,
 	int* score, int* skl_out, int cap, double* seconds);
 int shim_s1_adapter(const Seq** seqs, const PwdB* pwd, int lw, int up,
 	int kind, int device, int* score, int* skl_out, int cap);
+int shim_s1_adapter_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up, int device,
+	const void* int53, const short* sig53tab, int* score, int* skl_out, int cap);
 }
 
 namespace {
@@ -386,10 +388,27 @@ void ref_task_scan_factors(void* h, float* fvals, int* ivals)
 	ivals[2] = b->many;
 }
 
+// the genetic code table Seq::nuc2tron translates with (src/utilseq.cc:38, set by -C)
+void ref_get_gencode(unsigned char* out64)
+{
+	for (int i = 0; i < 64; ++i) out64[i] = gencode[i];
+}
+
 int ref_task_scalar(void* h, int lw, int up, int* score, int* skl_out, int cap, double* seconds)
 {
 	RefTask* t = (RefTask*) h;
 	return shim_s1_scalar((const Seq**) t->sqs, g_pwd, lw, up, score, skl_out, cap, seconds);
+}
+
+// drop-in check of the whole driver: Aln2s1::lspS_ng through the adapter (needs a GPU)
+int ref_task_adapter_lsp(void* h, int lw, int up, int device, int* score, int* skl_out, int cap)
+{
+	RefTask* t = (RefTask*) h;
+	const Seq* b = t->sqs[1];
+	const INT53* i53 = b->exin? b->exin->*get(ExinonInt53()): 0;
+	STYPE** tab = b->exin? b->exin->*get(ExinonTab()): 0;
+	return shim_s1_adapter_lsp((const Seq**) t->sqs, g_pwd, lw, up, device, i53,
+	    tab? tab[0]: 0, score, skl_out, cap);
 }
 
 int ref_task_lsp(void* h, int lw, int up, int* score, int* skl_out, int cap,

@@ -149,4 +149,23 @@ int shim_s1_adapter(const Seq** seqs, const PwdB* pwd, int lw, int up,
 	return copy_out(mfd, (SKL*) skl_out, cap);
 }
 
+// Aln2s1::lspS_ng through the adapter (GPU): int53 / sig53tab come from the caller because they
+// are private to Exinon (the main shim reads them, see ref_shim_main.cc).  Returns the number
+// of corners, or -1 if the adapter reports the problem as unsupported.
+int shim_s1_adapter_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up, int device,
+	const void* int53, const short* sig53tab, int* score, int* skl_out, int cap)
+{
+	static gspaln::SpalnEngine* eng = 0;
+	if (!eng) {
+	    eng = new gspaln::SpalnEngine(pwd, device, seqs[1]->inex.intr);
+	    if (sig53tab) eng->enable_scalar(pwd, sig53tab, 1 << 19);
+	}
+	WINDOW wdw = {lw, up, up - lw + 3};
+	Mfile mfd(sizeof(SKL));
+	VTYPE scr = 0;
+	if (!eng->lspS_ng(seqs, wdw, &mfd, (const INT53*) int53, &scr)) return -1;
+	*score = scr;
+	return copy_out(mfd, (SKL*) skl_out, cap);
+}
+
 }	// extern "C"

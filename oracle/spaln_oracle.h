@@ -104,6 +104,10 @@ typedef struct {
 void so_exinon_scan_n(const so_scan_params* sp, const uint8_t* codes, int len,
                       int16_t* sig5, int16_t* sig3, uint16_t* int53);
 
+/* Seq::nuc2tron (src/seq.cc:774-798): tron codes of a genomic DNA segment for protein queries;
+ * codes points at at(0) and codes[-1], codes[len] must be readable (terminal residues) */
+void so_nuc2tron(const uint8_t* gencode, const uint8_t* codes, int len, uint8_t* tron);
+
 /* Aln2s1::lspS_ng driver (trace-back vs multi-intermediate Hirschberg dispatch,
  * src/fwd2s1.cc:1801-1897) */
 typedef struct {

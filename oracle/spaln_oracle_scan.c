@@ -101,3 +101,32 @@ void so_exinon_scan_n(const so_scan_params* sp, const uint8_t* codes, int len,
         sig3[n] = s3;
     }
 }
+
+/* Seq::nuc2tron (src/seq.cc:774-798) with nuc2tron3 (src/utilseq.cc:205-224), Seq::many == 1:
+ * the "tron" code of position i is the translation of the codon (i - 1, i, i + 1).  codes points
+ * at at(0); codes[-1] and codes[len] are the terminal residues of the Seq (NUL).  gencode: the 64
+ * codon table in use (src/utilseq.cc:38). */
+void so_nuc2tron(const uint8_t* gencode, const uint8_t* codes, int len, uint8_t* tron)
+{
+    /* ncelements, src/seq.cc:33; most_abund, src/utilseq.cc:176; residue codes, src/cmn.h:115-117 */
+    static const unsigned char ncel[17] = { 0, 0, 0, 1, 2, 2, 0, 2, 0, 3, 3, 3, 1, 1, 2, 3, 0 };
+    static const unsigned char abund[4] = { 14, 3, 10, 13 };    /* LYS, ALA, GLY, LEU */
+    enum { UNP = 1, AMB = 2, SER = 18, SER2 = 23, TRM2 = 24, TRM = 25, G = 5 };
+    for (int i = 0; i < len; ++i) {
+        const unsigned m = codes[i];
+        int aa;
+        if (m <= UNP) aa = UNP;                                 /* IsGap: middle residue deleted */
+        else {
+            const int c2 = red(m);
+            if (c2 >= 4) aa = AMB;
+            else {
+                const int c1 = red(codes[i - 1]);
+                const unsigned t = codes[i + 1];
+                aa = c1 >= 4 ? abund[c2] : gencode[16 * c1 + 4 * c2 + ncel[t < 17 ? t : 0]];
+                if (aa == SER && m == G) aa = SER2;
+                else if (aa == TRM && m == G) aa = TRM2;
+            }
+        }
+        tron[i] = (uint8_t) aa;
+    }
+}

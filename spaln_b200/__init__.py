@@ -8,6 +8,6 @@ Only what the DP hot path needs lives here:
 """
 from .capi import FORWARD_WIP, SCOREONLY_WIP  # noqa: F401
 from .engine import (Engine, EngineError, EngineH, ExinonScan, PackedBatch, Problem,  # noqa: F401
-                     ProblemH, Result, Timing)
+                     ProblemH, Result, Timing, nuc2tron)
 
 __version__ = "0.1.0"

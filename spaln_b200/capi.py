@@ -35,6 +35,7 @@ EXPORTS = [
     "gspaln_queue_create", "gspaln_queue_submit", "gspaln_queue_stats", "gspaln_queue_destroy",
     "gspaln_scan_create", "gspaln_scan_destroy", "gspaln_exinon_scan", "gspaln_scan_upload",
     "gspaln_scan_run", "gspaln_scan_download", "gspaln_scan_get_timing", "gspaln_scan_last_error",
+    "gspaln_nuc2tron",
 ]
 
 
@@ -176,6 +177,7 @@ def load():
                                            C.POINTER(C.c_float)]
     lib.gspaln_scan_last_error.argtypes = [C.c_void_p]
     lib.gspaln_scan_last_error.restype = C.c_char_p
+    lib.gspaln_nuc2tron.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_float)]
     lib.gspaln_h_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(GspalnHParams), C.c_int]
     lib.gspaln_h_destroy.argtypes = [C.c_void_p]
     lib.gspaln_h_destroy.restype = None

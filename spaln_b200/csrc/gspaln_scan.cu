@@ -390,6 +390,60 @@ exinon_scan_fast_kernel(const DevScanParams* __restrict__ gP, const float* __res
     }
 }
 
+// ---------------------------------------------------------------------------
+// Seq::nuc2tron (src/seq.cc:774-798): tron code of position i = translation of the codon
+// (i - 1, i, i + 1).  Pure streaming, 1 byte in and 1 byte out per position: each thread turns one
+// aligned 16-byte vector of residues (plus the byte on either side) into one 16-byte vector of
+// tron codes; the four small tables live in shared memory.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nuc2tron_kernel(const unsigned char* __restrict__ gencode, const unsigned char* __restrict__ in,
+                long long len, long long nvec, unsigned char* __restrict__ out)
+{
+    // ncredctab, ncelements (src/seq.cc:31-33), most_abund (src/utilseq.cc:176)
+    __shared__ unsigned char s_red[32], s_el[32], s_gc[64];
+    if (threadIdx.x < 32) {
+        const unsigned char el[17] = {0, 0, 0, 1, 2, 2, 0, 2, 0, 3, 3, 3, 1, 1, 2, 3, 0};
+        s_red[threadIdx.x] = threadIdx.x < 17 ? c_ncred[threadIdx.x] : 15;
+        s_el[threadIdx.x] = threadIdx.x < 17 ? el[threadIdx.x] : 0;
+    }
+    if (threadIdx.x < 64) s_gc[threadIdx.x] = gencode[threadIdx.x];
+    __syncthreads();
+    const long long v = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvec) return;
+    // in + 16 is at(0); vector v covers positions 16 v .. 16 v + 15
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(in + 16 + 16 * v));
+    unsigned char c[18];
+    c[0] = in[15 + 16 * v];
+    c[17] = in[32 + 16 * v];
+    const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) c[j + 1] = (unsigned char) (ww[j >> 2] >> (8 * (j & 3)));
+    unsigned o[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const unsigned m = c[j + 1];
+        unsigned aa;
+        if (m <= 1) aa = 1;                                     // IsGap -> UNP
+        else {
+            const unsigned c2 = s_red[m & 31];
+            if (c2 >= 4) aa = 2;                                // AMB
+            else {
+                const unsigned c1 = s_red[c[j] & 31];
+                if (c1 >= 4) aa = (0x0d0a030eu >> (8 * c2)) & 0xffu;     // most_abund: LYS, ALA, GLY, LEU
+                else aa = s_gc[16 * c1 + 4 * c2 + s_el[c[j + 2] & 31]];
+                if (m == 5 && aa == 18) aa = 23;                // SER -> SER2 when the middle nt is G
+                else if (m == 5 && aa == 25) aa = 24;           // TRM -> TRM2
+            }
+        }
+        o[j >> 2] |= aa << (8 * (j & 3));
+    }
+    if (16 * v + 16 <= len)
+        *reinterpret_cast<uint4*>(out + 16 * v) = make_uint4(o[0], o[1], o[2], o[3]);
+    else
+        for (int j = 0; 16 * v + j < len; ++j) out[16 * v + j] = (unsigned char) (o[j >> 2] >> (8 * (j & 3)));
+}
+
 constexpr size_t fast_smem(int c5, int c3)
 {
     return 8192 + ((size_t) (c5 + c3) * 64 * 32 + 1024 + 20 * 32) * sizeof(float) +
@@ -563,6 +617,51 @@ int gspaln_exinon_scan(gspaln_scan* sc, const uint8_t* codes, int64_t len,
     if (rc == GSPALN_OK) rc = gspaln_scan_run(sc);
     if (rc == GSPALN_OK) rc = gspaln_scan_download(sc, sig5, sig3, int53);
     return rc;
+}
+
+int gspaln_nuc2tron(int device, const uint8_t* gencode, const uint8_t* codes, int64_t len,
+                    uint8_t* tron, float* kernel_ms)
+{
+    if (!gencode || len < 0 || (len && (!codes || !tron))) return GSPALN_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return GSPALN_ENODEV; }
+    if (ndev <= 0 || device < 0 || device >= ndev) return GSPALN_ENODEV;
+    if (cudaSetDevice(device) != cudaSuccess) return GSPALN_ECUDA;
+    if (len == 0) { if (kernel_ms) *kernel_ms = 0.f; return GSPALN_OK; }
+    // device layout: 15 pad bytes, at(-1), at(0 .. len - 1) from a 16-byte boundary, at(len), pad
+    const size_t nvec = ((size_t) len + 15) / 16;
+    unsigned char *d_in = nullptr, *d_out = nullptr, *d_gc = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = GSPALN_OK;
+    auto done = [&](int code) {
+        if (d_in) cudaFree(d_in);
+        if (d_out) cudaFree(d_out);
+        if (d_gc) cudaFree(d_gc);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (code != GSPALN_OK) cudaGetLastError();
+        return code;
+    };
+    if (cudaMalloc(&d_in, 16 * nvec + 48) != cudaSuccess || cudaMalloc(&d_out, 16 * nvec + 16) != cudaSuccess ||
+        cudaMalloc(&d_gc, 64) != cudaSuccess)
+        return done(GSPALN_ENOMEM);
+    if (cudaMemset(d_in, 0, 16 * nvec + 48) != cudaSuccess ||
+        cudaMemcpy(d_in + 15, codes, (size_t) len + 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d_gc, gencode, 64, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)
+        return done(GSPALN_ECUDA);
+    const unsigned grid = (unsigned) ((nvec + 255) / 256);
+    for (int rep = 0; rep < 2; ++rep) {         // the second run is the timed one (warm caches, resident input)
+        cudaEventRecord(e0);
+        nuc2tron_kernel<<<grid, 256>>>(d_gc, d_in, (long long) len, (long long) nvec, d_out);
+        cudaEventRecord(e1);
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) return done(GSPALN_ECUDA);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (kernel_ms) *kernel_ms = ms;
+    if (cudaMemcpy(tron, d_out, (size_t) len, cudaMemcpyDeviceToHost) != cudaSuccess) rc = GSPALN_ECUDA;
+    return done(rc);
 }
 
 int gspaln_scan_get_timing(const gspaln_scan* sc, float* h2d_ms, float* kernel_ms, float* d2h_ms)

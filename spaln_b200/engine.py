@@ -545,3 +545,20 @@ class ExinonScan:
         a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
         self.lib.gspaln_scan_get_timing(self._h, C.byref(a), C.byref(b), C.byref(c))
         return {"h2d_ms": a.value, "kernel_ms": b.value, "d2h_ms": c.value}
+
+
+def nuc2tron(gencode, codes_with_ends, device: int = 0):
+    """Seq::nuc2tron on the device (src/seq.cc:774-798): codes_with_ends = at(-1 .. len) of a DNA
+    segment; returns (tron codes of at(0 .. len - 1), kernel ms).  No CPU fallback."""
+    lib = capi.load()
+    g = np.ascontiguousarray(gencode, np.uint8)
+    c = np.ascontiguousarray(codes_with_ends, np.uint8)
+    if g.size != 64 or c.size < 2:
+        raise ValueError("gencode must hold 64 entries, codes at least the two terminal residues")
+    n = c.size - 2
+    out = np.zeros(n, np.uint8)
+    ms = C.c_float(0)
+    rc = lib.gspaln_nuc2tron(device, g.ctypes.data, c.ctypes.data, n, out.ctypes.data, C.byref(ms))
+    if rc != 0:
+        raise EngineError(f"gspaln_nuc2tron failed ({rc}); there is no CPU fallback")
+    return out, ms.value

@@ -207,6 +207,19 @@ def exinon_scan(p: dict, codes):
     return {"sig5": s5, "sig3": s3, "int53": i53}
 
 
+def nuc2tron(gencode, codes_with_ends):
+    """codes_with_ends: at(-1 .. len) (len + 2 bytes); returns the tron codes of at(0 .. len - 1)"""
+    c = np.ascontiguousarray(codes_with_ends, np.uint8)
+    g = np.ascontiguousarray(gencode, np.uint8)
+    n = len(c) - 2
+    out = np.zeros(max(n, 0), np.uint8)
+    lib().so_nuc2tron.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib().so_nuc2tron.restype = None
+    if n > 0:
+        lib().so_nuc2tron(g.ctypes.data, c.ctypes.data + 1, n, out.ctypes.data)
+    return out
+
+
 class SoLspOpts(C.Structure):
     _fields_ = [("max_vmf_space", C.c_int32), ("sh", C.c_int32), ("ubh", C.c_int32),
                 ("alg", C.c_int32)]

@@ -73,6 +73,7 @@ class Reference:
                                    C.c_void_p, C.c_int, C.c_void_p]
         L.ref_task_adapter.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_task_adapter_lsp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.ref_task_export_p.argtypes = [C.c_void_p] * 4
         L.ref_get_params_p.argtypes = [C.c_void_p, C.c_int]
         L.ref_task_inject_p.argtypes = [C.c_void_p, C.c_void_p]
@@ -119,6 +120,12 @@ class Reference:
                                       "codonk1", "termk1", "sim_rows", "sim_cols"]):
                 p[name] = int(pb[i])
         return p
+
+    def gencode(self):
+        out = np.zeros(64, np.uint8)
+        self.lib.ref_get_gencode.argtypes = [C.c_void_p]
+        self.lib.ref_get_gencode(out.ctypes.data)
+        return out
 
     def patmat(self, which: int):
         """EijPat::pattern5 (0) / pattern3 (1): the splice-site PSSM the signal scan applies"""
@@ -300,6 +307,16 @@ class RefTask:
         skl = np.zeros((cap, 2), np.int32)
         n = self.lib.ref_task_adapter(self.h, lw, up, kind, device, C.byref(score),
                                       skl.ctypes.data, cap)
+        return {"score": score.value, "skl": skl[:n].copy()}
+
+    def adapter_lsp(self, lw, up, device=0, cap=1 << 16):
+        """Aln2s1::lspS_ng through include/gspaln_spaln_adapter.hpp (GPU drop-in of the driver);
+        returns None if the adapter reports the problem as unsupported"""
+        score = C.c_int(0)
+        skl = np.zeros((cap, 2), np.int32)
+        n = self.lib.ref_task_adapter_lsp(self.h, lw, up, device, C.byref(score), skl.ctypes.data, cap)
+        if n < 0:
+            return None
         return {"score": score.value, "skl": skl[:n].copy()}
 
     def lsp(self, lw, up, cap=1 << 16):

@@ -12,7 +12,7 @@ ROOT = Path(__file__).resolve().parent.parent
 def declared_functions():
     txt = (ROOT / "include" / "gspaln.h").read_text()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(gspaln_[a-z_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(gspaln_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_header_declares_expected_surface():

@@ -28,3 +28,28 @@ def test_adapter_dropin_matches_reference():
         assert np.array_equal(a["skl"], r["skl"]), i
         assert t.adapter(lw, up, 1)["score"] == t.kernel(lw, up, 1)["score"], i
         t.close()
+
+
+def test_adapter_dropin_driver_matches_reference():
+    """the whole driver: the reference's Aln2s1::lspS_ng on the CPU against SpalnEngine::lspS_ng
+    (gspaln_lsp on the GPU) on the reference's own objects -- trace-back problems, Hirschberg
+    route (the set-up keeps the default -V, so the larger problems take it) and tiny problems that
+    the reference aligns with its scalar kernel"""
+    from spaln_b200 import workload
+    ref = ref_harness.Reference._instance or ref_harness.Reference("-Q0 -A2 -S1 -yX0 -TDictyost")
+    p = ref.params()
+    rng = np.random.default_rng(123)
+    shapes = [((60, 600), (50, 600))] * 5 + [((2, 7), (30, 300))] * 3 + [((1800, 2600), (1500, 4000))] * 2
+    n_udh = 0
+    for i, (qr, fl) in enumerate(shapes):
+        g, q, _ = workload.plant_gene(rng, qlen_range=qr, flank=fl)
+        t = ref.task(g, q, comrev_query=(i % 5 == 4))
+        lw, up = t.stripe(p["sh"])
+        r = t.lsp(lw, up, cap=1 << 17)
+        a = t.adapter_lsp(lw, up, cap=1 << 17)
+        assert a is not None, i
+        assert a["score"] == r["score"], (i, a["score"], r["score"])
+        assert np.array_equal(a["skl"], r["skl"]), i
+        n_udh += 2.0 * len(q) * (len(g) + len(q)) >= p["MaxVmfSpace"]
+        t.close()
+    assert n_udh >= 2

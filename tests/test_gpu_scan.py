@@ -96,3 +96,24 @@ def test_scan_genome_scale_properties(oracle):
     t = sc.timing()
     assert t["kernel_ms"] > 0
     sc.close()
+
+
+def test_nuc2tron_matches_reference_and_oracle(oracle):
+    """gspaln_nuc2tron against the reference's tron codes (golden) and the oracle on seeded
+    segments of every length around the 16-byte vector width"""
+    from spaln_b200 import nuc2tron
+    z = np.load(golden_io.GOLDEN_DIR / "nuc2tron.npz")
+    gc = z["gencode"]
+    for i in range(int(z["n"])):
+        got, _ = nuc2tron(gc, z[f"dna{i}"])
+        assert np.array_equal(got, z[f"tron{i}"][1:-1]), i
+    rng = np.random.default_rng(12)
+    for n in list(range(0, 40)) + [255, 256, 257, 4095, 4096, 4097, 1_000_003]:
+        codes = np.concatenate([[0], _random_codes(rng, n, amb=0.02), [0]]).astype(np.uint8)
+        got, ms = nuc2tron(gc, codes)
+        assert np.array_equal(got, oracle.nuc2tron(gc, codes)), n
+    # a non-standard table goes through unchanged semantics
+    gc2 = gc.copy()
+    gc2[[56, 58]] = 20
+    codes = np.concatenate([[0], _random_codes(rng, 5000, amb=0.0), [0]]).astype(np.uint8)
+    assert np.array_equal(nuc2tron(gc2, codes)[0], oracle.nuc2tron(gc2, codes))

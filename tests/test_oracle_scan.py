@@ -32,3 +32,17 @@ def test_oracle_scan_handles_ambiguity_and_short_segments(oracle):
         got = oracle.exinon_scan(prm, workload.encode_dna(s))
         assert np.array_equal(got["int53"], workload.synthetic_int53(workload.encode_dna(s)))
         assert got["sig5"][len(s)] == 0 and got["sig5"][len(s) + 1] == 0
+
+
+def test_oracle_nuc2tron_matches_reference(oracle):
+    """Seq::nuc2tron: residue codes as the reference reads the DNA (DNA set-up) against the tron
+    codes the protein set-up holds for the same segments (tests/golden/make_golden_nuc2tron.py),
+    all fifteen IUPAC codes included"""
+    z = np.load(golden_io.GOLDEN_DIR / "nuc2tron.npz")
+    assert int(z["n"]) >= 10
+    seen = set()
+    for i in range(int(z["n"])):
+        d, t = z[f"dna{i}"], z[f"tron{i}"]
+        assert np.array_equal(oracle.nuc2tron(z["gencode"], d), t[1:-1]), i
+        seen |= set(d.tolist())
+    assert len(seen) >= 16
