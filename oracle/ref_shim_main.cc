@@ -366,7 +366,9 @@ int ref_task_export_ng_tables(void* h, short* sig53tab, short* penalty, int n_pe
 int ref_get_patmat(int which, int* meta, float* fmeta, float* mtx, int cap)
 {
 	if (!g_pwd || !g_pwd->eijpat) return -1;
-	const PatMat* pm = which == 0? g_pwd->eijpat->pattern5: g_pwd->eijpat->pattern3;
+	const EijPat* ep = g_pwd->eijpat;
+	const PatMat* pm = which == 0? ep->pattern5: which == 1? ep->pattern3:
+	    which == 2? ep->patternI: which == 3? ep->patternT: ep->patternB;
 	if (!pm) return 0;
 	meta[0] = pm->rows; meta[1] = pm->cols; meta[2] = pm->offset;
 	meta[3] = pm->nalpha; meta[4] = pm->order();
@@ -392,6 +394,34 @@ void ref_task_scan_factors(void* h, float* fvals, int* ivals)
 void ref_get_gencode(unsigned char* out64)
 {
 	for (int i = 0; i < 64; ++i) out64[i] = gencode[i];
+}
+
+// protein-side scan (Exinon::intron53_p, src/codepot.cc:525-619): which potentials exist and the
+// factors applied to them.  ivals: codepot present, its size() (ndata), dsize(), exonpot present,
+// intnpot present, DvsP, bpprm.maxb3d; fvals: Exinon::fact, alprm2.z, alprm2.Z, alprm2.bti,
+// bpprm.factor, alprm2.o, EijPat::tonicB
+void ref_task_scan_factors_p(void* h, float* fvals, int* ivals)
+{
+	RefTask* t = (RefTask*) h;
+	const Seq* b = t->sqs[1];
+	ivals[0] = g_pwd->codepot != 0;
+	ivals[1] = g_pwd->codepot? g_pwd->codepot->size(): 0;
+	ivals[2] = g_pwd->codepot? g_pwd->codepot->dsize(): 0;
+	ivals[3] = g_pwd->exonpot != 0;
+	ivals[4] = g_pwd->intnpot != 0;
+	ivals[5] = g_pwd->DvsP;
+	ivals[6] = bpprm.maxb3d;
+	fvals[0] = b->exin->fact; fvals[1] = alprm2.z; fvals[2] = alprm2.Z; fvals[3] = alprm2.bti;
+	fvals[4] = bpprm.factor; fvals[5] = alprm2.o; fvals[6] = g_pwd->eijpat->tonicB;
+}
+
+// the coding potential table (ExinPot::begin(), dsize() floats)
+int ref_get_codepot(float* out, int cap)
+{
+	if (!g_pwd || !g_pwd->codepot) return 0;
+	int n = g_pwd->codepot->dsize();
+	for (int i = 0; i < n && i < cap; ++i) out[i] = g_pwd->codepot->begin()[i];
+	return n;
 }
 
 int ref_task_scalar(void* h, int lw, int up, int* score, int* skl_out, int cap, double* seconds)

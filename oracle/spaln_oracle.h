@@ -104,6 +104,18 @@ typedef struct {
 void so_exinon_scan_n(const so_scan_params* sp, const uint8_t* codes, int len,
                       int16_t* sig5, int16_t* sig3, uint16_t* int53);
 
+/* protein-side scan: Exinon::intron53_p (src/codepot.cc:525-619) over a TRON segment */
+typedef struct {
+    so_scan_params base;        /* pat5, pat3, fS, sss, any, sig53tab */
+    so_patmat patI, patT;       /* EijPat::patternI (start codon), patternT (termination codon) */
+    const float* codepot;       /* ExinPot::begin() of PwdB::codepot: [ndata][3], or NULL */
+    int32_t ndata, cp_order;    /* 4^(order + 1), Markov order */
+    float fact, z, bti, o;      /* Exinon::fact, alprm2.z, alprm2.bti, alprm2.o */
+} so_scan_params_p;
+
+/* out: 8 shorts per column n in [0, len + 1] (sig5, sig3, sigS, sigT, sigE, sigI, phs5, phs3) */
+void so_exinon_scan_p(const so_scan_params_p* sp, const uint8_t* tron, int len, int16_t* out, uint16_t* int53);
+
 /* Seq::nuc2tron (src/seq.cc:774-798): tron codes of a genomic DNA segment for protein queries;
  * codes points at at(0) and codes[-1], codes[len] must be readable (terminal residues) */
 void so_nuc2tron(const uint8_t* gencode, const uint8_t* codes, int len, uint8_t* tron);
