@@ -244,6 +244,29 @@ int  gspaln_scan_download(gspaln_scan* sc, int16_t* sig5, int16_t* sig3, uint16_
 int  gspaln_scan_get_timing(const gspaln_scan* sc, float* h2d_ms, float* kernel_ms, float* d2h_ms);
 const char* gspaln_scan_last_error(const gspaln_scan* sc);
 
+/* Protein-side scan: Exinon::intron53_p (src/codepot.cc:525-619) over a TRON segment (the output
+ * of gspaln_nuc2tron): per column the SGPT6 record -- sig5 / sig3 as above, sigS / sigT from the
+ * start- and termination-codon PSSMs (EijPat::patternI / patternT), sigE from the coding potential
+ * (ExinPot::calcScr_3, src/utilseq.cc:1423-1459: 5th-order Markov model in three phases) with the
+ * termination-codon adjustments, and the intron phases phs5 / phs3 -- plus INT53.  A tron code
+ * keeps the middle nucleotide of its codon (tnredctab, src/seq.cc:41), which is what the PSSMs and
+ * the potential read.  Limits of this version: algmode.any == 0, no branch-point PSSM, no intron
+ * potential (alprm2.Z == 0), Seq::many == 1; entries that depend on INT53 halves the reference
+ * leaves uninitialised (sig3 / phs3 of columns 0-1, sig5 / phs5 of the last two columns) use
+ * dinucleotide code 0. */
+typedef struct gspaln_scan_params_p {
+    gspaln_scan_params base;
+    gspaln_patmat patI, patT;       /* mtx may be NULL */
+    const float* codepot;           /* ExinPot::begin() of PwdB::codepot, [ndata][3]; may be NULL */
+    int32_t ndata, cp_order;        /* 4^(order + 1), Markov order */
+    float fact, z, bti, o;          /* Exinon::fact, alprm2.z, alprm2.bti, alprm2.o */
+} gspaln_scan_params_p;
+
+int  gspaln_scan_create_p(gspaln_scan** out, const gspaln_scan_params_p* prm, int device);
+/* blocking, host buffers: tron[i] == *Seq::at(i) of the TRON segment; sg and int53 hold len + 2 entries */
+int  gspaln_exinon_scan_p(gspaln_scan* sc, const uint8_t* tron, int64_t len,
+                          struct gspaln_sgpt6* sg, uint16_t* int53);
+
 /* Seq::nuc2tron (src/seq.cc:774-798, nuc2tron3 src/utilseq.cc:205-224; Seq::many == 1): the "tron"
  * residues a protein query is aligned against -- position i becomes the translation of the codon
  * (i - 1, i, i + 1) with the genetic code table `gencode` (src/utilseq.cc:38).  codes holds

@@ -249,9 +249,8 @@ void so_exinon_scan_p(const so_scan_params_p* sp, const uint8_t* tron, int len, 
         if (sp->patT.mtx) o[3] = (int16_t) (fT * patmat_nt(&sp->patT, nt, len, n - sp->patT.offset));
         if (sp->codepot) {
             /* prefE is computed over [left - 1, right + 1) and read from its second entry on, and
-             * calcScr_3 delays its output by five characters: column n sees the character n + 4 */
-            float sigE = n + 4 < len ? fE * pot[n + 4] : 0.f;
-            if (n + 4 >= len) sigE = fE * 0.f;
+             * calcScr_3 delays its output by five characters: column n sees the character n + 5 */
+            float sigE = fE * (n + 5 < len ? pot[n + 5] : 0.f);
             if (tron[n] == TRM || tron[n] == TRM2) sigE += fO;
             else if (n + 3 < len && (tron[n + 3] == TRM || tron[n + 3] == TRM2)) sigE = 0;
             o[4] = (int16_t) sigE;

@@ -7,7 +7,7 @@ Only what the DP hot path needs lives here:
   workload.py seeded synthetic problems of the BASELINE.json shapes
 """
 from .capi import FORWARD_WIP, SCOREONLY_WIP  # noqa: F401
-from .engine import (Engine, EngineError, EngineH, ExinonScan, PackedBatch, Problem,  # noqa: F401
+from .engine import (Engine, EngineError, EngineH, ExinonScan, ExinonScanP, PackedBatch, Problem,  # noqa: F401
                      ProblemH, Result, Timing, nuc2tron)
 
 __version__ = "0.1.0"

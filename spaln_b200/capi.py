@@ -35,7 +35,7 @@ EXPORTS = [
     "gspaln_queue_create", "gspaln_queue_submit", "gspaln_queue_stats", "gspaln_queue_destroy",
     "gspaln_scan_create", "gspaln_scan_destroy", "gspaln_exinon_scan", "gspaln_scan_upload",
     "gspaln_scan_run", "gspaln_scan_download", "gspaln_scan_get_timing", "gspaln_scan_last_error",
-    "gspaln_nuc2tron",
+    "gspaln_nuc2tron", "gspaln_scan_create_p", "gspaln_exinon_scan_p",
 ]
 
 
@@ -89,6 +89,12 @@ class GspalnPatMat(C.Structure):
 class GspalnScanParams(C.Structure):
     _fields_ = [("pat5", GspalnPatMat), ("pat3", GspalnPatMat), ("fS", C.c_float), ("sss", C.c_float),
                 ("any", C.c_int32), ("sig53tab", C.c_int16 * 32)]
+
+
+class GspalnScanParamsP(C.Structure):
+    _fields_ = [("base", GspalnScanParams), ("patI", GspalnPatMat), ("patT", GspalnPatMat),
+                ("codepot", C.c_void_p), ("ndata", C.c_int32), ("cp_order", C.c_int32),
+                ("fact", C.c_float), ("z", C.c_float), ("bti", C.c_float), ("o", C.c_float)]
 
 
 class GspalnHParams(C.Structure):
@@ -177,6 +183,8 @@ def load():
                                            C.POINTER(C.c_float)]
     lib.gspaln_scan_last_error.argtypes = [C.c_void_p]
     lib.gspaln_scan_last_error.restype = C.c_char_p
+    lib.gspaln_scan_create_p.argtypes = [C.POINTER(C.c_void_p), C.POINTER(GspalnScanParamsP), C.c_int]
+    lib.gspaln_exinon_scan_p.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.gspaln_nuc2tron.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_float)]
     lib.gspaln_h_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(GspalnHParams), C.c_int]
     lib.gspaln_h_destroy.argtypes = [C.c_void_p]
@@ -243,6 +251,33 @@ def make_scan_params(p: dict):
     tab = np.asarray(p["sig53tab"], np.int16)
     for i in range(32):
         sp.sig53tab[i] = int(tab[i])
+    return sp, keep
+
+
+def make_scan_params_p(p: dict):
+    """protein-side scan parameters: make_scan_params keys + patI_* / patT_*, codepot (flat
+    [ndata][3]), scan_fp = (Exinon::fact, alprm2.z, alprm2.bti, alprm2.o)"""
+    sp = GspalnScanParamsP()
+    base, keep = make_scan_params(p)
+    sp.base = base
+    for name, pm in (("patI", sp.patI), ("patT", sp.patT)):
+        if p.get(name + "_mtx") is None:
+            continue
+        meta = [int(x) for x in p[name + "_meta"]]
+        f = np.asarray(p[name + "_f"], np.float32)
+        mtx = np.ascontiguousarray(p[name + "_mtx"], np.float32)
+        pm.rows, pm.cols, pm.offset, pm.nalpha, pm.morder = meta
+        pm.tonic, pm.min_elem = float(f[0]), float(f[1])
+        pm.mtx = mtx.ctypes.data
+        keep.append(mtx)
+    if p.get("codepot") is not None:
+        cp = np.ascontiguousarray(p["codepot"], np.float32)
+        sp.codepot = cp.ctypes.data
+        sp.ndata = cp.size // 3
+        sp.cp_order = int(round(np.log(sp.ndata) / np.log(4))) - 1
+        keep.append(cp)
+    fp = np.asarray(p["scan_fp"], np.float32)
+    sp.fact, sp.z, sp.bti, sp.o = [float(x) for x in fp]
     return sp, keep
 
 

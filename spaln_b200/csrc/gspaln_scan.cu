@@ -32,10 +32,17 @@ struct DevScanParams {
     float fs;               // fS * sss (fp32 product, as the reference forms it)
     int any;
     short tab[32];
+    // protein-side scan only (intron53_p)
+    DevPat pI, pT;
+    int cp_present, ndata, cp_kk;   // coding potential: table size 4^(order + 1), order + 1
+    float fE, fT, fO;               // alprm2.z * fact, alprm2.bti * fact, -alprm2.o * fact
 };
 
 // ncredctab, src/seq.cc:31
 __constant__ unsigned char c_ncred[17] = {15, 15, 0, 1, 4, 2, 5, 6, 10, 3, 7, 8, 10, 9, 12, 13, 14};
+
+// tnredctab, src/seq.cc:41-42: the middle nucleotide of the codon a tron code stands for
+__constant__ unsigned char c_tnred[26] = {4, 4, 4, 1, 2, 0, 0, 2, 0, 0, 2, 0, 3, 3, 0, 3, 3, 1, 1, 1, 2, 0, 3, 2, 2, 0};
 
 // PatMat::calcPatMat for the window that starts at position n.  rc: reduced codes of the tile,
 // rc[i - base] for position i (0..3 = A, C, G, T; >= 4 anything else).
@@ -450,6 +457,133 @@ constexpr size_t fast_smem(int c5, int c3)
            (FAST_WORDS + 2) * sizeof(unsigned) + (FAST_WORDS + 4) * sizeof(unsigned short) + 16;
 }
 
+
+// ---------------------------------------------------------------------------
+// Protein-side scan: Exinon::intron53_p (src/codepot.cc:525-619) over a TRON segment.  Generic
+// kernel, one thread per column (the bank-replicated fast path of the DNA scan is not extended to
+// the two extra PSSMs and the coding potential yet).  All four PSSMs in shared memory, the coding
+// potential table (48 KB for the 5th-order model) through the read-only cache.
+// ---------------------------------------------------------------------------
+struct __align__(2) DevSgpt6 { short sig5, sig3, sigS, sigT, sigE, sigI; signed char phs5, phs3; };
+static_assert(sizeof(DevSgpt6) == 14 && sizeof(gspaln_sgpt6) == 14, "SGPT6 is 14 bytes (src/codepot.h:34-43)");
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+exinon_scan_p_kernel(const DevScanParams* __restrict__ gP, const float* __restrict__ gmtx /* 5 | 3 | I | T */,
+                     const float* __restrict__ codepot, const unsigned char* __restrict__ tron,
+                     long long len, DevSgpt6* __restrict__ sg, unsigned short* __restrict__ int53)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ DevScanParams P;
+    if (threadIdx.x < sizeof(DevScanParams) / 4)
+        reinterpret_cast<int*>(&P)[threadIdx.x] = reinterpret_cast<const int*>(gP)[threadIdx.x];
+    __syncthreads();
+    const int n5 = P.p5.present ? P.p5.rows * P.p5.cols : 0, n3 = P.p3.present ? P.p3.rows * P.p3.cols : 0;
+    const int nI = P.pI.present ? P.pI.rows * P.pI.cols : 0, nT = P.pT.present ? P.pT.rows * P.pT.cols : 0;
+    float* mtx5 = reinterpret_cast<float*>(smem);
+    float* mtx3 = mtx5 + n5;
+    float* mtxI = mtx3 + n3;
+    float* mtxT = mtxI + nI;
+    unsigned char* rc = reinterpret_cast<unsigned char*>(mtxT + nT);
+    for (int i = threadIdx.x; i < n5 + n3 + nI + nT; i += SCAN_THREADS) mtx5[i] = gmtx[i];
+    const int back = 64, fwd = SCAN_MAXCOLS + 8;
+    const long long t0 = (long long) blockIdx.x * SCAN_TILE;
+    const long long base = t0 - back;
+    const int span = back + SCAN_TILE + fwd;
+    for (int i = threadIdx.x; i < span; i += SCAN_THREADS) {
+        const long long pos = base + i;
+        unsigned c = 4;
+        if (pos >= 0 && pos < len) { const unsigned v = tron[pos]; c = v < 26 ? c_tnred[v] : 4; }
+        rc[i] = (unsigned char) c;
+    }
+    __syncthreads();
+    auto code2 = [&](long long i) -> unsigned {
+        if (i < 0) return 1u;
+        const unsigned c = rc[i - base];
+        return c >= 4 ? 1u : c;
+    };
+    // site classes for algmode.any == 0 (the only mode this kernel accepts): GT, GC -> 3, AT -> 2; AG -> 3, AC -> 2
+    auto cano5_of = [&](long long n) -> unsigned {      // 0 outside [0, len - 2]
+        if (n < 0 || n > len - 2) return 0u;
+        const unsigned d = (code2(n) << 2) | code2(n + 1);
+        return d == 3 ? 2u : (d == 9 || d == 11) ? 3u : 0u;
+    };
+    auto cano3_of = [&](long long n) -> unsigned {      // 0 outside [1, len]
+        if (n < 1 || n > len) return 0u;
+        const unsigned d = (code2(n - 2) << 2) | code2(n - 1);
+        return d == 1 ? 2u : d == 2 ? 3u : 0u;
+    };
+#pragma unroll 1
+    for (int u = 0; u < SCAN_PER_THREAD; ++u) {
+        const long long n = t0 + u * SCAN_THREADS + threadIdx.x;
+        if (n > len + 1) continue;
+        unsigned w = 0, d5 = 0, d3 = 0;
+        if (n <= len - 2) { d5 = (code2(n) << 2) | code2(n + 1); w |= d5 | (cano5_of(n) << 8); }
+        if (n >= 1 && n <= len) { d3 = (code2(n - 2) << 2) | code2(n - 1); w |= (d3 << 4) | (cano3_of(n) << 12); }
+        int53[n] = (unsigned short) w;
+        DevSgpt6 o;
+        o.sig5 = o.sig3 = o.sigS = o.sigT = o.sigE = o.sigI = 0;
+        // intron phases: the reference's left-to-right pass (a class > 1 site marks its right
+        // neighbour 1 and its left neighbour -1, or 2 if that one was already marked) as a local
+        // rule; adjacent sites cannot both be canonical when algmode.any == 0.  The pass runs over
+        // columns 0 .. len - 1 only.
+        auto phase = [&](unsigned here, unsigned left, unsigned right, bool left_ok, bool right_ok) -> int {
+            if (right_ok && right > 1) return (left_ok && left > 1) ? 2 : -1;
+            if (left_ok && left > 1) return 1;
+            return here ? 0 : -2;
+        };
+        o.phs5 = (signed char) phase(n < len ? cano5_of(n) : 0u, cano5_of(n - 1), cano5_of(n + 1),
+                                     n - 1 >= 0 && n - 1 < len, n + 1 < len);
+        o.phs3 = (signed char) phase(n < len ? cano3_of(n) : 0u, cano3_of(n - 1), cano3_of(n + 1),
+                                     n - 1 >= 0 && n - 1 < len, n + 1 < len);
+        if (n < len) {
+            short s5 = 0, s3 = 0;
+            if (P.p5.present) s5 = (short) __fmul_rn(P.fs, patmat_at(P.p5, mtx5, rc, base, len, n - P.p5.offset));
+            if (P.p3.present) s3 = (short) __fmul_rn(P.fs, patmat_at(P.p3, mtx3, rc, base, len, n - P.p3.offset));
+            o.sig5 = (short) (s5 + P.tab[d5]);
+            o.sig3 = (short) (s3 + P.tab[16 + d3]);
+            if (P.pI.present) o.sigS = (short) __fmul_rn(P.fT, patmat_at(P.pI, mtxI, rc, base, len, n - P.pI.offset));
+            if (P.pT.present) o.sigT = (short) __fmul_rn(P.fT, patmat_at(P.pT, mtxT, rc, base, len, n - P.pT.offset));
+            if (P.cp_present) {
+                // ExinPot::calcScr_3 at the character n + 5: needs cp_kk valid nucleotides in a row
+                // ending there; the k-mer words of the last three characters start at the last
+                // invalid character (or the segment start) and are taken modulo the table size
+                float val = 0.f;
+                const long long t = n + 5;
+                if (t < len) {
+                    const int look = P.cp_kk + 2;
+                    int run = 0;                    // valid characters ending at t (capped)
+                    while (run < look && t - run >= 0 && rc[t - run - base] < 4) ++run;
+                    const bool reset_inside = run < look && t - run >= 0;    // an invalid character stopped the run
+                    if (run >= P.cp_kk) {
+                        // words at t - 2, t - 1, t: accumulate from the start of the run (or of the
+                        // look-back window, which holds at least cp_kk characters before t - 2)
+                        int wd[3];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const long long e = t - 2 + j;
+                            long long s0 = reset_inside ? t - run + 1 : e - (P.cp_kk - 1);
+                            if (s0 < e - (P.cp_kk - 1)) s0 = e - (P.cp_kk - 1);
+                            if (s0 < 0) s0 = 0;
+                            int wv = 0;
+                            for (long long i = s0; i <= e; ++i) wv = (4 * wv + rc[i - base]) % P.ndata;
+                            wd[j] = wv;
+                        }
+                        val = __fadd_rn(val, __ldg(codepot + 3 * wd[0] + 2));
+                        val = __fadd_rn(val, __ldg(codepot + 3 * wd[1]));
+                        val = __fadd_rn(val, __ldg(codepot + 3 * wd[2] + 1));
+                    }
+                }
+                float sigE = __fmul_rn(P.fE, val);
+                const unsigned here = tron[n];
+                if (here == 25 || here == 24) sigE = __fadd_rn(sigE, P.fO);             // TRM, TRM2
+                else if (n + 3 < len) { const unsigned nx = tron[n + 3]; if (nx == 25 || nx == 24) sigE = 0.f; }
+                o.sigE = (short) sigE;
+            }
+        }
+        sg[n] = o;
+    }
+}
+
 }   // namespace
 
 struct gspaln_scan {
@@ -461,6 +595,10 @@ struct gspaln_scan {
     DevBuf<unsigned char> d_codes;
     DevBuf<short> d_sig5, d_sig3;
     DevBuf<unsigned short> d_int53;
+    DevBuf<float> d_mtxp, d_codepot;        // protein-side scan: PSSMs 5 | 3 | I | T, coding potential
+    DevBuf<DevSgpt6> d_sg;
+    bool protein = false;
+    size_t smem_p = 0;
     DevScanParams hP;
     size_t smem = 0;
     bool fast = false;              // both PSSMs have the stock shape: bank-replicated kernel
@@ -497,6 +635,7 @@ void gspaln_scan_destroy(gspaln_scan* sc)
     cudaSetDevice(sc->device);
     sc->d_prm.release(); sc->d_mtx5.release(); sc->d_mtx3.release(); sc->d_codes.release();
     sc->d_sig5.release(); sc->d_sig3.release(); sc->d_int53.release();
+    sc->d_mtxp.release(); sc->d_codepot.release(); sc->d_sg.release();
     for (auto& e : sc->ev) if (e) cudaEventDestroy(e);
     if (sc->stream) cudaStreamDestroy(sc->stream);
     delete sc;
@@ -617,6 +756,83 @@ int gspaln_exinon_scan(gspaln_scan* sc, const uint8_t* codes, int64_t len,
     if (rc == GSPALN_OK) rc = gspaln_scan_run(sc);
     if (rc == GSPALN_OK) rc = gspaln_scan_download(sc, sig5, sig3, int53);
     return rc;
+}
+
+int gspaln_scan_create_p(gspaln_scan** out, const gspaln_scan_params_p* prm, int device)
+{
+    if (!out || !prm) return GSPALN_EINVAL;
+    *out = nullptr;
+    if (prm->base.any != 0 || !pat_ok(prm->patI) || !pat_ok(prm->patT) ||
+        (prm->codepot && (prm->ndata < 4 || prm->cp_order < 0 || prm->cp_order > 5 ||
+                          prm->ndata != (1 << (2 * (prm->cp_order + 1))))))
+        return GSPALN_EINVAL;
+    gspaln_scan* sc = nullptr;
+    int rc = gspaln_scan_create(&sc, &prm->base, device);
+    if (rc != GSPALN_OK) return rc;
+    DevScanParams& P = sc->hP;
+    auto cp = [](DevPat& d, const gspaln_patmat& s) {
+        d.present = s.mtx != nullptr;
+        d.rows = s.rows; d.cols = s.cols; d.offset = s.offset; d.nalpha = s.nalpha; d.morder = s.morder;
+        d.tonic = s.tonic; d.min_elem = s.min_elem;
+    };
+    cp(P.pI, prm->patI); cp(P.pT, prm->patT);
+    P.cp_present = prm->codepot != nullptr;
+    P.ndata = prm->ndata; P.cp_kk = prm->cp_order + 1;
+    P.fE = prm->z * prm->fact; P.fT = prm->bti * prm->fact; P.fO = -prm->o * prm->fact;
+    const gspaln_patmat* pats[4] = {&prm->base.pat5, &prm->base.pat3, &prm->patI, &prm->patT};
+    std::vector<float> all;
+    for (const gspaln_patmat* pm : pats)
+        if (pm->mtx) all.insert(all.end(), pm->mtx, pm->mtx + (size_t) pm->rows * pm->cols);
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = sc->d_mtxp.reserve(all.size() + 1);
+    if (e == cudaSuccess && !all.empty())
+        e = cudaMemcpy(sc->d_mtxp.p, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && prm->codepot) {
+        e = sc->d_codepot.reserve((size_t) 3 * prm->ndata);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(sc->d_codepot.p, prm->codepot, (size_t) 3 * prm->ndata * sizeof(float), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(sc->d_prm.p, &P, sizeof(P), cudaMemcpyHostToDevice);
+    sc->smem_p = all.size() * sizeof(float) + 64 + SCAN_TILE + SCAN_MAXCOLS + 8 + 16;
+    if (e == cudaSuccess && sc->smem_p > 48 * 1024)
+        e = cudaFuncSetAttribute(exinon_scan_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sc->smem_p);
+    if (e != cudaSuccess) { cudaGetLastError(); gspaln_scan_destroy(sc); return GSPALN_ECUDA; }
+    sc->protein = true;
+    *out = sc;
+    return GSPALN_OK;
+}
+
+int gspaln_exinon_scan_p(gspaln_scan* sc, const uint8_t* tron, int64_t len, gspaln_sgpt6* sg, uint16_t* int53)
+{
+    if (!sc || !sc->protein || len < 0 || !sg || !int53 || (len && !tron)) return GSPALN_EINVAL;
+    SCK(cudaSetDevice(sc->device));
+    if (sc->d_codes.reserve((size_t) len + 16) != cudaSuccess || sc->d_sg.reserve((size_t) len + 2) != cudaSuccess ||
+        sc->d_int53.reserve((size_t) len + 2) != cudaSuccess) {
+        cudaGetLastError();
+        return sfail(sc, GSPALN_ENOMEM, "device allocation");
+    }
+    SCK(cudaEventRecord(sc->ev[0], sc->stream));
+    if (len) SCK(cudaMemcpyAsync(sc->d_codes.p, tron, (size_t) len, cudaMemcpyHostToDevice, sc->stream));
+    SCK(cudaEventRecord(sc->ev[1], sc->stream));
+    const long long cols = len + 2;
+    const unsigned grid = (unsigned) ((cols + SCAN_TILE - 1) / SCAN_TILE);
+    for (int rep = 0; rep < 2; ++rep) {         // the second run is the timed one
+        SCK(cudaEventRecord(sc->ev[2], sc->stream));
+        exinon_scan_p_kernel<<<grid, SCAN_THREADS, sc->smem_p, sc->stream>>>(
+            sc->d_prm.p, sc->d_mtxp.p, sc->d_codepot.p, sc->d_codes.p, len, sc->d_sg.p, sc->d_int53.p);
+        SCK(cudaGetLastError());
+        SCK(cudaEventRecord(sc->ev[3], sc->stream));
+    }
+    SCK(cudaEventRecord(sc->ev[4], sc->stream));
+    SCK(cudaMemcpyAsync(sg, sc->d_sg.p, (size_t) cols * sizeof(DevSgpt6), cudaMemcpyDeviceToHost, sc->stream));
+    SCK(cudaMemcpyAsync(int53, sc->d_int53.p, (size_t) cols * sizeof(unsigned short), cudaMemcpyDeviceToHost, sc->stream));
+    SCK(cudaEventRecord(sc->ev[5], sc->stream));
+    SCK(cudaStreamSynchronize(sc->stream));
+    cudaEventElapsedTime(&sc->h2d_ms, sc->ev[0], sc->ev[1]);
+    cudaEventElapsedTime(&sc->kernel_ms, sc->ev[2], sc->ev[3]);
+    cudaEventElapsedTime(&sc->d2h_ms, sc->ev[4], sc->ev[5]);
+    sc->len = len;
+    return GSPALN_OK;
 }
 
 int gspaln_nuc2tron(int device, const uint8_t* gencode, const uint8_t* codes, int64_t len,

@@ -547,6 +547,30 @@ class ExinonScan:
         return {"h2d_ms": a.value, "kernel_ms": b.value, "d2h_ms": c.value}
 
 
+class ExinonScanP(ExinonScan):
+    """Protein-side scan (Exinon::intron53_p over a TRON segment): SGPT6 records + INT53"""
+
+    def __init__(self, params: dict, device: int = 0):
+        self.lib = capi.load()
+        self._sp, self._keep = capi.make_scan_params_p(params)
+        self._h = C.c_void_p()
+        rc = self.lib.gspaln_scan_create_p(C.byref(self._h), C.byref(self._sp), device)
+        if rc != 0:
+            raise EngineError(f"gspaln_scan_create_p failed ({rc}): no usable CUDA device or parameters "
+                              "outside this version's limits; the scan has no CPU fallback")
+        self._len = 0
+
+    def scan(self, tron):
+        """tron[i] == *Seq::at(i); returns (SGPT6 records (capi.SGPT6_DTYPE, len + 2), int53)"""
+        c = np.ascontiguousarray(tron, np.uint8)
+        sg = np.zeros(len(c) + 2, capi.SGPT6_DTYPE)
+        i53 = np.zeros(len(c) + 2, np.uint16)
+        self._check(self.lib.gspaln_exinon_scan_p(self._h, c.ctypes.data, len(c), sg.ctypes.data,
+                                                  i53.ctypes.data), "gspaln_exinon_scan_p")
+        self._len = len(c)
+        return sg, i53
+
+
 def nuc2tron(gencode, codes_with_ends, device: int = 0):
     """Seq::nuc2tron on the device (src/seq.cc:774-798): codes_with_ends = at(-1 .. len) of a DNA
     segment; returns (tron codes of at(0 .. len - 1), kernel ms).  No CPU fallback."""

@@ -207,6 +207,49 @@ def exinon_scan(p: dict, codes):
     return {"sig5": s5, "sig3": s3, "int53": i53}
 
 
+class SoScanParamsP(C.Structure):
+    _fields_ = [("base", SoScanParams), ("patI", SoPatMat), ("patT", SoPatMat), ("codepot", C.c_void_p),
+                ("ndata", C.c_int32), ("cp_order", C.c_int32), ("fact", C.c_float), ("z", C.c_float),
+                ("bti", C.c_float), ("o", C.c_float)]
+
+
+def exinon_scan_p(p: dict, tron):
+    """Exinon::intron53_p over a whole TRON segment (tron[i] == *Seq::at(i)).  p: as for exinon_scan
+    plus patI_* / patT_*, codepot (flat [ndata][3] floats), scan_fp = (fact, z, bti, o).
+    Returns the SGPT6 table as (len + 2, 8) int16 and int53."""
+    sp = SoScanParamsP()
+    base = make_scan_params(p)
+    sp.base = base
+    keep = [base]
+    for name, pm in (("patI", sp.patI), ("patT", sp.patT)):
+        if p.get(name + "_mtx") is None:
+            continue
+        meta = [int(x) for x in p[name + "_meta"]]
+        f = np.asarray(p[name + "_f"], np.float32)
+        mtx = np.ascontiguousarray(p[name + "_mtx"], np.float32)
+        pm.rows, pm.cols, pm.offset, pm.nalpha, pm.morder = meta
+        pm.tonic, pm.min_elem = float(f[0]), float(f[1])
+        pm.mtx = mtx.ctypes.data
+        keep.append(mtx)
+    if p.get("codepot") is not None:
+        cp = np.ascontiguousarray(p["codepot"], np.float32)
+        sp.codepot = cp.ctypes.data
+        sp.ndata = cp.size // 3
+        sp.cp_order = int(round(np.log(sp.ndata) / np.log(4))) - 1
+        keep.append(cp)
+    fp = np.asarray(p["scan_fp"], np.float32)
+    sp.fact, sp.z, sp.bti, sp.o = [float(x) for x in fp]
+    c = np.ascontiguousarray(tron, np.uint8)
+    n = len(c)
+    buf = np.concatenate([c, np.zeros(8, np.uint8)])
+    out = np.zeros((n + 2, 8), np.int16)
+    i53 = np.zeros(n + 2, np.uint16)
+    lib().so_exinon_scan_p.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib().so_exinon_scan_p.restype = None
+    lib().so_exinon_scan_p(C.byref(sp), buf.ctypes.data, n, out.ctypes.data, i53.ctypes.data)
+    return {"sgpt6": out, "int53": i53}
+
+
 def nuc2tron(gencode, codes_with_ends):
     """codes_with_ends: at(-1 .. len) (len + 2 bytes); returns the tron codes of at(0 .. len - 1)"""
     c = np.ascontiguousarray(codes_with_ends, np.uint8)

@@ -121,6 +121,13 @@ class Reference:
                 p[name] = int(pb[i])
         return p
 
+    def codepot(self):
+        """PwdB::codepot table (ExinPot::begin(), dsize() floats) or None"""
+        buf = np.zeros(1 << 16, np.float32)
+        self.lib.ref_get_codepot.argtypes = [C.c_void_p, C.c_int]
+        n = self.lib.ref_get_codepot(buf.ctypes.data, buf.size)
+        return buf[:n].copy() if n > 0 else None
+
     def gencode(self):
         out = np.zeros(64, np.uint8)
         self.lib.ref_get_gencode.argtypes = [C.c_void_p]
@@ -266,6 +273,17 @@ class RefTask:
         self.lib.ref_task_scan_factors(self.h, f.ctypes.data, i.ctypes.data)
         return {"fS": np.float32(f[0]), "sss": np.float32(f[1]), "tonic5": np.float32(f[2]),
                 "tonic3": np.float32(f[3]), "any": int(i[0]), "cmpc": int(i[1]), "many": int(i[2])}
+
+    def scan_factors_p(self):
+        """protein-side scan (Exinon::intron53_p): factors and which potentials exist"""
+        f = np.zeros(8, np.float32)
+        i = np.zeros(8, np.int32)
+        self.lib.ref_task_scan_factors_p.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib.ref_task_scan_factors_p(self.h, f.ctypes.data, i.ctypes.data)
+        return {"fact": np.float32(f[0]), "z": np.float32(f[1]), "Z": np.float32(f[2]), "bti": np.float32(f[3]),
+                "bp_factor": np.float32(f[4]), "o": np.float32(f[5]), "tonicB": np.float32(f[6]),
+                "codepot": int(i[0]), "ndata": int(i[1]), "dsize": int(i[2]), "exonpot": int(i[3]),
+                "intnpot": int(i[4]), "DvsP": int(i[5]), "maxb3d": int(i[6])}
 
     def scalar(self, lw, up, cap=1 << 16):
         """Aln2s1::trcbkalignS_ng forced onto its scalar branch (forwardS_ng + Vmf), raw Mfile corners"""

@@ -117,3 +117,38 @@ def test_nuc2tron_matches_reference_and_oracle(oracle):
     gc2[[56, 58]] = 20
     codes = np.concatenate([[0], _random_codes(rng, 5000, amb=0.0), [0]]).astype(np.uint8)
     assert np.array_equal(nuc2tron(gc2, codes)[0], oracle.nuc2tron(gc2, codes))
+
+
+def _sg_table(sg):
+    """SGPT6 records -> (n, 8) int16 table in the fixture's column order"""
+    return np.stack([sg[k].astype(np.int16) for k in ("sig5", "sig3", "sigS", "sigT", "sigE", "sigI", "phs5", "phs3")], 1)
+
+
+def test_protein_scan_matches_reference_and_oracle(oracle):
+    """gspaln_exinon_scan_p (Exinon::intron53_p on a TRON segment) against the reference's SGPT6
+    tables (golden) and against the oracle on seeded segments incl. ambiguity codes, stop codons
+    and lengths around the CTA tile"""
+    from spaln_b200 import ExinonScanP, nuc2tron
+    from test_oracle_scan import load_scan_p, sgpt6_equal
+    prm, segs = load_scan_p()
+    sc = ExinonScanP(prm, device=0)
+    for i, s in enumerate(segs):
+        tron = s["tron"][1:-1]
+        sg, i53 = sc.scan(tron)
+        assert sgpt6_equal(_sg_table(sg), s["sgpt6"], len(tron)), i
+    gc = np.load(golden_io.GOLDEN_DIR / "nuc2tron.npz")["gencode"]
+    rng = np.random.default_rng(77)
+    for n in (0, 1, 2, 5, 6, 7, 8, 30, 1023, 1024, 1025, 50_001):
+        codes = np.concatenate([[0], _random_codes(rng, n, amb=0.01), [0]]).astype(np.uint8)
+        tron = oracle.nuc2tron(gc, codes)
+        sg, i53 = sc.scan(tron)
+        o = oracle.exinon_scan_p(prm, tron)
+        assert np.array_equal(_sg_table(sg), o["sgpt6"]), n
+        assert np.array_equal(i53, o["int53"]), n
+    sc.close()
+    # parameters outside this version's limits are refused, not approximated
+    from spaln_b200 import EngineError
+    bad = dict(prm)
+    bad["any"] = 2
+    with pytest.raises(EngineError):
+        ExinonScanP(bad, device=0)

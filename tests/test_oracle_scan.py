@@ -46,3 +46,37 @@ def test_oracle_nuc2tron_matches_reference(oracle):
         assert np.array_equal(oracle.nuc2tron(z["gencode"], d), t[1:-1]), i
         seen |= set(d.tolist())
     assert len(seen) >= 16
+
+
+SGPT6_NAMES = ["sig5", "sig3", "sigS", "sigT", "sigE", "sigI", "phs5", "phs3"]
+
+
+def load_scan_p():
+    z = np.load(golden_io.GOLDEN_DIR / "scan_p.npz")
+    prm = {k[4:]: (z[k] if z[k].ndim else z[k].item()) for k in z.files if k.startswith("prm_")}
+    segs = [{"tron": z[f"s{i}_tron"], "sgpt6": z[f"s{i}_sgpt6"], "int53": z[f"s{i}_int53"]} for i in range(int(z["n"]))]
+    return prm, segs
+
+
+def sgpt6_equal(got, want, L):
+    """got / want: (len + 2, 8) tables.  Entries that depend on the INT53 halves the reference never
+    writes (column 0's 3' half, column len - 1's 5' half: uninitialised memory) are skipped."""
+    for c, nm in enumerate(SGPT6_NAMES):
+        lo, hi = {"sig3": (1, L), "sig5": (0, L - 1), "phs3": (2, L), "phs5": (0, L - 2)}.get(nm, (0, L))
+        if not np.array_equal(got[lo:hi, c], want[lo:hi, c]):
+            return False
+    return True
+
+
+def test_oracle_protein_scan_matches_reference_tables(oracle):
+    """Exinon::intron53_p (four PSSMs on tron codes, ExinPot::calcScr_3, termination-codon rules,
+    intron phases) against the SGPT6 tables of the unmodified reference"""
+    prm, segs = load_scan_p()
+    assert len(segs) >= 8 and prm["codepot"].size == 3 * 4096
+    for i, sg in enumerate(segs):
+        tron = sg["tron"][1:-1]
+        o = oracle.exinon_scan_p(prm, tron)
+        assert sgpt6_equal(o["sgpt6"], sg["sgpt6"], len(tron)), i
+        L = len(tron)
+        assert np.array_equal(o["int53"][0:L - 1] & 0x0f0f, sg["int53"][0:L - 1] & 0x0f0f), i
+        assert np.array_equal(o["int53"][1:L + 1] & 0xf0f0, sg["int53"][1:L + 1] & 0xf0f0), i
