@@ -366,9 +366,34 @@ def scan_leg(prm, with_cpu):
                        "roofline": {"bound": "hbm", "bytes_per_position": 2.0, "achieved": 2.0 * n / t_ms / 1e6,
                                     "peak": peak, "unit": "GB/s", "frac": 2.0 * n / t_ms / 1e6 / peak,
                                     "kernel": "nuc2tron_kernel"}}
+    # ... and the protein-side scan of the tron segment (Exinon::intron53_p): SGPT6 records + INT53
+    from spaln_b200 import ExinonScanP
+    zp = np.load(ROOT / "tests" / "golden" / "scan_p.npz")
+    prm_p = {k[4:]: (zp[k] if zp[k].ndim else zp[k].item()) for k in zp.files if k.startswith("prm_")}
+    scp = ExinonScanP(prm_p, device=0)
+    t0 = time.perf_counter()
+    sg, i53p = scp.scan(tron)
+    p_e2e = time.perf_counter() - t0
+    p_ms = scp.timing()["kernel_ms"]
+    scp.close()
+    out["protein_scan"] = {"note": "Exinon::intron53_p over the 100 Mb tron segment (4 PSSMs, 5th-order coding "
+                                   "potential, phases): generic one-thread-per-column kernel",
+                           "kernel_ms": p_ms, "gnt_per_s": n / p_ms / 1e6, "e2e_ms": 1e3 * p_e2e,
+                           "roofline": {"bound": "hbm", "bytes_per_position": 17.0, "achieved": 17.0 * n / p_ms / 1e6,
+                                        "peak": peak, "unit": "GB/s", "frac": 17.0 * n / p_ms / 1e6 / peak,
+                                        "kernel": "exinon_scan_p_kernel"}}
     if with_cpu:
         sys.path.insert(0, str(ROOT / "tests"))
         import oracle_harness
+        kp = 5_000_000
+        t0 = time.perf_counter()
+        op = oracle_harness.exinon_scan_p(prm_p, tron[:kp])
+        cpu_p = time.perf_counter() - t0
+        names = ("sig5", "sig3", "sigS", "sigT", "sigE", "sigI", "phs5", "phs3")
+        okp = all(np.array_equal(sg[nm][: kp - 64].astype(np.int16), op["sgpt6"][: kp - 64, c])
+                  for c, nm in enumerate(names))
+        out["protein_scan"]["cpu_baseline"] = {"value": kp / cpu_p / 1e9, "unit": "Gnt/s", "cores": 1, "kind": "port",
+                                               "sample": "first 5 Mb", "parity_on_sample": bool(okp)}
         kk = 20_000_000
         t0 = time.perf_counter()
         ot = oracle_harness.nuc2tron(z["gencode"], ends[: kk + 2])
