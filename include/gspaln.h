@@ -58,11 +58,14 @@ enum {                          /* gspaln_task.kind */
     GSPALN_HIRSCHBERG_WIP = 2,  /* SimdAln2s1::hirschbergS1_wip(Dim10* cpos, n_imd)
                                    (src/fwd2s1_wip_simd.h:476-864): score, crossing records
                                    and the narrowed sequence ranges; global / semi-global only */
-    GSPALN_FORWARD_NG = 3       /* Aln2s1::trcbkalignS_ng on its scalar branch: forwardS_ng
+    GSPALN_FORWARD_NG = 3,      /* Aln2s1::trcbkalignS_ng on its scalar branch: forwardS_ng
                                    (src/fwd2s1.cc:217-444) + Vmf::traceback + end adjustment
                                    (1667-1710), exact intron scoring.  The reference runs it for
                                    blocks with fewer than 8 query rows.  Needs
                                    gspaln_set_ng_tables() and gspaln_task.int53. */
+    GSPALN_SCOREALONE_NG = 4    /* Aln2s1::scorealoneS_ng (src/fwd2s1.cc:1163-1336): the scalar
+                                   score-only kernel HomScoreS_ng runs under -A0 and for queries
+                                   shorter than 4 residues (src/fwd2s1.cc:2704-2705).  Same tables. */
 };
 
 enum {                          /* gspaln_result.status */

@@ -38,6 +38,7 @@ int shim_s1_kernel(const Seq** seqs, const PwdB* pwd, int lw, int up,
 int shim_s1_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up,
 	int* score, int* skl_out, int cap, double* seconds);
 int shim_s1_nelem();
+int shim_s1_scorealone(const Seq** seqs, const PwdB* pwd, int lw, int up);
 int shim_s1_scalar(const Seq** seqs, const PwdB* pwd, int lw, int up,
 	int* score, int* skl_out, int cap, double* seconds);
 int shim_h1_udh(const Seq** seqs, const PwdB* pwd, int lw, int up, int n_imd, int* score,
@@ -422,6 +423,12 @@ int ref_get_codepot(float* out, int cap)
 	int n = g_pwd->codepot->dsize();
 	for (int i = 0; i < n && i < cap; ++i) out[i] = g_pwd->codepot->begin()[i];
 	return n;
+}
+
+int ref_task_scorealone(void* h, int lw, int up)
+{
+	RefTask* t = (RefTask*) h;
+	return shim_s1_scorealone((const Seq**) t->sqs, g_pwd, lw, up);
 }
 
 int ref_task_scalar(void* h, int lw, int up, int* score, int* skl_out, int cap, double* seconds)

@@ -133,6 +133,15 @@ int shim_s1_scalar(const Seq** seqs, const PwdB* pwd, int lw, int up,
 	return n;
 }
 
+// the scalar score-only kernel Aln2s1::scorealoneS_ng (src/fwd2s1.cc:1163-1336), what
+// HomScoreS_ng runs under -A0 and for queries shorter than 4 residues (src/fwd2s1.cc:2704-2705)
+int shim_s1_scorealone(const Seq** seqs, const PwdB* pwd, int lw, int up)
+{
+	WINDOW wdw = {lw, up, up - lw + 3};
+	Aln2s1 alnv(seqs, pwd);
+	return (int) alnv.scorealoneS_ng(wdw);
+}
+
 // same call as shim_s1_kernel(kind 0 | 1) but through the gspaln adapter (GPU)
 int shim_s1_adapter(const Seq** seqs, const PwdB* pwd, int lw, int up,
 	int kind, int device, int* score, int* skl_out, int cap)

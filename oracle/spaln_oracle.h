@@ -120,6 +120,9 @@ void so_exinon_scan_p(const so_scan_params_p* sp, const uint8_t* tron, int len, 
  * codes points at at(0) and codes[-1], codes[len] must be readable (terminal residues) */
 void so_nuc2tron(const uint8_t* gencode, const uint8_t* codes, int len, uint8_t* tron);
 
+/* Aln2s1::scorealoneS_ng (src/fwd2s1.cc:1163-1336): the scalar score-only kernel */
+int so_scorealone_ng(const so_params* p, const so_task* t, int32_t* score);
+
 /* Aln2s1::lspS_ng driver (trace-back vs multi-intermediate Hirschberg dispatch,
  * src/fwd2s1.cc:1801-1897) */
 typedef struct {

@@ -262,3 +262,151 @@ int so_trcbk_ng(const so_params* p, const so_task* t, int32_t* score, int32_t* s
     free(buf); free(dbuf); free(vmf.rec);
     return cnt;
 }
+
+/* Aln2s1::scorealoneS_ng (src/fwd2s1.cc:1163-1336) with sinitS_ng / slastS_ng (1112-1161): the
+ * scalar score-only kernel (HomScoreS_ng under -A0 and for queries shorter than 4 residues,
+ * src/fwd2s1.cc:2704-2705).  Same recurrences as forwardS_ng without path records, but with its
+ * own tie rules (strict comparisons where forwardS_ng accepts ties, ties accepted in the donor
+ * list) and its own initial rows.  Returns 0, -1 allocation failure, -3 missing tables. */
+int so_scorealone_ng(const so_params* p, const so_task* t, int32_t* score)
+{
+    const int width = t->up - t->lw + 3;
+    *score = NEVSEL32;
+    if (width < 3) return 0;
+    if (!p->penalty || !p->sig53tab || !t->int53 || t->b_right - t->b_left >= p->n_penalty) return -3;
+    const int dagp = p->noll == 3;
+    const int nod = 2 * p->noll - 1;
+    const int gop_k[3] = { 0, p->gop, p->lgop };
+    const int LocalL = p->local && t->a_exgl && t->b_exgl;
+    const int LocalR = p->local && t->a_exgr && t->b_exgr;
+    const int a_left = t->a_left, a_right = t->a_right, b_left = t->b_left, b_right = t->b_right;
+    const int lw = t->lw, up = t->up;
+    int* buf = (int*) malloc((size_t) 3 * width * sizeof(int));
+    if (!buf) return -1;
+    for (int i = 0; i < 3 * width; ++i) buf[i] = NEVSEL32;
+    int* H = buf - lw + 1;
+    int* F = H + width;
+    int* F2 = F + width;
+    /* ---- sinitS_ng ---- */
+    {
+        int r = b_left - a_left, rr = b_right - a_left;
+        H[r] = 0;
+        if (t->a_exgl) {
+            if (up < rr) rr = up;
+            for (int q = r + 1; q <= rr; ++q) H[q] = 0;
+        }
+        rr = b_left - a_right;
+        if (lw > rr) rr = lw;
+        if (t->b_exgl) {
+            for (int q = rr; q < r; ++q) H[q] = 0;
+        } else {
+            for (int i = 1; --r >= rr; ++i) {
+                H[r] = H[r + 1];
+                if (i == 1) { H[r] += p->gappen1; F[r] = H[r]; }
+                else { F[r] = F[r + 1]; H[r] += gap_ext(p, i); F[r] += p->gep; }
+            }
+        }
+    }
+    int maxh = NEVSEL32;
+    int m = a_left;
+    if (!t->a_exgl) --m;
+    for (++m; m <= a_right; ++m) {
+        int n = (m - 1) + lw > b_left ? (m - 1) + lw : b_left;
+        const int n9 = (m - 1) + up + 1 < b_right ? (m - 1) + up + 1 : b_right;
+        const int32_t* qprof = p->simmtx + (size_t) t->a[m > 0 ? m - 1 : 0] * p->simdim;
+        int e1 = NEVSEL32, e2 = NEVSEL32;
+        struct { int val, dir, jnc; } rcd[NG_NCAND + 1];
+        int idx[NG_NCAND + 1];
+        for (int l = 0; l <= NG_NCAND; ++l) { rcd[l].val = NEVSEL32; rcd[l].dir = rcd[l].jnc = 0; idx[l] = l; }
+        int ncand = -1, psp = 0;
+        while (++n <= n9) {
+            const int r = n - m;
+            int black = NEVSEL32;
+            int* hf[5] = { &H[r], &e1, &F[r], &e2, dagp ? &F2[r] : &black };
+            int* h = hf[0];
+            int* mx = h;
+            if (m != a_left) {
+                *h += qprof[t->b[n - 1]];
+                int x = H[r + 1] + p->gop;
+                F[r] = (x > F[r + 1] ? x : F[r + 1]) + p->gep;
+                if (F[r] > *mx) mx = &F[r];
+                if (dagp) {
+                    x = H[r + 1] + p->lgop;
+                    F2[r] = (x > F2[r + 1] ? x : F2[r + 1]) + p->lgep;
+                    if (F2[r] > *mx) mx = &F2[r];
+                }
+            }
+            {
+                int x = H[r - 1] + p->gop;
+                const int prev_psp = psp;
+                if (x > e1) { e1 = x; psp = psp ? 1 : 0; }
+                else psp &= 1;
+                e1 += p->gep;
+                if (e1 > *mx) mx = &e1;
+                if (dagp) {
+                    x = H[r - 1] + p->lgop;
+                    if (x > e2) { e2 = x; if (prev_psp) psp |= 2; }
+                    else psp |= prev_psp & 2;
+                    e2 += p->lgep;
+                    if (e2 > *mx) mx = &e2;
+                }
+            }
+            if (cano3(t, n)) {
+                int top[5] = { 0, 0, 0, 0, 0 };
+                for (int l = 0; l <= ncand; ++l) {
+                    const int j = idx[l];
+                    if (n - rcd[j].jnc < p->llmt) continue;
+                    const int x = rcd[j].val + spjscr(p, t, rcd[j].jnc, n);
+                    if (x > *hf[rcd[j].dir]) { *hf[rcd[j].dir] = x; top[rcd[j].dir] = 1; }
+                }
+                for (int k = 0; k < nod; ++k) {
+                    if (!top[k]) continue;
+                    psp |= ng_psp_bit[k];
+                    if (*hf[k] > *mx) mx = hf[k];
+                }
+            }
+            const int y = *h;
+            if (h != mx) *h = *mx;
+            else if (LocalR && y > maxh) maxh = y;
+            if (LocalL && *h < 0) *h = 0;
+            int hd = 0;
+            while (mx != hf[hd]) ++hd;
+            if (cano5(t, n)) {
+                const int sigJ = t->sig5[n];
+                for (int k = hd == 0 ? 0 : 1; k < nod; ++k) {
+                    if (psp & ng_psp_bit[k]) continue;
+                    if (k != hd) {
+                        int z = *mx;
+                        if (hd == 0 || (k - hd) % 2) z += gop_k[k / 2];
+                        if (*hf[k] <= z) continue;
+                    }
+                    const int x = *hf[k] + sigJ;
+                    int l = ncand < NG_NCAND ? ++ncand : NG_NCAND;
+                    while (--l >= 0) {
+                        if (x >= rcd[idx[l]].val) { int s = idx[l]; idx[l] = idx[l + 1]; idx[l + 1] = s; }
+                        else break;
+                    }
+                    if (++l < NG_NCAND) { rcd[idx[l]].val = x; rcd[idx[l]].jnc = n; rcd[idx[l]].dir = k; }
+                    else --ncand;
+                }
+            }
+        }
+    }
+    if (!LocalR) {
+        /* slastS_ng */
+        const int r9 = b_right - a_right;
+        int mxv = H[r9];
+        if (t->b_exgr) {
+            const int rw = up < b_right - a_left ? up : b_right - a_left;
+            for (int r = rw; r > r9; --r) if (H[r] > mxv) mxv = H[r];
+        }
+        if (t->a_exgr) {
+            const int rw = lw > b_left - a_right ? lw : b_left - a_right;
+            for (int r = rw; r < r9; ++r) if (H[r] > mxv) mxv = H[r];
+        }
+        maxh = mxv;
+    }
+    *score = maxh;
+    free(buf);
+    return 0;
+}

@@ -23,6 +23,7 @@ FORWARD_WIP = 0
 SCOREONLY_WIP = 1
 HIRSCHBERG_WIP = 2
 FORWARD_NG = 3          # scalar exact-ILD kernel (Aln2s1::forwardS_ng + Vmf trace-back)
+SCOREALONE_NG = 4       # scalar score-only kernel (Aln2s1::scorealoneS_ng)
 END_OF_ULK = 2 ** 31 - 1 - 2
 
 EXPORTS = [

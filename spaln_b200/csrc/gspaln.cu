@@ -62,6 +62,9 @@ struct gspaln_ctx {
     bool ng_ready = false;
     int n_ng = 0, grid_run_ng = 0, ng_rec_cap = 0;
     size_t ng_slab = 0, ng_width = 0;
+    DevBuf<int> d_ngs;              // score-only scalar kernel: three int rows per thread
+    int n_ngs = 0, grid_run_ngs = 0;
+    size_t ngs_width = 0;
     PinBuf<DevTask> h_tasks;
     PinBuf<int> h_order;
     PinBuf<unsigned char> h_apool;
@@ -312,9 +315,9 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         const gspaln_task& t = tasks[i];
         if (t.a_right < t.a_left || t.b_right < t.b_left || t.up - t.lw + 3 < 0 ||
             (t.kind != GSPALN_FORWARD_WIP && t.kind != GSPALN_SCOREONLY_WIP && t.kind != GSPALN_HIRSCHBERG_WIP &&
-             t.kind != GSPALN_FORWARD_NG) ||
+             t.kind != GSPALN_FORWARD_NG && t.kind != GSPALN_SCOREALONE_NG) ||
             (t.kind == GSPALN_HIRSCHBERG_WIP && (t.n_imd < 1 || t.a_right - t.a_left < 2 || ctx->prm.noll != 2)) ||
-            (t.kind == GSPALN_FORWARD_NG && ctx->prm.spj &&
+            ((t.kind == GSPALN_FORWARD_NG || t.kind == GSPALN_SCOREALONE_NG) && ctx->prm.spj &&
              (!ctx->ng_ready || !t.int53 || t.b_right - t.b_left >= ctx->n_pen)) ||
             !t.a || !t.b || (ctx->prm.spj && (!t.sig5 || !t.sig3))) {
             char msg[256];
@@ -332,8 +335,8 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
                      [&](int x, int y) { return ctx->cells[x] > ctx->cells[y]; });
     size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, skl_elems = 0;
     size_t udh_slab = 0, cpos_elems = 0;
-    int n_trace = 0, n_score = 0, n_udh = 0, n_ng = 0;
-    size_t ng_width = 0, ng_rec = 0;
+    int n_trace = 0, n_score = 0, n_udh = 0, n_ng = 0, n_ngs = 0;
+    size_t ng_width = 0, ng_rec = 0, ngs_width = 0;
     for (int k = 0; k < n; ++k) {
         const int i = ctx->h_order.p[k];
         const gspaln_task& t = tasks[i];
@@ -364,6 +367,9 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             ng_rec = std::max(ng_rec, (size_t) std::min<int64_t>(3 * ctx->cells[i] + 2 * width + 64, INT_MAX / 4));
             skl_elems += (size_t) d.skl_cap;
             ++n_ng;
+        } else if (t.kind == GSPALN_SCOREALONE_NG) {
+            ngs_width = std::max(ngs_width, (size_t) width);
+            ++n_ngs;
         } else if (t.kind == GSPALN_HIRSCHBERG_WIP) {
             d.pad0 = t.n_imd;
             d.pad1 = (long long) cpos_elems;
@@ -427,8 +433,20 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             ctx->grid_run_ng = g;
             ctx->ng_slab = slab; ctx->ng_width = ng_width; ctx->ng_rec_cap = (int) ng_rec;
         }
+        ctx->grid_run_ngs = 0;
+        if (n_ngs) {
+            // 32 problems per CTA, up to 16 CTAs per SM: thousands of problems in flight
+            const int g = std::min((n_ngs + NG_THREADS - 1) / NG_THREADS, 16 * ctx->sm_count);
+            if (ctx->d_ngs.reserve((size_t) g * NG_THREADS * 3 * ngs_width + 64) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(ctx, GSPALN_ENOMEM, "device scalar score-only workspace allocation");
+            }
+            ctx->grid_run_ngs = g;
+            ctx->ngs_width = ngs_width;
+        }
     }
     ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score; ctx->n_udh = n_udh; ctx->n_ng = n_ng;
+    ctx->n_ngs = n_ngs;
     ctx->udh_slab = udh_slab; ctx->cpos_elems = cpos_elems;
     ctx->a_bytes = a_bytes; ctx->c_elems = c_elems; ctx->band_slab = band_slab;
     ctx->trace_slab = trace_slab; ctx->skl_elems = skl_elems;
@@ -538,6 +556,12 @@ static int launch_range(gspaln_ctx* ctx, int lo, int hi, int slot, int& launches
             ctx->d_prm.p, ctx->d_ngtab.p, ctx->n_pen, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 8,
             ctx->d_apool.p, ctx->d_cpool.p, ctx->d_ngwork.p, (long long) ctx->ng_slab,
             (long long) ctx->ng_width, ctx->ng_rec_cap, ctx->d_skl.p, ctx->d_res.p, ready);
+        ++launches;
+    }
+    if (ctx->n_ngs) {
+        dp_ng_score_kernel<<<ctx->grid_run_ngs, NG_THREADS, 0, ctx->stream>>>(
+            ctx->d_prm.p, ctx->d_ngtab.p, ctx->n_pen, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 9,
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_ngs.p, (long long) ctx->ngs_width, ctx->d_res.p, ready);
         ++launches;
     }
     CK(cudaGetLastError());

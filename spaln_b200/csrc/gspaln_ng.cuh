@@ -308,4 +308,191 @@ dp_ng_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs, i
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Aln2s1::scorealoneS_ng (src/fwd2s1.cc:1163-1336) with sinitS_ng / slastS_ng (1112-1161): the
+// scalar score-only kernel (HomScoreS_ng under -A0 and for queries shorter than 4 residues,
+// src/fwd2s1.cc:2704-2705).  Same frame as dp_ng_kernel (one thread per problem) but no path
+// records: the workspace is three int rows of the band width, so it also takes full-size problems.
+// Its tie rules differ from forwardS_ng's (strict comparisons for the gap states and the
+// acceptors, ties accepted in the donor list) and so do its initial rows.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(NG_THREADS)
+dp_ng_score_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs, int n_pen,
+                   const DevTask* __restrict__ tasks, const int* __restrict__ order, int ntasks, int* ticket,
+                   const unsigned char* __restrict__ apool, const ColInfo* __restrict__ cpool,
+                   int* workpool, long long width_max, DevResult* results, const int* ready)
+{
+    __shared__ DevParams sP;
+    {
+        const int* src = reinterpret_cast<const int*>(gP);
+        int* dst = reinterpret_cast<int*>(&sP);
+        for (int i = threadIdx.x; i < (int) (sizeof(DevParams) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const DevParams& P = sP;
+    const bool dagp = P.noll == 3;
+    const int nod = 2 * P.noll - 1;
+    const int gop_k[3] = {0, P.gop, P.lgop};
+    const int psp_bit[5] = {4, 1, 8, 2, 16};
+    int* wbase = workpool + ((long long) blockIdx.x * NG_THREADS + threadIdx.x) * 3 * width_max;
+
+    for (;;) {
+        const int tk = atomicAdd(ticket, 1);
+        if (tk >= ntasks) break;
+        const int ti = order[tk];
+        const DevTask t = tasks[ti];
+        if (t.kind != 4) continue;
+        if (ready) {
+            const volatile int* r = ready;
+            const long long t0 = clock64();
+            bool ok = true;
+            while (*r <= tk) {
+                __nanosleep(256);
+                if (clock64() - t0 > (1ll << 33)) { ok = false; break; }
+            }
+            if (!ok) { DevResult rr; rr.score = 0; rr.status = 4; rr.n_skl = 0; rr.pad = 0; results[ti] = rr; continue; }
+        }
+        const unsigned char* aseq = apool + t.a_off;
+        const ColInfo* cols = cpool + t.col_off;
+        const int width = t.up - t.lw + 3;
+        const bool a_exgl = t.flags & 1, a_exgr = t.flags & 2, b_exgl = t.flags & 4, b_exgr = t.flags & 8;
+        const bool LocalL = P.local && a_exgl && b_exgl, LocalR = P.local && a_exgr && b_exgr;
+        const int a_left = t.a_left, a_right = t.a_right, b_left = t.b_left, b_right = t.b_right;
+        const int lw = t.lw, up = t.up;
+        int* H = wbase - lw + 1;
+        int* F = H + width;
+        int* F2 = F + width;
+        for (int i = 0; i < 3 * width; ++i) wbase[i] = NG_NEVSEL;
+        // ---- sinitS_ng
+        {
+            int r = b_left - a_left, rr = b_right - a_left;
+            H[r] = 0;
+            if (a_exgl) {
+                if (up < rr) rr = up;
+                for (int q = r + 1; q <= rr; ++q) H[q] = 0;
+            }
+            rr = max(b_left - a_right, lw);
+            if (b_exgl) {
+                for (int q = rr; q < r; ++q) H[q] = 0;
+            } else {
+                for (int i = 1; --r >= rr; ++i) {
+                    int h = H[r + 1];
+                    if (i == 1) { h += P.gappen1; F[r] = h; }
+                    else { h += i > P.codonk1 ? P.lgep : P.gep; F[r] = F[r + 1] + P.gep; }
+                    H[r] = h;
+                }
+            }
+        }
+        int maxh = NG_NEVSEL;
+        for (int m = a_exgl ? a_left + 1 : a_left; m <= a_right; ++m) {
+            const bool first = m == a_left;
+            int n = max((m - 1) + lw, b_left);
+            const int n9 = min((m - 1) + up + 1, b_right);
+            const int arow = first ? ZROW : (int) aseq[m - 1 - a_left];
+            int e1 = NG_NEVSEL, e2 = NG_NEVSEL;
+            int cval[NG_NCAND + 1], cdir[NG_NCAND + 1], cjnc[NG_NCAND + 1], idx[NG_NCAND + 1];
+#pragma unroll
+            for (int l = 0; l <= NG_NCAND; ++l) { cval[l] = NG_NEVSEL; cdir[l] = 0; cjnc[l] = 0; idx[l] = l; }
+            int ncand = -1, psp = 0;
+            int hleft = H[n - m];
+            while (++n <= n9) {
+                const int r = n - m;
+                const ColInfo col = cols[n - b_left];
+                int st[5];                              // H, E1, F, E2, F2 (the reference's hf[] order)
+                st[0] = H[r]; st[1] = e1; st[2] = F[r]; st[3] = e2; st[4] = dagp ? F2[r] : NG_NEVSEL;
+                int mx = 0;
+                if (!first) {
+                    st[0] += P.mtxT[(int) col.code * MTX_LD + arow];
+                    const int up_h = H[r + 1];
+                    st[2] = max(up_h + P.gop, F[r + 1]) + P.gep;
+                    if (st[2] > st[mx]) mx = 2;
+                    if (dagp) {
+                        st[4] = max(up_h + P.lgop, F2[r + 1]) + P.lgep;
+                        if (st[4] > st[mx]) mx = 4;
+                    }
+                }
+                {
+                    int x = hleft + P.gop;
+                    const int prev_psp = psp;
+                    if (x > st[1]) { st[1] = x; psp = psp ? 1 : 0; }
+                    else psp &= 1;
+                    st[1] += P.gep;
+                    if (st[1] > st[mx]) mx = 1;
+                    if (dagp) {
+                        x = hleft + P.lgop;
+                        if (x > st[3]) { st[3] = x; if (prev_psp) psp |= 2; }
+                        else psp |= prev_psp & 2;
+                        st[3] += P.lgep;
+                        if (st[3] > st[mx]) mx = 3;
+                    }
+                }
+                const int cano5 = col.pad[1] & 15, cano3 = col.pad[1] >> 4;
+                if (cano3) {
+                    unsigned top = 0;
+                    for (int l = 0; l <= ncand; ++l) {
+                        const int j = idx[l];
+                        if (n - cjnc[j] < P.llmt) continue;
+                        const int x = cval[j] + ng_spjscr(tabs, n_pen, cols, b_left, cjnc[j], n);
+                        if (x > st[cdir[j]]) { st[cdir[j]] = x; top |= 1u << cdir[j]; }
+                    }
+                    for (int k = 0; k < nod; ++k) {
+                        if (!(top >> k & 1u)) continue;
+                        psp |= psp_bit[k];
+                        if (st[k] > st[mx]) mx = k;
+                    }
+                }
+                const int y = st[0];
+                const int mxval = st[mx];
+                if (mx != 0) st[0] = mxval;
+                else if (LocalR && y > maxh) maxh = y;
+                int mx_now = mxval;
+                if (LocalL && st[0] < 0) { st[0] = 0; if (mx == 0) mx_now = 0; }
+                const int hd = mx;
+                if (cano5) {
+                    const int sigJ = col.sig5;
+                    for (int k = hd == 0 ? 0 : 1; k < nod; ++k) {
+                        if (psp & psp_bit[k]) continue;
+                        const int from = k == 0 ? st[0] : st[k];
+                        if (k != hd) {
+                            int z = mx_now;
+                            if (hd == 0 || (k - hd) % 2) z += gop_k[k / 2];
+                            if (from <= z) continue;
+                        }
+                        const int x = from + sigJ;
+                        int l = ncand < NG_NCAND ? ++ncand : NG_NCAND;
+                        while (--l >= 0) {
+                            if (x >= cval[idx[l]]) { const int s = idx[l]; idx[l] = idx[l + 1]; idx[l + 1] = s; }
+                            else break;
+                        }
+                        if (++l < NG_NCAND) { cval[idx[l]] = x; cjnc[idx[l]] = n; cdir[idx[l]] = k; }
+                        else --ncand;
+                    }
+                }
+                H[r] = st[0]; F[r] = st[2];
+                if (dagp) F2[r] = st[4];
+                e1 = st[1]; e2 = st[3];
+                hleft = st[0];
+            }
+        }
+        if (!LocalR) {
+            // slastS_ng
+            const int r9 = b_right - a_right;
+            int mxv = H[r9];
+            if (b_exgr) {
+                const int rw = min(up, b_right - a_left);
+                for (int r = rw; r > r9; --r) mxv = max(mxv, H[r]);
+            }
+            if (a_exgr) {
+                const int rw = max(lw, b_left - a_right);
+                for (int r = rw; r < r9; ++r) mxv = max(mxv, H[r]);
+            }
+            maxh = mxv;
+        }
+        DevResult res;
+        res.score = maxh; res.status = 0; res.n_skl = 0; res.pad = 0;
+        results[ti] = res;
+    }
+}
+
 }   // namespace gspaln

@@ -236,6 +236,11 @@ class Engine:
         scoring; src/fwd2s1.cc:217-444, 1667-1710): score + corners.  Problems carry int53."""
         return self.submit(problems, capi.FORWARD_NG)
 
+    def scorealoneS_ng(self, problems):
+        """Aln2s1::scorealoneS_ng (src/fwd2s1.cc:1163-1336): scalar score-only kernel, exact intron
+        scoring; problems carry int53"""
+        return self.submit(problems, capi.SCOREALONE_NG)
+
     def hirschbergS1_wip(self, problems):
         """problems carry n_imd; results carry score, ranges and cpos (Dim10 records)"""
         return self.submit(problems, capi.HIRSCHBERG_WIP)

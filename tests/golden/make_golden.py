@@ -158,6 +158,7 @@ def gen(name: str):
         out[pre + "int53"] = t.export_int53()
         out[pre + "ng_score"] = np.int32(rn["score"])
         out[pre + "ng_skl"] = rn["skl"].astype(np.int32)
+        out[pre + "ng_score_only"] = np.int32(t.scorealone(lw, up))     # Aln2s1::scorealoneS_ng
         nonlocal ng_tables, scan_f
         scan_f = t.scan_factors()
         if ng_tables is None or len(ng_tables["penalty"]) < ex["blen"] + 2:

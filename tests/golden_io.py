@@ -26,7 +26,7 @@ def load(name):
              "score_only": int(z[pre + "score_only"]), "tag": str(z[pre + "tag"])}
         d.update({k: int(v) for k, v in zip(GEOM_KEYS, z[pre + "geom"])})
         for k in ("lsp_score", "lsp_skl", "udh_nim", "udh_score", "udh_cpos", "udh_ranges",
-                  "int53", "ng_score", "ng_skl"):
+                  "int53", "ng_score", "ng_skl", "ng_score_only"):
             if pre + k in z.files:
                 v = z[pre + k]
                 d[k] = v if v.ndim else int(v)

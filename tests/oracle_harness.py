@@ -140,6 +140,17 @@ def trcbk_ng(p: dict, t: dict, cap: int = 1 << 16):
     return {"score": score.value, "skl": skl[:n].copy()}
 
 
+def scorealone_ng(p: dict, t: dict):
+    """Aln2s1::scorealoneS_ng (scalar score-only kernel)"""
+    sp, st = make_params(p), make_task(t)
+    score = C.c_int32(0)
+    lib().so_scorealone_ng.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = lib().so_scorealone_ng(C.byref(sp), C.byref(st), C.byref(score))
+    if rc < 0:
+        raise RuntimeError(f"so_scorealone_ng failed: {rc}")
+    return {"score": score.value}
+
+
 def scoreonly_wip(p: dict, t: dict):
     sp, st = make_params(p), make_task(t)
     score = C.c_int32(0)

@@ -285,6 +285,11 @@ class RefTask:
                 "codepot": int(i[0]), "ndata": int(i[1]), "dsize": int(i[2]), "exonpot": int(i[3]),
                 "intnpot": int(i[4]), "DvsP": int(i[5]), "maxb3d": int(i[6])}
 
+    def scorealone(self, lw, up):
+        """Aln2s1::scorealoneS_ng (scalar score-only kernel)"""
+        self.lib.ref_task_scorealone.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        return int(self.lib.ref_task_scorealone(self.h, lw, up))
+
     def scalar(self, lw, up, cap=1 << 16):
         """Aln2s1::trcbkalignS_ng forced onto its scalar branch (forwardS_ng + Vmf), raw Mfile corners"""
         score = C.c_int(0)

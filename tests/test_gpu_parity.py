@@ -243,6 +243,24 @@ def test_scalar_kernel_matches_oracle_seeded(oracle, name, flags, sub):
     eng.close()
 
 
+@pytest.mark.parametrize("name", golden_io.GOLDEN_NAMES + golden_io.DAGP_NAMES)
+def test_scalar_scoreonly_kernel_matches_reference_and_oracle(oracle, name):
+    """Aln2s1::scorealoneS_ng on the device: reference goldens (any size: three int rows of
+    workspace per problem), then seeded problems against the oracle"""
+    prm, probs = golden_io.load(name)
+    eng = _engine(prm)
+    for i, (pb, r) in enumerate(zip(probs, eng.scorealoneS_ng(_problems(probs)))):
+        assert r.status == 0 and r.score == pb["ng_score_only"], (name, i, pb["tag"], r.score, pb["ng_score_only"])
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(("sa" + name).encode()))
+    more = _synthetic(prm, rng, 30, (2, 12), (20, 1500), flags=(1, 0, 0, 1))
+    more += _synthetic(prm, rng, 20, (100, 900), (50, 900))
+    more += _synthetic(prm, rng, 10, (30, 300), (30, 400), flags=(0, 0, 0, 0), sub=(2, 1, 11, 5))
+    for i, (pb, r) in enumerate(zip(more, eng.scorealoneS_ng(_problems(more)))):
+        assert r.status == 0 and r.score == oracle.scorealone_ng(prm, pb)["score"], (name, i)
+    eng.close()
+
+
 def test_scalar_kernel_needs_its_tables():
     """without gspaln_set_ng_tables / int53 the kind is refused, and the driver reports
     GSPALN_ST_UNSUPPORTED for blocks with fewer than 8 query rows"""

@@ -28,6 +28,8 @@ def test_oracle_scalar_kernel_matches_reference_golden(oracle, name):
         o = oracle.trcbk_ng(prm, pb)
         assert o["score"] == pb["ng_score"], (name, i, pb["tag"])
         assert np.array_equal(o["skl"], pb["ng_skl"]), (name, i, pb["tag"])
+        # Aln2s1::scorealoneS_ng, the scalar score-only kernel
+        assert oracle.scorealone_ng(prm, pb)["score"] == pb["ng_score_only"], (name, i, pb["tag"])
 
 
 def test_golden_covers_edge_cases():

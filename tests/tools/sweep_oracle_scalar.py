@@ -41,6 +41,11 @@ for i in range(N):
     pp.update(t.export_ng_tables(max(4096, ex["blen"] + 2)))
     rs = t.scalar(lw, up)
     o = O.trcbk_ng(pp, ex)
+    sa, so = t.scorealone(lw, up), O.scorealone_ng(pp, ex)["score"]
+    if sa != so:
+        bad += 1
+        if bad < 4:
+            print("SCOREALONE MISMATCH", i, len(q), len(g), f, sa, so)
     if rs["score"] != o["score"] or not np.array_equal(rs["skl"], o["skl"]):
         bad += 1
         if bad < 4:
