@@ -122,6 +122,21 @@ def measured_traffic_per_cell():
         return None
 
 
+def binding_resource():
+    """what binds the DP kernel according to the committed `ncu --set full` capture (the HBM
+    roofline is reported as the contract asks, but the kernel is integer-ALU bound)"""
+    p = ROOT / "profiles" / "r01_ncu_full_dp_wip_q3000.json"
+    try:
+        d = json.loads(p.read_text())[0]
+        return {"resource": "integer ALU pipe (max / add / select recurrences on int16 cells)",
+                "pipe_alu_pct_of_peak": d["pipe_alu_pct"]["value"], "pipe_fma_pct_of_peak": d["pipe_fma_pct"]["value"],
+                "issue_slots_busy_pct": d["issue_slots_busy_pct"]["value"],
+                "warp_instructions_per_cell": d["warp_instructions"]["value"] / d["cells"],
+                "source": "profiles/r01_ncu_full_dp_wip_q3000.json"}
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -721,7 +736,8 @@ def main():
                          "peak_kind": peak_kind,
                          "bytes_per_cell": B_CELL, "kernel": "dp_wip_kernel<true>",
                          "kernel_ms": k_ms,
-                         "note": "integer-ALU bound DP: see DESIGN.md (HBM roof is not the binding one)"},
+                         "note": "integer-ALU bound DP: see DESIGN.md (HBM roof is not the binding one)",
+                         "binding": binding_resource()},
             "status_errors": bad,
             "lsp_path": {"note": "Aln2s1::lspS_ng dispatch at -V 32 MiB (trace-back or multi-intermediate "
                                  "Hirschberg + block re-alignment), wall clock, this rank",

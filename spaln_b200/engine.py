@@ -241,6 +241,21 @@ class Engine:
         scoring; problems carry int53"""
         return self.submit(problems, capi.SCOREALONE_NG)
 
+    def HomScoreS_ng(self, problems):
+        """HomScoreS_ng's kernel choice (src/fwd2s1.cc:2696-2716) for -A2 / -A3: queries shorter
+        than 4 residues go to the scalar score-only kernel, the rest to scoreonlyS1_wip.  (The band
+        is the caller's: the reference computes it with stripe(seqs, &wdw, alprm.sh).)"""
+        small = [i for i, p in enumerate(problems) if p.a_right - p.a_left < 4]
+        big = [i for i, p in enumerate(problems) if p.a_right - p.a_left >= 4]
+        out = [None] * len(problems)
+        if small:
+            for i, r in zip(small, self.submit([problems[i] for i in small], capi.SCOREALONE_NG)):
+                out[i] = r
+        if big:
+            for i, r in zip(big, self.submit([problems[i] for i in big], capi.SCOREONLY_WIP)):
+                out[i] = r
+        return out
+
     def hirschbergS1_wip(self, problems):
         """problems carry n_imd; results carry score, ranges and cpos (Dim10 records)"""
         return self.submit(problems, capi.HIRSCHBERG_WIP)

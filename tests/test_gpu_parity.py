@@ -261,6 +261,20 @@ def test_scalar_scoreonly_kernel_matches_reference_and_oracle(oracle, name):
     eng.close()
 
 
+def test_homscore_dispatch_matches_reference_golden():
+    """HomScoreS_ng: m < 4 -> scorealoneS_ng, otherwise scoreonlyS1_wip (src/fwd2s1.cc:2704-2712)"""
+    prm, probs = golden_io.load("dna_A2_global")
+    eng = _engine(prm)
+    res = eng.HomScoreS_ng(_problems(probs))
+    n_small = 0
+    for pb, r in zip(probs, res):
+        small = pb["a_right"] - pb["a_left"] < 4
+        n_small += small
+        assert r.score == (pb["ng_score_only"] if small else pb["score_only"]), pb["tag"]
+    assert n_small >= 2
+    eng.close()
+
+
 def test_scalar_kernel_needs_its_tables():
     """without gspaln_set_ng_tables / int53 the kind is refused, and the driver reports
     GSPALN_ST_UNSUPPORTED for blocks with fewer than 8 query rows"""
