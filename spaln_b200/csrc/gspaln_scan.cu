@@ -188,10 +188,14 @@ constexpr int FAST_WORDS = (FAST_BACK + FAST_TILE + FAST_FWD) / 16;
 
 // generic PSSM value straight from global memory (slow path of the fast kernel)
 __device__ __noinline__ float patmat_at_global(const DevPat& pm, const float* __restrict__ mtx,
-                                               const unsigned char* __restrict__ codes, long long len, long long n)
+                                               const unsigned char* __restrict__ codes, long long len, long long n,
+                                               bool tron)
 {
     const int rows = pm.rows, na = pm.nalpha;
-    auto rcode = [&](long long i) -> int { const unsigned v = codes[i]; return v < 17 ? c_ncred[v] : 15; };
+    auto rcode = [&](long long i) -> int {
+        const unsigned v = codes[i];
+        return tron ? (v < 26 ? c_tnred[v] : 4) : (v < 17 ? c_ncred[v] : 15);
+    };
     long long s = n, e = n + pm.cols;
     if (e > len - 2) e = len - 2;
     const float* ptn = mtx;
@@ -251,7 +255,8 @@ __device__ __forceinline__ float fast_sum(unsigned t_addr, unsigned p_addr, unsi
     return FastCols<0, C>::run(fit, t_addr, w << 7);
 }
 
-template <int C5, int C3>
+// TRON: the residues are tron codes (protein-side scan), reduced with tnredctab
+template <int C5, int C3, bool TRON>
 __global__ void __launch_bounds__(FAST_THREADS, 1)
 exinon_scan_fast_kernel(const DevScanParams* __restrict__ gP, const float* __restrict__ gmtx5,
                         const float* __restrict__ gmtx3, const unsigned char* __restrict__ codes,
@@ -324,7 +329,7 @@ exinon_scan_fast_kernel(const DevScanParams* __restrict__ gP, const float* __res
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const unsigned c = (vv[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                    const unsigned r = c < 17 ? c_ncred[c] : 15u;
+                    const unsigned r = TRON ? (c < 26 ? c_tnred[c] : 4u) : (c < 17 ? c_ncred[c] : 15u);
                     word |= (r > 3 ? 1u : r) << (2 * j);
                     bad |= (r > 3 ? 1u : 0u) << j;
                 }
@@ -335,7 +340,7 @@ exinon_scan_fast_kernel(const DevScanParams* __restrict__ gP, const float* __res
                     bool b = true;
                     if (pos >= 0 && pos < len) {
                         const unsigned c = codes[pos];
-                        r = c < 17 ? c_ncred[c] : 15u;
+                        r = TRON ? (c < 26 ? c_tnred[c] : 4u) : (c < 17 ? c_ncred[c] : 15u);
                         b = r > 3;
                         if (b) r = 1u;
                     }
@@ -383,9 +388,9 @@ exinon_scan_fast_kernel(const DevScanParams* __restrict__ gP, const float* __res
                                  ((B >> i3) & ((1u << (C3 + 2)) - 1u)) == 0;
                 float f5, f3;
                 if (ok5) f5 = __fadd_rn(fast_sum<C5>(t5, p5, W >> (2 * i5)), P.p5.tonic);
-                else f5 = patmat_at_global(P.p5, gmtx5, codes, len, n - o5);
+                else f5 = patmat_at_global(P.p5, gmtx5, codes, len, n - o5, TRON);
                 if (ok3) f3 = __fadd_rn(fast_sum<C3>(t3, p3, W >> (2 * i3)), P.p3.tonic);
-                else f3 = patmat_at_global(P.p3, gmtx3, codes, len, n - o3);
+                else f3 = patmat_at_global(P.p3, gmtx3, codes, len, n - o3, TRON);
                 s5 = (short) __fmul_rn(P.fs, f5);
                 s3 = (short) __fmul_rn(P.fs, f3);
                 s5 = (short) (s5 + P.tab[d5]);
@@ -482,7 +487,8 @@ static_assert(sizeof(DevSgpt6) == 14 && sizeof(gspaln_sgpt6) == 14, "SGPT6 is 14
 __global__ void __launch_bounds__(SCAN_THREADS)
 exinon_scan_p_kernel(const DevScanParams* __restrict__ gP, const float* __restrict__ gmtx /* 5 | 3 | I | T */,
                      const float* __restrict__ codepot, const unsigned char* __restrict__ tron,
-                     long long len, DevSgpt6* __restrict__ sg, unsigned short* __restrict__ int53)
+                     long long len, DevSgpt6* __restrict__ sg, unsigned short* __restrict__ int53,
+                     const short* __restrict__ pre5, const short* __restrict__ pre3)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ DevScanParams P;
@@ -531,7 +537,7 @@ exinon_scan_p_kernel(const DevScanParams* __restrict__ gP, const float* __restri
         unsigned w = 0, d5 = 0, d3 = 0;
         if (n <= len - 2) { d5 = (code2(n) << 2) | code2(n + 1); w |= d5 | (cano5_of(n) << 8); }
         if (n >= 1 && n <= len) { d3 = (code2(n - 2) << 2) | code2(n - 1); w |= (d3 << 4) | (cano3_of(n) << 12); }
-        int53[n] = (unsigned short) w;
+        if (!pre5) int53[n] = (unsigned short) w;       // else the bank-replicated kernel wrote it
         DevSgpt6 o;
         o.sig5 = o.sig3 = o.sigS = o.sigT = o.sigE = o.sigI = 0;
         // intron phases: the reference's left-to-right pass (a class > 1 site marks its right
@@ -548,11 +554,17 @@ exinon_scan_p_kernel(const DevScanParams* __restrict__ gP, const float* __restri
         o.phs3 = (signed char) phase(n < len ? cano3_of(n) : 0u, cano3_of(n - 1), cano3_of(n + 1),
                                      n - 1 >= 0 && n - 1 < len, n + 1 < len);
         if (n < len) {
-            short s5 = 0, s3 = 0;
-            if (P.p5.present) s5 = (short) __fmul_rn(P.fs, patmat_at(P.p5, mtx5, rc, base, len, n - P.p5.offset));
-            if (P.p3.present) s3 = (short) __fmul_rn(P.fs, patmat_at(P.p3, mtx3, rc, base, len, n - P.p3.offset));
-            o.sig5 = (short) (s5 + P.tab[d5]);
-            o.sig3 = (short) (s3 + P.tab[16 + d3]);
+            if (pre5) {
+                // 5' / 3' signals already computed by the bank-replicated kernel (same arithmetic)
+                o.sig5 = pre5[n];
+                o.sig3 = pre3[n];
+            } else {
+                short s5 = 0, s3 = 0;
+                if (P.p5.present) s5 = (short) __fmul_rn(P.fs, patmat_at(P.p5, mtx5, rc, base, len, n - P.p5.offset));
+                if (P.p3.present) s3 = (short) __fmul_rn(P.fs, patmat_at(P.p3, mtx3, rc, base, len, n - P.p3.offset));
+                o.sig5 = (short) (s5 + P.tab[d5]);
+                o.sig3 = (short) (s3 + P.tab[16 + d3]);
+            }
             if (P.pI.present) o.sigS = (short) __fmul_rn(P.fT, patmat_at(P.pI, mtxI, rc, base, len, n - P.pI.offset));
             if (P.pT.present) o.sigT = (short) __fmul_rn(P.fT, patmat_at(P.pT, mtxT, rc, base, len, n - P.pT.offset));
             if (P.cp_present) {
@@ -695,8 +707,11 @@ int gspaln_scan_create(gspaln_scan** out, const gspaln_scan_params* prm, int dev
         cudaDeviceProp prop;
         e = cudaGetDeviceProperties(&prop, device);
         if (e == cudaSuccess && fast_smem(8, 18) <= (size_t) prop.sharedMemPerBlockOptin) {
-            e = cudaFuncSetAttribute(exinon_scan_fast_kernel<8, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            e = cudaFuncSetAttribute(exinon_scan_fast_kernel<8, 18, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int) fast_smem(8, 18));
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(exinon_scan_fast_kernel<8, 18, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) fast_smem(8, 18));
             sc->fast = e == cudaSuccess;
             sc->sm_count = prop.multiProcessorCount;
         }
@@ -734,7 +749,7 @@ int gspaln_scan_run(gspaln_scan* sc)
     if (sc->fast) {
         const long long ntiles = (cols + FAST_TILE - 1) / FAST_TILE;
         const unsigned g = (unsigned) std::min<long long>(ntiles, sc->sm_count);
-        exinon_scan_fast_kernel<8, 18><<<g, FAST_THREADS, fast_smem(8, 18), sc->stream>>>(
+        exinon_scan_fast_kernel<8, 18, false><<<g, FAST_THREADS, fast_smem(8, 18), sc->stream>>>(
             sc->d_prm.p, sc->d_mtx5.p, sc->d_mtx3.p, sc->d_codes.p, sc->len, sc->d_sig5.p, sc->d_sig3.p, sc->d_int53.p);
     } else
         exinon_scan_kernel<<<grid, SCAN_THREADS, sc->smem, sc->stream>>>(
@@ -819,7 +834,9 @@ int gspaln_exinon_scan_p(gspaln_scan* sc, const uint8_t* tron, int64_t len, gspa
     if (!sc || !sc->protein || len < 0 || !sg || !int53 || (len && !tron)) return GSPALN_EINVAL;
     SCK(cudaSetDevice(sc->device));
     if (sc->d_codes.reserve((size_t) len + 16) != cudaSuccess || sc->d_sg.reserve((size_t) len + 2) != cudaSuccess ||
-        sc->d_int53.reserve((size_t) len + 2) != cudaSuccess) {
+        sc->d_int53.reserve((size_t) len + 2) != cudaSuccess ||
+        (sc->fast && (sc->d_sig5.reserve((size_t) len + 2) != cudaSuccess ||
+                      sc->d_sig3.reserve((size_t) len + 2) != cudaSuccess))) {
         cudaGetLastError();
         return sfail(sc, GSPALN_ENOMEM, "device allocation");
     }
@@ -830,8 +847,17 @@ int gspaln_exinon_scan_p(gspaln_scan* sc, const uint8_t* tron, int64_t len, gspa
     const unsigned grid = (unsigned) ((cols + SCAN_TILE - 1) / SCAN_TILE);
     for (int rep = 0; rep < 2; ++rep) {         // the second run is the timed one
         SCK(cudaEventRecord(sc->ev[2], sc->stream));
+        if (sc->fast) {
+            // stock PSSM shapes: 5' / 3' signals and INT53 on the bank-replicated kernel, the rest
+            // (start / stop PSSMs, coding potential, phases) on the generic one
+            const long long ntiles = (cols + FAST_TILE - 1) / FAST_TILE;
+            const unsigned g = (unsigned) std::min<long long>(ntiles, sc->sm_count);
+            exinon_scan_fast_kernel<8, 18, true><<<g, FAST_THREADS, fast_smem(8, 18), sc->stream>>>(
+                sc->d_prm.p, sc->d_mtx5.p, sc->d_mtx3.p, sc->d_codes.p, len, sc->d_sig5.p, sc->d_sig3.p, sc->d_int53.p);
+        }
         exinon_scan_p_kernel<<<grid, SCAN_THREADS, sc->smem_p, sc->stream>>>(
-            sc->d_prm.p, sc->d_mtxp.p, sc->d_codepot.p, sc->d_codes.p, len, sc->d_sg.p, sc->d_int53.p);
+            sc->d_prm.p, sc->d_mtxp.p, sc->d_codepot.p, sc->d_codes.p, len, sc->d_sg.p, sc->d_int53.p,
+            sc->fast ? sc->d_sig5.p : nullptr, sc->fast ? sc->d_sig3.p : nullptr);
         SCK(cudaGetLastError());
         SCK(cudaEventRecord(sc->ev[3], sc->stream));
     }
