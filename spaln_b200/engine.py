@@ -272,6 +272,14 @@ class Engine:
         self._n = n
         return self._collect(n, res, bufs, arr)
 
+    def lsp_packed(self, batch: PackedBatch, max_vmf_space=32 * 1024 * 1024, sh=100, ubh=0, alg=2) -> PackedBatch:
+        """lspS_ng over task descriptors marshalled once (`pack`): host buffers in, scores / status /
+        corners in `batch` -- the driver without the per-call Python marshalling"""
+        res = batch.res.ctypes.data_as(C.POINTER(capi.GspalnResult))
+        o = capi.GspalnLspOpts(int(max_vmf_space), int(sh), int(ubh), int(alg))
+        self._check(self.lib.gspaln_lsp(self._h, batch.arr, batch.n, C.byref(o), res), "gspaln_lsp")
+        return batch
+
     # ---- coalescing queue: the shape of the literal drop-in ---------------
     def queue(self, max_batch=256, max_wait_us=200) -> "SubmitQueue":
         """Thread-safe single-problem submits, coalesced into batches by a dispatcher thread

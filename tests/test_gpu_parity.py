@@ -369,6 +369,19 @@ def test_lsp_driver_config4_shape_local(oracle):
     eng.close()
 
 
+def test_lsp_packed_equals_object_api():
+    prm, probs = golden_io.load("dna_A2_udh")
+    eng = _engine(prm)
+    P = _problems(probs)
+    opts = dict(max_vmf_space=int(prm["MaxVmfSpace"]), sh=int(prm["sh"]), ubh=int(prm["ubh"]), alg=int(prm["alg"]))
+    want = eng.lspS_ng(P, **opts)
+    b = eng.lsp_packed(eng.pack(P), **opts)
+    for i, w in enumerate(want):
+        assert b.scores[i] == w.score and b.status[i] == w.status
+        assert np.array_equal(b.corners(i), w.skl)
+    eng.close()
+
+
 def test_packed_batch_api_equals_object_api():
     prm, probs = golden_io.load("dna_A2_global")
     eng = _engine(prm)
