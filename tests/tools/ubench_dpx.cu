@@ -1,4 +1,5 @@
 // micro-benchmark: issue rate of the packed int16x2 DPX forms against their 32-bit twins on sm_100a
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tests/tools/ubench_dpx tests/tools/ubench_dpx.cu (binary is git-ignored; results: profiles/r01_ubench_dpx.txt)
 #include <cstdio>
 #include <cuda_runtime.h>
 template <int OP>
