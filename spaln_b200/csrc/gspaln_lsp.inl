@@ -313,8 +313,9 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
         }
     }
 
-    // ---- assemble the corner lists in the reference's write order (depth first)
-    for (int i = 0; i < n; ++i) {
+    // ---- assemble the corner lists in the reference's write order (depth first); the problems
+    // are independent, so the loop is dealt to a few host threads
+    auto assemble = [&](int i) {
         gspaln_result& o = results[i];
         std::vector<int2> out;
         std::vector<std::pair<int, size_t>> stack;      // (item, next piece)
@@ -337,6 +338,17 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
         if (o.status == GSPALN_ST_OK && o.n_skl > cap) o.status = GSPALN_ST_SKL_OVERFLOW;
         if (o.skl)
             for (int k = 0; k < std::min(o.n_skl, cap); ++k) { o.skl[2 * k] = out[k].x; o.skl[2 * k + 1] = out[k].y; }
+    };
+    {
+        const int nthr = n >= 512 ? (int) std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u) : 1;
+        if (nthr == 1) {
+            for (int i = 0; i < n; ++i) assemble(i);
+        } else {
+            std::vector<std::thread> pool;
+            for (int w = 0; w < nthr; ++w)
+                pool.emplace_back([&, w] { for (int i = w; i < n; i += nthr) assemble(i); });
+            for (auto& th : pool) th.join();
+        }
     }
     if (dbg)
         fprintf(stderr, "gspaln lsp: %d problems, %zu forward tasks; classify %.1f ms, submits %.1f ms "
