@@ -88,6 +88,37 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
     };
     size_t fwd_done = 0;
     int64_t cells_total = 0;
+    // Corner buffers of the block re-alignments: a block of m rows and n columns can in theory
+    // return m + n corners, in practice a few dozen.  The first submit gives every forward task
+    // LSP_SKL_CAP corners (the pool of the whole level is copied back, so its size matters); a
+    // task that reports GSPALN_ST_SKL_OVERFLOW is run again with the size it asked for.
+    constexpr int LSP_SKL_CAP = 192;
+    std::vector<std::vector<int>> retry_buf;
+    auto retry_overflow = [&](std::vector<Task>& bt, std::vector<gspaln_result>& br, size_t first) -> int {
+        std::vector<size_t> again;
+        for (size_t k = first; k < bt.size(); ++k)
+            if (br[k].status == GSPALN_ST_SKL_OVERFLOW) again.push_back(k);
+        if (again.empty()) return GSPALN_OK;
+        std::vector<Task> t2;
+        std::vector<gspaln_result> r2(again.size());
+        const size_t keep = retry_buf.size();
+        retry_buf.resize(keep + again.size());
+        for (size_t j = 0; j < again.size(); ++j) {
+            Task t = bt[again[j]];
+            t.skl_cap = br[again[j]].n_skl + 8;
+            retry_buf[keep + j].assign(2 * (size_t) t.skl_cap, 0);
+            r2[j].skl = retry_buf[keep + j].data();
+            r2[j].cpos = nullptr;
+            t2.push_back(t);
+        }
+        int rc = TR::submit(ctx, t2.data(), (int) t2.size(), r2.data());
+        if (rc != GSPALN_OK) return rc;
+        for (size_t j = 0; j < again.size(); ++j) {
+            bt[again[j]].skl_cap = t2[j].skl_cap;
+            br[again[j]] = r2[j];
+        }
+        return GSPALN_OK;
+    };
     const bool dbg = getenv("GSPALN_LSP_DEBUG") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto msec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
@@ -175,16 +206,23 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
             cposbuf[k].assign(10 * (size_t) (it.n_imd + 1), 0);
         }
         const size_t fwd_first = fwd_done;
-        std::vector<std::vector<int>> sklbuf(fwds.size() - fwd_first);
+        size_t skl_ints = 0;
         for (size_t f = fwd_first; f < fwds.size(); ++f) {
             batch.push_back(TR::make_task(tasks[fwds[f].root], fwds[f].g, fwds[f].kind, 0));
-            sklbuf[f - fwd_first].assign(2 * (size_t) batch.back().skl_cap, 0);
+            batch.back().skl_cap = std::min(batch.back().skl_cap, LSP_SKL_CAP);
+            skl_ints += 2 * (size_t) batch.back().skl_cap;
         }
+        std::vector<int> sklflat(skl_ints + 2);
         bres.resize(batch.size());
         for (size_t k = 0; k < udh_items.size(); ++k) { bres[k].skl = nullptr; bres[k].cpos = cposbuf[k].data(); }
-        for (size_t f = fwd_first; f < fwds.size(); ++f) {
-            bres[udh_items.size() + (f - fwd_first)].skl = sklbuf[f - fwd_first].data();
-            bres[udh_items.size() + (f - fwd_first)].cpos = nullptr;
+        {
+            size_t at = 0;
+            for (size_t f = fwd_first; f < fwds.size(); ++f) {
+                const size_t k = udh_items.size() + (f - fwd_first);
+                bres[k].skl = sklflat.data() + at;
+                bres[k].cpos = nullptr;
+                at += 2 * (size_t) batch[k].skl_cap;
+            }
         }
         auto t1 = now();
         t_classify += msec(t0, t1);
@@ -195,6 +233,8 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
             kernel_ms += ctx->tim.kernel_ms; h2d_ms += ctx->tim.h2d_ms; d2h_ms += ctx->tim.d2h_ms;
             launches += ctx->tim.launches; h2d_bytes += ctx->tim.h2d_bytes; d2h_bytes += ctx->tim.d2h_bytes;
             cells_total += ctx->tim.cells;
+            rc = retry_overflow(batch, bres, udh_items.size());
+            if (rc != GSPALN_OK) return rc;
         }
         // forward results
         for (size_t f = fwd_first; f < fwds.size(); ++f) {
@@ -202,7 +242,7 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
             fwds[f].score = r.score;
             if (r.status != GSPALN_ST_OK) status[fwds[f].root] = r.status;
             const int cnt = std::min(r.n_skl, batch[udh_items.size() + (f - fwd_first)].skl_cap);
-            const int* s = sklbuf[f - fwd_first].data();
+            const int* s = r.skl;
             fwds[f].skl.resize(std::max(cnt, 0));
             for (int k = 0; k < cnt; ++k) fwds[f].skl[k] = make_int2(s[2 * k], s[2 * k + 1]);
         }
@@ -287,13 +327,22 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
             // a level with only forward tasks: loop once more with no items to classify
             std::vector<Task> b2;
             std::vector<gspaln_result> r2;
-            std::vector<std::vector<int>> s2(fwds.size() - fwd_done);
+            size_t ints2 = 0;
             for (size_t f = fwd_done; f < fwds.size(); ++f) {
                 b2.push_back(TR::make_task(tasks[fwds[f].root], fwds[f].g, fwds[f].kind, 0));
-                s2[f - fwd_done].assign(2 * (size_t) b2.back().skl_cap, 0);
+                b2.back().skl_cap = std::min(b2.back().skl_cap, LSP_SKL_CAP);
+                ints2 += 2 * (size_t) b2.back().skl_cap;
             }
+            std::vector<int> flat2(ints2 + 2);
             r2.resize(b2.size());
-            for (size_t f = 0; f < b2.size(); ++f) { r2[f].skl = s2[f].data(); r2[f].cpos = nullptr; }
+            {
+                size_t at = 0;
+                for (size_t f = 0; f < b2.size(); ++f) {
+                    r2[f].skl = flat2.data() + at;
+                    r2[f].cpos = nullptr;
+                    at += 2 * (size_t) b2[f].skl_cap;
+                }
+            }
             auto t3 = now();
             int rc = TR::submit(ctx, b2.data(), (int) b2.size(), r2.data());
             if (rc != GSPALN_OK) return rc;
@@ -301,13 +350,15 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
             kernel_ms += ctx->tim.kernel_ms; h2d_ms += ctx->tim.h2d_ms; d2h_ms += ctx->tim.d2h_ms;
             launches += ctx->tim.launches; h2d_bytes += ctx->tim.h2d_bytes; d2h_bytes += ctx->tim.d2h_bytes;
             cells_total += ctx->tim.cells;
+            rc = retry_overflow(b2, r2, 0);
+            if (rc != GSPALN_OK) return rc;
             for (size_t f = 0; f < b2.size(); ++f) {
                 LspFwd& F = fwds[fwd_done + f];
                 F.score = r2[f].score;
                 if (r2[f].status != GSPALN_ST_OK) status[F.root] = r2[f].status;
                 const int cnt = std::min(r2[f].n_skl, b2[f].skl_cap);
                 F.skl.resize(std::max(cnt, 0));
-                for (int k = 0; k < cnt; ++k) F.skl[k] = make_int2(s2[f][2 * k], s2[f][2 * k + 1]);
+                for (int k = 0; k < cnt; ++k) F.skl[k] = make_int2(r2[f].skl[2 * k], r2[f].skl[2 * k + 1]);
             }
             fwd_done = fwds.size();
         }
