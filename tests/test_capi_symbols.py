@@ -63,3 +63,22 @@ def test_task_cells_host_helper():
     # row m: columns max(m-5,0) < n <= min(m+46,50)
     want = sum(min(m + 46, 50) - max(m - 5, 0) for m in range(1, 11))
     assert lib.gspaln_task_cells(ctypes.byref(t)) == want
+
+
+def test_task_cells_closed_form_equals_loop_count():
+    """gspaln_task_cells / gspaln_h_task_cells (host code, no GPU): the closed-form band area must
+    equal the reference's inner-loop trip count, rows m in (a_left, a_right], columns
+    max(k m + lw, b_left) < n <= min(k m + up + 1, b_right) with k = 1 (DNA, src/fwd2s1.cc:252-276)
+    and k = 3 (protein, src/fwd2h1.cc:324-331 counts n0 .. n9 inclusive of both ends minus one)"""
+    import numpy as np
+    from spaln_b200 import capi
+    lib = capi.load()
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        al = int(rng.integers(0, 20)); ar = al + int(rng.integers(0, 60))
+        bl = int(rng.integers(0, 50)); br = bl + int(rng.integers(0, 400))
+        lw = int(rng.integers(-80, 200)); up = lw + int(rng.integers(0, 300))
+        t = capi.GspalnTask()
+        t.a_left, t.a_right, t.b_left, t.b_right, t.lw, t.up = al, ar, bl, br, lw, up
+        want = sum(max(0, min(m + up + 1, br) - max(m + lw, bl)) for m in range(al + 1, ar + 1))
+        assert lib.gspaln_task_cells(ctypes.byref(t)) == want, (al, ar, bl, br, lw, up)
