@@ -72,6 +72,44 @@ struct ShimAln2h1 : public Aln2h1 {
 	}
 };
 
+// Aln2h1::trcbkalignH_ng (src/fwd2h1.cc:1997-2041) with the SIMD level forced to 0: its scalar branch
+// (forwardH_ng + Vmf::traceback + end adjustment), what the stock code runs for blocks with < 8 rows
+struct ShimAln2h1Scalar : public ShimAln2h1 {
+	ShimAln2h1Scalar(const Seq** sqs, const PwdB* pwd) : ShimAln2h1(sqs, pwd) {}
+	VTYPE run_scalar(const WINDOW& w, SKL* out, int cap, int* n_out) {
+	    *const_cast<int*>(&simd) = 0;
+	    mfd = new Mfile(sizeof(SKL));
+	    VTYPE scr = trcbkalignH_ng(w, b->inex.intr);
+	    int n = (int) mfd->size();
+	    SKL* skl = (SKL*) mfd->flush();
+	    *n_out = n;
+	    for (int i = 0; i < n && i < cap; ++i) out[i] = skl[i];
+	    delete[] skl;
+	    delete mfd; mfd = 0;
+	    return scr;
+	}
+};
+
+int shim_h1_scalar(const Seq** seqs, const PwdB* pwd, int lw, int up, int* score, int* skl_out, int cap)
+{
+	WINDOW wdw = {lw, up, up - lw + 7};
+	int n = 0;
+	ShimAln2h1Scalar aln(seqs, pwd);
+	*score = aln.run_scalar(wdw, (SKL*) skl_out, cap, &n);
+	return n;
+}
+
+// split-codon tables of SpJunc::spjseq (src/codepot.h:130-190) and aa2nuc (src/seq.cc:76):
+// out = spj_tron_tab[257][2] | spj_amb_tron_tab[64][2] | spj_tron_amb_tab[64][2] | aa2nuc[26]
+void shim_h1_spj_tables(unsigned char* out)
+{
+	int k = 0;
+	for (int i = 0; i < 257; ++i) { out[k++] = spj_tron_tab[i][0]; out[k++] = spj_tron_tab[i][1]; }
+	for (int i = 0; i < 64; ++i) { out[k++] = spj_amb_tron_tab[i][0]; out[k++] = spj_amb_tron_tab[i][1]; }
+	for (int i = 0; i < 64; ++i) { out[k++] = spj_tron_amb_tab[i][0]; out[k++] = spj_tron_amb_tab[i][1]; }
+	for (int i = 0; i < 26; ++i) out[k++] = aa2nuc[i];
+}
+
 int shim_h1_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up, int* score, int* skl_out,
 	int cap, double* seconds)
 {

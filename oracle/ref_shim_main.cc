@@ -45,6 +45,8 @@ int shim_h1_udh(const Seq** seqs, const PwdB* pwd, int lw, int up, int n_imd, in
 	int* cpos_out, double* seconds);
 int shim_h1_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up, int* score, int* skl_out,
 	int cap, double* seconds);
+int shim_h1_scalar(const Seq** seqs, const PwdB* pwd, int lw, int up, int* score, int* skl_out, int cap);
+void shim_h1_spj_tables(unsigned char* out);
 int shim_h1_kernel(const Seq** seqs, const PwdB* pwd, int lw, int up, int kind,
 	int* score, int* skl_out, int cap, double* seconds);
 int shim_s1_adapter(const Seq** seqs, const PwdB* pwd, int lw, int up,
@@ -423,6 +425,21 @@ int ref_get_codepot(float* out, int cap)
 	int n = g_pwd->codepot->dsize();
 	for (int i = 0; i < n && i < cap; ++i) out[i] = g_pwd->codepot->begin()[i];
 	return n;
+}
+
+int ref_task_scalar_p(void* h, int lw, int up, int* score, int* skl_out, int cap)
+{
+	RefTask* t = (RefTask*) h;
+	return shim_h1_scalar((const Seq**) t->sqs, g_pwd, lw, up, score, skl_out, cap);
+}
+
+// spj tables (see shim_h1_spj_tables) and the protein-side scalar parameters:
+// ivals = IntronPrm.minl, ExtraGOP, GapW3L, alprm2.termk1
+void ref_get_scalar_p(unsigned char* tabs, int* ivals)
+{
+	shim_h1_spj_tables(tabs);
+	ivals[0] = IntronPrm.minl; ivals[1] = g_pwd->ExtraGOP; ivals[2] = g_pwd->GapW3L;
+	ivals[3] = (int) alprm2.termk1;
 }
 
 int ref_task_scorealone(void* h, int lw, int up)

@@ -173,6 +173,20 @@ int so_hirschberg_h1_wip(const so_params_h* p, const so_task_h* t, int n_im, int
 int so_lsp_h(const so_params_h* p, const so_task_h* t, const so_lsp_opts* o, int32_t* score,
              int32_t* skl, int cap, int* unsupported);
 
+/* extra inputs of the scalar protein kernel */
+typedef struct {
+    const int16_t* penalty; int32_t n_penalty;      /* IntronPenalty::Penalty(len) */
+    const int16_t* sig53tab;                        /* Exinon::sig53tab[0][0..543] */
+    const uint16_t* int53;                          /* INT53 nibbles by column */
+    const uint8_t* spj_tabs;    /* spj_tron_tab[257][2] | spj_amb_tron_tab[64][2] | spj_tron_amb_tab[64][2] | aa2nuc[26] */
+    int32_t minl, extragop, gw3l, noll;             /* IntronPrm.minl, PwdB::ExtraGOP, GapW3L, Noll */
+} so_ng_h;
+
+/* Aln2h1::trcbkalignH_ng on its scalar branch (src/fwd2h1.cc:1997-2041): forwardH_ng (294-617)
+ * with initH_ng / lastH_ng (143-292), Vmf trace-back and the end-point adjustment */
+int so_trcbk_h_ng(const so_params_h* p, const so_ng_h* x, const so_task_h* t, int32_t* score,
+                  int32_t* skl, int cap);
+
 #ifdef __cplusplus
 }
 #endif

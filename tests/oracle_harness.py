@@ -379,3 +379,30 @@ def lsp_h(p: dict, t: dict, cap: int = 1 << 16, max_vmf_space=None):
     n = lib().so_lsp_h(C.byref(sp), C.byref(st), C.byref(o), C.byref(score), skl.ctypes.data, cap,
                        C.byref(unsup))
     return {"score": score.value, "skl": skl[:min(n, cap)].copy(), "unsupported": bool(unsup.value)}
+
+
+class SoNgH(C.Structure):
+    _fields_ = [("penalty", C.c_void_p), ("n_penalty", C.c_int32), ("sig53tab", C.c_void_p),
+                ("int53", C.c_void_p), ("spj_tabs", C.c_void_p), ("minl", C.c_int32),
+                ("extragop", C.c_int32), ("gw3l", C.c_int32), ("noll", C.c_int32)]
+
+
+def trcbk_h_ng(p: dict, t: dict, cap: int = 1 << 16):
+    """scalar protein kernel (Aln2h1::trcbkalignH_ng's scalar branch): score + corners.  p carries
+    penalty, sig53tab, spj_tabs, minl, ExtraGOP, GapW3L; t carries int53"""
+    sp, st = _params_h(p), _task_h(t)
+    x = SoNgH()
+    pen = np.ascontiguousarray(p["penalty"], np.int16)
+    tab = np.ascontiguousarray(p["sig53tab"], np.int16)
+    i53 = np.ascontiguousarray(t["int53"], np.uint16)
+    spj = np.ascontiguousarray(p["spj_tabs"], np.uint8)
+    x.penalty, x.n_penalty, x.sig53tab = pen.ctypes.data, len(pen), tab.ctypes.data
+    x.int53, x.spj_tabs = i53.ctypes.data, spj.ctypes.data
+    x.minl, x.extragop, x.gw3l, x.noll = int(p["minl"]), int(p["ExtraGOP"]), int(p["GapW3L"]), int(p["Noll"])
+    score = C.c_int32(0)
+    skl = np.zeros((cap, 2), np.int32)
+    lib().so_trcbk_h_ng.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    n = lib().so_trcbk_h_ng(C.byref(sp), C.byref(x), C.byref(st), C.byref(score), skl.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError(f"so_trcbk_h_ng failed: {n}")
+    return {"score": score.value, "skl": skl[:n].copy()}

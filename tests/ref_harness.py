@@ -121,6 +121,14 @@ class Reference:
                 p[name] = int(pb[i])
         return p
 
+    def scalar_p_tables(self):
+        """split-codon tables of SpJunc::spjseq + aa2nuc, and minl / ExtraGOP / GapW3L / termk1"""
+        tabs = np.zeros(257 * 2 + 64 * 2 + 64 * 2 + 26, np.uint8)
+        iv = np.zeros(4, np.int32)
+        self.lib.ref_get_scalar_p.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.ref_get_scalar_p(tabs.ctypes.data, iv.ctypes.data)
+        return {"spj_tabs": tabs, "minl": int(iv[0]), "ExtraGOP": int(iv[1]), "GapW3L": int(iv[2]), "termk1": int(iv[3])}
+
     def codepot(self):
         """PwdB::codepot table (ExinPot::begin(), dsize() floats) or None"""
         buf = np.zeros(1 << 16, np.float32)
@@ -284,6 +292,14 @@ class RefTask:
                 "bp_factor": np.float32(f[4]), "o": np.float32(f[5]), "tonicB": np.float32(f[6]),
                 "codepot": int(i[0]), "ndata": int(i[1]), "dsize": int(i[2]), "exonpot": int(i[3]),
                 "intnpot": int(i[4]), "DvsP": int(i[5]), "maxb3d": int(i[6])}
+
+    def scalar_p(self, lw, up, cap=1 << 16):
+        """Aln2h1::trcbkalignH_ng forced onto its scalar branch (forwardH_ng + Vmf)"""
+        self.lib.ref_task_scalar_p.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        score = C.c_int(0)
+        skl = np.zeros((cap, 2), np.int32)
+        n = self.lib.ref_task_scalar_p(self.h, lw, up, C.byref(score), skl.ctypes.data, cap)
+        return {"score": score.value, "skl": skl[:n].copy()}
 
     def scorealone(self, lw, up):
         """Aln2s1::scorealoneS_ng (scalar score-only kernel)"""
