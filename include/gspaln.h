@@ -332,6 +332,8 @@ typedef struct gspaln_h_task {
     int32_t skl_cap;
     int32_t n_imd;              /* GSPALN_HIRSCHBERG_WIP: number of intermediate rows (>= 1) */
     int32_t a_len;              /* Seq::len of the query (driver: range check of mimd_postwork) */
+    const uint16_t* int53;      /* GSPALN_FORWARD_NG (and gspaln_h_lsp blocks with < 8 rows), else may be
+                                   NULL: Exinon::int53[n] by column, as in gspaln_task.int53 */
 } gspaln_h_task;
 
 typedef struct gspaln_h_ctx gspaln_h_ctx;
@@ -339,6 +341,16 @@ typedef struct gspaln_h_ctx gspaln_h_ctx;
 int  gspaln_h_create(gspaln_h_ctx** out, const gspaln_h_params* prm, int device);
 void gspaln_h_destroy(gspaln_h_ctx* ctx);
 int  gspaln_h_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gspaln_result* results);
+
+/* Tables of the scalar kernel GSPALN_FORWARD_NG for protein queries: Aln2h1::trcbkalignH_ng on its
+ * scalar branch (src/fwd2h1.cc:1997-2041): forwardH_ng (294-617) + Vmf::traceback + end adjustment,
+ * what the reference runs for blocks with fewer than 8 query rows.  sig53tab, penalty as in
+ * gspaln_set_ng_tables; spj_tabs = spj_tron_tab[257][2] | spj_amb_tron_tab[64][2] |
+ * spj_tron_amb_tab[64][2] (src/codepot.h:130-190) | aa2nuc[26] (src/seq.cc:76), 796 bytes;
+ * minl = IntronPrm.minl, extragop = PwdB::ExtraGOP, gw3l = PwdB::GapW3L, noll = PwdB::Noll. */
+int  gspaln_h_set_ng_tables(gspaln_h_ctx* ctx, const int16_t* sig53tab, const int16_t* penalty,
+                            int32_t n_penalty, const uint8_t* spj_tabs, int32_t minl,
+                            int32_t extragop, int32_t gw3l, int32_t noll);
 int  gspaln_h_upload(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n);
 int  gspaln_h_run(gspaln_h_ctx* ctx);
 int  gspaln_h_download(gspaln_h_ctx* ctx, gspaln_result* results);

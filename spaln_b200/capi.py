@@ -32,7 +32,7 @@ EXPORTS = [
     "gspaln_version", "gspaln_task_cells", "gspaln_lsp", "gspaln_set_ng_tables",
     "gspaln_h_create", "gspaln_h_destroy", "gspaln_h_submit", "gspaln_h_upload", "gspaln_h_run",
     "gspaln_h_download", "gspaln_h_get_timing", "gspaln_h_last_error", "gspaln_h_task_cells",
-    "gspaln_h_lsp",
+    "gspaln_h_lsp", "gspaln_h_set_ng_tables",
     "gspaln_queue_create", "gspaln_queue_submit", "gspaln_queue_stats", "gspaln_queue_destroy",
     "gspaln_scan_create", "gspaln_scan_destroy", "gspaln_exinon_scan", "gspaln_scan_upload",
     "gspaln_scan_run", "gspaln_scan_download", "gspaln_scan_get_timing", "gspaln_scan_last_error",
@@ -118,7 +118,7 @@ class GspalnHTask(C.Structure):
         ("a_left", C.c_int32), ("a_right", C.c_int32), ("b_left", C.c_int32), ("b_right", C.c_int32),
         ("a_exgl", C.c_int32), ("a_exgr", C.c_int32), ("b_exgl", C.c_int32), ("b_exgr", C.c_int32),
         ("lw", C.c_int32), ("up", C.c_int32), ("skl_cap", C.c_int32), ("n_imd", C.c_int32),
-        ("a_len", C.c_int32),
+        ("a_len", C.c_int32), ("int53", C.c_void_p),
     ]
 
 
@@ -190,6 +190,8 @@ def load():
     lib.gspaln_h_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(GspalnHParams), C.c_int]
     lib.gspaln_h_destroy.argtypes = [C.c_void_p]
     lib.gspaln_h_destroy.restype = None
+    lib.gspaln_h_set_ng_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                           C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     lib.gspaln_h_submit.argtypes = [C.c_void_p, C.POINTER(GspalnHTask), C.c_int, C.POINTER(GspalnResult)]
     lib.gspaln_h_upload.argtypes = [C.c_void_p, C.POINTER(GspalnHTask), C.c_int]
     lib.gspaln_h_run.argtypes = [C.c_void_p]

@@ -5,6 +5,7 @@
 #include "../../include/gspaln.h"
 #include "gspaln_h1.cuh"
 #include "gspaln_h1_udh.cuh"
+#include "gspaln_hng.cuh"
 #include "gspaln_host.hpp"
 
 #include <algorithm>
@@ -24,6 +25,13 @@ using namespace gspaln;
 struct gspaln_h_ctx {
     int device = 0;
     int sm_count = 0;
+    // scalar kernel (GSPALN_FORWARD_NG): tables + frozen scalars on the device
+    DevBuf<short> d_ngtab;              // sig53tab[544] | Penalty(0 .. n_pen - 1)
+    DevBuf<unsigned char> d_ngspj;      // split-codon tables + aa2nuc
+    DevBuf<int> d_ngmtx;                // simmtx[aa][tron]
+    DevBuf<DevNgHParams> d_ngprm;
+    int n_pen = 0;
+    bool ng_ready = false;
     gspaln_h_params prm;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;    // H2D of the chunks that follow the first one
@@ -210,6 +218,7 @@ void gspaln_h_destroy(gspaln_h_ctx* ctx)
     ctx->d_band.release(); ctx->d_trace.release(); ctx->d_rows.release(); ctx->d_skl.release();
     ctx->d_res.release(); ctx->d_ws.release(); ctx->d_cpos.release(); ctx->d_ures.release();
     ctx->h_cpos.release(); ctx->h_ures.release();
+    ctx->d_ngtab.release(); ctx->d_ngspj.release(); ctx->d_ngmtx.release(); ctx->d_ngprm.release();
     ctx->h_tasks.release(); ctx->h_order.release(); ctx->h_apool.release(); ctx->h_cpool.release();
     ctx->h_epool.release(); ctx->h_skl.release(); ctx->h_res.release();
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -538,7 +547,168 @@ int gspaln_h_download(gspaln_h_ctx* ctx, gspaln_result* results)
 }
 
 // One-shot path: the batch is streamed in behind the persistent kernels (see gspaln_submit)
+static int h_submit_core(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gspaln_result* results);
+static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gspaln_result* results);
+
+// tasks of kind GSPALN_FORWARD_NG run on the scalar kernel, the rest on the persistent kernels
 int gspaln_h_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gspaln_result* results)
+{
+    if (!ctx || !tasks || n < 0) return GSPALN_EINVAL;
+    int n_ng = 0;
+    for (int i = 0; i < n; ++i) n_ng += tasks[i].kind == GSPALN_FORWARD_NG;
+    if (!n_ng) return h_submit_core(ctx, tasks, n, results);
+    std::vector<gspaln_h_task> t_ng, t_rest;
+    std::vector<gspaln_result> r_ng, r_rest;
+    std::vector<int> i_ng, i_rest;
+    for (int i = 0; i < n; ++i) {
+        const bool ng = tasks[i].kind == GSPALN_FORWARD_NG;
+        (ng ? t_ng : t_rest).push_back(tasks[i]);
+        (ng ? r_ng : r_rest).push_back(results[i]);
+        (ng ? i_ng : i_rest).push_back(i);
+    }
+    int rc = GSPALN_OK;
+    gspaln_timing tim_rest;
+    memset(&tim_rest, 0, sizeof(tim_rest));
+    if (!t_rest.empty()) {
+        rc = h_submit_core(ctx, t_rest.data(), (int) t_rest.size(), r_rest.data());
+        if (rc != GSPALN_OK) return rc;
+        tim_rest = ctx->tim;
+    }
+    rc = h_ng_submit(ctx, t_ng.data(), (int) t_ng.size(), r_ng.data());
+    if (rc != GSPALN_OK) return rc;
+    ctx->tim.kernel_ms += tim_rest.kernel_ms; ctx->tim.h2d_ms += tim_rest.h2d_ms; ctx->tim.d2h_ms += tim_rest.d2h_ms;
+    ctx->tim.launches += tim_rest.launches; ctx->tim.h2d_bytes += tim_rest.h2d_bytes;
+    ctx->tim.d2h_bytes += tim_rest.d2h_bytes; ctx->tim.cells += tim_rest.cells;
+    for (size_t k = 0; k < i_ng.size(); ++k) results[i_ng[k]] = r_ng[k];
+    for (size_t k = 0; k < i_rest.size(); ++k) results[i_rest[k]] = r_rest[k];
+    return GSPALN_OK;
+}
+
+int gspaln_h_set_ng_tables(gspaln_h_ctx* ctx, const int16_t* sig53tab, const int16_t* penalty,
+                           int32_t n_penalty, const uint8_t* spj_tabs, int32_t minl,
+                           int32_t extragop, int32_t gw3l, int32_t noll)
+{
+    if (!ctx || !sig53tab || !penalty || !spj_tabs || n_penalty < 1 || (noll != 2 && noll != 3)) return GSPALN_EINVAL;
+    CKH(cudaSetDevice(ctx->device));
+    const gspaln_h_params& q = ctx->prm;
+    const size_t nm = (size_t) q.simdim * q.simdim;
+    if (ctx->d_ngtab.reserve(544 + (size_t) n_penalty) != cudaSuccess || ctx->d_ngspj.reserve(800) != cudaSuccess ||
+        ctx->d_ngmtx.reserve(nm + 1) != cudaSuccess || ctx->d_ngprm.reserve(1) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, GSPALN_ENOMEM, "device allocation");
+    }
+    CKH(cudaMemcpy(ctx->d_ngtab.p, sig53tab, 544 * sizeof(short), cudaMemcpyHostToDevice));
+    CKH(cudaMemcpy(ctx->d_ngtab.p + 544, penalty, (size_t) n_penalty * sizeof(short), cudaMemcpyHostToDevice));
+    CKH(cudaMemcpy(ctx->d_ngspj.p, spj_tabs, 796, cudaMemcpyHostToDevice));
+    CKH(cudaMemcpy(ctx->d_ngmtx.p, q.simmtx, nm * sizeof(int), cudaMemcpyHostToDevice));
+    DevNgHParams P;
+    memset(&P, 0, sizeof(P));
+    P.gop = q.gop; P.gep = q.gep; P.lgop = q.lgop; P.lgep = q.lgep; P.codonk1 = q.codonk1;
+    P.gw1 = q.gw1; P.gw2 = q.gw2; P.gw3 = q.gw3; P.gw3l = gw3l; P.gape1 = q.gape1; P.gape2 = q.gape2;
+    P.extragop = extragop; P.local = (q.lcl & 16) ? 1 : 0; P.spj = q.spj ? 1 : 0; P.noll = noll; P.minl = minl;
+    P.simdim = q.simdim; P.n_penalty = n_penalty;
+    P.mtx = ctx->d_ngmtx.p; P.penalty = ctx->d_ngtab.p + 544; P.sig53tab = ctx->d_ngtab.p; P.spj_tabs = ctx->d_ngspj.p;
+    CKH(cudaMemcpy(ctx->d_ngprm.p, &P, sizeof(P), cudaMemcpyHostToDevice));
+    ctx->n_pen = n_penalty;
+    ctx->ng_ready = true;
+    return GSPALN_OK;
+}
+
+// the scalar kernel: one thread per problem, raw inputs copied per problem with a margin
+static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gspaln_result* results)
+{
+    if (!ctx->ng_ready) return fail(ctx, GSPALN_EINVAL, "GSPALN_FORWARD_NG needs gspaln_h_set_ng_tables");
+    CKH(cudaSetDevice(ctx->device));
+    std::vector<DevNgHTask> dt(n);
+    std::vector<unsigned char> apool, bpool;
+    std::vector<short> sgpool;
+    std::vector<unsigned short> ipool;
+    size_t skl_elems = 0, work_bytes = 0;
+    int64_t cells_total = 0;
+    for (int i = 0; i < n; ++i) {
+        const gspaln_h_task& t = tasks[i];
+        if (!t.a || !t.b || !t.sg || !t.int53 || t.a_right < t.a_left || t.b_right < t.b_left ||
+            t.up - t.lw + 7 < 0 || t.b_right - t.b_left >= ctx->n_pen)
+            return fail(ctx, GSPALN_EINVAL, "bad GSPALN_FORWARD_NG task");
+        DevNgHTask& d = dt[i];
+        d.a_left = t.a_left; d.a_right = t.a_right; d.b_left = t.b_left; d.b_right = t.b_right;
+        d.lw = t.lw; d.up = t.up;
+        d.a_exgl = t.a_exgl; d.a_exgr = t.a_exgr; d.b_exgl = t.b_exgl; d.b_exgr = t.b_exgr;
+        d.skl_cap = std::max(0, t.skl_cap);
+        const int width = t.up - t.lw + 7;
+        const int64_t cells = gspaln_h_task_cells(&t);
+        cells_total += cells;
+        d.rec_cap = (int) std::min<int64_t>(4 * cells + 4 * width + 64, INT_MAX / 4);
+        // query residues a_left - 1 .. a_right, genome columns b_left - 4 .. b_right + 4 (zeros outside
+        // the sequences, as the terminal residues of the reference's arrays)
+        d.a_lo = t.a_left - 1; d.a_off = (long long) apool.size();
+        for (int p = d.a_lo; p <= t.a_right; ++p) apool.push_back(p >= 0 && p < t.a_len ? t.a[p] : 0);
+        d.b_lo = t.b_left - 4; d.b_off = (long long) bpool.size(); d.sg_off = (long long) ipool.size();
+        for (int p = d.b_lo; p <= t.b_right + 4; ++p) {
+            bpool.push_back(p >= 0 && p < t.b_len ? t.b[p] : 0);
+            const bool in = p >= 0 && p <= t.b_len + 1;
+            const gspaln_sgpt6 z = {0, 0, 0, 0, 0, 0, -2, -2};
+            const gspaln_sgpt6& g = in ? t.sg[p] : z;
+            const short rec[8] = {g.sig5, g.sig3, g.sigS, g.sigT, g.sigE, g.sigI, g.phs5, g.phs3};
+            sgpool.insert(sgpool.end(), rec, rec + 8);
+            ipool.push_back(in ? t.int53[p] : 0);
+        }
+        d.skl_off = (long long) skl_elems; skl_elems += (size_t) d.skl_cap;
+        d.work_off = (long long) work_bytes;
+        work_bytes += align_up((size_t) 3 * (width + 8) * sizeof(HRvpd) + (size_t) d.rec_cap * 12 + 16, 16);
+    }
+    unsigned char *d_a = nullptr, *d_b = nullptr, *d_work = nullptr;
+    short* d_sg = nullptr; unsigned short* d_i = nullptr; DevNgHTask* d_t = nullptr;
+    int2* d_skl = nullptr; DevResult* d_res = nullptr; int* d_tick = nullptr;
+    auto freeall = [&] {
+        cudaFree(d_a); cudaFree(d_b); cudaFree(d_work); cudaFree(d_sg); cudaFree(d_i); cudaFree(d_t);
+        cudaFree(d_skl); cudaFree(d_res); cudaFree(d_tick);
+    };
+    cudaError_t e = cudaSuccess;
+    auto up = [&](void** dp, const void* hp, size_t bytes) {
+        if (e != cudaSuccess) return;
+        e = cudaMalloc(dp, bytes + 16);
+        if (e == cudaSuccess && bytes) e = cudaMemcpy(*dp, hp, bytes, cudaMemcpyHostToDevice);
+    };
+    up((void**) &d_a, apool.data(), apool.size());
+    up((void**) &d_b, bpool.data(), bpool.size());
+    up((void**) &d_sg, sgpool.data(), sgpool.size() * sizeof(short));
+    up((void**) &d_i, ipool.data(), ipool.size() * sizeof(unsigned short));
+    up((void**) &d_t, dt.data(), dt.size() * sizeof(DevNgHTask));
+    if (e == cudaSuccess) e = cudaMalloc((void**) &d_work, work_bytes + 16);
+    if (e == cudaSuccess) e = cudaMalloc((void**) &d_skl, (skl_elems + 1) * sizeof(int2));
+    if (e == cudaSuccess) e = cudaMalloc((void**) &d_res, (size_t) (n + 1) * sizeof(DevResult));
+    if (e == cudaSuccess) e = cudaMalloc((void**) &d_tick, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(d_tick, 0, sizeof(int));
+    if (e != cudaSuccess) { freeall(); cudaGetLastError(); return fail(ctx, GSPALN_ENOMEM, "scalar kernel buffers", e); }
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    const int grid = std::max(1, std::min((n + HNG_THREADS - 1) / HNG_THREADS, 8 * ctx->sm_count));
+    dp_hng_kernel<<<grid, HNG_THREADS, 0, ctx->stream>>>(ctx->d_ngprm.p, d_t, n, d_tick, d_a, d_b, d_sg, d_i,
+                                                         d_work, d_skl, d_res);
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    std::vector<DevResult> hres(n);
+    std::vector<int2> hskl(skl_elems + 1);
+    if (e == cudaSuccess) e = cudaMemcpy(hres.data(), d_res, (size_t) n * sizeof(DevResult), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && skl_elems) e = cudaMemcpy(hskl.data(), d_skl, skl_elems * sizeof(int2), cudaMemcpyDeviceToHost);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+    freeall();
+    if (e != cudaSuccess) return fail(ctx, GSPALN_ECUDA, "scalar kernel", e);
+    memset(&ctx->tim, 0, sizeof(ctx->tim));
+    ctx->tim.kernel_ms = ms; ctx->tim.launches = 1; ctx->tim.cells = cells_total;
+    for (int i = 0; i < n; ++i) {
+        gspaln_result& o = results[i];
+        o.score = hres[i].score; o.status = hres[i].status; o.n_skl = hres[i].n_skl; o.reserved = 0;
+        o.cells = gspaln_h_task_cells(&tasks[i]);
+        if (o.skl && dt[i].skl_cap > 0)
+            memcpy(o.skl, hskl.data() + dt[i].skl_off, sizeof(int2) * (size_t) std::max(0, std::min(o.n_skl, dt[i].skl_cap)));
+    }
+    return GSPALN_OK;
+}
+
+static int h_submit_core(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gspaln_result* results)
 {
     if (!ctx || !tasks || n < 0) return GSPALN_EINVAL;
     int rc = plan_batch_h(ctx, tasks, n);
@@ -647,7 +817,10 @@ struct LspTraitsH {
     static bool is_local(const gspaln_h_params& P) { return (P.lcl & 16) != 0; }
     static bool udh_ok(const gspaln_h_params&) { return true; }
     // no scalar forwardH_ng on the device: blocks with fewer than 8 rows stay unsupported
-    static bool scalar_ok(const gspaln_h_ctx*, const gspaln_h_task&, const LspGeo&) { return false; }
+    static bool scalar_ok(const gspaln_h_ctx* ctx, const gspaln_h_task& base, const LspGeo& g)
+    {
+        return ctx->ng_ready && base.int53 && g.b_right - g.b_left < ctx->n_pen;
+    }
     static int trivial_score(const gspaln_h_params& P, const LspGeo& g, int m, int nn)
     {
         auto ext = [&](int i) { return i > P.codonk1 ? P.lgep : P.gep; };
@@ -686,7 +859,7 @@ struct LspTraitsH {
         t.a_exgl = g.a_exgl; t.a_exgr = g.a_exgr; t.b_exgl = g.b_exgl; t.b_exgr = g.b_exgr;
         t.lw = g.lw; t.up = g.up;
         t.n_imd = n_imd;
-        t.skl_cap = kind == GSPALN_FORWARD_WIP ? (g.a_right - g.a_left) + (g.b_right - g.b_left) + 8 : 0;
+        t.skl_cap = (kind == GSPALN_FORWARD_WIP || kind == GSPALN_FORWARD_NG) ? (g.a_right - g.a_left) + (g.b_right - g.b_left) + 8 : 0;
         return t;
     }
     static int submit(gspaln_h_ctx* ctx, const gspaln_h_task* t, int n, gspaln_result* r) { return gspaln_h_submit(ctx, t, n, r); }

@@ -362,11 +362,14 @@ class ProblemH:
     skl_cap: int = 0
     a_len: int = 0          # Seq::len of the query (0: len(a) - 1, arrays carry one pad residue)
     n_imd: int = 0          # hirschbergH1_wip only: number of intermediate rows
+    int53: np.ndarray = None    # uint16 Exinon::int53[n] nibbles by column (scalar kernel only)
 
     @staticmethod
     def from_export(ex: dict, lw: int, up: int) -> "ProblemH":
         """ex: tests/ref_harness.py::RefTask.export_p() layout (arrays start at at(-1))."""
-        return ProblemH(a=np.ascontiguousarray(ex["a"][1:], np.uint8),
+        return ProblemH(int53=(np.ascontiguousarray(ex["int53"], np.uint16)
+                               if ex.get("int53") is not None else None),
+                        a=np.ascontiguousarray(ex["a"][1:], np.uint8),
                         b=np.ascontiguousarray(ex["b"][1:], np.uint8),
                         sgpt6=capi.sgpt6_from_table(ex["sgpt6"]), b_len=int(ex["blen"]),
                         a_left=ex["a_left"], a_right=ex["a_right"],
@@ -392,6 +395,19 @@ class EngineH:
         self._tasks = None
         self._keep = None
         self._n = 0
+        # tables of the scalar kernel, when the parameter set carries them
+        if all(params.get(k) is not None for k in ("penalty", "sig53tab", "spj_tabs")):
+            tab = np.ascontiguousarray(params["sig53tab"], np.int16)
+            pen = np.ascontiguousarray(params["penalty"], np.int16)
+            spj = np.ascontiguousarray(params["spj_tabs"], np.uint8)
+            self._check(self.lib.gspaln_h_set_ng_tables(
+                self._h, tab.ctypes.data, pen.ctypes.data, pen.size, spj.ctypes.data, int(params["minl"]),
+                int(params["ExtraGOP"]), int(params["GapW3L"]), int(params["Noll"])), "gspaln_h_set_ng_tables")
+
+    def forwardH_ng(self, problems):
+        """Aln2h1::trcbkalignH_ng on its scalar branch (forwardH_ng + Vmf trace-back, exact intron
+        scoring; src/fwd2h1.cc:294-617, 1997-2041): score + corners.  Problems carry int53."""
+        return self.submit(problems, capi.FORWARD_NG)
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -414,17 +430,19 @@ class EngineH:
             sg = np.ascontiguousarray(p.sgpt6, capi.SGPT6_DTYPE)
             if len(a) < p.a_right or len(b) < p.b_right or p.b_len < p.b_right or len(sg) < p.b_len + 2:
                 raise ValueError("problem arrays shorter than the stated ranges")
-            keep.append((a, b, sg))
+            i53 = np.ascontiguousarray(p.int53, np.uint16) if p.int53 is not None else None
+            keep.append((a, b, sg, i53))
             t = arr[i]
             t.kind = kind
             t.a, t.b, t.sg = a.ctypes.data, b.ctypes.data, sg.ctypes.data
+            t.int53 = i53.ctypes.data if i53 is not None else None
             t.b_len = int(p.b_len)
             t.a_left, t.a_right, t.b_left, t.b_right = p.a_left, p.a_right, p.b_left, p.b_right
             t.a_exgl, t.a_exgr, t.b_exgl, t.b_exgr = p.a_exgl, p.a_exgr, p.b_exgl, p.b_exgr
             t.lw, t.up = p.lw, p.up
             t.a_len = int(p.a_len or (len(a) - 1))
             cap = p.skl_cap or ((p.a_right - p.a_left) + (p.b_right - p.b_left) + 8)
-            t.skl_cap = cap if kind == capi.FORWARD_WIP else 0
+            t.skl_cap = cap if kind in (capi.FORWARD_WIP, capi.FORWARD_NG) else 0
             t.n_imd = int(p.n_imd) if kind == capi.HIRSCHBERG_WIP else 0
         return arr, keep
 

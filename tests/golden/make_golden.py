@@ -59,6 +59,7 @@ def gen_protein(name: str):
         out["prm_" + k] = np.asarray(v)
     n = 0
     udh = "udh" in name
+    ng_tables = None
 
     def add(g, q, tag="", **setkw):
         nonlocal n
@@ -80,6 +81,14 @@ def gen_protein(name: str):
         out[pre + "skl"] = r["skl"].astype(np.int32)
         out[pre + "score_only"] = np.int32(r1["score"])
         out[pre + "tag"] = np.array(tag)
+        # scalar kernel (Aln2h1::trcbkalignH_ng, scalar branch) and its extra inputs
+        rn = t.scalar_p(lw, up)
+        out[pre + "int53"] = t.export_int53()
+        out[pre + "ng_score"] = np.int32(rn["score"])
+        out[pre + "ng_skl"] = rn["skl"].astype(np.int32)
+        nonlocal ng_tables
+        if ng_tables is None:
+            ng_tables = t.export_ng_tables(1 << 17)
         if udh:
             # the whole driver (Aln2h1::lspH_ng) and the Hirschberg pass alone
             rl = t.lsp_p(lw, up)
@@ -110,6 +119,11 @@ def gen_protein(name: str):
     g, q, _ = synth.plant_protein_gene(rng, plen_range=(640, 700), n_exons=3, flank=(40, 80))
     add(g, q, tag="rebase")     # > 544 rows: crosses the int16 re-basing check point
     out["n"] = np.int32(n)
+    # inputs of the scalar kernel: Penalty() table, sig53tab, split-codon tables, minl
+    out["prm_penalty"] = ng_tables["penalty"]
+    out["prm_sig53tab"] = ng_tables["sig53tab"]
+    for k, v in ref.scalar_p_tables().items():
+        out["prm_" + k] = np.asarray(v)
     path = HERE / f"{name}.npz"
     np.savez_compressed(path, **out)
     print(name, "problems:", n, "->", path, f"{path.stat().st_size / 1024:.0f} KiB")

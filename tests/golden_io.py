@@ -54,7 +54,8 @@ def load_protein(name):
              "score_only": int(z[pre + "score_only"]), "tag": str(z[pre + "tag"])}
         d.update({k: int(v) for k, v in zip(GEOM_KEYS_P, z[pre + "geom"])})
         d.setdefault("alen", len(d["a"]) - 2)
-        for k in ("lsp_score", "lsp_skl", "udh_nim", "udh_score", "udh_cpos", "udh_ranges"):
+        for k in ("lsp_score", "lsp_skl", "udh_nim", "udh_score", "udh_cpos", "udh_ranges",
+                  "int53", "ng_score", "ng_skl"):
             if pre + k in z.files:
                 v = z[pre + k]
                 d[k] = v if v.ndim else int(v)

@@ -39,7 +39,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(capi.GspalnTask) == 8 + 4 * 8 + 4 * 12 + 8     # ... + int53 pointer
     assert ctypes.sizeof(capi.GspalnResult) == 32 + 16 + 8
     assert ctypes.sizeof(capi.GspalnHParams) == 4 * (10 + 8 + 8 + 4) + 4 * 32 * 32 + 4 * 3
-    assert ctypes.sizeof(capi.GspalnHTask) == 8 + 3 * 8 + 4 * 14
+    assert ctypes.sizeof(capi.GspalnHTask) == 8 + 3 * 8 + 4 * 14 + 8     # ... + int53 pointer
     assert capi.SGPT6_DTYPE.itemsize == 14
 
 

@@ -40,3 +40,14 @@ def test_oracle_protein_udh_and_driver_match_reference_golden(oracle, name):
         assert np.array_equal(o["skl"], pb["lsp_skl"]), (name, i, pb["tag"])
         n_lsp += 1
     assert n_udh >= 10 and n_lsp >= 15
+
+
+@pytest.mark.parametrize("name", golden_io.PROTEIN_NAMES + golden_io.PROTEIN_UDH_NAMES)
+def test_oracle_scalar_protein_kernel_matches_reference_golden(oracle, name):
+    """Aln2h1::trcbkalignH_ng on its scalar branch (forwardH_ng + initH_ng / lastH_ng + Vmf,
+    split-codon translation): the kernel the reference uses for blocks with fewer than 8 rows"""
+    prm, probs = golden_io.load_protein(name)
+    for i, pb in enumerate(probs):
+        o = oracle.trcbk_h_ng(prm, pb)
+        assert o["score"] == pb["ng_score"], (name, i, pb["tag"])
+        assert np.array_equal(o["skl"], pb["ng_skl"]), (name, i, pb["tag"])
