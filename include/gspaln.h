@@ -320,8 +320,9 @@ typedef struct gspaln_h_params {
 } gspaln_h_params;
 
 typedef struct gspaln_h_task {
-    int32_t kind;               /* GSPALN_FORWARD_WIP, GSPALN_SCOREONLY_WIP or GSPALN_HIRSCHBERG_WIP
-                                   (SimdAln2h1::hirschbergH1_wip, src/fwd2h1_wip_simd.h:338-773) */
+    int32_t kind;               /* GSPALN_FORWARD_WIP, GSPALN_SCOREONLY_WIP, GSPALN_HIRSCHBERG_WIP
+                                   (SimdAln2h1::hirschbergH1_wip, src/fwd2h1_wip_simd.h:338-773) or
+                                   GSPALN_FORWARD_NG (scalar forwardH_ng, see gspaln_h_set_ng_tables) */
     const uint8_t* a;           /* amino-acid codes; a[i] == *Seq::at(i) */
     const uint8_t* b;           /* tron codes (Seq::nuc2tron, src/seq.cc:774-798); b[i] == *Seq::at(i) */
     const gspaln_sgpt6* sg;     /* Exinon::data_p[n], n in [0, b_len + 1] */
@@ -361,8 +362,9 @@ const char* gspaln_h_last_error(const gspaln_h_ctx* ctx);
  * single-diagonal case (diagonalH_ng, 1963-1995) on the host, trace-back problems
  * (trcbkalignH_ng, 1997-2041, SIMD branch), Hirschberg passes (hirschbergH1_wip) and the block
  * re-alignments of mimd_postwork / rcsv_postwork (2045-2132, re-banded with stripe31) as device
- * batches, one per recursion level.  Blocks with fewer than 8 query rows need the reference's
- * scalar kernel forwardH_ng and set GSPALN_ST_UNSUPPORTED. */
+ * batches, one per recursion level.  Blocks with fewer than 8 query rows go to the scalar kernel
+ * (GSPALN_FORWARD_NG: forwardH_ng) like in the reference; without gspaln_h_set_ng_tables() /
+ * task.int53 they set GSPALN_ST_UNSUPPORTED. */
 int  gspaln_h_lsp(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, const gspaln_lsp_opts* opts,
                   gspaln_result* results);
 /* amino acid x nucleotide band cells as the scalar reference counts them

@@ -102,6 +102,11 @@ def test_lspH_ng_driver_matches_reference_and_oracle(oracle, name):
             o = oracle.lsp_h(prm, pb, max_vmf_space=vmf)
             # blocks with < 8 query rows run on the scalar kernel (forwardH_ng), like in the reference;
             # the lspH_ng oracle does not restate that branch, the reference fixture does cover it
+            if r.status == 3:
+                # a Hirschberg pass narrowed a range to outside the sequences (the reference reads
+                # foreign memory from there on): reported as unsupported by driver and oracle alike
+                assert o["unsupported"] and pb["a_right"] - pb["a_left"] >= 8, (name, i, pb["tag"])
+                continue
             assert r.status == 0, (name, i, pb["tag"], r.status)
             if not o["unsupported"]:
                 assert r.score == o["score"] and np.array_equal(r.skl, o["skl"]), (name, i, pb["tag"])
