@@ -146,6 +146,8 @@ typedef struct {
     const int32_t* simmtx;  /* [aa code][tron code] */
     int32_t lgop;           /* PwdB::LongGOP (GapPenalty beyond codonk1; driver only) */
     int32_t gape1, gape2;   /* PwdB::GapE1, GapE2 (UnpPenalty3; driver only) */
+    const struct so_ng_h_s* ng; /* driver only: inputs of the scalar kernel for blocks with fewer than 8
+                                   rows (NULL: such blocks are reported as unsupported) */
 } so_params_h;
 
 typedef struct {
@@ -174,7 +176,7 @@ int so_lsp_h(const so_params_h* p, const so_task_h* t, const so_lsp_opts* o, int
              int32_t* skl, int cap, int* unsupported);
 
 /* extra inputs of the scalar protein kernel */
-typedef struct {
+typedef struct so_ng_h_s {
     const int16_t* penalty; int32_t n_penalty;      /* IntronPenalty::Penalty(len) */
     const int16_t* sig53tab;                        /* Exinon::sig53tab[0][0..543] */
     const uint16_t* int53;                          /* INT53 nibbles by column */

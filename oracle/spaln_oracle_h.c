@@ -1041,10 +1041,17 @@ static int drvh_trcbk(so_drvh* d, const so_task_h* t)
     const int width = t->up - t->lw + 7;
     if (width < 0) return NEVSEL32_H;
     const int m = t->a_right - t->a_left;
-    if (m < 8 || t->b_right < t->b_left || t->a_left < 0 || t->b_left < 0 || t->b_right > t->b_len ||
+    if ((m < 8 && !d->p->ng) || t->b_right < t->b_left || t->a_left < 0 || t->b_left < 0 || t->b_right > t->b_len ||
         t->a_right > t->a_len) { d->unsupported = 1; return NEVSEL32_H; }
     int32_t score = 0;
     int room = d->cap > d->n ? d->cap - d->n : 0;
+    if (m < 8) {
+        /* scalar kernel forwardH_ng (src/fwd2h1.cc:2007), restated in spaln_oracle_hng.c */
+        int c = so_trcbk_h_ng(d->p, d->p->ng, t, &score, d->skl + 2 * (d->n < d->cap ? d->n : d->cap), room);
+        if (c < 0) { d->unsupported = 1; return NEVSEL32_H; }
+        d->n += c;
+        return score;
+    }
     int cnt = so_forward_h1_wip(d->p, t, 1, &score, d->skl + 2 * (d->n < d->cap ? d->n : d->cap), room);
     if (cnt < 0) { d->unsupported = 1; return NEVSEL32_H; }
     d->n += cnt;

@@ -301,7 +301,7 @@ class SoParamsH(C.Structure):
                 ("quant_len", C.c_int32 * MAXQ), ("quant_pen", C.c_int32 * MAXQ),
                 ("avmch", C.c_int32), ("local", C.c_int32), ("lcl", C.c_int32), ("spj", C.c_int32),
                 ("simdim", C.c_int32), ("simmtx", C.c_void_p),
-                ("lgop", C.c_int32), ("gape1", C.c_int32), ("gape2", C.c_int32)]
+                ("lgop", C.c_int32), ("gape1", C.c_int32), ("gape2", C.c_int32), ("ng", C.c_void_p)]
 
 
 class SoTaskH(C.Structure):
@@ -371,6 +371,10 @@ def hirschberg_h1_wip(p: dict, t: dict, n_im: int):
 def lsp_h(p: dict, t: dict, cap: int = 1 << 16, max_vmf_space=None):
     """Aln2h1::lspH_ng restatement: score + corner list in Mfile order"""
     sp, st = _params_h(p), _task_h(t)
+    keep = None
+    if all(p.get(k) is not None for k in ("penalty", "sig53tab", "spj_tabs")) and t.get("int53") is not None:
+        keep = _ng_h(p, t)          # blocks with fewer than 8 rows: scalar kernel
+        sp.ng = C.addressof(keep[0])
     o = SoLspOpts(int(max_vmf_space if max_vmf_space is not None else p["MaxVmfSpace"]),
                   int(p["sh"]), int(p["ubh"]), int(p["alg"]))
     score = C.c_int32(0)
@@ -387,10 +391,7 @@ class SoNgH(C.Structure):
                 ("extragop", C.c_int32), ("gw3l", C.c_int32), ("noll", C.c_int32)]
 
 
-def trcbk_h_ng(p: dict, t: dict, cap: int = 1 << 16):
-    """scalar protein kernel (Aln2h1::trcbkalignH_ng's scalar branch): score + corners.  p carries
-    penalty, sig53tab, spj_tabs, minl, ExtraGOP, GapW3L; t carries int53"""
-    sp, st = _params_h(p), _task_h(t)
+def _ng_h(p: dict, t: dict):
     x = SoNgH()
     pen = np.ascontiguousarray(p["penalty"], np.int16)
     tab = np.ascontiguousarray(p["sig53tab"], np.int16)
@@ -399,6 +400,15 @@ def trcbk_h_ng(p: dict, t: dict, cap: int = 1 << 16):
     x.penalty, x.n_penalty, x.sig53tab = pen.ctypes.data, len(pen), tab.ctypes.data
     x.int53, x.spj_tabs = i53.ctypes.data, spj.ctypes.data
     x.minl, x.extragop, x.gw3l, x.noll = int(p["minl"]), int(p["ExtraGOP"]), int(p["GapW3L"]), int(p["Noll"])
+    return x, pen, tab, i53, spj
+
+
+def trcbk_h_ng(p: dict, t: dict, cap: int = 1 << 16):
+    """scalar protein kernel (Aln2h1::trcbkalignH_ng's scalar branch): score + corners.  p carries
+    penalty, sig53tab, spj_tabs, minl, ExtraGOP, GapW3L; t carries int53"""
+    sp, st = _params_h(p), _task_h(t)
+    keep = _ng_h(p, t)
+    x = keep[0]
     score = C.c_int32(0)
     skl = np.zeros((cap, 2), np.int32)
     lib().so_trcbk_h_ng.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
