@@ -404,6 +404,21 @@ class EngineH:
                 self._h, tab.ctypes.data, pen.ctypes.data, pen.size, spj.ctypes.data, int(params["minl"]),
                 int(params["ExtraGOP"]), int(params["GapW3L"]), int(params["Noll"])), "gspaln_h_set_ng_tables")
 
+    def HomScoreH_ng(self, problems):
+        """HomScoreH_ng's kernel choice (src/fwd2h1.cc:3293-3312) for -A2 / -A3: queries shorter than
+        8 residues go to the scalar kernel forwardH_ng (its score does not depend on the path
+        records), the rest to forwardH1_wip without trace-back"""
+        small = [i for i, p in enumerate(problems) if p.a_right - p.a_left < 8]
+        big = [i for i, p in enumerate(problems) if p.a_right - p.a_left >= 8]
+        out = [None] * len(problems)
+        if small:
+            for i, r in zip(small, self.submit([problems[i] for i in small], capi.FORWARD_NG)):
+                out[i] = r
+        if big:
+            for i, r in zip(big, self.submit([problems[i] for i in big], capi.SCOREONLY_WIP)):
+                out[i] = r
+        return out
+
     def forwardH_ng(self, problems):
         """Aln2h1::trcbkalignH_ng on its scalar branch (forwardH_ng + Vmf trace-back, exact intron
         scoring; src/fwd2h1.cc:294-617, 1997-2041): score + corners.  Problems carry int53."""

@@ -210,3 +210,15 @@ def test_scalar_protein_kernel_matches_reference_and_oracle(oracle, name):
         assert r.status == 0 and r.score == pb["ng_score"], (name, i, pb["tag"], r.status, r.score, pb["ng_score"])
         assert np.array_equal(r.skl, pb["ng_skl"]), (name, i, pb["tag"])
     eng.close()
+
+
+def test_homscore_protein_dispatch_matches_reference_golden():
+    """HomScoreH_ng: m < 8 -> forwardH_ng (scalar), otherwise forwardH1_wip(0) (src/fwd2h1.cc:3301-3309)"""
+    from spaln_b200 import EngineH
+    prm, probs = golden_io.load_protein("prot_A2_global")
+    eng = EngineH(prm, device=0)
+    res = eng.HomScoreH_ng(_problems(probs))
+    for pb, r in zip(probs, res):
+        small = pb["a_right"] - pb["a_left"] < 8
+        assert r.score == (pb["ng_score"] if small else pb["score_only"]), pb["tag"]
+    eng.close()
