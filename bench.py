@@ -167,9 +167,20 @@ def reference_run(raw, steps, warmup, threads, lsp=False):
         tasks.append(t)
     cells = sum(int(r["cells"]) for r in raw)
     out = [None] * len(tasks)
+    # shared work queue, largest problems first: every host thread stays busy until the sample is
+    # done (the ctypes call releases the GIL), as the reference's own pthread queue does
+    order = sorted(range(len(tasks)), key=lambda i: -int(raw[i]["cells"]))
+    nxt = [0]
+    lock = threading.Lock()
 
-    def work(tid):
-        for i in range(tid, len(tasks), threads):
+    def work():
+        while True:
+            with lock:
+                k = nxt[0]
+                nxt[0] += 1
+            if k >= len(order):
+                return
+            i = order[k]
             if lsp:     # the whole driver: trace-back vs UDH dispatch at the default -V
                 out[i] = tasks[i].lsp(raw[i]["lw"], raw[i]["up"], cap=4096)
             else:
@@ -177,8 +188,9 @@ def reference_run(raw, steps, warmup, threads, lsp=False):
 
     times = []
     for s in range(warmup + steps):
+        nxt[0] = 0
         t0 = time.perf_counter()
-        th = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+        th = [threading.Thread(target=work) for _ in range(threads)]
         [x.start() for x in th]
         [x.join() for x in th]
         dt = time.perf_counter() - t0

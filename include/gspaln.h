@@ -196,6 +196,10 @@ int  gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n, const gspaln_l
 typedef struct gspaln_queue gspaln_queue;
 int  gspaln_queue_create(gspaln_queue** out, gspaln_ctx* ctx, int max_batch, int max_wait_us);
 int  gspaln_queue_submit(gspaln_queue* q, const gspaln_task* task, gspaln_result* result);
+/* the same for whole driver calls: one Aln2s1::lspS_ng call (src/fwd2s1.cc:1801-1897) per worker,
+ * coalesced into gspaln_lsp() batches (calls with equal options share a batch) */
+int  gspaln_queue_submit_lsp(gspaln_queue* q, const gspaln_task* task, const gspaln_lsp_opts* opts,
+                             gspaln_result* result);
 int  gspaln_queue_stats(const gspaln_queue* q, int64_t* tasks, int64_t* batches);
 void gspaln_queue_destroy(gspaln_queue* q);
 
@@ -367,6 +371,15 @@ const char* gspaln_h_last_error(const gspaln_h_ctx* ctx);
  * task.int53 they set GSPALN_ST_UNSUPPORTED. */
 int  gspaln_h_lsp(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, const gspaln_lsp_opts* opts,
                   gspaln_result* results);
+/* coalescing queue of the protein path: as gspaln_queue_* (Aln2h1::trcbkalignH_ng / lspH_ng calls
+ * of the pthread workers, src/spaln.cc:1363-1468) */
+typedef struct gspaln_h_queue gspaln_h_queue;
+int  gspaln_h_queue_create(gspaln_h_queue** out, gspaln_h_ctx* ctx, int max_batch, int max_wait_us);
+int  gspaln_h_queue_submit(gspaln_h_queue* q, const gspaln_h_task* task, gspaln_result* result);
+int  gspaln_h_queue_submit_lsp(gspaln_h_queue* q, const gspaln_h_task* task, const gspaln_lsp_opts* opts,
+                               gspaln_result* result);
+int  gspaln_h_queue_stats(const gspaln_h_queue* q, int64_t* tasks, int64_t* batches);
+void gspaln_h_queue_destroy(gspaln_h_queue* q);
 /* amino acid x nucleotide band cells as the scalar reference counts them
  * (Aln2h1::forwardH_ng inner loop, src/fwd2h1.cc:326-331) */
 int64_t gspaln_h_task_cells(const gspaln_h_task* t);

@@ -49,10 +49,6 @@ int shim_h1_scalar(const Seq** seqs, const PwdB* pwd, int lw, int up, int* score
 void shim_h1_spj_tables(unsigned char* out);
 int shim_h1_kernel(const Seq** seqs, const PwdB* pwd, int lw, int up, int kind,
 	int* score, int* skl_out, int cap, double* seconds);
-int shim_s1_adapter(const Seq** seqs, const PwdB* pwd, int lw, int up,
-	int kind, int device, int* score, int* skl_out, int cap);
-int shim_s1_adapter_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up, int device,
-	const void* int53, const short* sig53tab, int* score, int* skl_out, int cap);
 }
 
 namespace {
@@ -326,13 +322,21 @@ int ref_task_kernel(void* h, int lw, int up, int kind, int n_imd, int mode,
 	    mode, score, skl_out, cap, cpos_out, seconds);
 }
 
-// drop-in check: the same problem through include/gspaln_spaln_adapter.hpp (needs a GPU)
-int ref_task_adapter(void* h, int lw, int up, int kind, int device,
-	int* score, int* skl_out, int cap)
+// raw handles for oracle/dropin_shim.cc (libspaln_dropin.so), which runs the same Seq / PwdB
+// objects through include/gspaln_spaln_adapter.hpp
+const void* ref_pwd() { return g_pwd; }
+void* ref_task_seqs(void* h) { return ((RefTask*) h)->sqs; }
+const void* ref_task_int53_ptr(void* h)
 {
-	RefTask* t = (RefTask*) h;
-	return shim_s1_adapter((const Seq**) t->sqs, g_pwd, lw, up, kind, device,
-	    score, skl_out, cap);
+	const Seq* b = ((RefTask*) h)->sqs[1];
+	return b->exin? (const void*) (b->exin->*get(ExinonInt53())): 0;
+}
+const void* ref_task_sig53tab_ptr(void* h)
+{
+	const Seq* b = ((RefTask*) h)->sqs[1];
+	if (!b->exin) return 0;
+	STYPE** tab = b->exin->*get(ExinonTab());
+	return tab? (const void*) tab[0]: 0;
 }
 
 // inputs of the exact intron scoring (Aln2s1::forwardS_ng): per column n = 0 .. b.len + 1 the
@@ -454,16 +458,6 @@ int ref_task_scalar(void* h, int lw, int up, int* score, int* skl_out, int cap, 
 	return shim_s1_scalar((const Seq**) t->sqs, g_pwd, lw, up, score, skl_out, cap, seconds);
 }
 
-// drop-in check of the whole driver: Aln2s1::lspS_ng through the adapter (needs a GPU)
-int ref_task_adapter_lsp(void* h, int lw, int up, int device, int* score, int* skl_out, int cap)
-{
-	RefTask* t = (RefTask*) h;
-	const Seq* b = t->sqs[1];
-	const INT53* i53 = b->exin? b->exin->*get(ExinonInt53()): 0;
-	STYPE** tab = b->exin? b->exin->*get(ExinonTab()): 0;
-	return shim_s1_adapter_lsp((const Seq**) t->sqs, g_pwd, lw, up, device, i53,
-	    tab? tab[0]: 0, score, skl_out, cap);
-}
 
 int ref_task_lsp(void* h, int lw, int up, int* score, int* skl_out, int cap,
 	double* seconds)

@@ -13,10 +13,6 @@
 #include <chrono>
 #include <cwchar>
 #include "fwd2s1.cc"
-// the adapter a Spaln maintainer would add (include/gspaln_spaln_adapter.hpp),
-// compiled here against the reference headers so that tests can run it as a
-// true drop-in inside the reference process
-#include "gspaln_spaln_adapter.hpp"
 
 namespace {
 
@@ -140,41 +136,6 @@ int shim_s1_scorealone(const Seq** seqs, const PwdB* pwd, int lw, int up)
 	WINDOW wdw = {lw, up, up - lw + 3};
 	Aln2s1 alnv(seqs, pwd);
 	return (int) alnv.scorealoneS_ng(wdw);
-}
-
-// same call as shim_s1_kernel(kind 0 | 1) but through the gspaln adapter (GPU)
-int shim_s1_adapter(const Seq** seqs, const PwdB* pwd, int lw, int up,
-	int kind, int device, int* score, int* skl_out, int cap)
-{
-	static gspaln::SpalnEngine* eng = 0;
-	if (!eng) eng = new gspaln::SpalnEngine(pwd, device, seqs[1]->inex.intr);
-	WINDOW wdw = {lw, up, up - lw + 3};
-	if (kind == 1) {
-	    *score = eng->scoreonlyS1_wip(seqs, wdw);
-	    return 0;
-	}
-	Mfile mfd(sizeof(SKL));
-	*score = eng->forwardS1_wip(seqs, wdw, &mfd);
-	return copy_out(mfd, (SKL*) skl_out, cap);
-}
-
-// Aln2s1::lspS_ng through the adapter (GPU): int53 / sig53tab come from the caller because they
-// are private to Exinon (the main shim reads them, see ref_shim_main.cc).  Returns the number
-// of corners, or -1 if the adapter reports the problem as unsupported.
-int shim_s1_adapter_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up, int device,
-	const void* int53, const short* sig53tab, int* score, int* skl_out, int cap)
-{
-	static gspaln::SpalnEngine* eng = 0;
-	if (!eng) {
-	    eng = new gspaln::SpalnEngine(pwd, device, seqs[1]->inex.intr);
-	    if (sig53tab) eng->enable_scalar(pwd, sig53tab, 1 << 19);
-	}
-	WINDOW wdw = {lw, up, up - lw + 3};
-	Mfile mfd(sizeof(SKL));
-	VTYPE scr = 0;
-	if (!eng->lspS_ng(seqs, wdw, &mfd, (const INT53*) int53, &scr)) return -1;
-	*score = scr;
-	return copy_out(mfd, (SKL*) skl_out, cap);
 }
 
 }	// extern "C"

@@ -34,6 +34,8 @@ EXPORTS = [
     "gspaln_h_download", "gspaln_h_get_timing", "gspaln_h_last_error", "gspaln_h_task_cells",
     "gspaln_h_lsp", "gspaln_h_set_ng_tables",
     "gspaln_queue_create", "gspaln_queue_submit", "gspaln_queue_stats", "gspaln_queue_destroy",
+    "gspaln_queue_submit_lsp", "gspaln_h_queue_create", "gspaln_h_queue_submit",
+    "gspaln_h_queue_submit_lsp", "gspaln_h_queue_stats", "gspaln_h_queue_destroy",
     "gspaln_scan_create", "gspaln_scan_destroy", "gspaln_exinon_scan", "gspaln_scan_upload",
     "gspaln_scan_run", "gspaln_scan_download", "gspaln_scan_get_timing", "gspaln_scan_last_error",
     "gspaln_nuc2tron", "gspaln_scan_create_p", "gspaln_exinon_scan_p",

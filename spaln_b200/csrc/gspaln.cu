@@ -20,10 +20,6 @@
 #include <cstring>
 #include <numeric>
 #include <string>
-#include <condition_variable>
-#include <deque>
-#include <mutex>
-#include <thread>
 #include <vector>
 
 using namespace gspaln;
@@ -771,8 +767,14 @@ struct LspTraitsS {
     }
     static int trivial_score(const gspaln_params& P, const LspGeo& g, int m, int nn)
     {
-        if (m) return (g.a_exgl || g.a_exgr) ? P.gep : (P.gop + m * P.gep);
-        return (g.b_exgl || g.b_exgr) ? P.gep : nn * P.gep;
+        // PwdB::GapPenalty / GapExtPen / UnpPenalty (src/aln.h:275-287).  Double affine
+        // (Noll == 3): beyond codonk1 = k1 residues the long-gap terms apply; k1 follows from
+        // LongGOP = BasicGOP - diffu * k1 with diffu = LongGEP - BasicGEP (src/aln2.cc:109-114).
+        const int diffu = P.lgep - P.gep;
+        const int k1 = (P.noll == 3 && diffu) ? (P.gop - P.lgop) / diffu : INT_MAX;
+        auto ext = [&](int i) { return i > k1 ? P.lgep : P.gep; };
+        if (m) return (g.a_exgl || g.a_exgr) ? ext(m) : (m > k1 ? P.lgop + m * P.lgep : P.gop + m * P.gep);
+        return (g.b_exgl || g.b_exgr) ? ext(nn) : (nn <= k1 ? nn * P.gep : nn * P.gep + diffu * (nn - k1));
     }
     static void diagonal(const gspaln_params& P, const gspaln_task& base, const LspGeo& g, int (&c4)[4], int& score)
     {
@@ -824,63 +826,10 @@ extern "C" int gspaln_lsp(gspaln_ctx* ctx, const gspaln_task* tasks, int n,
 }
 
 // ---------------------------------------------------------------------------
-// coalescing queue (include/gspaln.h): one dispatcher thread turns the single-task calls of
-// many host threads into batched submits
+// coalescing queue (include/gspaln.h): one dispatcher thread turns the single-problem calls of
+// many host threads into batched gspaln_submit / gspaln_lsp calls (gspaln_host.hpp)
 // ---------------------------------------------------------------------------
-struct gspaln_queue {
-    struct Item {
-        const gspaln_task* task;
-        gspaln_result* result;
-        int rc = 0;
-        bool done = false;
-    };
-    gspaln_ctx* ctx = nullptr;
-    int max_batch = 256, max_wait_us = 200;
-    std::mutex mu;
-    std::condition_variable cv_work, cv_done;
-    std::deque<Item*> pending;
-    bool stop = false;
-    int64_t n_tasks = 0, n_batches = 0;
-    std::thread worker;
-
-    void run()
-    {
-        std::vector<Item*> take;
-        std::vector<gspaln_task> tasks;
-        std::vector<gspaln_result> results;
-        for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv_work.wait(lk, [&] { return stop || !pending.empty(); });
-                if (stop && pending.empty()) return;
-                // stragglers: the other workers are usually a few microseconds behind
-                if ((int) pending.size() < max_batch && max_wait_us > 0)
-                    cv_work.wait_for(lk, std::chrono::microseconds(max_wait_us),
-                                     [&] { return stop || (int) pending.size() >= max_batch; });
-                take.clear();
-                while (!pending.empty() && (int) take.size() < max_batch) {
-                    take.push_back(pending.front());
-                    pending.pop_front();
-                }
-            }
-            tasks.resize(take.size());
-            results.resize(take.size());
-            for (size_t i = 0; i < take.size(); ++i) { tasks[i] = *take[i]->task; results[i] = *take[i]->result; }
-            const int rc = gspaln_submit(ctx, tasks.data(), (int) tasks.size(), results.data());
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                for (size_t i = 0; i < take.size(); ++i) {
-                    *take[i]->result = results[i];
-                    take[i]->rc = rc;
-                    take[i]->done = true;
-                }
-                n_tasks += (int64_t) take.size();
-                ++n_batches;
-            }
-            cv_done.notify_all();
-        }
-    }
-};
+struct gspaln_queue : gspaln::CoalescingQueue<gspaln_ctx, gspaln_task, gspaln_result, gspaln_lsp_opts> {};
 
 extern "C" {
 
@@ -889,9 +838,12 @@ int gspaln_queue_create(gspaln_queue** out, gspaln_ctx* ctx, int max_batch, int 
     if (!out || !ctx) return GSPALN_EINVAL;
     gspaln_queue* q = new gspaln_queue;
     q->ctx = ctx;
+    q->submit_fn = gspaln_submit;
+    q->lsp_fn = gspaln_lsp;
+    q->einval = GSPALN_EINVAL;
     if (max_batch > 0) q->max_batch = max_batch;
     if (max_wait_us >= 0) q->max_wait_us = max_wait_us;
-    q->worker = std::thread([q] { q->run(); });
+    q->start();
     *out = q;
     return GSPALN_OK;
 }
@@ -899,33 +851,27 @@ int gspaln_queue_create(gspaln_queue** out, gspaln_ctx* ctx, int max_batch, int 
 int gspaln_queue_submit(gspaln_queue* q, const gspaln_task* task, gspaln_result* result)
 {
     if (!q || !task || !result) return GSPALN_EINVAL;
-    gspaln_queue::Item it;
-    it.task = task; it.result = result;
-    std::unique_lock<std::mutex> lk(q->mu);
-    if (q->stop) return GSPALN_EINVAL;
-    q->pending.push_back(&it);
-    q->cv_work.notify_one();
-    q->cv_done.wait(lk, [&] { return it.done; });
-    return it.rc;
+    return q->submit(task, nullptr, result);
+}
+
+int gspaln_queue_submit_lsp(gspaln_queue* q, const gspaln_task* task, const gspaln_lsp_opts* opts,
+                            gspaln_result* result)
+{
+    if (!q || !task || !opts || !result) return GSPALN_EINVAL;
+    return q->submit(task, opts, result);
 }
 
 int gspaln_queue_stats(const gspaln_queue* q, int64_t* tasks, int64_t* batches)
 {
     if (!q) return GSPALN_EINVAL;
-    if (tasks) *tasks = q->n_tasks;
-    if (batches) *batches = q->n_batches;
+    const_cast<gspaln_queue*>(q)->stats(tasks, batches);
     return GSPALN_OK;
 }
 
 void gspaln_queue_destroy(gspaln_queue* q)
 {
     if (!q) return;
-    {
-        std::lock_guard<std::mutex> lk(q->mu);
-        q->stop = true;
-    }
-    q->cv_work.notify_all();
-    if (q->worker.joinable()) q->worker.join();
+    q->shutdown();
     delete q;
 }
 

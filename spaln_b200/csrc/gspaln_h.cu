@@ -825,9 +825,12 @@ struct LspTraitsH {
     {
         auto ext = [&](int i) { return i > P.codonk1 ? P.lgep : P.gep; };
         if (m) return (g.a_exgl || g.a_exgr) ? ext(m) : (m > P.codonk1 ? P.lgop + m * P.lgep : P.gop + m * P.gep);
-        // PwdB::UnpPenalty3 (src/aln.h:289-301), i <= codonk1
-        return (g.b_exgl || g.b_exgr) ? ext(nn)
-                                      : (nn / 3) * P.gep + (nn % 3 == 1 ? P.gape1 : (nn % 3 == 2 ? P.gape2 : 0));
+        // PwdB::UnpPenalty3 (src/aln.h:290-301); beyond codonk1 (= 3 k1 nt) the long-gap slope
+        // enters as -diffu (d - k1), diffu = LongGEP - BasicGEP
+        if (g.b_exgl || g.b_exgr) return ext(nn);
+        const int d = nn / 3;
+        const int unp = d * P.gep + (nn % 3 == 1 ? P.gape1 : (nn % 3 == 2 ? P.gape2 : 0));
+        return nn <= P.codonk1 ? unp : unp - (P.lgep - P.gep) * (d - P.codonk1 / 3);
     }
     static void diagonal(const gspaln_h_params& P, const gspaln_h_task& t, const LspGeo& g, int (&c4)[4], int& score)
     {
@@ -873,3 +876,52 @@ extern "C" int gspaln_h_lsp(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n
 {
     return lsp_driver<LspTraitsH>(ctx, tasks, n, opts, results);
 }
+
+// coalescing queue of the protein path (same dispatcher as the DNA one, gspaln_host.hpp)
+struct gspaln_h_queue : gspaln::CoalescingQueue<gspaln_h_ctx, gspaln_h_task, gspaln_result, gspaln_lsp_opts> {};
+
+extern "C" {
+
+int gspaln_h_queue_create(gspaln_h_queue** out, gspaln_h_ctx* ctx, int max_batch, int max_wait_us)
+{
+    if (!out || !ctx) return GSPALN_EINVAL;
+    gspaln_h_queue* q = new gspaln_h_queue;
+    q->ctx = ctx;
+    q->submit_fn = gspaln_h_submit;
+    q->lsp_fn = gspaln_h_lsp;
+    q->einval = GSPALN_EINVAL;
+    if (max_batch > 0) q->max_batch = max_batch;
+    if (max_wait_us >= 0) q->max_wait_us = max_wait_us;
+    q->start();
+    *out = q;
+    return GSPALN_OK;
+}
+
+int gspaln_h_queue_submit(gspaln_h_queue* q, const gspaln_h_task* task, gspaln_result* result)
+{
+    if (!q || !task || !result) return GSPALN_EINVAL;
+    return q->submit(task, nullptr, result);
+}
+
+int gspaln_h_queue_submit_lsp(gspaln_h_queue* q, const gspaln_h_task* task, const gspaln_lsp_opts* opts,
+                              gspaln_result* result)
+{
+    if (!q || !task || !opts || !result) return GSPALN_EINVAL;
+    return q->submit(task, opts, result);
+}
+
+int gspaln_h_queue_stats(const gspaln_h_queue* q, int64_t* tasks, int64_t* batches)
+{
+    if (!q) return GSPALN_EINVAL;
+    const_cast<gspaln_h_queue*>(q)->stats(tasks, batches);
+    return GSPALN_OK;
+}
+
+void gspaln_h_queue_destroy(gspaln_h_queue* q)
+{
+    if (!q) return;
+    q->shutdown();
+    delete q;
+}
+
+}   // extern "C"

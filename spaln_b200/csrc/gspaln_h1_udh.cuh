@@ -73,7 +73,13 @@ dp_h1_udh_kernel(const DevParamsH* __restrict__ gP, const int2* __restrict__ gpe
         const DevTaskH t = tasks[ti];
         if (t.kind != 2) continue;
         if (!wait_inputs(ready, tk)) {
-            if (lane == 0) { DevUdhOutH r; memset(&r, 0, sizeof(r)); r.status = 4; results[ti] = r; }
+            if (lane == 0) {
+                // inputs never arrived: no crossing records (the driver skips the post-work)
+                DevUdhOutH r; memset(&r, 0, sizeof(r)); r.status = 4; r.score = INT_MIN / 16 * 7; results[ti] = r;
+                int* cp = cpospool + (t.pad1 & ((1ll << 40) - 1));
+                const int nim = (int) (t.pad1 >> 40);
+                for (int i = 0; i <= nim; ++i) cp[10 * i] = cp[10 * i + 2] = INT_MAX - 2;
+            }
             continue;
         }
         const int n_im = (int) (t.pad1 >> 40);

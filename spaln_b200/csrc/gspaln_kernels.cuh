@@ -135,7 +135,9 @@ struct WarpMax { int val, mr, nr, err; };
 
 // One-shot submits stream the batch in while the persistent kernel runs: `ready` counts the
 // problems (in ticket order) whose inputs have arrived in HBM.  Returns false on time-out
-// (~4 s: the host died or a copy failed) so that the kernel never spins forever.
+// (1 << 36 cycles, ~35 s: the host died or a copy failed -- far beyond what a loaded host needs
+// to pack the next chunk) so that the kernel never spins forever; the problem then carries
+// status GSPALN_ST_INTERNAL and the drivers skip its post-work.
 __device__ __forceinline__ bool wait_inputs(const int* ready, int tk)
 {
     if (!ready) return true;
@@ -145,7 +147,7 @@ __device__ __forceinline__ bool wait_inputs(const int* ready, int tk)
         const long long t0 = clock64();
         while (*r <= tk) {
             __nanosleep(256);
-            if (clock64() - t0 > (1ll << 33)) { ok = 0; break; }
+            if (clock64() - t0 > (1ll << 36)) { ok = 0; break; }
         }
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);

@@ -256,6 +256,13 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
             const gspaln_result& r = bres[k];
             const int* cpos = cposbuf[k].data();
             items[id].score = r.score;
+            if (r.status != GSPALN_ST_OK) {
+                // the pass did not run to its end (e.g. its inputs never arrived): no post-work on
+                // records that were not written
+                status[items[id].root] = r.status;
+                items[id].score = NEVSEL;
+                continue;
+            }
             if (!(r.score > NEVSEL)) continue;
             LspGeo g = items[id].g;
             g.a_left = r.ranges[0]; g.a_right = r.ranges[1]; g.b_left = r.ranges[2]; g.b_right = r.ranges[3];

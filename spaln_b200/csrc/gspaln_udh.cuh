@@ -436,7 +436,12 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
         const DevTask t = tasks[ti];
         if (t.kind != 2) continue;
         if (!wait_inputs(ready, tk)) {
-            if (lane == 0) { DevUdhOut r; memset(&r, 0, sizeof(r)); r.status = 4; results[ti] = r; }
+            if (lane == 0) {
+                // inputs never arrived: no crossing records (the driver skips the post-work)
+                DevUdhOut r; memset(&r, 0, sizeof(r)); r.status = 4; r.score = INT_MIN / 16 * 7; results[ti] = r;
+                int* cp = cpospool + t.pad1;
+                for (int i = 0; i <= t.pad0; ++i) cp[10 * i] = cp[10 * i + 2] = INT_MAX - 2;
+            }
             continue;
         }
         const unsigned char* aseq = apool + t.a_off;

@@ -116,7 +116,10 @@ class Engine:
 
     def __init__(self, params: dict, device: int = 0):
         self.lib = capi.load()
-        self._gp = capi.make_params(params)
+        raw = isinstance(params, capi.GspalnParams)     # a frozen gspaln_params as the C-ABI takes it
+        self._gp = params if raw else capi.make_params(params)
+        if raw:
+            params = {}
         self._h = C.c_void_p()
         rc = self.lib.gspaln_create(C.byref(self._h), C.byref(self._gp), device)
         if rc != 0:
@@ -385,7 +388,10 @@ class EngineH:
 
     def __init__(self, params: dict, device: int = 0):
         self.lib = capi.load()
-        self._gp = capi.make_h_params(params)
+        raw = isinstance(params, capi.GspalnHParams)
+        self._gp = params if raw else capi.make_h_params(params)
+        if raw:
+            params = {}
         self._h = C.c_void_p()
         rc = self.lib.gspaln_h_create(C.byref(self._h), C.byref(self._gp), device)
         if rc != 0:
@@ -397,12 +403,17 @@ class EngineH:
         self._n = 0
         # tables of the scalar kernel, when the parameter set carries them
         if all(params.get(k) is not None for k in ("penalty", "sig53tab", "spj_tabs")):
-            tab = np.ascontiguousarray(params["sig53tab"], np.int16)
-            pen = np.ascontiguousarray(params["penalty"], np.int16)
-            spj = np.ascontiguousarray(params["spj_tabs"], np.uint8)
-            self._check(self.lib.gspaln_h_set_ng_tables(
-                self._h, tab.ctypes.data, pen.ctypes.data, pen.size, spj.ctypes.data, int(params["minl"]),
-                int(params["ExtraGOP"]), int(params["GapW3L"]), int(params["Noll"])), "gspaln_h_set_ng_tables")
+            self.set_ng_tables(params["sig53tab"], params["penalty"], params["spj_tabs"], int(params["minl"]),
+                               int(params["ExtraGOP"]), int(params["GapW3L"]), int(params["Noll"]))
+
+    def set_ng_tables(self, sig53tab, penalty, spj_tabs, minl, extragop, gw3l, noll):
+        """tables of the scalar kernel forwardH_ng (gspaln_h_set_ng_tables)"""
+        tab = np.ascontiguousarray(sig53tab, np.int16)
+        pen = np.ascontiguousarray(penalty, np.int16)
+        spj = np.ascontiguousarray(spj_tabs, np.uint8)
+        self._check(self.lib.gspaln_h_set_ng_tables(
+            self._h, tab.ctypes.data, pen.ctypes.data, pen.size, spj.ctypes.data, int(minl),
+            int(extragop), int(gw3l), int(noll)), "gspaln_h_set_ng_tables")
 
     def HomScoreH_ng(self, problems):
         """HomScoreH_ng's kernel choice (src/fwd2h1.cc:3293-3312) for -A2 / -A3: queries shorter than

@@ -42,6 +42,24 @@ def revcomp(s: str) -> str:
     return s.translate(_COMP)[::-1]
 
 
+_DROPIN = None
+
+
+def dropin_lib():
+    """oracle/_ref/libspaln_dropin.so: the adapter of include/ compiled against the reference
+    (links libgspaln; separate from libspaln_ref.so so that the CPU arm never maps the product)"""
+    global _DROPIN
+    if _DROPIN is None:
+        D = C.CDLL(str(REF_DIR / "libspaln_dropin.so"))
+        V = C.c_void_p
+        D.dropin_s1_adapter.argtypes = [V, V, C.c_int, C.c_int, C.c_int, C.c_int, V, V, C.c_int]
+        D.dropin_h1_adapter.argtypes = [V, V, C.c_int, C.c_int, C.c_int, C.c_int, V, V, C.c_int]
+        D.dropin_s1_adapter_lsp.argtypes = [V, V, C.c_int, C.c_int, C.c_int, V, V, V, V, C.c_int]
+        D.dropin_h1_adapter_lsp.argtypes = [V, V, C.c_int, C.c_int, C.c_int, V, V, V, V, V, C.c_int]
+        _DROPIN = D
+    return _DROPIN
+
+
 class Reference:
     """One process-wide reference set-up (the reference keeps its parameters
     in globals, so a process can hold exactly one option string)."""
@@ -71,9 +89,10 @@ class Reference:
                                       C.c_void_p, C.c_void_p]
         L.ref_task_lsp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_void_p]
-        L.ref_task_adapter.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                                       C.c_void_p, C.c_void_p, C.c_int]
-        L.ref_task_adapter_lsp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        for fn in ("ref_pwd", "ref_task_seqs", "ref_task_int53_ptr", "ref_task_sig53tab_ptr"):
+            getattr(L, fn).restype = C.c_void_p
+        for fn in ("ref_task_seqs", "ref_task_int53_ptr", "ref_task_sig53tab_ptr"):
+            getattr(L, fn).argtypes = [C.c_void_p]
         L.ref_task_export_p.argtypes = [C.c_void_p] * 4
         L.ref_get_params_p.argtypes = [C.c_void_p, C.c_int]
         L.ref_task_inject_p.argtypes = [C.c_void_p, C.c_void_p]
@@ -340,20 +359,31 @@ class RefTask:
                 "seconds": secs.value,
                 "ranges": [after["a_left"], after["a_right"], after["b_left"], after["b_right"]]}
 
-    def adapter(self, lw, up, kind=0, device=0, cap=1 << 16):
-        """the same problem through include/gspaln_spaln_adapter.hpp (GPU drop-in)"""
+    def adapter(self, lw, up, kind=0, device=0, cap=1 << 16, protein=False):
+        """the same problem through include/gspaln_spaln_adapter.hpp (GPU drop-in):
+        SpalnEngine::forwardS1_wip / scoreonlyS1_wip, or SpalnEngineH::forwardH1_wip"""
+        D = dropin_lib()
         score = C.c_int(0)
         skl = np.zeros((cap, 2), np.int32)
-        n = self.lib.ref_task_adapter(self.h, lw, up, kind, device, C.byref(score),
-                                      skl.ctypes.data, cap)
+        fn = D.dropin_h1_adapter if protein else D.dropin_s1_adapter
+        n = fn(self.lib.ref_task_seqs(self.h), self.lib.ref_pwd(), lw, up, kind, device, C.byref(score),
+               skl.ctypes.data, cap)
         return {"score": score.value, "skl": skl[:n].copy()}
 
-    def adapter_lsp(self, lw, up, device=0, cap=1 << 16):
-        """Aln2s1::lspS_ng through include/gspaln_spaln_adapter.hpp (GPU drop-in of the driver);
-        returns None if the adapter reports the problem as unsupported"""
+    def adapter_lsp(self, lw, up, device=0, cap=1 << 16, protein=False, spj_tabs=None):
+        """Aln2s1::lspS_ng / Aln2h1::lspH_ng through include/gspaln_spaln_adapter.hpp (GPU drop-in
+        of the driver); returns None if the adapter reports the problem as unsupported"""
+        D = dropin_lib()
         score = C.c_int(0)
         skl = np.zeros((cap, 2), np.int32)
-        n = self.lib.ref_task_adapter_lsp(self.h, lw, up, device, C.byref(score), skl.ctypes.data, cap)
+        common = (self.lib.ref_task_seqs(self.h), self.lib.ref_pwd(), lw, up, device,
+                  self.lib.ref_task_int53_ptr(self.h), self.lib.ref_task_sig53tab_ptr(self.h))
+        if protein:
+            tabs = np.ascontiguousarray(spj_tabs, np.uint8) if spj_tabs is not None else None
+            n = D.dropin_h1_adapter_lsp(*common, tabs.ctypes.data if tabs is not None else None,
+                                        C.byref(score), skl.ctypes.data, cap)
+        else:
+            n = D.dropin_s1_adapter_lsp(*common, C.byref(score), skl.ctypes.data, cap)
         if n < 0:
             return None
         return {"score": score.value, "skl": skl[:n].copy()}
