@@ -414,31 +414,25 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         }
         ctx->grid_run_trace = gt;
         ctx->grid_run_score = gs;
-        // scalar kernel: one thread per problem, workspace = band rows + direction bytes + records
-        ctx->grid_run_ng = 0;
-        if (n_ng) {
-            const size_t slab = align_up(3 * ng_width * sizeof(NgRvp) + align_up(ng_width, 16) + 12 * ng_rec, 16);
-            int g = std::min((n_ng + NG_THREADS - 1) / NG_THREADS, 4 * ctx->sm_count);
+        // exact-ILD kernels: one warp per problem, per-warp workspace = band rows (H, F, F2 as
+        // {value, record}) + direction bytes + path records; the trace-back and the score-only
+        // kernel never run at the same time, so they share the pool
+        ctx->grid_run_ng = ctx->grid_run_ngs = 0;
+        if (n_ng || n_ngs) {
+            const size_t w = std::max(ng_width, ngs_width);
+            const size_t rec = n_ng ? ng_rec + 32 * NG_CHUNK + 64 : 64;
+            const size_t slab = align_up(3 * w * sizeof(NgRvp) + align_up(w, 16) + 12 * rec, 16);
+            int g = std::min((std::max(n_ng, n_ngs) + NG_WARPS - 1) / NG_WARPS, 4 * ctx->sm_count);
             cudaMemGetInfo(&free_b, &total_b);
             const size_t room = (size_t) (0.5 * (double) (free_b + ctx->d_ngwork.cap));
-            while (g > 1 && (size_t) g * NG_THREADS * slab > room) g = g * 3 / 4;
-            if (ctx->d_ngwork.reserve((size_t) g * NG_THREADS * slab + 64) != cudaSuccess) {
+            while (g > 1 && (size_t) g * NG_WARPS * slab > room) g = g * 3 / 4;
+            if (ctx->d_ngwork.reserve((size_t) g * NG_WARPS * slab + 64) != cudaSuccess) {
                 cudaGetLastError();
-                return fail(ctx, GSPALN_ENOMEM, "device scalar-kernel workspace allocation");
+                return fail(ctx, GSPALN_ENOMEM, "device exact-ILD workspace allocation");
             }
-            ctx->grid_run_ng = g;
-            ctx->ng_slab = slab; ctx->ng_width = ng_width; ctx->ng_rec_cap = (int) ng_rec;
-        }
-        ctx->grid_run_ngs = 0;
-        if (n_ngs) {
-            // 32 problems per CTA, up to 16 CTAs per SM: thousands of problems in flight
-            const int g = std::min((n_ngs + NG_THREADS - 1) / NG_THREADS, 16 * ctx->sm_count);
-            if (ctx->d_ngs.reserve((size_t) g * NG_THREADS * 3 * ngs_width + 64) != cudaSuccess) {
-                cudaGetLastError();
-                return fail(ctx, GSPALN_ENOMEM, "device scalar score-only workspace allocation");
-            }
-            ctx->grid_run_ngs = g;
-            ctx->ngs_width = ngs_width;
+            ctx->grid_run_ng = n_ng ? std::min(g, (n_ng + NG_WARPS - 1) / NG_WARPS) : 0;
+            ctx->grid_run_ngs = n_ngs ? std::min(g, (n_ngs + NG_WARPS - 1) / NG_WARPS) : 0;
+            ctx->ng_slab = slab; ctx->ng_width = w; ctx->ng_rec_cap = (int) rec;
         }
     }
     ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score; ctx->n_udh = n_udh; ctx->n_ng = n_ng;
@@ -548,16 +542,17 @@ static int launch_range(gspaln_ctx* ctx, int lo, int hi, int slot, int& launches
         ++launches;
     }
     if (ctx->n_ng) {
-        dp_ng_kernel<<<ctx->grid_run_ng, NG_THREADS, 0, ctx->stream>>>(
+        dp_xild_kernel<false><<<ctx->grid_run_ng, NG_THREADS, 0, ctx->stream>>>(
             ctx->d_prm.p, ctx->d_ngtab.p, ctx->n_pen, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 8,
             ctx->d_apool.p, ctx->d_cpool.p, ctx->d_ngwork.p, (long long) ctx->ng_slab,
             (long long) ctx->ng_width, ctx->ng_rec_cap, ctx->d_skl.p, ctx->d_res.p, ready);
         ++launches;
     }
     if (ctx->n_ngs) {
-        dp_ng_score_kernel<<<ctx->grid_run_ngs, NG_THREADS, 0, ctx->stream>>>(
+        dp_xild_kernel<true><<<ctx->grid_run_ngs, NG_THREADS, 0, ctx->stream>>>(
             ctx->d_prm.p, ctx->d_ngtab.p, ctx->n_pen, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 9,
-            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_ngs.p, (long long) ctx->ngs_width, ctx->d_res.p, ready);
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_ngwork.p, (long long) ctx->ng_slab,
+            (long long) ctx->ng_width, ctx->ng_rec_cap, ctx->d_skl.p, ctx->d_res.p, ready);
         ++launches;
     }
     CK(cudaGetLastError());

@@ -1,69 +1,138 @@
-// gspaln_ng.cuh -- the scalar spliced DP kernel with exact intron scoring on the device.
+// gspaln_ng.cuh -- exact intron-length DP (the reference's scalar formulation) as a warp kernel.
 //
-// Reference: Aln2s1::trcbkalignS_ng on its scalar branch (src/fwd2s1.cc:1667-1710), i.e.
-// forwardS_ng (217-444) with initS_ng / lastS_ng (141-215), the Vmf record store and walk
-// (src/vmf.cc:66-140) and the end-point adjustment; intron score SpJunc::spjscr
-// (src/codepot.cc:74-77) = IntronPenalty::Penalty(length) + pair-corrected 3' signal
-// (Exinon::sig53(IE53), src/codepot.cc:410-415).  The reference takes this branch for every
-// block with fewer than 8 query rows, also under -A2 / -A3 (src/fwd2s1.cc:1676); the lsp driver
-// meets such blocks between the intermediate rows of a Hirschberg pass.
+// Semantics: bit-identical to Aln2s1::trcbkalignS_ng on its scalar branch (src/fwd2s1.cc:1667-1710:
+// forwardS_ng 217-444 with initS_ng / lastS_ng 141-215, the Vmf path records src/vmf.cc:66-140 and
+// the start-point adjustment) and to Aln2s1::scorealoneS_ng (1112-1336); intron score
+// SpJunc::spjscr (src/codepot.cc:74-77) = IntronPenalty::Penalty(length) + pair-corrected 3'
+// signal (Exinon::sig53(IE53), src/codepot.cc:410-415).  int32 cells, a sorted list of the best
+// donors of every query row, path records instead of a trace matrix.
 //
-// Shape of the work: at most a handful of query rows against a band, int32, with a sorted list
-// of the NCAND best donors per row and a linked list of path records -- sequential in the
-// column index by construction.  One THREAD per problem (problems of this kind come in
-// hundreds per driver level and are a few thousand cells each); band rows, direction bytes and
-// the record store live in a per-thread HBM workspace.  This is the exactness kernel of the
-// path, not the throughput kernel (that is dp_wip_kernel).
+// Mapping (NOT the reference's row-by-row loop): one warp per problem, the 32 lanes own 32
+// consecutive query rows and sweep them as an anti-diagonal wavefront -- at step s lane l sits on
+// column s - l of row m0 + l -- so the 32 cells of a step are independent.  A lane receives the
+// (H, F, F2, direction) of the row above from its neighbour by warp shuffle; lane 0 takes them
+// from the problem's diagonal-indexed band rows in global memory (exactly the reference's
+// hh[0..2][r] arrays, every lane stores its cell there too), staged 32 diagonals at a time through
+// shared memory with one coalesced load.  Everything a row carries along its columns -- the two
+// horizontal gap states, the post-splice flags, the donor list (5 entries x {value, record, state,
+// column}) -- lives in the registers of its lane.  Path records are appended to a per-warp store
+// in lane-private chunks (the record numbering differs from the reference's, the linked list does
+// not); lane 0 walks the list at the end and writes the corner array.
 #pragma once
 #include "gspaln_kernels.cuh"
 
 namespace gspaln {
 
-constexpr int NG_NCAND = 4;             // NCAND, src/aln.h:55
+constexpr int NG_NCAND = 4;             // NCAND, src/aln.h:55 (the list holds one more: see NgList)
 constexpr int NG_NEWD = 8;              // Newd, src/fwd2s1.cc:48
-constexpr int NG_THREADS = 32;          // threads per CTA (one problem each)
+constexpr int NG_WARPS = 4;             // warps (problems in flight) per CTA
+constexpr int NG_THREADS = 32 * NG_WARPS;
 constexpr int NG_NEVSEL = INT_MIN / 16 * 7;     // NEVSEL, src/cmn.h:79
+constexpr int NG_CHUNK = 32;            // path records a lane reserves at a time
 
-struct NgRvp { int val, ptr; };
-struct NgCand { int val, ptr, dir, jnc; };
+struct NgRvp { int val, ptr; };         // value + path record (the reference's RVP)
 
-struct NgWork {                         // per-thread workspace (device pointers)
-    NgRvp* band;                        // 3 x width: H | F | F2, index 0 <-> diagonal lw - 1
-    unsigned char* dirs;                // width
-    int* rec;                           // Vmf records {m, n, prev} x rec_cap
+// per-warp workspace in global memory: band rows by diagonal (index 0 <-> diagonal lw - 1)
+struct NgBand {
+    NgRvp* H; NgRvp* F; NgRvp* F2;
+    unsigned char* dirs;
+    int* rec;                           // path records {m, n, previous} x rec_cap
     int rec_cap;
-    int n_rec;
-    bool overflow;
-    __device__ __forceinline__ int add(int m, int n, int p)
-    {
-        if (n_rec >= rec_cap) { overflow = true; return 0; }
-        int* r = rec + 3 * (long long) n_rec;
-        r[0] = m; r[1] = n; r[2] = p;
-        return n_rec++;
-    }
 };
 
-// tabs: [0, 544) Exinon::sig53tab, [544, 544 + n_pen) IntronPenalty::Penalty(length)
-__device__ __forceinline__ int ng_spjscr(const short* __restrict__ tabs, int n_pen, const ColInfo* cols,
-                                         int b_left, int n5, int n3)
+// lane-private slice of the warp's record store
+struct NgAlloc {
+    int cur = 0, end = 0;
+    bool overflow = false;
+};
+
+__device__ __forceinline__ int ng_add(const NgBand& W, NgAlloc& A, int* warp_next, int m, int n, int prev)
 {
-    const int len = n3 - n5;
+    if (A.overflow) return 0;
+    if (A.cur == A.end) {
+        A.cur = atomicAdd(warp_next, NG_CHUNK);
+        A.end = A.cur + NG_CHUNK;
+    }
+    if (A.end > W.rec_cap) { A.overflow = true; A.cur = A.end = 0; return 0; }
+    int* r = W.rec + 3 * (long long) A.cur;
+    r[0] = m; r[1] = n; r[2] = prev;
+    return A.cur++;
+}
+
+// tabs: [0, 544) Exinon::sig53tab, [544, 544 + n_pen) IntronPenalty::Penalty(length)
+__device__ __forceinline__ int ng_spjscr(const short* __restrict__ tabs, int n_pen, int d5, int len,
+                                         const ColInfo& c3)
+{
     const int pen = tabs[544 + min(len, n_pen - 1)];
-    const ColInfo& c5 = cols[n5 - b_left];
-    const ColInfo& c3 = cols[n3 - b_left];
-    const int d5 = c5.pad[0] & 15, d3 = c3.pad[0] >> 4;
+    const int d3 = c3.pad[0] >> 4;
     const short sig = (short) (c3.sig3 - tabs[16 + d3] + tabs[32 + 16 * d5 + d3]);
     return pen + sig;
 }
 
+// The donor list of one row.  The reference keeps NCAND + 1 slots behind an index permutation
+// (src/fwd2s1.cc:395-404); what that code does is: the list is sorted by value, best first; a new
+// donor enters behind the entries that are at least as good (STRICT: better ones only); the entry
+// it pushes out of the best NCAND survives in slot NCAND until the next insertion attempt, which
+// drops it whether or not the newcomer gets in.
+struct NgList {
+    int val[NG_NCAND + 1], ptr[NG_NCAND + 1], jnc[NG_NCAND + 1];
+    int inf[NG_NCAND + 1];              // gap state (0..4) | 5' dinucleotide code << 4
+    int n;
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int l = 0; l <= NG_NCAND; ++l) { val[l] = NG_NEVSEL; ptr[l] = 0; jnc[l] = 0; inf[l] = 0; }
+        n = 0;
+    }
+    template <bool TIES_AHEAD>          // scorealoneS_ng lets an equal newcomer pass (src/fwd2s1.cc:1311)
+    __device__ __forceinline__ void insert(int x, int p, int info, int j)
+    {
+        if (n > NG_NCAND) n = NG_NCAND;
+        int pos = 0;
+#pragma unroll
+        for (int l = 0; l < NG_NCAND; ++l)
+            if (l < n && (TIES_AHEAD ? val[l] > x : val[l] >= x)) ++pos;
+        if (pos >= NG_NCAND) return;
+#pragma unroll
+        for (int l = NG_NCAND; l > 0; --l)
+            if (l > pos) { val[l] = val[l - 1]; ptr[l] = ptr[l - 1]; jnc[l] = jnc[l - 1]; inf[l] = inf[l - 1]; }
+#pragma unroll
+        for (int l = 0; l < NG_NCAND; ++l)
+            if (l == pos) { val[l] = x; ptr[l] = p; jnc[l] = j; inf[l] = info; }
+        ++n;
+    }
+};
+
+// band rows are written by one lane and read by another within a step or two: read them through
+// L2 (ld.global.cg) so that a stale L1 line can never be seen
+__device__ __forceinline__ NgRvp ng_ld(const NgRvp* p)
+{
+    const int2 v = __ldcg(reinterpret_cast<const int2*>(p));
+    return NgRvp{v.x, v.y};
+}
+__device__ __forceinline__ int ng_ldd(const unsigned char* p) { return (int) __ldcg(p); }
+
+// first / last column (exclusive / inclusive) of query row m: max(m - 1 + lw, b_left) < n <= min(m + up, b_right)
+__device__ __forceinline__ int ng_row_lo(const DevTask& t, int m) { return max(m - 1 + t.lw, t.b_left); }
+__device__ __forceinline__ int ng_row_hi(const DevTask& t, int m) { return min(m + t.up, t.b_right); }
+
+// ---------------------------------------------------------------------------
+// SCORE = false: forwardS_ng + path records + walk (task kind GSPALN_FORWARD_NG)
+// SCORE = true : scorealoneS_ng (GSPALN_SCOREALONE_NG); its tie rules differ: strict comparisons
+//                for the gap states and acceptors, ties accepted in the donor list
+// ---------------------------------------------------------------------------
+template <bool SCORE>
 __global__ void __launch_bounds__(NG_THREADS)
-dp_ng_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs, int n_pen,
-             const DevTask* __restrict__ tasks, const int* __restrict__ order, int ntasks, int* ticket,
-             const unsigned char* __restrict__ apool, const ColInfo* __restrict__ cpool,
-             unsigned char* workpool, long long work_slab, long long width_max, int rec_cap,
-             int2* sklpool, DevResult* results, const int* ready)
+dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs, int n_pen,
+               const DevTask* __restrict__ tasks, const int* __restrict__ order, int ntasks, int* ticket,
+               const unsigned char* __restrict__ apool, const ColInfo* __restrict__ cpool,
+               unsigned char* workpool, long long work_slab, long long width_max, int rec_cap,
+               int2* sklpool, DevResult* results, const int* ready)
 {
     __shared__ DevParams sP;
+    __shared__ NgRvp stageH[NG_WARPS][32], stageF[NG_WARPS][32], stageF2[NG_WARPS][32];
+    __shared__ int stageD[NG_WARPS][32];
+    __shared__ int warp_next[NG_WARPS];
     {
         const int* src = reinterpret_cast<const int*>(gP);
         int* dst = reinterpret_cast<int*>(&sP);
@@ -71,35 +140,34 @@ dp_ng_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs, i
     }
     __syncthreads();
     const DevParams& P = sP;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool dagp = P.noll == 3, spj = P.spj != 0;
     const int nod = 2 * P.noll - 1;
-    const int gop_k[3] = {0, P.gop, P.lgop};                // PwdB::GOP, src/aln2.cc:111
-    const int psp_bit[5] = {4, 1, 8, 2, 16};                // src/aln.h:56
+    constexpr int WANT = SCORE ? 4 : 3;
 
-    NgWork W;
+    NgBand W;
     {
-        unsigned char* base = workpool + ((long long) blockIdx.x * NG_THREADS + threadIdx.x) * work_slab;
-        W.band = reinterpret_cast<NgRvp*>(base);
-        W.dirs = base + 3 * width_max * (long long) sizeof(NgRvp);
+        unsigned char* base = workpool + ((long long) blockIdx.x * NG_WARPS + wid) * work_slab;
+        W.H = reinterpret_cast<NgRvp*>(base);
+        W.F = W.H + width_max;
+        W.F2 = W.F + width_max;
+        W.dirs = reinterpret_cast<unsigned char*>(W.F2 + width_max);
         W.rec = reinterpret_cast<int*>(W.dirs + ((width_max + 15) / 16) * 16);
         W.rec_cap = rec_cap;
     }
 
     for (;;) {
-        const int tk = atomicAdd(ticket, 1);
+        int tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1);
+        tk = __shfl_sync(FULL, tk, 0);
         if (tk >= ntasks) break;
         const int ti = order[tk];
         const DevTask t = tasks[ti];
-        if (t.kind != 3) continue;                          // handled by another kernel
-        if (ready) {                                        // streamed batch: wait for the inputs
-            const volatile int* r = ready;
-            const long long t0 = clock64();
-            bool ok = true;
-            while (*r <= tk) {
-                __nanosleep(256);
-                if (clock64() - t0 > (1ll << 33)) { ok = false; break; }
-            }
-            if (!ok) { DevResult rr; rr.score = 0; rr.status = 4; rr.n_skl = 0; rr.pad = 0; results[ti] = rr; continue; }
+        if (t.kind != WANT) continue;                       // handled by another kernel
+        if (!wait_inputs(ready, tk)) {
+            if (lane == 0) { DevResult rr; rr.score = 0; rr.status = 4; rr.n_skl = 0; rr.pad = 0; results[ti] = rr; }
+            continue;
         }
         const unsigned char* aseq = apool + t.a_off;        // aseq[i] pairs query row a_left + i + 1
         const ColInfo* cols = cpool + t.col_off;            // cols[j] is column b_left + j
@@ -108,390 +176,307 @@ dp_ng_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs, i
         const bool LocalL = P.local && a_exgl && b_exgl, LocalR = P.local && a_exgr && b_exgr;
         const int a_left = t.a_left, a_right = t.a_right, b_left = t.b_left, b_right = t.b_right;
         const int lw = t.lw, up = t.up;
-        NgRvp* H = W.band - lw + 1;                         // by diagonal r = n - m in [lw - 1, up + 1]
-        NgRvp* F = H + width;
-        NgRvp* F2 = F + width;
-        unsigned char* dirs = W.dirs - lw + 1;
-        for (int i = 0; i < 3 * width; ++i) W.band[i] = NgRvp{NG_NEVSEL, 0};
-        for (int i = 0; i < width; ++i) W.dirs[i] = 0;
-        W.n_rec = 0; W.overflow = false;
-        W.add(0, 0, 0);                                     // record 0 is never a path node
+        // band rows by diagonal r = n - m in [lw - 1, up + 1]
+        NgRvp* H = W.H - (lw - 1);
+        NgRvp* F = W.F - (lw - 1);
+        NgRvp* F2 = W.F2 - (lw - 1);
+        unsigned char* dirs = W.dirs - (lw - 1);
+        NgAlloc A;
+        if (lane == 0) warp_next[wid] = NG_CHUNK;           // record 0 is never a path node
+        for (int i = lane; i < width; i += 32) {
+            W.H[i] = NgRvp{NG_NEVSEL, 0}; W.F[i] = NgRvp{NG_NEVSEL, 0}; W.F2[i] = NgRvp{NG_NEVSEL, 0};
+            W.dirs[i] = 0;
+        }
+        __syncwarp();
 
-        // ---- initS_ng (src/fwd2s1.cc:141-184)
+        // ---- first row and first column (initS_ng src/fwd2s1.cc:141-184, sinitS_ng 1112-1140)
         {
-            int r = b_left - a_left, rr = b_right - a_left;
-            H[r].val = 0; dirs[r] = 0;
-            H[r].ptr = W.add(a_left, b_left, 0);
+            const int r0 = b_left - a_left;
+            int p0 = 0;
+            if (!SCORE && lane == 0) p0 = ng_add(W, A, &warp_next[wid], a_left, b_left, 0);
+            p0 = __shfl_sync(FULL, p0, 0);
+            if (lane == 0) H[r0] = NgRvp{0, p0};
             if (a_exgl) {
-                if (up < rr) rr = up;
-                while (++r <= rr) { H[r] = NgRvp{0, 0}; dirs[r] = 1; }
+                const int rr = min(up, b_right - a_left);
+                for (int r = r0 + 1 + lane; r <= rr; r += 32) { H[r] = NgRvp{0, 0}; dirs[r] = 1; }
             }
-            r = b_left - a_left;
-            rr = max(b_left - a_right, lw);
-            for (int i = 1; --r >= rr; ++i) {
-                dirs[r] = 2;
-                if (b_exgl) H[r] = NgRvp{0, 0};
-                else {
-                    NgRvp v = H[r + 1];
-                    v.val += i == 1 ? P.gappen1 : (i > P.codonk1 ? P.lgep : P.gep);
-                    H[r] = v;
+            const int rr = max(b_left - a_right, lw);
+            if (b_exgl) {
+                for (int r = rr + lane; r < r0; r += 32) { H[r] = NgRvp{0, 0}; dirs[r] = 2; }
+            } else if (lane == 0) {
+                // a leading gap in the genome: opened once, extended per residue (long-gap slope
+                // beyond codonk1); the score-only kernel seeds the vertical state as well
+                int v = 0, f = NG_NEVSEL;
+                for (int i = 1, r = r0 - 1; r >= rr; --r, ++i) {
+                    if (i == 1) { v += P.gappen1; f = v; }
+                    else { v += i > P.codonk1 ? P.lgep : P.gep; f += P.gep; }
+                    H[r] = NgRvp{v, p0};
+                    dirs[r] = 2;
+                    if (SCORE) F[r] = NgRvp{f, 0};
                 }
             }
         }
+        __threadfence_block();
+        __syncwarp();
 
-        int best_val = NG_NEVSEL, best_m = a_left, best_n = b_left, best_p = 0;     // LocalR
-        for (int m = a_exgl ? a_left + 1 : a_left; m <= a_right; ++m) {
-            const bool internal = spj && (!a_exgr || m < a_right);
+        int best_val = NG_NEVSEL, best_m = a_left, best_n = b_left, best_p = 0;     // LocalR (lane-local)
+        const int m_first = a_exgl ? a_left + 1 : a_left;
+        for (int m0 = m_first; m0 <= a_right; m0 += 32) {
+            const int m = m0 + lane;
+            const bool row = m <= a_right;
             const bool first = m == a_left;                 // global start row: horizontal moves only
-            int n = max((m - 1) + lw, b_left);
-            const int n9 = min((m - 1) + up + 1, b_right);
-            const int arow = first ? ZROW : (int) aseq[m - 1 - a_left];
-            NgRvp e1{NG_NEVSEL, 0}, e2{NG_NEVSEL, 0};
-            NgCand rcd[NG_NCAND + 1];
-            int idx[NG_NCAND + 1];
-#pragma unroll
-            for (int l = 0; l <= NG_NCAND; ++l) { rcd[l] = NgCand{NG_NEVSEL, 0, 0, 0}; idx[l] = l; }
-            int ncand = -1, psp = 0;
-            NgRvp hleft = H[n - m];                         // H[m][n] of the previous column
-            while (++n <= n9) {
+            const bool internal = spj && (!a_exgr || m < a_right);
+            const int lo = ng_row_lo(t, m), hi = ng_row_hi(t, m);
+            const int lo_up = ng_row_lo(t, m - 1), hi_up = ng_row_hi(t, m - 1);     // row above
+            const bool has_up = lane > 0;                   // the row above belongs to this pass
+            const int arow = (first || !row) ? ZROW : (int) aseq[m - 1 - a_left];
+            const int last_lane = min(31, a_right - m0);
+            const int s_begin = ng_row_lo(t, m0) + 1;
+            const int s_end = ng_row_hi(t, m0 + last_lane) + last_lane;
+
+            NgRvp hleft{NG_NEVSEL, 0}, e1{NG_NEVSEL, 0}, e2{NG_NEVSEL, 0};
+            NgRvp oH{NG_NEVSEL, 0}, oF{NG_NEVSEL, 0}, oF2{NG_NEVSEL, 0};           // this lane's last cell
+            int oD = 0;
+            NgRvp dH{NG_NEVSEL, 0};                         // the cell above-left (received one step ago)
+            int dD = 0;
+            int psp = 0;
+            NgList L;
+            L.clear();
+            ColInfo col_next = ColInfo{0, 0, 0, {0, 0, 0}};
+
+            for (int s = s_begin; s <= s_end; ++s) {
+                const int k = s - s_begin;
+                // lane 0's row above: 32 diagonals of the band rows per coalesced load
+                if ((k & 31) == 0) {
+                    __syncwarp();
+                    const int r = (s - m0 + 1) + lane;      // diagonal lane 0 reads `lane` steps from now
+                    const bool in = r >= lw - 1 && r <= up + 1;
+                    stageH[wid][lane] = in ? ng_ld(H + r) : NgRvp{NG_NEVSEL, 0};
+                    stageF[wid][lane] = in ? ng_ld(F + r) : NgRvp{NG_NEVSEL, 0};
+                    if (dagp) stageF2[wid][lane] = in ? ng_ld(F2 + r) : NgRvp{NG_NEVSEL, 0};
+                    stageD[wid][lane] = in ? ng_ldd(dirs + r) : 0;
+                    __syncwarp();
+                }
+                // the cell above: neighbour's result of the previous step
+                NgRvp uH, uF, uF2;
+                int uD;
+                uH.val = __shfl_up_sync(FULL, oH.val, 1); uH.ptr = __shfl_up_sync(FULL, oH.ptr, 1);
+                uF.val = __shfl_up_sync(FULL, oF.val, 1); uF.ptr = __shfl_up_sync(FULL, oF.ptr, 1);
+                uF2.val = dagp ? __shfl_up_sync(FULL, oF2.val, 1) : NG_NEVSEL;
+                uF2.ptr = dagp ? __shfl_up_sync(FULL, oF2.ptr, 1) : 0;
+                uD = __shfl_up_sync(FULL, oD, 1);
+                const int n = s - lane;
                 const int r = n - m;
-                const ColInfo col = cols[n - b_left];
-                // cell state: 0 H, 1 E1, 2 F, 3 E2, 4 F2 (the reference's hf[] order)
-                NgRvp st[5];
-                st[0] = H[r]; st[1] = e1; st[2] = F[r]; st[3] = e2; st[4] = dagp ? F2[r] : NgRvp{NG_NEVSEL, 0};
-                int mx = 0;
-                const int diag = st[0].val;
-                int dir = dirs[r];
-                if (!first) {
-                    st[0].val += P.mtxT[(int) col.code * MTX_LD + arow];
-                    dir = (dir % NG_NEWD) ? NG_NEWD : 0;
-                    const NgRvp up_h = H[r + 1];
-                    const NgRvp up_f = F[r + 1];
-                    int x = up_h.val + P.gop;
-                    if (x >= up_f.val) st[2] = NgRvp{x, up_h.ptr}; else st[2] = up_f;
-                    st[2].val += P.gep;
-                    if (st[2].val > st[mx].val) mx = 2;
-                    if (dagp) {
-                        const NgRvp up_f2 = F2[r + 1];
-                        x = up_h.val + P.lgop;
-                        if (x >= up_f2.val) st[4] = NgRvp{x, up_h.ptr}; else st[4] = up_f2;
-                        st[4].val += P.lgep;
-                        if (st[4].val > st[mx].val) mx = 4;
-                    }
+                if (lane == 0) {
+                    uH = stageH[wid][k & 31]; uF = stageF[wid][k & 31];
+                    if (dagp) uF2 = stageF2[wid][k & 31];
+                    uD = stageD[wid][k & 31];
+                } else if (!(n > lo_up && n <= hi_up)) {
+                    // the row above never evaluated column n: what the band rows hold there
+                    const bool in = r + 1 <= up + 1 && r + 1 >= lw - 1;
+                    uH = in ? ng_ld(H + r + 1) : NgRvp{NG_NEVSEL, 0};
+                    uF = in ? ng_ld(F + r + 1) : NgRvp{NG_NEVSEL, 0};
+                    if (dagp) uF2 = in ? ng_ld(F2 + r + 1) : NgRvp{NG_NEVSEL, 0};
+                    uD = in ? ng_ldd(dirs + r + 1) : 0;
                 }
-                {
-                    int x = hleft.val + P.gop;
-                    const int prev_psp = psp;
-                    if (x >= st[1].val) { st[1] = NgRvp{x, hleft.ptr}; psp = psp ? 1 : 0; }
-                    else psp &= 1;
-                    st[1].val += P.gep;
-                    if (st[1].val >= st[mx].val) mx = 1;
-                    if (dagp) {
-                        x = hleft.val + P.lgop;
-                        if (x >= st[3].val) { st[3] = NgRvp{x, hleft.ptr}; if (prev_psp) psp |= 2; }
-                        else psp |= prev_psp & 2;
-                        st[3].val += P.lgep;
-                        if (st[3].val >= st[mx].val) mx = 3;
+                const bool act = row && n > lo && n <= hi;
+                if (act) {
+                    const ColInfo col = cols[n - b_left];
+                    if (n == lo + 1) {
+                        // row start: the band entry left of the first cell, and the cell above-left
+                        // if the row above did not evaluate it
+                        hleft = ng_ld(H + (lo - m));
+                        if (!(has_up && lo > lo_up && lo <= hi_up)) { dH = ng_ld(H + r); dD = ng_ldd(dirs + r); }
                     }
-                }
-                const int cano5 = col.pad[1] & 15, cano3 = col.pad[1] >> 4;
-                // acceptor: every stored donor of this row, per gap state
-                if (internal && cano3) {
-                    int top[5] = {-1, -1, -1, -1, -1};
-                    for (int l = 0; l <= ncand; ++l) {
-                        const NgCand& c = rcd[idx[l]];
-                        if (n - c.jnc < P.llmt) continue;
-                        const int x = c.val + ng_spjscr(tabs, n_pen, cols, b_left, c.jnc, n);
-                        if (x >= st[c.dir].val) { st[c.dir].val = x; top[c.dir] = idx[l]; }
-                    }
-                    for (int k = 0; k < nod; ++k) {
-                        if (top[k] < 0) continue;
-                        const NgCand& c = rcd[top[k]];
-                        psp |= psp_bit[k];
-                        const int inner = W.add(m, c.jnc, c.ptr);
-                        st[k].ptr = W.add(m, n, inner);
-                        if (st[k].val >= st[mx].val) mx = k;
-                    }
-                }
-                // best state
-                const int hd = mx;
-                const int mxval = st[mx].val;               // the reference reads mx->val later on
-                if (mx != 0) {
-                    st[0] = st[mx];
-                    dir = hd;
-                } else if (P.local && st[0].val > diag) {
-                    if (LocalL && diag == 0) st[0].ptr = W.add(m - 1, n - 1, 0);
-                    else if (LocalR && st[0].val > best_val) {
-                        best_val = st[0].val; best_p = st[0].ptr; best_m = m; best_n = n;
-                    }
-                }
-                int mx_now = mxval;
-                if (LocalL && st[0].val <= 0) { st[0].val = 0; dir = 1; if (mx == 0) mx_now = 0; }
-                else if (dir == NG_NEWD && !(psp & psp_bit[0])) st[0].ptr = W.add(m - 1, n - 1, st[0].ptr);
-                // donor: keep the NCAND best (value + 5' signal) of this row
-                if (internal && cano5) {
-                    const int sigJ = col.sig5;
-                    for (int k = hd == 0 ? 0 : 1; k < nod; ++k) {
-                        if (psp & psp_bit[k]) continue;
-                        const NgRvp from = st[k];
-                        if (k != hd) {
-                            int z = mx_now;
-                            if (hd == 0 || (k - hd) % 2) z += gop_k[k / 2];
-                            if (from.val <= z) continue;
+                    // cell states in the reference's order: 0 H, 1 E, 2 F, 3 E2, 4 F2
+                    NgRvp h = dH;
+                    const int diag = h.val;
+                    int dir = dD;
+                    NgRvp f{NG_NEVSEL, 0}, f2{NG_NEVSEL, 0};
+                    int mx = 0, mxv;
+                    if (!first) {
+                        h.val += P.mtxT[(int) col.code * MTX_LD + arow];
+                        dir = (dir % NG_NEWD) ? NG_NEWD : 0;
+                        int x = uH.val + P.gop;
+                        f = (x >= uF.val) ? NgRvp{x, uH.ptr} : uF;
+                        f.val += P.gep;
+                        mxv = h.val;
+                        if (f.val > mxv) { mx = 2; mxv = f.val; }
+                        if (dagp) {
+                            x = uH.val + P.lgop;
+                            f2 = (x >= uF2.val) ? NgRvp{x, uH.ptr} : uF2;
+                            f2.val += P.lgep;
+                            if (f2.val > mxv) { mx = 4; mxv = f2.val; }
                         }
-                        const int x = from.val + sigJ;
-                        int l = ncand < NG_NCAND ? ++ncand : NG_NCAND;
-                        while (--l >= 0) {
-                            if (x > rcd[idx[l]].val) { const int s = idx[l]; idx[l] = idx[l + 1]; idx[l + 1] = s; }
-                            else break;
-                        }
-                        if (++l < NG_NCAND) rcd[idx[l]] = NgCand{x, from.ptr, k, n};
-                        else --ncand;
+                    } else {
+                        f = ng_ld(F + r); if (dagp) f2 = ng_ld(F2 + r);     // untouched band entries
+                        mxv = h.val;
                     }
+                    {
+                        int x = hleft.val + P.gop;
+                        const int prev_psp = psp;
+                        if (SCORE ? x > e1.val : x >= e1.val) { e1 = NgRvp{x, hleft.ptr}; psp = psp ? 1 : 0; }
+                        else psp &= 1;
+                        e1.val += P.gep;
+                        if (SCORE ? e1.val > mxv : e1.val >= mxv) { mx = 1; mxv = e1.val; }
+                        if (dagp) {
+                            x = hleft.val + P.lgop;
+                            if (SCORE ? x > e2.val : x >= e2.val) { e2 = NgRvp{x, hleft.ptr}; if (prev_psp) psp |= 2; }
+                            else psp |= prev_psp & 2;
+                            e2.val += P.lgep;
+                            if (SCORE ? e2.val > mxv : e2.val >= mxv) { mx = 3; mxv = e2.val; }
+                        }
+                    }
+                    const int cano5 = col.pad[1] & 15, cano3 = col.pad[1] >> 4;
+                    // acceptor: every stored donor of this row, per gap state (the last entry that is
+                    // at least as good as the state wins)
+                    if ((SCORE || internal) && cano3 && L.n > 0) {
+                        int tj[5], tp[5];
+                        unsigned hit = 0;
+#pragma unroll
+                        for (int l = 0; l <= NG_NCAND; ++l) {
+                            if (l >= L.n || n - L.jnc[l] < P.llmt) continue;
+                            const int st = L.inf[l] & 15;
+                            const int x = L.val[l] + ng_spjscr(tabs, n_pen, L.inf[l] >> 4, n - L.jnc[l], col);
+#pragma unroll
+                            for (int q = 0; q < 5; ++q) {
+                                if (q != st) continue;
+                                int& sv = q == 0 ? h.val : q == 1 ? e1.val : q == 2 ? f.val : q == 3 ? e2.val : f2.val;
+                                if (SCORE ? x > sv : x >= sv) { sv = x; tj[q] = L.jnc[l]; tp[q] = L.ptr[l]; hit |= 1u << q; }
+                            }
+                        }
+                        // the running best may itself have been raised by a donor
+                        mxv = mx == 0 ? h.val : mx == 1 ? e1.val : mx == 2 ? f.val : mx == 3 ? e2.val : f2.val;
+                        const int psp_bit[5] = {4, 1, 8, 2, 16};    // src/aln.h:56
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            if (q >= nod || !(hit >> q & 1u)) continue;
+                            NgRvp& sq = q == 0 ? h : q == 1 ? e1 : q == 2 ? f : q == 3 ? e2 : f2;
+                            psp |= psp_bit[q];
+                            if (!SCORE) {
+                                const int inner = ng_add(W, A, &warp_next[wid], m, tj[q], tp[q]);
+                                sq.ptr = ng_add(W, A, &warp_next[wid], m, n, inner);
+                            }
+                            if (SCORE ? sq.val > mxv : sq.val >= mxv) { mx = q; mxv = sq.val; }
+                        }
+                    }
+                    // best state
+                    const int hd = mx;
+                    const int y = h.val;
+                    if (mx != 0) {
+                        h = mx == 1 ? e1 : mx == 2 ? f : mx == 3 ? e2 : f2;
+                        dir = hd;
+                    } else if (SCORE) {
+                        if (LocalR && y > best_val) best_val = y;
+                    } else if (P.local && h.val > diag) {
+                        if (LocalL && diag == 0) h.ptr = ng_add(W, A, &warp_next[wid], m - 1, n - 1, 0);
+                        else if (LocalR && h.val > best_val) { best_val = h.val; best_p = h.ptr; best_m = m; best_n = n; }
+                    }
+                    int mx_now = mxv;
+                    if (LocalL && (SCORE ? h.val < 0 : h.val <= 0)) { h.val = 0; dir = 1; if (mx == 0) mx_now = 0; }
+                    else if (!SCORE && dir == NG_NEWD && !(psp & 4))
+                        h.ptr = ng_add(W, A, &warp_next[wid], m - 1, n - 1, h.ptr);
+                    // donor: the best (value + 5' signal) of this row by gap state
+                    if ((SCORE || internal) && cano5) {
+                        const int sigJ = col.sig5;
+                        const int d5 = col.pad[0] & 15;
+                        const int psp_bit[5] = {4, 1, 8, 2, 16};
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            if (q >= nod || q < (hd == 0 ? 0 : 1) || (psp & psp_bit[q])) continue;
+                            const NgRvp from = q == 0 ? h : q == 1 ? e1 : q == 2 ? f : q == 3 ? e2 : f2;
+                            if (q != hd) {
+                                int z = mx_now;
+                                if (hd == 0 || (q - hd) % 2) z += q / 2 == 0 ? 0 : (q / 2 == 1 ? P.gop : P.lgop);
+                                if (from.val <= z) continue;
+                            }
+                            L.template insert<SCORE>(from.val + sigJ, from.ptr, q | (d5 << 4), n);
+                        }
+                    }
+                    // results: to the band rows (what the rows of the next pass and the end-point
+                    // search read) and to the neighbour
+                    H[r] = h; F[r] = f;
+                    if (dagp) F2[r] = f2;
+                    dirs[r] = (unsigned char) dir;
+                    oH = h; oF = f; oF2 = f2; oD = dir;
+                    hleft = h;
                 }
-                H[r] = st[0]; F[r] = st[2];
-                if (dagp) F2[r] = st[4];
-                dirs[r] = (unsigned char) dir;
-                e1 = st[1]; e2 = st[3];
-                hleft = st[0];
+                dH = uH; dD = uD;
+                __syncwarp();
             }
+            __threadfence_block();
+            __syncwarp();
         }
 
-        int ptr, val;
+        // ---- end point (lastS_ng src/fwd2s1.cc:186-215, slastS_ng 1142-1161)
+        int val = NG_NEVSEL, ptr = 0;
         if (LocalR) {
-            ptr = W.add(best_m, best_n, best_p);
-            val = best_val;
-        } else {
-            // lastS_ng (src/fwd2s1.cc:186-215)
-            int rw = max(lw, b_left - a_right);
+            // row-major order: the first cell that reached the maximum
+            int bv = best_val, bm = best_m, bn = best_n, bp = best_p;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const int ov = __shfl_xor_sync(FULL, bv, o), om = __shfl_xor_sync(FULL, bm, o);
+                const int on = __shfl_xor_sync(FULL, bn, o), op = __shfl_xor_sync(FULL, bp, o);
+                if (ov > bv || (ov == bv && ov > NG_NEVSEL && (om < bm || (om == bm && on < bn)))) { bv = ov; bm = om; bn = on; bp = op; }
+            }
+            val = bv;
+            if (!SCORE && lane == 0) ptr = ng_add(W, A, &warp_next[wid], bm, bn, bp);
+        } else if (lane == 0) {
             const int r9 = b_right - a_right;
             int mxr = r9;
-            if (a_exgr)
-                for (int r = rw; r <= r9; ++r) if (H[r].val > H[mxr].val) mxr = r;
-            if (b_exgr) {
-                rw = min(up, b_right - a_left);
-                for (int r = rw; r > r9; --r) if (H[r].val > H[mxr].val) mxr = r;
-            }
-            const int i = mxr - r9;
-            int m9 = a_right, n9 = b_right;
-            if (i > 0) m9 -= i;
-            if (i < 0) n9 += i;
-            ptr = W.add(m9, n9, H[mxr].ptr);
-            val = H[mxr].val;
-        }
-
-        // ---- Vmf::traceback + the start-point adjustment of trcbkalignS_ng
-        int2* skl = sklpool + t.skl_off;
-        int cnt = 0;
-        if (!W.overflow && ptr) {
-            int m_last = 0, n_last = 0;
-            for (int q = ptr; ; ) {
-                const int* rr = W.rec + 3 * (long long) q;
-                m_last = rr[0]; n_last = rr[1];
-                if (cnt < t.skl_cap) skl[cnt] = make_int2(m_last, n_last);
-                ++cnt;
-                q = rr[2];
-                if (!q) break;
-            }
-            const int rd = P.local ? 0 : (n_last - m_last) - b_left + a_left;
-            if (rd) {
-                if (cnt < t.skl_cap)
-                    skl[cnt] = rd > 0 ? make_int2(a_left, b_left + rd) : make_int2(a_left - rd, b_left);
-                ++cnt;
-            }
-        }
-        DevResult res;
-        res.score = val;
-        res.status = W.overflow ? 5 : (cnt > t.skl_cap ? 1 : 0);
-        res.n_skl = cnt; res.pad = 0;
-        results[ti] = res;
-    }
-}
-
-
-// ---------------------------------------------------------------------------
-// Aln2s1::scorealoneS_ng (src/fwd2s1.cc:1163-1336) with sinitS_ng / slastS_ng (1112-1161): the
-// scalar score-only kernel (HomScoreS_ng under -A0 and for queries shorter than 4 residues,
-// src/fwd2s1.cc:2704-2705).  Same frame as dp_ng_kernel (one thread per problem) but no path
-// records: the workspace is three int rows of the band width, so it also takes full-size problems.
-// Its tie rules differ from forwardS_ng's (strict comparisons for the gap states and the
-// acceptors, ties accepted in the donor list) and so do its initial rows.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(NG_THREADS)
-dp_ng_score_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs, int n_pen,
-                   const DevTask* __restrict__ tasks, const int* __restrict__ order, int ntasks, int* ticket,
-                   const unsigned char* __restrict__ apool, const ColInfo* __restrict__ cpool,
-                   int* workpool, long long width_max, DevResult* results, const int* ready)
-{
-    __shared__ DevParams sP;
-    {
-        const int* src = reinterpret_cast<const int*>(gP);
-        int* dst = reinterpret_cast<int*>(&sP);
-        for (int i = threadIdx.x; i < (int) (sizeof(DevParams) / 4); i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-    const DevParams& P = sP;
-    const bool dagp = P.noll == 3;
-    const int nod = 2 * P.noll - 1;
-    const int gop_k[3] = {0, P.gop, P.lgop};
-    const int psp_bit[5] = {4, 1, 8, 2, 16};
-    int* wbase = workpool + ((long long) blockIdx.x * NG_THREADS + threadIdx.x) * 3 * width_max;
-
-    for (;;) {
-        const int tk = atomicAdd(ticket, 1);
-        if (tk >= ntasks) break;
-        const int ti = order[tk];
-        const DevTask t = tasks[ti];
-        if (t.kind != 4) continue;
-        if (ready) {
-            const volatile int* r = ready;
-            const long long t0 = clock64();
-            bool ok = true;
-            while (*r <= tk) {
-                __nanosleep(256);
-                if (clock64() - t0 > (1ll << 33)) { ok = false; break; }
-            }
-            if (!ok) { DevResult rr; rr.score = 0; rr.status = 4; rr.n_skl = 0; rr.pad = 0; results[ti] = rr; continue; }
-        }
-        const unsigned char* aseq = apool + t.a_off;
-        const ColInfo* cols = cpool + t.col_off;
-        const int width = t.up - t.lw + 3;
-        const bool a_exgl = t.flags & 1, a_exgr = t.flags & 2, b_exgl = t.flags & 4, b_exgr = t.flags & 8;
-        const bool LocalL = P.local && a_exgl && b_exgl, LocalR = P.local && a_exgr && b_exgr;
-        const int a_left = t.a_left, a_right = t.a_right, b_left = t.b_left, b_right = t.b_right;
-        const int lw = t.lw, up = t.up;
-        int* H = wbase - lw + 1;
-        int* F = H + width;
-        int* F2 = F + width;
-        for (int i = 0; i < 3 * width; ++i) wbase[i] = NG_NEVSEL;
-        // ---- sinitS_ng
-        {
-            int r = b_left - a_left, rr = b_right - a_left;
-            H[r] = 0;
-            if (a_exgl) {
-                if (up < rr) rr = up;
-                for (int q = r + 1; q <= rr; ++q) H[q] = 0;
-            }
-            rr = max(b_left - a_right, lw);
-            if (b_exgl) {
-                for (int q = rr; q < r; ++q) H[q] = 0;
+            if (SCORE) {
+                int mxv = ng_ld(H + r9).val;
+                if (b_exgr) for (int r = min(up, b_right - a_left); r > r9; --r) mxv = max(mxv, ng_ld(H + r).val);
+                if (a_exgr) for (int r = max(lw, b_left - a_right); r < r9; ++r) mxv = max(mxv, ng_ld(H + r).val);
+                val = mxv;
             } else {
-                for (int i = 1; --r >= rr; ++i) {
-                    int h = H[r + 1];
-                    if (i == 1) { h += P.gappen1; F[r] = h; }
-                    else { h += i > P.codonk1 ? P.lgep : P.gep; F[r] = F[r + 1] + P.gep; }
-                    H[r] = h;
-                }
+                int mxval = ng_ld(H + r9).val;
+                if (a_exgr)
+                    for (int r = max(lw, b_left - a_right); r <= r9; ++r) {
+                        const int v = ng_ld(H + r).val;
+                        if (v > mxval) { mxr = r; mxval = v; }
+                    }
+                if (b_exgr)
+                    for (int r = min(up, b_right - a_left); r > r9; --r) {
+                        const int v = ng_ld(H + r).val;
+                        if (v > mxval) { mxr = r; mxval = v; }
+                    }
+                const int i = mxr - r9;
+                ptr = ng_add(W, A, &warp_next[wid], a_right - max(i, 0), b_right + min(i, 0), ng_ld(H + mxr).ptr);
+                val = mxval;
             }
         }
-        int maxh = NG_NEVSEL;
-        for (int m = a_exgl ? a_left + 1 : a_left; m <= a_right; ++m) {
-            const bool first = m == a_left;
-            int n = max((m - 1) + lw, b_left);
-            const int n9 = min((m - 1) + up + 1, b_right);
-            const int arow = first ? ZROW : (int) aseq[m - 1 - a_left];
-            int e1 = NG_NEVSEL, e2 = NG_NEVSEL;
-            int cval[NG_NCAND + 1], cdir[NG_NCAND + 1], cjnc[NG_NCAND + 1], idx[NG_NCAND + 1];
-#pragma unroll
-            for (int l = 0; l <= NG_NCAND; ++l) { cval[l] = NG_NEVSEL; cdir[l] = 0; cjnc[l] = 0; idx[l] = l; }
-            int ncand = -1, psp = 0;
-            int hleft = H[n - m];
-            while (++n <= n9) {
-                const int r = n - m;
-                const ColInfo col = cols[n - b_left];
-                int st[5];                              // H, E1, F, E2, F2 (the reference's hf[] order)
-                st[0] = H[r]; st[1] = e1; st[2] = F[r]; st[3] = e2; st[4] = dagp ? F2[r] : NG_NEVSEL;
-                int mx = 0;
-                if (!first) {
-                    st[0] += P.mtxT[(int) col.code * MTX_LD + arow];
-                    const int up_h = H[r + 1];
-                    st[2] = max(up_h + P.gop, F[r + 1]) + P.gep;
-                    if (st[2] > st[mx]) mx = 2;
-                    if (dagp) {
-                        st[4] = max(up_h + P.lgop, F2[r + 1]) + P.lgep;
-                        if (st[4] > st[mx]) mx = 4;
-                    }
+        const bool overflow = __any_sync(FULL, A.overflow);
+        __threadfence_block();
+        __syncwarp();
+
+        if (lane == 0) {
+            int cnt = 0;
+            if (!SCORE && !overflow && ptr) {
+                // Vmf::traceback + the start-point adjustment of trcbkalignS_ng (src/fwd2s1.cc:1690-1706)
+                int2* skl = sklpool + t.skl_off;
+                int m_last = 0, n_last = 0;
+                for (int q = ptr; q; ) {
+                    const int* rr = W.rec + 3 * (long long) q;
+                    m_last = rr[0]; n_last = rr[1];
+                    if (cnt < t.skl_cap) skl[cnt] = make_int2(m_last, n_last);
+                    ++cnt;
+                    q = rr[2];
                 }
-                {
-                    int x = hleft + P.gop;
-                    const int prev_psp = psp;
-                    if (x > st[1]) { st[1] = x; psp = psp ? 1 : 0; }
-                    else psp &= 1;
-                    st[1] += P.gep;
-                    if (st[1] > st[mx]) mx = 1;
-                    if (dagp) {
-                        x = hleft + P.lgop;
-                        if (x > st[3]) { st[3] = x; if (prev_psp) psp |= 2; }
-                        else psp |= prev_psp & 2;
-                        st[3] += P.lgep;
-                        if (st[3] > st[mx]) mx = 3;
-                    }
+                const int rd = P.local ? 0 : (n_last - m_last) - b_left + a_left;
+                if (rd) {
+                    if (cnt < t.skl_cap)
+                        skl[cnt] = rd > 0 ? make_int2(a_left, b_left + rd) : make_int2(a_left - rd, b_left);
+                    ++cnt;
                 }
-                const int cano5 = col.pad[1] & 15, cano3 = col.pad[1] >> 4;
-                if (cano3) {
-                    unsigned top = 0;
-                    for (int l = 0; l <= ncand; ++l) {
-                        const int j = idx[l];
-                        if (n - cjnc[j] < P.llmt) continue;
-                        const int x = cval[j] + ng_spjscr(tabs, n_pen, cols, b_left, cjnc[j], n);
-                        if (x > st[cdir[j]]) { st[cdir[j]] = x; top |= 1u << cdir[j]; }
-                    }
-                    for (int k = 0; k < nod; ++k) {
-                        if (!(top >> k & 1u)) continue;
-                        psp |= psp_bit[k];
-                        if (st[k] > st[mx]) mx = k;
-                    }
-                }
-                const int y = st[0];
-                const int mxval = st[mx];
-                if (mx != 0) st[0] = mxval;
-                else if (LocalR && y > maxh) maxh = y;
-                int mx_now = mxval;
-                if (LocalL && st[0] < 0) { st[0] = 0; if (mx == 0) mx_now = 0; }
-                const int hd = mx;
-                if (cano5) {
-                    const int sigJ = col.sig5;
-                    for (int k = hd == 0 ? 0 : 1; k < nod; ++k) {
-                        if (psp & psp_bit[k]) continue;
-                        const int from = k == 0 ? st[0] : st[k];
-                        if (k != hd) {
-                            int z = mx_now;
-                            if (hd == 0 || (k - hd) % 2) z += gop_k[k / 2];
-                            if (from <= z) continue;
-                        }
-                        const int x = from + sigJ;
-                        int l = ncand < NG_NCAND ? ++ncand : NG_NCAND;
-                        while (--l >= 0) {
-                            if (x >= cval[idx[l]]) { const int s = idx[l]; idx[l] = idx[l + 1]; idx[l + 1] = s; }
-                            else break;
-                        }
-                        if (++l < NG_NCAND) { cval[idx[l]] = x; cjnc[idx[l]] = n; cdir[idx[l]] = k; }
-                        else --ncand;
-                    }
-                }
-                H[r] = st[0]; F[r] = st[2];
-                if (dagp) F2[r] = st[4];
-                e1 = st[1]; e2 = st[3];
-                hleft = st[0];
             }
+            DevResult res;
+            res.score = val;
+            res.status = overflow ? 5 : (cnt > t.skl_cap ? 1 : 0);
+            res.n_skl = cnt; res.pad = 0;
+            results[ti] = res;
         }
-        if (!LocalR) {
-            // slastS_ng
-            const int r9 = b_right - a_right;
-            int mxv = H[r9];
-            if (b_exgr) {
-                const int rw = min(up, b_right - a_left);
-                for (int r = rw; r > r9; --r) mxv = max(mxv, H[r]);
-            }
-            if (a_exgr) {
-                const int rw = max(lw, b_left - a_right);
-                for (int r = rw; r < r9; ++r) mxv = max(mxv, H[r]);
-            }
-            maxh = mxv;
-        }
-        DevResult res;
-        res.score = maxh; res.status = 0; res.n_skl = 0; res.pad = 0;
-        results[ti] = res;
+        __syncwarp();
     }
 }
 
