@@ -44,17 +44,37 @@ def load_params():
     return prm
 
 
-def make_workload(n_queries, seed):
+SEED = 20251017
+_LETTERS = np.zeros(256, np.uint8)
+for _c, _ch in ((2, "A"), (3, "C"), (5, "G"), (9, "T")):
+    _LETTERS[_c] = ord(_ch)
+
+
+def make_workload(n_queries, seed=SEED, first=0):
+    """problems [first, first + n) of the seeded global config-2 query set (with the FASTA strings
+    the reference arm needs)"""
     from spaln_b200 import workload
-    rng = np.random.default_rng(seed)
-    return [workload.config2_problem(rng) for _ in range(n_queries)]
+    out = []
+    for i in range(first, first + n_queries):
+        r = workload.config2_problem_seeded(seed, i)
+        r["int53"] = workload.synthetic_int53(r["b"])
+        out.append(r)
+    return out
+
+
+def with_strings(raw):
+    for r in raw:
+        if "genome_str" not in r:
+            r["genome_str"] = _LETTERS[r["b"]].tobytes().decode()
+            r["query_str"] = _LETTERS[r["a"]].tobytes().decode()
+    return raw
 
 
 def to_problems(raw):
     from spaln_b200 import Problem, workload
     # int53 (site classes, as Exinon::intron53_c derives them from the residues): blocks with fewer
     # than 8 query rows that the lsp driver cuts go to the scalar exact-ILD kernel, as in the reference
-    return [Problem(int53=workload.synthetic_int53(r["b"]),
+    return [Problem(int53=r["int53"] if r.get("int53") is not None else workload.synthetic_int53(r["b"]),
                     a=r["a"], b=r["b"], sig5=r["sig5"], sig3=r["sig3"], a_left=r["a_left"],
                     a_right=r["a_right"], b_left=r["b_left"], b_right=r["b_right"], lw=r["lw"],
                     up=r["up"], a_exgl=1, a_exgr=1, b_exgl=1, b_exgr=1, skl_cap=512) for r in raw]
@@ -529,6 +549,77 @@ def config4_reference_child(args):
     return 0
 
 
+def config5_sweep(args, prm, rank, local_rank, world):
+    """BASELINE config 5: band width x query length sweep (256 - 64k DP cells per task), trace-back
+    kernel (forwardS1_wip semantics), `--sweep-tasks` tasks per point and rank.  Per point: kernel
+    GCUPS with the tasks resident (CUDA events), end-to-end GCUPS with host buffers, HBM roofline
+    fraction.  Tasks: random query of m residues against a locus that contains it with 0 / 1 / 2
+    planted GT..AG introns; band = stripe() with the shoulder that makes the band W diagonals wide."""
+    import ctypes as C
+    import torch
+    from spaln_b200 import Engine, Problem, capi, workload
+    rng = np.random.default_rng(SEED + 5 + 1000 * rank)
+    eng = Engine(prm, device=local_rank)
+    peak, peak_kind = measured_peak()
+    points = []
+    distinct = 1024
+    for W in (16, 32, 64, 128, 256, 512, 1024):
+        for m in (16, 32, 64, 128, 256, 512, 1024, 2048, 4096):
+            if not (256 <= m * W <= 65536):
+                continue
+            probs = []
+            for k in range(distinct):
+                nin = k % 3 if (W >= 64 and m >= 32) else 0
+                intr = [int(x) for x in rng.integers(20, max(21, W // 4), size=nin)]
+                q = workload.random_dna(rng, m)
+                cuts = np.sort(rng.choice(np.arange(4, m - 4), size=nin, replace=False)) if nin else []
+                parts, pos = [], 0
+                for c, il in zip(cuts, intr):
+                    it = workload.random_dna(rng, il)
+                    it[:2] = np.frombuffer(b"GT", np.uint8)
+                    it[-2:] = np.frombuffer(b"AG", np.uint8)
+                    parts += [q[pos:c], it]
+                    pos = c
+                parts.append(q[pos:])
+                gseq = np.concatenate(parts)
+                a, b = workload.DNA_CODE[q], workload.DNA_CODE[gseq]
+                s5, s3 = workload.synthetic_signals(b, rng)
+                sh = max(1, (W - (len(b) - len(a))) // 2)
+                lw, up = workload.stripe(0, len(a), 0, len(b), sh)
+                probs.append(Problem(a=a, b=b, sig5=s5, sig3=s3, a_left=0, a_right=len(a), b_left=0,
+                                     b_right=len(b), lw=lw, up=up, skl_cap=24))
+            arr, keep = eng._pack(probs, capi.FORWARD_WIP)
+            reps = max(1, args.sweep_tasks // distinct)
+            n = distinct * reps
+            big = (capi.GspalnTask * n)()
+            C.memmove(big, arr, C.sizeof(capi.GspalnTask) * distinct)
+            for r in range(1, reps):        # the same host buffers, independent device problems
+                C.memmove(C.byref(big, r * distinct * C.sizeof(capi.GspalnTask)), arr,
+                          C.sizeof(capi.GspalnTask) * distinct)
+            cells = sum(int(eng.lib.gspaln_task_cells(C.byref(arr[i]))) for i in range(distinct)) * reps
+            from spaln_b200.engine import PackedBatch
+            batch = PackedBatch(big, keep, n)
+            eng._check(eng.lib.gspaln_upload(eng._h, big, n), "gspaln_upload")
+            ks = []
+            for i in range(4):
+                eng.run()
+                if i:
+                    ks.append(eng.timing().kernel_ms)
+            eng.submit_packed(batch)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            eng.submit_packed(batch)
+            e2e_s = time.perf_counter() - t0
+            bad = int(np.count_nonzero(batch.status))
+            k_ms = float(np.mean(ks))
+            gc = cells / (k_ms * 1e-3) / 1e9
+            points.append({"W": W, "m": m, "tasks": n, "cells_per_task": cells // n, "kernel_ms": k_ms,
+                           "gcups": gc, "e2e_gcups": cells / e2e_s / 1e9, "tasks_per_s": n / (k_ms * 1e-3),
+                           "roofline_frac": gc * B_CELL / peak, "status_nonzero": bad})
+    eng.close()
+    return points
+
+
 def host_cells(raw):
     import ctypes as C
     from spaln_b200 import capi
@@ -573,6 +664,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--protein-queries", type=int, default=3000,
                     help="problems of the protein x genome leg per GPU (0 = skip the leg)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 5],
+                    help="2: the headline workload (default); 5: band-width x query-length sweep")
+    ap.add_argument("--sweep-tasks", type=int, default=102400, help="tasks per sweep point and rank")
     ap.add_argument("--leg", default="", help=argparse.SUPPRESS)
     ap.add_argument("--leg-seed", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--leg-out", default="", help=argparse.SUPPRESS)
@@ -596,8 +690,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        nsample = max(ncores, min(args.cpu_sample, 4 * ncores))
-        raw = make_workload(nsample, seed=20251017)
+        # a bounded sample of the same workload: >= 8 problems per host thread from a shared queue
+        nsample = max(args.cpu_sample, 8 * ncores)
+        raw = with_strings(make_workload(nsample))
         host_cells(raw)
         r = reference_run(raw, args.steps, max(1, args.warmup), ncores)
         if r is None:
@@ -606,6 +701,10 @@ def main():
         times, cells, _ = r
         ms = 1e3 * float(np.mean(times))
         val = cells / (ms * 1e-3) / 1e9
+        one_raw = with_strings(make_workload(6, first=nsample))
+        host_cells(one_raw)
+        one = reference_run(one_raw, 1, 0, 1)
+        val1 = sum(x["cells"] for x in one_raw) / float(np.mean(one[0])) / 1e9
         line = {
             "metric": METRIC, "value": val, "unit": "GCUPS", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(1, args.warmup), "ms_per_step": ms, "higher_is_better": True,
@@ -613,30 +712,63 @@ def main():
             "impl": "reference",
             "config": {"workload": workload_name, "sample": f"{nsample} problems of the workload per step"},
             "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": ncores, "kind": "reference",
-                             "sample": f"{nsample} config-2 problems ({cells / 1e6:.0f} Mcells) per step, "
-                                       f"SimdAln2s1::forwardS1_wip AVX2, {ncores} threads"},
+                             "per_core": val / ncores, "one_thread": val1,
+                             "sample": f"{nsample} config-2 problems ({cells / 1e6:.0f} Mcells) per step from a "
+                                       f"shared queue (largest first), SimdAln2s1::forwardS1_wip AVX2, "
+                                       f"{ncores} threads; one_thread = 6 further problems on one thread"},
             "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
         emit(line)
         return 0
 
+    if args.config == 5:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        pts = config5_sweep(args, prm, rank, local_rank, world)
+        if world > 1:
+            # weak scaling: every rank runs its own tasks of each point; a point ends when the slowest rank does
+            t = torch.tensor([[p["kernel_ms"], p["tasks"] * p["cells_per_task"] / p["e2e_gcups"] / 1e9] for p in pts],
+                             dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            for p, (k, e) in zip(pts, t.tolist()):
+                cells = p["tasks"] * p["cells_per_task"] * world
+                p.update(kernel_ms=k, gcups=cells / (k * 1e-3) / 1e9, e2e_gcups=cells / e / 1e9,
+                         tasks=p["tasks"] * world, tasks_per_s=p["tasks"] * world / (k * 1e-3))
+                p["roofline_frac"] = p["gcups"] / world * B_CELL / measured_peak()[0]
+            dist.destroy_process_group()
+        if rank == 0:
+            worst = min(pts, key=lambda p: p["gcups"])
+            best = max(pts, key=lambda p: p["gcups"])
+            emit({"metric": "GCUPS per (band width W, query length m) point, forwardS1_wip trace-back kernel",
+                  "value": float(np.exp(np.mean(np.log([p["gcups"] for p in pts])))), "unit": "GCUPS (geometric mean over points)",
+                  "n_gpus": n_gpus, "steps": 3, "warmup": 1, "higher_is_better": True, "scaling": "weak",
+                  "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+                  "config": {"workload": f"config5: band x length sweep, {args.sweep_tasks} tasks per point and GPU, "
+                                         "256 <= m*W <= 65536 cells per task"},
+                  "worst_point": worst, "best_point": best, "sweep": pts})
+        return 0
+
     # ------------------------------------------------------------------ our arm
+    # ONE job: rank 0 owns the formatted genome (the concatenated loci) and the query set of
+    # queries_per_gpu x N problems (weak scaling), generated before CUDA is touched (worker
+    # processes are forked)
+    from spaln_b200 import shard, workload
+    total_q = args.queries * world
+    g = workload.config2_global(total_q, SEED, procs=min(ncores, 48)) if rank == 0 else None
+
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
         print("bench.py: no CUDA device; the DP engine has no CPU fallback", file=sys.stderr)
         return 2
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    from spaln_b200 import Engine
-    raw = make_workload(args.queries, seed=20251017 + 7919 * rank)
-    host_cells(raw)
-    problems = to_problems(raw)
-    cells_step = sum(r["cells"] for r in raw)
-    eng = Engine(prm, device=local_rank)
+        dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -644,7 +776,40 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput (`value`)
+    KEYS = ("a", "b", "lens", "sig5", "sig3", "int53")
+
+    def job_inputs():
+        """formatted genome + query set + index (what a run broadcasts once), then the derived
+        per-column tables (in a real run each rank computes them with the scan kernels)"""
+        bufs = shard.broadcast_buffers([g[k] for k in KEYS] if rank == 0 else [None] * len(KEYS), 0, dev)
+        return dict(zip(KEYS, bufs))
+
+    def all_cells(lens):
+        """DP cells of every problem of the job (gspaln_task_cells), for the partition"""
+        import ctypes as C
+        from spaln_b200 import capi
+        lib = capi.load()
+        t = capi.GspalnTask()
+        out = np.empty(len(lens), np.int64)
+        for i, (la, lb) in enumerate(lens.tolist()):
+            t.a_left, t.a_right, t.b_left, t.b_right = 0, la, 0, lb
+            t.lw, t.up = workload.stripe(0, la, 0, lb, 100)
+            out[i] = lib.gspaln_task_cells(C.byref(t))
+        return out
+
+    from spaln_b200 import Engine
+    G = job_inputs()
+    cells_all = all_cells(G["lens"])
+    mine = shard.lpt_partition(cells_all, world)[rank]
+    raw = workload.global_problems(G, mine)
+    for r, c in zip(raw, cells_all[mine]):
+        r["cells"] = int(c)
+    problems = to_problems(raw)
+    cells_step = int(cells_all[mine].sum())
+    cells_job = int(cells_all.sum())
+    eng = Engine(prm, device=local_rank)
+
+    # ---- device-resident throughput (`value`): this rank's share, inputs in HBM
     eng.upload(problems)
     for _ in range(args.warmup):
         eng.run()
@@ -665,48 +830,64 @@ def main():
     res = eng.download()
     bad = sum(1 for r in res if r.status != 0)
 
-    # ---- end to end through the public API with host buffers (`e2e`)
-    e2e_steps = max(1, min(args.steps, 3))
-    packed = eng.pack(problems)                             # task descriptors (metadata) marshalled once
+    # ---- end to end (`e2e`): the whole job through the public API with HOST buffers, every
+    # step = broadcast of the formatted genome + query set from rank 0 (N > 1), cell-balanced
+    # partition, plan + marshal + pinned pack + H2D + kernels (+ walk) + D2H, hit records
+    # (GeneRecord headers + corners) gathered on rank 0
+    e2e_steps = max(1, min(args.steps, 5))
+    qlen = np.array([r["a_right"] for r in raw], np.int64)
+
+    def job_step():
+        t_a = time.perf_counter()
+        if world > 1:
+            shard.broadcast_buffers([g[k] for k in KEYS[:3]] if rank == 0 else [None] * 3, 0, dev)
+        t_b = time.perf_counter()
+        part = shard.lpt_partition(cells_all, world)[rank]
+        t_c = time.perf_counter()
+        packed = eng.pack(problems)                 # task descriptors marshalled inside the call
+        eng.submit_packed(packed)
+        t_d = time.perf_counter()
+        n_skl = np.minimum(packed.res["n_skl"][:packed.n], np.diff(packed.off)).astype(np.int64)
+        lens_c = np.repeat(np.cumsum(n_skl) - n_skl, n_skl)
+        src = np.repeat(packed.off[:-1], n_skl) + (np.arange(int(n_skl.sum())) - lens_c)
+        corners = packed.skl[src]
+        hits = shard.make_hits(part, packed.scores, n_skl, qlen, corners, min_intron=int(prm["llmt"]))
+        got = shard.gather_hit_records(hits, corners, 0, dev)
+        t_e = time.perf_counter()
+        return packed, got, (t_b - t_a, t_c - t_b, t_d - t_c, t_e - t_d)
+
     eng.submit(problems[: max(1, len(problems) // 50)])     # warm the pinned/device pools
-    eng.submit_packed(packed)                               # one untimed full step (host threads, page tables)
+    job_step()                                              # one untimed full step (host threads, page tables)
     barrier()
+    phases = np.zeros(4)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        # host numpy buffers -> pinned pack -> H2D -> kernels (+ walk) -> D2H -> host results
-        eng.submit_packed(packed)
+        packed, got, ph = job_step()
+        phases += ph
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    phases /= e2e_steps
     tm2 = eng.timing()
+    n_hits = len(got[0]) if got is not None else 0
+    if rank == 0:
+        assert n_hits == total_q and np.array_equal(got[0]["Rid"], np.arange(total_q))
     res2 = eng.forwardS1_wip(problems[: args.cpu_sample])   # sample kept as objects for the parity check
 
     # ---- the driver path (lspS_ng dispatch at the reference's default -V = 32 MiB):
     # Hirschberg passes + block re-alignments for the larger problems, host in the loop
-    eng.lspS_ng(problems, max_vmf_space=32 * 1024 * 1024, sh=int(prm["sh"]), alg=2)   # warm-up: pools of this path
+    lsp_opts = dict(max_vmf_space=32 * 1024 * 1024, sh=int(prm["sh"]), alg=2)
+    eng.lspS_ng(problems, **lsp_opts)   # warm-up: pools of this path
     barrier()
     t0 = time.perf_counter()
-    eng.lsp_packed(packed, max_vmf_space=32 * 1024 * 1024, sh=int(prm["sh"]), alg=2)     # descriptors marshalled once, as in `e2e`
+    packed3 = eng.pack(problems)
+    eng.lsp_packed(packed3, **lsp_opts)
     barrier()
     lsp_s = time.perf_counter() - t0
     tm3 = eng.timing()
-    lsp_bad = int(np.count_nonzero(packed.status))
+    lsp_bad = int(np.count_nonzero(packed3.status))
     from spaln_b200 import Result
-    res3 = [Result(int(packed.scores[i]), int(packed.status[i]), packed.corners(i).copy(), 0)
+    res3 = [Result(int(packed3.scores[i]), int(packed3.status[i]), packed3.corners(i).copy(), 0)
             for i in range(min(args.cpu_sample, len(problems)))]      # sample kept for the parity check
-
-    # ---- multi-GPU only: the final gather of the hit records (score + corners per query) to
-    # rank 0 -- the one collective of the query-sharded job, outside the DP timing
-    gather_ms = None
-    if world > 1:
-        from spaln_b200 import shard
-        barrier()
-        t0 = time.perf_counter()
-        hits = shard.gather_hits(np.arange(len(res)) * world + rank, [r.score for r in res],
-                                 [r.skl for r in res], dst=0, device=torch.device("cuda", local_rank))
-        barrier()
-        gather_ms = 1e3 * (time.perf_counter() - t0)
-        if rank == 0:
-            assert len(hits) == len(res) * world
 
     prot = None
     if args.protein_queries > 0:
@@ -714,14 +895,16 @@ def main():
                            with_cpu=(n_gpus == 1 and not args.no_cpu_baseline))
 
     if world > 1:
-        t = torch.tensor([dev_s, wall, e2e_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_s, wall, e2e_s] + phases.tolist(), dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_s, wall, e2e_s = [float(x) for x in t.tolist()]
+        dev_s, wall, e2e_s = [float(x) for x in t.tolist()[:3]]
+        phases = np.array(t.tolist()[3:])
         c = torch.tensor([cells_step, bad], dtype=torch.int64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         cells_total, bad = int(c[0]), int(c[1])
     else:
         cells_total = cells_step
+    assert cells_total == cells_job
 
     if rank == 0:
         ms_per_step = 1e3 * dev_s / args.steps
@@ -734,18 +917,25 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16", "data": "synthetic",
-            "config": {"workload": workload_name, "queries_per_gpu": args.queries,
-                       "cells_per_step_per_gpu": cells_step,
+            "config": {"workload": workload_name, "queries_per_gpu": args.queries, "queries_total": total_q,
+                       "cells_per_step_per_gpu": cells_step, "cells_per_step": cells_total,
                        "l2_policy": "inputs+trace per step far larger than L2 (no flush needed)",
-                       "parallelism": f"query-shard x{n_gpus}, no data-path collective"},
+                       "parallelism": f"ONE job of {total_q} queries: rank 0 broadcasts the formatted genome + "
+                                      f"query set (NCCL), LPT partition by gspaln_task_cells over {n_gpus} rank(s), "
+                                      "no data-path collective, GeneRecord hit records gathered on rank 0"},
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "queries_per_s": args.queries * n_gpus / (ms_per_step * 1e-3),
             "clocks": clocks,
             "e2e": {"value": cells_total / e2e_s / 1e9, "unit": "GCUPS",
                     "h2d_bytes_per_step": int(tm2.h2d_bytes), "d2h_bytes_per_step": int(tm2.d2h_bytes),
-                    "queries_per_s": args.queries * n_gpus / e2e_s,
-                    "phases_ms": {"h2d": tm2.h2d_ms, "kernel": tm2.kernel_ms, "d2h": tm2.d2h_ms,
-                                  "total": 1e3 * e2e_s}},
+                    "queries_per_s": args.queries * n_gpus / e2e_s, "steps": e2e_steps,
+                    "hit_records_on_rank0": n_hits,
+                    "phases_ms": {"bcast": 1e3 * phases[0], "partition": 1e3 * phases[1],
+                                  "marshal+pack+h2d+kernel+d2h": 1e3 * phases[2],
+                                  "hit_records+gather": 1e3 * phases[3],
+                                  "h2d_first_chunk": tm2.h2d_ms, "kernel": tm2.kernel_ms, "d2h": tm2.d2h_ms,
+                                  "total": 1e3 * e2e_s},
+                    "note": "max over ranks; per-rank bytes are this rank's"},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
@@ -769,28 +959,32 @@ def main():
         if n_gpus == 1:
             line["scan_path"] = scan_leg(prm, with_cpu=not args.no_cpu_baseline)
             line["config4_path"] = config4_leg(args, ncores, with_cpu=not args.no_cpu_baseline)
-        if gather_ms is not None:
-            line["gather_hits_ms"] = gather_ms
+        if world > 1:
+            line["bcast_ms"] = 1e3 * phases[0]
+            line["gather_ms"] = 1e3 * phases[3]
         if n_gpus == 1 and not args.no_cpu_baseline:
-            nsample = min(args.cpu_sample, len(raw))
-            sample = raw[:nsample]
+            nsample = min(max(args.cpu_sample, 8 * ncores), len(raw))
+            sample = with_strings(raw[:nsample])
+            npar = min(args.cpu_sample, nsample)    # problems whose results are compared
             r = reference_run(sample, 1, 1, ncores)
             if r is not None:
                 times, cells, out = r
                 # the reference results must equal ours on the sample
-                mism = sum(1 for i in range(nsample)
+                mism = sum(1 for i in range(npar)
                            if out[i]["score"] != res2[i].score or not np.array_equal(out[i]["skl"], res2[i].skl))
+                v = cells / float(np.mean(times)) / 1e9
                 line["cpu_baseline"] = {
-                    "value": cells / float(np.mean(times)) / 1e9, "unit": "GCUPS", "cores": ncores,
+                    "value": v, "unit": "GCUPS", "cores": ncores, "per_core": v / ncores,
                     "kind": "reference",
-                    "sample": f"first {nsample} problems of the step ({cells / 1e6:.0f} Mcells), "
-                              f"SimdAln2s1::forwardS1_wip AVX2 build, {ncores} threads",
+                    "sample": f"first {nsample} problems of the step ({cells / 1e6:.0f} Mcells) from a shared "
+                              f"queue (largest first), SimdAln2s1::forwardS1_wip AVX2 build, {ncores} threads; "
+                              f"results of the first {npar} compared with the GPU's",
                     "parity_mismatches_on_sample": mism}
                 # the same sample through the reference's own driver (default -V)
                 r = reference_run(sample, 1, 0, ncores, lsp=True)
                 times, cells, out = r
-                mism = sum(1 for i in range(nsample) if res3[i].status == 0 and
-                           (out[i]["score"] != res3[i].score or not np.array_equal(out[i]["skl"], res3[i].skl)))
+                mism = sum(1 for i in range(npar) if res3[i].status != 0 or
+                           out[i]["score"] != res3[i].score or not np.array_equal(out[i]["skl"], res3[i].skl))
                 line["cpu_baseline"]["lsp_path"] = {
                     "queries_per_s": nsample / float(np.mean(times)),
                     "gcups_root_cells": cells / float(np.mean(times)) / 1e9,

@@ -227,6 +227,62 @@ def config2_problem(rng, sh=100, **kw):
             "genome_str": g.tobytes().decode(), "query_str": q.tobytes().decode()}
 
 
+def config2_problem_seeded(seed: int, i: int, **kw):
+    """problem i of the seeded global config-2 query set: every problem has its own generator
+    state, so any rank (or worker process) can build any problem on its own"""
+    return config2_problem(np.random.default_rng([int(seed), int(i)]), **kw)
+
+
+def config2_chunk(args):
+    """worker of the global generator: problems [lo, hi) as flat arrays
+    (query codes, genome codes, sig5, sig3, int53, lengths)"""
+    seed, lo, hi, kw = args
+    A, B, S5, S3, I53, lens = [], [], [], [], [], []
+    for i in range(lo, hi):
+        r = config2_problem_seeded(seed, i, **kw)
+        A.append(r["a"]); B.append(r["b"]); S5.append(r["sig5"]); S3.append(r["sig3"])
+        I53.append(synthetic_int53(r["b"]))
+        lens.append((len(r["a"]), len(r["b"])))
+    return (np.concatenate(A), np.concatenate(B), np.concatenate(S5), np.concatenate(S3),
+            np.concatenate(I53), np.array(lens, np.int64))
+
+
+def config2_global(n: int, seed: int, procs: int = 1, **kw):
+    """The whole query set of a job as flat buffers: a dict with `a` (query codes), `b` (genome
+    codes: the concatenated loci, i.e. the formatted genome of the job), `sig5`, `sig3`, `int53`
+    (per locus len + 2 entries) and `lens` ((n, 2): query, locus length).  Problem i is
+    `config2_problem_seeded(seed, i)`.  procs > 1 forks worker processes (call before CUDA is
+    initialised)."""
+    step = 256
+    jobs = [(seed, lo, min(n, lo + step), kw) for lo in range(0, n, step)]
+    if procs > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(procs, len(jobs))) as pool:
+            parts = pool.map(config2_chunk, jobs)
+    else:
+        parts = [config2_chunk(j) for j in jobs]
+    keys = ("a", "b", "sig5", "sig3", "int53", "lens")
+    return {k: np.concatenate([p[j] for p in parts]) for j, k in enumerate(keys)}
+
+
+def global_problems(g: dict, index, sh=100):
+    """raw problem dicts (views into the flat buffers) of the problems `index` of a global set"""
+    lens = g["lens"]
+    a_off = np.concatenate([[0], np.cumsum(lens[:, 0])])
+    b_off = np.concatenate([[0], np.cumsum(lens[:, 1])])
+    t_off = np.concatenate([[0], np.cumsum(lens[:, 1] + 2)])
+    out = []
+    for i in index:
+        i = int(i)
+        la, lb = int(lens[i, 0]), int(lens[i, 1])
+        lw, up = stripe(0, la, 0, lb, sh)
+        out.append({"a": g["a"][a_off[i]:a_off[i] + la], "b": g["b"][b_off[i]:b_off[i] + lb],
+                    "sig5": g["sig5"][t_off[i]:t_off[i] + lb + 2], "sig3": g["sig3"][t_off[i]:t_off[i] + lb + 2],
+                    "int53": g["int53"][t_off[i]:t_off[i] + lb + 2],
+                    "a_left": 0, "a_right": la, "b_left": 0, "b_right": lb, "lw": lw, "up": up, "index": i})
+    return out
+
+
 # ---------------------------------------------------------------------------
 # protein x genome (BASELINE.json config 3 shape)
 # ---------------------------------------------------------------------------

@@ -32,10 +32,32 @@ def _worker(rank, world, port, n, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     genome = np.arange(1000, dtype=np.uint8) if rank == 0 else np.zeros(0, np.uint8)
     g = shard.broadcast_genome(genome)
+    # formatted genome + query set + index table in one call, dtypes and shapes preserved
+    src = [np.arange(77, dtype=np.uint8), np.arange(12, dtype=np.int64).reshape(6, 2) * 1000003,
+           np.arange(9, dtype=np.int16) - 4]
+    got = shard.broadcast_buffers(src if rank == 0 else [None] * 3)
+    assert all(x.dtype == y.dtype and x.shape == y.shape and np.array_equal(x, y) for x, y in zip(got, src))
     cells = np.random.default_rng(7).integers(100, 100000, size=n)
     mine = shard.lpt_partition(cells, world)[rank]
     hits = [_fake_hit(int(i)) for i in mine]
     out = shard.gather_hits(mine, [h[0] for h in hits], [h[1] for h in hits], dst=0)
+    # the vectorised form: GeneRecord headers + one flat corner block per rank
+    lens = np.array([len(h[1]) for h in hits], np.int64)
+    flat = np.concatenate([h[1] for h in hits]) if lens.sum() else np.zeros((0, 2), np.int32)
+    hdr = shard.make_hits(mine, [h[0] for h in hits], lens, 100 + np.asarray(mine), flat, scale=10.0)
+    rec = shard.gather_hit_records(hdr, flat, dst=0)
+    if rank == 0:
+        hh, cc = rec
+        assert hh.dtype == shard.HIT_DTYPE and np.array_equal(hh["Rid"], np.arange(n))
+        for i in range(n):
+            sc, sk = _fake_hit(i)
+            r = hh[i]
+            assert abs(float(r["Gscore"]) - sc / 10.0) < 1e-3 and r["Rlen"] == 100 + i
+            assert np.array_equal(cc[r["skl_off"]: r["skl_off"] + r["n_skl"]], sk)
+            if len(sk):
+                assert (r["Rend"], r["Gend"]) == tuple(sk[0]) and (r["Rstart"], r["Gstart"]) == tuple(sk[-1])
+    else:
+        assert rec is None
     if rank == 0:
         ok = len(out) == n and all(out[i][0] == _fake_hit(i)[0] and
                                    np.array_equal(out[i][1], _fake_hit(i)[1]) for i in range(n))
@@ -72,3 +94,16 @@ def test_gather_single_process_passthrough():
     from spaln_b200 import shard
     out = shard.gather_hits([3, 5], [10, 20], [np.zeros((2, 2), np.int32), np.zeros((0, 2), np.int32)])
     assert out[3][0] == 10 and out[3][1].shape == (2, 2) and out[5][1].shape == (0, 2)
+
+
+def test_hit_record_header_is_the_reference_generecord():
+    """leading 72 bytes == GeneRecord of src/seq.h:1235-1255 (14 ints, 3 floats, 2 shorts)"""
+    from spaln_b200 import shard
+    names = [f[0] for f in shard.GENE_RECORD_FIELDS]
+    assert names == ["Cid", "Gstart", "Gend", "Nrecord", "nexn", "Rid", "Rlen", "Rstart", "Rend", "mmc", "unp",
+                     "bmmc", "bunp", "ng", "Gscore", "Pmatch", "Pcover", "Csense", "Rsense"]
+    assert np.dtype(shard.GENE_RECORD_FIELDS).itemsize == 72
+    # exons = 1 + genomic jumps at a fixed query coordinate
+    corners = np.array([[90, 900], [60, 870], [60, 500], [30, 470], [30, 200], [0, 170]], np.int32)
+    h = shard.make_hits([7], [1234], [6], [90], corners, scale=10.0, min_intron=50)
+    assert h["nexn"][0] == 3 and h["Gstart"][0] == 170 and h["Gend"][0] == 900 and h["Rid"][0] == 7
