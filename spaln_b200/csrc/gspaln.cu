@@ -80,6 +80,10 @@ struct gspaln_ctx {
     gspaln_timing tim;
     std::string err;
     int grid_trace = 0, grid_score = 0;
+    // packed int16x2 kernels (gspaln_packed.cuh)
+    bool pk_ok = false;
+    size_t smem_pk = 0;
+    int grid_trace_pk = 0, grid_score_pk = 0;
 };
 
 namespace {
@@ -117,6 +121,16 @@ KernelFn kernel_fn(bool trace, bool local, bool spj, bool dagp = false)
 const void* kernel_ptr(bool trace, bool local, bool spj, bool dagp = false)
 {
     return reinterpret_cast<const void*>(kernel_fn(trace, local, spj, dagp));
+}
+
+// the packed int16x2 kernels: single affine, global / semi-global
+KernelFn pk_kernel_fn(bool trace, bool spj)
+{
+    static const KernelFn tab[4] = {
+        dp_wip_kernel<false, false, false, false, true>, dp_wip_kernel<false, false, true, false, true>,
+        dp_wip_kernel<true, false, false, false, true>, dp_wip_kernel<true, false, true, false, true>,
+    };
+    return tab[(trace ? 2 : 0) | (spj ? 1 : 0)];
 }
 
 using UdhKernelFn = void (*)(const DevParams*, const int2*, const DevTask*, const int*, int, int*,
@@ -230,6 +244,26 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
     }
     P.pen_cap = cap;
     ctx->pen_cap = cap;
+    // May the packed int16x2 kernel run problems of this parameter set?  It clamps the low side
+    // only (gap and intron penalties must be <= 0), keeps 8 x the intron-length counter in 16 bits,
+    // and knows the residue classes A, C, G, T, N of the DNA alphabet.
+    {
+        bool ok = prm->simdim == 17 && prm->noll == 2 && !prm->local && prm->gop <= 0 && cap <= 4000 &&
+                  getenv("GSPALN_NO_PACKED") == nullptr;
+        for (int j = 0; j < P.nquant; ++j) ok = ok && P.mean[j] <= 0 && P.mean[j] >= -PK_SIGMAX;
+        if (prm->spj) ok = ok && P.ipen <= PK_SIGMAX && P.ipen >= -PK_SIGMAX;
+        int pvmax = 0;
+        for (int q = 0; q < prm->simdim; ++q)
+            for (int g = 0; g < prm->simdim; ++g) {
+                const int v = (short) prm->simmtx[q * prm->simdim + g];
+                ok = ok && v >= -1024 && v <= 1024;
+                pvmax = std::max(pvmax, v);
+            }
+        P.pk_ok = ok ? 1 : 0;
+        P.pk_pvmax = pvmax;
+        P.pk_nidx = P.perm[16];
+        ctx->pk_ok = ok;
+    }
     ctx->hP = P;
     ctx->smem_bytes = sizeof(RingEntry) * RING * CTA_THREADS + sizeof(int2) * (size_t) (cap + 1);
     if (ctx->smem_bytes > 108 * 1024) {     // two CTAs per SM must fit
@@ -258,6 +292,18 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
         cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_bytes);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ku, CTA_THREADS, ctx->smem_bytes);
         ctx->grid_udh = std::max(1, occ) * ctx->sm_count;
+    }
+    if (ctx->pk_ok) {
+        ctx->smem_pk = (sizeof(PkRingA) + sizeof(PkRingB)) * PK_RING * CTA_THREADS + sizeof(uint2) * PK_T4 +
+                       sizeof(PkPen) * (size_t) (cap + 1);
+        const void* pt = reinterpret_cast<const void*>(pk_kernel_fn(true, P.spj));
+        const void* ps = reinterpret_cast<const void*>(pk_kernel_fn(false, P.spj));
+        cudaFuncSetAttribute(pt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_pk);
+        cudaFuncSetAttribute(ps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_pk);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt, CTA_THREADS, ctx->smem_pk);
+        ctx->grid_trace_pk = std::max(1, occ) * ctx->sm_count;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ps, CTA_THREADS, ctx->smem_pk);
+        ctx->grid_score_pk = std::max(1, occ) * ctx->sm_count;
     }
     if (cudaGetLastError() != cudaSuccess) { gspaln_destroy(ctx); return GSPALN_ECUDA; }
     *out = ctx;
@@ -393,8 +439,8 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         auto ctas = [&](int full, int count) {
             return std::max(1, std::min(full, (count + WARPS_PER_CTA - 1) / WARPS_PER_CTA));
         };
-        int gt = n_trace ? ctas(ctx->grid_trace, n_trace) : 0;
-        int gs = n_score ? ctas(ctx->grid_score, n_score) : 0;
+        int gt = n_trace ? ctas(std::max(ctx->grid_trace, ctx->grid_trace_pk), n_trace) : 0;
+        int gs = n_score ? ctas(std::max(ctx->grid_score, ctx->grid_score_pk), n_score) : 0;
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         free_b += ctx->d_trace.cap + ctx->d_band.cap * sizeof(unsigned);
@@ -461,7 +507,15 @@ static void pack_range(gspaln_ctx* ctx, const gspaln_task* tasks, int lo, int hi
             const DevTask& d = ctx->h_tasks.p[i];
             const int mw = t.a_right - t.a_left, nw = t.b_right - t.b_left;
             unsigned char* ap = ctx->h_apool.p + d.a_off;
-            for (int j = 0; j < mw; ++j) ap[j] = ctx->perm[t.a[t.a_left + j] & 31];
+            // residues the packed kernel knows: A, C, G, T, N (codes 2, 3, 5, 9, 16 of the DNA alphabet)
+            constexpr unsigned PK_CODES = (1u << 2) | (1u << 3) | (1u << 5) | (1u << 9) | (1u << 16);
+            unsigned seen = 0;
+            int sigmax = 0;
+            for (int j = 0; j < mw; ++j) {
+                const unsigned c = t.a[t.a_left + j] & 31;
+                seen |= 1u << c;
+                ap[j] = ctx->perm[c];
+            }
             ColInfo* col = ctx->h_cpool.p + d.col_off;
             const bool spj = ctx->prm.spj != 0;
             for (int j = 0; j <= nw; ++j) {
@@ -469,6 +523,8 @@ static void pack_range(gspaln_ctx* ctx, const gspaln_task* tasks, int lo, int hi
                 ColInfo ci;
                 ci.sig5 = spj ? t.sig5[c] : 0;
                 ci.sig3 = spj ? t.sig3[c] : 0;
+                sigmax = std::max(sigmax, std::max(std::abs((int) ci.sig5), std::abs((int) ci.sig3)));
+                if (j > 0) seen |= 1u << (t.b[c - 1] & 31);
                 ci.code = j > 0 ? ctx->perm[t.b[c - 1] & 31] : 0;
                 // INT53 nibbles ride in the padding: [0] dinc5 | dinc3 << 4, [1] cano5 | cano3 << 4
                 const unsigned i53 = t.int53 ? t.int53[c] : 0u;
@@ -477,6 +533,9 @@ static void pack_range(gspaln_ctx* ctx, const gspaln_task* tasks, int lo, int hi
                 ci.pad[2] = 0;
                 col[j] = ci;
             }
+            // the byte behind the query codes: this problem may run on the packed int16x2 kernel
+            ap[mw] = (ctx->pk_ok && !(seen & ~PK_CODES) && sigmax <= PK_SIGMAX &&
+                      (t.kind == GSPALN_FORWARD_WIP || t.kind == GSPALN_SCOREONLY_WIP)) ? 1 : 0;
         }
     };
     size_t work = 0;
@@ -519,15 +578,31 @@ static int launch_range(gspaln_ctx* ctx, int lo, int hi, int slot, int& launches
     const bool local = ctx->prm.local != 0, spj = ctx->prm.spj != 0, dagp = ctx->prm.noll == 3;
     int* tick = ctx->d_ticket.p + 3 * slot;
     const int cnt = hi - lo;
+    // packed int16x2 kernels first (problems the host marked eligible); the 32-bit kernels behind
+    // them take the rest and whatever the packed ones hand back (status 6)
+    if (ctx->pk_ok && ctx->n_trace) {
+        pk_kernel_fn(true, spj)<<<std::min(ctx->grid_run_trace, ctx->grid_trace_pk), CTA_THREADS, ctx->smem_pk, ctx->stream>>>(
+            ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 4,
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
+            ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p, ready);
+        ++launches;
+    }
+    if (ctx->pk_ok && ctx->n_score) {
+        pk_kernel_fn(false, spj)<<<std::min(ctx->grid_run_score, ctx->grid_score_pk), CTA_THREADS, ctx->smem_pk, ctx->stream>>>(
+            ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 5,
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
+            ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p, ready);
+        ++launches;
+    }
     if (ctx->n_trace) {
-        kernel_fn(true, local, spj, dagp)<<<ctx->grid_run_trace, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+        kernel_fn(true, local, spj, dagp)<<<std::min(ctx->grid_run_trace, ctx->grid_trace), CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
             ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick,
             ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
             ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p, ready);
         ++launches;
     }
     if (ctx->n_score) {
-        kernel_fn(false, local, spj, dagp)<<<ctx->grid_run_score, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+        kernel_fn(false, local, spj, dagp)<<<std::min(ctx->grid_run_score, ctx->grid_score), CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
             ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 1,
             ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
             ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p, ready);

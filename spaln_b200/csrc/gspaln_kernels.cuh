@@ -25,6 +25,7 @@
 #include <climits>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "gspaln_packed.cuh"
 
 namespace gspaln {
 
@@ -65,6 +66,9 @@ struct DevParams {
     int avmch, local, spj, simdim, gappen1, gop, gep;
     int pen_cap;                // pen table has pen_cap + 1 entries
     int lgop, lgep, noll, llmt, codonk1;    // raw values for the scalar kernel (gspaln_ng.cuh)
+    int pk_ok;                  // the packed int16x2 kernel may run problems of this parameter set
+    int pk_pvmax;               // largest positive substitution score (high-side monitor)
+    int pk_nidx;                // table index of the residue class N
     int mtxT[32 * MTX_LD];      // [genome index][query index] (remapped codes); row/col ZROW == 0
     unsigned char perm[32];     // residue code -> table index
 };
@@ -100,11 +104,11 @@ struct __align__(16) RingEntry {
     int pad;
 };
 
-__device__ __forceinline__ int sat16(int x) { return max(min(x, 32767), -32768); }
-__device__ __forceinline__ int satlo(int x) { return max(x, -32768); }     // addend <= 0
-__device__ __forceinline__ int lo16(unsigned w) { return (int) (short) (w & 0xffffu); }
-__device__ __forceinline__ int hi16(unsigned w) { return (int) (short) (w >> 16); }
-__device__ __forceinline__ unsigned pack16(int lo, int hi)
+__host__ __device__ __forceinline__ int sat16(int x) { return max(min(x, 32767), -32768); }
+__host__ __device__ __forceinline__ int satlo(int x) { return max(x, -32768); }     // addend <= 0
+__host__ __device__ __forceinline__ int lo16(unsigned w) { return (int) (short) (w & 0xffffu); }
+__host__ __device__ __forceinline__ int hi16(unsigned w) { return (int) (short) (w >> 16); }
+__host__ __device__ __forceinline__ unsigned pack16(int lo, int hi)
 {
     return ((unsigned) lo & 0xffffu) | ((unsigned) hi << 16);
 }
@@ -172,7 +176,7 @@ struct SmemLayout {
 //       clamp to the table size).
 // ---------------------------------------------------------------------------
 template <bool TRACE, bool LOCAL, bool SPJ, bool DAGP>
-__device__ __forceinline__ void strip_step(
+__host__ __device__ __forceinline__ void strip_step(
     int (&HO)[NR], const int (&HN)[NR], int (&F)[NR], int (&E)[NR],
     int (&F2)[NR], int (&E2)[NR], int up_f2, int gn2, int ge2,
     int (&V2)[NR], int (&NJ)[NR], const int (&arow)[NR],
@@ -533,9 +537,210 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
     }
 }
 
+// shared-memory carve-up of the packed kernel
+struct SmemPk {
+    PkRingA* ringA;             // [PK_RING][CTA_THREADS]
+    PkRingB* ringB;             // [PK_RING][CTA_THREADS]
+    const uint2* t4;            // [PK_T4] pair table
+    const PkPen* pen;           // [pen_cap + 1]
+};
+
+struct PkMonitor { int hmax, s3max, s5max; };
+
+// ---------------------------------------------------------------------------
+// run_pass with the packed cell update (gspaln_packed.cuh): same systolic chain, same band-row and
+// trace-slab traffic.  Differences: a thread holds its 8 strip rows as 4 registers of two rows
+// (j, j + 4); it follows the column its FIRST row sits on (n - row0), so that its private ring
+// needs only the last 4 column pairs; the two gap states travel minus gn (converted where they
+// meet the band rows); no local-mode bookkeeping (local problems run on the 32-bit kernel).
+// ---------------------------------------------------------------------------
+template <bool TRACE, bool SPJ>
+__device__ void run_pass_pk(const DevParams& P, const SmemPk& sm, const DevTask& t,
+                            const unsigned char* __restrict__ aseq, const ColInfo* __restrict__ cols,
+                            unsigned* band, unsigned char* trace, int ml0, int nstr, WarpMax& wmax,
+                            PkMonitor& mon)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int slot = lane / TPS;
+    const int sub = lane % TPS;
+    const int row0 = sub * NR;
+    const int pred_lane = ((slot + SPP - 1) % SPP) * TPS;
+    const int width = t.up - t.lw + 3;
+    static_assert(NR == 8 && TPS == 2, "the packed kernel is written for 8 rows per thread");
+
+    int sidx = slot;
+    StripGeom g = strip_geom<TRACE>(t, ml0 + NELEM * min(sidx, nstr - 1));
+    int nsteps = g.n_last - g.n_start + 1;
+    int off = 0;
+    int state = sidx < nstr ? (sidx == 0 ? (nsteps > 0 ? 1 : 3) : 0) : 2;
+    int rec_si = sidx == 0 ? 0 : -1000, rec_d = -g.n_start, old_si = -1000, old_d = 0;
+
+    PkConst K;
+    K.gn = pk_dup(P.gn); K.ge = pk_dup(P.ge); K.cgn = pk_dup(-32768 - P.gn); K.nev = pk_dup(NEV);
+    K.one = 0x00010001u; K.eight = 0x00080008u; K.cap8 = pk_dup(8 * P.pen_cap);
+    const unsigned nev2 = K.nev, hg0 = pk_max(K.nev, K.cgn), gt0 = pk_dup(NEV - P.gn);
+    unsigned HA[4], HB[4], HG[4], Ft[4], Et[4], V2[4], HL[4], arow4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        HA[j] = nev2; HB[j] = nev2; HG[j] = hg0; Ft[j] = gt0; Et[j] = gt0; V2[j] = nev2; HL[j] = 0u;
+        arow4[j] = (unsigned) ((PK_ZC * PK_NC + PK_ZC) * 8);
+    }
+    // incoming (row above) words: H in the half `sel` picks, likewise the vertical state
+    const unsigned sel = sub ? 0x5432u : 0x5410u;
+    const unsigned fconv = sub ? 0u : ((unsigned) (-P.gn) & 0xffffu);   // band rows hold F, registers F - gn
+    unsigned prev_in = nev2;
+    unsigned hmax = pk_dup(-32768);
+    int s3max = 0, s5max = 0;
+
+    PkRingA* ringA = sm.ringA + threadIdx.x;
+    PkRingB* ringB = sm.ringB + threadIdx.x;
+    const char* t4_bytes = reinterpret_cast<const char*>(sm.t4);
+    const char* pen_bytes = reinterpret_cast<const char*>(sm.pen);
+    const int ipen = P.ipen;
+    const int nidx = P.pk_nidx;
+    auto cls_of = [&](int idx) -> int { return idx < 4 ? idx : (idx == nidx ? 4 : PK_ZC); };
+
+    auto col_fetch = [&](int c) -> uint2 {
+        if (c >= t.b_left && c <= t.b_right)
+            return __ldg(reinterpret_cast<const uint2*>(cols + (c - t.b_left)));
+        return make_uint2(0u, 0xffffffffu);
+    };
+    // column c into the ring; columns left of the strip's first one pair residues but carry no signal
+    auto col_push = [&](uint2 ci, int c, bool with_sig) {
+        int cls = PK_ZC, s3 = 0, s5 = 0;
+        if (ci.y != 0xffffffffu) {
+            if (c > t.b_left) cls = cls_of((int) (ci.y & 0xffu));
+            if (SPJ && with_sig) {
+                s3 = hi16(ci.x);
+                s5 = (int) (short) (lo16(ci.x) + ipen);
+                s3max = max(s3max, s3); s5max = max(s5max, s5);
+            }
+        }
+        pk_ring_push(ringA, ringB, CTA_THREADS, c, cls, s3, s5);
+    };
+
+    unsigned pf_band = 0;
+    uint2 nxt_col = make_uint2(0u, 0xffffffffu);
+    const int max_iter = nstr * (width + 3 * NELEM + 8) + 64;
+    for (int i = -1; ; ++i) {
+        if (i > max_iter) { wmax.err = 1; break; }
+        {
+            const int p_rec_si = __shfl_sync(FULL, rec_si, pred_lane);
+            const int p_rec_d = __shfl_sync(FULL, rec_d, pred_lane);
+            const int p_old_si = __shfl_sync(FULL, old_si, pred_lane);
+            const int p_old_d = __shfl_sync(FULL, old_d, pred_lane);
+            if (state == 0 && (p_rec_si == sidx - 1 || p_old_si == sidx - 1)) {
+                const int pd = p_rec_si == sidx - 1 ? p_rec_d : p_old_d;
+                off = max(i + 1, pd + g.n_start + (NELEM - 1 + LAG));
+                old_si = rec_si; old_d = rec_d;
+                rec_si = sidx; rec_d = off - g.n_start;
+                state = nsteps > 0 ? 1 : 3;
+            } else if (state == 3) {
+                sidx += SPP;
+                if (sidx < nstr) {
+                    g = strip_geom<TRACE>(t, ml0 + NELEM * sidx);
+                    nsteps = g.n_last - g.n_start + 1;
+                    state = 0;
+                } else
+                    state = 2;
+            }
+        }
+        if (!__any_sync(FULL, state != 2)) break;
+        const bool run = state == 1;
+        const int j = i - off;
+        const int j8 = g.j9 - 1;
+        // the upper thread's row 7 (H of the previous step, vertical state) for the lower thread
+        const unsigned sh_h = __shfl_up_sync(FULL, (i & 1) ? HA[3] : HB[3], 1);
+        const unsigned sh_f = __shfl_up_sync(FULL, Ft[3], 1);
+        const int band_bias = g.ml + t.lw - 1;
+        if (run && j == -1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                HA[q] = nev2; HB[q] = nev2; HG[q] = hg0; Ft[q] = gt0; Et[q] = gt0; V2[q] = nev2; HL[q] = 0u;
+                const int r_lo = row0 + q, r_hi = row0 + q + 4;
+                const int a_lo = r_lo < g.j9 ? cls_of((int) aseq[(g.ml - t.a_left) + r_lo]) : PK_ZC;
+                const int a_hi = r_hi < g.j9 ? cls_of((int) aseq[(g.ml - t.a_left) + r_hi]) : PK_ZC;
+                arow4[q] = (unsigned) ((a_lo * PK_NC + a_hi) * 8);
+            }
+            prev_in = nev2;
+            if (sub == 0) {
+                if (nsteps > 0) pf_band = __ldcg(band + (g.n_start - band_bias));
+                prev_in = __ldcg(band + (g.n_start - 1 - band_bias));
+            }
+            const int cs = g.n_start - row0;            // first column of this thread's first row
+            nxt_col = col_fetch(cs);
+#pragma unroll 1
+            for (int d = 7; d >= 1; --d) col_push(col_fetch(cs - d), cs - d, false);
+        } else if (run && j >= 0) {
+            const int n = g.n_start + j;
+            const int cn = n - row0;
+            const unsigned cur_band = pf_band;
+            col_push(nxt_col, cn, cn >= g.n_start);
+            if (sub == 0 && j + 1 < nsteps) pf_band = __ldcg(band + (n + 1 - band_bias));
+            if (j + 1 < nsteps) nxt_col = col_fetch(cn + 1);
+            const int rslot = (cn & 3) + 4;
+            const char* ra_hi = reinterpret_cast<const char*>(ringA + rslot * CTA_THREADS);
+            const char* rb_hi = reinterpret_cast<const char*>(ringB + rslot * CTA_THREADS);
+            const unsigned in = sub ? sh_h : cur_band;
+            const unsigned in_f = sub ? sh_f : cur_band;
+            unsigned tw[2];
+            if (i & 1) {
+                const unsigned uh0 = pk_perm(in, HA[3], sel);
+                const unsigned uft0 = pk_add(pk_perm(in_f, Ft[3], 0x5432u), fconv);
+                const unsigned dg0 = pk_perm(prev_in, HB[3], sel);
+                strip_step_pk<TRACE, SPJ>(HB, HA, HG, Ft, Et, V2, HL, arow4, ra_hi, rb_hi,
+                                          CTA_THREADS * (int) sizeof(PkRingA), CTA_THREADS * (int) sizeof(PkRingB),
+                                          t4_bytes, pen_bytes, uh0, uft0, dg0, K, tw, hmax);
+            } else {
+                const unsigned uh0 = pk_perm(in, HB[3], sel);
+                const unsigned uft0 = pk_add(pk_perm(in_f, Ft[3], 0x5432u), fconv);
+                const unsigned dg0 = pk_perm(prev_in, HA[3], sel);
+                strip_step_pk<TRACE, SPJ>(HA, HB, HG, Ft, Et, V2, HL, arow4, ra_hi, rb_hi,
+                                          CTA_THREADS * (int) sizeof(PkRingA), CTA_THREADS * (int) sizeof(PkRingB),
+                                          t4_bytes, pen_bytes, uh0, uft0, dg0, K, tw, hmax);
+            }
+            prev_in = in;
+            if (TRACE) {
+                unsigned char* tr = trace + ((long long) (sidx + (ml0 - t.a_left) / NELEM) * (width + TRACE_PAD) + j) * NELEM + row0;
+                *reinterpret_cast<uint2*>(tr) = make_uint2(tw[0], tw[1]);
+            }
+            // bottom row of the strip -> band buffer (src/fwd2s1_wip_simd.h:438-442)
+            if (j8 >= row0 && j8 < row0 + NR) {
+                const int kbot = j8 - row0, kq = kbot & 3;
+                // (explicit selects: an indexed read would push the register arrays to local memory)
+                const unsigned h01 = (i & 1) ? (kq == 0 ? HB[0] : HB[1]) : (kq == 0 ? HA[0] : HA[1]);
+                const unsigned h23 = (i & 1) ? (kq == 2 ? HB[2] : HB[3]) : (kq == 2 ? HA[2] : HA[3]);
+                const unsigned hw = kq < 2 ? h01 : h23;
+                const unsigned fw = kq < 2 ? (kq == 0 ? Ft[0] : Ft[1]) : (kq == 2 ? Ft[2] : Ft[3]);
+                const int out_h = kbot < 4 ? lo16(hw) : hi16(hw);
+                const int out_f = (int) (short) ((kbot < 4 ? lo16(fw) : hi16(fw)) + P.gn);
+                const int cb = n - j8;
+                const int r0 = cb - (g.ml + g.j9);
+                if (cb > t.b_left && r0 >= t.lw && r0 <= t.up)
+                    __stcg(band + (r0 - t.lw + 1), pack16(out_h, out_f));
+            }
+            if (j == nsteps - 1) {
+                sidx += SPP;
+                if (sidx < nstr) {
+                    g = strip_geom<TRACE>(t, ml0 + NELEM * sidx);
+                    nsteps = g.n_last - g.n_start + 1;
+                    state = 0;
+                } else
+                    state = 2;
+            }
+        }
+        __syncwarp();
+    }
+    mon.hmax = max(mon.hmax, max(lo16(hmax), hi16(hmax)));
+    mon.s3max = max(mon.s3max, s3max);
+    mon.s5max = max(mon.s5max, s5max);
+}
+
 // ---------------------------------------------------------------------------
 // trace-code lookup for the walk (cells never evaluated read as STOP = 0)
 // ---------------------------------------------------------------------------
+template <bool PK>
 struct TraceView {
     const DevTask* t;
     const unsigned char* trace;
@@ -549,15 +754,19 @@ struct TraceView {
         const StripGeom g = strip_geom<true>(T, T.a_left + s * NELEM);
         const int j = cur_n + T.b_left + k - g.n_start;     // step at which row k sat on this column
         if (j < 0 || j > g.n_last - g.n_start) return 0u;
-        return trace[((long long) s * (width + TRACE_PAD) + j) * NELEM + k];
+        const unsigned char* cell = trace + ((long long) s * (width + TRACE_PAD) + j) * NELEM;
+        if (PK)     // raw decision bits, rows permuted inside each thread's 8 bytes
+            return pk_trace_code(cell[(k & 8) + pk_trace_byte(k & 7)]);
+        return cell[k];
     }
 };
 
 // Anti_rhomb_coord<CHAR>::traceback + go_back (src/rhomb_coord.h:142-235), step = 1
+template <bool PK>
 static __device__ int walk_trace(const DevTask& t, const unsigned char* trace, int m_abs, int n_abs,
                           int2* skl, int cap, int* status)
 {
-    TraceView tv{&t, trace, t.up - t.lw + 3};
+    TraceView<PK> tv{&t, trace, t.up - t.lw + 3};
     int m = m_abs - t.a_left, n = n_abs - t.b_left;
     unsigned code = tv.code(m, n);
     int cnt = 0;
@@ -609,7 +818,13 @@ static __device__ int walk_trace(const DevTask& t, const unsigned char* trace, i
 // ---------------------------------------------------------------------------
 // persistent kernel: each warp pulls problems from a global ticket counter
 // ---------------------------------------------------------------------------
-template <bool TRACE, bool LOCAL, bool SPJ, bool DAGP>
+// PK = true: the packed int16x2 kernel.  It takes the problems marked eligible by the host (residue
+// classes A, C, G, T, N only; bounded signals -- the byte behind the query codes) and reports
+// status 6 for a problem whose values came too close to +32767 (see gspaln_packed.cuh); the 32-bit
+// kernel (PK = false), launched behind it on the same stream, runs everything else plus those.
+constexpr int ST_NEED_EXACT = 6;
+
+template <bool TRACE, bool LOCAL, bool SPJ, bool DAGP, bool PK = false>
 __global__ void __launch_bounds__(CTA_THREADS, 3)
 dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
               const DevTask* __restrict__ tasks,
@@ -628,11 +843,41 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
     __syncthreads();
     const DevParams& P = sP;
     SmemLayout sm;
-    sm.ring = reinterpret_cast<RingEntry*>(smem_raw);
-    int2* spen = reinterpret_cast<int2*>(smem_raw + sizeof(RingEntry) * RING * CTA_THREADS);
-    for (int i = threadIdx.x; i <= P.pen_cap; i += blockDim.x) spen[i] = gpen[i];
-    sm.pen = spen;
-    sm.mtx = sP.mtxT;
+    SmemPk smk;
+    if (PK) {
+        smk.ringA = reinterpret_cast<PkRingA*>(smem_raw);
+        smk.ringB = reinterpret_cast<PkRingB*>(smem_raw + sizeof(PkRingA) * PK_RING * CTA_THREADS);
+        uint2* t4 = reinterpret_cast<uint2*>(smem_raw + (sizeof(PkRingA) + sizeof(PkRingB)) * PK_RING * CTA_THREADS);
+        PkPen* ppen = reinterpret_cast<PkPen*>(t4 + PK_T4);
+        struct Mfun {
+            const int* t; int nidx;
+            __device__ int operator()(int cc, int ac) const
+            {
+                const int g = cc < 4 ? cc : (cc == 4 ? nidx : ZROW), q = ac < 4 ? ac : (ac == 4 ? nidx : ZROW);
+                return t[g * MTX_LD + q];
+            }
+        } mfun{sP.mtxT, P.pk_nidx};
+        for (int i = threadIdx.x; i < PK_T4; i += blockDim.x) pk_t4_entry(t4[i], i, mfun);
+        for (int i = threadIdx.x; i <= P.pen_cap; i += blockDim.x) {
+            const int2 e = gpen[i];
+            const bool valid = e.y == -32768;
+            const int pv = valid ? e.x : 0;
+            ppen[i].pc = ((unsigned) pv & 0xffffu) | ((unsigned) (-32768 - pv) << 16);
+            ppen[i].valid = valid ? 0xffffu : 0u;
+        }
+        for (int sl = 0; sl < PK_RING; ++sl) {
+            smk.ringA[sl * CTA_THREADS + threadIdx.x] = PkRingA{0u, 0u, 0x80008000u, 0u};
+            smk.ringB[sl * CTA_THREADS + threadIdx.x] = PkRingB{0x80008000u, (unsigned) PK_ZC};
+        }
+        smk.t4 = t4;
+        smk.pen = ppen;
+    } else {
+        sm.ring = reinterpret_cast<RingEntry*>(smem_raw);
+        int2* spen = reinterpret_cast<int2*>(smem_raw + sizeof(RingEntry) * RING * CTA_THREADS);
+        for (int i = threadIdx.x; i <= P.pen_cap; i += blockDim.x) spen[i] = gpen[i];
+        sm.pen = spen;
+        sm.mtx = sP.mtxT;
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -656,6 +901,13 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
             if (lane == 0) { DevResult r; r.score = 0; r.status = 4; r.n_skl = 0; r.pad = 0; results[ti] = r; }
             continue;
         }
+        {
+            // who runs this problem: the packed kernel if the host marked it eligible, else (or if
+            // the packed kernel gave it back) the 32-bit kernel
+            const bool fast = P.pk_ok && apool[t.a_off + (t.a_right - t.a_left)] == 1;
+            if (PK ? !fast : (fast && results[ti].status != ST_NEED_EXACT)) continue;
+        }
+        PkMonitor mon{-32768, 0, 0};
         const unsigned char* aseq = apool + t.a_off;
         const ColInfo* cols = cpool + t.col_off;
         const int width = t.up - t.lw + 3;
@@ -704,8 +956,11 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
             int nstr = (t.a_right - ml0 + NELEM - 1) / NELEM;
             if (mc >= ml0 && mc < ml0 + nstr * NELEM && ((mc - ml0) % NELEM) == 0)
                 nstr = (mc - ml0) / NELEM + 1;
-            run_pass<TRACE, LOCAL, SPJ, DAGP>(P, sm, t, aseq, cols, band, band2, trace, ml0, nstr,
-                                              LocalL && !accscr, LocalR, accscr, wmax);
+            if constexpr (PK)
+                run_pass_pk<TRACE, SPJ>(P, smk, t, aseq, cols, band, trace, ml0, nstr, wmax, mon);
+            else
+                run_pass<TRACE, LOCAL, SPJ, DAGP>(P, sm, t, aseq, cols, band, band2, trace, ml0, nstr,
+                                                  LocalL && !accscr, LocalR, accscr, wmax);
             const int last_ml = ml0 + (nstr - 1) * NELEM;
             if (last_ml == mc) {
                 // src/fwd2s1_wip_simd.h:454-465
@@ -771,11 +1026,25 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
         }
 
         int status = 0, n_skl = 0;
-        if (TRACE) {
+        bool need_exact = false;
+        if (PK) {
+            // high-side monitor (gspaln_packed.cuh): no add of the whole problem can have wrapped
+            // unless the largest H plus the largest positive addend passes 32767
+            int hm = mon.hmax, s3m = mon.s3max, s5m = mon.s5max;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                hm = max(hm, __shfl_xor_sync(0xffffffffu, hm, o));
+                s3m = max(s3m, __shfl_xor_sync(0xffffffffu, s3m, o));
+                s5m = max(s5m, __shfl_xor_sync(0xffffffffu, s5m, o));
+            }
+            need_exact = hm + P.pk_pvmax > 32767 || hm + s5m + s3m > 32767;
+            if (need_exact) status = ST_NEED_EXACT;
+        }
+        if (TRACE && !need_exact) {
             __threadfence_block();
             __syncwarp();
             if (lane == 0)
-                n_skl = walk_trace(t, trace, wmax.mr, wmax.nr, sklpool + t.skl_off, t.skl_cap, &status);
+                n_skl = walk_trace<PK>(t, trace, wmax.mr, wmax.nr, sklpool + t.skl_off, t.skl_cap, &status);
             if (lane == 0 && n_skl > t.skl_cap && status == 0) status = 1;
         }
         if (lane == 0) {

@@ -513,3 +513,81 @@ def test_coalescing_queue_from_many_threads():
         assert g is not None and g.status == w.status and g.score == w.score, i
         assert np.array_equal(g.skl, w.skl), i
     eng.close()
+
+
+def test_packed_kernel_hands_back_and_skips_what_it_cannot_run(oracle):
+    """The packed int16x2 kernel (gspaln_packed.cuh) runs the eligible problems and the 32-bit
+    kernel the rest; both must give the oracle's answer:
+      * long near-perfect matches with large positive splice signals push max H + addends past
+        32767 -> the monitor hands the problem back (status 6 never reaches the caller),
+      * IUPAC codes other than A, C, G, T, N and signals beyond +-8192 are not eligible at all,
+      * values at the bottom of the int16 range (global mode, unrelated sequences) stay exact on
+        the packed path itself."""
+    from spaln_b200 import workload
+    prm, _ = golden_io.load("dna_A2_global")
+    rng = np.random.default_rng(4242)
+    probs = []
+    # (1) monitor: 1450-row queries, no mutations, signals up to +3000
+    for _ in range(3):
+        g, q, _t = workload.plant_gene(rng, qlen_range=(1440, 1460), flank=(30, 60), sub=0.0, indel=0.0)
+        a, b = workload.encode_dna(q), workload.encode_dna(g)
+        s5, s3 = workload.synthetic_signals(b, rng)
+        s5 = (s5.astype(np.int32) + rng.integers(0, 3000, size=len(s5))).astype(np.int16)
+        s3 = (s3.astype(np.int32) + rng.integers(0, 3000, size=len(s3))).astype(np.int16)
+        probs.append((a, b, s5, s3, (1, 1, 1, 1)))
+    # (2) not eligible: ambiguity codes / huge signals
+    for k in range(4):
+        g, q, _t = workload.plant_gene(rng, qlen_range=(100, 400), flank=(30, 200))
+        a, b = workload.encode_dna(q), workload.encode_dna(g)
+        s5, s3 = workload.synthetic_signals(b, rng)
+        if k % 2 == 0:
+            b = b.copy(); b[rng.integers(0, len(b), size=5)] = rng.choice([1, 4, 6, 7, 8, 10, 12, 15], size=5)
+            a = a.copy(); a[rng.integers(0, len(a), size=2)] = 16
+        else:
+            s3 = s3.copy(); s3[rng.integers(0, len(s3), size=4)] = -20000
+            s5 = s5.copy(); s5[rng.integers(0, len(s5), size=4)] = 12000
+        probs.append((a, b, s5, s3, (1, 1, 1, 1)))
+    # (3) deep negative values: unrelated sequences, no free end gaps, N runs
+    for _ in range(6):
+        a = workload.encode_dna(workload.random_dna(rng, int(rng.integers(300, 900))).tobytes().decode())
+        b = workload.encode_dna(workload.random_dna(rng, int(rng.integers(400, 1200))).tobytes().decode())
+        b = b.copy(); p = int(rng.integers(0, len(b) - 40)); b[p:p + 30] = 16
+        s5, s3 = workload.synthetic_signals(b, rng)
+        probs.append((a, b, s5, s3, (0, 0, 0, 0)))
+    pbs = []
+    for a, b, s5, s3, f in probs:
+        lw, up = workload.stripe(0, len(a), 0, len(b), int(prm["sh"]))
+        pbs.append({"a": np.concatenate([[0], a, [0]]).astype(np.uint8), "b": np.concatenate([[0], b, [0]]).astype(np.uint8),
+                    "sig5": s5, "sig3": s3, "int53": workload.synthetic_int53(b), "a_left": 0, "a_right": len(a),
+                    "b_left": 0, "b_right": len(b), "a_exgl": f[0], "a_exgr": f[1], "b_exgl": f[2], "b_exgr": f[3],
+                    "lw": lw, "up": up})
+    eng = _engine(prm)
+    res = eng.forwardS1_wip(_problems(pbs))
+    sco = eng.scoreonlyS1_wip(_problems(pbs))
+    for i, (pb, r, s) in enumerate(zip(pbs, res, sco)):
+        o = oracle.forward_wip(prm, pb, cap=1 << 16)
+        assert r.status == 0, (i, r.status)
+        assert r.score == o["score"], (i, r.score, o["score"])
+        assert np.array_equal(r.skl, o["skl"]), i
+        assert s.score == oracle.scoreonly_wip(prm, pb)["score"], i
+    eng.close()
+
+
+def test_packed_and_32bit_kernels_agree(monkeypatch):
+    """same batch with the packed kernels disabled (GSPALN_NO_PACKED=1): identical results"""
+    prm, _ = golden_io.load("dna_A2_global")
+    rng = np.random.default_rng(99)
+    probs = _synthetic(prm, rng, 40, (40, 900), (30, 600)) + _synthetic(prm, rng, 4, (1600, 2600), (100, 800))
+    eng = _engine(prm)
+    fast = eng.forwardS1_wip(_problems(probs))
+    fast_s = eng.scoreonlyS1_wip(_problems(probs))
+    eng.close()
+    monkeypatch.setenv("GSPALN_NO_PACKED", "1")
+    eng = _engine(prm)
+    slow = eng.forwardS1_wip(_problems(probs))
+    slow_s = eng.scoreonlyS1_wip(_problems(probs))
+    eng.close()
+    for f, s, fs, ss in zip(fast, slow, fast_s, slow_s):
+        assert f.status == 0 and s.status == 0
+        assert f.score == s.score and np.array_equal(f.skl, s.skl)
+        assert fs.score == ss.score
