@@ -844,7 +844,7 @@ def main():
         t_b = time.perf_counter()
         part = shard.lpt_partition(cells_all, world)[rank]
         t_c = time.perf_counter()
-        packed = eng.pack(problems)                 # task descriptors marshalled inside the call
+        packed = eng.pack_global(G, part)           # task descriptors marshalled inside the call
         eng.submit_packed(packed)
         t_d = time.perf_counter()
         n_skl = np.minimum(packed.res["n_skl"][:packed.n], np.diff(packed.off)).astype(np.int64)

@@ -82,6 +82,7 @@ struct gspaln_ctx {
     int grid_trace = 0, grid_score = 0;
     // packed int16x2 kernels (gspaln_packed.cuh)
     bool pk_ok = false;
+    int pk_np = 4;                  // packed registers per thread (GSPALN_PK_NP = 4 | 8)
     size_t smem_pk = 0;
     int grid_trace_pk = 0, grid_score_pk = 0;
 };
@@ -123,14 +124,17 @@ const void* kernel_ptr(bool trace, bool local, bool spj, bool dagp = false)
     return reinterpret_cast<const void*>(kernel_fn(trace, local, spj, dagp));
 }
 
-// the packed int16x2 kernels: single affine, global / semi-global
-KernelFn pk_kernel_fn(bool trace, bool spj)
+// the packed int16x2 kernels: single affine, global / semi-global; np = packed registers per
+// thread (4: two threads per strip, 16 strip slots per warp; 8: one thread per strip, 32 slots)
+KernelFn pk_kernel_fn(bool trace, bool spj, int np)
 {
-    static const KernelFn tab[4] = {
-        dp_wip_kernel<false, false, false, false, true>, dp_wip_kernel<false, false, true, false, true>,
-        dp_wip_kernel<true, false, false, false, true>, dp_wip_kernel<true, false, true, false, true>,
+    static const KernelFn tab[8] = {
+        dp_wip_kernel<false, false, false, false, 4>, dp_wip_kernel<false, false, true, false, 4>,
+        dp_wip_kernel<true, false, false, false, 4>, dp_wip_kernel<true, false, true, false, 4>,
+        dp_wip_kernel<false, false, false, false, 8>, dp_wip_kernel<false, false, true, false, 8>,
+        dp_wip_kernel<true, false, false, false, 8>, dp_wip_kernel<true, false, true, false, 8>,
     };
-    return tab[(trace ? 2 : 0) | (spj ? 1 : 0)];
+    return tab[(np == 8 ? 4 : 0) | (trace ? 2 : 0) | (spj ? 1 : 0)];
 }
 
 using UdhKernelFn = void (*)(const DevParams*, const int2*, const DevTask*, const int*, int, int*,
@@ -294,10 +298,11 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
         ctx->grid_udh = std::max(1, occ) * ctx->sm_count;
     }
     if (ctx->pk_ok) {
-        ctx->smem_pk = (sizeof(PkRingA) + sizeof(PkRingB)) * PK_RING * CTA_THREADS + sizeof(uint2) * PK_T4 +
+        if (const char* e = getenv("GSPALN_PK_NP")) ctx->pk_np = atoi(e) == 8 ? 8 : 4;
+        ctx->smem_pk = (sizeof(PkRingA) + sizeof(PkRingB)) * 2 * ctx->pk_np * CTA_THREADS + sizeof(uint2) * PK_T4 +
                        sizeof(PkPen) * (size_t) (cap + 1);
-        const void* pt = reinterpret_cast<const void*>(pk_kernel_fn(true, P.spj));
-        const void* ps = reinterpret_cast<const void*>(pk_kernel_fn(false, P.spj));
+        const void* pt = reinterpret_cast<const void*>(pk_kernel_fn(true, P.spj, ctx->pk_np));
+        const void* ps = reinterpret_cast<const void*>(pk_kernel_fn(false, P.spj, ctx->pk_np));
         cudaFuncSetAttribute(pt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_pk);
         cudaFuncSetAttribute(ps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_pk);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt, CTA_THREADS, ctx->smem_pk);
@@ -581,14 +586,14 @@ static int launch_range(gspaln_ctx* ctx, int lo, int hi, int slot, int& launches
     // packed int16x2 kernels first (problems the host marked eligible); the 32-bit kernels behind
     // them take the rest and whatever the packed ones hand back (status 6)
     if (ctx->pk_ok && ctx->n_trace) {
-        pk_kernel_fn(true, spj)<<<std::min(ctx->grid_run_trace, ctx->grid_trace_pk), CTA_THREADS, ctx->smem_pk, ctx->stream>>>(
+        pk_kernel_fn(true, spj, ctx->pk_np)<<<std::min(ctx->grid_run_trace, ctx->grid_trace_pk), CTA_THREADS, ctx->smem_pk, ctx->stream>>>(
             ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 4,
             ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
             ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p, ready);
         ++launches;
     }
     if (ctx->pk_ok && ctx->n_score) {
-        pk_kernel_fn(false, spj)<<<std::min(ctx->grid_run_score, ctx->grid_score_pk), CTA_THREADS, ctx->smem_pk, ctx->stream>>>(
+        pk_kernel_fn(false, spj, ctx->pk_np)<<<std::min(ctx->grid_run_score, ctx->grid_score_pk), CTA_THREADS, ctx->smem_pk, ctx->stream>>>(
             ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 5,
             ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
             ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p, ready);

@@ -539,8 +539,8 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
 
 // shared-memory carve-up of the packed kernel
 struct SmemPk {
-    PkRingA* ringA;             // [PK_RING][CTA_THREADS]
-    PkRingB* ringB;             // [PK_RING][CTA_THREADS]
+    PkRingA* ringA;             // [2 NP][CTA_THREADS]
+    PkRingB* ringB;             // [2 NP][CTA_THREADS]
     const uint2* t4;            // [PK_T4] pair table
     const PkPen* pen;           // [pen_cap + 1]
 };
@@ -554,7 +554,7 @@ struct PkMonitor { int hmax, s3max, s5max; };
 // needs only the last 4 column pairs; the two gap states travel minus gn (converted where they
 // meet the band rows); no local-mode bookkeeping (local problems run on the 32-bit kernel).
 // ---------------------------------------------------------------------------
-template <bool TRACE, bool SPJ>
+template <int NP, bool TRACE, bool SPJ>
 __device__ void run_pass_pk(const DevParams& P, const SmemPk& sm, const DevTask& t,
                             const unsigned char* __restrict__ aseq, const ColInfo* __restrict__ cols,
                             unsigned* band, unsigned char* trace, int ml0, int nstr, WarpMax& wmax,
@@ -562,12 +562,15 @@ __device__ void run_pass_pk(const DevParams& P, const SmemPk& sm, const DevTask&
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    constexpr int NR = 2 * NP;                  // rows per thread: 8 (two threads per strip) or 16 (one)
+    constexpr int TPS = NELEM / NR;
+    constexpr int SPP = 32 / TPS;               // strip slots of the warp
+    static_assert(NP == 4 || NP == 8, "4 or 8 packed registers per thread");
     const int slot = lane / TPS;
     const int sub = lane % TPS;
     const int row0 = sub * NR;
     const int pred_lane = ((slot + SPP - 1) % SPP) * TPS;
     const int width = t.up - t.lw + 3;
-    static_assert(NR == 8 && TPS == 2, "the packed kernel is written for 8 rows per thread");
 
     int sidx = slot;
     StripGeom g = strip_geom<TRACE>(t, ml0 + NELEM * min(sidx, nstr - 1));
@@ -580,9 +583,9 @@ __device__ void run_pass_pk(const DevParams& P, const SmemPk& sm, const DevTask&
     K.gn = pk_dup(P.gn); K.ge = pk_dup(P.ge); K.cgn = pk_dup(-32768 - P.gn); K.nev = pk_dup(NEV);
     K.one = 0x00010001u; K.eight = 0x00080008u; K.cap8 = pk_dup(8 * P.pen_cap);
     const unsigned nev2 = K.nev, hg0 = pk_max(K.nev, K.cgn), gt0 = pk_dup(NEV - P.gn);
-    unsigned HA[4], HB[4], HG[4], Ft[4], Et[4], V2[4], HL[4], arow4[4];
+    unsigned HA[NP], HB[NP], HG[NP], Ft[NP], Et[NP], V2[NP], HL[NP], arow4[NP];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NP; ++j) {
         HA[j] = nev2; HB[j] = nev2; HG[j] = hg0; Ft[j] = gt0; Et[j] = gt0; V2[j] = nev2; HL[j] = 0u;
         arow4[j] = (unsigned) ((PK_ZC * PK_NC + PK_ZC) * 8);
     }
@@ -617,15 +620,20 @@ __device__ void run_pass_pk(const DevParams& P, const SmemPk& sm, const DevTask&
                 s3max = max(s3max, s3); s5max = max(s5max, s5);
             }
         }
-        pk_ring_push(ringA, ringB, CTA_THREADS, c, cls, s3, s5);
+        pk_ring_push<NP>(ringA, ringB, CTA_THREADS, c, cls, s3, s5);
     };
 
     unsigned pf_band = 0;
     uint2 nxt_col = make_uint2(0u, 0xffffffffu);
+    unsigned char* tr = trace;          // trace cell of the current step (TRACE)
+    bool writer = false;                // this thread holds the strip's bottom row
+    int kbot = 0;
     const int max_iter = nstr * (width + 3 * NELEM + 8) + 64;
     for (int i = -1; ; ++i) {
         if (i > max_iter) { wmax.err = 1; break; }
-        {
+        // the schedule records only matter while some slot waits for the strip above it (or skips an
+        // empty strip): one vote per iteration instead of four shuffles
+        if (__any_sync(FULL, state == 0 || state == 3)) {
             const int p_rec_si = __shfl_sync(FULL, rec_si, pred_lane);
             const int p_rec_d = __shfl_sync(FULL, rec_d, pred_lane);
             const int p_old_si = __shfl_sync(FULL, old_si, pred_lane);
@@ -650,15 +658,18 @@ __device__ void run_pass_pk(const DevParams& P, const SmemPk& sm, const DevTask&
         const bool run = state == 1;
         const int j = i - off;
         const int j8 = g.j9 - 1;
-        // the upper thread's row 7 (H of the previous step, vertical state) for the lower thread
-        const unsigned sh_h = __shfl_up_sync(FULL, (i & 1) ? HA[3] : HB[3], 1);
-        const unsigned sh_f = __shfl_up_sync(FULL, Ft[3], 1);
+        // the upper thread's last row (H of the previous step, vertical state) for the lower thread
+        unsigned sh_h = 0, sh_f = 0;
+        if (TPS > 1) {
+            sh_h = __shfl_up_sync(FULL, (i & 1) ? HA[NP - 1] : HB[NP - 1], 1);
+            sh_f = __shfl_up_sync(FULL, Ft[NP - 1], 1);
+        }
         const int band_bias = g.ml + t.lw - 1;
         if (run && j == -1) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < NP; ++q) {
                 HA[q] = nev2; HB[q] = nev2; HG[q] = hg0; Ft[q] = gt0; Et[q] = gt0; V2[q] = nev2; HL[q] = 0u;
-                const int r_lo = row0 + q, r_hi = row0 + q + 4;
+                const int r_lo = row0 + q, r_hi = row0 + q + NP;
                 const int a_lo = r_lo < g.j9 ? cls_of((int) aseq[(g.ml - t.a_left) + r_lo]) : PK_ZC;
                 const int a_hi = r_hi < g.j9 ? cls_of((int) aseq[(g.ml - t.a_left) + r_hi]) : PK_ZC;
                 arow4[q] = (unsigned) ((a_lo * PK_NC + a_hi) * 8);
@@ -668,10 +679,14 @@ __device__ void run_pass_pk(const DevParams& P, const SmemPk& sm, const DevTask&
                 if (nsteps > 0) pf_band = __ldcg(band + (g.n_start - band_bias));
                 prev_in = __ldcg(band + (g.n_start - 1 - band_bias));
             }
+            if (TRACE)
+                tr = trace + ((long long) (sidx + (ml0 - t.a_left) / NELEM) * (width + TRACE_PAD)) * NELEM + row0;
+            writer = g.j9 - 1 >= row0 && g.j9 - 1 < row0 + NR;
+            kbot = g.j9 - 1 - row0;
             const int cs = g.n_start - row0;            // first column of this thread's first row
             nxt_col = col_fetch(cs);
 #pragma unroll 1
-            for (int d = 7; d >= 1; --d) col_push(col_fetch(cs - d), cs - d, false);
+            for (int d = 2 * NP - 1; d >= 1; --d) col_push(col_fetch(cs - d), cs - d, false);
         } else if (run && j >= 0) {
             const int n = g.n_start + j;
             const int cn = n - row0;
@@ -679,42 +694,48 @@ __device__ void run_pass_pk(const DevParams& P, const SmemPk& sm, const DevTask&
             col_push(nxt_col, cn, cn >= g.n_start);
             if (sub == 0 && j + 1 < nsteps) pf_band = __ldcg(band + (n + 1 - band_bias));
             if (j + 1 < nsteps) nxt_col = col_fetch(cn + 1);
-            const int rslot = (cn & 3) + 4;
+            const int rslot = (cn & (NP - 1)) + NP;
             const char* ra_hi = reinterpret_cast<const char*>(ringA + rslot * CTA_THREADS);
             const char* rb_hi = reinterpret_cast<const char*>(ringB + rslot * CTA_THREADS);
             const unsigned in = sub ? sh_h : cur_band;
             const unsigned in_f = sub ? sh_f : cur_band;
-            unsigned tw[2];
+            unsigned tw[NP / 2];
             if (i & 1) {
-                const unsigned uh0 = pk_perm(in, HA[3], sel);
-                const unsigned uft0 = pk_add(pk_perm(in_f, Ft[3], 0x5432u), fconv);
-                const unsigned dg0 = pk_perm(prev_in, HB[3], sel);
-                strip_step_pk<TRACE, SPJ>(HB, HA, HG, Ft, Et, V2, HL, arow4, ra_hi, rb_hi,
+                const unsigned uh0 = pk_perm(in, HA[NP - 1], sel);
+                const unsigned uft0 = pk_add(pk_perm(in_f, Ft[NP - 1], 0x5432u), fconv);
+                const unsigned dg0 = pk_perm(prev_in, HB[NP - 1], sel);
+                strip_step_pk<NP, TRACE, SPJ>(HB, HA, HG, Ft, Et, V2, HL, arow4, ra_hi, rb_hi,
                                           CTA_THREADS * (int) sizeof(PkRingA), CTA_THREADS * (int) sizeof(PkRingB),
                                           t4_bytes, pen_bytes, uh0, uft0, dg0, K, tw, hmax);
             } else {
-                const unsigned uh0 = pk_perm(in, HB[3], sel);
-                const unsigned uft0 = pk_add(pk_perm(in_f, Ft[3], 0x5432u), fconv);
-                const unsigned dg0 = pk_perm(prev_in, HA[3], sel);
-                strip_step_pk<TRACE, SPJ>(HA, HB, HG, Ft, Et, V2, HL, arow4, ra_hi, rb_hi,
+                const unsigned uh0 = pk_perm(in, HB[NP - 1], sel);
+                const unsigned uft0 = pk_add(pk_perm(in_f, Ft[NP - 1], 0x5432u), fconv);
+                const unsigned dg0 = pk_perm(prev_in, HA[NP - 1], sel);
+                strip_step_pk<NP, TRACE, SPJ>(HA, HB, HG, Ft, Et, V2, HL, arow4, ra_hi, rb_hi,
                                           CTA_THREADS * (int) sizeof(PkRingA), CTA_THREADS * (int) sizeof(PkRingB),
                                           t4_bytes, pen_bytes, uh0, uft0, dg0, K, tw, hmax);
             }
             prev_in = in;
             if (TRACE) {
-                unsigned char* tr = trace + ((long long) (sidx + (ml0 - t.a_left) / NELEM) * (width + TRACE_PAD) + j) * NELEM + row0;
-                *reinterpret_cast<uint2*>(tr) = make_uint2(tw[0], tw[1]);
+                if (NP == 8)
+                    *reinterpret_cast<uint4*>(tr) = make_uint4(tw[0], tw[1], tw[NP / 2 - 2], tw[NP / 2 - 1]);
+                else
+                    *reinterpret_cast<uint2*>(tr) = make_uint2(tw[0], tw[1]);
+                tr += NELEM;
             }
             // bottom row of the strip -> band buffer (src/fwd2s1_wip_simd.h:438-442)
-            if (j8 >= row0 && j8 < row0 + NR) {
-                const int kbot = j8 - row0, kq = kbot & 3;
-                // (explicit selects: an indexed read would push the register arrays to local memory)
-                const unsigned h01 = (i & 1) ? (kq == 0 ? HB[0] : HB[1]) : (kq == 0 ? HA[0] : HA[1]);
-                const unsigned h23 = (i & 1) ? (kq == 2 ? HB[2] : HB[3]) : (kq == 2 ? HA[2] : HA[3]);
-                const unsigned hw = kq < 2 ? h01 : h23;
-                const unsigned fw = kq < 2 ? (kq == 0 ? Ft[0] : Ft[1]) : (kq == 2 ? Ft[2] : Ft[3]);
-                const int out_h = kbot < 4 ? lo16(hw) : hi16(hw);
-                const int out_f = (int) (short) ((kbot < 4 ? lo16(fw) : hi16(fw)) + P.gn);
+            if (writer) {
+                const int kq = kbot & (NP - 1);
+                // (selects on values: an indexed read would push the register arrays to local memory)
+                unsigned hw = (i & 1) ? HB[0] : HA[0], fw = Ft[0];
+#pragma unroll
+                for (int q = 1; q < NP; ++q) {
+                    const unsigned hq = (i & 1) ? HB[q] : HA[q];
+                    hw = kq == q ? hq : hw;
+                    fw = kq == q ? Ft[q] : fw;
+                }
+                const int out_h = kbot < NP ? lo16(hw) : hi16(hw);
+                const int out_f = (int) (short) ((kbot < NP ? lo16(fw) : hi16(fw)) + P.gn);
                 const int cb = n - j8;
                 const int r0 = cb - (g.ml + g.j9);
                 if (cb > t.b_left && r0 >= t.lw && r0 <= t.up)
@@ -740,7 +761,7 @@ __device__ void run_pass_pk(const DevParams& P, const SmemPk& sm, const DevTask&
 // ---------------------------------------------------------------------------
 // trace-code lookup for the walk (cells never evaluated read as STOP = 0)
 // ---------------------------------------------------------------------------
-template <bool PK>
+template <int PK>
 struct TraceView {
     const DevTask* t;
     const unsigned char* trace;
@@ -755,14 +776,16 @@ struct TraceView {
         const int j = cur_n + T.b_left + k - g.n_start;     // step at which row k sat on this column
         if (j < 0 || j > g.n_last - g.n_start) return 0u;
         const unsigned char* cell = trace + ((long long) s * (width + TRACE_PAD) + j) * NELEM;
-        if (PK)     // raw decision bits, rows permuted inside each thread's 8 bytes
-            return pk_trace_code(cell[(k & 8) + pk_trace_byte(k & 7)]);
+        if constexpr (PK != 0) {    // raw decision bits, rows permuted inside each thread's 2 PK bytes
+            constexpr int NRP = 2 * PK;
+            return pk_trace_code(cell[(k / NRP) * NRP + pk_trace_byte<PK>(k % NRP)]);
+        }
         return cell[k];
     }
 };
 
 // Anti_rhomb_coord<CHAR>::traceback + go_back (src/rhomb_coord.h:142-235), step = 1
-template <bool PK>
+template <int PK>
 static __device__ int walk_trace(const DevTask& t, const unsigned char* trace, int m_abs, int n_abs,
                           int2* skl, int cap, int* status)
 {
@@ -818,14 +841,14 @@ static __device__ int walk_trace(const DevTask& t, const unsigned char* trace, i
 // ---------------------------------------------------------------------------
 // persistent kernel: each warp pulls problems from a global ticket counter
 // ---------------------------------------------------------------------------
-// PK = true: the packed int16x2 kernel.  It takes the problems marked eligible by the host (residue
+// PK = 4 / 8: the packed int16x2 kernel with 4 / 8 registers (8 / 16 rows) per thread.  It takes the problems marked eligible by the host (residue
 // classes A, C, G, T, N only; bounded signals -- the byte behind the query codes) and reports
 // status 6 for a problem whose values came too close to +32767 (see gspaln_packed.cuh); the 32-bit
-// kernel (PK = false), launched behind it on the same stream, runs everything else plus those.
+// kernel (PK = 0), launched behind it on the same stream, runs everything else plus those.
 constexpr int ST_NEED_EXACT = 6;
 
-template <bool TRACE, bool LOCAL, bool SPJ, bool DAGP, bool PK = false>
-__global__ void __launch_bounds__(CTA_THREADS, 3)
+template <bool TRACE, bool LOCAL, bool SPJ, bool DAGP, int PK = 0>
+__global__ void __launch_bounds__(CTA_THREADS, PK == 8 ? 2 : 3)
 dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
               const DevTask* __restrict__ tasks,
               const int* __restrict__ order, int ntasks, int* ticket,
@@ -846,6 +869,7 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
     SmemPk smk;
     if (PK) {
         smk.ringA = reinterpret_cast<PkRingA*>(smem_raw);
+        constexpr int PK_RING = 2 * (PK ? PK : 4);
         smk.ringB = reinterpret_cast<PkRingB*>(smem_raw + sizeof(PkRingA) * PK_RING * CTA_THREADS);
         uint2* t4 = reinterpret_cast<uint2*>(smem_raw + (sizeof(PkRingA) + sizeof(PkRingB)) * PK_RING * CTA_THREADS);
         PkPen* ppen = reinterpret_cast<PkPen*>(t4 + PK_T4);
@@ -905,7 +929,7 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
             // who runs this problem: the packed kernel if the host marked it eligible, else (or if
             // the packed kernel gave it back) the 32-bit kernel
             const bool fast = P.pk_ok && apool[t.a_off + (t.a_right - t.a_left)] == 1;
-            if (PK ? !fast : (fast && results[ti].status != ST_NEED_EXACT)) continue;
+            if (PK != 0 ? !fast : (fast && results[ti].status != ST_NEED_EXACT)) continue;
         }
         PkMonitor mon{-32768, 0, 0};
         const unsigned char* aseq = apool + t.a_off;
@@ -956,8 +980,8 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
             int nstr = (t.a_right - ml0 + NELEM - 1) / NELEM;
             if (mc >= ml0 && mc < ml0 + nstr * NELEM && ((mc - ml0) % NELEM) == 0)
                 nstr = (mc - ml0) / NELEM + 1;
-            if constexpr (PK)
-                run_pass_pk<TRACE, SPJ>(P, smk, t, aseq, cols, band, trace, ml0, nstr, wmax, mon);
+            if constexpr (PK != 0)
+                run_pass_pk<PK, TRACE, SPJ>(P, smk, t, aseq, cols, band, trace, ml0, nstr, wmax, mon);
             else
                 run_pass<TRACE, LOCAL, SPJ, DAGP>(P, sm, t, aseq, cols, band, band2, trace, ml0, nstr,
                                                   LocalL && !accscr, LocalR, accscr, wmax);

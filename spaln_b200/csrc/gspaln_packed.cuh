@@ -103,9 +103,9 @@ constexpr int PK_NC = 6;                // residue classes of the pair table: A,
 constexpr int PK_T4 = PK_NC * PK_NC * PK_NC * PK_NC;    // entries of the pair table (8 B each)
 constexpr int PK_ZC = 5;                // the zero class
 constexpr int PK_SIGMAX = 8192;         // |signal| bound of the packed path (checked while packing)
-constexpr int PK_RING = 8;              // doubled 4-entry ring of per-column-pair inputs
 
-// one column pair as the rows consume it: column c in the low halves, column c - 4 in the high ones
+// one column pair as the rows consume it: column c in the low halves, column c - NP in the high ones
+// (NP = registers per thread: 4 -> 8 rows and two threads per strip, 8 -> 16 rows, one thread)
 struct __align__(16) PkRingA {
     unsigned t4;                        // byte offset of the pair-table block of (code[c], code[c - 4])
     unsigned s3;                        // acceptor signals
@@ -138,17 +138,17 @@ struct PkPen { unsigned pc, valid; };
 //   ra_hi / rb_hi: ring slot of column n (register j reads the slot j entries below)
 //   tw: 8 trace bytes (TRACE); hmax: running maximum of every H (monitor)
 // ---------------------------------------------------------------------------
-template <bool TRACE, bool SPJ>
-GSPALN_HD void strip_step_pk(unsigned (&HO)[4], const unsigned (&HN)[4], unsigned (&HG)[4], unsigned (&Ft)[4],
-                             unsigned (&Et)[4], unsigned (&V2)[4], unsigned (&HL)[4], const unsigned (&arow4)[4],
+template <int NP, bool TRACE, bool SPJ>
+GSPALN_HD void strip_step_pk(unsigned (&HO)[NP], const unsigned (&HN)[NP], unsigned (&HG)[NP], unsigned (&Ft)[NP],
+                             unsigned (&Et)[NP], unsigned (&V2)[NP], unsigned (&HL)[NP], const unsigned (&arow4)[NP],
                              const char* ra_hi, const char* rb_hi, int ra_stride, int rb_stride,
                              const char* t4_bytes, const char* pen_bytes, unsigned uh0, unsigned uft0,
-                             unsigned dg0, const PkConst& K, unsigned (&tw)[2], unsigned& hmax)
+                             unsigned dg0, const PkConst& K, unsigned (&tw)[NP / 2], unsigned& hmax)
 {
     const unsigned hgup0 = pk_max(uh0, K.cgn);
-    unsigned code[4];
+    unsigned code[NP];
 #pragma unroll
-    for (int j = 3; j >= 0; --j) {
+    for (int j = NP - 1; j >= 0; --j) {
         const PkRingA ra = *reinterpret_cast<const PkRingA*>(ra_hi - j * ra_stride);
         const unsigned left_hg = HG[j];
         const unsigned up_hg = j ? HG[j ? j - 1 : 0] : hgup0;
@@ -209,22 +209,23 @@ GSPALN_HD void strip_step_pk(unsigned (&HO)[4], const unsigned (&HN)[4], unsigne
             code[j] = c;
         }
     }
-    hmax = pk_max3(hmax, HO[0], HO[1]);
-    hmax = pk_max3(hmax, HO[2], HO[3]);
+#pragma unroll
+    for (int j = 0; j < NP; j += 2) hmax = pk_max3(hmax, HO[j], HO[j + 1]);
     if (TRACE) {
-        // bytes (row 0, row 1, row 4, row 5) and (row 2, row 3, row 6, row 7)
-        tw[0] = code[0] | (code[1] << 8);
-        tw[1] = code[2] | (code[3] << 8);
+        // word w: bytes (row 2w, row 2w + 1, row 2w + NP, row 2w + 1 + NP)
+#pragma unroll
+        for (int w = 0; w < NP / 2; ++w) tw[w] = code[2 * w] | (code[2 * w + 1] << 8);
     }
 }
 
 // Column c enters a thread's ring: the new pair entry takes column c in its low halves and column
-// c - 4 -- the low halves of the entry it replaces (slot c & 3) -- in its high halves.  The ring is
-// doubled (slots s and s + 4 hold the same entry) so that register j reads column c - j at a
-// constant offset below slot (c & 3) + 4.
+// c - NP -- the low halves of the entry it replaces (slot c mod NP) -- in its high halves.  The ring
+// is doubled (slots s and s + NP hold the same entry) so that register j reads column c - j at a
+// constant offset below slot (c mod NP) + NP.
+template <int NP>
 GSPALN_HD void pk_ring_push(PkRingA* ringA, PkRingB* ringB, int stride, int c, int cls, int s3, int s5)
 {
-    const int slot = c & 3;
+    const int slot = c & (NP - 1);
     const PkRingA oa = ringA[slot * stride];
     const PkRingB ob = ringB[slot * stride];
     PkRingA na;
@@ -237,8 +238,8 @@ GSPALN_HD void pk_ring_push(PkRingA* ringA, PkRingB* ringB, int stride, int c, i
     na.s5 = pk_perm((unsigned) s5, oa.s5, 0x5410);
     nb.c5 = pk_perm(c5, ob.c5, 0x5410);
     nb.code = (unsigned) cls;
-    ringA[slot * stride] = na; ringA[(slot + 4) * stride] = na;
-    ringB[slot * stride] = nb; ringB[(slot + 4) * stride] = nb;
+    ringA[slot * stride] = na; ringA[(slot + NP) * stride] = na;
+    ringB[slot * stride] = nb; ringB[(slot + NP) * stride] = nb;
 }
 
 // pair table: entry ((cc * NC + cc4) * NC + ac) * NC + ac4 = {scores of (cc, ac) | (cc4, ac4) << 16,
@@ -263,10 +264,11 @@ GSPALN_HD unsigned pk_trace_code(unsigned c)
     return pb | ((c & 8u) ? 0u : 16u) | ((c & 16u) ? 0u : 32u) | ((c & 32u) ? 128u : 0u);
 }
 
-// byte of strip row k (0..7 within the thread) inside the thread's 8 trace bytes
+// byte of row k (0 .. 2 NP - 1 within the thread) inside the thread's 2 NP trace bytes
+template <int NP>
 GSPALN_HD int pk_trace_byte(int k)
 {
-    const int j = k & 3, half = k >> 2;
+    const int j = k & (NP - 1), half = k / NP;
     return 4 * (j >> 1) + (j & 1) + 2 * half;
 }
 

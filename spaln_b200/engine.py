@@ -91,7 +91,12 @@ class PackedBatch:
 
     def __init__(self, arr, keep, n):
         self.arr, self.keep, self.n = arr, keep, n
-        caps = np.array([arr[i].skl_cap for i in range(n)], np.int64)
+        if isinstance(arr, np.ndarray):     # descriptors built with array operations (pack_global)
+            caps = arr["skl_cap"][:n].astype(np.int64)
+            self.arr = arr.ctypes.data_as(C.c_void_p)
+            self.keep = (arr, keep)
+        else:
+            caps = np.array([arr[i].skl_cap for i in range(n)], np.int64)
         self.off = np.concatenate([[0], np.cumsum(caps)])
         self.skl = np.zeros((max(int(self.off[-1]), 1), 2), np.int32)
         self.res = np.zeros(max(n, 1), _RESULT_DTYPE)
@@ -227,6 +232,37 @@ class Engine:
         res = batch.res.ctypes.data_as(C.POINTER(capi.GspalnResult))
         self._check(self.lib.gspaln_submit(self._h, batch.arr, batch.n, res), "gspaln_submit")
         return batch
+
+    def pack_global(self, g: dict, index, kind=capi.FORWARD_WIP, skl_cap=512, sh=100) -> PackedBatch:
+        """Task descriptors of the problems `index` of a flat query set (the layout of
+        workload.config2_global: concatenated query / genome codes and per-column tables plus a
+        length table), filled with array operations: what a caller that keeps its sequences in
+        flat buffers does per job.  Same band (stripe) and flags as workload.global_problems."""
+        index = np.asarray(index, np.int64)
+        n = len(index)
+        off = g.get("_off")
+        if off is None:
+            lens = g["lens"]
+            off = g["_off"] = (np.concatenate([[0], np.cumsum(lens[:, 0])]), np.concatenate([[0], np.cumsum(lens[:, 1])]),
+                               np.concatenate([[0], np.cumsum(lens[:, 1] + 2)]))
+        la, lb = g["lens"][index, 0], g["lens"][index, 1]
+        arr = np.zeros(max(n, 1), np.dtype(capi.GspalnTask))
+        t = arr[:n]
+        t["kind"] = kind
+        t["a"] = g["a"].ctypes.data + off[0][index]
+        t["b"] = g["b"].ctypes.data + off[1][index]
+        t["sig5"] = g["sig5"].ctypes.data + 2 * off[2][index]
+        t["sig3"] = g["sig3"].ctypes.data + 2 * off[2][index]
+        t["int53"] = g["int53"].ctypes.data + 2 * off[2][index]
+        t["a_right"], t["b_right"] = la, lb
+        for k in ("a_exgl", "a_exgr", "b_exgl", "b_exgr"):
+            t[k] = 1
+        up, lw = lb - la, np.zeros(n, np.int64)
+        up, lw = np.maximum(up, lw), np.minimum(up, lw)
+        t["up"] = np.minimum(up + sh, lb)
+        t["lw"] = np.maximum(lw - sh, -la)
+        t["skl_cap"] = skl_cap if kind in (capi.FORWARD_WIP, capi.FORWARD_NG) else 0
+        return PackedBatch(arr, g, n)
 
     def forwardS1_wip(self, problems):
         return self.submit(problems, capi.FORWARD_WIP)

@@ -5,7 +5,9 @@
 // the int16 range, extreme signals).  Also checks the monitor argument: whenever the two disagree,
 // max H + largest positive addend must have passed 32767.
 //
-//   nvcc -O2 -std=c++17 -o check_packed tests/tools/check_packed.cu && ./check_packed [runs] [seed]
+//   nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a [-DGSPALN_NR=16] -o check_packed \
+//        tests/tools/check_packed.cu && ./check_packed [runs] [seed]
+// (default: 8 rows per thread = 4 packed registers; -DGSPALN_NR=16: 16 rows = 8 registers)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -17,6 +19,8 @@
 using namespace gspaln;
 
 struct Params { int gn, ge, ipen, nquant, mil, quant[8], mean[8]; int mtx[6][6]; };
+
+constexpr int NP = NR / 2;      // registers per thread of the packed form (compile with -DGSPALN_NR=16 for NP = 8)
 
 template <bool TRACE, bool SPJ>
 static long run_case(std::mt19937& rng, const Params& PR, int regime, int steps, long& trips, long& cmp)
@@ -62,17 +66,17 @@ static long run_case(std::mt19937& rng, const Params& PR, int regime, int steps,
     }
     std::vector<RingEntry> ring(RING * CTA_THREADS);
     // ---- packed state
-    unsigned pHA[4], pHB[4], pHG[4], pFt[4], pEt[4], pV2[4], pHL[4], parow[4];
-    for (int j = 0; j < 4; ++j) {
+    unsigned pHA[NP], pHB[NP], pHG[NP], pFt[NP], pEt[NP], pV2[NP], pHL[NP], parow[NP];
+    for (int j = 0; j < NP; ++j) {
         pHA[j] = pHB[j] = pV2[j] = pk_dup(NEV);
         pHG[j] = pk_max(pk_dup(NEV), K.cgn);
         pFt[j] = pEt[j] = pk_dup(NEV - PR.gn);
         pHL[j] = 0;
-        parow[j] = (unsigned) ((acls[j] * PK_NC + acls[j + 4]) * 8);
+        parow[j] = (unsigned) ((acls[j] * PK_NC + acls[j + NP]) * 8);
     }
-    PkRingA ringA[PK_RING];
-    PkRingB ringB[PK_RING];
-    for (int s = 0; s < PK_RING; ++s) { ringA[s] = PkRingA{0, 0, pk_dup(-32768), 0}; ringB[s] = PkRingB{pk_dup(-32768), PK_ZC}; }
+    PkRingA ringA[2 * NP];
+    PkRingB ringB[2 * NP];
+    for (int s = 0; s < 2 * NP; ++s) { ringA[s] = PkRingA{0, 0, pk_dup(-32768), 0}; ringB[s] = PkRingB{pk_dup(-32768), PK_ZC}; }
 
     // level around which the incoming row lives
     const int base = regime == 0 ? U(-3000, 20000) : regime == 1 ? U(-32768, -31000) : U(24000, 32000);
@@ -84,7 +88,7 @@ static long run_case(std::mt19937& rng, const Params& PR, int regime, int steps,
         const int cls = U(0, 11) == 0 ? (U(0, 1) ? 4 : 5) : U(0, 3);
         RingEntry re; re.pad = 0; re.prof = idx_of[cls] * (MTX_LD * 4); re.s3 = 0; re.s5 = 0;
         ring[(c & 15) * CTA_THREADS] = re; ring[((c & 15) + 16) * CTA_THREADS] = re;
-        if (d <= 7) pk_ring_push(ringA, ringB, 1, c, cls, 0, 0);
+        if (d <= 2 * NP - 1) pk_ring_push<NP>(ringA, ringB, 1, c, cls, 0, 0);
     }
     int prev_uh = NEV;
     unsigned prev_in = pk_dup(NEV);
@@ -122,36 +126,36 @@ static long run_case(std::mt19937& rng, const Params& PR, int regime, int steps,
         prev_uh = up_h;
         for (int k = 0; k < NR; ++k) if (HOs[k] > hmax_true) hmax_true = HOs[k];
         // ---- packed
-        pk_ring_push(ringA, ringB, 1, n, cls, SPJ ? s3 : 0, SPJ ? s5i : 0);
-        unsigned (&HOp)[4] = (j & 1) ? pHB : pHA;
-        unsigned (&HNp)[4] = (j & 1) ? pHA : pHB;
+        pk_ring_push<NP>(ringA, ringB, 1, n, cls, SPJ ? s3 : 0, SPJ ? s5i : 0);
+        unsigned (&HOp)[NP] = (j & 1) ? pHB : pHA;
+        unsigned (&HNp)[NP] = (j & 1) ? pHA : pHB;
         const unsigned in_h = pk_mk(up_h, 0), in_f = pk_mk(up_f - PR.gn, 0);
-        const unsigned uh0 = pk_perm(in_h, HNp[3], 0x5410);
-        const unsigned uft0 = pk_perm(in_f, pFt[3], 0x5410);
-        const unsigned dg0 = pk_perm(prev_in, HOp[3], 0x5410);
+        const unsigned uh0 = pk_perm(in_h, HNp[NP - 1], 0x5410);
+        const unsigned uft0 = pk_perm(in_f, pFt[NP - 1], 0x5410);
+        const unsigned dg0 = pk_perm(prev_in, HOp[NP - 1], 0x5410);
         prev_in = in_h;
-        unsigned ptw[2] = {0, 0};
-        const int slot = (n & 3) + 4;
-        strip_step_pk<TRACE, SPJ>(HOp, HNp, pHG, pFt, pEt, pV2, pHL, parow,
+        unsigned ptw[NP / 2] = {0};
+        const int slot = (n & (NP - 1)) + NP;
+        strip_step_pk<NP, TRACE, SPJ>(HOp, HNp, pHG, pFt, pEt, pV2, pHL, parow,
                                   reinterpret_cast<const char*>(ringA + slot), reinterpret_cast<const char*>(ringB + slot),
                                   (int) sizeof(PkRingA), (int) sizeof(PkRingB), reinterpret_cast<const char*>(t4.data()),
                                   reinterpret_cast<const char*>(ppen.data()), uh0, uft0, dg0, K, ptw, hmax_pk);
         // ---- compare
         bool diff = false;
         for (int k = 0; k < NR; ++k) {
-            const int jj = k & 3;
-            auto half = [&](unsigned w) { return k < 4 ? pk_lo(w) : pk_hi(w); };
+            const int jj = k & (NP - 1);
+            auto half = [&](unsigned w) { return k < NP ? pk_lo(w) : pk_hi(w); };
             const int ph = half(HOp[jj]), pf = (short) (half(pFt[jj]) + PR.gn), pe = (short) (half(pEt[jj]) + PR.gn);
             if (ph != HOs[k] || pf != F[k] || pe != E[k]) diff = true;
             if (SPJ) {
                 const int hil_s = (j + 1 + NJ[k]) < cap ? (j + 1 + NJ[k]) : cap;    // counter as the NEXT step sees it
-                const int hil_p = (int) ((k < 4 ? pHL[jj] & 0xffffu : pHL[jj] >> 16) / 8);
+                const int hil_p = (int) ((k < NP ? pHL[jj] & 0xffffu : pHL[jj] >> 16) / 8);
                 if (half(pV2[jj]) != V2[k] || hil_s != hil_p) diff = true;
             }
             if (TRACE) {
                 const unsigned sc = (tw[k >> 2] >> (8 * (k & 3))) & 0xffu;
-                const unsigned word = ptw[pk_trace_byte(k) >> 2];
-                const unsigned pc = pk_trace_code((word >> (8 * (pk_trace_byte(k) & 3))) & 0xffu);
+                const unsigned word = ptw[pk_trace_byte<NP>(k) >> 2];
+                const unsigned pc = pk_trace_code((word >> (8 * (pk_trace_byte<NP>(k) & 3))) & 0xffu);
                 if (sc != pc) diff = true;
             }
         }
@@ -197,7 +201,7 @@ int main(int argc, char** argv)
         default: bad += run_case<false, false>(rng, P, regime, steps, trips, cmp); break;
         }
     }
-    printf("check_packed: %d runs, %ld steps compared, %ld runs ended by the high-side monitor, %ld mismatches\n",
-           runs, cmp, trips, bad);
+    printf("check_packed (NP = %d): %d runs, %ld steps compared, %ld runs ended by the high-side monitor, %ld mismatches\n",
+           NP, runs, cmp, trips, bad);
     return bad ? 1 : 0;
 }
