@@ -93,7 +93,7 @@ class PackedBatch:
         self.arr, self.keep, self.n = arr, keep, n
         if isinstance(arr, np.ndarray):     # descriptors built with array operations (pack_global)
             caps = arr["skl_cap"][:n].astype(np.int64)
-            self.arr = arr.ctypes.data_as(C.c_void_p)
+            self.arr = arr.ctypes.data_as(C.POINTER(capi.GspalnTask))
             self.keep = (arr, keep)
         else:
             caps = np.array([arr[i].skl_cap for i in range(n)], np.int64)
