@@ -82,9 +82,10 @@ struct gspaln_ctx {
     int grid_trace = 0, grid_score = 0;
     // packed int16x2 kernels (gspaln_packed.cuh)
     bool pk_ok = false;
-    int pk_np = 4;                  // packed registers per thread (GSPALN_PK_NP = 4 | 8)
-    size_t smem_pk = 0;
-    int grid_trace_pk = 0, grid_score_pk = 0;
+    int pk_np = 4;                  // packed registers per thread of the current batch (4 | 8)
+    int pk_np_forced = 0;           // GSPALN_PK_NP
+    size_t smem_pk[2] = {0, 0};     // [np == 8]
+    int grid_trace_pk[2] = {0, 0}, grid_score_pk[2] = {0, 0};
 };
 
 namespace {
@@ -298,17 +299,20 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
         ctx->grid_udh = std::max(1, occ) * ctx->sm_count;
     }
     if (ctx->pk_ok) {
-        if (const char* e = getenv("GSPALN_PK_NP")) ctx->pk_np = atoi(e) == 8 ? 8 : 4;
-        ctx->smem_pk = (sizeof(PkRingA) + sizeof(PkRingB)) * 2 * ctx->pk_np * CTA_THREADS + sizeof(uint2) * PK_T4 +
-                       sizeof(PkPen) * (size_t) (cap + 1);
-        const void* pt = reinterpret_cast<const void*>(pk_kernel_fn(true, P.spj, ctx->pk_np));
-        const void* ps = reinterpret_cast<const void*>(pk_kernel_fn(false, P.spj, ctx->pk_np));
-        cudaFuncSetAttribute(pt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_pk);
-        cudaFuncSetAttribute(ps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_pk);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt, CTA_THREADS, ctx->smem_pk);
-        ctx->grid_trace_pk = std::max(1, occ) * ctx->sm_count;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ps, CTA_THREADS, ctx->smem_pk);
-        ctx->grid_score_pk = std::max(1, occ) * ctx->sm_count;
+        if (const char* e = getenv("GSPALN_PK_NP")) ctx->pk_np_forced = atoi(e) == 8 ? 8 : 4;
+        for (int v = 0; v < 2; ++v) {
+            const int np = v ? 8 : 4;
+            ctx->smem_pk[v] = (sizeof(PkRingA) + sizeof(PkRingB)) * 2 * np * CTA_THREADS + sizeof(uint2) * PK_T4 +
+                              sizeof(PkPen) * (size_t) (cap + 1);
+            const void* pt = reinterpret_cast<const void*>(pk_kernel_fn(true, P.spj, np));
+            const void* ps = reinterpret_cast<const void*>(pk_kernel_fn(false, P.spj, np));
+            cudaFuncSetAttribute(pt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_pk[v]);
+            cudaFuncSetAttribute(ps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_pk[v]);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt, CTA_THREADS, ctx->smem_pk[v]);
+            ctx->grid_trace_pk[v] = std::max(1, occ) * ctx->sm_count;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ps, CTA_THREADS, ctx->smem_pk[v]);
+            ctx->grid_score_pk[v] = std::max(1, occ) * ctx->sm_count;
+        }
     }
     if (cudaGetLastError() != cudaSuccess) { gspaln_destroy(ctx); return GSPALN_ECUDA; }
     *out = ctx;
@@ -444,8 +448,19 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         auto ctas = [&](int full, int count) {
             return std::max(1, std::min(full, (count + WARPS_PER_CTA - 1) / WARPS_PER_CTA));
         };
-        int gt = n_trace ? ctas(std::max(ctx->grid_trace, ctx->grid_trace_pk), n_trace) : 0;
-        int gs = n_score ? ctas(std::max(ctx->grid_score, ctx->grid_score_pk), n_score) : 0;
+        // packed kernels: 8 registers per thread (one thread per strip, 32 strip slots per warp) pay
+        // off when the queries are long enough to keep 32 strips in flight, 4 otherwise
+        {
+            double rows_w = 0, w = 0;
+            for (int i = 0; i < n; ++i) {
+                rows_w += (double) ctx->cells[i] * (tasks[i].a_right - tasks[i].a_left);
+                w += (double) ctx->cells[i];
+            }
+            ctx->pk_np = ctx->pk_np_forced ? ctx->pk_np_forced : (w > 0 && rows_w / w >= 768 ? 8 : 4);
+        }
+        const int v8 = ctx->pk_np == 8;
+        int gt = n_trace ? ctas(std::max(ctx->grid_trace, ctx->grid_trace_pk[v8]), n_trace) : 0;
+        int gs = n_score ? ctas(std::max(ctx->grid_score, ctx->grid_score_pk[v8]), n_score) : 0;
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         free_b += ctx->d_trace.cap + ctx->d_band.cap * sizeof(unsigned);
@@ -586,14 +601,14 @@ static int launch_range(gspaln_ctx* ctx, int lo, int hi, int slot, int& launches
     // packed int16x2 kernels first (problems the host marked eligible); the 32-bit kernels behind
     // them take the rest and whatever the packed ones hand back (status 6)
     if (ctx->pk_ok && ctx->n_trace) {
-        pk_kernel_fn(true, spj, ctx->pk_np)<<<std::min(ctx->grid_run_trace, ctx->grid_trace_pk), CTA_THREADS, ctx->smem_pk, ctx->stream>>>(
+        pk_kernel_fn(true, spj, ctx->pk_np)<<<std::min(ctx->grid_run_trace, ctx->grid_trace_pk[ctx->pk_np == 8]), CTA_THREADS, ctx->smem_pk[ctx->pk_np == 8], ctx->stream>>>(
             ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 4,
             ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
             ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p, ready);
         ++launches;
     }
     if (ctx->pk_ok && ctx->n_score) {
-        pk_kernel_fn(false, spj, ctx->pk_np)<<<std::min(ctx->grid_run_score, ctx->grid_score_pk), CTA_THREADS, ctx->smem_pk, ctx->stream>>>(
+        pk_kernel_fn(false, spj, ctx->pk_np)<<<std::min(ctx->grid_run_score, ctx->grid_score_pk[ctx->pk_np == 8]), CTA_THREADS, ctx->smem_pk[ctx->pk_np == 8], ctx->stream>>>(
             ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 5,
             ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
             ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p, ready);

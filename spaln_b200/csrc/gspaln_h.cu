@@ -614,7 +614,7 @@ int gspaln_h_set_ng_tables(gspaln_h_ctx* ctx, const int16_t* sig53tab, const int
     return GSPALN_OK;
 }
 
-// the scalar kernel: one thread per problem, raw inputs copied per problem with a margin
+// the exact-ILD kernel (gspaln_hng.cuh): one warp per problem, raw inputs copied per problem with a margin
 static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gspaln_result* results)
 {
     if (!ctx->ng_ready) return fail(ctx, GSPALN_EINVAL, "GSPALN_FORWARD_NG needs gspaln_h_set_ng_tables");
@@ -638,7 +638,7 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
         const int width = t.up - t.lw + 7;
         const int64_t cells = gspaln_h_task_cells(&t);
         cells_total += cells;
-        d.rec_cap = (int) std::min<int64_t>(4 * cells + 4 * width + 64, INT_MAX / 4);
+        d.rec_cap = (int) std::min<int64_t>(4 * cells + 4 * width + 64 + 33 * HNG_CHUNK, INT_MAX / 4);
         // query residues a_left - 1 .. a_right, genome columns b_left - 4 .. b_right + 4 (zeros outside
         // the sequences, as the terminal residues of the reference's arrays)
         d.a_lo = t.a_left - 1; d.a_off = (long long) apool.size();
@@ -655,7 +655,7 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
         }
         d.skl_off = (long long) skl_elems; skl_elems += (size_t) d.skl_cap;
         d.work_off = (long long) work_bytes;
-        work_bytes += align_up((size_t) 3 * (width + 8) * sizeof(HRvpd) + (size_t) d.rec_cap * 12 + 16, 16);
+        work_bytes += align_up((size_t) 3 * (width + 8) * sizeof(HCell) + (size_t) d.rec_cap * 12 + 16, 16);
     }
     unsigned char *d_a = nullptr, *d_b = nullptr, *d_work = nullptr;
     short* d_sg = nullptr; unsigned short* d_i = nullptr; DevNgHTask* d_t = nullptr;
@@ -682,8 +682,8 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
     if (e == cudaSuccess) e = cudaMemset(d_tick, 0, sizeof(int));
     if (e != cudaSuccess) { freeall(); cudaGetLastError(); return fail(ctx, GSPALN_ENOMEM, "scalar kernel buffers", e); }
     cudaEventRecord(ctx->ev[2], ctx->stream);
-    const int grid = std::max(1, std::min((n + HNG_THREADS - 1) / HNG_THREADS, 8 * ctx->sm_count));
-    dp_hng_kernel<<<grid, HNG_THREADS, 0, ctx->stream>>>(ctx->d_ngprm.p, d_t, n, d_tick, d_a, d_b, d_sg, d_i,
+    const int grid = std::max(1, std::min((n + HNG_WARPS - 1) / HNG_WARPS, 4 * ctx->sm_count));
+    dp_hxild_kernel<<<grid, HNG_THREADS, 0, ctx->stream>>>(ctx->d_ngprm.p, d_t, n, d_tick, d_a, d_b, d_sg, d_i,
                                                          d_work, d_skl, d_res);
     cudaEventRecord(ctx->ev[3], ctx->stream);
     e = cudaStreamSynchronize(ctx->stream);

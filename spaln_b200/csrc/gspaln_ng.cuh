@@ -242,7 +242,6 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
             int psp = 0;
             NgList L;
             L.clear();
-            ColInfo col_next = ColInfo{0, 0, 0, {0, 0, 0}};
 
             for (int s = s_begin; s <= s_end; ++s) {
                 const int k = s - s_begin;
