@@ -80,6 +80,12 @@ struct gspaln_ctx {
     gspaln_timing tim;
     std::string err;
     int grid_trace = 0, grid_score = 0;
+    // narrower systolic chains for problems that cannot fill 16 strip slots: class c runs with
+    // NRT = 4 >> c strip rows per thread, i.e. 8 / 4 / 2 strip slots per warp (gspaln_kernels.cuh)
+    int n_trace_c[3] = {0, 0, 0}, n_score_c[3] = {0, 0, 0};
+    size_t band_slab_c[3] = {0, 0, 0}, trace_slab_c[3] = {0, 0, 0};
+    int grid_trace_c[3] = {0, 0, 0}, grid_score_c[3] = {0, 0, 0};
+    int grid_run_trace_c[3] = {0, 0, 0}, grid_run_score_c[3] = {0, 0, 0};
     // packed int16x2 kernels (gspaln_packed.cuh)
     bool pk_ok = false;
     int pk_np = 4;                  // packed registers per thread of the current batch (4 | 8)
@@ -123,6 +129,34 @@ KernelFn kernel_fn(bool trace, bool local, bool spj, bool dagp = false)
 const void* kernel_ptr(bool trace, bool local, bool spj, bool dagp = false)
 {
     return reinterpret_cast<const void*>(kernel_fn(trace, local, spj, dagp));
+}
+
+// 32-bit kernels with 4 / 2 / 1 strip rows per thread (8 / 4 / 2 strip slots per warp), single affine
+KernelFn thin_kernel_fn(bool trace, bool local, bool spj, int nrt)
+{
+    static const KernelFn tab[24] = {
+#define GSPALN_THIN(N) \
+        dp_wip_kernel<false, false, false, false, 0, N>, dp_wip_kernel<false, false, true, false, 0, N>, \
+        dp_wip_kernel<false, true, false, false, 0, N>, dp_wip_kernel<false, true, true, false, 0, N>,   \
+        dp_wip_kernel<true, false, false, false, 0, N>, dp_wip_kernel<true, false, true, false, 0, N>,   \
+        dp_wip_kernel<true, true, false, false, 0, N>, dp_wip_kernel<true, true, true, false, 0, N>
+        GSPALN_THIN(4), GSPALN_THIN(2), GSPALN_THIN(1)
+#undef GSPALN_THIN
+    };
+    const int c = nrt == 4 ? 0 : (nrt == 2 ? 1 : 2);
+    return tab[8 * c + ((trace ? 4 : 0) | (local ? 2 : 0) | (spj ? 1 : 0))];
+}
+
+// Chain width of a forward / score-only problem: a strip can start ~33 steps after the strip above
+// it and lives for width + 31 steps, so at most (width + 31) / 33 + 1 strips of a problem are in
+// flight, and never more than it has.  The class is the widest chain (2 x rows-per-thread strip
+// slots) the problem can keep full: all 32 lanes of its warp stay busy.
+int wip_class(int rows, int width, bool dagp)
+{
+    if (dagp || getenv("GSPALN_NO_THIN")) return 8;
+    const int nstr = (rows + NELEM - 1) / NELEM;
+    const int need = std::min(nstr, (width + 31) / 33 + 1);
+    return need >= 16 ? 8 : (need >= 8 ? 4 : (need >= 4 ? 2 : 1));
 }
 
 // the packed int16x2 kernels: single affine, global / semi-global; np = packed registers per
@@ -298,6 +332,17 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ku, CTA_THREADS, ctx->smem_bytes);
         ctx->grid_udh = std::max(1, occ) * ctx->sm_count;
     }
+    if (!dagp)
+        for (int c = 0; c < 3; ++c) {
+            const void* kt2 = reinterpret_cast<const void*>(thin_kernel_fn(true, P.local, P.spj, 4 >> c));
+            const void* ks2 = reinterpret_cast<const void*>(thin_kernel_fn(false, P.local, P.spj, 4 >> c));
+            cudaFuncSetAttribute(kt2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_bytes);
+            cudaFuncSetAttribute(ks2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_bytes);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kt2, CTA_THREADS, ctx->smem_bytes);
+            ctx->grid_trace_c[c] = std::max(1, occ) * ctx->sm_count;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ks2, CTA_THREADS, ctx->smem_bytes);
+            ctx->grid_score_c[c] = std::max(1, occ) * ctx->sm_count;
+        }
     if (ctx->pk_ok) {
         if (const char* e = getenv("GSPALN_PK_NP")) ctx->pk_np_forced = atoi(e) == 8 ? 8 : 4;
         for (int v = 0; v < 2; ++v) {
@@ -388,6 +433,9 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
     size_t udh_slab = 0, cpos_elems = 0;
     int n_trace = 0, n_score = 0, n_udh = 0, n_ng = 0, n_ngs = 0;
     size_t ng_width = 0, ng_rec = 0, ngs_width = 0;
+    int n_trace_c[3] = {0, 0, 0}, n_score_c[3] = {0, 0, 0};
+    size_t band_slab_c[3] = {0, 0, 0}, trace_slab_c[3] = {0, 0, 0};
+    const bool dagp_prm = ctx->prm.noll == 3;
     for (int k = 0; k < n; ++k) {
         const int i = ctx->h_order.p[k];
         const gspaln_task& t = tasks[i];
@@ -404,14 +452,23 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         // one that is already being read (one-shot submits stream the batch in)
         d.a_off = (long long) a_bytes;      a_bytes += align_up((size_t) mw + 1, 128);
         d.col_off = (long long) c_elems;    c_elems += align_up((size_t) nw + 2, 16);
-        band_slab = std::max(band_slab, align_up((size_t) width + 2 * NELEM, 32));
+        const size_t bslab = align_up((size_t) width + 2 * NELEM, 32);
         d.skl_off = (long long) skl_elems;
         d.pad1 = 0;
+        int cls = 8;
+        if (t.kind == GSPALN_FORWARD_WIP || t.kind == GSPALN_SCOREONLY_WIP) {
+            cls = wip_class(mw, width, dagp_prm);
+            d.pad0 = cls;
+        }
+        const int ci = cls == 4 ? 0 : (cls == 2 ? 1 : 2);
+        if (cls == 8) band_slab = std::max(band_slab, bslab);
+        else band_slab_c[ci] = std::max(band_slab_c[ci], bslab);
         if (t.kind == GSPALN_FORWARD_WIP) {
             const size_t nstrips = (mw + NELEM - 1) / NELEM;
-            trace_slab = std::max(trace_slab, align_up(nstrips * (size_t) (width + TRACE_PAD) * NELEM + 64, 256));
+            const size_t tslab = align_up(nstrips * (size_t) (width + TRACE_PAD) * NELEM + 64, 256);
             skl_elems += (size_t) d.skl_cap;
-            ++n_trace;
+            if (cls == 8) { trace_slab = std::max(trace_slab, tslab); ++n_trace; }
+            else { trace_slab_c[ci] = std::max(trace_slab_c[ci], tslab); ++n_trace_c[ci]; }
         } else if (t.kind == GSPALN_FORWARD_NG) {
             // path records: at most one per cell plus two per gap state at acceptor columns
             ng_width = std::max(ng_width, (size_t) width);
@@ -428,8 +485,10 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             udh_slab = std::max(udh_slab, align_up(4 * ((size_t) width + 2 * NELEM + 2) +
                                                    (size_t) t.n_imd * 4 * width + 8, 64));
             ++n_udh;
-        } else
+        } else if (cls == 8)
             ++n_score;
+        else
+            ++n_score_c[ci];
         ctx->skl_cap[i] = d.skl_cap;
     }
     if (ctx->h_apool.reserve(a_bytes + 16) != cudaSuccess || ctx->h_cpool.reserve(c_elems + 4) != cudaSuccess ||
@@ -468,13 +527,26 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         while (gt > 1 && (size_t) gt * WARPS_PER_CTA * (trace_slab + band_slab * 8) > budget) gt = gt * 3 / 4;
         int gu = n_udh ? ctas(ctx->grid_udh, n_udh) : 0;
         const size_t warps = (size_t) std::max(std::max(gt, gs), gu) * WARPS_PER_CTA;
+        // the narrower chain classes share the pools (the kernels run one after the other)
+        size_t band_words = warps * band_slab * (ctx->prm.noll == 3 ? 2 : 1);
+        size_t trace_bytes = (size_t) gt * WARPS_PER_CTA * trace_slab;
+        for (int c = 0; c < 3; ++c) {
+            int g1 = n_trace_c[c] ? ctas(ctx->grid_trace_c[c], n_trace_c[c]) : 0;
+            const int g2 = n_score_c[c] ? ctas(ctx->grid_score_c[c], n_score_c[c]) : 0;
+            while (g1 > 1 && (size_t) g1 * WARPS_PER_CTA * (trace_slab_c[c] + band_slab_c[c] * 8) > budget) g1 = g1 * 3 / 4;
+            ctx->grid_run_trace_c[c] = g1; ctx->grid_run_score_c[c] = g2;
+            ctx->n_trace_c[c] = n_trace_c[c]; ctx->n_score_c[c] = n_score_c[c];
+            ctx->band_slab_c[c] = band_slab_c[c]; ctx->trace_slab_c[c] = trace_slab_c[c];
+            band_words = std::max(band_words, (size_t) std::max(g1, g2) * WARPS_PER_CTA * band_slab_c[c]);
+            trace_bytes = std::max(trace_bytes, (size_t) g1 * WARPS_PER_CTA * trace_slab_c[c]);
+        }
         if (ctx->d_udh.reserve((size_t) gu * WARPS_PER_CTA * udh_slab + 64) != cudaSuccess) {
             cudaGetLastError();
             return fail(ctx, GSPALN_ENOMEM, "device UDH workspace allocation");
         }
         ctx->grid_run_udh = gu;
-        if (ctx->d_band.reserve(warps * band_slab * (ctx->prm.noll == 3 ? 2 : 1) + 32) != cudaSuccess ||
-            ctx->d_trace.reserve((size_t) gt * WARPS_PER_CTA * trace_slab + 256) != cudaSuccess) {
+        if (ctx->d_band.reserve(band_words + 32) != cudaSuccess ||
+            ctx->d_trace.reserve(trace_bytes + 256) != cudaSuccess) {
             cudaGetLastError();
             return fail(ctx, GSPALN_ENOMEM, "device workspace allocation");
         }
@@ -627,6 +699,22 @@ static int launch_range(gspaln_ctx* ctx, int lo, int hi, int slot, int& launches
             ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
             ctx->d_trace.p, (long long) ctx->trace_slab, ctx->d_skl.p, ctx->d_res.p, ready);
         ++launches;
+    }
+    for (int c = 0; c < 3 && !dagp; ++c) {
+        if (ctx->n_trace_c[c]) {
+            thin_kernel_fn(true, local, spj, 4 >> c)<<<ctx->grid_run_trace_c[c], CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+                ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 12 + 2 * c,
+                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab_c[c],
+                ctx->d_trace.p, (long long) ctx->trace_slab_c[c], ctx->d_skl.p, ctx->d_res.p, ready);
+            ++launches;
+        }
+        if (ctx->n_score_c[c]) {
+            thin_kernel_fn(false, local, spj, 4 >> c)<<<ctx->grid_run_score_c[c], CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+                ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 13 + 2 * c,
+                ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab_c[c],
+                ctx->d_trace.p, (long long) ctx->trace_slab_c[c], ctx->d_skl.p, ctx->d_res.p, ready);
+            ++launches;
+        }
     }
     if (ctx->n_udh) {
         auto ku = udh_kernel_fn(spj, local);

@@ -175,19 +175,19 @@ struct SmemLayout {
 //       last reset (counter value == step + NJ; saturation is implied by the
 //       clamp to the table size).
 // ---------------------------------------------------------------------------
-template <bool TRACE, bool LOCAL, bool SPJ, bool DAGP>
+template <int NR, bool TRACE, bool LOCAL, bool SPJ, bool DAGP>
 __host__ __device__ __forceinline__ void strip_step(
     int (&HO)[NR], const int (&HN)[NR], int (&F)[NR], int (&E)[NR],
     int (&F2)[NR], int (&E2)[NR], int up_f2, int gn2, int ge2,
     int (&V2)[NR], int (&NJ)[NR], const int (&arow)[NR],
     const char* __restrict__ ring_hi, const char* __restrict__ mtx_bytes,
     const int2* __restrict__ pen_tab, int pen_cap, int step,
-    int up_h, int up_f, int up_d, int gn, int ge, int floorL, unsigned (&tw)[NR / 4],
+    int up_h, int up_f, int up_d, int gn, int ge, int floorL, unsigned (&tw)[(NR + 3) / 4],
     int& best_v, int& best_k)
 {
     if (TRACE) {
 #pragma unroll
-        for (int w = 0; w < NR / 4; ++w) tw[w] = 0u;
+        for (int w = 0; w < (NR + 3) / 4; ++w) tw[w] = 0u;
     }
 #pragma unroll
     for (int k = NR - 1; k >= 0; --k) {
@@ -272,13 +272,15 @@ __host__ __device__ __forceinline__ void strip_step(
 // that finishes a strip starts its next one as soon as the strip above that one
 // is 15 + LAG steps ahead, so the systolic chain never drains inside a segment.
 // ---------------------------------------------------------------------------
-template <bool TRACE, bool LOCAL, bool SPJ, bool DAGP>
+template <int NR, bool TRACE, bool LOCAL, bool SPJ, bool DAGP>
 __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
                          const DevTask& t, const unsigned char* __restrict__ aseq,
                          const ColInfo* __restrict__ cols, unsigned* band, int* band2,
                          unsigned char* trace, int ml0, int nstr, bool localL_now,
                          bool localR, int accscr, WarpMax& wmax)
 {
+    constexpr int TPS = NELEM / NR;             // threads per strip (lock step)
+    constexpr int SPP = 32 / TPS;               // strip slots of the warp
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int slot = lane / TPS;                // strip slot of this thread
@@ -449,14 +451,14 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
             }
             up_d = prev_uh;
             prev_uh = up_h;
-            unsigned tw[NR / 4];
+            unsigned tw[(NR + 3) / 4];
             int sv = INT_MIN, sk = 0;
             if (i & 1)      // warp-uniform ping-pong (every thread steps once per iteration)
-                strip_step<TRACE, LOCAL, SPJ, DAGP>(HB, HA, F, E, F2, E2, up_f2, gn2, ge2, V2, NJ, arow, ring_hi,
+                strip_step<NR, TRACE, LOCAL, SPJ, DAGP>(HB, HA, F, E, F2, E2, up_f2, gn2, ge2, V2, NJ, arow, ring_hi,
                                                     mtx_bytes, sm.pen, P.pen_cap, j, up_h, up_f, up_d, gn, ge,
                                                     floorL, tw, sv, sk);
             else
-                strip_step<TRACE, LOCAL, SPJ, DAGP>(HA, HB, F, E, F2, E2, up_f2, gn2, ge2, V2, NJ, arow, ring_hi,
+                strip_step<NR, TRACE, LOCAL, SPJ, DAGP>(HA, HB, F, E, F2, E2, up_f2, gn2, ge2, V2, NJ, arow, ring_hi,
                                                     mtx_bytes, sm.pen, P.pen_cap, j, up_h, up_f, up_d, gn, ge,
                                                     floorL, tw, sv, sk);
             if (LOCAL && localR) {
@@ -474,12 +476,17 @@ __device__ void run_pass(const DevParams& P, const SmemLayout& sm,
             }
             if (TRACE) {
                 unsigned char* tr = trace + ((long long) (sidx + (ml0 - t.a_left) / NELEM) * (width + TRACE_PAD) + j) * NELEM + row0;
+                constexpr int NW = (NR + 3) / 4;
                 if (NR == 16)
-                    *reinterpret_cast<uint4*>(tr) = make_uint4(tw[0], tw[1], tw[NR / 4 - 2], tw[NR / 4 - 1]);
+                    *reinterpret_cast<uint4*>(tr) = make_uint4(tw[0], tw[NW > 1 ? 1 : 0], tw[NW > 2 ? 2 : 0], tw[NW - 1]);
                 else if (NR == 8)
-                    *reinterpret_cast<uint2*>(tr) = make_uint2(tw[0], tw[NR / 4 - 1]);
-                else
+                    *reinterpret_cast<uint2*>(tr) = make_uint2(tw[0], tw[NW - 1]);
+                else if (NR == 4)
                     *reinterpret_cast<unsigned*>(tr) = tw[0];
+                else if (NR == 2)
+                    *reinterpret_cast<unsigned short*>(tr) = (unsigned short) tw[0];
+                else
+                    *tr = (unsigned char) tw[0];
             }
             // bottom row of the strip -> band buffer (src/fwd2s1_wip_simd.h:438-442)
             if (j8 >= row0 && j8 < row0 + NR) {
@@ -847,7 +854,11 @@ static __device__ int walk_trace(const DevTask& t, const unsigned char* trace, i
 // kernel (PK = 0), launched behind it on the same stream, runs everything else plus those.
 constexpr int ST_NEED_EXACT = 6;
 
-template <bool TRACE, bool LOCAL, bool SPJ, bool DAGP, int PK = 0>
+// NRT = strip rows per thread of the 32-bit kernel: 8 (two threads per strip, 16 strip slots per warp)
+// for problems that can fill such a chain, 4 / 2 / 1 (8 / 4 / 2 slots) for problems whose band or
+// row count allows fewer strips in flight -- the host assigns the class (DevTask::pad0) so that a
+// thin or narrow problem still keeps all 32 lanes of its warp busy.
+template <bool TRACE, bool LOCAL, bool SPJ, bool DAGP, int PK = 0, int NRT = 8>
 __global__ void __launch_bounds__(CTA_THREADS, PK == 8 ? 2 : 3)
 dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
               const DevTask* __restrict__ tasks,
@@ -921,6 +932,7 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
         const int ti = order[tk];
         const DevTask t = tasks[ti];
         if (t.kind > 1 || (t.kind == 0) != TRACE) continue;    // handled by another kernel
+        if ((t.pad0 ? t.pad0 : 8) != NRT) continue;             // another chain width runs this problem
         if (!wait_inputs(ready, tk)) {
             if (lane == 0) { DevResult r; r.score = 0; r.status = 4; r.n_skl = 0; r.pad = 0; results[ti] = r; }
             continue;
@@ -928,7 +940,7 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
         {
             // who runs this problem: the packed kernel if the host marked it eligible, else (or if
             // the packed kernel gave it back) the 32-bit kernel
-            const bool fast = P.pk_ok && apool[t.a_off + (t.a_right - t.a_left)] == 1;
+            const bool fast = NRT == 8 && P.pk_ok && apool[t.a_off + (t.a_right - t.a_left)] == 1;
             if (PK != 0 ? !fast : (fast && results[ti].status != ST_NEED_EXACT)) continue;
         }
         PkMonitor mon{-32768, 0, 0};
@@ -983,8 +995,8 @@ dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
             if constexpr (PK != 0)
                 run_pass_pk<PK, TRACE, SPJ>(P, smk, t, aseq, cols, band, trace, ml0, nstr, wmax, mon);
             else
-                run_pass<TRACE, LOCAL, SPJ, DAGP>(P, sm, t, aseq, cols, band, band2, trace, ml0, nstr,
-                                                  LocalL && !accscr, LocalR, accscr, wmax);
+                run_pass<NRT, TRACE, LOCAL, SPJ, DAGP>(P, sm, t, aseq, cols, band, band2, trace, ml0, nstr,
+                                                       LocalL && !accscr, LocalR, accscr, wmax);
             const int last_ml = ml0 + (nstr - 1) * NELEM;
             if (last_ml == mc) {
                 // src/fwd2s1_wip_simd.h:454-465

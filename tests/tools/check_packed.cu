@@ -120,7 +120,7 @@ static long run_case(std::mt19937& rng, const Params& PR, int regime, int steps,
         int sv = INT_MIN, sk = 0;
         int (&HOs)[NR] = (j & 1) ? HB : HA;
         int (&HNs)[NR] = (j & 1) ? HA : HB;
-        strip_step<TRACE, false, SPJ, false>(HOs, HNs, F, E, F2, E2, NEV, 0, 0, V2, NJ, arow, ring_hi,
+        strip_step<NR, TRACE, false, SPJ, false>(HOs, HNs, F, E, F2, E2, NEV, 0, 0, V2, NJ, arow, ring_hi,
                                              reinterpret_cast<const char*>(mtxT), pen.data(), cap, j, up_h, up_f,
                                              prev_uh, PR.gn, PR.ge, INT_MIN, tw, sv, sk);
         prev_uh = up_h;
