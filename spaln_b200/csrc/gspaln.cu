@@ -772,7 +772,7 @@ int gspaln_run(gspaln_ctx* ctx)
     int launches = 0;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (n > 0) {
-        CK(cudaMemsetAsync(ctx->d_ticket.p, 0, 16 * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_ticket.p, 0, 32 * sizeof(int), ctx->stream));
         int rc = launch_range(ctx, 0, n, 0, launches);
         if (rc != GSPALN_OK) return rc;
     }

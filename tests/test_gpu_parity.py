@@ -591,3 +591,25 @@ def test_packed_and_32bit_kernels_agree(monkeypatch):
         assert f.status == 0 and s.status == 0
         assert f.score == s.score and np.array_equal(f.skl, s.skl)
         assert fs.score == ss.score
+
+
+def test_resident_runs_repeat_for_every_chain_class(oracle):
+    """upload once, run three times (every kernel of every chain-width class gets its ticket counter
+    reset), download: the same answers as the one-shot submit and the oracle"""
+    prm, _ = golden_io.load("dna_A2_global")
+    rng = np.random.default_rng(31337)
+    probs = (_synthetic(prm, rng, 12, (10, 40), (3, 30)) + _synthetic(prm, rng, 10, (50, 120), (10, 80)) +
+             _synthetic(prm, rng, 8, (130, 300), (30, 300)) + _synthetic(prm, rng, 4, (600, 900), (300, 900)))
+    eng = _engine(prm)
+    ps = _problems(probs)
+    eng.upload(ps)
+    for _ in range(3):
+        eng.run()
+    res = eng.download()
+    one = eng.forwardS1_wip(ps)
+    for i, (pb, r, o1) in enumerate(zip(probs, res, one)):
+        o = oracle.forward_wip(prm, pb)
+        assert r.status == 0 and o1.status == 0
+        assert r.score == o["score"] == o1.score, i
+        assert np.array_equal(r.skl, o["skl"]) and np.array_equal(o1.skl, o["skl"]), i
+    eng.close()
