@@ -31,18 +31,25 @@ HIT_DTYPE = np.dtype(GENE_RECORD_FIELDS + [("n_skl", "<i4"), ("skl_off", "<i4")]
 assert HIT_DTYPE.itemsize == 72 + 8
 
 
-def lpt_partition(cells, world: int):
-    """Longest-processing-time-first assignment of problems to ranks.
-    cells[i] = estimated DP cells of problem i.  Returns a list of index arrays (ascending
-    inside each rank) whose cell totals differ by at most the largest problem."""
+def lpt_partition(cells, world: int, exact_below: int = 4096):
+    """Cell-balanced assignment of problems to ranks, largest problems first.
+    cells[i] = DP cells of problem i (gspaln_task_cells).  Up to `exact_below` problems: the
+    longest-processing-time rule proper (each problem to the least loaded rank, heap).  Larger
+    jobs: the sorted problems are dealt in serpentine order (0 .. N-1, N-1 .. 0, ...), which is
+    one vectorised sort and balances the ranks to within the largest problem just the same.
+    Returns a list of index arrays (ascending inside each rank)."""
     cells = np.asarray(cells, np.int64)
     order = np.argsort(-cells, kind="stable")
     owner = np.empty(len(cells), np.int64)
-    heap = [(0, r) for r in range(world)]
-    for i, c in zip(order.tolist(), cells[order].tolist()):
-        load, r = heapq.heappop(heap)
-        owner[i] = r
-        heapq.heappush(heap, (load + c, r))
+    if len(cells) <= exact_below:
+        heap = [(0, r) for r in range(world)]
+        for i, c in zip(order.tolist(), cells[order].tolist()):
+            load, r = heapq.heappop(heap)
+            owner[i] = r
+            heapq.heappush(heap, (load + c, r))
+    else:
+        k = np.arange(len(cells)) % (2 * world)
+        owner[order] = np.where(k < world, k, 2 * world - 1 - k)
     return [np.nonzero(owner == r)[0] for r in range(world)]
 
 
@@ -52,28 +59,36 @@ def _dist():
     return torch, dist
 
 
-def broadcast_buffers(bufs, src: int = 0, device=None):
+def broadcast_buffers(bufs, src: int = 0, device=None, to_host: bool = True):
     """One-off broadcast of the formatted genome / query set / index tables from rank `src`:
     every buffer is sent as raw bytes and comes back with the dtype and shape it had on `src`
-    (pass None on the other ranks).  NCCL when `device` is a CUDA device, gloo otherwise."""
+    (pass None on the other ranks).  NCCL when `device` is a CUDA device, gloo otherwise.
+    `bufs` may hold torch tensors (e.g. pinned host staging buffers) instead of numpy arrays.
+    to_host = False leaves the received bytes on the device (uint8 tensors) -- where the scan and
+    DP kernels of a run consume them -- and skips the device-to-host copy."""
     torch, dist = _dist()
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        return [np.asarray(b) for b in bufs]
+        return [b if not to_host or isinstance(b, np.ndarray) else b.numpy() for b in bufs]
     dev = device if device is not None else "cpu"
     rank = dist.get_rank()
     meta = [None]
     if rank == src:
-        bufs = [np.ascontiguousarray(b) for b in bufs]
-        meta = [[(b.dtype.str, b.shape) for b in bufs]]
+        bufs = [b if torch.is_tensor(b) else torch.from_numpy(np.ascontiguousarray(b)) for b in bufs]
+        meta = [[(str(b.numpy().dtype.str), tuple(b.shape)) for b in bufs]]
     dist.broadcast_object_list(meta, src)
     out = []
     for k, (dt, shape) in enumerate(meta[0]):
         nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dt).itemsize
         t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         if rank == src:
-            t.copy_(torch.from_numpy(bufs[k].view(np.uint8).reshape(-1)))
+            t.copy_(bufs[k].view(torch.uint8).reshape(-1), non_blocking=True)
         dist.broadcast(t, src)
-        out.append(bufs[k] if rank == src else t.cpu().numpy().view(np.dtype(dt)).reshape(shape))
+        if not to_host:
+            out.append(t)
+        elif rank == src:
+            out.append(bufs[k].numpy())
+        else:
+            out.append(t.cpu().numpy().view(np.dtype(dt)).reshape(shape))
     return out
 
 

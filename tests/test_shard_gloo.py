@@ -107,3 +107,14 @@ def test_hit_record_header_is_the_reference_generecord():
     corners = np.array([[90, 900], [60, 870], [60, 500], [30, 470], [30, 200], [0, 170]], np.int32)
     h = shard.make_hits([7], [1234], [6], [90], corners, scale=10.0, min_intron=50)
     assert h["nexn"][0] == 3 and h["Gstart"][0] == 170 and h["Gend"][0] == 900 and h["Rid"][0] == 7
+
+
+def test_partition_of_large_jobs_is_balanced_too():
+    """beyond 4096 problems the sorted problems are dealt in serpentine order (vectorised)"""
+    from spaln_b200 import shard
+    cells = np.random.default_rng(5).lognormal(16, 0.8, size=80000).astype(np.int64)
+    parts = shard.lpt_partition(cells, 8)
+    assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(80000))
+    loads = np.array([int(cells[p].sum()) for p in parts])
+    assert loads.max() - loads.min() <= int(cells.max())
+    assert loads.max() / loads.mean() < 1.01
