@@ -620,6 +620,152 @@ def config5_sweep(args, prm, rank, local_rank, world):
     return points
 
 
+def _shape_chunk(args):
+    """worker: problems [lo, hi) step `stride` of a config-3 / config-4 job (seeded per problem)"""
+    cfg, seed, idx = args
+    from spaln_b200 import workload
+    out = []
+    for i in idx:
+        rng = np.random.default_rng([seed, cfg, int(i)])
+        if cfg == 3:
+            r = workload.protein_problem(rng, plen_range=(300, 800), flank=(500, 5000), sh=100)
+            r.pop("genome"); r.pop("query")
+        else:
+            r = workload.config2_problem(rng, qlen_range=(1500, 3500), intron_scale=20.0)
+            r["int53"] = workload.synthetic_int53(r["b"])
+            r.pop("genome_str"); r.pop("query_str")
+        r["index"] = int(i)
+        out.append(r)
+    return out
+
+
+def shape_job(args, cfg, rank, local_rank, world, ncores):
+    """BASELINE configs 3 / 4 at their stated scale as ONE query-sharded job over N GPUs (weak
+    scaling: 100 000 proteins resp. 200 000 mRNAs over 8 GPUs = 12 500 / 25 000 per GPU by default):
+    problem i of the job belongs to rank i mod N and is built there from its own seed (the loci of a
+    3 Gb genome do not fit one host buffer here, so nothing is broadcast in this mode); every rank
+    runs its share -- config 3: SimdAln2h1::forwardH1_wip semantics (score + corners), config 4:
+    Aln2s1::lspS_ng at the default -V with -LS, i.e. the multi-intermediate Hirschberg route + block
+    re-alignments -- and the GeneRecord hit records are gathered on rank 0."""
+    import multiprocessing as mp
+    per_gpu = args.queries if args.queries != 10000 else (12500 if cfg == 3 else 25000)
+    total = per_gpu * world
+    mine = np.arange(rank, total, world)
+    chunks = [(cfg, SEED, mine[k:k + 128]) for k in range(0, len(mine), 128)]
+    procs = max(1, min(ncores // max(world, 1), 32))
+    if procs > 1:
+        with mp.get_context("fork").Pool(procs) as pool:
+            raw = [r for part in pool.map(_shape_chunk, chunks) for r in part]
+    else:
+        raw = [r for c in chunks for r in _shape_chunk(c)]
+
+    import torch
+    import torch.distributed as dist
+    import golden_io
+    from spaln_b200 import Engine, EngineH, shard
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if cfg == 3:
+        prm, _ = golden_io.load_protein(PROT_FIXTURE)
+        host_cells_h(raw)
+        problems = to_problems_h(raw)
+        eng = EngineH(prm, device=local_rank)
+        bcell, kname = B_CELL_H, "dp_h1_kernel<true>"
+    else:
+        prm, _ = golden_io.load("dna_A2_local")
+        host_cells(raw)
+        problems = to_problems(raw)
+        eng = Engine(prm, device=local_rank)
+        bcell, kname = 1.5, "dp_udh_kernel + dp_wip_kernel<true, LOCAL> (lspS_ng levels)"
+        lsp_opts = dict(max_vmf_space=32 * 1024 * 1024, sh=int(prm["sh"]), alg=2)
+    cells = sum(r["cells"] for r in raw)
+    qlen = np.array([r["a_right"] for r in raw], np.int64)
+
+    def run_once():
+        """host buffers in -> hit records on rank 0; returns (kernel ms, device cells, phases)"""
+        t0 = time.perf_counter()
+        packed = eng.pack(problems)
+        if cfg == 3:
+            eng.submit_packed(packed)
+        else:
+            eng.lsp_packed(packed, **lsp_opts)
+        tm = eng.timing()
+        t1 = time.perf_counter()
+        if world > 1:
+            dist.barrier()
+        t2 = time.perf_counter()
+        n_skl = np.minimum(packed.res["n_skl"][:packed.n], np.diff(packed.off)).astype(np.int64)
+        src = np.repeat(packed.off[:-1], n_skl) + (np.arange(int(n_skl.sum())) - np.repeat(np.cumsum(n_skl) - n_skl, n_skl))
+        corners = packed.skl[src]
+        hits = shard.make_hits(mine, packed.scores, n_skl, qlen, corners, min_intron=int(prm["llmt"]))
+        got = shard.gather_hit_records(hits, corners, 0, dev)
+        t3 = time.perf_counter()
+        bad = int(np.count_nonzero(packed.status))
+        return tm, got, bad, (t1 - t0, t2 - t1, t3 - t2)
+
+    run_once() if len(problems) <= 2000 else (eng.submit(problems[:64]) if cfg == 3 else eng.lspS_ng(problems[:64], **lsp_opts))
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    steps = max(1, min(args.steps, 2))
+    kms, ph = 0.0, np.zeros(3)
+    for _ in range(steps):
+        tm, got, bad, p3 = run_once()
+        kms += tm.kernel_ms
+        ph += p3
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / steps
+    clocks = sampler.stop()
+    kms /= steps
+    ph /= steps
+    if world > 1:
+        t = torch.tensor([kms, e2e_s] + ph.tolist(), dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kms, e2e_s = float(t[0]), float(t[1])
+        ph = np.array(t.tolist()[2:])
+        c = torch.tensor([cells, bad], dtype=torch.int64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        cells_total, bad = int(c[0]), int(c[1])
+    else:
+        cells_total = cells
+    if rank == 0:
+        assert got is not None and len(got[0]) == total
+        peak, peak_kind = measured_peak()
+        name = ("config3: proteins 300-800 aa x genomic locus (+-0.5-5 kb), forwardH1_wip semantics, aa x nt cells"
+                if cfg == 3 else
+                "config4: mRNA 1.5-3.5 kb x locus with 20x introns (tens of kb), -LS, lspS_ng at -V 32 MiB "
+                "(Hirschberg route + block re-alignments), root cells")
+        emit({"metric": f"GCUPS ({name})", "value": cells_total / (kms * 1e-3) / 1e9, "unit": "GCUPS",
+              "n_gpus": world, "steps": steps, "warmup": 1, "ms_per_step": kms, "higher_is_better": True,
+              "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+              "config": {"workload": name, "queries_per_gpu": per_gpu, "queries_total": total,
+                         "parallelism": f"ONE job: problem i -> rank i mod {world}, GeneRecord hit records gathered on rank 0"},
+              "queries_per_s": total / e2e_s, "clocks": clocks, "status_errors": bad,
+              "e2e": {"value": cells_total / e2e_s / 1e9, "unit": "GCUPS", "queries_per_s": total / e2e_s,
+                      "h2d_bytes_per_step": int(tm.h2d_bytes), "d2h_bytes_per_step": int(tm.d2h_bytes),
+                      "hit_records_on_rank0": total,
+                      "phases_ms": {"marshal+pack+h2d+kernels+d2h": 1e3 * ph[0], "wait_for_slowest_rank": 1e3 * ph[1],
+                                    "hit_records+gather": 1e3 * ph[2], "total": 1e3 * e2e_s}},
+              "gpu_launches": int(tm.launches) * steps,
+              "roofline": {"bound": "hbm", "bytes_per_cell": bcell, "unit": "GB/s", "peak": peak, "peak_kind": peak_kind,
+                           "achieved": cells / (kms * 1e-3) / 1e9 * bcell, "frac": cells / (kms * 1e-3) / 1e9 * bcell / peak,
+                           "kernel": kname, "traffic": None}})
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def host_cells(raw):
     import ctypes as C
     from spaln_b200 import capi
@@ -664,8 +810,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--protein-queries", type=int, default=3000,
                     help="problems of the protein x genome leg per GPU (0 = skip the leg)")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 5],
-                    help="2: the headline workload (default); 5: band-width x query-length sweep")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="2: the headline workload (default); 3 / 4: the protein and the long-intron mRNA "
+                         "jobs at their stated scale; 5: band-width x query-length sweep")
     ap.add_argument("--sweep-tasks", type=int, default=102400, help="tasks per sweep point and rank")
     ap.add_argument("--leg", default="", help=argparse.SUPPRESS)
     ap.add_argument("--leg-seed", type=int, default=0, help=argparse.SUPPRESS)
@@ -722,6 +869,8 @@ def main():
         emit(line)
         return 0
 
+    if args.config in (3, 4) and args.impl != "reference":
+        return shape_job(args, args.config, rank, local_rank, world, ncores)
     if args.config == 5:
         import torch
         import torch.distributed as dist
