@@ -496,7 +496,8 @@ def config4_leg(args, ncores, with_cpu):
                                 "--queries", str(args.queries)], capture_output=True, text=True)
         try:
             c = json.loads(child.stdout.strip().splitlines()[-1])
-            mism = sum(1 for i in range(k) if c["scores"][i] != res[i].score or c["nskl"][i] != len(res[i].skl))
+            mism = sum(1 for i in range(k) if res[i].status != 0 or c["scores"][i] != res[i].score or
+                       not np.array_equal(np.array(c["skl"][i], np.int32).reshape(-1, 2), res[i].skl))
             out["cpu_baseline"] = {"queries_per_s": c["queries_per_s"], "gcups_root_cells": c["gcups"],
                                    "cores": c["cores"], "kind": "reference",
                                    "sample": f"first {k} problems, Aln2s1::lspS_ng of the AVX2 build, -LS, "
@@ -545,7 +546,7 @@ def config4_reference_child(args):
     host_cells(raw)
     cells = sum(r["cells"] for r in raw)
     print(json.dumps({"queries_per_s": k / dt, "gcups": cells / dt / 1e9, "cores": min(ncores, k),
-                      "scores": [o["score"] for o in outs], "nskl": [len(o["skl"]) for o in outs]}))
+                      "scores": [o["score"] for o in outs], "skl": [o["skl"].tolist() for o in outs]}))
     return 0
 
 

@@ -268,8 +268,9 @@ dp_hxild_kernel(const DevNgHParams* __restrict__ gP, const DevNgHTask* __restric
             int q = 0;
             HxList don[3];
             don[0].clear(); don[1].clear(); don[2].clear();
-            const int* prof_prev = P.mtx + T.aa(m > 0 ? m - 1 : 0) * P.simdim;  // residue the row pairs
-            const int* prof_next = P.mtx + T.aa(m) * P.simdim;                  // the one after it
+            // (lanes past the last row own nothing: they must not touch the query array)
+            const int* prof_prev = P.mtx + (row ? T.aa(m > 0 ? m - 1 : 0) : 0) * P.simdim;  // residue the row pairs
+            const int* prof_next = P.mtx + (row ? T.aa(m) : 0) * P.simdim;                  // the one after it
             bool started = false;
 
             for (int s = s_begin; s <= s_end; ++s) {
