@@ -115,6 +115,11 @@ typedef struct gspaln_task {
     const uint16_t* int53;      /* GSPALN_FORWARD_NG (and gspaln_lsp blocks with < 8 rows), else may be
                                    NULL: Exinon::int53[n] by column n (src/codepot.h:49-54) as
                                    dinc5 | dinc3 << 4 | cano5 << 8 | cano3 << 12 */
+    const int32_t* cip;         /* optional (NULL: none): Cip_score::cip_score(m) by query position m in
+                                   [0, a_right] (src/gsinfo.h:127-139), the bonus for intron positions
+                                   conserved with the query's own annotation.  Added at acceptors by the
+                                   exact-ILD kernels (`sigB`, src/fwd2s1.cc:254,338 and 1191,1262); the
+                                   `_wip` kernels of the reference do not read it, nor do ours */
 } gspaln_task;
 
 typedef struct gspaln_result {
@@ -339,6 +344,10 @@ typedef struct gspaln_h_task {
     int32_t a_len;              /* Seq::len of the query (driver: range check of mimd_postwork) */
     const uint16_t* int53;      /* GSPALN_FORWARD_NG (and gspaln_h_lsp blocks with < 8 rows), else may be
                                    NULL: Exinon::int53[n] by column, as in gspaln_task.int53 */
+    const int32_t* cip;         /* optional (NULL: none): Cip_score::cip_score(c) by coding position
+                                   c = 3 m - phase in [0, 3 a_right + 1] (src/gsinfo.h:127-139), added
+                                   at acceptors by the exact-ILD kernel (sigB[phs], src/fwd2h1.cc:352-354,
+                                   483); the `_wip` kernels do not read it */
 } gspaln_h_task;
 
 typedef struct gspaln_h_ctx gspaln_h_ctx;

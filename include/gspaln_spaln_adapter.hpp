@@ -68,7 +68,17 @@ class SpalnEngine {
         std::vector<short> sig5, sig3;
         std::vector<unsigned short> int53;
         std::vector<int> skl;
+        std::vector<int32_t> cip;
     };
+
+    // gspaln_task.cip: Cip_score::cip_score(m) of the rows of the current range (src/gsinfo.h:127-139)
+    static void fill_cip(gspaln_task& t, Scratch& s, const Seq* a, const Cip_score* cip)
+    {
+        if (!cip) return;
+        s.cip.assign((size_t) a->right + 1, 0);
+        for (int m = a->left; m <= a->right; ++m) s.cip[m] = (int32_t) cip->cip_score(m);
+        t.cip = s.cip.data();
+    }
 
     static void fill(gspaln_task& t, Scratch& s, const Seq** seqs, const WINDOW& wdw, int kind)
     {
@@ -180,7 +190,8 @@ public:
     // int53: the INT53 array of seqs[1]->exin indexed by column (may be 0: blocks with fewer than
     // 8 rows are then reported as unsupported).  Returns false if the problem needs a kernel that
     // is not on the device (the caller falls back to the stock lspS_ng); *scr receives the score.
-    bool lspS_ng(const Seq** seqs, const WINDOW& wdw, Mfile* mfd, const INT53* int53, VTYPE* scr)
+    bool lspS_ng(const Seq** seqs, const WINDOW& wdw, Mfile* mfd, const INT53* int53, VTYPE* scr,
+                 const Cip_score* cip = 0)
     {
         gspaln_task t;
         gspaln_result r;
@@ -190,6 +201,7 @@ public:
             pack_int53(s.int53, int53, seqs[1]);
             t.int53 = s.int53.data();
         }
+        fill_cip(t, s, seqs[0], cip);   // read by the exact-ILD kernel of blocks with < 8 rows
         const gspaln_lsp_opts o = lsp_opts_now();
         int cap = 256;
         for (;;) {
@@ -225,7 +237,7 @@ public:
 
     // == Aln2s1::scorealoneS_ng(wdw): what HomScoreS_ng runs for queries shorter than 4 residues
     // (src/fwd2s1.cc:2704-2705).  Needs enable_scalar() and the segment's INT53 array.
-    VTYPE scorealoneS_ng(const Seq** seqs, const WINDOW& wdw, const INT53* int53)
+    VTYPE scorealoneS_ng(const Seq** seqs, const WINDOW& wdw, const INT53* int53, const Cip_score* cip = 0)
     {
         gspaln_task t;
         gspaln_result r;
@@ -233,6 +245,7 @@ public:
         fill(t, s, seqs, wdw, GSPALN_SCOREALONE_NG);
         pack_int53(s.int53, int53, seqs[1]);
         t.int53 = s.int53.data();
+        fill_cip(t, s, seqs[0], cip);
         memset(&r, 0, sizeof(r));
         int rc = gspaln_queue_submit(q_, &t, &r);
         if (rc != GSPALN_OK) die("gspaln_submit", rc, ctx_);
@@ -256,6 +269,7 @@ class SpalnEngineH {
     struct Scratch {
         std::vector<unsigned short> int53;
         std::vector<int> skl;
+        std::vector<int32_t> cip;
     };
 
     // one task == what the SimdAln2h1 constructor dereferences (src/fwd2h1_simd.h:196-382): the
@@ -358,7 +372,8 @@ public:
 
     // == Aln2h1::lspH_ng(wdw) with the corners appended to mfd (src/fwd2h1.cc:2134-2230); false:
     // the problem needs a kernel that is not on the device (the caller runs the stock lspH_ng)
-    bool lspH_ng(const Seq** seqs, const WINDOW& wdw, Mfile* mfd, const INT53* int53, VTYPE* scr)
+    bool lspH_ng(const Seq** seqs, const WINDOW& wdw, Mfile* mfd, const INT53* int53, VTYPE* scr,
+                 const Cip_score* cip = 0)
     {
         gspaln_h_task t;
         gspaln_result r;
@@ -367,6 +382,14 @@ public:
         if (int53) {
             pack_int53(s.int53, int53, seqs[1]);
             t.int53 = s.int53.data();
+        }
+        if (cip) {
+            // gspaln_h_task.cip: by coding position 3 m - phase (src/fwd2h1.cc:352-354)
+            const Seq* a = seqs[0];
+            s.cip.assign((size_t) 3 * a->right + 2, 0);
+            for (int c = std::max(0, 3 * a->left - 1); c <= 3 * a->right + 1; ++c)
+                s.cip[c] = (int32_t) cip->cip_score(c);
+            t.cip = s.cip.data();
         }
         const gspaln_lsp_opts o = lsp_opts_now();
         int cap = 256;

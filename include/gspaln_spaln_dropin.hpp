@@ -104,8 +104,9 @@ inline SpalnEngineH* engineH(const PwdB* pwd, const Seq* b)
     return e;
 }
 
-// what the device covers: the `_wip` formulation (-A2 / -A3: simd >= 2), no Cip_score bonus
-inline bool covered(int simd, const Cip_score* cip) { return simd >= 2 && !cip; }
+// what the device covers: the `_wip` formulation (-A2 / -A3: simd >= 2).  Cip_score (queries annotated
+// with intron positions) is read by the exact-ILD kernels only and travels with the task
+inline bool covered(int simd, const Cip_score*) { return simd >= 2; }
 
 // ---------------------------------------------------------------------------------- DNA hooks
 inline bool lspS(const Seq** seqs, const PwdB* pwd, const WINDOW& wdw, Mfile* mfd, int simd,
@@ -115,7 +116,7 @@ inline bool lspS(const Seq** seqs, const PwdB* pwd, const WINDOW& wdw, Mfile* mf
     const Seq* b = seqs[1];
     SpalnEngine* e = engineS(pwd, b);
     const INT53* i53 = (b->inex.intr && e->same_sig53tab(sig53tab_of(b))) ? int53_of(b) : 0;
-    return e->lspS_ng(seqs, wdw, mfd, i53, scr);
+    return e->lspS_ng(seqs, wdw, mfd, i53, scr, cip);
 }
 
 inline bool trcbkS(const Seq** seqs, const PwdB* pwd, const WINDOW& wdw, Mfile* mfd, int simd,
@@ -133,7 +134,7 @@ inline bool homscoreS(const Seq** seqs, const PwdB* pwd, VTYPE* scr)
     const int simd = algmode.alg & 3;
     const Seq* a = seqs[0];
     const Seq* b = seqs[1];
-    if (simd < 2 || (b->inex.intr && a->sigII)) return false;
+    if (simd < 2) return false;
     if (simd == 3) IntronPrm.nquant = 1;        // what the Aln2s1 constructor does (src/fwd2s1.cc:125)
     WINDOW wdw;
     stripe(seqs, &wdw, alprm.sh);
@@ -141,7 +142,11 @@ inline bool homscoreS(const Seq** seqs, const PwdB* pwd, VTYPE* scr)
     if (a->right - a->left < 4) {               // src/fwd2s1.cc:2704-2705
         if (b->inex.intr && !(int53_of(b) && e->same_sig53tab(sig53tab_of(b)))) return false;
         if (!b->inex.intr || b->right - b->left >= MAX_SEGMENT) return false;
-        *scr = e->scorealoneS_ng(seqs, wdw, int53_of(b));
+        if (a->sigII) {                         // the Aln2s1 constructor's Cip_score (src/fwd2s1.cc:124)
+            const Cip_score cs(a);
+            *scr = e->scorealoneS_ng(seqs, wdw, int53_of(b), &cs);
+        } else
+            *scr = e->scorealoneS_ng(seqs, wdw, int53_of(b));
         return true;
     }
     *scr = e->scoreonlyS1_wip(seqs, wdw);
@@ -156,7 +161,7 @@ inline bool lspH(const Seq** seqs, const PwdB* pwd, const WINDOW& wdw, Mfile* mf
     if (!covered(simd, cip) || !b->exin || !b->exin->data_p) return false;
     SpalnEngineH* e = engineH(pwd, b);
     const INT53* i53 = (b->inex.intr && e->same_sig53tab(sig53tab_of(b))) ? int53_of(b) : 0;
-    return e->lspH_ng(seqs, wdw, mfd, i53, scr);
+    return e->lspH_ng(seqs, wdw, mfd, i53, scr, cip);
 }
 
 inline bool trcbkH(const Seq** seqs, const PwdB* pwd, const WINDOW& wdw, Mfile* mfd, int simd,
@@ -175,7 +180,7 @@ inline bool homscoreH(const Seq** seqs, const PwdB* pwd, VTYPE* scr)
     const int simd = algmode.alg & 3;
     const Seq* a = seqs[0];
     const Seq* b = seqs[1];
-    if (simd < 2 || (b->inex.intr && a->sigII) || !b->exin || !b->exin->data_p) return false;
+    if (simd < 2 || !b->exin || !b->exin->data_p) return false;
     if (a->right - a->left < 8) return false;   // forwardH_ng score: stock scalar code (src/fwd2h1.cc:3298)
     if (simd == 3) IntronPrm.nquant = 1;
     WINDOW wdw;

@@ -6,6 +6,7 @@
 #include <cwchar>
 #include "aln.h"
 #include "vmf.h"
+#include "gsinfo.h"
 #include "gspaln_spaln_adapter.hpp"
 
 namespace {
@@ -51,7 +52,11 @@ int dropin_s1_adapter_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up, int
 	WINDOW wdw = {lw, up, up - lw + 3};
 	Mfile mfd(sizeof(SKL));
 	VTYPE scr = 0;
-	if (!eng->lspS_ng(seqs, wdw, &mfd, (const INT53*) int53, &scr)) return -1;
+	// the Aln2s1 constructor's Cip_score for an annotated query (src/fwd2s1.cc:124)
+	const Cip_score* cip = (seqs[1]->inex.intr && seqs[0]->sigII)? new Cip_score(seqs[0]): 0;
+	const bool ok = eng->lspS_ng(seqs, wdw, &mfd, (const INT53*) int53, &scr, cip);
+	delete cip;
+	if (!ok) return -1;
 	*score = scr;
 	return copy_out(mfd, (SKL*) skl_out, cap);
 }
@@ -85,7 +90,11 @@ int dropin_h1_adapter_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up, int
 	WINDOW wdw = {lw, up, up - lw + 7};
 	Mfile mfd(sizeof(SKL));
 	VTYPE scr = 0;
-	if (!eng->lspH_ng(seqs, wdw, &mfd, (const INT53*) int53, &scr)) return -1;
+	// the Aln2h1 constructor's Cip_score for an annotated query (src/fwd2h1.cc:126)
+	const Cip_score* cip = (seqs[1]->inex.intr && seqs[0]->sigII)? new Cip_score(seqs[0]): 0;
+	const bool ok = eng->lspH_ng(seqs, wdw, &mfd, (const INT53*) int53, &scr, cip);
+	delete cip;
+	if (!ok) return -1;
 	*score = scr;
 	return copy_out(mfd, (SKL*) skl_out, cap);
 }

@@ -324,6 +324,30 @@ int ref_task_kernel(void* h, int lw, int up, int kind, int n_imd, int mode,
 
 // raw handles for oracle/dropin_shim.cc (libspaln_dropin.so), which runs the same Seq / PwdB
 // objects through include/gspaln_spaln_adapter.hpp
+// Attach intron-position annotation to the query (what a `;B` / `;b` block of the query file
+// produces, src/gsinfo.h:76-126): n boundaries at positions pos[] with multiplicities num[].
+// The Aln2* constructors build their Cip_score from it (src/fwd2s1.cc:124, src/fwd2h1.cc:126).
+void ref_task_set_cip(void* h, const int* pos, const int* num, int n)
+{
+	Seq* a = ((RefTask*) h)->sqs[0];
+	delete a->sigII;
+	a->sigII = new SigII(pos, n, a->isprotein()? 3: 1);
+	for (int i = 0; i < n; ++i) {
+	    a->sigII->pfq[i].num = num[i];
+#if USE_WEIGHT
+	    a->sigII->pfq[i].dns = num[i];
+#endif
+	}
+	if (n) a->sigII->pfq[n] = pfqend;
+}
+
+// Cip_score::cip_score(c) for c in [0, n) as the DP kernels of this task would see it
+void ref_task_cip_table(void* h, int* out, int n)
+{
+	Cip_score cs(((RefTask*) h)->sqs[0]);
+	for (int c = 0; c < n; ++c) out[c] = (int) cs.cip_score(c);
+}
+
 const void* ref_pwd() { return g_pwd; }
 void* ref_task_seqs(void* h) { return ((RefTask*) h)->sqs; }
 const void* ref_task_int53_ptr(void* h)

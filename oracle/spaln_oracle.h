@@ -60,6 +60,9 @@ typedef struct {
     int32_t lw, up;         /* WINDOW (width = up - lw + 3) */
     const uint16_t* int53;  /* scalar kernel only: INT53 nibbles by column n in [0, blen + 1]:
                                dinc5 | dinc3 << 4 | cano5 << 8 | cano3 << 12 (src/codepot.h:49-54) */
+    const int32_t* cip;     /* scalar kernels only, may be NULL: Cip_score::cip_score(m) by query
+                               position m in [0, a_right] (src/gsinfo.h:127-139; `sigB`,
+                               src/fwd2s1.cc:254,338 and 1191,1262) */
 } so_task;
 
 /* forwardS1_wip: returns number of SKL corners written to skl[2*i], skl[2*i+1]
@@ -160,6 +163,8 @@ typedef struct {
     int32_t a_exgl, a_exgr, b_exgl, b_exgr;     /* INEX flags, values 0..3 */
     int32_t lw, up;         /* WINDOW from stripe31 (width = up - lw + 7) */
     int32_t a_len;          /* Seq::len of the query (range check of mimd_postwork; driver only) */
+    const int32_t* cip;     /* scalar kernel only, may be NULL: Cip_score::cip_score(c) by coding
+                               position c = 3 m - phase in [0, 3 a_right + 1] (src/fwd2h1.cc:352-354) */
 } so_task_h;
 
 /* returns number of corners (want_trace) or 0; -1 allocation failure, -2 bad trace code */

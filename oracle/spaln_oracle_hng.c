@@ -2,7 +2,7 @@
  * spliced DP kernel, the one Aln2h1::trcbkalignH_ng falls back to for blocks with fewer than 8
  * query rows (src/fwd2h1.cc:2007) and the `-A0` kernel in general.
  *   src/fwd2h1.cc:143-202   initH_ng          src/fwd2h1.cc:204-292  lastH_ng
- *   src/fwd2h1.cc:294-617   forwardH_ng (cutrng == 0, cip == 0)
+ *   src/fwd2h1.cc:294-617   forwardH_ng (cutrng == 0)
  *   src/fwd2h1.cc:1997-2041 trcbkalignH_ng (scalar branch + end-point adjustment)
  *   src/codepot.cc:74-102   SpJunc::spjscr / spjseq, src/vmf.cc:66-140 Vmf
  * Pinned against the unmodified reference (tests/tools/sweep_oracle_scalar_p.py).
@@ -197,6 +197,9 @@ int so_trcbk_h_ng(const so_params_h* p, const so_ng_h* x, const so_task_h* t, in
                 nx[ph][l] = l;
             }
         int ncand[3] = { -1, -1, -1 };
+        int sigB[3] = { 0, 0, 0 };                  /* src/fwd2h1.cc:352-354 */
+        if (t->cip)
+            for (int phs = -1; phs < 2; ++phs) sigB[phs + 1] = t->cip[3 * m - phs];
         h_rvpd* h = hh[0] + r;
         h_rvpd* f = hh[1] + r;
         h_rvpd* f2 = dagp ? hh[2] + r : 0;
@@ -278,7 +281,7 @@ int so_trcbk_h_ng(const so_params_h* p, const so_ng_h* x, const so_task_h* t, in
                         const h_cand* phl = hl[phs + 1] + pnx[l];
                         if (phs == 1 && phl->dir == 2) continue;
                         if (nb - phl->jnc < x->minl) continue;
-                        xv = phl->val + spjscr_h(x, t, phl->jnc, nb);
+                        xv = phl->val + sigB[phs + 1] + spjscr_h(x, t, phl->jnc, nb);
                         if (phl->dir == 0 && phs) {
                             const uint8_t* cs = spjseq(x, t, phl->jnc, nb);
                             if (phs == 1) xv += qprof0[cs[0]];

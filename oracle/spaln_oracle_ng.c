@@ -4,7 +4,7 @@
  *
  * Reference code restated (paths relative to /root/reference):
  *   src/fwd2s1.cc:141-215   initS_ng / lastS_ng
- *   src/fwd2s1.cc:217-444   forwardS_ng (cutrng == 0, cip == 0)
+ *   src/fwd2s1.cc:217-444   forwardS_ng (cutrng == 0)
  *   src/fwd2s1.cc:1667-1710 trcbkalignS_ng (scalar branch + end-point adjustment)
  *   src/vmf.cc:66-140       Vmf::add / traceback
  *   src/codepot.cc:74-77, 401-416  SpJunc::spjscr, Exinon::sig53(IE5 | IE53), alprm2.Z == 0
@@ -104,6 +104,7 @@ int so_trcbk_ng(const so_params* p, const so_task* t, int32_t* score, int32_t* s
     if (!t->a_exgl) --m;
     for (++m; m <= a_right; ++m) {
         const int internal = spj && (!t->a_exgr || m < a_right);
+        const int sigB = t->cip ? t->cip[m] : 0;    /* src/fwd2s1.cc:254 */
         int n = (m - 1) + lw > b_left ? (m - 1) + lw : b_left;
         const int n9 = (m - 1) + up + 1 < b_right ? (m - 1) + up + 1 : b_right;
         const int32_t* qprof = p->simmtx + (size_t) t->a[m > 0 ? m - 1 : 0] * p->simdim;
@@ -162,7 +163,7 @@ int so_trcbk_ng(const so_params* p, const so_task* t, int32_t* score, int32_t* s
                 for (int l = 0; l <= ncand; ++l) {
                     const ng_cand* c = rcd + idx[l];
                     if (n - c->jnc < p->llmt) continue;
-                    const int x = c->val + spjscr(p, t, c->jnc, n);
+                    const int x = c->val + sigB + spjscr(p, t, c->jnc, n);
                     ng_rvp* to = hf[c->dir];
                     if (x >= to->val) { to->val = x; top[c->dir] = c; }
                 }
@@ -319,6 +320,7 @@ int so_scorealone_ng(const so_params* p, const so_task* t, int32_t* score)
         int idx[NG_NCAND + 1];
         for (int l = 0; l <= NG_NCAND; ++l) { rcd[l].val = NEVSEL32; rcd[l].dir = rcd[l].jnc = 0; idx[l] = l; }
         int ncand = -1, psp = 0;
+        const int sigB = t->cip ? t->cip[m] : 0;    /* src/fwd2s1.cc:1191 */
         while (++n <= n9) {
             const int r = n - m;
             int black = NEVSEL32;
@@ -356,7 +358,7 @@ int so_scorealone_ng(const so_params* p, const so_task* t, int32_t* score)
                 for (int l = 0; l <= ncand; ++l) {
                     const int j = idx[l];
                     if (n - rcd[j].jnc < p->llmt) continue;
-                    const int x = rcd[j].val + spjscr(p, t, rcd[j].jnc, n);
+                    const int x = rcd[j].val + sigB + spjscr(p, t, rcd[j].jnc, n);
                     if (x > *hf[rcd[j].dir]) { *hf[rcd[j].dir] = x; top[rcd[j].dir] = 1; }
                 }
                 for (int k = 0; k < nod; ++k) {

@@ -60,7 +60,7 @@ class GspalnTask(C.Structure):
         ("a_left", C.c_int32), ("a_right", C.c_int32), ("b_left", C.c_int32), ("b_right", C.c_int32),
         ("a_exgl", C.c_int32), ("a_exgr", C.c_int32), ("b_exgl", C.c_int32), ("b_exgr", C.c_int32),
         ("lw", C.c_int32), ("up", C.c_int32), ("skl_cap", C.c_int32), ("n_imd", C.c_int32),
-        ("int53", C.c_void_p),
+        ("int53", C.c_void_p), ("cip", C.c_void_p),
     ]
 
 
@@ -120,7 +120,7 @@ class GspalnHTask(C.Structure):
         ("a_left", C.c_int32), ("a_right", C.c_int32), ("b_left", C.c_int32), ("b_right", C.c_int32),
         ("a_exgl", C.c_int32), ("a_exgr", C.c_int32), ("b_exgl", C.c_int32), ("b_exgr", C.c_int32),
         ("lw", C.c_int32), ("up", C.c_int32), ("skl_cap", C.c_int32), ("n_imd", C.c_int32),
-        ("a_len", C.c_int32), ("int53", C.c_void_p),
+        ("a_len", C.c_int32), ("int53", C.c_void_p), ("cip", C.c_void_p),
     ]
 
 

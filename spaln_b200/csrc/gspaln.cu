@@ -399,6 +399,19 @@ int gspaln_set_ng_tables(gspaln_ctx* ctx, const int16_t* sig53tab, const int16_t
     return GSPALN_OK;
 }
 
+// Query bytes of one problem in the a pool: mw codes, the packed-kernel eligibility byte and, for
+// the exact-ILD kinds with a Cip_score table, the int32 bonuses of rows a_left .. a_right behind them
+static inline size_t cip_offset(const gspaln_task& t)
+{
+    const bool with = t.cip && (t.kind == GSPALN_FORWARD_NG || t.kind == GSPALN_SCOREALONE_NG);
+    return with ? align_up((size_t) (t.a_right - t.a_left) + 1, 4) : 0;
+}
+static inline size_t a_span(const gspaln_task& t)
+{
+    const size_t mw1 = (size_t) (t.a_right - t.a_left) + 1, at = cip_offset(t);
+    return align_up(at ? at + 4 * mw1 : mw1, 128);
+}
+
 // ---- planning: validation, longest-first order, pool offsets (assigned along that order so
 // that any contiguous range of the order is contiguous in every pool), workspaces, grids
 static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
@@ -450,11 +463,12 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         const int width = t.up - t.lw + 3;
         // 128-byte granules: a problem whose inputs arrive later never shares a cache line with
         // one that is already being read (one-shot submits stream the batch in)
-        d.a_off = (long long) a_bytes;      a_bytes += align_up((size_t) mw + 1, 128);
+        d.a_off = (long long) a_bytes;      a_bytes += a_span(t);
+        const size_t cip_at = cip_offset(t);
         d.col_off = (long long) c_elems;    c_elems += align_up((size_t) nw + 2, 16);
         const size_t bslab = align_up((size_t) width + 2 * NELEM, 32);
         d.skl_off = (long long) skl_elems;
-        d.pad1 = 0;
+        d.pad1 = (long long) cip_at;
         int cls = 8;
         if (t.kind == GSPALN_FORWARD_WIP || t.kind == GSPALN_SCOREONLY_WIP) {
             cls = wip_class(mw, width, dagp_prm);
@@ -628,6 +642,8 @@ static void pack_range(gspaln_ctx* ctx, const gspaln_task* tasks, int lo, int hi
             // the byte behind the query codes: this problem may run on the packed int16x2 kernel
             ap[mw] = (ctx->pk_ok && !(seen & ~PK_CODES) && sigmax <= PK_SIGMAX &&
                       (t.kind == GSPALN_FORWARD_WIP || t.kind == GSPALN_SCOREONLY_WIP)) ? 1 : 0;
+            if ((t.kind == GSPALN_FORWARD_NG || t.kind == GSPALN_SCOREALONE_NG) && d.pad1)
+                memcpy(ap + d.pad1, t.cip + t.a_left, sizeof(int32_t) * ((size_t) mw + 1));   // rows a_left .. a_right
         }
     };
     size_t work = 0;
@@ -660,7 +676,7 @@ static void pool_span(const gspaln_ctx* ctx, const gspaln_task* tasks, int lo, i
     const int li = ctx->h_order.p[hi - 1];
     const DevTask& l = ctx->h_tasks.p[li];
     a0 = (size_t) f.a_off; c0 = (size_t) f.col_off;
-    a1 = (size_t) l.a_off + align_up((size_t) (tasks[li].a_right - tasks[li].a_left) + 1, 128);
+    a1 = (size_t) l.a_off + a_span(tasks[li]);
     c1 = (size_t) l.col_off + align_up((size_t) (tasks[li].b_right - tasks[li].b_left) + 2, 16);
 }
 

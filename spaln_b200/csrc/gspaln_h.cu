@@ -623,6 +623,7 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
     std::vector<unsigned char> apool, bpool;
     std::vector<short> sgpool;
     std::vector<unsigned short> ipool;
+    std::vector<int> cippool;       // Cip_score words of the tasks that carry them
     size_t skl_elems = 0, work_bytes = 0;
     int64_t cells_total = 0;
     for (int i = 0; i < n; ++i) {
@@ -653,15 +654,21 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
             sgpool.insert(sgpool.end(), rec, rec + 8);
             ipool.push_back(in ? t.int53[p] : 0);
         }
+        d.cip_off = -1;
+        if (t.cip) {
+            // coding positions 3 a_left - 1 .. 3 a_right + 1 (3 m - phase of every row and splice phase)
+            d.cip_off = (long long) cippool.size();
+            for (int c = 3 * t.a_left - 1; c <= 3 * t.a_right + 1; ++c) cippool.push_back(c >= 0 ? t.cip[c] : 0);
+        }
         d.skl_off = (long long) skl_elems; skl_elems += (size_t) d.skl_cap;
         d.work_off = (long long) work_bytes;
         work_bytes += align_up((size_t) 3 * (width + 8) * sizeof(HCell) + (size_t) d.rec_cap * 12 + 16, 16);
     }
     unsigned char *d_a = nullptr, *d_b = nullptr, *d_work = nullptr;
-    short* d_sg = nullptr; unsigned short* d_i = nullptr; DevNgHTask* d_t = nullptr;
+    short* d_sg = nullptr; unsigned short* d_i = nullptr; DevNgHTask* d_t = nullptr; int* d_cip = nullptr;
     int2* d_skl = nullptr; DevResult* d_res = nullptr; int* d_tick = nullptr;
     auto freeall = [&] {
-        cudaFree(d_a); cudaFree(d_b); cudaFree(d_work); cudaFree(d_sg); cudaFree(d_i); cudaFree(d_t);
+        cudaFree(d_a); cudaFree(d_b); cudaFree(d_work); cudaFree(d_sg); cudaFree(d_i); cudaFree(d_t); cudaFree(d_cip);
         cudaFree(d_skl); cudaFree(d_res); cudaFree(d_tick);
     };
     cudaError_t e = cudaSuccess;
@@ -675,6 +682,7 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
     up((void**) &d_sg, sgpool.data(), sgpool.size() * sizeof(short));
     up((void**) &d_i, ipool.data(), ipool.size() * sizeof(unsigned short));
     up((void**) &d_t, dt.data(), dt.size() * sizeof(DevNgHTask));
+    up((void**) &d_cip, cippool.data(), cippool.size() * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**) &d_work, work_bytes + 16);
     if (e == cudaSuccess) e = cudaMalloc((void**) &d_skl, (skl_elems + 1) * sizeof(int2));
     if (e == cudaSuccess) e = cudaMalloc((void**) &d_res, (size_t) (n + 1) * sizeof(DevResult));
@@ -684,7 +692,7 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
     cudaEventRecord(ctx->ev[2], ctx->stream);
     const int grid = std::max(1, std::min((n + HNG_WARPS - 1) / HNG_WARPS, 4 * ctx->sm_count));
     dp_hxild_kernel<<<grid, HNG_THREADS, 0, ctx->stream>>>(ctx->d_ngprm.p, d_t, n, d_tick, d_a, d_b, d_sg, d_i,
-                                                         d_work, d_skl, d_res);
+                                                         d_cip, d_work, d_skl, d_res);
     cudaEventRecord(ctx->ev[3], ctx->stream);
     e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaGetLastError();

@@ -59,6 +59,7 @@ struct DevNgHTask {
     long long a_off, b_off;     // into the byte pools (element 0 == position a_lo / b_lo)
     long long sg_off;           // SGPT6 shorts (8 per column), int53: column b_lo first
     long long skl_off, work_off;    // corners (int2), workspace bytes
+    long long cip_off;          // Cip_score words from coding position 3 a_left - 1 on; -1: none
 };
 
 enum { F_SIG5, F_SIG3, F_SIGS, F_SIGT, F_SIGE, F_SIGI, F_PHS5, F_PHS3 };
@@ -66,6 +67,7 @@ enum { F_SIG5, F_SIG3, F_SIGS, F_SIGT, F_SIGE, F_SIGI, F_PHS5, F_PHS3 };
 // the inputs of one problem with the reference's indexing (positions, not offsets)
 struct HngIn {
     const unsigned char* a; const unsigned char* b; const short* sg; const unsigned short* i53;
+    const int* cip; int cip_lo;     // Cip_score::cip_score(c) = cip[c - cip_lo] (nullptr: none)
     int a_lo, b_lo, b_left, b_right;
     __device__ __forceinline__ int aa(int m) const { return a[m - a_lo]; }
     __device__ __forceinline__ int tron(int n) const { return b[n - b_lo]; }
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(HNG_THREADS)
 dp_hxild_kernel(const DevNgHParams* __restrict__ gP, const DevNgHTask* __restrict__ tasks, int ntasks, int* ticket,
                 const unsigned char* __restrict__ apool, const unsigned char* __restrict__ bpool,
                 const short* __restrict__ sgpool, const unsigned short* __restrict__ i53pool,
-                unsigned char* workpool, int2* sklpool, DevResult* results)
+                const int* __restrict__ cippool, unsigned char* workpool, int2* sklpool, DevResult* results)
 {
     __shared__ DevNgHParams P;
     __shared__ int warp_next[HNG_WARPS];
@@ -178,6 +180,7 @@ dp_hxild_kernel(const DevNgHParams* __restrict__ gP, const DevNgHTask* __restric
         HngIn T;
         T.a = apool + t.a_off; T.b = bpool + t.b_off; T.sg = sgpool + 8 * t.sg_off; T.i53 = i53pool + t.sg_off;
         T.a_lo = t.a_lo; T.b_lo = t.b_lo; T.b_left = t.b_left; T.b_right = t.b_right;
+        T.cip = t.cip_off >= 0 ? cippool + t.cip_off : nullptr; T.cip_lo = 3 * t.a_left - 1;
         const int a_exgl = t.a_exgl, a_exgr = t.a_exgr, b_exgl = t.b_exgl, b_exgr = t.b_exgr;
         const int width = t.up - t.lw + 7;
         const int nod = 2 * P.noll - 1;
@@ -272,6 +275,10 @@ dp_hxild_kernel(const DevNgHParams* __restrict__ gP, const DevNgHTask* __restric
             const int* prof_prev = P.mtx + (row ? T.aa(m > 0 ? m - 1 : 0) : 0) * P.simdim;  // residue the row pairs
             const int* prof_next = P.mtx + (row ? T.aa(m) : 0) * P.simdim;                  // the one after it
             bool started = false;
+            // bonus of an intron conserved with the query's annotation, by splice phase -1, 0, 1
+            int sigB[3] = {0, 0, 0};
+            if (T.cip && row)
+                for (int phs = -1; phs < 2; ++phs) sigB[phs + 1] = T.cip[3 * m - phs - T.cip_lo];
 
             for (int s = s_begin; s <= s_end; ++s) {
                 const int n = s - lane;
@@ -362,7 +369,7 @@ dp_hxild_kernel(const DevNgHParams* __restrict__ gP, const DevNgHTask* __restric
                             for (int l = 0; l < L.n; ++l) {
                                 const int k = L.st[l];
                                 if ((phs == 1 && k == 2) || nb - L.jnc[l] < P.minl) continue;
-                                int x = L.val[l] + hx_spjscr(P, T, L.jnc[l], nb);
+                                int x = L.val[l] + sigB[phs + 1] + hx_spjscr(P, T, L.jnc[l], nb);
                                 if (k == 0 && phs) {
                                     // the codon the intron splits is scored with its true translation
                                     const unsigned char* cs = hx_spjseq(P, T, L.jnc[l], nb);

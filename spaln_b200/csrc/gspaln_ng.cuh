@@ -170,6 +170,8 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
             continue;
         }
         const unsigned char* aseq = apool + t.a_off;        // aseq[i] pairs query row a_left + i + 1
+        // Cip_score of the rows (src/gsinfo.h:127-139), word i = row a_left + i; absent: no bonus
+        const int* cip = t.pad1 ? reinterpret_cast<const int*>(aseq + t.pad1) : nullptr;
         const ColInfo* cols = cpool + t.col_off;            // cols[j] is column b_left + j
         const int width = t.up - t.lw + 3;
         const bool a_exgl = t.flags & 1, a_exgr = t.flags & 2, b_exgl = t.flags & 4, b_exgr = t.flags & 8;
@@ -230,6 +232,7 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
             const int lo_up = ng_row_lo(t, m - 1), hi_up = ng_row_hi(t, m - 1);     // row above
             const bool has_up = lane > 0;                   // the row above belongs to this pass
             const int arow = (first || !row) ? ZROW : (int) aseq[m - 1 - a_left];
+            const int sigB = (cip && row) ? cip[m - a_left] : 0;    // bonus of an intron conserved at this row
             const int last_lane = min(31, a_right - m0);
             const int s_begin = ng_row_lo(t, m0) + 1;
             const int s_end = ng_row_hi(t, m0 + last_lane) + last_lane;
@@ -336,7 +339,7 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
                         for (int l = 0; l <= NG_NCAND; ++l) {
                             if (l >= L.n || n - L.jnc[l] < P.llmt) continue;
                             const int st = L.inf[l] & 15;
-                            const int x = L.val[l] + ng_spjscr(tabs, n_pen, L.inf[l] >> 4, n - L.jnc[l], col);
+                            const int x = L.val[l] + sigB + ng_spjscr(tabs, n_pen, L.inf[l] >> 4, n - L.jnc[l], col);
 #pragma unroll
                             for (int q = 0; q < 5; ++q) {
                                 if (q != st) continue;

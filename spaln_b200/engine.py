@@ -38,12 +38,14 @@ class Problem:
     skl_cap: int = 0        # 0: a_len + b_len + 8
     n_imd: int = 0          # hirschbergS1_wip only: number of intermediate rows
     int53: np.ndarray = None    # uint16 Exinon::int53[n] nibbles by column (scalar kernel only)
+    cip: np.ndarray = None      # int32 Cip_score::cip_score(m) by query position 0 .. a_right (optional)
 
     @staticmethod
     def from_export(ex: dict, lw: int, up: int) -> "Problem":
         """ex: tests/ref_harness.py::RefTask.export() layout (arrays start at at(-1))."""
         return Problem(int53=(np.ascontiguousarray(ex["int53"], np.uint16)
                               if ex.get("int53") is not None else None),
+                       cip=(np.ascontiguousarray(ex["cip"], np.int32) if ex.get("cip") is not None else None),
                        a=np.ascontiguousarray(ex["a"][1:], np.uint8),
                        b=np.ascontiguousarray(ex["b"][1:], np.uint8),
                        sig5=np.ascontiguousarray(ex["sig5"], np.int16),
@@ -175,12 +177,18 @@ class Engine:
                 i53 = np.ascontiguousarray(p.int53, np.uint16)
                 if len(i53) <= p.b_right:
                     raise ValueError("int53 shorter than the stated range")
-            keep.append((a, b, s5, s3, i53))
+            cip = None
+            if p.cip is not None:
+                cip = np.ascontiguousarray(p.cip, np.int32)
+                if len(cip) <= p.a_right:
+                    raise ValueError("cip shorter than the stated range")
+            keep.append((a, b, s5, s3, i53, cip))
             t = arr[i]
             t.kind = kind
             t.a, t.b = a.ctypes.data, b.ctypes.data
             t.sig5, t.sig3 = s5.ctypes.data, s3.ctypes.data
             t.int53 = i53.ctypes.data if i53 is not None else None
+            t.cip = cip.ctypes.data if cip is not None else None
             t.a_left, t.a_right, t.b_left, t.b_right = p.a_left, p.a_right, p.b_left, p.b_right
             t.a_exgl, t.a_exgr, t.b_exgl, t.b_exgr = p.a_exgl, p.a_exgr, p.b_exgl, p.b_exgr
             t.lw, t.up = p.lw, p.up
@@ -402,12 +410,14 @@ class ProblemH:
     a_len: int = 0          # Seq::len of the query (0: len(a) - 1, arrays carry one pad residue)
     n_imd: int = 0          # hirschbergH1_wip only: number of intermediate rows
     int53: np.ndarray = None    # uint16 Exinon::int53[n] nibbles by column (scalar kernel only)
+    cip: np.ndarray = None      # int32 Cip_score::cip_score(c) by coding position 0 .. 3 a_right + 1 (optional)
 
     @staticmethod
     def from_export(ex: dict, lw: int, up: int) -> "ProblemH":
         """ex: tests/ref_harness.py::RefTask.export_p() layout (arrays start at at(-1))."""
         return ProblemH(int53=(np.ascontiguousarray(ex["int53"], np.uint16)
                                if ex.get("int53") is not None else None),
+                        cip=(np.ascontiguousarray(ex["cip"], np.int32) if ex.get("cip") is not None else None),
                         a=np.ascontiguousarray(ex["a"][1:], np.uint8),
                         b=np.ascontiguousarray(ex["b"][1:], np.uint8),
                         sgpt6=capi.sgpt6_from_table(ex["sgpt6"]), b_len=int(ex["blen"]),
@@ -493,11 +503,17 @@ class EngineH:
             if len(a) < p.a_right or len(b) < p.b_right or p.b_len < p.b_right or len(sg) < p.b_len + 2:
                 raise ValueError("problem arrays shorter than the stated ranges")
             i53 = np.ascontiguousarray(p.int53, np.uint16) if p.int53 is not None else None
-            keep.append((a, b, sg, i53))
+            cip = None
+            if p.cip is not None:
+                cip = np.ascontiguousarray(p.cip, np.int32)
+                if len(cip) < 3 * p.a_right + 2:
+                    raise ValueError("cip shorter than the stated range")
+            keep.append((a, b, sg, i53, cip))
             t = arr[i]
             t.kind = kind
             t.a, t.b, t.sg = a.ctypes.data, b.ctypes.data, sg.ctypes.data
             t.int53 = i53.ctypes.data if i53 is not None else None
+            t.cip = cip.ctypes.data if cip is not None else None
             t.b_len = int(p.b_len)
             t.a_left, t.a_right, t.b_left, t.b_right = p.a_left, p.a_right, p.b_left, p.b_right
             t.a_exgl, t.a_exgr, t.b_exgl, t.b_exgr = p.a_exgl, p.a_exgr, p.b_exgl, p.b_exgr

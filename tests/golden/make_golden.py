@@ -36,6 +36,10 @@ CONFIGS = {
     "dna_A2_udh": ("-Q0 -A2 -S1 -yX0 -V256K -TDictyost", 15),
     "dna_A2_udh_local": ("-Q0 -A2 -S1 -yX0 -V256K -LS -TDictyost", 16),
     "dna_A6_udh_recursive": ("-Q0 -A6 -S1 -yX0 -V128K -TDictyost", 17),
+    # intron positions annotated on the query (Cip_score, src/gsinfo.h:127-139): read by the
+    # exact-ILD kernels only; small -V so that the driver reaches them through block re-alignment
+    "dna_A2_cip": ("-Q0 -A2 -S1 -yX0 -V256K -TDictyost", 31),
+    "prot_A2_cip": ("-Q0 -A2 -yX0 -V128K -TDictyost", 32),
     # protein query x genomic segment (SimdAln2h1::forwardH1_wip)
     "prot_A2_global": ("-Q0 -A2 -yX0 -TDictyost", 21),
     "prot_A2_local": ("-Q0 -A2 -yX0 -LS -TDictyost", 22),
@@ -44,6 +48,24 @@ CONFIGS = {
     "prot_A2_udh_local": ("-Q0 -A2 -yX0 -V128K -LS -TDictyost", 24),
     "prot_A6_udh_recursive": ("-Q0 -A6 -yX0 -V96K -TDictyost", 25),
 }
+
+
+def annotation(rng, qlen, truth, step):
+    """intron positions to annotate a query with (src/gsinfo.h:76-126): the true exon boundaries in
+    query coordinates (coding positions for a protein: step 3), a few neighbours of them and some
+    random positions, each with a multiplicity 1 .. 3.  Returns (positions, multiplicities), sorted."""
+    pos = set()
+    if truth is not None and len(truth) > 1:
+        acc = 0
+        for (s, e) in truth[:-1]:
+            acc += e - s
+            pos.add(acc)
+            if rng.random() < 0.5:
+                pos.add(acc + int(rng.integers(-2, 3)))
+    for _ in range(int(rng.integers(1, 6))):
+        pos.add(int(rng.integers(1, max(2, step * qlen))))
+    pos = sorted(x for x in pos if 0 < x < step * qlen)
+    return np.array(pos, np.int32), rng.integers(1, 4, size=len(pos)).astype(np.int32)
 
 
 def gen_protein(name: str):
@@ -58,14 +80,18 @@ def gen_protein(name: str):
     for k, v in p.items():
         out["prm_" + k] = np.asarray(v)
     n = 0
-    udh = "udh" in name
+    with_cip = "cip" in name
+    udh = "udh" in name or with_cip
     ng_tables = None
 
-    def add(g, q, tag="", **setkw):
+    def add(g, q, tag="", truth=None, **setkw):
         nonlocal n
         t = ref.task(g, q)
         if setkw:
             t.set(**setkw)
+        cip = None
+        if with_cip:
+            cip = t.set_cip(*annotation(rng, len(q), truth, 3))
         lw, up = t.stripe31(p["sh"])
         ex = t.export_p()
         r = t.kernel_p(lw, up, 0)
@@ -86,6 +112,8 @@ def gen_protein(name: str):
         out[pre + "int53"] = t.export_int53()
         out[pre + "ng_score"] = np.int32(rn["score"])
         out[pre + "ng_skl"] = rn["skl"].astype(np.int32)
+        if cip is not None:
+            out[pre + "cip"] = cip
         nonlocal ng_tables
         if ng_tables is None:
             ng_tables = t.export_ng_tables(1 << 17)
@@ -106,8 +134,18 @@ def gen_protein(name: str):
         t.close()
 
     for i in range(10):
-        g, q, _ = synth.plant_protein_gene(rng, plen_range=(20, 200), flank=(40, 250))
-        add(g, q, tag="gene")
+        g, q, tr = synth.plant_protein_gene(rng, plen_range=(20, 200), flank=(40, 250))
+        add(g, q, tag="gene", truth=tr)
+    if with_cip:
+        # a window of rows around an exon junction, all ends global: a post-work block
+        for k, (lo, hi) in enumerate(((2, 3), (1, 2), (3, 3), (2, 5), (4, 2), (1, 1))):
+            g, q, tr = synth.plant_protein_gene(rng, plen_range=(60, 120), n_exons=3, flank=(30, 90), sub=0)
+            j = k % 2
+            c = sum(e - s for s, e in tr[: j + 1])      # coding position of the junction
+            m = c // 3
+            add(g, q, tag=f"few{lo + hi}", truth=tr, a_left=m - lo, a_right=m + hi,
+                b_left=tr[j][1] - (c - 3 * (m - lo)), b_right=tr[j + 1][0] + (3 * (m + hi) - c),
+                a_exgl=0, a_exgr=0, b_exgl=0, b_exgr=0)
     g, q, _ = synth.plant_protein_gene(rng, plen_range=(80, 150), flank=(60, 200))
     add(g, q, tag="global_left", a_exgl=0, b_exgl=0)
     add(g, q, tag="global_right", a_exgr=0, b_exgr=0)
@@ -142,14 +180,18 @@ def gen(name: str):
     for k, v in p.items():
         out["prm_" + k] = np.asarray(v)
     probs = []
-    udh = "udh" in name
+    with_cip = "cip" in name
+    udh = "udh" in name or with_cip
     ng_tables = None
     scan_f = None
 
-    def add(g, q, comrev=False, tag="", **setkw):
+    def add(g, q, comrev=False, tag="", truth=None, **setkw):
         t = ref.task(g, q, comrev)
         if setkw:
             t.set(**setkw)
+        cip = None
+        if with_cip:
+            cip = t.set_cip(*annotation(rng, len(q), None if comrev else truth, 1))
         lw, up = t.stripe(p["sh"])
         ex = t.export()
         r = t.kernel(lw, up, 0, cap=1 << 16)
@@ -173,6 +215,8 @@ def gen(name: str):
         out[pre + "ng_score"] = np.int32(rn["score"])
         out[pre + "ng_skl"] = rn["skl"].astype(np.int32)
         out[pre + "ng_score_only"] = np.int32(t.scorealone(lw, up))     # Aln2s1::scorealoneS_ng
+        if cip is not None:
+            out[pre + "cip"] = cip
         nonlocal ng_tables, scan_f
         scan_f = t.scan_factors()
         if ng_tables is None or len(ng_tables["penalty"]) < ex["blen"] + 2:
@@ -197,11 +241,20 @@ def gen(name: str):
 
     # planted genes, both orientations of the query
     for i in range(10):
-        g, q, _ = synth.plant_gene(rng, qlen_range=(60, 900) if udh else (60, 500),
-                                   flank=(50, 900) if udh else (50, 300))
-        add(g, q, tag="gene")
+        g, q, tr = synth.plant_gene(rng, qlen_range=(60, 900) if udh else (60, 500),
+                                    flank=(50, 900) if udh else (50, 300))
+        add(g, q, tag="gene", truth=tr)
         if i % 3 == 0:
             add(g, q, comrev=True, tag="gene_rc")
+    if with_cip:
+        # few-row problems with introns: what the driver hands to the exact-ILD kernel
+        # (a window of rows around an exon junction, all ends global: a post-work block)
+        for k, (lo, hi) in enumerate(((3, 4), (2, 2), (1, 5), (4, 3), (3, 3), (6, 6), (2, 4), (5, 2))):
+            g, q, tr = synth.plant_gene(rng, qlen_range=(120, 300), n_exons=3, flank=(40, 120), sub=0, indel=0)
+            j = k % 2
+            J = sum(e - s for s, e in tr[: j + 1])
+            add(g, q, tag=f"few{lo + hi}", truth=tr, a_left=J - lo, a_right=J + hi,
+                b_left=tr[j][1] - lo, b_right=tr[j + 1][0] + hi, a_exgl=0, a_exgr=0, b_exgl=0, b_exgr=0)
     # end-gap variants and sub-ranges (UDH post-work style: all four flags 0)
     g, q, _ = synth.plant_gene(rng, qlen_range=(150, 300), flank=(60, 200))
     add(g, q, tag="global_left", a_exgl=0, b_exgl=0)

@@ -7,6 +7,8 @@ GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
 GOLDEN_NAMES = ["dna_A2_global", "dna_A2_local", "dna_A3_global", "dna_A2_tetrapod"]
 DAGP_NAMES = ["dna_A2_dagp"]        # double affine gaps (-yl3)
 UDH_NAMES = ["dna_A2_udh", "dna_A2_udh_local", "dna_A6_udh_recursive"]
+CIP_NAMES = ["dna_A2_cip"]          # queries annotated with intron positions (Cip_score)
+PROTEIN_CIP_NAMES = ["prot_A2_cip"]
 GEOM_KEYS = ["a_left", "a_right", "b_left", "b_right", "a_exgl", "a_exgr", "b_exgl", "b_exgr",
              "lw", "up"]
 
@@ -26,7 +28,7 @@ def load(name):
              "score_only": int(z[pre + "score_only"]), "tag": str(z[pre + "tag"])}
         d.update({k: int(v) for k, v in zip(GEOM_KEYS, z[pre + "geom"])})
         for k in ("lsp_score", "lsp_skl", "udh_nim", "udh_score", "udh_cpos", "udh_ranges",
-                  "int53", "ng_score", "ng_skl", "ng_score_only"):
+                  "int53", "ng_score", "ng_skl", "ng_score_only", "cip"):
             if pre + k in z.files:
                 v = z[pre + k]
                 d[k] = v if v.ndim else int(v)
@@ -55,7 +57,7 @@ def load_protein(name):
         d.update({k: int(v) for k, v in zip(GEOM_KEYS_P, z[pre + "geom"])})
         d.setdefault("alen", len(d["a"]) - 2)
         for k in ("lsp_score", "lsp_skl", "udh_nim", "udh_score", "udh_cpos", "udh_ranges",
-                  "int53", "ng_score", "ng_skl"):
+                  "int53", "ng_score", "ng_skl", "cip"):
             if pre + k in z.files:
                 v = z[pre + k]
                 d[k] = v if v.ndim else int(v)

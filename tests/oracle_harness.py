@@ -30,7 +30,7 @@ class SoTask(C.Structure):
         ("a", C.c_void_p), ("b", C.c_void_p), ("sig5", C.c_void_p), ("sig3", C.c_void_p),
         ("a_left", C.c_int32), ("a_right", C.c_int32), ("b_left", C.c_int32), ("b_right", C.c_int32),
         ("a_exgl", C.c_int32), ("a_exgr", C.c_int32), ("b_exgl", C.c_int32), ("b_exgr", C.c_int32),
-        ("lw", C.c_int32), ("up", C.c_int32), ("int53", C.c_void_p),
+        ("lw", C.c_int32), ("up", C.c_int32), ("int53", C.c_void_p), ("cip", C.c_void_p),
     ]
 
 
@@ -114,6 +114,10 @@ def make_task(t: dict):
         i53 = np.ascontiguousarray(t["int53"], np.uint16)
         st.int53 = i53.ctypes.data
         st._keep.append(i53)
+    if t.get("cip") is not None:
+        cip = np.ascontiguousarray(t["cip"], np.int32)
+        st.cip = cip.ctypes.data
+        st._keep.append(cip)
     return st
 
 
@@ -308,7 +312,7 @@ class SoTaskH(C.Structure):
     _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("sgpt6", C.c_void_p), ("b_len", C.c_int32),
                 ("a_left", C.c_int32), ("a_right", C.c_int32), ("b_left", C.c_int32), ("b_right", C.c_int32),
                 ("a_exgl", C.c_int32), ("a_exgr", C.c_int32), ("b_exgl", C.c_int32), ("b_exgr", C.c_int32),
-                ("lw", C.c_int32), ("up", C.c_int32), ("a_len", C.c_int32)]
+                ("lw", C.c_int32), ("up", C.c_int32), ("a_len", C.c_int32), ("cip", C.c_void_p)]
 
 
 def _params_h(p: dict):
@@ -342,6 +346,10 @@ def _task_h(t: dict):
     for k in ("a_left", "a_right", "b_left", "b_right", "a_exgl", "a_exgr", "b_exgl", "b_exgr", "lw", "up"):
         setattr(st, k, int(t[k]))
     st._keep = (a, b, g)
+    if t.get("cip") is not None:
+        cip = np.ascontiguousarray(t["cip"], np.int32)
+        st.cip = cip.ctypes.data
+        st._keep = (a, b, g, cip)
     return st
 
 

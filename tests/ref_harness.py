@@ -320,6 +320,21 @@ class RefTask:
         n = self.lib.ref_task_scalar_p(self.h, lw, up, C.byref(score), skl.ctypes.data, cap)
         return {"score": score.value, "skl": skl[:n].copy()}
 
+    def set_cip(self, pos, num=None):
+        """annotate the query with intron positions (a `;B` / `;b` block, src/gsinfo.h:76-126);
+        returns Cip_score::cip_score(c) for every position c the kernels may ask for"""
+        pos = np.ascontiguousarray(pos, np.int32)
+        num = np.ascontiguousarray(num if num is not None else np.ones(len(pos)), np.int32)
+        self.lib.ref_task_set_cip.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        self.lib.ref_task_set_cip.restype = None
+        self.lib.ref_task_set_cip(self.h, pos.ctypes.data, num.ctypes.data, len(pos))
+        n = 3 * (int(self.info()["alen"]) + 2)
+        tab = np.zeros(n, np.int32)
+        self.lib.ref_task_cip_table.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self.lib.ref_task_cip_table.restype = None
+        self.lib.ref_task_cip_table(self.h, tab.ctypes.data, n)
+        return tab
+
     def scorealone(self, lw, up):
         """Aln2s1::scorealoneS_ng (scalar score-only kernel)"""
         self.lib.ref_task_scorealone.argtypes = [C.c_void_p, C.c_int, C.c_int]

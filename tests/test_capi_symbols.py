@@ -36,10 +36,10 @@ def test_struct_layouts_match_header():
     from spaln_b200 import capi
     # sizes implied by include/gspaln.h on LP64
     assert ctypes.sizeof(capi.GspalnParams) == 4 * (8 + 8 + 8 + 5) + 4 * 32 * 32
-    assert ctypes.sizeof(capi.GspalnTask) == 8 + 4 * 8 + 4 * 12 + 8     # ... + int53 pointer
+    assert ctypes.sizeof(capi.GspalnTask) == 8 + 4 * 8 + 4 * 12 + 8 + 8     # ... + int53, cip pointers
     assert ctypes.sizeof(capi.GspalnResult) == 32 + 16 + 8
     assert ctypes.sizeof(capi.GspalnHParams) == 4 * (10 + 8 + 8 + 4) + 4 * 32 * 32 + 4 * 3
-    assert ctypes.sizeof(capi.GspalnHTask) == 8 + 3 * 8 + 4 * 14 + 8     # ... + int53 pointer
+    assert ctypes.sizeof(capi.GspalnHTask) == 8 + 3 * 8 + 4 * 14 + 8 + 8     # ... + int53, cip pointers
     assert capi.SGPT6_DTYPE.itemsize == 14
 
 

@@ -205,7 +205,7 @@ def test_hirschberg_wip_matches_oracle_seeded(oracle, flags, fixture):
 # ---------------------------------------------------------------------------
 # scalar exact-ILD kernel: Aln2s1::trcbkalignS_ng's scalar branch (forwardS_ng + Vmf)
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("name", golden_io.GOLDEN_NAMES + golden_io.DAGP_NAMES + golden_io.UDH_NAMES)
+@pytest.mark.parametrize("name", golden_io.GOLDEN_NAMES + golden_io.DAGP_NAMES + golden_io.UDH_NAMES + golden_io.CIP_NAMES)
 def test_scalar_kernel_matches_reference_golden(name):
     prm, probs = golden_io.load(name)
     eng = _engine(prm)
@@ -243,7 +243,33 @@ def test_scalar_kernel_matches_oracle_seeded(oracle, name, flags, sub):
     eng.close()
 
 
-@pytest.mark.parametrize("name", golden_io.GOLDEN_NAMES + golden_io.DAGP_NAMES)
+@pytest.mark.parametrize("name", ["dna_A2_global", "dna_A2_dagp", "dna_A2_local"])
+def test_exact_ild_kernels_with_cip_score_match_oracle(oracle, name):
+    """Cip_score (gspaln_task.cip; src/gsinfo.h:127-139, `sigB` at src/fwd2s1.cc:254,338,1191,1262):
+    seeded problems with a random bonus table by query position, trace-back and score-only"""
+    prm, _ = golden_io.load(name)
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(("cip" + name).encode()))
+    probs = _synthetic(prm, rng, 30, (3, 8), (20, 2500), flags=(0, 0, 0, 0))
+    probs += _synthetic(prm, rng, 20, (30, 300), (30, 400))
+    for pb in probs:
+        tab = np.zeros(len(pb["a"]) + 2, np.int32)
+        k = rng.integers(0, len(tab), size=max(2, len(tab) // 8))
+        tab[k] = rng.integers(1, 4, size=len(k)) * 20 * int(prm.get("scale", 10)) // 10
+        pb["cip"] = tab
+    eng = _engine(prm)
+    n_diff = 0
+    for i, (pb, r) in enumerate(zip(probs, eng.forwardS_ng(_problems(probs)))):
+        o = oracle.trcbk_ng(prm, pb)
+        assert r.status == 0 and r.score == o["score"] and np.array_equal(r.skl, o["skl"]), (name, i)
+        n_diff += o["score"] != oracle.trcbk_ng(prm, dict(pb, cip=None))["score"]
+    assert n_diff >= 10, n_diff
+    for i, (pb, r) in enumerate(zip(probs, eng.scorealoneS_ng(_problems(probs)))):
+        assert r.status == 0 and r.score == oracle.scorealone_ng(prm, pb)["score"], (name, i)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", golden_io.GOLDEN_NAMES + golden_io.DAGP_NAMES + golden_io.CIP_NAMES)
 def test_scalar_scoreonly_kernel_matches_reference_and_oracle(oracle, name):
     """Aln2s1::scorealoneS_ng on the device: reference goldens (any size: three int rows of
     workspace per problem), then seeded problems against the oracle"""
@@ -294,7 +320,7 @@ def test_scalar_kernel_needs_its_tables():
 # ---------------------------------------------------------------------------
 # the whole driver: lspS_ng (trace-back vs UDH dispatch + block re-alignment)
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["dna_A2_udh", "dna_A6_udh_recursive", "dna_A2_global", "dna_A2_udh_local"])
+@pytest.mark.parametrize("name", ["dna_A2_udh", "dna_A6_udh_recursive", "dna_A2_global", "dna_A2_udh_local", "dna_A2_cip"])
 def test_lsp_driver_matches_reference_golden(oracle, name):
     prm, probs = golden_io.load(name)
     eng = _engine(prm)

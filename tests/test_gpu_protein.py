@@ -86,7 +86,7 @@ def test_forwardH1_wip_matches_oracle_on_random_problems(oracle, case):
     eng.close()
 
 
-@pytest.mark.parametrize("name", golden_io.PROTEIN_NAMES + golden_io.PROTEIN_UDH_NAMES)
+@pytest.mark.parametrize("name", golden_io.PROTEIN_NAMES + golden_io.PROTEIN_UDH_NAMES + golden_io.PROTEIN_CIP_NAMES)
 def test_lspH_ng_driver_matches_reference_and_oracle(oracle, name):
     """gspaln_h_lsp: Aln2h1::lspH_ng (dispatch, Hirschberg passes, block re-alignment) at the
     reference's default -V (every golden problem takes the trace-back route) and at the
@@ -199,7 +199,7 @@ def test_protein_batch_properties_full_size_and_streamed_submit():
     eng.close()
 
 
-@pytest.mark.parametrize("name", golden_io.PROTEIN_NAMES + golden_io.PROTEIN_UDH_NAMES)
+@pytest.mark.parametrize("name", golden_io.PROTEIN_NAMES + golden_io.PROTEIN_UDH_NAMES + golden_io.PROTEIN_CIP_NAMES)
 def test_scalar_protein_kernel_matches_reference_and_oracle(oracle, name):
     """gspaln_h_submit(GSPALN_FORWARD_NG): Aln2h1::trcbkalignH_ng on its scalar branch (forwardH_ng +
     Vmf) against the reference fixtures and, on seeded tiny problems, against the oracle"""

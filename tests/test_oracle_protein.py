@@ -20,7 +20,7 @@ def test_oracle_protein_matches_reference_golden(oracle, name):
     assert max(len(pb["skl"]) for pb in probs) >= 6
 
 
-@pytest.mark.parametrize("name", golden_io.PROTEIN_UDH_NAMES)
+@pytest.mark.parametrize("name", golden_io.PROTEIN_UDH_NAMES + golden_io.PROTEIN_CIP_NAMES)
 def test_oracle_protein_udh_and_driver_match_reference_golden(oracle, name):
     """hirschbergH1_wip (crossing records, narrowed ranges) and the whole driver Aln2h1::lspH_ng
     (trace-back vs Hirschberg dispatch + block re-alignment) against the reference's outputs"""
@@ -46,7 +46,7 @@ def test_oracle_protein_udh_and_driver_match_reference_golden(oracle, name):
     assert n_udh >= 10 and n_lsp >= 15
 
 
-@pytest.mark.parametrize("name", golden_io.PROTEIN_NAMES + golden_io.PROTEIN_UDH_NAMES)
+@pytest.mark.parametrize("name", golden_io.PROTEIN_NAMES + golden_io.PROTEIN_UDH_NAMES + golden_io.PROTEIN_CIP_NAMES)
 def test_oracle_scalar_protein_kernel_matches_reference_golden(oracle, name):
     """Aln2h1::trcbkalignH_ng on its scalar branch (forwardH_ng + initH_ng / lastH_ng + Vmf,
     split-codon translation): the kernel the reference uses for blocks with fewer than 8 rows"""
