@@ -911,9 +911,20 @@ static void so_stripe(so_task* t, int sh)
     t->up = up; t->lw = lw;
 }
 
-static int gap_ext_pen(const so_params* p, int i) { (void) i; return p->gep; }   /* codonk1 == LARGEN */
-static int gap_penalty(const so_params* p, int i) { return i == 0 ? 0 : p->gop + i * p->gep; }
-static int unp_penalty(const so_params* p, int d) { return d * p->gep; }
+/* PwdB::GapExtPen / GapPenalty / UnpPenalty (src/aln.h:275-287); codonk1 is LARGEN unless the gap
+ * penalty is double affine; so_params.codonk1 == 0 (a fixture without it) means the same */
+static int drv_k1(const so_params* p) { return (p->noll == 3 && p->codonk1 > 0) ? p->codonk1 : INT_MAX; }
+static int gap_ext_pen(const so_params* p, int i) { return i > drv_k1(p) ? p->lgep : p->gep; }
+static int gap_penalty(const so_params* p, int i)
+{
+    if (i == 0) return 0;
+    return i > drv_k1(p) ? p->lgop + i * p->lgep : p->gop + i * p->gep;
+}
+static int unp_penalty(const so_params* p, int d)
+{
+    const int unp = d * p->gep;
+    return d <= drv_k1(p) ? unp : unp + (p->lgep - p->gep) * (d - drv_k1(p));
+}
 
 static int drv_trcbk(so_drv* d, const so_task* t)
 {
