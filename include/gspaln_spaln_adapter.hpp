@@ -235,6 +235,39 @@ public:
         return (VTYPE) r.score;
     }
 
+    // == Aln2s1::trcbkalignS_ng(wdw) on its scalar branch (src/fwd2s1.cc:1676-1706): forwardS_ng +
+    // Vmf::traceback + the start-point adjustment -- every trace-back of `-A0`, and the blocks with
+    // fewer than 8 query rows of the other modes.  Needs enable_scalar() and the segment's INT53
+    // array.  false: the kernel ran out of path records (the caller runs the stock code).
+    bool forwardS_ng(const Seq** seqs, const WINDOW& wdw, Mfile* mfd, const INT53* int53, VTYPE* scr,
+                     const Cip_score* cip = 0)
+    {
+        gspaln_task t;
+        gspaln_result r;
+        Scratch s;
+        fill(t, s, seqs, wdw, GSPALN_FORWARD_NG);
+        if (int53) {
+            pack_int53(s.int53, int53, seqs[1]);
+            t.int53 = s.int53.data();
+        }
+        fill_cip(t, s, seqs[0], cip);
+        int cap = 256;
+        for (;;) {
+            s.skl.assign(2 * (size_t) cap, 0);
+            t.skl_cap = cap;
+            memset(&r, 0, sizeof(r));
+            r.skl = s.skl.data();
+            int rc = gspaln_queue_submit(q_, &t, &r);
+            if (rc != GSPALN_OK) die("gspaln_submit", rc, ctx_);
+            if (r.status != GSPALN_ST_SKL_OVERFLOW) break;
+            cap = r.n_skl + 8;
+        }
+        if (r.status != GSPALN_ST_OK) return false;
+        write_corners(mfd, s.skl, r.n_skl);
+        *scr = (VTYPE) r.score;
+        return true;
+    }
+
     // == Aln2s1::scorealoneS_ng(wdw): what HomScoreS_ng runs for queries shorter than 4 residues
     // (src/fwd2s1.cc:2704-2705).  Needs enable_scalar() and the segment's INT53 array.
     VTYPE scorealoneS_ng(const Seq** seqs, const WINDOW& wdw, const INT53* int53, const Cip_score* cip = 0)
@@ -271,6 +304,16 @@ class SpalnEngineH {
         std::vector<int> skl;
         std::vector<int32_t> cip;
     };
+
+    // gspaln_h_task.cip: Cip_score::cip_score(c) by coding position c = 3 m - phase (src/fwd2h1.cc:352-354)
+    static void fill_cip(gspaln_h_task& t, Scratch& s, const Seq* a, const Cip_score* cip)
+    {
+        if (!cip) return;
+        s.cip.assign((size_t) 3 * a->right + 2, 0);
+        for (int c = std::max(0, 3 * a->left - 1); c <= 3 * a->right + 1; ++c)
+            s.cip[c] = (int32_t) cip->cip_score(c);
+        t.cip = s.cip.data();
+    }
 
     // one task == what the SimdAln2h1 constructor dereferences (src/fwd2h1_simd.h:196-382): the
     // SGPT6 array is taken as it is (gspaln_sgpt6 has the layout of src/codepot.h:34-43)
@@ -370,6 +413,37 @@ public:
         return (VTYPE) r.score;
     }
 
+    // == Aln2h1::trcbkalignH_ng(wdw) on its scalar branch (src/fwd2h1.cc:2007-2037): forwardH_ng +
+    // Vmf::traceback + the start-point adjustment; mfd == 0: the score alone (HomScoreH_ng under
+    // `-A0` and for queries shorter than 8 residues, src/fwd2h1.cc:3297-3298 -- the score does not
+    // depend on the path records).  false: out of path records (the caller runs the stock code).
+    bool forwardH_ng(const Seq** seqs, const WINDOW& wdw, Mfile* mfd, const INT53* int53, VTYPE* scr,
+                     const Cip_score* cip = 0)
+    {
+        gspaln_h_task t;
+        gspaln_result r;
+        Scratch s;
+        fill(t, seqs, wdw, GSPALN_FORWARD_NG);
+        pack_int53(s.int53, int53, seqs[1]);
+        t.int53 = s.int53.data();
+        fill_cip(t, s, seqs[0], cip);
+        int cap = 256;
+        for (;;) {
+            s.skl.assign(2 * (size_t) cap, 0);
+            t.skl_cap = cap;
+            memset(&r, 0, sizeof(r));
+            r.skl = s.skl.data();
+            int rc = gspaln_h_queue_submit(q_, &t, &r);
+            if (rc != GSPALN_OK) die("gspaln_h_submit", rc, ctx_);
+            if (r.status != GSPALN_ST_SKL_OVERFLOW || !mfd) break;
+            cap = r.n_skl + 8;
+        }
+        if (r.status != GSPALN_ST_OK && !(r.status == GSPALN_ST_SKL_OVERFLOW && !mfd)) return false;
+        if (mfd) write_corners(mfd, s.skl, r.n_skl);
+        *scr = (VTYPE) r.score;
+        return true;
+    }
+
     // == Aln2h1::lspH_ng(wdw) with the corners appended to mfd (src/fwd2h1.cc:2134-2230); false:
     // the problem needs a kernel that is not on the device (the caller runs the stock lspH_ng)
     bool lspH_ng(const Seq** seqs, const WINDOW& wdw, Mfile* mfd, const INT53* int53, VTYPE* scr,
@@ -383,14 +457,7 @@ public:
             pack_int53(s.int53, int53, seqs[1]);
             t.int53 = s.int53.data();
         }
-        if (cip) {
-            // gspaln_h_task.cip: by coding position 3 m - phase (src/fwd2h1.cc:352-354)
-            const Seq* a = seqs[0];
-            s.cip.assign((size_t) 3 * a->right + 2, 0);
-            for (int c = std::max(0, 3 * a->left - 1); c <= 3 * a->right + 1; ++c)
-                s.cip[c] = (int32_t) cip->cip_score(c);
-            t.cip = s.cip.data();
-        }
+        fill_cip(t, s, seqs[0], cip);
         const gspaln_lsp_opts o = lsp_opts_now();
         int cap = 256;
         for (;;) {

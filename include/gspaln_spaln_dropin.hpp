@@ -28,6 +28,7 @@
 #include "gspaln_spaln_adapter.hpp"
 
 #include <cstdio>
+#include <atomic>
 #include <map>
 #include <mutex>
 
@@ -62,6 +63,35 @@ inline int device_index()
 }
 
 inline std::mutex& registry_mutex() { static std::mutex m; return m; }
+
+// Calls answered by the device, by hook.  GSPALN_DROPIN_STATS=1 prints them to stderr at exit (what
+// the whole-program tests read to prove that a run went through the CUDA kernels).
+struct HookStats {
+    enum { LSP, TRCBK_WIP, TRCBK_EXACT, HOM_WIP, HOM_EXACT, EXACT_NO_TABLES, EXACT_OVERFLOW, N };
+    std::atomic<long long> n[2][N];
+    HookStats()
+    {
+        for (auto& row : n) for (auto& c : row) c = 0;
+        if (getenv("GSPALN_DROPIN_STATS")) atexit(report);
+    }
+    static HookStats& get() { static HookStats s; return s; }
+    static void report()
+    {
+        static const char* names[N] = {"lsp", "trcbk_wip", "trcbk_exact", "homscore_wip", "homscore_exact",
+                                       "exact_no_tables", "exact_overflow"};
+        HookStats& s = get();
+        for (int p = 0; p < 2; ++p) {
+            fprintf(stderr, "gspaln drop-in (%s):", p ? "protein" : "dna");
+            for (int k = 0; k < N; ++k) fprintf(stderr, " %s=%lld", names[k], (long long) s.n[p][k]);
+            fputc('\n', stderr);
+        }
+    }
+};
+inline bool counted(bool ok, int protein, int what)
+{
+    if (ok) ++HookStats::get().n[protein][what];
+    return ok;
+}
 
 // split-codon tables of SpJunc::spjseq (src/codepot.h:130-190) and aa2nuc (src/seq.cc:76) in the
 // layout of gspaln_h_set_ng_tables
@@ -104,9 +134,17 @@ inline SpalnEngineH* engineH(const PwdB* pwd, const Seq* b)
     return e;
 }
 
-// what the device covers: the `_wip` formulation (-A2 / -A3: simd >= 2).  Cip_score (queries annotated
-// with intron positions) is read by the exact-ILD kernels only and travels with the task
+// What the device covers.  Drivers (lsp*_ng): the `_wip` formulation, -A2 / -A3 (simd >= 2).
+// Kernels behind trcbkalign*_ng / HomScore*_ng: the `_wip` kernels for simd >= 2, the exact-ILD
+// kernels for every call the reference sends to its scalar code -- all of `-A0` (simd == 0, the
+// reference's default) and blocks with fewer than 8 query rows in any mode; the Hirschberg passes
+// of `-A0` and the int16 exact-ILD kernels of `-A1` stay with the stock code.  Cip_score (queries
+// annotated with intron positions) is read by the exact-ILD kernels only and travels with the task.
 inline bool covered(int simd, const Cip_score*) { return simd >= 2; }
+inline bool exact_tables_ok(const Seq* b, bool same_tab)
+{
+    return !b->inex.intr || (int53_of(b) && same_tab && b->right - b->left < MAX_SEGMENT);
+}
 
 // ---------------------------------------------------------------------------------- DNA hooks
 inline bool lspS(const Seq** seqs, const PwdB* pwd, const WINDOW& wdw, Mfile* mfd, int simd,
@@ -116,17 +154,28 @@ inline bool lspS(const Seq** seqs, const PwdB* pwd, const WINDOW& wdw, Mfile* mf
     const Seq* b = seqs[1];
     SpalnEngine* e = engineS(pwd, b);
     const INT53* i53 = (b->inex.intr && e->same_sig53tab(sig53tab_of(b))) ? int53_of(b) : 0;
-    return e->lspS_ng(seqs, wdw, mfd, i53, scr, cip);
+    return counted(e->lspS_ng(seqs, wdw, mfd, i53, scr, cip), 0, HookStats::LSP);
 }
 
 inline bool trcbkS(const Seq** seqs, const PwdB* pwd, const WINDOW& wdw, Mfile* mfd, int simd,
                    const Cip_score* cip, const RANGE* mc, VTYPE* scr)
 {
-    // the SIMD branch of trcbkalignS_ng (src/fwd2s1.cc:1680-1685); m < 8 and the cut-range
-    // variant stay with the stock scalar code
-    if (!covered(simd, cip) || mc || wdw.width < 0 || seqs[0]->right - seqs[0]->left < 8) return false;
-    *scr = engineS(pwd, seqs[1])->forwardS1_wip(seqs, wdw, mfd);
-    return true;
+    // trcbkalignS_ng (src/fwd2s1.cc:1667-1710): its SIMD branch for -A2 / -A3, its scalar branch
+    // (forwardS_ng + Vmf) for -A0 and for m < 8; the cut-range variant and -A1's forwardS1 stay
+    // with the stock code
+    if (mc || wdw.width < 0) return false;
+    const Seq* b = seqs[1];
+    const int m = seqs[0]->right - seqs[0]->left;
+    if (simd >= 2 && m >= 8) {
+        *scr = engineS(pwd, b)->forwardS1_wip(seqs, wdw, mfd);
+        return counted(true, 0, HookStats::TRCBK_WIP);
+    }
+    if (simd != 0 && m >= 8) return false;
+    if (m < 1 || b->right <= b->left || !b->inex.intr) return false;
+    SpalnEngine* e = engineS(pwd, b);
+    if (!exact_tables_ok(b, e->same_sig53tab(sig53tab_of(b)))) return !counted(true, 0, HookStats::EXACT_NO_TABLES);
+    if (counted(e->forwardS_ng(seqs, wdw, mfd, int53_of(b), scr, cip), 0, HookStats::TRCBK_EXACT)) return true;
+    return !counted(true, 0, HookStats::EXACT_OVERFLOW);
 }
 
 inline bool homscoreS(const Seq** seqs, const PwdB* pwd, VTYPE* scr)
@@ -134,12 +183,12 @@ inline bool homscoreS(const Seq** seqs, const PwdB* pwd, VTYPE* scr)
     const int simd = algmode.alg & 3;
     const Seq* a = seqs[0];
     const Seq* b = seqs[1];
-    if (simd < 2) return false;
+    if (simd == 1 && a->right - a->left >= 4) return false;     // -A1: scoreonlyS1, stock code
     if (simd == 3) IntronPrm.nquant = 1;        // what the Aln2s1 constructor does (src/fwd2s1.cc:125)
     WINDOW wdw;
     stripe(seqs, &wdw, alprm.sh);
     SpalnEngine* e = engineS(pwd, b);
-    if (a->right - a->left < 4) {               // src/fwd2s1.cc:2704-2705
+    if (simd == 0 || a->right - a->left < 4) {  // src/fwd2s1.cc:2704-2705
         if (b->inex.intr && !(int53_of(b) && e->same_sig53tab(sig53tab_of(b)))) return false;
         if (!b->inex.intr || b->right - b->left >= MAX_SEGMENT) return false;
         if (a->sigII) {                         // the Aln2s1 constructor's Cip_score (src/fwd2s1.cc:124)
@@ -147,10 +196,10 @@ inline bool homscoreS(const Seq** seqs, const PwdB* pwd, VTYPE* scr)
             *scr = e->scorealoneS_ng(seqs, wdw, int53_of(b), &cs);
         } else
             *scr = e->scorealoneS_ng(seqs, wdw, int53_of(b));
-        return true;
+        return counted(true, 0, HookStats::HOM_EXACT);
     }
     *scr = e->scoreonlyS1_wip(seqs, wdw);
-    return true;
+    return counted(true, 0, HookStats::HOM_WIP);
 }
 
 // ------------------------------------------------------------------------------ protein hooks
@@ -161,18 +210,26 @@ inline bool lspH(const Seq** seqs, const PwdB* pwd, const WINDOW& wdw, Mfile* mf
     if (!covered(simd, cip) || !b->exin || !b->exin->data_p) return false;
     SpalnEngineH* e = engineH(pwd, b);
     const INT53* i53 = (b->inex.intr && e->same_sig53tab(sig53tab_of(b))) ? int53_of(b) : 0;
-    return e->lspH_ng(seqs, wdw, mfd, i53, scr, cip);
+    return counted(e->lspH_ng(seqs, wdw, mfd, i53, scr, cip), 1, HookStats::LSP);
 }
 
 inline bool trcbkH(const Seq** seqs, const PwdB* pwd, const WINDOW& wdw, Mfile* mfd, int simd,
-                   const Cip_score* cip, const RANGE* mc, VTYPE* scr)
+                   const Cip_score* cip, bool spj, const RANGE* mc, VTYPE* scr)
 {
+    // trcbkalignH_ng (src/fwd2h1.cc:1997-2041): SIMD branch for -A2 / -A3, scalar branch (forwardH_ng
+    // + Vmf) for -A0 and m < 8, there only with the splice switch the engine was frozen with
     const Seq* b = seqs[1];
-    if (!covered(simd, cip) || mc || wdw.width < 0 || seqs[0]->right - seqs[0]->left < 8 ||
-        !b->exin || !b->exin->data_p)
-        return false;
-    *scr = engineH(pwd, b)->forwardH1_wip(seqs, wdw, mfd);
-    return true;
+    if (mc || wdw.width < 0 || !b->exin || !b->exin->data_p) return false;
+    const int m = seqs[0]->right - seqs[0]->left;
+    if (simd >= 2 && m >= 8) {
+        *scr = engineH(pwd, b)->forwardH1_wip(seqs, wdw, mfd);
+        return counted(true, 1, HookStats::TRCBK_WIP);
+    }
+    if ((simd != 0 && m >= 8) || m < 1 || b->right <= b->left || !b->inex.intr || !spj) return false;
+    SpalnEngineH* e = engineH(pwd, b);
+    if (!exact_tables_ok(b, e->same_sig53tab(sig53tab_of(b)))) return !counted(true, 1, HookStats::EXACT_NO_TABLES);
+    if (counted(e->forwardH_ng(seqs, wdw, mfd, int53_of(b), scr, cip), 1, HookStats::TRCBK_EXACT)) return true;
+    return !counted(true, 1, HookStats::EXACT_OVERFLOW);
 }
 
 inline bool homscoreH(const Seq** seqs, const PwdB* pwd, VTYPE* scr)
@@ -180,13 +237,23 @@ inline bool homscoreH(const Seq** seqs, const PwdB* pwd, VTYPE* scr)
     const int simd = algmode.alg & 3;
     const Seq* a = seqs[0];
     const Seq* b = seqs[1];
-    if (simd < 2 || !b->exin || !b->exin->data_p) return false;
-    if (a->right - a->left < 8) return false;   // forwardH_ng score: stock scalar code (src/fwd2h1.cc:3298)
+    if (!b->exin || !b->exin->data_p) return false;
     if (simd == 3) IntronPrm.nquant = 1;
     WINDOW wdw;
     stripe31(seqs, &wdw, alprm.sh);
+    if (simd == 0 || a->right - a->left < 8) {  // forwardH_ng's score (src/fwd2h1.cc:3297-3298)
+        if (!b->inex.intr || a->right <= a->left || b->right <= b->left || wdw.up - wdw.lw + 7 < 0) return false;
+        SpalnEngineH* e = engineH(pwd, b);
+        if (!exact_tables_ok(b, e->same_sig53tab(sig53tab_of(b)))) return false;
+        if (a->sigII) {
+            const Cip_score cs(a);
+            return counted(e->forwardH_ng(seqs, wdw, 0, int53_of(b), scr, &cs), 1, HookStats::HOM_EXACT);
+        }
+        return counted(e->forwardH_ng(seqs, wdw, 0, int53_of(b), scr), 1, HookStats::HOM_EXACT);
+    }
+    if (simd < 2) return false;                 // -A1: forwardH1, stock code
     *scr = engineH(pwd, b)->forwardH1_wip(seqs, wdw, 0);
-    return true;
+    return counted(true, 1, HookStats::HOM_WIP);
 }
 
 #ifdef GSPALN_HARVEST
@@ -350,7 +417,7 @@ inline void harvest_after(bool protein, const Seq** seqs, const PwdB* pwd, const
 #define GSPALN_HOOK_TRCBKS { VTYPE s_; if (gspaln::dropin::trcbkS(seqs, pwd, wdw, mfd, simd, cip, mc, &s_)) return s_; }
 #define GSPALN_HOOK_HOMS   { VTYPE s_; if (gspaln::dropin::homscoreS(seqs, pwd, &s_)) return s_; }
 #define GSPALN_HOOK_LSPH   { VTYPE s_; if (gspaln::dropin::lspH(seqs, pwd, wdw, mfd, simd, cip, &s_)) return s_; }
-#define GSPALN_HOOK_TRCBKH { VTYPE s_; if (gspaln::dropin::trcbkH(seqs, pwd, wdw, mfd, simd, cip, mc, &s_)) return s_; }
+#define GSPALN_HOOK_TRCBKH { VTYPE s_; if (gspaln::dropin::trcbkH(seqs, pwd, wdw, mfd, simd, cip, spj, mc, &s_)) return s_; }
 #define GSPALN_HOOK_HOMH   { VTYPE s_; if (gspaln::dropin::homscoreH(seqs, pwd, &s_)) return s_; }
 
 #endif  // GSPALN_HARVEST

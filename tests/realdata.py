@@ -60,14 +60,23 @@ class Workspace:
                     g.write(line)
         return out
 
-    def run(self, binary: str, opts: list, query: Path, harvest: Path = None, timeout=3600) -> bytes:
+    def run(self, binary: str, opts: list, query: Path, harvest: Path = None, timeout=3600, stats=None) -> bytes:
+        """stats: a dict that receives the drop-in's call counters (GSPALN_DROPIN_STATS), e.g.
+        {"dna": {"lsp": 12, ...}, "protein": {...}}"""
         env = dict(self.env)
         if harvest is not None:
             env["GSPALN_HARVEST_FILE"] = str(harvest)
+        if stats is not None:
+            env["GSPALN_DROPIN_STATS"] = "1"
         r = subprocess.run([str(REF / binary)] + opts + ["-ddictdisc_g", str(query)], cwd=self.dir, env=env,
                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
         if r.returncode != 0:
             raise RuntimeError(f"{binary} {' '.join(opts)} failed ({r.returncode}): {r.stderr[-400:].decode(errors='replace')}")
+        if stats is not None:
+            for ln in r.stderr.decode(errors="replace").splitlines():
+                if ln.startswith("gspaln drop-in ("):
+                    kind = ln[len("gspaln drop-in ("):].split(")")[0]
+                    stats[kind] = {k: int(v) for k, v in (x.split("=") for x in ln.split(":", 1)[1].split())}
         return r.stdout
 
     def close(self):

@@ -72,16 +72,45 @@ def test_protein_sample_gff_identical_through_dropin(ws):
     assert gff_records(gpu8) == gff_records(cpu)
 
 
+PROT_MD5_A0 = "387c8c749d45fccd7fbf6fde01e1071c"  # the same at -A0 (the reference's default mode), SURVEY.md 8c
+PROT_MD5_A1 = "0a31a60ecbfba6f22b8c76609721b3ea"  # -A1
+
+
+@pytest.mark.parametrize("alg,md5", [("-A0", PROT_MD5_A0), ("-A1", PROT_MD5_A1)])
+def test_protein_sample_gff_identical_through_dropin_scalar_modes(ws, alg, md5):
+    """`-A0`: every trcbkalignH_ng / HomScoreH_ng call of the run takes the reference's scalar branch
+    (forwardH_ng), which the drop-in sends to the exact-ILD kernel; the drivers and the Hirschberg
+    passes stay with the stock code.  `-A1`: only blocks with fewer than 8 query rows do."""
+    opts = ["-Q7", "-O0", alg, "-t1", "-pq", "-Tdictdisc"]
+    q = realdata.SEQDB / "dictdisc.faa"
+    cpu = ws.run("spaln", opts, q)
+    assert hashlib.md5(cpu).hexdigest() == md5
+    st = {}
+    assert ws.run("spaln_gpu", opts, q, stats=st) == cpu
+    # the device answered: every trace-back of -A0, the few-row blocks of -A1
+    # (the protein sample makes 61 non-trivial trcbkalignH_ng calls; -A2 answers as many lspH_ng calls)
+    assert st["protein"]["trcbk_exact"] >= (50 if alg == "-A0" else 1), st
+    assert st["protein"]["lsp"] == 0 and st["protein"]["trcbk_wip"] == 0, st
+    assert st["protein"]["exact_no_tables"] == 0 and st["protein"]["exact_overflow"] == 0, st
+
+
 @pytest.mark.parametrize("opts", [["-Q7", "-O4", "-S3", "-A2"], ["-Q7", "-O0", "-S3", "-A3"],
-                                  ["-Q5", "-O4", "-S3", "-A2", "-LS"]])
+                                  ["-Q5", "-O4", "-S3", "-A2", "-LS"], ["-Q7", "-O4", "-S3", "-A0"],
+                                  ["-Q7", "-O4", "-S3", "-A1"]])
 def test_cdna_sample_identical_through_dropin(ws, opts):
     """cDNA sample (first n queries): exon coordinates (-O4) / GFF (-O0) of the drop-in build equal
     the stock build's, line for line"""
-    q = ws.head_fasta(realdata.SEQDB / "dictdisc.cf", min(600, n_cdna()))
+    scalar = "-A0" in opts or "-A1" in opts     # (slow stock modes: fewer queries)
+    q = ws.head_fasta(realdata.SEQDB / "dictdisc.cf", min(200 if scalar else 600, n_cdna()))
     full = opts + [f"-t{ws.threads}", "-pq", "-Tdictdisc"]
     cpu = ws.run("spaln", full, q)
-    gpu = ws.run("spaln_gpu", full, q)
-    assert len(cpu.splitlines()) > 500
+    st = {}
+    gpu = ws.run("spaln_gpu", full, q, stats=st)
+    assert len(cpu.splitlines()) > (150 if scalar else 500)
+    if "-A0" in opts:
+        assert st["dna"]["trcbk_exact"] >= 100 and st["dna"]["lsp"] == 0, st
+    elif not scalar:
+        assert st["dna"]["lsp"] >= 100, st
     if "-O0" in opts:
         assert gff_records(gpu) == gff_records(cpu)
     else:

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """GPU-box tool: throughput of the exact-ILD kernels (forwardS_ng with path records, scorealoneS_ng)
 on config-2 problems.  usage: quick_xild.py [n_queries] [take]   (take: keep the `take` problems
-closest to the median size, e.g. for a profiler run)"""
+closest to the median size; a third argument "rows,cols" crops every problem to that many query
+rows / genome columns -- a short kernel for a profiler run)"""
 import sys
 from pathlib import Path
 
@@ -22,6 +23,14 @@ if len(sys.argv) > 2:
     k = int(sys.argv[2])
     raw = raw[(n - k) // 2: (n - k) // 2 + k]
     n = k
+if len(sys.argv) > 3:
+    from spaln_b200 import workload
+    rows, colsn = (int(x) for x in sys.argv[3].split(","))
+    for r in raw:
+        r["a_right"] = min(r["a_right"], rows)
+        r["b_right"] = min(r["b_right"], colsn)
+        r["lw"], r["up"] = workload.stripe(r["a_left"], r["a_right"], r["b_left"], r["b_right"], 100)
+    bench.host_cells(raw)
 probs = bench.to_problems(raw)
 cells = sum(r["cells"] for r in raw)
 eng = Engine(prm, device=0)
