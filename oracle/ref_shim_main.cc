@@ -41,6 +41,8 @@ int shim_s1_nelem();
 int shim_s1_scorealone(const Seq** seqs, const PwdB* pwd, int lw, int up);
 int shim_s1_scalar(const Seq** seqs, const PwdB* pwd, int lw, int up,
 	int* score, int* skl_out, int cap, double* seconds);
+int shim_s1_scalar_udh(const Seq** seqs, const PwdB* pwd, int lw, int up, int n_imd, int intvl,
+	int* score, int* cpos_out);
 int shim_h1_udh(const Seq** seqs, const PwdB* pwd, int lw, int up, int n_imd, int* score,
 	int* cpos_out, double* seconds);
 int shim_h1_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up, int* score, int* skl_out,
@@ -346,6 +348,13 @@ void ref_task_cip_table(void* h, int* out, int n)
 {
 	Cip_score cs(((RefTask*) h)->sqs[0]);
 	for (int c = 0; c < n; ++c) out[c] = (int) cs.cip_score(c);
+}
+
+// Aln2s1::hirschbergS_ng (the scalar Hirschberg pass of `-A0`) on the task's current ranges
+int ref_task_scalar_udh(void* h, int lw, int up, int n_imd, int intvl, int* score, int* cpos_out)
+{
+	RefTask* t = (RefTask*) h;
+	return shim_s1_scalar_udh((const Seq**) t->sqs, g_pwd, lw, up, n_imd, intvl, score, cpos_out);
 }
 
 const void* ref_pwd() { return g_pwd; }

@@ -47,6 +47,12 @@ struct ShimAln2s1 : public Aln2s1 {
 	    delete mfd; mfd = 0;
 	    return scr;
 	}
+	// Aln2s1::hirschbergS_ng (src/fwd2s1.cc:764-1104), the scalar Hirschberg pass of `-A0`, with the
+	// spacing of the intermediate rows set as lspS_ng does (src/fwd2s1.cc:1840,1853)
+	VTYPE	run_scalar_udh(const WINDOW& wdw, int n_imd, int intvl, Dim10* cpos) {
+	    imd_intvl = intvl;
+	    return hirschbergS_ng(cpos, n_imd, wdw);
+	}
 };
 
 int copy_out(Mfile& mfd, SKL* out, int cap)
@@ -136,6 +142,25 @@ int shim_s1_scorealone(const Seq** seqs, const PwdB* pwd, int lw, int up)
 	WINDOW wdw = {lw, up, up - lw + 3};
 	Aln2s1 alnv(seqs, pwd);
 	return (int) alnv.scorealoneS_ng(wdw);
+}
+
+// the scalar Hirschberg pass Aln2s1::hirschbergS_ng on the current ranges; the Seq ranges are left
+// as the pass narrowed them (read them back with ref_task_info)
+int shim_s1_scalar_udh(const Seq** seqs, const PwdB* pwd, int lw, int up, int n_imd, int intvl,
+	int* score, int* cpos_out)
+{
+	WINDOW wdw = {lw, up, up - lw + 3};
+	ShimAln2s1 alnv(seqs, pwd);
+	Dim10* cpos = new Dim10[n_imd + 1];
+	for (int i = 0; i <= n_imd; ++i) {
+	    for (int j = 0; j < 10; ++j) cpos[i][j] = 0;
+	    cpos[i][0] = cpos[i][2] = end_of_ulk;
+	}
+	*score = (int) alnv.run_scalar_udh(wdw, n_imd, intvl, cpos);
+	for (int i = 0; i <= n_imd; ++i)
+	    for (int j = 0; j < 10; ++j) cpos_out[10 * i + j] = cpos[i][j];
+	delete[] cpos;
+	return 0;
 }
 
 }	// extern "C"

@@ -872,7 +872,9 @@ int so_hirschberg_wip(const so_params* p, const so_task* t, int n_im,
  * The DP driver: Aln2s1::lspS_ng (src/fwd2s1.cc:1801-1897) with its helpers
  * trcbkalignS_ng (1667-1710, SIMD branch), mimd_postwork (1714-1756),
  * rcsv_postwork (1758-1799), diagonalS_ng (1629-1665) and stripe
- * (src/aln2.cc:156-176), for simd = 2 | 3 (-A2 / -A3) and single affine gaps.
+ * (src/aln2.cc:156-176), for simd = 2 | 3 (-A2 / -A3: `_wip` kernels, single affine gaps on the
+ * Hirschberg route) and simd = 0 (-A0: scalar kernels, hirschbergS_ng, blocks banded by the
+ * diagonal bounds the pass records).
  * Problems with fewer than 8 query rows go to the scalar exact-ILD kernel in
  * the reference (src/fwd2s1.cc:1676), restated in spaln_oracle_ng.c; without
  * its tables (so_params.penalty / sig53tab, so_task.int53) such calls set
@@ -933,8 +935,8 @@ static int drv_trcbk(so_drv* d, const so_task* t)
     const int m = t->a_right - t->a_left;
     int32_t score = 0;
     int room = d->cap > d->n ? d->cap - d->n : 0;
-    if (m < 8) {
-        /* scalar exact-ILD kernel (src/fwd2s1.cc:1676): needs the intron tables */
+    if (m < 8 || (d->o.alg & 3) == 0) {
+        /* scalar exact-ILD kernel (src/fwd2s1.cc:1676; every trace-back of -A0): needs the intron tables */
         int c = so_trcbk_ng(d->p, t, &score, d->skl + 2 * (d->n < d->cap ? d->n : d->cap), room);
         if (c < 0) { d->unsupported = 1; return NEVSEL32; }
         d->n += c;
@@ -974,6 +976,14 @@ static int drv_diagonal(so_drv* d, const so_task* t)
 
 static int drv_lsp(so_drv* d, so_task* t);
 
+/* band of a block after a Hirschberg pass: re-derived from the ranges by the SIMD modes, the lowest /
+ * highest diagonal the pass recorded (cpos[.][8], [9]) under -A0 (src/fwd2s1.cc:1736-1741) */
+static void drv_window(so_drv* d, so_task* t, const int32_t* row)
+{
+    if (d->o.alg & 3) so_stripe(t, d->o.sh);
+    else { t->lw = row[8]; t->up = row[9]; }
+}
+
 static void drv_mimd_postwork(so_drv* d, so_task* t, const int32_t* cpos, int n_imd)
 {
     const int aleft = t->a_left, bleft = t->b_left;
@@ -987,7 +997,7 @@ static void drv_mimd_postwork(so_drv* d, so_task* t, const int32_t* cpos, int n_
         t->b_left = cpos[10 * i + (++c)];
         if (t->b_left < 0 || t->b_left > t->b_right) break;
         while (cpos[10 * i + (++c)] < END_OF_ULK) drv_write(d, t->a_left, cpos[10 * i + c]);
-        so_stripe(t, d->o.sh);
+        drv_window(d, t, cpos + 10 * (i + 1));
         drv_trcbk(d, t);
         t->a_right = t->a_left;
         t->b_right = cpos[10 * i + c - 1];
@@ -995,7 +1005,7 @@ static void drv_mimd_postwork(so_drv* d, so_task* t, const int32_t* cpos, int n_
     if ((i < 0 && cpos[0] != END_OF_ULK) || cpos[2] != END_OF_ULK) {
         t->a_left = aleft;
         t->b_left = bleft;
-        so_stripe(t, d->o.sh);
+        drv_window(d, t, cpos);
         drv_trcbk(d, t);
     }
 }
@@ -1009,14 +1019,14 @@ static void drv_rcsv_postwork(so_drv* d, so_task* t, const int32_t* cpos)
         const int aright = t->a_right, bright = t->b_right;
         t->a_right = cpos[0];
         t->b_right = cpos[c - 1];
-        so_stripe(t, d->o.sh);
+        drv_window(d, t, cpos);
         drv_lsp(d, t);
         t->a_left = cpos[0];
         t->b_exgl = cpos[1];
         t->b_left = cpos[2];
         t->a_right = aright;
         t->b_right = bright;
-        so_stripe(t, d->o.sh);
+        drv_window(d, t, cpos + 10);
         drv_lsp(d, t);
     } else if (d->p->local) {
         so_stripe(t, d->o.sh);
@@ -1042,8 +1052,16 @@ static int drv_lsp(so_drv* d, so_task* t)
     int n_imd = 1;
     int recursive = d->o.alg & 4;
     const float coef_B = 2.f, coef_C = (float) ((p->noll + 1) * 4);
+    const int simd = d->o.alg & 3;
+    if (simd == 1) { d->unsupported = 1; return NEVSEL32; }    /* -A1: kernels not restated */
     float cvol = (float) m * (n + m);                   /* rhombic, simd >= 2 */
+    if (simd < 2) {                                     /* hexagonal (src/fwd2s1.cc:1830-1833) */
+        const float k = (float) (t->lw - t->b_left + t->a_right);
+        const float q = (float) (t->b_right - t->a_left - t->up);
+        cvol = (float) m * n - (k * k + q * q) / 2;
+    }
     if (coef_B * cvol < d->o.max_vmf_space) return drv_trcbk(d, t);
+    int imd_intvl = (m + 1) / 2;
     if (!recursive) {
         const double z = 2. * m * coef_B / coef_C;
         const int imd1 = (int) (pow(z, 1. / 3) + 0.5) - 1;
@@ -1053,7 +1071,7 @@ static int drv_lsp(so_drv* d, so_task* t)
             const int imd3 = m / NELEM;
             if (d->o.ubh) n_imd = d->o.ubh;
             else n_imd = imd1 < imd3 ? imd1 : imd3;
-            int imd_intvl = (m + n_imd) / (n_imd + 1);
+            imd_intvl = (m + n_imd) / (n_imd + 1);
             if (imd_intvl * n_imd == m) --n_imd;
             if (n_imd == 0) return drv_trcbk(d, t);
         }
@@ -1062,7 +1080,9 @@ static int drv_lsp(so_drv* d, so_task* t)
     int32_t* cpos = (int32_t*) malloc(sizeof(int32_t) * 10 * (n_imd + 1));
     int32_t ranges[4];
     int32_t scr = 0;
-    if (so_hirschberg_wip(p, t, n_imd, &scr, cpos, ranges) < 0) { d->unsupported = 1; free(cpos); return NEVSEL32; }
+    const int rc = simd ? so_hirschberg_wip(p, t, n_imd, &scr, cpos, ranges)
+                        : so_hirschberg_ng(p, t, n_imd, imd_intvl, &scr, cpos, ranges);
+    if (rc < 0) { d->unsupported = 1; free(cpos); return NEVSEL32; }
     t->a_left = ranges[0]; t->a_right = ranges[1]; t->b_left = ranges[2]; t->b_right = ranges[3];
     if (scr > NEVSEL32) {
         if (cpos[0] == END_OF_ULK) {

@@ -123,6 +123,13 @@ void so_exinon_scan_p(const so_scan_params_p* sp, const uint8_t* tron, int len, 
  * codes points at at(0) and codes[-1], codes[len] must be readable (terminal residues) */
 void so_nuc2tron(const uint8_t* gencode, const uint8_t* codes, int len, uint8_t* tron);
 
+/* Aln2s1::hirschbergS_ng (src/fwd2s1.cc:764-1104) with hinitS_ng / hlastS_ng (701-762): the scalar
+ * unidirectional Hirschberg pass of `-A0`.  imd_intvl: spacing of the intermediate rows (the member
+ * lspS_ng sets, src/fwd2s1.cc:1839-1851); cpos: (n_im + 1) x 10 ints, entries [8], [9] = lowest /
+ * highest diagonal of each block; ranges as for so_hirschberg_wip. */
+int so_hirschberg_ng(const so_params* p, const so_task* t, int n_im, int imd_intvl,
+                     int32_t* score, int32_t* cpos, int32_t* ranges);
+
 /* Aln2s1::scorealoneS_ng (src/fwd2s1.cc:1163-1336): the scalar score-only kernel */
 int so_scorealone_ng(const so_params* p, const so_task* t, int32_t* score);
 

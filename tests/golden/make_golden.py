@@ -36,6 +36,10 @@ CONFIGS = {
     "dna_A2_udh": ("-Q0 -A2 -S1 -yX0 -V256K -TDictyost", 15),
     "dna_A2_udh_local": ("-Q0 -A2 -S1 -yX0 -V256K -LS -TDictyost", 16),
     "dna_A6_udh_recursive": ("-Q0 -A6 -S1 -yX0 -V128K -TDictyost", 17),
+    # the reference's default mode (-A0): scalar kernels, scalar Hirschberg pass hirschbergS_ng
+    "dna_A0_udh": ("-Q0 -A0 -S1 -yX0 -V256K -TDictyost", 41),
+    "dna_A0_udh_local": ("-Q0 -A0 -S1 -yX0 -V256K -LS -TDictyost", 42),
+    "dna_A0_udh_dagp": ("-Q0 -A0 -S1 -yX0 -yl3 -V256K -TDictyost", 43),
     # intron positions annotated on the query (Cip_score, src/gsinfo.h:127-139): read by the
     # exact-ILD kernels only; small -V so that the driver reaches them through block re-alignment
     "dna_A2_cip": ("-Q0 -A2 -S1 -yX0 -V256K -TDictyost", 31),
@@ -182,6 +186,7 @@ def gen(name: str):
     probs = []
     with_cip = "cip" in name
     udh = "udh" in name or with_cip
+    scalar_mode = "_A0_" in name
     ng_tables = None
     scan_f = None
 
@@ -194,8 +199,13 @@ def gen(name: str):
             cip = t.set_cip(*annotation(rng, len(q), None if comrev else truth, 1))
         lw, up = t.stripe(p["sh"])
         ex = t.export()
-        r = t.kernel(lw, up, 0, cap=1 << 16)
-        r1 = t.kernel(lw, up, 1)
+        if scalar_mode:
+            # -A0 leaves the quantised intron penalty of the `_wip` kernels unset: scalar kernels only
+            r = {"score": 0, "skl": np.zeros((0, 2), np.int32)}
+            r1 = {"score": 0}
+        else:
+            r = t.kernel(lw, up, 0, cap=1 << 16)
+            r1 = t.kernel(lw, up, 1)
         i = len(probs)
         pre = f"p{i}_"
         out[pre + "a"] = ex["a"]
@@ -230,7 +240,24 @@ def gen(name: str):
             width = up - lw + 3
             mode = 2 if (max(abs(lw), up) + width) < 32767 else 4
             n_im = max(1, min(3, m // 16))
-            if m >= 16:
+            if scalar_mode and not tag.startswith("tiny"):
+                # the scalar pass, with the spacing of the intermediate rows as lspS_ng sets it
+                # (unrelated random pairs make the reference dereference a null intermediate,
+                # src/fwd2s1.cc:1093: skipped)
+                for nn in (1, 2, 5):
+                    if m < 4 * nn:
+                        continue
+                    intvl = (m + nn) // (nn + 1)
+                    nq = nn - 1 if intvl * nn == m else nn
+                    if nq < 1:
+                        continue
+                    rs = t.scalar_udh(lw, up, nq, intvl)
+                    out[pre + f"sudh{nn}_nim"] = np.int32(nq)
+                    out[pre + f"sudh{nn}_intvl"] = np.int32(intvl)
+                    out[pre + f"sudh{nn}_score"] = np.int32(rs["score"])
+                    out[pre + f"sudh{nn}_cpos"] = rs["cpos"].astype(np.int32)
+                    out[pre + f"sudh{nn}_ranges"] = np.array(rs["ranges"], np.int32)
+            if m >= 16 and not scalar_mode:
                 rh = t.kernel(lw, up, 2, n_imd=n_im, mode=mode)
                 out[pre + "udh_nim"] = np.int32(n_im)
                 out[pre + "udh_score"] = np.int32(rh["score"])

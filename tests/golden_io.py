@@ -7,6 +7,8 @@ GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
 GOLDEN_NAMES = ["dna_A2_global", "dna_A2_local", "dna_A3_global", "dna_A2_tetrapod"]
 DAGP_NAMES = ["dna_A2_dagp"]        # double affine gaps (-yl3)
 UDH_NAMES = ["dna_A2_udh", "dna_A2_udh_local", "dna_A6_udh_recursive"]
+A0_NAMES = ["dna_A0_udh", "dna_A0_udh_local", "dna_A0_udh_dagp"]   # -A0: scalar kernels + hirschbergS_ng
+SUDH_KEYS = tuple(f"sudh{nn}_{k}" for nn in (1, 2, 5) for k in ("nim", "intvl", "score", "cpos", "ranges"))
 CIP_NAMES = ["dna_A2_cip"]          # queries annotated with intron positions (Cip_score)
 PROTEIN_CIP_NAMES = ["prot_A2_cip"]
 GEOM_KEYS = ["a_left", "a_right", "b_left", "b_right", "a_exgl", "a_exgr", "b_exgl", "b_exgr",
@@ -28,7 +30,7 @@ def load(name):
              "score_only": int(z[pre + "score_only"]), "tag": str(z[pre + "tag"])}
         d.update({k: int(v) for k, v in zip(GEOM_KEYS, z[pre + "geom"])})
         for k in ("lsp_score", "lsp_skl", "udh_nim", "udh_score", "udh_cpos", "udh_ranges",
-                  "int53", "ng_score", "ng_skl", "ng_score_only", "cip"):
+                  "int53", "ng_score", "ng_skl", "ng_score_only", "cip") + SUDH_KEYS:
             if pre + k in z.files:
                 v = z[pre + k]
                 d[k] = v if v.ndim else int(v)

@@ -186,6 +186,21 @@ class SoScanParams(C.Structure):
                 ("any", C.c_int32), ("sig53tab", C.c_void_p)]
 
 
+def hirschberg_ng(p: dict, t: dict, n_im: int, intvl: int):
+    """Aln2s1::hirschbergS_ng (scalar Hirschberg pass of `-A0`)"""
+    sp, st = make_params(p), make_task(t)
+    score = C.c_int32(0)
+    cpos = np.zeros((n_im + 1, 10), np.int32)
+    ranges = np.zeros(4, np.int32)
+    L = lib()
+    L.so_hirschberg_ng.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.so_hirschberg_ng(C.byref(sp), C.byref(st), n_im, intvl, C.byref(score), cpos.ctypes.data,
+                            ranges.ctypes.data)
+    if rc < 0:
+        raise RuntimeError(f"so_hirschberg_ng failed ({rc})")
+    return {"score": score.value, "cpos": cpos, "ranges": ranges.tolist()}
+
+
 def make_scan_params(p: dict):
     """p: fixture parameters with the splice PSSMs (pat5_* / pat3_*), scan_f = (fS, sss), sig53tab"""
     sp = SoScanParams()

@@ -374,6 +374,19 @@ class RefTask:
                 "seconds": secs.value,
                 "ranges": [after["a_left"], after["a_right"], after["b_left"], after["b_right"]]}
 
+    def scalar_udh(self, lw, up, n_imd, intvl):
+        """Aln2s1::hirschbergS_ng (scalar Hirschberg pass, `-A0`); the narrowed ranges are reported,
+        then restored"""
+        score = C.c_int(0)
+        cpos = np.zeros((n_imd + 1, 10), np.int32)
+        before = self.info()
+        self.lib.ref_task_scalar_udh.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        self.lib.ref_task_scalar_udh(self.h, lw, up, n_imd, intvl, C.byref(score), cpos.ctypes.data)
+        after = self.info()
+        self.set(**before)
+        return {"score": score.value, "cpos": cpos,
+                "ranges": [after["a_left"], after["a_right"], after["b_left"], after["b_right"]]}
+
     def adapter(self, lw, up, kind=0, device=0, cap=1 << 16, protein=False):
         """the same problem through include/gspaln_spaln_adapter.hpp (GPU drop-in):
         SpalnEngine::forwardS1_wip / scoreonlyS1_wip, or SpalnEngineH::forwardH1_wip"""

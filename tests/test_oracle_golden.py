@@ -96,3 +96,43 @@ def test_oracle_udh_matches_reference_golden(oracle, name):
         assert np.array_equal(o["skl"], pb["lsp_skl"]), (name, i, pb["tag"])
         n_lsp += 1
     assert n_udh >= 20 and n_lsp == len(probs)
+
+
+def sudh_cpos_equal(a, b):
+    """records of the scalar pass: the crossing list up to its end_of_ulk terminator and, for rows
+    that were crossed, the diagonal bounds in [8], [9]"""
+    for ra, rb in zip(a.tolist(), b.tolist()):
+        ka = ra.index(EOU) if EOU in ra[:8] else 8
+        kb = rb.index(EOU) if EOU in rb[:8] else 8
+        if ra[:ka] != rb[:kb] or (ka > 0 and ra[8:] != rb[8:]):
+            return False
+    return True
+
+
+@pytest.mark.parametrize("name", golden_io.A0_NAMES)
+def test_oracle_scalar_mode_matches_reference_golden(oracle, name):
+    """`-A0`, the reference's default mode: the scalar kernels, the scalar Hirschberg pass
+    hirschbergS_ng (1, 2 and 5 intermediate rows) and the whole driver with blocks banded by the
+    recorded diagonal bounds -- global, local and double affine"""
+    prm, probs = golden_io.load(name)
+    assert int(prm["alg"]) & 3 == 0
+    n_pass = n_route = 0
+    for i, pb in enumerate(probs):
+        o = oracle.trcbk_ng(prm, pb)
+        assert o["score"] == pb["ng_score"] and np.array_equal(o["skl"], pb["ng_skl"]), (name, i, pb["tag"])
+        for nn in (1, 2, 5):
+            if f"sudh{nn}_nim" not in pb:
+                continue
+            o = oracle.hirschberg_ng(prm, pb, pb[f"sudh{nn}_nim"], pb[f"sudh{nn}_intvl"])
+            assert o["score"] == pb[f"sudh{nn}_score"], (name, i, pb["tag"], nn)
+            if o["score"] > -(1 << 28):
+                assert o["ranges"] == pb[f"sudh{nn}_ranges"].tolist(), (name, i, pb["tag"], nn)
+                assert sudh_cpos_equal(o["cpos"], pb[f"sudh{nn}_cpos"]), (name, i, pb["tag"], nn)
+            n_pass += 1
+        o = oracle.lsp(prm, pb)
+        assert not o["unsupported"], (name, i, pb["tag"])
+        assert o["score"] == pb["lsp_score"] and np.array_equal(o["skl"], pb["lsp_skl"]), (name, i, pb["tag"])
+        m, n = pb["a_right"] - pb["a_left"], pb["b_right"] - pb["b_left"]
+        k, q = pb["lw"] - pb["b_left"] + pb["a_right"], pb["b_right"] - pb["a_left"] - pb["up"]
+        n_route += 2.0 * (m * n - (k * k + q * q) / 2) >= prm["MaxVmfSpace"]
+    assert n_pass >= 50 and n_route >= 12, (n_pass, n_route)
