@@ -63,9 +63,16 @@ enum {                          /* gspaln_task.kind */
                                    (1667-1710), exact intron scoring.  The reference runs it for
                                    blocks with fewer than 8 query rows.  Needs
                                    gspaln_set_ng_tables() and gspaln_task.int53. */
-    GSPALN_SCOREALONE_NG = 4    /* Aln2s1::scorealoneS_ng (src/fwd2s1.cc:1163-1336): the scalar
+    GSPALN_SCOREALONE_NG = 4,   /* Aln2s1::scorealoneS_ng (src/fwd2s1.cc:1163-1336): the scalar
                                    score-only kernel HomScoreS_ng runs under -A0 and for queries
                                    shorter than 4 residues (src/fwd2s1.cc:2704-2705).  Same tables. */
+    GSPALN_HIRSCHBERG_NG = 5    /* Aln2s1::hirschbergS_ng (src/fwd2s1.cc:764-1104): the scalar Hirschberg
+                                   pass of -A0 with exact intron scoring.  n_imd = the number of
+                                   intermediate rows lspS_ng asks for BEFORE its even-division
+                                   correction (src/fwd2s1.cc:1850-1851; spacing (m + n_imd) / (n_imd + 1),
+                                   one row fewer when it divides the query evenly).  Results as for
+                                   GSPALN_HIRSCHBERG_WIP; cpos[i][8], [9] = lowest / highest diagonal of
+                                   block i (the band of its re-alignment).  Same tables as FORWARD_NG. */
 };
 
 enum {                          /* gspaln_result.status */
@@ -111,7 +118,7 @@ typedef struct gspaln_task {
     int32_t b_exgl, b_exgr;
     int32_t lw, up;             /* WINDOW (src/cmn.h:133); width = up - lw + 3 */
     int32_t skl_cap;            /* capacity of result.skl in corners */
-    int32_t n_imd;              /* GSPALN_HIRSCHBERG_WIP: number of intermediate rows (>= 1) */
+    int32_t n_imd;              /* GSPALN_HIRSCHBERG_WIP / _NG: number of intermediate rows (>= 1) */
     const uint16_t* int53;      /* GSPALN_FORWARD_NG (and gspaln_lsp blocks with < 8 rows), else may be
                                    NULL: Exinon::int53[n] by column n (src/codepot.h:49-54) as
                                    dinc5 | dinc3 << 4 | cano5 << 8 | cano3 << 12 */

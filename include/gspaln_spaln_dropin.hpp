@@ -134,12 +134,14 @@ inline SpalnEngineH* engineH(const PwdB* pwd, const Seq* b)
     return e;
 }
 
-// What the device covers.  Drivers (lsp*_ng): the `_wip` formulation, -A2 / -A3 (simd >= 2).
-// Kernels behind trcbkalign*_ng / HomScore*_ng: the `_wip` kernels for simd >= 2, the exact-ILD
-// kernels for every call the reference sends to its scalar code -- all of `-A0` (simd == 0, the
-// reference's default) and blocks with fewer than 8 query rows in any mode; the Hirschberg passes
-// of `-A0` and the int16 exact-ILD kernels of `-A1` stay with the stock code.  Cip_score (queries
-// annotated with intron positions) is read by the exact-ILD kernels only and travels with the task.
+// What the device covers.  Drivers: lspS_ng under -A2 / -A3 (`_wip` kernels) and under -A0, the
+// reference's default (exact-ILD kernels + the scalar Hirschberg pass hirschbergS_ng); lspH_ng under
+// -A2 / -A3.  Kernels behind trcbkalign*_ng / HomScore*_ng: the `_wip` kernels for simd >= 2, the
+// exact-ILD kernels for every call the reference sends to its scalar code -- all of `-A0` and
+// blocks with fewer than 8 query rows in any mode.  The protein Hirschberg pass of `-A0`
+// (hirschbergH_ng) and the int16 exact-ILD kernels of `-A1` stay with the stock code.  Cip_score
+// (queries annotated with intron positions) is read by the exact-ILD kernels only and travels with
+// the task.
 inline bool covered(int simd, const Cip_score*) { return simd >= 2; }
 inline bool exact_tables_ok(const Seq* b, bool same_tab)
 {
@@ -150,10 +152,11 @@ inline bool exact_tables_ok(const Seq* b, bool same_tab)
 inline bool lspS(const Seq** seqs, const PwdB* pwd, const WINDOW& wdw, Mfile* mfd, int simd,
                  const Cip_score* cip, VTYPE* scr)
 {
-    if (!covered(simd, cip)) return false;
+    if (simd == 1) return false;
     const Seq* b = seqs[1];
     SpalnEngine* e = engineS(pwd, b);
     const INT53* i53 = (b->inex.intr && e->same_sig53tab(sig53tab_of(b))) ? int53_of(b) : 0;
+    if (simd == 0 && (!i53 || b->right - b->left >= MAX_SEGMENT)) return false;    // -A0 runs on the exact-ILD tables
     return counted(e->lspS_ng(seqs, wdw, mfd, i53, scr, cip), 0, HookStats::LSP);
 }
 
@@ -304,7 +307,7 @@ inline void harvest_call(bool protein, const Seq** seqs, const PwdB* pwd, const 
     const bool spliced = b->inex.intr;
     if (!H.params_written) {
         std::vector<char> v;
-        const int n_pen = 1 << 17;
+        const int n_pen = 1 << 20;      // (-A0 runs every block on the exact intron-length table)
         std::vector<short> pen(n_pen, 0);
         if (pwd->IntPen) for (int n = 0; n < n_pen; ++n) pen[n] = pwd->IntPen->Penalty(n);
         std::vector<short> tab(544, 0);
@@ -393,7 +396,7 @@ inline void harvest_after(bool protein, const Seq** seqs, const PwdB* pwd, const
 #define GSPALN_HARVEST_BODY(PROT, SELF_CALL)                                                         \
     {                                                                                                \
         static thread_local int gspaln_depth_ = 0;                                                   \
-        if (!gspaln_depth_ && simd >= 2 && !cip && gspaln::dropin::harvest().fp) {                   \
+        if (!gspaln_depth_ && simd != 1 && !cip && gspaln::dropin::harvest().fp) {                   \
             RANGE rng_[2] = {{a->left, a->right}, {b->left, b->right}};                              \
             const INT exg_[4] = {a->inex.exgl, a->inex.exgr, b->inex.exgl, b->inex.exgr};            \
             const size_t mark_ = mfd->size();                                                        \

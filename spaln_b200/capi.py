@@ -24,6 +24,7 @@ SCOREONLY_WIP = 1
 HIRSCHBERG_WIP = 2
 FORWARD_NG = 3          # scalar exact-ILD kernel (Aln2s1::forwardS_ng + Vmf trace-back)
 SCOREALONE_NG = 4       # scalar score-only kernel (Aln2s1::scorealoneS_ng)
+HIRSCHBERG_NG = 5       # scalar Hirschberg pass (Aln2s1::hirschbergS_ng)
 END_OF_ULK = 2 ** 31 - 1 - 2
 
 EXPORTS = [
@@ -217,10 +218,14 @@ def make_params(p: dict) -> GspalnParams:
     gp.noll = int(p["Noll"])
     gp.ipen = int(p["GapWI"])
     gp.llmt = int(p["llmt"])
-    gp.nquant = int(p["nquant"])
+    # under -A0 / -A1 the reference does not build the quantised intron penalty of the `_wip` kernels
+    # (IntronPenalty::qm); such parameter sets drive the exact-ILD kernels only and get one flat bin
+    gp.nquant = min(int(p["nquant"]), len(p["quant_len"]))
     for j in range(gp.nquant):
         gp.quant_len[j] = int(p["quant_len"][j])
         gp.quant_pen[j] = int(p["quant_pen"][j])
+    if gp.nquant == 0:
+        gp.nquant, gp.quant_len[0], gp.quant_pen[0] = 1, 0, 0
     gp.avmch = int(p["avmch"])
     gp.local = 1 if (int(p["lcl"]) & 16) else 0
     gp.spj = int(p.get("spj", 1))

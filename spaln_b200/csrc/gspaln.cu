@@ -9,6 +9,7 @@
 #include "gspaln_kernels.cuh"
 #include "gspaln_udh.cuh"
 #include "gspaln_ng.cuh"
+#include "gspaln_xudh.cuh"
 #include "gspaln_host.hpp"
 
 #include <algorithm>
@@ -61,6 +62,8 @@ struct gspaln_ctx {
     DevBuf<int> d_ngs;              // score-only scalar kernel: three int rows per thread
     int n_ngs = 0, grid_run_ngs = 0;
     size_t ngs_width = 0;
+    int n_xudh = 0, grid_run_xudh = 0;  // scalar Hirschberg pass (GSPALN_HIRSCHBERG_NG)
+    size_t xudh_width = 0;
     PinBuf<DevTask> h_tasks;
     PinBuf<int> h_order;
     PinBuf<unsigned char> h_apool;
@@ -403,7 +406,8 @@ int gspaln_set_ng_tables(gspaln_ctx* ctx, const int16_t* sig53tab, const int16_t
 // the exact-ILD kinds with a Cip_score table, the int32 bonuses of rows a_left .. a_right behind them
 static inline size_t cip_offset(const gspaln_task& t)
 {
-    const bool with = t.cip && (t.kind == GSPALN_FORWARD_NG || t.kind == GSPALN_SCOREALONE_NG);
+    const bool with = t.cip && (t.kind == GSPALN_FORWARD_NG || t.kind == GSPALN_SCOREALONE_NG ||
+                                t.kind == GSPALN_HIRSCHBERG_NG);
     return with ? align_up((size_t) (t.a_right - t.a_left) + 1, 4) : 0;
 }
 static inline size_t a_span(const gspaln_task& t)
@@ -424,10 +428,11 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         const gspaln_task& t = tasks[i];
         if (t.a_right < t.a_left || t.b_right < t.b_left || t.up - t.lw + 3 < 0 ||
             (t.kind != GSPALN_FORWARD_WIP && t.kind != GSPALN_SCOREONLY_WIP && t.kind != GSPALN_HIRSCHBERG_WIP &&
-             t.kind != GSPALN_FORWARD_NG && t.kind != GSPALN_SCOREALONE_NG) ||
+             t.kind != GSPALN_FORWARD_NG && t.kind != GSPALN_SCOREALONE_NG && t.kind != GSPALN_HIRSCHBERG_NG) ||
             (t.kind == GSPALN_HIRSCHBERG_WIP && (t.n_imd < 1 || t.a_right - t.a_left < 2 || ctx->prm.noll != 2)) ||
-            ((t.kind == GSPALN_FORWARD_NG || t.kind == GSPALN_SCOREALONE_NG) && ctx->prm.spj &&
-             (!ctx->ng_ready || !t.int53 || t.b_right - t.b_left >= ctx->n_pen)) ||
+            (t.kind == GSPALN_HIRSCHBERG_NG && (t.n_imd < 1 || t.a_right - t.a_left < 2 || !ctx->prm.spj)) ||
+            ((t.kind == GSPALN_FORWARD_NG || t.kind == GSPALN_SCOREALONE_NG || t.kind == GSPALN_HIRSCHBERG_NG) &&
+             ctx->prm.spj && (!ctx->ng_ready || !t.int53 || t.b_right - t.b_left >= ctx->n_pen)) ||
             !t.a || !t.b || (ctx->prm.spj && (!t.sig5 || !t.sig3))) {
             char msg[256];
             snprintf(msg, sizeof(msg), "bad task %d: kind %d a (%d, %d] b (%d, %d] band [%d, %d] n_imd %d",
@@ -444,8 +449,8 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
                      [&](int x, int y) { return ctx->cells[x] > ctx->cells[y]; });
     size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, skl_elems = 0;
     size_t udh_slab = 0, cpos_elems = 0;
-    int n_trace = 0, n_score = 0, n_udh = 0, n_ng = 0, n_ngs = 0;
-    size_t ng_width = 0, ng_rec = 0, ngs_width = 0;
+    int n_trace = 0, n_score = 0, n_udh = 0, n_ng = 0, n_ngs = 0, n_xudh = 0;
+    size_t ng_width = 0, ng_rec = 0, ngs_width = 0, xudh_width = 0, xudh_links = 0;
     int n_trace_c[3] = {0, 0, 0}, n_score_c[3] = {0, 0, 0};
     size_t band_slab_c[3] = {0, 0, 0}, trace_slab_c[3] = {0, 0, 0};
     const bool dagp_prm = ctx->prm.noll == 3;
@@ -469,6 +474,7 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         const size_t bslab = align_up((size_t) width + 2 * NELEM, 32);
         d.skl_off = (long long) skl_elems;
         d.pad1 = (long long) cip_at;
+        if (cip_at) d.flags |= 16;          // a Cip_score table rides behind the query codes
         int cls = 8;
         if (t.kind == GSPALN_FORWARD_WIP || t.kind == GSPALN_SCOREONLY_WIP) {
             cls = wip_class(mw, width, dagp_prm);
@@ -492,6 +498,14 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         } else if (t.kind == GSPALN_SCOREALONE_NG) {
             ngs_width = std::max(ngs_width, (size_t) width);
             ++n_ngs;
+        } else if (t.kind == GSPALN_HIRSCHBERG_NG) {
+            // band rows of 32-byte cells + hlnk | vlnk | lwrb | uprb per intermediate row
+            d.pad0 = t.n_imd;
+            d.pad1 = (long long) cpos_elems;
+            cpos_elems += (size_t) 10 * (t.n_imd + 1);
+            xudh_width = std::max(xudh_width, (size_t) width);
+            xudh_links = std::max(xudh_links, (size_t) t.n_imd * 4 * ctx->prm.noll * (size_t) width);
+            ++n_xudh;
         } else if (t.kind == GSPALN_HIRSCHBERG_WIP) {
             d.pad0 = t.n_imd;
             d.pad1 = (long long) cpos_elems;
@@ -569,12 +583,15 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         // exact-ILD kernels: one warp per problem, per-warp workspace = band rows (H, F, F2 as
         // {value, record}) + direction bytes + path records; the trace-back and the score-only
         // kernel never run at the same time, so they share the pool
-        ctx->grid_run_ng = ctx->grid_run_ngs = 0;
-        if (n_ng || n_ngs) {
+        ctx->grid_run_ng = ctx->grid_run_ngs = ctx->grid_run_xudh = 0;
+        if (n_ng || n_ngs || n_xudh) {
             const size_t w = std::max(ng_width, ngs_width);
             const size_t rec = n_ng ? ng_rec + 32 * NG_CHUNK + 64 : 64;
-            const size_t slab = align_up(3 * w * sizeof(NgRvp) + align_up(w, 16) + 12 * rec, 16);
-            int g = std::min((std::max(n_ng, n_ngs) + NG_WARPS - 1) / NG_WARPS, 4 * ctx->sm_count);
+            size_t slab = align_up(3 * w * sizeof(NgRvp) + align_up(w, 16) + 12 * rec, 16);
+            // the scalar Hirschberg pass shares the pool (the kernels run one after the other)
+            const size_t xslab = n_xudh ? align_up(3 * xudh_width * sizeof(UxSlot) + 4 * xudh_links + 64, 32) : 0;
+            slab = align_up(std::max(slab, xslab), 32);
+            int g = std::min((std::max(std::max(n_ng, n_ngs), n_xudh) + NG_WARPS - 1) / NG_WARPS, 4 * ctx->sm_count);
             cudaMemGetInfo(&free_b, &total_b);
             const size_t room = (size_t) (0.5 * (double) (free_b + ctx->d_ngwork.cap));
             while (g > 1 && (size_t) g * NG_WARPS * slab > room) g = g * 3 / 4;
@@ -584,11 +601,13 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             }
             ctx->grid_run_ng = n_ng ? std::min(g, (n_ng + NG_WARPS - 1) / NG_WARPS) : 0;
             ctx->grid_run_ngs = n_ngs ? std::min(g, (n_ngs + NG_WARPS - 1) / NG_WARPS) : 0;
+            ctx->grid_run_xudh = n_xudh ? std::min(g, (n_xudh + NG_WARPS - 1) / NG_WARPS) : 0;
             ctx->ng_slab = slab; ctx->ng_width = w; ctx->ng_rec_cap = (int) rec;
+            ctx->xudh_width = xudh_width;
         }
     }
     ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score; ctx->n_udh = n_udh; ctx->n_ng = n_ng;
-    ctx->n_ngs = n_ngs;
+    ctx->n_ngs = n_ngs; ctx->n_xudh = n_xudh;
     ctx->udh_slab = udh_slab; ctx->cpos_elems = cpos_elems;
     ctx->a_bytes = a_bytes; ctx->c_elems = c_elems; ctx->band_slab = band_slab;
     ctx->trace_slab = trace_slab; ctx->skl_elems = skl_elems;
@@ -642,8 +661,8 @@ static void pack_range(gspaln_ctx* ctx, const gspaln_task* tasks, int lo, int hi
             // the byte behind the query codes: this problem may run on the packed int16x2 kernel
             ap[mw] = (ctx->pk_ok && !(seen & ~PK_CODES) && sigmax <= PK_SIGMAX &&
                       (t.kind == GSPALN_FORWARD_WIP || t.kind == GSPALN_SCOREONLY_WIP)) ? 1 : 0;
-            if ((t.kind == GSPALN_FORWARD_NG || t.kind == GSPALN_SCOREALONE_NG) && d.pad1)
-                memcpy(ap + d.pad1, t.cip + t.a_left, sizeof(int32_t) * ((size_t) mw + 1));   // rows a_left .. a_right
+            if (const size_t cip_at = cip_offset(t))
+                memcpy(ap + cip_at, t.cip + t.a_left, sizeof(int32_t) * ((size_t) mw + 1));     // rows a_left .. a_right
         }
     };
     size_t work = 0;
@@ -754,6 +773,13 @@ static int launch_range(gspaln_ctx* ctx, int lo, int hi, int slot, int& launches
             (long long) ctx->ng_width, ctx->ng_rec_cap, ctx->d_skl.p, ctx->d_res.p, ready);
         ++launches;
     }
+    if (ctx->n_xudh) {
+        dp_xudh_kernel<<<ctx->grid_run_xudh, NG_THREADS, 0, ctx->stream>>>(
+            ctx->d_prm.p, ctx->d_ngtab.p, ctx->n_pen, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 10,
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_ngwork.p, (long long) ctx->ng_slab,
+            (long long) ctx->xudh_width, ctx->d_cpos.p, ctx->d_ures.p, ready);
+        ++launches;
+    }
     CK(cudaGetLastError());
     return GSPALN_OK;
 }
@@ -810,7 +836,7 @@ int gspaln_download(gspaln_ctx* ctx, gspaln_result* results)
     if (n) CK(cudaMemcpyAsync(ctx->h_res.p, ctx->d_res.p, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (ctx->skl_elems)
         CK(cudaMemcpyAsync(ctx->h_skl.p, ctx->d_skl.p, sizeof(int2) * ctx->skl_elems, cudaMemcpyDeviceToHost, ctx->stream));
-    if (ctx->n_udh) {
+    if (ctx->n_udh || ctx->n_xudh) {
         CK(cudaMemcpyAsync(ctx->h_ures.p, ctx->d_ures.p, sizeof(DevUdhOut) * n, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_cpos.p, ctx->d_cpos.p, sizeof(int) * ctx->cpos_elems, cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -826,7 +852,7 @@ int gspaln_download(gspaln_ctx* ctx, gspaln_result* results)
         o.score = r.score; o.status = r.status; o.n_skl = r.n_skl; o.reserved = 0;
         o.cells = ctx->cells[i];
         const DevTask& d = ctx->h_tasks.p[i];
-        if (d.kind == GSPALN_HIRSCHBERG_WIP) {
+        if (d.kind == GSPALN_HIRSCHBERG_WIP || d.kind == GSPALN_HIRSCHBERG_NG) {
             const DevUdhOut& u = ctx->h_ures.p[i];
             o.score = u.score; o.status = u.status; o.n_skl = 0;
             o.ranges[0] = u.a_left; o.ranges[1] = u.a_right; o.ranges[2] = u.b_left; o.ranges[3] = u.b_right;
@@ -934,6 +960,8 @@ struct LspTraitsS {
     using Ctx = gspaln_ctx;
     using Task = gspaln_task;
     static constexpr int WPAD = 3;
+    static constexpr bool SCALAR_MODE = true;               // -A0: forwardS_ng + hirschbergS_ng on the device
+    static constexpr int KIND_SCALAR_UDH = GSPALN_HIRSCHBERG_NG;
     static void stripe(LspGeo& g, int sh)       // stripe(), src/aln2.cc:156-176
     {
         if (sh < 0) {

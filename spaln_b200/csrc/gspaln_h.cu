@@ -803,6 +803,8 @@ struct LspTraitsH {
     using Ctx = gspaln_h_ctx;
     using Task = gspaln_h_task;
     static constexpr int WPAD = 7;
+    static constexpr bool SCALAR_MODE = false;              // the scalar Hirschberg pass hirschbergH_ng is not on the device
+    static constexpr int KIND_SCALAR_UDH = GSPALN_HIRSCHBERG_WIP;
     static void stripe(LspGeo& g, int sh)       // stripe31(), src/aln2.cc:178-199
     {
         if (sh < 0) {

@@ -29,7 +29,8 @@ struct LspItem {
     LspGeo g;
     int score = 0;
     bool recursive = false;
-    int n_imd = 0;
+    int n_imd = 0;              // intermediate rows of the Hirschberg pass
+    int n_req = 0;              // ... before lspS_ng's even-division correction (what the scalar pass is given)
     std::vector<LspPiece> pieces;
 };
 
@@ -52,6 +53,21 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
     const auto& P = ctx->prm;
     const int NEVSEL = INT_MIN / 16 * 7;
     const int EOU = INT_MAX - 2;
+    // algmode.alg & 3: 2 / 3 = the `_wip` kernels; 0 = the scalar mode (-A0: exact-ILD kernels,
+    // hexagonal volume, blocks banded by the diagonal bounds of the pass); 1 (-A1) is not on the device
+    const int simd = opts->alg & 3;
+    if (simd == 1 || (simd == 0 && !TR::SCALAR_MODE)) {
+        for (int i = 0; i < n; ++i) {
+            results[i].score = NEVSEL; results[i].status = GSPALN_ST_UNSUPPORTED; results[i].n_skl = 0;
+            results[i].reserved = 0; results[i].cells = TR::cells(tasks[i]);
+        }
+        return GSPALN_OK;
+    }
+    // band of a block after a Hirschberg pass (src/fwd2s1.cc:1736-1741)
+    auto window = [&](LspGeo& g, const int* row) {
+        if (simd) TR::stripe(g, opts->sh);
+        else { g.lw = row[8]; g.up = row[9]; }
+    };
     std::vector<LspItem> items;
     std::vector<LspFwd> fwds;
     std::vector<int> status(n, GSPALN_ST_OK);
@@ -73,7 +89,7 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
     // returns the index of the queued forward task or -1 (nothing to do / unsupported)
     auto queue_trcbk = [&](int item, const LspGeo& g) -> int {
         if (g.up - g.lw + TR::WPAD < 0) return -1;
-        const bool scalar = g.a_right - g.a_left < 8;     // src/fwd2s1.cc:1676, src/fwd2h1.cc:2007
+        const bool scalar = simd == 0 || g.a_right - g.a_left < 8;     // src/fwd2s1.cc:1676, src/fwd2h1.cc:2007
         if ((scalar && !TR::scalar_ok(ctx, tasks[items[item].root], g)) || g.b_right < g.b_left ||
             g.a_left < 0 || g.b_left < 0 || TR::beyond(tasks[items[item].root], g)) {
             status[items[item].root] = GSPALN_ST_UNSUPPORTED;
@@ -162,10 +178,14 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
                 continue;
             }
             bool trcbk = TR::small(m, nn);
-            int n_imd = 1;
+            int n_imd = 1, n_req = 1;
             bool recursive = (opts->alg & 4) != 0;
             const float coef_B = 2.f, coef_C = TR::coef_c(P);
-            const float cvol = TR::cvol(m, nn);                 // rhombic (simd >= 2)
+            float cvol = TR::cvol(m, nn);                       // rhombic (simd >= 2)
+            if (simd < 2) {                                     // hexagonal (src/fwd2s1.cc:1830-1833)
+                const float k = (float) (g.lw - g.b_left + g.a_right), q = (float) (g.b_right - g.a_left - g.up);
+                cvol = (float) m * nn - (k * k + q * q) / 2;
+            }
             if (!trcbk && coef_B * cvol < opts->max_vmf_space) trcbk = true;
             if (!trcbk && !recursive) {
                 const double z = 2. * m * coef_B / coef_C;
@@ -175,6 +195,7 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
                 else {
                     const int imd3 = m / NELEM;
                     n_imd = opts->ubh ? opts->ubh : std::min(imd1, imd3);
+                    n_req = n_imd;
                     const int imd_intvl = (m + n_imd) / (n_imd + 1);
                     if (imd_intvl * n_imd == m) --n_imd;
                     if (n_imd == 0) trcbk = true;
@@ -185,13 +206,14 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
                 if (f >= 0) item_fwd.push_back({id, f}); else it.score = NEVSEL;
                 continue;
             }
-            if (!TR::udh_ok(P)) {       // the Hirschberg route needs a pass that is not on the device
+            if (simd ? !TR::udh_ok(P) : !TR::scalar_ok(ctx, base, g)) {     // the Hirschberg route needs a pass that is not on the device
                 status[it.root] = GSPALN_ST_UNSUPPORTED;
                 it.score = NEVSEL;
                 continue;
             }
             it.recursive = recursive;
             it.n_imd = n_imd;
+            it.n_req = n_req;
             udh_items.push_back(id);
         }
         pending.clear();
@@ -202,8 +224,9 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
         std::vector<std::vector<int>> cposbuf(udh_items.size());
         for (size_t k = 0; k < udh_items.size(); ++k) {
             const LspItem& it = items[udh_items[k]];
-            batch.push_back(TR::make_task(tasks[it.root], it.g, GSPALN_HIRSCHBERG_WIP, it.n_imd));
-            cposbuf[k].assign(10 * (size_t) (it.n_imd + 1), 0);
+            if (simd) batch.push_back(TR::make_task(tasks[it.root], it.g, GSPALN_HIRSCHBERG_WIP, it.n_imd));
+            else batch.push_back(TR::make_task(tasks[it.root], it.g, TR::KIND_SCALAR_UDH, it.n_req));
+            cposbuf[k].assign(10 * (size_t) (std::max(it.n_imd, it.n_req) + 1), 0);
         }
         const size_t fwd_first = fwd_done;
         size_t skl_ints = 0;
@@ -280,11 +303,11 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
                     const int aright = g.a_right, bright = g.b_right;
                     LspGeo g1 = g;
                     g1.a_right = cpos[0]; g1.b_right = cpos[c - 1];
-                    TR::stripe(g1, opts->sh);
+                    window(g1, cpos);
                     LspGeo g2 = g1;
                     g2.a_left = cpos[0]; g2.b_exgl = cpos[1]; g2.b_left = cpos[2];
                     g2.a_right = aright; g2.b_right = bright;
-                    TR::stripe(g2, opts->sh);
+                    window(g2, cpos + 10);
                     for (const LspGeo& gg : {g1, g2}) {
                         LspItem child; child.root = items[id].root; child.g = gg;
                         items.push_back(child);
@@ -313,7 +336,7 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
                     LspPiece p; p.kind = 0; p.ref = -1;
                     while (cpos[10 * i + (++c)] < EOU) p.lit.push_back(make_int2(g.a_left, cpos[10 * i + c]));
                     if (!p.lit.empty()) items[id].pieces.push_back(std::move(p));
-                    TR::stripe(g, opts->sh);
+                    window(g, cpos + 10 * (i + 1));
                     queue_trcbk(id, g);
                     g.a_right = g.a_left;
                     g.b_right = cpos[10 * i + c - 1];
@@ -321,7 +344,7 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
                 if (i != -2 && ((i < 0 && cpos[0] != EOU) || cpos[2] != EOU)) {
                     g.a_left = aleft;
                     g.b_left = bleft;
-                    TR::stripe(g, opts->sh);
+                    window(g, cpos);
                     queue_trcbk(id, g);
                 }
             }

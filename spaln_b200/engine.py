@@ -194,7 +194,7 @@ class Engine:
             t.lw, t.up = p.lw, p.up
             cap = p.skl_cap or ((p.a_right - p.a_left) + (p.b_right - p.b_left) + 8)
             t.skl_cap = cap if kind in (capi.FORWARD_WIP, capi.FORWARD_NG) else 0
-            t.n_imd = int(p.n_imd) if kind == capi.HIRSCHBERG_WIP else 0
+            t.n_imd = int(p.n_imd) if kind in (capi.HIRSCHBERG_WIP, capi.HIRSCHBERG_NG) else 0
         return arr, keep
 
     def _check(self, rc, what):
@@ -208,7 +208,7 @@ class Engine:
         for i in range(n):
             cap = arr[i].skl_cap
             buf = np.zeros((max(cap, 1), 2), np.int32)
-            cp = np.zeros((arr[i].n_imd + 1, 10), np.int32) if arr[i].kind == capi.HIRSCHBERG_WIP else None
+            cp = np.zeros((arr[i].n_imd + 1, 10), np.int32) if arr[i].kind in (capi.HIRSCHBERG_WIP, capi.HIRSCHBERG_NG) else None
             bufs.append((buf, cp))
             res[i].skl = buf.ctypes.data if cap > 0 else None
             res[i].cpos = cp.ctypes.data if cp is not None else None
@@ -306,6 +306,13 @@ class Engine:
     def hirschbergS1_wip(self, problems):
         """problems carry n_imd; results carry score, ranges and cpos (Dim10 records)"""
         return self.submit(problems, capi.HIRSCHBERG_WIP)
+
+    def hirschbergS_ng(self, problems):
+        """Aln2s1::hirschbergS_ng, the scalar Hirschberg pass of `-A0` (src/fwd2s1.cc:764-1104).  Problems
+        carry n_imd = the number of intermediate rows lspS_ng asks for before its even-division
+        correction, and int53; results carry score, ranges and cpos (entries [8], [9]: the diagonal
+        bounds of each block)"""
+        return self.submit(problems, capi.HIRSCHBERG_NG)
 
     def lspS_ng(self, problems, max_vmf_space=32 * 1024 * 1024, sh=100, ubh=0, alg=2):
         """Aln2s1::lspS_ng over a batch (src/fwd2s1.cc:1801-1897): trace-back vs

@@ -639,3 +639,104 @@ def test_resident_runs_repeat_for_every_chain_class(oracle):
         assert r.score == o["score"] == o1.score, i
         assert np.array_equal(r.skl, o["skl"]) and np.array_equal(o1.skl, o["skl"]), i
     eng.close()
+
+
+# ---------------------------------------------------------------------------
+# -A0, the reference's default mode: scalar Hirschberg pass + the driver on the exact-ILD kernels
+# ---------------------------------------------------------------------------
+def _sudh_cpos_equal(a, b):
+    for ra, rb in zip(a.tolist(), b.tolist()):
+        ka = ra.index(EOU) if EOU in ra[:8] else 8
+        kb = rb.index(EOU) if EOU in rb[:8] else 8
+        if ra[:ka] != rb[:kb] or (ka > 0 and ra[8:] != rb[8:]):
+            return False
+    return True
+
+
+EOU = 2 ** 31 - 1 - 2
+
+
+@pytest.mark.parametrize("name", golden_io.A0_NAMES)
+def test_scalar_hirschberg_pass_matches_reference_golden(name):
+    """GSPALN_HIRSCHBERG_NG == Aln2s1::hirschbergS_ng: score, crossing records with their diagonal
+    bounds, narrowed ranges -- 1, 2 and 5 intermediate rows; global, local, double affine"""
+    prm, probs = golden_io.load(name)
+    eng = _engine(prm)
+    n = 0
+    for nn in (1, 2, 5):
+        sel = [pb for pb in probs if f"sudh{nn}_nim" in pb]
+        P = _problems(sel)
+        for p in P:
+            p.n_imd = nn
+        for i, (pb, r) in enumerate(zip(sel, eng.hirschbergS_ng(P))):
+            assert r.status == 0, (name, nn, i, pb["tag"], r.status)
+            assert r.score == pb[f"sudh{nn}_score"], (name, nn, i, pb["tag"], r.score, pb[f"sudh{nn}_score"])
+            if r.score > -(1 << 28):
+                assert list(r.ranges) == pb[f"sudh{nn}_ranges"].tolist(), (name, nn, i, pb["tag"])
+                assert _sudh_cpos_equal(r.cpos[: pb[f"sudh{nn}_nim"] + 1], pb[f"sudh{nn}_cpos"]), (name, nn, i, pb["tag"])
+            n += 1
+    assert n >= 50
+    eng.close()
+
+
+@pytest.mark.parametrize("name,flags,sub", [
+    ("dna_A0_udh", None, None),
+    ("dna_A0_udh", (0, 0, 0, 0), None),
+    ("dna_A0_udh", (1, 0, 0, 1), (7, 3, 11, 5)),
+    ("dna_A0_udh_local", None, None),
+    ("dna_A0_udh_dagp", None, None),
+    ("dna_A0_udh_dagp", (0, 1, 1, 0), None),
+])
+def test_scalar_hirschberg_pass_matches_oracle_seeded(oracle, name, flags, sub):
+    """seeded planted genes (synthetic signals: many more candidate sites than real tables), any
+    number of intermediate rows, rows spaced closer than one pass of the kernel included"""
+    prm, _ = golden_io.load(name)
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(repr(("xudh", name, flags, sub)).encode()))
+    probs = _synthetic(prm, rng, 16, (40, 700), (30, 500), flags=flags, sub=sub)
+    probs += _synthetic(prm, rng, 4, (900, 1500), (100, 300), flags=flags, sub=sub)
+    P = _problems(probs)
+    want = []
+    for pb, p in zip(probs, P):
+        m = pb["a_right"] - pb["a_left"]
+        p.n_imd = int(rng.choice([1, 2, 3, 7, max(1, m // 16), max(1, m // 9)]))
+        intvl = (m + p.n_imd) // (p.n_imd + 1)
+        nq = p.n_imd - 1 if intvl * p.n_imd == m else p.n_imd
+        want.append(oracle.hirschberg_ng(prm, pb, nq, intvl) if nq >= 1 else None)
+    eng = _engine(prm)
+    n = 0
+    for i, (pb, p, r, o) in enumerate(zip(probs, P, eng.hirschbergS_ng(P), want)):
+        if o is None:
+            continue
+        assert r.status == 0 and r.score == o["score"], (name, i, p.n_imd, r.status, r.score, o["score"])
+        if r.score > -(1 << 28):
+            assert list(r.ranges) == o["ranges"], (name, i, p.n_imd)
+            assert _sudh_cpos_equal(r.cpos[: len(o["cpos"])], o["cpos"]), (name, i, p.n_imd)
+        n += 1
+    assert n >= 15
+    eng.close()
+
+
+@pytest.mark.parametrize("name", golden_io.A0_NAMES)
+def test_lsp_driver_scalar_mode_matches_reference_golden(oracle, name):
+    """gspaln_lsp with alg = 0 == Aln2s1::lspS_ng under -A0: hexagonal volume in the dispatch, exact-ILD
+    trace-back for every block, the scalar Hirschberg pass, blocks banded by its diagonal bounds"""
+    prm, probs = golden_io.load(name)
+    eng = _engine(prm)
+    n_route = 0
+    for vmf in (int(prm["MaxVmfSpace"]), 32 * 1024 * 1024):
+        res = eng.lspS_ng(_problems(probs), max_vmf_space=vmf, sh=int(prm["sh"]), ubh=int(prm["ubh"]), alg=0)
+        for i, (pb, r) in enumerate(zip(probs, res)):
+            assert r.status == 0, (name, vmf, i, pb["tag"], r.status)
+            if vmf == int(prm["MaxVmfSpace"]):
+                want_score, want_skl = pb["lsp_score"], pb["lsp_skl"]
+                m, n = pb["a_right"] - pb["a_left"], pb["b_right"] - pb["b_left"]
+                k, q = pb["lw"] - pb["b_left"] + pb["a_right"], pb["b_right"] - pb["a_left"] - pb["up"]
+                n_route += 2.0 * (m * n - (k * k + q * q) / 2) >= vmf
+            else:
+                o = oracle.lsp(prm, pb, max_vmf_space=vmf)
+                want_score, want_skl = o["score"], o["skl"]
+            assert r.score == want_score, (name, vmf, i, pb["tag"], r.score, want_score)
+            assert np.array_equal(r.skl, want_skl), (name, vmf, i, pb["tag"])
+    assert n_route >= 12
+    eng.close()

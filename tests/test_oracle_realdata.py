@@ -50,11 +50,11 @@ def ws():
     w.close()
 
 
-@pytest.mark.parametrize("kind", ["cdna", "protein"])
+@pytest.mark.parametrize("kind", ["cdna", "protein", "cdna_A0"])
 def test_oracle_reproduces_harvested_lsp_calls(ws, kind):
-    if kind == "cdna":
+    if kind.startswith("cdna"):
         q = ws.head_fasta(realdata.SEQDB / "dictdisc.cf", 120)
-        opts = ["-Q7", "-O4", "-S3", "-A2", f"-t{ws.threads}", "-pq", "-Tdictdisc"]
+        opts = ["-Q7", "-O4", "-S3", "-A0" if kind == "cdna_A0" else "-A2", f"-t{ws.threads}", "-pq", "-Tdictdisc"]
     else:
         q = realdata.SEQDB / "dictdisc.faa"
         opts = ["-Q7", "-O0", "-A2", "-t1", "-pq", "-Tdictdisc"]
