@@ -90,6 +90,31 @@ struct ShimAln2h1Scalar : public ShimAln2h1 {
 	}
 };
 
+// Aln2h1::hirschbergH_ng (src/fwd2h1.cc:1085-1520), the scalar Hirschberg pass of `-A0`, with the
+// spacing of the intermediate rows set as lspH_ng does (src/fwd2h1.cc:2170,2183); the Seq ranges are
+// left as the pass narrowed them
+struct ShimAln2h1Udh : public ShimAln2h1 {
+	ShimAln2h1Udh(const Seq** sqs, const PwdB* pwd) : ShimAln2h1(sqs, pwd) {}
+	VTYPE run(const WINDOW& w, int n_imd, int intvl, Dim10* cpos) {
+	    imd_intvl = intvl;
+	    return hirschbergH_ng(cpos, n_imd, w);
+	}
+};
+
+int shim_h1_scalar_udh(const Seq** seqs, const PwdB* pwd, int lw, int up, int n_imd, int intvl,
+	int* score, int* cpos_out)
+{
+	WINDOW wdw = {lw, up, up - lw + 7};
+	ShimAln2h1Udh aln(seqs, pwd);
+	Dim10* cpos = new Dim10[n_imd + 1];
+	for (int i = 0; i <= n_imd; ++i) vset(cpos[i], end_of_ulk, 10);
+	*score = (int) aln.run(wdw, n_imd, intvl, cpos);
+	for (int i = 0; i <= n_imd; ++i)
+	    for (int j = 0; j < 10; ++j) cpos_out[10 * i + j] = cpos[i][j];
+	delete[] cpos;
+	return 0;
+}
+
 int shim_h1_scalar(const Seq** seqs, const PwdB* pwd, int lw, int up, int* score, int* skl_out, int cap)
 {
 	WINDOW wdw = {lw, up, up - lw + 7};

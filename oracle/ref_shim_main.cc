@@ -48,6 +48,8 @@ int shim_h1_udh(const Seq** seqs, const PwdB* pwd, int lw, int up, int n_imd, in
 int shim_h1_lsp(const Seq** seqs, const PwdB* pwd, int lw, int up, int* score, int* skl_out,
 	int cap, double* seconds);
 int shim_h1_scalar(const Seq** seqs, const PwdB* pwd, int lw, int up, int* score, int* skl_out, int cap);
+int shim_h1_scalar_udh(const Seq** seqs, const PwdB* pwd, int lw, int up, int n_imd, int intvl,
+	int* score, int* cpos_out);
 void shim_h1_spj_tables(unsigned char* out);
 int shim_h1_kernel(const Seq** seqs, const PwdB* pwd, int lw, int up, int kind,
 	int* score, int* skl_out, int cap, double* seconds);
@@ -355,6 +357,13 @@ int ref_task_scalar_udh(void* h, int lw, int up, int n_imd, int intvl, int* scor
 {
 	RefTask* t = (RefTask*) h;
 	return shim_s1_scalar_udh((const Seq**) t->sqs, g_pwd, lw, up, n_imd, intvl, score, cpos_out);
+}
+
+// Aln2h1::hirschbergH_ng (the scalar protein Hirschberg pass of `-A0`) on the task's current ranges
+int ref_task_scalar_udh_p(void* h, int lw, int up, int n_imd, int intvl, int* score, int* cpos_out)
+{
+	RefTask* t = (RefTask*) h;
+	return shim_h1_scalar_udh((const Seq**) t->sqs, g_pwd, lw, up, n_imd, intvl, score, cpos_out);
 }
 
 const void* ref_pwd() { return g_pwd; }

@@ -201,6 +201,12 @@ typedef struct so_ng_h_s {
 int so_trcbk_h_ng(const so_params_h* p, const so_ng_h* x, const so_task_h* t, int32_t* score,
                   int32_t* skl, int cap);
 
+/* Aln2h1::hirschbergH_ng (src/fwd2h1.cc:1085-1520) with hinitH_ng / hlastH_ng (941-1083): the scalar
+ * protein Hirschberg pass of `-A0`.  imd_intvl: spacing of the intermediate rows (lspH_ng,
+ * src/fwd2h1.cc:2170-2183); cpos: (n_im + 1) x 10 ints, [8], [9] = diagonal bounds of each block. */
+int so_hirschberg_h_ng(const so_params_h* p, const struct so_ng_h_s* x, const so_task_h* t, int n_im,
+                       int imd_intvl, int32_t* score, int32_t* cpos, int32_t* ranges);
+
 #ifdef __cplusplus
 }
 #endif

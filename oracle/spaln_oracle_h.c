@@ -1041,12 +1041,13 @@ static int drvh_trcbk(so_drvh* d, const so_task_h* t)
     const int width = t->up - t->lw + 7;
     if (width < 0) return NEVSEL32_H;
     const int m = t->a_right - t->a_left;
-    if ((m < 8 && !d->p->ng) || t->b_right < t->b_left || t->a_left < 0 || t->b_left < 0 || t->b_right > t->b_len ||
+    const int scalar = m < 8 || (d->o.alg & 3) == 0;
+    if ((scalar && !d->p->ng) || t->b_right < t->b_left || t->a_left < 0 || t->b_left < 0 || t->b_right > t->b_len ||
         t->a_right > t->a_len) { d->unsupported = 1; return NEVSEL32_H; }
     int32_t score = 0;
     int room = d->cap > d->n ? d->cap - d->n : 0;
-    if (m < 8) {
-        /* scalar kernel forwardH_ng (src/fwd2h1.cc:2007), restated in spaln_oracle_hng.c */
+    if (scalar) {
+        /* scalar kernel forwardH_ng (src/fwd2h1.cc:2007; every trace-back of -A0), restated in spaln_oracle_hng.c */
         int c = so_trcbk_h_ng(d->p, d->p->ng, t, &score, d->skl + 2 * (d->n < d->cap ? d->n : d->cap), room);
         if (c < 0) { d->unsupported = 1; return NEVSEL32_H; }
         d->n += c;
@@ -1079,6 +1080,14 @@ static int drvh_diagonal(so_drvh* d, const so_task_h* t)
 
 static int drvh_lsp(so_drvh* d, so_task_h* t);
 
+/* band of a block after a Hirschberg pass: re-derived from the ranges by the SIMD modes, the diagonal
+ * bounds the pass recorded (cpos[.][8], [9]) under -A0 (src/fwd2h1.cc:2066-2072) */
+static void drvh_window(so_drvh* d, so_task_h* t, const int32_t* row)
+{
+    if (d->o.alg & 3) so_stripe31(t, d->o.sh);
+    else { t->lw = row[8]; t->up = row[9]; }
+}
+
 static void drvh_mimd_postwork(so_drvh* d, so_task_h* t, const int32_t* cpos, int n_imd)
 {
     const int aleft = t->a_left, bleft = t->b_left;
@@ -1093,7 +1102,7 @@ static void drvh_mimd_postwork(so_drvh* d, so_task_h* t, const int32_t* cpos, in
         if (t->a_right > t->a_len || t->b_right > t->b_len || t->a_left < 0 || t->b_left < 0) return;
         if (t->b_left < 0 || t->b_left > t->b_right) break;
         while (cpos[10 * i + (++c)] < END_OF_ULK_H) drvh_write(d, t->a_left, cpos[10 * i + c]);
-        so_stripe31(t, d->o.sh);
+        drvh_window(d, t, cpos + 10 * (i + 1));
         drvh_trcbk(d, t);
         t->a_right = t->a_left;
         t->b_right = cpos[10 * i + c - 1];
@@ -1101,7 +1110,7 @@ static void drvh_mimd_postwork(so_drvh* d, so_task_h* t, const int32_t* cpos, in
     if ((i < 0 && cpos[0] != END_OF_ULK_H) || cpos[2] != END_OF_ULK_H) {
         t->a_left = aleft;
         t->b_left = bleft;
-        so_stripe31(t, d->o.sh);
+        drvh_window(d, t, cpos);
         drvh_trcbk(d, t);
     }
 }
@@ -1115,14 +1124,14 @@ static void drvh_rcsv_postwork(so_drvh* d, so_task_h* t, const int32_t* cpos)
         const int aright = t->a_right, bright = t->b_right;
         t->a_right = cpos[0];
         t->b_right = cpos[c - 1];
-        so_stripe31(t, d->o.sh);
+        drvh_window(d, t, cpos);
         drvh_lsp(d, t);
         t->a_left = cpos[0];
         t->b_exgl = cpos[1];
         t->b_left = cpos[2];
         t->a_right = aright;
         t->b_right = bright;
-        so_stripe31(t, d->o.sh);
+        drvh_window(d, t, cpos + 10);
         drvh_lsp(d, t);
     } else if (d->p->local) {
         so_stripe31(t, d->o.sh);
@@ -1153,9 +1162,18 @@ static int drvh_lsp(so_drvh* d, so_task_h* t)
     if (abs(n - m) < NELEM || m == 1 || n <= 3) return drvh_trcbk(d, t);
     int n_imd = 1;
     int recursive = d->o.alg & 4;
-    const float coef_B = 2.f, coef_C = 12.f;            /* sizeof(short), (Noll + 1) * sizeof(int) */
+    const int simd = d->o.alg & 3;
+    if (simd == 1) { d->unsupported = 1; return NEVSEL32_H; }       /* -A1: kernels not restated */
+    const float coef_B = 2.f;                           /* sizeof(short) */
+    const float coef_C = (float) (((p->ng ? p->ng->noll : 2) + 1) * 4);    /* (Noll + 1) * sizeof(int) */
     float cvol = (float) m * (n + 3 * m);               /* rhombic, simd >= 2 */
+    if (simd < 2) {                                     /* hexagonal (src/fwd2h1.cc:2161-2164) */
+        const float k = (float) (t->lw - t->b_left + 3 * t->a_right);
+        const float q = (float) (t->b_right - 3 * t->a_left - t->up);
+        cvol = (float) m * n - (k * k + q * q) / 6;
+    }
     if (coef_B * cvol < d->o.max_vmf_space) return drvh_trcbk(d, t);
+    int imd_intvl = (m + 1) / 2;
     if (!recursive) {
         const double z = 2. * m * coef_B / coef_C;
         const int imd1 = (int) (pow(z, 1. / 3) + 0.5) - 1;
@@ -1165,7 +1183,7 @@ static int drvh_lsp(so_drvh* d, so_task_h* t)
             const int imd3 = m / NELEM;
             if (d->o.ubh) n_imd = d->o.ubh;
             else n_imd = imd1 < imd3 ? imd1 : imd3;
-            int imd_intvl = (m + n_imd) / (n_imd + 1);
+            imd_intvl = (m + n_imd) / (n_imd + 1);
             if (imd_intvl * n_imd == m) --n_imd;
             if (n_imd == 0) return drvh_trcbk(d, t);
         }
@@ -1174,7 +1192,9 @@ static int drvh_lsp(so_drvh* d, so_task_h* t)
     int32_t* cpos = (int32_t*) malloc(sizeof(int32_t) * 10 * (n_imd + 1));
     int32_t ranges[4];
     int32_t scr = 0;
-    if (so_hirschberg_h1_wip(p, t, n_imd, &scr, cpos, ranges) < 0) { d->unsupported = 1; free(cpos); return NEVSEL32_H; }
+    const int rc = simd ? so_hirschberg_h1_wip(p, t, n_imd, &scr, cpos, ranges)
+                        : so_hirschberg_h_ng(p, p->ng, t, n_imd, imd_intvl, &scr, cpos, ranges);
+    if (rc < 0) { d->unsupported = 1; free(cpos); return NEVSEL32_H; }
     t->a_left = ranges[0]; t->a_right = ranges[1]; t->b_left = ranges[2]; t->b_right = ranges[3];
     if (scr > NEVSEL32_H) {
         if (cpos[0] == END_OF_ULK_H) {

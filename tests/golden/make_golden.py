@@ -40,6 +40,8 @@ CONFIGS = {
     "dna_A0_udh": ("-Q0 -A0 -S1 -yX0 -V256K -TDictyost", 41),
     "dna_A0_udh_local": ("-Q0 -A0 -S1 -yX0 -V256K -LS -TDictyost", 42),
     "dna_A0_udh_dagp": ("-Q0 -A0 -S1 -yX0 -yl3 -V256K -TDictyost", 43),
+    "prot_A0_udh": ("-Q0 -A0 -yX0 -V128K -TDictyost", 44),
+    "prot_A0_udh_local": ("-Q0 -A0 -yX0 -V128K -LS -TDictyost", 45),
     # intron positions annotated on the query (Cip_score, src/gsinfo.h:127-139): read by the
     # exact-ILD kernels only; small -V so that the driver reaches them through block re-alignment
     "dna_A2_cip": ("-Q0 -A2 -S1 -yX0 -V256K -TDictyost", 31),
@@ -86,6 +88,7 @@ def gen_protein(name: str):
     n = 0
     with_cip = "cip" in name
     udh = "udh" in name or with_cip
+    scalar_mode = "_A0_" in name
     ng_tables = None
 
     def add(g, q, tag="", truth=None, **setkw):
@@ -98,8 +101,13 @@ def gen_protein(name: str):
             cip = t.set_cip(*annotation(rng, len(q), truth, 3))
         lw, up = t.stripe31(p["sh"])
         ex = t.export_p()
-        r = t.kernel_p(lw, up, 0)
-        r1 = t.kernel_p(lw, up, 1)
+        if scalar_mode:
+            # -A0 leaves the quantised intron penalty of the `_wip` kernels unset: scalar kernels only
+            r = {"score": 0, "skl": np.zeros((0, 2), np.int32)}
+            r1 = {"score": 0}
+        else:
+            r = t.kernel_p(lw, up, 0)
+            r1 = t.kernel_p(lw, up, 1)
         pre = f"p{n}_"
         out[pre + "a"] = ex["a"]
         out[pre + "b"] = ex["b"]
@@ -127,7 +135,21 @@ def gen_protein(name: str):
             out[pre + "lsp_score"] = np.int32(rl["score"])
             out[pre + "lsp_skl"] = rl["skl"].astype(np.int32)
             m = ex["a_right"] - ex["a_left"]
-            if m >= 16:
+            if scalar_mode and not tag.startswith("tiny"):
+                for nn in (1, 2, 5):
+                    if m < 4 * nn:
+                        continue
+                    intvl = (m + nn) // (nn + 1)
+                    nq = nn - 1 if intvl * nn == m else nn
+                    if nq < 1:
+                        continue
+                    rs = t.scalar_udh_p(lw, up, nq, intvl)
+                    out[pre + f"sudh{nn}_nim"] = np.int32(nq)
+                    out[pre + f"sudh{nn}_intvl"] = np.int32(intvl)
+                    out[pre + f"sudh{nn}_score"] = np.int32(rs["score"])
+                    out[pre + f"sudh{nn}_cpos"] = rs["cpos"].astype(np.int32)
+                    out[pre + f"sudh{nn}_ranges"] = np.array(rs["ranges"], np.int32)
+            if m >= 16 and not scalar_mode:
                 n_im = max(1, min(3, m // 16))
                 rh = t.udh_p(lw, up, n_im)
                 out[pre + "udh_nim"] = np.int32(n_im)

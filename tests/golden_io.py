@@ -11,6 +11,7 @@ A0_NAMES = ["dna_A0_udh", "dna_A0_udh_local", "dna_A0_udh_dagp"]   # -A0: scalar
 SUDH_KEYS = tuple(f"sudh{nn}_{k}" for nn in (1, 2, 5) for k in ("nim", "intvl", "score", "cpos", "ranges"))
 CIP_NAMES = ["dna_A2_cip"]          # queries annotated with intron positions (Cip_score)
 PROTEIN_CIP_NAMES = ["prot_A2_cip"]
+PROTEIN_A0_NAMES = ["prot_A0_udh", "prot_A0_udh_local"]     # -A0: forwardH_ng + hirschbergH_ng
 GEOM_KEYS = ["a_left", "a_right", "b_left", "b_right", "a_exgl", "a_exgr", "b_exgl", "b_exgr",
              "lw", "up"]
 
@@ -59,7 +60,7 @@ def load_protein(name):
         d.update({k: int(v) for k, v in zip(GEOM_KEYS_P, z[pre + "geom"])})
         d.setdefault("alen", len(d["a"]) - 2)
         for k in ("lsp_score", "lsp_skl", "udh_nim", "udh_score", "udh_cpos", "udh_ranges",
-                  "int53", "ng_score", "ng_skl", "cip"):
+                  "int53", "ng_score", "ng_skl", "cip") + SUDH_KEYS:
             if pre + k in z.files:
                 v = z[pre + k]
                 d[k] = v if v.ndim else int(v)

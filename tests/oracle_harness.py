@@ -335,7 +335,7 @@ def _params_h(p: dict):
     sp.gop, sp.gep, sp.lgep, sp.codonk1 = p["BasicGOP"], p["BasicGEP"], p["LongGEP"], p["codonk1"]
     sp.gw1, sp.gw2, sp.gw3 = p["GapW1"], p["GapW2"], p["GapW3"]
     sp.ipen, sp.llmt, sp.nquant = p["GapWI"], p["llmt"], p["nquant"]
-    for j in range(p["nquant"]):
+    for j in range(min(p["nquant"], len(p["quant_len"]))):      # (-A0 fixtures carry no quantile table)
         sp.quant_len[j] = int(p["quant_len"][j])
         sp.quant_pen[j] = int(p["quant_pen"][j])
     sp.avmch = p["avmch"]
@@ -439,3 +439,21 @@ def trcbk_h_ng(p: dict, t: dict, cap: int = 1 << 16):
     if n < 0:
         raise RuntimeError(f"so_trcbk_h_ng failed: {n}")
     return {"score": score.value, "skl": skl[:n].copy()}
+
+
+def hirschberg_h_ng(p: dict, t: dict, n_im: int, intvl: int):
+    """Aln2h1::hirschbergH_ng (scalar protein Hirschberg pass of `-A0`)"""
+    sp, st = _params_h(p), _task_h(t)
+    keep = _ng_h(p, t)
+    x = keep[0]
+    score = C.c_int32(0)
+    cpos = np.zeros((n_im + 1, 10), np.int32)
+    ranges = np.zeros(4, np.int32)
+    L = lib()
+    L.so_hirschberg_h_ng.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
+    rc = L.so_hirschberg_h_ng(C.byref(sp), C.byref(x), C.byref(st), n_im, intvl, C.byref(score),
+                              cpos.ctypes.data, ranges.ctypes.data)
+    if rc < 0:
+        raise RuntimeError(f"so_hirschberg_h_ng failed ({rc})")
+    return {"score": score.value, "cpos": cpos, "ranges": ranges.tolist()}

@@ -387,6 +387,18 @@ class RefTask:
         return {"score": score.value, "cpos": cpos,
                 "ranges": [after["a_left"], after["a_right"], after["b_left"], after["b_right"]]}
 
+    def scalar_udh_p(self, lw, up, n_imd, intvl):
+        """Aln2h1::hirschbergH_ng (scalar protein Hirschberg pass, `-A0`); ranges reported, then restored"""
+        score = C.c_int(0)
+        cpos = np.zeros((n_imd + 1, 10), np.int32)
+        before = self.info()
+        self.lib.ref_task_scalar_udh_p.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        self.lib.ref_task_scalar_udh_p(self.h, lw, up, n_imd, intvl, C.byref(score), cpos.ctypes.data)
+        after = self.info()
+        self.set(**before)
+        return {"score": score.value, "cpos": cpos,
+                "ranges": [after["a_left"], after["a_right"], after["b_left"], after["b_right"]]}
+
     def adapter(self, lw, up, kind=0, device=0, cap=1 << 16, protein=False):
         """the same problem through include/gspaln_spaln_adapter.hpp (GPU drop-in):
         SpalnEngine::forwardS1_wip / scoreonlyS1_wip, or SpalnEngineH::forwardH1_wip"""

@@ -55,3 +55,43 @@ def test_oracle_scalar_protein_kernel_matches_reference_golden(oracle, name):
         o = oracle.trcbk_h_ng(prm, pb)
         assert o["score"] == pb["ng_score"], (name, i, pb["tag"])
         assert np.array_equal(o["skl"], pb["ng_skl"]), (name, i, pb["tag"])
+
+
+EOU = 2 ** 31 - 1 - 2
+
+
+def _sudh_cpos_equal(a, b):
+    for ra, rb in zip(a.tolist(), b.tolist()):
+        ka = ra.index(EOU) if EOU in ra[:8] else 8
+        kb = rb.index(EOU) if EOU in rb[:8] else 8
+        if ra[:ka] != rb[:kb] or (ka > 0 and ra[8:] != rb[8:]):
+            return False
+    return True
+
+
+@pytest.mark.parametrize("name", golden_io.PROTEIN_A0_NAMES)
+def test_oracle_protein_scalar_mode_matches_reference_golden(oracle, name):
+    """`-A0` for protein queries: forwardH_ng, the scalar Hirschberg pass hirschbergH_ng (1, 2 and 5
+    intermediate rows) and the whole driver lspH_ng with blocks banded by the recorded diagonal bounds"""
+    prm, probs = golden_io.load_protein(name)
+    assert int(prm["alg"]) & 3 == 0
+    n_pass = n_route = 0
+    for i, pb in enumerate(probs):
+        o = oracle.trcbk_h_ng(prm, pb)
+        assert o["score"] == pb["ng_score"] and np.array_equal(o["skl"], pb["ng_skl"]), (name, i, pb["tag"])
+        for nn in (1, 2, 5):
+            if f"sudh{nn}_nim" not in pb:
+                continue
+            o = oracle.hirschberg_h_ng(prm, pb, pb[f"sudh{nn}_nim"], pb[f"sudh{nn}_intvl"])
+            assert o["score"] == pb[f"sudh{nn}_score"], (name, i, pb["tag"], nn)
+            if o["score"] > -(1 << 28):
+                assert o["ranges"] == pb[f"sudh{nn}_ranges"].tolist(), (name, i, pb["tag"], nn)
+                assert _sudh_cpos_equal(o["cpos"], pb[f"sudh{nn}_cpos"]), (name, i, pb["tag"], nn)
+            n_pass += 1
+        o = oracle.lsp_h(prm, pb)
+        assert not o["unsupported"], (name, i, pb["tag"])
+        assert o["score"] == pb["lsp_score"] and np.array_equal(o["skl"], pb["lsp_skl"]), (name, i, pb["tag"])
+        m, n = pb["a_right"] - pb["a_left"], pb["b_right"] - pb["b_left"]
+        k, q = pb["lw"] - pb["b_left"] + 3 * pb["a_right"], pb["b_right"] - 3 * pb["a_left"] - pb["up"]
+        n_route += 2.0 * (m * n - (k * k + q * q) / 6) >= prm["MaxVmfSpace"]
+    assert n_pass >= 40 and n_route >= 6, (n_pass, n_route)
