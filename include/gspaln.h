@@ -337,8 +337,10 @@ typedef struct gspaln_h_params {
 
 typedef struct gspaln_h_task {
     int32_t kind;               /* GSPALN_FORWARD_WIP, GSPALN_SCOREONLY_WIP, GSPALN_HIRSCHBERG_WIP
-                                   (SimdAln2h1::hirschbergH1_wip, src/fwd2h1_wip_simd.h:338-773) or
-                                   GSPALN_FORWARD_NG (scalar forwardH_ng, see gspaln_h_set_ng_tables) */
+                                   (SimdAln2h1::hirschbergH1_wip, src/fwd2h1_wip_simd.h:338-773),
+                                   GSPALN_FORWARD_NG (scalar forwardH_ng, see gspaln_h_set_ng_tables) or
+                                   GSPALN_HIRSCHBERG_NG (scalar Aln2h1::hirschbergH_ng, src/fwd2h1.cc:1085-1520:
+                                   the Hirschberg pass of -A0; n_imd as for the DNA kind) */
     const uint8_t* a;           /* amino-acid codes; a[i] == *Seq::at(i) */
     const uint8_t* b;           /* tron codes (Seq::nuc2tron, src/seq.cc:774-798); b[i] == *Seq::at(i) */
     const gspaln_sgpt6* sg;     /* Exinon::data_p[n], n in [0, b_len + 1] */
@@ -347,7 +349,7 @@ typedef struct gspaln_h_task {
     int32_t a_exgl, a_exgr, b_exgl, b_exgr;     /* INEX values 0..3 */
     int32_t lw, up;             /* WINDOW from stripe31 (src/aln2.cc:178-199); width = up - lw + 7 */
     int32_t skl_cap;
-    int32_t n_imd;              /* GSPALN_HIRSCHBERG_WIP: number of intermediate rows (>= 1) */
+    int32_t n_imd;              /* GSPALN_HIRSCHBERG_WIP / _NG: number of intermediate rows (>= 1) */
     int32_t a_len;              /* Seq::len of the query (driver: range check of mimd_postwork) */
     const uint16_t* int53;      /* GSPALN_FORWARD_NG (and gspaln_h_lsp blocks with < 8 rows), else may be
                                    NULL: Exinon::int53[n] by column, as in gspaln_task.int53 */

@@ -134,15 +134,13 @@ inline SpalnEngineH* engineH(const PwdB* pwd, const Seq* b)
     return e;
 }
 
-// What the device covers.  Drivers: lspS_ng under -A2 / -A3 (`_wip` kernels) and under -A0, the
-// reference's default (exact-ILD kernels + the scalar Hirschberg pass hirschbergS_ng); lspH_ng under
-// -A2 / -A3.  Kernels behind trcbkalign*_ng / HomScore*_ng: the `_wip` kernels for simd >= 2, the
-// exact-ILD kernels for every call the reference sends to its scalar code -- all of `-A0` and
-// blocks with fewer than 8 query rows in any mode.  The protein Hirschberg pass of `-A0`
-// (hirschbergH_ng) and the int16 exact-ILD kernels of `-A1` stay with the stock code.  Cip_score
-// (queries annotated with intron positions) is read by the exact-ILD kernels only and travels with
-// the task.
-inline bool covered(int simd, const Cip_score*) { return simd >= 2; }
+// What the device covers.  Drivers: lspS_ng / lspH_ng under -A2 / -A3 (`_wip` kernels) and under
+// -A0, the reference's default (exact-ILD kernels + the scalar Hirschberg passes hirschbergS_ng /
+// hirschbergH_ng).  Kernels behind trcbkalign*_ng / HomScore*_ng: the `_wip` kernels for
+// simd >= 2, the exact-ILD kernels for every call the reference sends to its scalar code -- all
+// of `-A0` and blocks with fewer than 8 query rows in any mode.  The int16 exact-ILD kernels of
+// `-A1` stay with the stock code.  Cip_score (queries annotated with intron positions) is read by
+// the exact-ILD kernels only and travels with the task.
 inline bool exact_tables_ok(const Seq* b, bool same_tab)
 {
     return !b->inex.intr || (int53_of(b) && same_tab && b->right - b->left < MAX_SEGMENT);
@@ -210,9 +208,10 @@ inline bool lspH(const Seq** seqs, const PwdB* pwd, const WINDOW& wdw, Mfile* mf
                  const Cip_score* cip, VTYPE* scr)
 {
     const Seq* b = seqs[1];
-    if (!covered(simd, cip) || !b->exin || !b->exin->data_p) return false;
+    if (simd == 1 || !b->exin || !b->exin->data_p) return false;
     SpalnEngineH* e = engineH(pwd, b);
     const INT53* i53 = (b->inex.intr && e->same_sig53tab(sig53tab_of(b))) ? int53_of(b) : 0;
+    if (simd == 0 && (!i53 || b->right - b->left >= MAX_SEGMENT)) return false;    // -A0 runs on the exact-ILD tables
     return counted(e->lspH_ng(seqs, wdw, mfd, i53, scr, cip), 1, HookStats::LSP);
 }
 

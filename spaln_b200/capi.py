@@ -297,10 +297,13 @@ def make_h_params(p: dict) -> GspalnHParams:
     gp.gop, gp.gep = int(p["BasicGOP"]), int(p["BasicGEP"])
     gp.lgep, gp.codonk1 = int(p["LongGEP"]), int(p["codonk1"])
     gp.gw1, gp.gw2, gp.gw3 = int(p["GapW1"]), int(p["GapW2"]), int(p["GapW3"])
-    gp.ipen, gp.llmt, gp.nquant = int(p["GapWI"]), int(p["llmt"]), int(p["nquant"])
+    gp.ipen, gp.llmt = int(p["GapWI"]), int(p["llmt"])
+    gp.nquant = min(int(p["nquant"]), len(p["quant_len"]))      # (-A0 / -A1 parameter sets: see the DNA twin)
     for j in range(gp.nquant):
         gp.quant_len[j] = int(p["quant_len"][j])
         gp.quant_pen[j] = int(p["quant_pen"][j])
+    if gp.nquant == 0:
+        gp.nquant, gp.quant_len[0], gp.quant_pen[0] = 1, 0, 0
     gp.avmch = int(p["avmch"])
     gp.lcl = int(p["lcl"])
     gp.spj = int(p.get("spj", 1))

@@ -979,6 +979,11 @@ struct LspTraitsS {
     }
     static bool small(int m, int nn) { return std::abs(nn - m) < 8 || m == 1 || nn == 1; }
     static float cvol(int m, int nn) { return (float) m * (nn + m); }
+    static float cvol_hex(const LspGeo& g, int m, int nn)
+    {
+        const float k = (float) (g.lw - g.b_left + g.a_right), q = (float) (g.b_right - g.a_left - g.up);
+        return (float) m * nn - (k * k + q * q) / 2;
+    }
     static float coef_c(const gspaln_params& P) { return (float) ((P.noll + 1) * 4); }
     static bool is_local(const gspaln_params& P) { return P.local != 0; }
     static bool udh_ok(const gspaln_params& P) { return P.noll == 2; }   // no double-affine Hirschberg pass yet

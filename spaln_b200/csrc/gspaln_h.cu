@@ -6,6 +6,7 @@
 #include "gspaln_h1.cuh"
 #include "gspaln_h1_udh.cuh"
 #include "gspaln_hng.cuh"
+#include "gspaln_hxudh.cuh"
 #include "gspaln_host.hpp"
 
 #include <algorithm>
@@ -32,6 +33,7 @@ struct gspaln_h_ctx {
     DevBuf<DevNgHParams> d_ngprm;
     int n_pen = 0;
     bool ng_ready = false;
+    int ng_noll = 2;                // PwdB::Noll the exact-ILD tables were bound with
     gspaln_h_params prm;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;    // H2D of the chunks that follow the first one
@@ -555,13 +557,13 @@ int gspaln_h_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gspaln
 {
     if (!ctx || !tasks || n < 0) return GSPALN_EINVAL;
     int n_ng = 0;
-    for (int i = 0; i < n; ++i) n_ng += tasks[i].kind == GSPALN_FORWARD_NG;
+    for (int i = 0; i < n; ++i) n_ng += tasks[i].kind == GSPALN_FORWARD_NG || tasks[i].kind == GSPALN_HIRSCHBERG_NG;
     if (!n_ng) return h_submit_core(ctx, tasks, n, results);
     std::vector<gspaln_h_task> t_ng, t_rest;
     std::vector<gspaln_result> r_ng, r_rest;
     std::vector<int> i_ng, i_rest;
     for (int i = 0; i < n; ++i) {
-        const bool ng = tasks[i].kind == GSPALN_FORWARD_NG;
+        const bool ng = tasks[i].kind == GSPALN_FORWARD_NG || tasks[i].kind == GSPALN_HIRSCHBERG_NG;
         (ng ? t_ng : t_rest).push_back(tasks[i]);
         (ng ? r_ng : r_rest).push_back(results[i]);
         (ng ? i_ng : i_rest).push_back(i);
@@ -574,8 +576,26 @@ int gspaln_h_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gspaln
         if (rc != GSPALN_OK) return rc;
         tim_rest = ctx->tim;
     }
-    rc = h_ng_submit(ctx, t_ng.data(), (int) t_ng.size(), r_ng.data());
-    if (rc != GSPALN_OK) return rc;
+    {
+        // trace-back problems, then Hirschberg passes (two kernels over the same kind of pools)
+        std::vector<gspaln_h_task> part[2];
+        std::vector<gspaln_result> rpart[2];
+        std::vector<size_t> ipart[2];
+        for (size_t k = 0; k < t_ng.size(); ++k) {
+            const int w = t_ng[k].kind == GSPALN_HIRSCHBERG_NG;
+            part[w].push_back(t_ng[k]); rpart[w].push_back(r_ng[k]); ipart[w].push_back(k);
+        }
+        gspaln_timing acc;
+        memset(&acc, 0, sizeof(acc));
+        for (int w = 0; w < 2; ++w) {
+            if (part[w].empty()) continue;
+            rc = h_ng_submit(ctx, part[w].data(), (int) part[w].size(), rpart[w].data());
+            if (rc != GSPALN_OK) return rc;
+            acc.kernel_ms += ctx->tim.kernel_ms; acc.launches += ctx->tim.launches; acc.cells += ctx->tim.cells;
+            for (size_t k = 0; k < ipart[w].size(); ++k) r_ng[ipart[w][k]] = rpart[w][k];
+        }
+        ctx->tim = acc;
+    }
     ctx->tim.kernel_ms += tim_rest.kernel_ms; ctx->tim.h2d_ms += tim_rest.h2d_ms; ctx->tim.d2h_ms += tim_rest.d2h_ms;
     ctx->tim.launches += tim_rest.launches; ctx->tim.h2d_bytes += tim_rest.h2d_bytes;
     ctx->tim.d2h_bytes += tim_rest.d2h_bytes; ctx->tim.cells += tim_rest.cells;
@@ -606,6 +626,8 @@ int gspaln_h_set_ng_tables(gspaln_h_ctx* ctx, const int16_t* sig53tab, const int
     P.gop = q.gop; P.gep = q.gep; P.lgop = q.lgop; P.lgep = q.lgep; P.codonk1 = q.codonk1;
     P.gw1 = q.gw1; P.gw2 = q.gw2; P.gw3 = q.gw3; P.gw3l = gw3l; P.gape1 = q.gape1; P.gape2 = q.gape2;
     P.extragop = extragop; P.local = (q.lcl & 16) ? 1 : 0; P.spj = q.spj ? 1 : 0; P.noll = noll; P.minl = minl;
+    P.lcl2 = (q.lcl & 2) ? 1 : 0;
+    ctx->ng_noll = noll;
     P.simdim = q.simdim; P.n_penalty = n_penalty;
     P.mtx = ctx->d_ngmtx.p; P.penalty = ctx->d_ngtab.p + 544; P.sig53tab = ctx->d_ngtab.p; P.spj_tabs = ctx->d_ngspj.p;
     CKH(cudaMemcpy(ctx->d_ngprm.p, &P, sizeof(P), cudaMemcpyHostToDevice));
@@ -619,7 +641,10 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
 {
     if (!ctx->ng_ready) return fail(ctx, GSPALN_EINVAL, "GSPALN_FORWARD_NG needs gspaln_h_set_ng_tables");
     CKH(cudaSetDevice(ctx->device));
+    const bool udh = n > 0 && tasks[0].kind == GSPALN_HIRSCHBERG_NG;    // (the caller sends one kind at a time)
     std::vector<DevNgHTask> dt(n);
+    std::vector<DevUdhHTask> du(udh ? n : 0);
+    size_t cpos_elems = 0;
     std::vector<unsigned char> apool, bpool;
     std::vector<short> sgpool;
     std::vector<unsigned short> ipool;
@@ -629,8 +654,9 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
     for (int i = 0; i < n; ++i) {
         const gspaln_h_task& t = tasks[i];
         if (!t.a || !t.b || !t.sg || !t.int53 || t.a_right < t.a_left || t.b_right < t.b_left ||
-            t.up - t.lw + 7 < 0 || t.b_right - t.b_left >= ctx->n_pen)
-            return fail(ctx, GSPALN_EINVAL, "bad GSPALN_FORWARD_NG task");
+            t.up - t.lw + 7 < 0 || t.b_right - t.b_left >= ctx->n_pen ||
+            (udh && (t.n_imd < 1 || t.a_right - t.a_left < 2)))
+            return fail(ctx, GSPALN_EINVAL, "bad GSPALN_FORWARD_NG / GSPALN_HIRSCHBERG_NG task");
         DevNgHTask& d = dt[i];
         d.a_left = t.a_left; d.a_right = t.a_right; d.b_left = t.b_left; d.b_right = t.b_right;
         d.lw = t.lw; d.up = t.up;
@@ -662,14 +688,24 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
         }
         d.skl_off = (long long) skl_elems; skl_elems += (size_t) d.skl_cap;
         d.work_off = (long long) work_bytes;
-        work_bytes += align_up((size_t) 3 * (width + 8) * sizeof(HCell) + (size_t) d.rec_cap * 12 + 16, 16);
+        if (udh) {
+            // band rows of 32-byte cells + hlnk | vlnk | lwrb | uprb (noll x width ints each) per intermediate row
+            work_bytes += align_up((size_t) 3 * (width + 8) * sizeof(HuSlot) +
+                                   (size_t) t.n_imd * 4 * ctx->ng_noll * (size_t) width * sizeof(int) + 64, 32);
+            du[i].g = d;
+            du[i].n_req = t.n_imd; du[i].pad = 0;
+            du[i].cpos_off = (long long) cpos_elems;
+            cpos_elems += (size_t) 10 * (t.n_imd + 1);
+        } else
+            work_bytes += align_up((size_t) 3 * (width + 8) * sizeof(HCell) + (size_t) d.rec_cap * 12 + 16, 16);
     }
     unsigned char *d_a = nullptr, *d_b = nullptr, *d_work = nullptr;
     short* d_sg = nullptr; unsigned short* d_i = nullptr; DevNgHTask* d_t = nullptr; int* d_cip = nullptr;
     int2* d_skl = nullptr; DevResult* d_res = nullptr; int* d_tick = nullptr;
+    DevUdhHTask* d_tu = nullptr; int* d_cpos = nullptr; DevUdhOut* d_ures = nullptr;
     auto freeall = [&] {
         cudaFree(d_a); cudaFree(d_b); cudaFree(d_work); cudaFree(d_sg); cudaFree(d_i); cudaFree(d_t); cudaFree(d_cip);
-        cudaFree(d_skl); cudaFree(d_res); cudaFree(d_tick);
+        cudaFree(d_skl); cudaFree(d_res); cudaFree(d_tick); cudaFree(d_tu); cudaFree(d_cpos); cudaFree(d_ures);
     };
     cudaError_t e = cudaSuccess;
     auto up = [&](void** dp, const void* hp, size_t bytes) {
@@ -681,8 +717,11 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
     up((void**) &d_b, bpool.data(), bpool.size());
     up((void**) &d_sg, sgpool.data(), sgpool.size() * sizeof(short));
     up((void**) &d_i, ipool.data(), ipool.size() * sizeof(unsigned short));
-    up((void**) &d_t, dt.data(), dt.size() * sizeof(DevNgHTask));
+    if (udh) up((void**) &d_tu, du.data(), du.size() * sizeof(DevUdhHTask));
+    else up((void**) &d_t, dt.data(), dt.size() * sizeof(DevNgHTask));
     up((void**) &d_cip, cippool.data(), cippool.size() * sizeof(int));
+    if (udh && e == cudaSuccess) e = cudaMalloc((void**) &d_cpos, (cpos_elems + 1) * sizeof(int));
+    if (udh && e == cudaSuccess) e = cudaMalloc((void**) &d_ures, (size_t) (n + 1) * sizeof(DevUdhOut));
     if (e == cudaSuccess) e = cudaMalloc((void**) &d_work, work_bytes + 16);
     if (e == cudaSuccess) e = cudaMalloc((void**) &d_skl, (skl_elems + 1) * sizeof(int2));
     if (e == cudaSuccess) e = cudaMalloc((void**) &d_res, (size_t) (n + 1) * sizeof(DevResult));
@@ -691,11 +730,35 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
     if (e != cudaSuccess) { freeall(); cudaGetLastError(); return fail(ctx, GSPALN_ENOMEM, "scalar kernel buffers", e); }
     cudaEventRecord(ctx->ev[2], ctx->stream);
     const int grid = std::max(1, std::min((n + HNG_WARPS - 1) / HNG_WARPS, 4 * ctx->sm_count));
-    dp_hxild_kernel<<<grid, HNG_THREADS, 0, ctx->stream>>>(ctx->d_ngprm.p, d_t, n, d_tick, d_a, d_b, d_sg, d_i,
-                                                         d_cip, d_work, d_skl, d_res);
+    if (udh)
+        dp_hxudh_kernel<<<grid, HNG_THREADS, 0, ctx->stream>>>(ctx->d_ngprm.p, d_tu, n, d_tick, d_a, d_b, d_sg, d_i,
+                                                             d_cip, d_work, d_cpos, d_ures);
+    else
+        dp_hxild_kernel<<<grid, HNG_THREADS, 0, ctx->stream>>>(ctx->d_ngprm.p, d_t, n, d_tick, d_a, d_b, d_sg, d_i,
+                                                             d_cip, d_work, d_skl, d_res);
     cudaEventRecord(ctx->ev[3], ctx->stream);
     e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
+    if (udh) {
+        std::vector<DevUdhOut> hu(n);
+        std::vector<int> hc(cpos_elems + 1);
+        if (e == cudaSuccess) e = cudaMemcpy(hu.data(), d_ures, (size_t) n * sizeof(DevUdhOut), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(hc.data(), d_cpos, cpos_elems * sizeof(int), cudaMemcpyDeviceToHost);
+        float ums = 0;
+        cudaEventElapsedTime(&ums, ctx->ev[2], ctx->ev[3]);
+        freeall();
+        if (e != cudaSuccess) return fail(ctx, GSPALN_ECUDA, "scalar Hirschberg kernel", e);
+        memset(&ctx->tim, 0, sizeof(ctx->tim));
+        ctx->tim.kernel_ms = ums; ctx->tim.launches = 1; ctx->tim.cells = cells_total;
+        for (int i = 0; i < n; ++i) {
+            gspaln_result& o = results[i];
+            o.score = hu[i].score; o.status = hu[i].status; o.n_skl = 0; o.reserved = 0;
+            o.cells = gspaln_h_task_cells(&tasks[i]);
+            o.ranges[0] = hu[i].a_left; o.ranges[1] = hu[i].a_right; o.ranges[2] = hu[i].b_left; o.ranges[3] = hu[i].b_right;
+            if (o.cpos) memcpy(o.cpos, hc.data() + du[i].cpos_off, sizeof(int) * 10 * (size_t) (tasks[i].n_imd + 1));
+        }
+        return GSPALN_OK;
+    }
     std::vector<DevResult> hres(n);
     std::vector<int2> hskl(skl_elems + 1);
     if (e == cudaSuccess) e = cudaMemcpy(hres.data(), d_res, (size_t) n * sizeof(DevResult), cudaMemcpyDeviceToHost);
@@ -803,8 +866,8 @@ struct LspTraitsH {
     using Ctx = gspaln_h_ctx;
     using Task = gspaln_h_task;
     static constexpr int WPAD = 7;
-    static constexpr bool SCALAR_MODE = false;              // the scalar Hirschberg pass hirschbergH_ng is not on the device
-    static constexpr int KIND_SCALAR_UDH = GSPALN_HIRSCHBERG_WIP;
+    static constexpr bool SCALAR_MODE = true;               // -A0: forwardH_ng + hirschbergH_ng on the device
+    static constexpr int KIND_SCALAR_UDH = GSPALN_HIRSCHBERG_NG;
     static void stripe(LspGeo& g, int sh)       // stripe31(), src/aln2.cc:178-199
     {
         if (sh < 0) {
@@ -823,6 +886,11 @@ struct LspTraitsH {
     }
     static bool small(int m, int nn) { return std::abs(nn - m) < NELEM || m == 1 || nn <= 3; }
     static float cvol(int m, int nn) { return (float) m * (nn + 3 * m); }
+    static float cvol_hex(const LspGeo& g, int m, int nn)
+    {
+        const float k = (float) (g.lw - g.b_left + 3 * g.a_right), q = (float) (g.b_right - 3 * g.a_left - g.up);
+        return (float) m * nn - (k * k + q * q) / 6;
+    }
     static float coef_c(const gspaln_h_params&) { return 12.f; }     // (Noll + 1) * sizeof(int), Noll == 2
     static bool is_local(const gspaln_h_params& P) { return (P.lcl & 16) != 0; }
     static bool udh_ok(const gspaln_h_params&) { return true; }

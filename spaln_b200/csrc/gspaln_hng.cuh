@@ -45,6 +45,7 @@ struct __align__(16) HCell { int val, ptr, dir, pad; };     // RVPD: value, path
 struct DevNgHParams {           // frozen scalars + device pointers of the tables
     int gop, gep, lgop, lgep, codonk1, gw1, gw2, gw3, gw3l, gape1, gape2, extragop;
     int local, spj, noll, minl, simdim, n_penalty;
+    int lcl2, pad_;             // algmode.lcl & 2 (hlastH_ng's termination-codon candidate)
     const int* mtx;             // simmtx[aa][tron], simdim x simdim
     const short* penalty;       // IntronPenalty::Penalty(len)
     const short* sig53tab;      // 544 shorts

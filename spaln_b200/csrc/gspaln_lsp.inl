@@ -182,10 +182,7 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
             bool recursive = (opts->alg & 4) != 0;
             const float coef_B = 2.f, coef_C = TR::coef_c(P);
             float cvol = TR::cvol(m, nn);                       // rhombic (simd >= 2)
-            if (simd < 2) {                                     // hexagonal (src/fwd2s1.cc:1830-1833)
-                const float k = (float) (g.lw - g.b_left + g.a_right), q = (float) (g.b_right - g.a_left - g.up);
-                cvol = (float) m * nn - (k * k + q * q) / 2;
-            }
+            if (simd < 2) cvol = TR::cvol_hex(g, m, nn);         // hexagonal (src/fwd2s1.cc:1830-1833, src/fwd2h1.cc:2161-2164)
             if (!trcbk && coef_B * cvol < opts->max_vmf_space) trcbk = true;
             if (!trcbk && !recursive) {
                 const double z = 2. * m * coef_B / coef_C;

@@ -26,6 +26,17 @@ constexpr int SPPU = 32 / TPSU;         // strips per pass
 constexpr int END_OF_ULK = INT_MAX - 2; // src/aln.h:49
 constexpr int NEVSEL32 = INT_MIN / 16 * 7;  // NEVSEL, src/cmn.h:79
 
+// link arrays of the scalar passes (gspaln_xudh.cuh, gspaln_hxudh.cuh), intermediate i of a problem:
+// hlnk | vlnk | lwrb | uprb, each noll x width ints, indexed by diagonal from lw - 1
+// (UdhIntermediate with bounds, src/udh_intermediate.h:29-66)
+struct UxImd {
+    int* base; int width, noll, lw;
+    __device__ __forceinline__ int& at(int i, int which, int k, int r) const
+    {
+        return base[((long long) (4 * i + which) * noll + k) * width + (r - (lw - 1))];
+    }
+};
+
 // per-row event bits handed from the cell loop to the intermediate-row logic
 enum : unsigned { EV_HORI = 1, EV_VERT = 2, EV_ACC = 4, EV_DON = 8 };
 

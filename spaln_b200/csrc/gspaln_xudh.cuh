@@ -83,15 +83,6 @@ __device__ __forceinline__ int ux_val(const UxCell (&st)[5], int k)
     return v;
 }
 
-// per-problem link arrays of intermediate i: hlnk | vlnk | lwrb | uprb, each noll x width ints
-struct UxImd {
-    int* base; int width, noll, lw;
-    __device__ __forceinline__ int& at(int i, int which, int k, int r) const
-    {
-        return base[((long long) (4 * i + which) * noll + k) * width + (r - (lw - 1))];
-    }
-};
-
 __global__ void __launch_bounds__(NG_THREADS)
 dp_xudh_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs, int n_pen,
                const DevTask* __restrict__ tasks, const int* __restrict__ order, int ntasks, int* ticket,

@@ -483,6 +483,12 @@ class EngineH:
                 out[i] = r
         return out
 
+    def hirschbergH_ng(self, problems):
+        """Aln2h1::hirschbergH_ng, the scalar protein Hirschberg pass of `-A0` (src/fwd2h1.cc:1085-1520).
+        Problems carry n_imd (the count before lspH_ng's even-division correction) and int53; results
+        carry score, ranges and cpos (entries [8], [9]: the diagonal bounds of each block)"""
+        return self.submit(problems, capi.HIRSCHBERG_NG)
+
     def forwardH_ng(self, problems):
         """Aln2h1::trcbkalignH_ng on its scalar branch (forwardH_ng + Vmf trace-back, exact intron
         scoring; src/fwd2h1.cc:294-617, 1997-2041): score + corners.  Problems carry int53."""
@@ -528,7 +534,7 @@ class EngineH:
             t.a_len = int(p.a_len or (len(a) - 1))
             cap = p.skl_cap or ((p.a_right - p.a_left) + (p.b_right - p.b_left) + 8)
             t.skl_cap = cap if kind in (capi.FORWARD_WIP, capi.FORWARD_NG) else 0
-            t.n_imd = int(p.n_imd) if kind == capi.HIRSCHBERG_WIP else 0
+            t.n_imd = int(p.n_imd) if kind in (capi.HIRSCHBERG_WIP, capi.HIRSCHBERG_NG) else 0
         return arr, keep
 
     def _check(self, rc, what):
@@ -542,7 +548,7 @@ class EngineH:
         for i in range(n):
             cap = arr[i].skl_cap
             buf = np.zeros((max(cap, 1), 2), np.int32)
-            cp = np.zeros((arr[i].n_imd + 1, 10), np.int32) if arr[i].kind == capi.HIRSCHBERG_WIP else None
+            cp = np.zeros((arr[i].n_imd + 1, 10), np.int32) if arr[i].kind in (capi.HIRSCHBERG_WIP, capi.HIRSCHBERG_NG) else None
             bufs.append((buf, cp))
             res[i].skl = buf.ctypes.data if cap > 0 else None
             res[i].cpos = cp.ctypes.data if cp is not None else None

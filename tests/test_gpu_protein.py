@@ -222,3 +222,103 @@ def test_homscore_protein_dispatch_matches_reference_golden():
         small = pb["a_right"] - pb["a_left"] < 8
         assert r.score == (pb["ng_score"] if small else pb["score_only"]), pb["tag"]
     eng.close()
+
+
+# ---------------------------------------------------------------------------
+# -A0 for protein queries: scalar Hirschberg pass + the driver on the exact-ILD kernels
+# ---------------------------------------------------------------------------
+EOU = 2 ** 31 - 1 - 2
+
+
+def _sudh_cpos_equal(a, b):
+    for ra, rb in zip(a.tolist(), b.tolist()):
+        ka = ra.index(EOU) if EOU in ra[:8] else 8
+        kb = rb.index(EOU) if EOU in rb[:8] else 8
+        if ra[:ka] != rb[:kb] or (ka > 0 and ra[8:] != rb[8:]):
+            return False
+    return True
+
+
+@pytest.mark.parametrize("name", golden_io.PROTEIN_A0_NAMES)
+def test_scalar_protein_hirschberg_pass_matches_reference_golden(name):
+    """gspaln_h_submit(GSPALN_HIRSCHBERG_NG) == Aln2h1::hirschbergH_ng: score, crossing records with
+    their diagonal bounds, narrowed ranges -- 1, 2 and 5 intermediate rows, global and local"""
+    from spaln_b200 import EngineH
+    prm, probs = golden_io.load_protein(name)
+    eng = EngineH(prm, device=0)
+    n = 0
+    for nn in (1, 2, 5):
+        sel = [pb for pb in probs if f"sudh{nn}_nim" in pb]
+        P = _problems(sel)
+        for p in P:
+            p.n_imd = nn
+        for i, (pb, r) in enumerate(zip(sel, eng.hirschbergH_ng(P))):
+            assert r.status == 0, (name, nn, i, pb["tag"], r.status)
+            assert r.score == pb[f"sudh{nn}_score"], (name, nn, i, pb["tag"], r.score, pb[f"sudh{nn}_score"])
+            if r.score > -(1 << 28):
+                assert list(r.ranges) == pb[f"sudh{nn}_ranges"].tolist(), (name, nn, i, pb["tag"])
+                assert _sudh_cpos_equal(r.cpos[: pb[f"sudh{nn}_nim"] + 1], pb[f"sudh{nn}_cpos"]), (name, nn, i, pb["tag"])
+            n += 1
+    assert n >= 40
+    eng.close()
+
+
+@pytest.mark.parametrize("name,flags", [
+    ("prot_A0_udh", None),
+    ("prot_A0_udh", [(0, 0, 0, 0), (1, 0, 1, 0), (0, 1, 0, 1), (1, 1, 0, 0), (0, 0, 1, 1)]),
+    ("prot_A0_udh_local", None),
+])
+def test_scalar_protein_hirschberg_pass_matches_oracle_seeded(oracle, name, flags):
+    from spaln_b200 import EngineH, workload
+    prm, _ = golden_io.load_protein(name)
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(repr(("hxudh", name, flags)).encode()))
+    probs = _synthetic_protein(prm, rng, 20, (30, 300), (30, 400), flags, False)
+    for pb in probs:
+        if pb.get("int53") is None:     # site classes from the nucleotide sequence behind the tron codes
+            pb["int53"] = workload.synthetic_int53(workload.encode_dna(pb["genome"]))
+    P = _problems(probs)
+    want = []
+    for pb, p in zip(probs, P):
+        m = pb["a_right"] - pb["a_left"]
+        p.n_imd = int(rng.choice([1, 2, 3, 6, max(1, m // 16), max(1, m // 9)]))
+        intvl = (m + p.n_imd) // (p.n_imd + 1)
+        nq = p.n_imd - 1 if intvl * p.n_imd == m else p.n_imd
+        want.append(oracle.hirschberg_h_ng(prm, pb, nq, intvl) if nq >= 1 else None)
+    eng = EngineH(prm, device=0)
+    n = 0
+    for i, (p, r, o) in enumerate(zip(P, eng.hirschbergH_ng(P), want)):
+        if o is None:
+            continue
+        assert r.status == 0 and r.score == o["score"], (name, i, p.n_imd, r.status, r.score, o["score"])
+        if r.score > -(1 << 28):
+            assert list(r.ranges) == o["ranges"], (name, i, p.n_imd)
+            assert _sudh_cpos_equal(r.cpos[: len(o["cpos"])], o["cpos"]), (name, i, p.n_imd)
+        n += 1
+    assert n >= 15
+    eng.close()
+
+
+@pytest.mark.parametrize("name", golden_io.PROTEIN_A0_NAMES)
+def test_lspH_ng_driver_scalar_mode_matches_reference_golden(oracle, name):
+    """gspaln_h_lsp with alg = 0 == Aln2h1::lspH_ng under -A0"""
+    from spaln_b200 import EngineH
+    prm, probs = golden_io.load_protein(name)
+    eng = EngineH(prm, device=0)
+    n_route = 0
+    for vmf in (int(prm["MaxVmfSpace"]), 32 * 1024 * 1024):
+        res = eng.lspH_ng(_problems(probs), max_vmf_space=vmf, sh=int(prm["sh"]), alg=0)
+        for i, (pb, r) in enumerate(zip(probs, res)):
+            assert r.status == 0, (name, vmf, i, pb["tag"], r.status)
+            if vmf == int(prm["MaxVmfSpace"]):
+                want_score, want_skl = pb["lsp_score"], pb["lsp_skl"]
+                m, n = pb["a_right"] - pb["a_left"], pb["b_right"] - pb["b_left"]
+                k, q = pb["lw"] - pb["b_left"] + 3 * pb["a_right"], pb["b_right"] - 3 * pb["a_left"] - pb["up"]
+                n_route += 2.0 * (m * n - (k * k + q * q) / 6) >= vmf
+            else:
+                o = oracle.lsp_h(prm, pb, max_vmf_space=vmf)
+                want_score, want_skl = o["score"], o["skl"]
+            assert r.score == want_score, (name, vmf, i, pb["tag"], r.score, want_score)
+            assert np.array_equal(r.skl, want_skl), (name, vmf, i, pb["tag"])
+    assert n_route >= 6
+    eng.close()

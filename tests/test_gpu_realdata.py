@@ -78,19 +78,21 @@ PROT_MD5_A1 = "0a31a60ecbfba6f22b8c76609721b3ea"  # -A1
 
 @pytest.mark.parametrize("alg,md5", [("-A0", PROT_MD5_A0), ("-A1", PROT_MD5_A1)])
 def test_protein_sample_gff_identical_through_dropin_scalar_modes(ws, alg, md5):
-    """`-A0`: every trcbkalignH_ng / HomScoreH_ng call of the run takes the reference's scalar branch
-    (forwardH_ng), which the drop-in sends to the exact-ILD kernel; the drivers and the Hirschberg
-    passes stay with the stock code.  `-A1`: only blocks with fewer than 8 query rows do."""
+    """`-A0`: lspH_ng runs on the device as a whole (forwardH_ng / hirschbergH_ng kernels), as does every
+    other trcbkalignH_ng / HomScoreH_ng call.  `-A1`: only blocks with fewer than 8 query rows do."""
     opts = ["-Q7", "-O0", alg, "-t1", "-pq", "-Tdictdisc"]
     q = realdata.SEQDB / "dictdisc.faa"
     cpu = ws.run("spaln", opts, q)
     assert hashlib.md5(cpu).hexdigest() == md5
     st = {}
     assert ws.run("spaln_gpu", opts, q, stats=st) == cpu
-    # the device answered: every trace-back of -A0, the few-row blocks of -A1
-    # (the protein sample makes 61 non-trivial trcbkalignH_ng calls; -A2 answers as many lspH_ng calls)
-    assert st["protein"]["trcbk_exact"] >= (50 if alg == "-A0" else 1), st
-    assert st["protein"]["lsp"] == 0 and st["protein"]["trcbk_wip"] == 0, st
+    # the device answered: the whole driver at -A0 (61 lspH_ng calls on this sample, as at -A2), the
+    # few-row blocks of -A1
+    if alg == "-A0":
+        assert st["protein"]["lsp"] >= 50, st
+    else:
+        assert st["protein"]["trcbk_exact"] >= 1 and st["protein"]["lsp"] == 0, st
+    assert st["protein"]["trcbk_wip"] == 0, st
     assert st["protein"]["exact_no_tables"] == 0 and st["protein"]["exact_overflow"] == 0, st
 
 
@@ -168,6 +170,7 @@ def harvest_runs(ws, prot, cq):
     runs = []
     for q in ("-Q7", "-Q6", "-Q5"):       # (-Q4 crashes the stock reference on this sample)
         runs.append((f"prot{q}", [q, "-O0", "-A2", "-t1", "-pq", "-Tdictdisc"], prot))
+    runs.append(("prot-Q7A0", ["-Q7", "-O0", "-A0", "-t1", "-pq", "-Tdictdisc"], prot))
     for tag, o in (("Q7", ["-Q7", "-A2"]), ("Q4", ["-Q4", "-A2"]), ("Q7A3", ["-Q7", "-A3"]),
                    ("Q5LS", ["-Q5", "-A2", "-LS"]), ("Q7A0", ["-Q7", "-A0"])):
         runs.append((f"cdna{tag}", o + ["-O4", "-S3", f"-t{ws.threads}", "-pq", "-Tdictdisc"], cq))

@@ -50,14 +50,14 @@ def ws():
     w.close()
 
 
-@pytest.mark.parametrize("kind", ["cdna", "protein", "cdna_A0"])
+@pytest.mark.parametrize("kind", ["cdna", "protein", "cdna_A0", "protein_A0"])
 def test_oracle_reproduces_harvested_lsp_calls(ws, kind):
     if kind.startswith("cdna"):
         q = ws.head_fasta(realdata.SEQDB / "dictdisc.cf", 120)
         opts = ["-Q7", "-O4", "-S3", "-A0" if kind == "cdna_A0" else "-A2", f"-t{ws.threads}", "-pq", "-Tdictdisc"]
     else:
         q = realdata.SEQDB / "dictdisc.faa"
-        opts = ["-Q7", "-O0", "-A2", "-t1", "-pq", "-Tdictdisc"]
+        opts = ["-Q7", "-O0", "-A0" if kind == "protein_A0" else "-A2", "-t1", "-pq", "-Tdictdisc"]
     hv = ws.dir / f"oracle_{kind}.harvest"
     ws.run("spaln_harvest", opts, q, harvest=hv)
     prm = None
