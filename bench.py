@@ -133,28 +133,36 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# newest first: the packed kernel the config-2 batch runs on (PK = 8), then the round-1 32-bit kernel
+TRAFFIC_FILES = ("r02_traffic.json", "r01_traffic.json")
+NCU_FILES = ("r02_ncu_full_dp_wip_pk8_q3000.json", "r02_ncu_full_dp_wip_pk4_q3000.json", "r01_ncu_full_dp_wip_q3000.json")
+
+
 def measured_traffic_per_cell():
     """DRAM bytes per cell of the DP kernel from the committed `ncu --set full` capture"""
-    p = ROOT / "profiles" / "r01_traffic.json"
-    try:
-        return float(json.loads(p.read_text())["dram_bytes_per_cell"])
-    except Exception:
-        return None
+    for name in TRAFFIC_FILES:
+        try:
+            return float(json.loads((ROOT / "profiles" / name).read_text())["dram_bytes_per_cell"]), name
+        except Exception:
+            continue
+    return None, None
 
 
 def binding_resource():
     """what binds the DP kernel according to the committed `ncu --set full` capture (the HBM
     roofline is reported as the contract asks, but the kernel is integer-ALU bound)"""
-    p = ROOT / "profiles" / "r01_ncu_full_dp_wip_q3000.json"
-    try:
-        d = json.loads(p.read_text())[0]
-        return {"resource": "integer ALU pipe (max / add / select recurrences on int16 cells)",
-                "pipe_alu_pct_of_peak": d["pipe_alu_pct"]["value"], "pipe_fma_pct_of_peak": d["pipe_fma_pct"]["value"],
-                "issue_slots_busy_pct": d["issue_slots_busy_pct"]["value"],
-                "warp_instructions_per_cell": d["warp_instructions"]["value"] / d["cells"],
-                "source": "profiles/r01_ncu_full_dp_wip_q3000.json"}
-    except Exception:
-        return None
+    for name in NCU_FILES:
+        try:
+            d = json.loads((ROOT / "profiles" / name).read_text())[0]
+            return {"resource": "integer ALU pipe (packed int16x2 max / add / select recurrences)",
+                    "pipe_alu_pct_of_peak": d["pipe_alu_pct"]["value"], "pipe_fma_pct_of_peak": d["pipe_fma_pct"]["value"],
+                    "issue_slots_busy_pct": d["issue_slots_busy_pct"]["value"],
+                    "warp_instructions_per_cell": d["warp_instructions"]["value"] / d["cells"],
+                    "thread_instructions_per_cell": d["warp_instructions"]["value"] * d["active_threads_per_warp_inst"]["value"] / d["cells"],
+                    "source": "profiles/" + name}
+        except Exception:
+            continue
+    return None
 
 
 def measured_peak():
@@ -1099,11 +1107,11 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         "traffic": (measured_traffic_per_cell() * cells_step
-                                     if measured_traffic_per_cell() else None),
-                         "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes per cell x cells of this launch)",
+                         "traffic": (measured_traffic_per_cell()[0] * cells_step
+                                     if measured_traffic_per_cell()[0] else None),
+                         "traffic_source": f"profiles/{measured_traffic_per_cell()[1]} (ncu dram__bytes per cell x cells of this launch)",
                          "peak_kind": peak_kind,
-                         "bytes_per_cell": B_CELL, "kernel": "dp_wip_kernel<true>",
+                         "bytes_per_cell": B_CELL, "kernel": "dp_wip_kernel<TRACE, PK> (packed int16x2)",
                          "kernel_ms": k_ms,
                          "note": "integer-ALU bound DP: see DESIGN.md (HBM roof is not the binding one)",
                          "binding": binding_resource()},
