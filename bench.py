@@ -517,6 +517,91 @@ def config4_leg(args, ncores, with_cpu):
     return out
 
 
+def a0_leg(args, ncores, with_cpu):
+    """The reference's DEFAULT mode (-A0: exact intron-length scoring, scalar kernels) on config-2
+    problems through the driver: Aln2s1::lspS_ng with algmode.alg == 0 at -V 32 MiB -- exact-ILD
+    trace-backs (forwardS_ng), the scalar Hirschberg pass (hirschbergS_ng) for the problems above the
+    space limit, blocks banded by the pass.  Wall clock with host buffers."""
+    import golden_io
+    from spaln_b200 import Engine, Result
+    prm, _ = golden_io.load("dna_A0_udh")
+    nq = max(64, args.queries // 10)
+    raw = make_workload(nq, SEED + 7)
+    problems = to_problems(raw)
+    host_cells(raw)
+    cells = sum(r["cells"] for r in raw)
+    eng = Engine(prm, device=0)
+    opts = dict(max_vmf_space=32 * 1024 * 1024, sh=int(prm["sh"]), alg=0)
+    eng.lspS_ng(problems[: max(8, nq // 10)], **opts)       # pools
+    pk = eng.pack(problems)
+    t0 = time.perf_counter()
+    eng.lsp_packed(pk, **opts)
+    dt = time.perf_counter() - t0
+    tm = eng.timing()
+    res = [Result(int(pk.scores[i]), int(pk.status[i]), pk.corners(i).copy(), 0) for i in range(nq)]
+    out = {"note": "the reference's default mode -A0 on config-2 problems: Aln2s1::lspS_ng (alg 0) at -V 32 MiB -- "
+                   "exact-ILD kernels dp_xild_kernel / dp_xudh_kernel, wall clock with host buffers",
+           "queries": nq, "root_cells": cells, "queries_per_s": nq / dt, "gcups_root_cells": cells / dt / 1e9,
+           "kernel_ms": tm.kernel_ms, "total_ms": 1e3 * dt, "launches": tm.launches, "device_cells": tm.cells,
+           "status_nonzero": sum(1 for r in res if r.status != 0)}
+    eng.close()
+    if with_cpu:
+        k = min(nq, 2 * ncores)
+        child = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--leg", "a0-ref", "--leg-seed", str(k),
+                                "--queries", str(args.queries)], capture_output=True, text=True)
+        try:
+            c = json.loads(child.stdout.strip().splitlines()[-1])
+            mism = sum(1 for i in range(k) if res[i].status != 0 or c["scores"][i] != res[i].score or
+                       not np.array_equal(np.array(c["skl"][i], np.int32).reshape(-1, 2), res[i].skl))
+            out["cpu_baseline"] = {"queries_per_s": c["queries_per_s"], "gcups_root_cells": c["gcups"],
+                                   "cores": c["cores"], "kind": "reference",
+                                   "sample": f"first {k} problems, Aln2s1::lspS_ng of the AVX2 build at -A0 "
+                                             f"(scalar forwardS_ng / hirschbergS_ng), {c['cores']} threads, own process",
+                                   "parity_mismatches_on_sample": mism}
+        except Exception as e:      # the reference arm is a reported baseline, never the product
+            out["cpu_baseline"] = {"value": None, "error": f"{type(e).__name__}: {child.stderr[-200:]}"}
+    return out
+
+
+def a0_reference_child(args):
+    """child process: the reference's own lspS_ng at -A0 on the first k problems of the -A0 leg"""
+    import threading
+    import ref_harness
+    k = args.leg_seed
+    nq = max(64, args.queries // 10)
+    raw = with_strings(make_workload(nq, SEED + 7))[:k]
+    ref = ref_harness.Reference("-Q0 -A0 -S1 -yX0 -TDictyost")
+    tasks = []
+    for r in raw:
+        t = ref.task(r["genome_str"], r["query_str"])
+        t.inject(r["sig5"], r["sig3"])
+        tasks.append(t)
+    ncores = os.cpu_count() or 1
+    outs = [None] * k
+    nxt = [0]
+    lock = threading.Lock()
+
+    def work():
+        while True:
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+            if i >= k:
+                return
+            outs[i] = tasks[i].lsp(raw[i]["lw"], raw[i]["up"], cap=1 << 17)
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work) for _ in range(min(ncores, k))]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    dt = time.perf_counter() - t0
+    host_cells(raw)
+    cells = sum(r["cells"] for r in raw)
+    print(json.dumps({"queries_per_s": k / dt, "gcups": cells / dt / 1e9, "cores": min(ncores, k),
+                      "scores": [o["score"] for o in outs], "skl": [o["skl"].tolist() for o in outs]}))
+    return 0
+
+
 def config4_reference_child(args):
     """child process: the reference's own lspS_ng (-LS) on the first k config-4 problems"""
     import threading
@@ -831,6 +916,8 @@ def main():
         return protein_reference_child(args.cpu_sample, args.leg_seed, os.cpu_count() or 1, args.leg_out)
     if args.leg == "config4-ref":
         return config4_reference_child(args)
+    if args.leg == "a0-ref":
+        return a0_reference_child(args)
     _quiet_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -1127,6 +1214,7 @@ def main():
         if n_gpus == 1:
             line["scan_path"] = scan_leg(prm, with_cpu=not args.no_cpu_baseline)
             line["config4_path"] = config4_leg(args, ncores, with_cpu=not args.no_cpu_baseline)
+            line["a0_path"] = a0_leg(args, ncores, with_cpu=not args.no_cpu_baseline)
         if world > 1:
             line["bcast_ms"] = 1e3 * phases[0]
             line["gather_ms"] = 1e3 * phases[3]

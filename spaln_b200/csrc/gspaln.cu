@@ -62,6 +62,8 @@ struct gspaln_ctx {
     DevBuf<int> d_ngs;              // score-only scalar kernel: three int rows per thread
     int n_ngs = 0, grid_run_ngs = 0;
     size_t ngs_width = 0;
+    bool ng_full_records = false;       // second run of the trace-backs whose record store overflowed
+    int ng_rec_eighths = 4;             // records per cell of the first run, in eighths (GSPALN_NG_REC_EIGHTHS)
     int n_xudh = 0, grid_run_xudh = 0;  // scalar Hirschberg pass (GSPALN_HIRSCHBERG_NG)
     size_t xudh_width = 0;
     PinBuf<DevTask> h_tasks;
@@ -399,6 +401,7 @@ int gspaln_set_ng_tables(gspaln_ctx* ctx, const int16_t* sig53tab, const int16_t
     CK(cudaMemcpy(ctx->d_prm.p, &ctx->hP, sizeof(DevParams), cudaMemcpyHostToDevice));
     ctx->n_pen = n_penalty;
     ctx->ng_ready = true;
+    if (const char* e = getenv("GSPALN_NG_REC_EIGHTHS")) ctx->ng_rec_eighths = std::max(1, std::min(24, atoi(e)));
     return GSPALN_OK;
 }
 
@@ -492,7 +495,9 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         } else if (t.kind == GSPALN_FORWARD_NG) {
             // path records: at most one per cell plus two per gap state at acceptor columns
             ng_width = std::max(ng_width, (size_t) width);
-            ng_rec = std::max(ng_rec, (size_t) std::min<int64_t>(3 * ctx->cells[i] + 2 * width + 64, INT_MAX / 4));
+            const int64_t full = 3 * ctx->cells[i] + 2 * width + 64;
+            const int64_t typical = ctx->cells[i] * ctx->ng_rec_eighths / 8 + 2 * width + 4096;
+            ng_rec = std::max(ng_rec, (size_t) std::min<int64_t>(ctx->ng_full_records ? full : std::min(full, typical), INT_MAX / 4));
             skl_elems += (size_t) d.skl_cap;
             ++n_ng;
         } else if (t.kind == GSPALN_SCOREALONE_NG) {
@@ -872,9 +877,40 @@ int gspaln_download(gspaln_ctx* ctx, gspaln_result* results)
 // kernels start, and while they run the host threads pack the following chunks into pinned
 // memory and a second stream copies them and advances a watermark the kernels wait on.
 // Packing and H2D of everything but the first chunk hide behind the DP.
+static int submit_once(gspaln_ctx* ctx, const gspaln_task* tasks, int n, gspaln_result* results);
+
+// The path records of GSPALN_FORWARD_NG (the reference's Vmf) can number three per cell in theory
+// and a fraction of one in practice; sizing every warp's store for the worst case leaves room for a
+// few dozen problems in flight.  So the first run gives each problem a store for its typical need
+// and the (rare) problems that report GSPALN_ST_VMF_OVERFLOW are run once more with the full bound.
 int gspaln_submit(gspaln_ctx* ctx, const gspaln_task* tasks, int n, gspaln_result* results)
 {
     if (!ctx || !tasks || n < 0) return GSPALN_EINVAL;
+    int rc = submit_once(ctx, tasks, n, results);
+    if (rc != GSPALN_OK || ctx->ng_full_records) return rc;
+    std::vector<int> again;
+    for (int i = 0; i < n; ++i)
+        if (tasks[i].kind == GSPALN_FORWARD_NG && results[i].status == GSPALN_ST_VMF_OVERFLOW) again.push_back(i);
+    if (again.empty()) return GSPALN_OK;
+    static const bool dbg = getenv("GSPALN_LSP_DEBUG") != nullptr;
+    if (dbg) fprintf(stderr, "gspaln: %zu of %d exact-ILD trace-backs need the full record store\n", again.size(), n);
+    std::vector<gspaln_task> t2(again.size());
+    std::vector<gspaln_result> r2(again.size());
+    for (size_t k = 0; k < again.size(); ++k) { t2[k] = tasks[again[k]]; r2[k] = results[again[k]]; }
+    const gspaln_timing first = ctx->tim;
+    ctx->ng_full_records = true;
+    rc = submit_once(ctx, t2.data(), (int) t2.size(), r2.data());
+    ctx->ng_full_records = false;
+    if (rc != GSPALN_OK) return rc;
+    for (size_t k = 0; k < again.size(); ++k) results[again[k]] = r2[k];
+    ctx->tim.kernel_ms += first.kernel_ms; ctx->tim.h2d_ms += first.h2d_ms; ctx->tim.d2h_ms += first.d2h_ms;
+    ctx->tim.launches += first.launches; ctx->tim.h2d_bytes += first.h2d_bytes; ctx->tim.d2h_bytes += first.d2h_bytes;
+    ctx->tim.cells += first.cells; ctx->tim.trace_bytes += first.trace_bytes;
+    return GSPALN_OK;
+}
+
+static int submit_once(gspaln_ctx* ctx, const gspaln_task* tasks, int n, gspaln_result* results)
+{
     int rc = plan_batch(ctx, tasks, n);
     if (rc != GSPALN_OK) return rc;
     int bounds[MAX_CHUNKS + 1];

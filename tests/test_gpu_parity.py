@@ -740,3 +740,20 @@ def test_lsp_driver_scalar_mode_matches_reference_golden(oracle, name):
             assert np.array_equal(r.skl, want_skl), (name, vmf, i, pb["tag"])
     assert n_route >= 12
     eng.close()
+
+
+def test_exact_ild_trace_back_reruns_with_the_full_record_store(oracle, monkeypatch):
+    """the first run of GSPALN_FORWARD_NG sizes the path-record store (the reference's Vmf) for a
+    typical problem; problems that overflow it are run again with the worst-case bound inside
+    gspaln_submit.  With a starved first run (1/8 record per cell) every larger problem takes that
+    second run, and the results must not change."""
+    monkeypatch.setenv("GSPALN_NG_REC_EIGHTHS", "1")
+    prm, _ = golden_io.load("dna_A2_global")
+    rng = np.random.default_rng(4242)
+    probs = _synthetic(prm, rng, 24, (100, 600), (200, 1500))
+    eng = _engine(prm)
+    res = eng.forwardS_ng(_problems(probs))
+    for i, (pb, r) in enumerate(zip(probs, res)):
+        o = oracle.trcbk_ng(prm, pb)
+        assert r.status == 0 and r.score == o["score"] and np.array_equal(r.skl, o["skl"]), (i, r.status)
+    eng.close()
