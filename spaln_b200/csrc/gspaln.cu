@@ -64,7 +64,9 @@ struct gspaln_ctx {
     size_t ngs_width = 0;
     bool ng_full_records = false;       // second run of the trace-backs whose record store overflowed
     int ng_rec_eighths = 4;             // records per cell of the first run, in eighths (GSPALN_NG_REC_EIGHTHS)
-    int n_xudh = 0, grid_run_xudh = 0;  // scalar Hirschberg pass (GSPALN_HIRSCHBERG_NG)
+    int n_xudh = 0, grid_run_xudh = 0;  // scalar Hirschberg pass (GSPALN_HIRSCHBERG_NG): one warp per problem
+    int n_xudh_w = 0, grid_run_xudh_w = 0;  // ... queries of XUDH_WIDE_ROWS rows and more: XUDH_WIDE warps per problem
+    int n_ng_w = 0, grid_run_ng_w = 0, n_ngs_w = 0, grid_run_ngs_w = 0;    // exact-ILD kernels, wide class (NG_WIDE warps per problem)
     size_t xudh_width = 0;
     PinBuf<DevTask> h_tasks;
     PinBuf<int> h_order;
@@ -452,7 +454,7 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
                      [&](int x, int y) { return ctx->cells[x] > ctx->cells[y]; });
     size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, skl_elems = 0;
     size_t udh_slab = 0, cpos_elems = 0;
-    int n_trace = 0, n_score = 0, n_udh = 0, n_ng = 0, n_ngs = 0, n_xudh = 0;
+    int n_trace = 0, n_score = 0, n_udh = 0, n_ng = 0, n_ngs = 0, n_xudh = 0, n_xudh_w = 0, n_ng_w = 0, n_ngs_w = 0;
     size_t ng_width = 0, ng_rec = 0, ngs_width = 0, xudh_width = 0, xudh_links = 0;
     int n_trace_c[3] = {0, 0, 0}, n_score_c[3] = {0, 0, 0};
     size_t band_slab_c[3] = {0, 0, 0}, trace_slab_c[3] = {0, 0, 0};
@@ -499,10 +501,12 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             const int64_t typical = ctx->cells[i] * ctx->ng_rec_eighths / 8 + 2 * width + 4096;
             ng_rec = std::max(ng_rec, (size_t) std::min<int64_t>(ctx->ng_full_records ? full : std::min(full, typical), INT_MAX / 4));
             skl_elems += (size_t) d.skl_cap;
-            ++n_ng;
+            if (mw >= NG_WIDE_ROWS) { d.flags |= 32; ++n_ng_w; }           // a CTA of warps per problem
+            else ++n_ng;
         } else if (t.kind == GSPALN_SCOREALONE_NG) {
             ngs_width = std::max(ngs_width, (size_t) width);
-            ++n_ngs;
+            if (mw >= NG_WIDE_ROWS) { d.flags |= 32; ++n_ngs_w; }
+            else ++n_ngs;
         } else if (t.kind == GSPALN_HIRSCHBERG_NG) {
             // band rows of 32-byte cells + hlnk | vlnk | lwrb | uprb per intermediate row
             d.pad0 = t.n_imd;
@@ -510,7 +514,8 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             cpos_elems += (size_t) 10 * (t.n_imd + 1);
             xudh_width = std::max(xudh_width, (size_t) width);
             xudh_links = std::max(xudh_links, (size_t) t.n_imd * 4 * ctx->prm.noll * (size_t) width);
-            ++n_xudh;
+            if (mw >= XUDH_WIDE_ROWS) { d.flags |= 32; ++n_xudh_w; }       // a CTA of warps per problem
+            else ++n_xudh;
         } else if (t.kind == GSPALN_HIRSCHBERG_WIP) {
             d.pad0 = t.n_imd;
             d.pad1 = (long long) cpos_elems;
@@ -588,15 +593,19 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         // exact-ILD kernels: one warp per problem, per-warp workspace = band rows (H, F, F2 as
         // {value, record}) + direction bytes + path records; the trace-back and the score-only
         // kernel never run at the same time, so they share the pool
-        ctx->grid_run_ng = ctx->grid_run_ngs = ctx->grid_run_xudh = 0;
-        if (n_ng || n_ngs || n_xudh) {
+        ctx->grid_run_ng = ctx->grid_run_ngs = ctx->grid_run_xudh = ctx->grid_run_xudh_w = 0;
+        ctx->grid_run_ng_w = ctx->grid_run_ngs_w = 0;
+        if (n_ng || n_ngs || n_xudh || n_xudh_w || n_ng_w || n_ngs_w) {
             const size_t w = std::max(ng_width, ngs_width);
-            const size_t rec = n_ng ? ng_rec + 32 * NG_CHUNK + 64 : 64;
+            const size_t rec = (n_ng || n_ng_w) ? ng_rec + 32 * NG_WIDE * NG_CHUNK + 64 : 64;
             size_t slab = align_up(3 * w * sizeof(NgRvp) + align_up(w, 16) + 12 * rec, 16);
             // the scalar Hirschberg pass shares the pool (the kernels run one after the other)
-            const size_t xslab = n_xudh ? align_up(3 * xudh_width * sizeof(UxSlot) + 4 * xudh_links + 64, 32) : 0;
+            const size_t xslab = (n_xudh || n_xudh_w) ? align_up(3 * xudh_width * sizeof(UxSlot) + 4 * xudh_links + 64, 32) : 0;
             slab = align_up(std::max(slab, xslab), 32);
-            int g = std::min((std::max(std::max(n_ng, n_ngs), n_xudh) + NG_WARPS - 1) / NG_WARPS, 4 * ctx->sm_count);
+            // (the wide class runs one problem per CTA: a quarter of the slabs of a 4-warp CTA)
+            const int wide = std::max(std::max(n_xudh_w, n_ng_w), n_ngs_w);
+            const int need = std::max(std::max(std::max(n_ng, n_ngs), n_xudh), std::min(wide, 2 * ctx->sm_count));
+            int g = std::min((need + NG_WARPS - 1) / NG_WARPS, 4 * ctx->sm_count);
             cudaMemGetInfo(&free_b, &total_b);
             const size_t room = (size_t) (0.5 * (double) (free_b + ctx->d_ngwork.cap));
             while (g > 1 && (size_t) g * NG_WARPS * slab > room) g = g * 3 / 4;
@@ -607,12 +616,15 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             ctx->grid_run_ng = n_ng ? std::min(g, (n_ng + NG_WARPS - 1) / NG_WARPS) : 0;
             ctx->grid_run_ngs = n_ngs ? std::min(g, (n_ngs + NG_WARPS - 1) / NG_WARPS) : 0;
             ctx->grid_run_xudh = n_xudh ? std::min(g, (n_xudh + NG_WARPS - 1) / NG_WARPS) : 0;
+            ctx->grid_run_xudh_w = n_xudh_w ? std::min(std::min(n_xudh_w, g * NG_WARPS), 2 * ctx->sm_count) : 0;
+            ctx->grid_run_ng_w = n_ng_w ? std::min(std::min(n_ng_w, g * NG_WARPS), 2 * ctx->sm_count) : 0;
+            ctx->grid_run_ngs_w = n_ngs_w ? std::min(std::min(n_ngs_w, g * NG_WARPS), 2 * ctx->sm_count) : 0;
             ctx->ng_slab = slab; ctx->ng_width = w; ctx->ng_rec_cap = (int) rec;
             ctx->xudh_width = xudh_width;
         }
     }
     ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score; ctx->n_udh = n_udh; ctx->n_ng = n_ng;
-    ctx->n_ngs = n_ngs; ctx->n_xudh = n_xudh;
+    ctx->n_ngs = n_ngs; ctx->n_xudh = n_xudh; ctx->n_xudh_w = n_xudh_w; ctx->n_ng_w = n_ng_w; ctx->n_ngs_w = n_ngs_w;
     ctx->udh_slab = udh_slab; ctx->cpos_elems = cpos_elems;
     ctx->a_bytes = a_bytes; ctx->c_elems = c_elems; ctx->band_slab = band_slab;
     ctx->trace_slab = trace_slab; ctx->skl_elems = skl_elems;
@@ -764,22 +776,43 @@ static int launch_range(gspaln_ctx* ctx, int lo, int hi, int slot, int& launches
             ctx->d_udh.p, (long long) ctx->udh_slab, ctx->d_cpos.p, ctx->d_ures.p, ready);
         ++launches;
     }
+    if (ctx->n_ng_w) {
+        dp_xild_kernel<false, NG_WIDE><<<ctx->grid_run_ng_w, 32 * NG_WIDE, 0, ctx->stream>>>(
+            ctx->d_prm.p, ctx->d_ngtab.p, ctx->n_pen, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 6,
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_ngwork.p, (long long) ctx->ng_slab,
+            (long long) ctx->ng_width, ctx->ng_rec_cap, ctx->d_skl.p, ctx->d_res.p, ready);
+        ++launches;
+    }
+    if (ctx->n_ngs_w) {
+        dp_xild_kernel<true, NG_WIDE><<<ctx->grid_run_ngs_w, 32 * NG_WIDE, 0, ctx->stream>>>(
+            ctx->d_prm.p, ctx->d_ngtab.p, ctx->n_pen, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 7,
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_ngwork.p, (long long) ctx->ng_slab,
+            (long long) ctx->ng_width, ctx->ng_rec_cap, ctx->d_skl.p, ctx->d_res.p, ready);
+        ++launches;
+    }
     if (ctx->n_ng) {
-        dp_xild_kernel<false><<<ctx->grid_run_ng, NG_THREADS, 0, ctx->stream>>>(
+        dp_xild_kernel<false, 1><<<ctx->grid_run_ng, NG_THREADS, 0, ctx->stream>>>(
             ctx->d_prm.p, ctx->d_ngtab.p, ctx->n_pen, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 8,
             ctx->d_apool.p, ctx->d_cpool.p, ctx->d_ngwork.p, (long long) ctx->ng_slab,
             (long long) ctx->ng_width, ctx->ng_rec_cap, ctx->d_skl.p, ctx->d_res.p, ready);
         ++launches;
     }
     if (ctx->n_ngs) {
-        dp_xild_kernel<true><<<ctx->grid_run_ngs, NG_THREADS, 0, ctx->stream>>>(
+        dp_xild_kernel<true, 1><<<ctx->grid_run_ngs, NG_THREADS, 0, ctx->stream>>>(
             ctx->d_prm.p, ctx->d_ngtab.p, ctx->n_pen, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 9,
             ctx->d_apool.p, ctx->d_cpool.p, ctx->d_ngwork.p, (long long) ctx->ng_slab,
             (long long) ctx->ng_width, ctx->ng_rec_cap, ctx->d_skl.p, ctx->d_res.p, ready);
         ++launches;
     }
+    if (ctx->n_xudh_w) {
+        dp_xudh_kernel<XUDH_WIDE><<<ctx->grid_run_xudh_w, 32 * XUDH_WIDE, 0, ctx->stream>>>(
+            ctx->d_prm.p, ctx->d_ngtab.p, ctx->n_pen, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 11,
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_ngwork.p, (long long) ctx->ng_slab,
+            (long long) ctx->xudh_width, ctx->d_cpos.p, ctx->d_ures.p, ready);
+        ++launches;
+    }
     if (ctx->n_xudh) {
-        dp_xudh_kernel<<<ctx->grid_run_xudh, NG_THREADS, 0, ctx->stream>>>(
+        dp_xudh_kernel<1><<<ctx->grid_run_xudh, NG_THREADS, 0, ctx->stream>>>(
             ctx->d_prm.p, ctx->d_ngtab.p, ctx->n_pen, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 10,
             ctx->d_apool.p, ctx->d_cpool.p, ctx->d_ngwork.p, (long long) ctx->ng_slab,
             (long long) ctx->xudh_width, ctx->d_cpos.p, ctx->d_ures.p, ready);
@@ -841,7 +874,7 @@ int gspaln_download(gspaln_ctx* ctx, gspaln_result* results)
     if (n) CK(cudaMemcpyAsync(ctx->h_res.p, ctx->d_res.p, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (ctx->skl_elems)
         CK(cudaMemcpyAsync(ctx->h_skl.p, ctx->d_skl.p, sizeof(int2) * ctx->skl_elems, cudaMemcpyDeviceToHost, ctx->stream));
-    if (ctx->n_udh || ctx->n_xudh) {
+    if (ctx->n_udh || ctx->n_xudh || ctx->n_xudh_w) {
         CK(cudaMemcpyAsync(ctx->h_ures.p, ctx->d_ures.p, sizeof(DevUdhOut) * n, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_cpos.p, ctx->d_cpos.p, sizeof(int) * ctx->cpos_elems, cudaMemcpyDeviceToHost, ctx->stream));
     }

@@ -121,8 +121,15 @@ __device__ __forceinline__ int ng_row_hi(const DevTask& t, int m) { return min(m
 // SCORE = true : scorealoneS_ng (GSPALN_SCOREALONE_NG); its tie rules differ: strict comparisons
 //                for the gap states and acceptors, ties accepted in the donor list
 // ---------------------------------------------------------------------------
-template <bool SCORE>
-__global__ void __launch_bounds__(NG_THREADS)
+// NW = warps per problem.  NW == 1: a CTA runs NG_WARPS independent problems, one per warp.  NW > 1
+// (queries of NG_WIDE_ROWS rows and more): the wavefront is 32 NW rows tall, one problem per CTA,
+// barrier per step = the CTA's; the first lane of every warp but the first reads the row above from
+// the band rows (its neighbour sits in another warp), written one step earlier.
+constexpr int NG_WIDE = 8;
+constexpr int NG_WIDE_ROWS = 128;
+
+template <bool SCORE, int NW>
+__global__ void __launch_bounds__(NW == 1 ? NG_THREADS : 32 * NW)
 dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs, int n_pen,
                const DevTask* __restrict__ tasks, const int* __restrict__ order, int ntasks, int* ticket,
                const unsigned char* __restrict__ apool, const ColInfo* __restrict__ cpool,
@@ -130,9 +137,12 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
                int2* sklpool, DevResult* results, const int* ready)
 {
     __shared__ DevParams sP;
-    __shared__ NgRvp stageH[NG_WARPS][32], stageF[NG_WARPS][32], stageF2[NG_WARPS][32];
-    __shared__ int stageD[NG_WARPS][32];
-    __shared__ int warp_next[NG_WARPS];
+    constexpr int NT = 32 * NW;                         // lanes (= rows of a pass) per problem
+    constexpr int NWARP = NW == 1 ? NG_WARPS : NW;      // warps of the CTA
+    __shared__ NgRvp stageH[NWARP][32], stageF[NWARP][32], stageF2[NWARP][32];
+    __shared__ int stageD[NWARP][32];
+    __shared__ int warp_next[NWARP];
+    __shared__ int s_tk, s_best[NWARP][4];
     {
         const int* src = reinterpret_cast<const int*>(gP);
         int* dst = reinterpret_cast<int*>(&sP);
@@ -141,14 +151,17 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
     __syncthreads();
     const DevParams& P = sP;
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int wl = threadIdx.x & 31, wid = threadIdx.x >> 5;    // lane of the warp (shuffles), warp of the CTA
+    const int lane = threadIdx.x % NT;                  // lane of the problem's wavefront
+    const int slot = NW == 1 ? wid : 0;                 // problem slot of the CTA
+    auto sync_problem = [] { if (NW == 1) __syncwarp(); else __syncthreads(); };
     const bool dagp = P.noll == 3, spj = P.spj != 0;
     const int nod = 2 * P.noll - 1;
     constexpr int WANT = SCORE ? 4 : 3;
 
     NgBand W;
     {
-        unsigned char* base = workpool + ((long long) blockIdx.x * NG_WARPS + wid) * work_slab;
+        unsigned char* base = workpool + ((long long) blockIdx.x * (NW == 1 ? NG_WARPS : 1) + slot) * work_slab;
         W.H = reinterpret_cast<NgRvp*>(base);
         W.F = W.H + width_max;
         W.F2 = W.F + width_max;
@@ -159,13 +172,22 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
 
     for (;;) {
         int tk = 0;
-        if (lane == 0) tk = atomicAdd(ticket, 1);
-        tk = __shfl_sync(FULL, tk, 0);
+        if (NW == 1) {
+            if (lane == 0) tk = atomicAdd(ticket, 1);
+            tk = __shfl_sync(FULL, tk, 0);
+        } else {
+            __syncthreads();
+            if (threadIdx.x == 0) s_tk = atomicAdd(ticket, 1);
+            __syncthreads();
+            tk = s_tk;
+        }
         if (tk >= ntasks) break;
         const int ti = order[tk];
         const DevTask t = tasks[ti];
-        if (t.kind != WANT) continue;                       // handled by another kernel
-        if (!wait_inputs(ready, tk)) {
+        if (t.kind != WANT || ((t.flags & 32) != 0) != (NW > 1)) continue;  // another kernel / class runs it
+        bool arrived = wait_inputs(ready, tk);
+        if (NW > 1) arrived = __syncthreads_and(arrived) != 0;
+        if (!arrived) {
             if (lane == 0) { DevResult rr; rr.score = 0; rr.status = 4; rr.n_skl = 0; rr.pad = 0; results[ti] = rr; }
             continue;
         }
@@ -184,27 +206,27 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
         NgRvp* F2 = W.F2 - (lw - 1);
         unsigned char* dirs = W.dirs - (lw - 1);
         NgAlloc A;
-        if (lane == 0) warp_next[wid] = NG_CHUNK;           // record 0 is never a path node
-        for (int i = lane; i < width; i += 32) {
+        if (lane == 0) warp_next[slot] = NG_CHUNK;          // record 0 is never a path node
+        for (int i = lane; i < width; i += NT) {
             W.H[i] = NgRvp{NG_NEVSEL, 0}; W.F[i] = NgRvp{NG_NEVSEL, 0}; W.F2[i] = NgRvp{NG_NEVSEL, 0};
             W.dirs[i] = 0;
         }
-        __syncwarp();
+        sync_problem();
 
         // ---- first row and first column (initS_ng src/fwd2s1.cc:141-184, sinitS_ng 1112-1140)
         {
             const int r0 = b_left - a_left;
             int p0 = 0;
-            if (!SCORE && lane == 0) p0 = ng_add(W, A, &warp_next[wid], a_left, b_left, 0);
+            if (!SCORE && lane == 0) p0 = ng_add(W, A, &warp_next[slot], a_left, b_left, 0);
             p0 = __shfl_sync(FULL, p0, 0);
             if (lane == 0) H[r0] = NgRvp{0, p0};
             if (a_exgl) {
                 const int rr = min(up, b_right - a_left);
-                for (int r = r0 + 1 + lane; r <= rr; r += 32) { H[r] = NgRvp{0, 0}; dirs[r] = 1; }
+                for (int r = r0 + 1 + lane; r <= rr; r += NT) { H[r] = NgRvp{0, 0}; dirs[r] = 1; }
             }
             const int rr = max(b_left - a_right, lw);
             if (b_exgl) {
-                for (int r = rr + lane; r < r0; r += 32) { H[r] = NgRvp{0, 0}; dirs[r] = 2; }
+                for (int r = rr + lane; r < r0; r += NT) { H[r] = NgRvp{0, 0}; dirs[r] = 2; }
             } else if (lane == 0) {
                 // a leading gap in the genome: opened once, extended per residue (long-gap slope
                 // beyond codonk1); the score-only kernel seeds the vertical state as well
@@ -219,11 +241,11 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
             }
         }
         __threadfence_block();
-        __syncwarp();
+        sync_problem();
 
         int best_val = NG_NEVSEL, best_m = a_left, best_n = b_left, best_p = 0;     // LocalR (lane-local)
         const int m_first = a_exgl ? a_left + 1 : a_left;
-        for (int m0 = m_first; m0 <= a_right; m0 += 32) {
+        for (int m0 = m_first; m0 <= a_right; m0 += NT) {
             const int m = m0 + lane;
             const bool row = m <= a_right;
             const bool first = m == a_left;                 // global start row: horizontal moves only
@@ -233,7 +255,7 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
             const bool has_up = lane > 0;                   // the row above belongs to this pass
             const int arow = (first || !row) ? ZROW : (int) aseq[m - 1 - a_left];
             const int sigB = (cip && row) ? cip[m - a_left] : 0;    // bonus of an intron conserved at this row
-            const int last_lane = min(31, a_right - m0);
+            const int last_lane = min(NT - 1, a_right - m0);
             const int s_begin = ng_row_lo(t, m0) + 1;
             const int s_end = ng_row_hi(t, m0 + last_lane) + last_lane;
 
@@ -249,7 +271,7 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
             for (int s = s_begin; s <= s_end; ++s) {
                 const int k = s - s_begin;
                 // lane 0's row above: 32 diagonals of the band rows per coalesced load
-                if ((k & 31) == 0) {
+                if ((k & 31) == 0 && (NW == 1 || wid == 0)) {
                     __syncwarp();
                     const int r = (s - m0 + 1) + lane;      // diagonal lane 0 reads `lane` steps from now
                     const bool in = r >= lw - 1 && r <= up + 1;
@@ -273,7 +295,8 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
                     uH = stageH[wid][k & 31]; uF = stageF[wid][k & 31];
                     if (dagp) uF2 = stageF2[wid][k & 31];
                     uD = stageD[wid][k & 31];
-                } else if (!(n > lo_up && n <= hi_up)) {
+                } else if (wl == 0 || !(n > lo_up && n <= hi_up)) {
+                    // the neighbour sits in another warp (its cell went to the band rows one step ago), or
                     // the row above never evaluated column n: what the band rows hold there
                     const bool in = r + 1 <= up + 1 && r + 1 >= lw - 1;
                     uH = in ? ng_ld(H + r + 1) : NgRvp{NG_NEVSEL, 0};
@@ -356,8 +379,8 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
                             NgRvp& sq = q == 0 ? h : q == 1 ? e1 : q == 2 ? f : q == 3 ? e2 : f2;
                             psp |= psp_bit[q];
                             if (!SCORE) {
-                                const int inner = ng_add(W, A, &warp_next[wid], m, tj[q], tp[q]);
-                                sq.ptr = ng_add(W, A, &warp_next[wid], m, n, inner);
+                                const int inner = ng_add(W, A, &warp_next[slot], m, tj[q], tp[q]);
+                                sq.ptr = ng_add(W, A, &warp_next[slot], m, n, inner);
                             }
                             if (SCORE ? sq.val > mxv : sq.val >= mxv) { mx = q; mxv = sq.val; }
                         }
@@ -371,13 +394,13 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
                     } else if (SCORE) {
                         if (LocalR && y > best_val) best_val = y;
                     } else if (P.local && h.val > diag) {
-                        if (LocalL && diag == 0) h.ptr = ng_add(W, A, &warp_next[wid], m - 1, n - 1, 0);
+                        if (LocalL && diag == 0) h.ptr = ng_add(W, A, &warp_next[slot], m - 1, n - 1, 0);
                         else if (LocalR && h.val > best_val) { best_val = h.val; best_p = h.ptr; best_m = m; best_n = n; }
                     }
                     int mx_now = mxv;
                     if (LocalL && (SCORE ? h.val < 0 : h.val <= 0)) { h.val = 0; dir = 1; if (mx == 0) mx_now = 0; }
                     else if (!SCORE && dir == NG_NEWD && !(psp & 4))
-                        h.ptr = ng_add(W, A, &warp_next[wid], m - 1, n - 1, h.ptr);
+                        h.ptr = ng_add(W, A, &warp_next[slot], m - 1, n - 1, h.ptr);
                     // donor: the best (value + 5' signal) of this row by gap state
                     if ((SCORE || internal) && cano5) {
                         const int sigJ = col.sig5;
@@ -404,10 +427,10 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
                     hleft = h;
                 }
                 dH = uH; dD = uD;
-                __syncwarp();
+                sync_problem();
             }
             __threadfence_block();
-            __syncwarp();
+            sync_problem();
         }
 
         // ---- end point (lastS_ng src/fwd2s1.cc:186-215, slastS_ng 1142-1161)
@@ -421,8 +444,18 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
                 const int on = __shfl_xor_sync(FULL, bn, o), op = __shfl_xor_sync(FULL, bp, o);
                 if (ov > bv || (ov == bv && ov > NG_NEVSEL && (om < bm || (om == bm && on < bn)))) { bv = ov; bm = om; bn = on; bp = op; }
             }
+            if (NW > 1) {
+                // across the warps of the problem, same order
+                if (wl == 0) { s_best[wid][0] = bv; s_best[wid][1] = bm; s_best[wid][2] = bn; s_best[wid][3] = bp; }
+                __syncthreads();
+                if (threadIdx.x == 0)
+                    for (int w = 1; w < NW; ++w) {
+                        const int ov = s_best[w][0], om = s_best[w][1], on = s_best[w][2];
+                        if (ov > bv || (ov == bv && ov > NG_NEVSEL && (om < bm || (om == bm && on < bn)))) { bv = ov; bm = om; bn = on; bp = s_best[w][3]; }
+                    }
+            }
             val = bv;
-            if (!SCORE && lane == 0) ptr = ng_add(W, A, &warp_next[wid], bm, bn, bp);
+            if (!SCORE && lane == 0) ptr = ng_add(W, A, &warp_next[slot], bm, bn, bp);
         } else if (lane == 0) {
             const int r9 = b_right - a_right;
             int mxr = r9;
@@ -444,13 +477,13 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
                         if (v > mxval) { mxr = r; mxval = v; }
                     }
                 const int i = mxr - r9;
-                ptr = ng_add(W, A, &warp_next[wid], a_right - max(i, 0), b_right + min(i, 0), ng_ld(H + mxr).ptr);
+                ptr = ng_add(W, A, &warp_next[slot], a_right - max(i, 0), b_right + min(i, 0), ng_ld(H + mxr).ptr);
                 val = mxval;
             }
         }
-        const bool overflow = __any_sync(FULL, A.overflow);
+        const bool overflow = NW == 1 ? __any_sync(FULL, A.overflow) != 0 : __syncthreads_or(A.overflow) != 0;
         __threadfence_block();
-        __syncwarp();
+        sync_problem();
 
         if (lane == 0) {
             int cnt = 0;
@@ -478,7 +511,7 @@ dp_xild_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
             res.n_skl = cnt; res.pad = 0;
             results[ti] = res;
         }
-        __syncwarp();
+        sync_problem();
     }
 }
 

@@ -17,6 +17,10 @@
 // flags, the donor list with its bounds and links) lives in the registers of its lane.  A pass
 // holds at most one intermediate row: the "last diagonal on the row" register of the reference
 // runs along that row and is handed from pass to pass.
+//
+// NW = warps per problem.  NW == 1: a CTA runs NG_WARPS independent problems, one per warp.  NW > 1
+// (queries with hundreds of rows): the wavefront is 32 NW rows tall, one problem per CTA, and the
+// per-step barrier is the CTA's -- the hazard argument above is about steps, not about warps.
 #pragma once
 #include "gspaln_ng.cuh"
 #include "gspaln_udh.cuh"
@@ -83,14 +87,20 @@ __device__ __forceinline__ int ux_val(const UxCell (&st)[5], int k)
     return v;
 }
 
-__global__ void __launch_bounds__(NG_THREADS)
+constexpr int XUDH_WIDE = 8;            // warps per problem of the wide class
+constexpr int XUDH_WIDE_ROWS = 128;     // queries with at least this many rows run in the wide class
+
+template <int NW>
+__global__ void __launch_bounds__(NW == 1 ? NG_THREADS : 32 * NW)
 dp_xudh_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs, int n_pen,
                const DevTask* __restrict__ tasks, const int* __restrict__ order, int ntasks, int* ticket,
                const unsigned char* __restrict__ apool, const ColInfo* __restrict__ cpool,
                unsigned char* workpool, long long work_slab, long long width_max,
                int* cpospool, DevUdhOut* results, const int* ready)
 {
+    constexpr int NT = 32 * NW;                         // lanes (= rows of a pass) per problem
     __shared__ DevParams sP;
+    __shared__ int s_tk, s_rlst, s_best[NW][7];
     {
         const int* src = reinterpret_cast<const int*>(gP);
         int* dst = reinterpret_cast<int*>(&sP);
@@ -99,23 +109,34 @@ dp_xudh_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
     __syncthreads();
     const DevParams& P = sP;
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x % NT;                  // lane of the problem's wavefront
+    const int slot = threadIdx.x / NT;                  // problem slot of the CTA (NW == 1: its warps)
+    auto sync_problem = [] { if (NW == 1) __syncwarp(); else __syncthreads(); };
     const bool dagp = P.noll == 3;
     const int noll = P.noll, nod = 2 * P.noll - 1;
-    unsigned char* wbase = workpool + ((long long) blockIdx.x * NG_WARPS + wid) * work_slab;
+    unsigned char* wbase = workpool + ((long long) blockIdx.x * (NW == 1 ? NG_WARPS : 1) + slot) * work_slab;
 
     for (;;) {
         int tk = 0;
-        if (lane == 0) tk = atomicAdd(ticket, 1);
-        tk = __shfl_sync(FULL, tk, 0);
+        if (NW == 1) {
+            if (lane == 0) tk = atomicAdd(ticket, 1);
+            tk = __shfl_sync(FULL, tk, 0);
+        } else {
+            __syncthreads();
+            if (threadIdx.x == 0) s_tk = atomicAdd(ticket, 1);
+            __syncthreads();
+            tk = s_tk;
+        }
         if (tk >= ntasks) break;
         const int ti = order[tk];
         const DevTask t = tasks[ti];
-        if (t.kind != 5) continue;
+        if (t.kind != 5 || ((t.flags & 32) != 0) != (NW > 1)) continue;     // another kernel / class runs it
         const int n_req = t.pad0;
         int* cpos = cpospool + t.pad1;
-        for (int i = lane; i < 10 * (n_req + 1); i += 32) cpos[i] = (i % 10 == 0 || i % 10 == 2) ? END_OF_ULK : 0;
-        if (!wait_inputs(ready, tk)) {
+        for (int i = lane; i < 10 * (n_req + 1); i += NT) cpos[i] = (i % 10 == 0 || i % 10 == 2) ? END_OF_ULK : 0;
+        bool arrived = wait_inputs(ready, tk);
+        if (NW > 1) arrived = __syncthreads_and(arrived) != 0;
+        if (!arrived) {
             if (lane == 0) { DevUdhOut r; memset(&r, 0, sizeof(r)); r.status = 4; r.score = NEVSEL32; results[ti] = r; }
             continue;
         }
@@ -141,29 +162,29 @@ dp_xudh_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
 
         const int r_black = b_left - a_right;
         const UxCell black{NG_NEVSEL, r_black, r_black, 0, END_OF_ULK};
-        for (int i = lane; i < width; i += 32) {
+        for (int i = lane; i < width; i += NT) {
             ux_st(Hs + (lw - 1) + i, black); ux_st(Fs + (lw - 1) + i, black);
             if (dagp) ux_st(F2s + (lw - 1) + i, black);
         }
         {
             const long long u = (long long) noll * width;
-            for (long long i = lane; i < 4 * u * n_im; i += 32) {
+            for (long long i = lane; i < 4 * u * n_im; i += NT) {
                 const int which = (int) ((i / u) & 3);
                 I.base[i] = which < 2 ? END_OF_ULK : (which == 2 ? INT_MAX : INT_MIN);
             }
         }
-        __syncwarp();
+        sync_problem();
         // ---- first row and first column (hinitS_ng)
         {
             const int r0 = b_left - a_left;
             if (lane == 0) ux_st(Hs + r0, UxCell{0, r0, r0, a_left, r0});
             if (a_exgl) {
                 const int rr = min(up, b_right - a_left);
-                for (int r = r0 + 1 + lane; r <= rr; r += 32) ux_st(Hs + r, UxCell{0, r, r, a_left, r});
+                for (int r = r0 + 1 + lane; r <= rr; r += NT) ux_st(Hs + r, UxCell{0, r, r, a_left, r});
             }
             const int rr = max(b_left - a_right, lw);
             if (b_exgl) {
-                for (int r = rr + lane; r < r0; r += 32) ux_st(Hs + r, UxCell{0, r, r, a_left + (r0 - r), r});
+                for (int r = rr + lane; r < r0; r += NT) ux_st(Hs + r, UxCell{0, r, r, a_left + (r0 - r), r});
             } else if (lane == 0) {
                 int v = 0;
                 for (int i = 1, r = r0 - 1; r >= rr; --r, ++i) {
@@ -173,14 +194,14 @@ dp_xudh_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
             }
         }
         __threadfence_block();
-        __syncwarp();
+        sync_problem();
 
-        int rlst = INT_MAX;                                 // warp-uniform between passes
+        int rlst = INT_MAX;                                 // uniform over the problem's lanes between passes
         int bval = NG_NEVSEL, bupr = 0, blwr = 0, bml = a_left, bulk = 0, bmr = a_right, bnr = b_right;   // LocalR
         const int m_first = a_exgl ? a_left + 1 : a_left;
         for (int m0 = m_first; m0 <= a_right; ) {
             // rows m0 .. m9 of this pass, cut so that it holds at most one intermediate row
-            int m9 = min(m0 + 31, a_right);
+            int m9 = min(m0 + NT - 1, a_right);
             int ia = (m0 - a_left + intvl - 1) / intvl - 1;     // first intermediate at or below m0
             if (ia < 0) ia = 0;
             const int mi_a = ia < n_im ? MI(ia) : INT_MAX;
@@ -349,15 +370,21 @@ dp_xudh_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
                     if (dagp) ux_st(F2s + r, st[4]);
                     hleft = st[0];
                 }
-                __syncwarp();
+                sync_problem();
             }
             // hand the intermediate row's last diagonal to the next pass
-            {
+            if (NW == 1) {
                 const unsigned who = __ballot_sync(FULL, is_imd);
                 if (who) rlst = __shfl_sync(FULL, my_rlst, __ffs(who) - 1);
+            } else {
+                if (threadIdx.x == 0) s_rlst = rlst;
+                __syncthreads();
+                if (is_imd) s_rlst = my_rlst;
+                __syncthreads();
+                rlst = s_rlst;
             }
             __threadfence_block();
-            __syncwarp();
+            sync_problem();
             m0 = m9 + 1;
         }
 
@@ -373,6 +400,21 @@ dp_xudh_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
                 if (ov > bval || (ov == bval && ov > NG_NEVSEL && (omr < bmr || (omr == bmr && onr < bnr)))) {
                     bval = ov; bupr = ou; blwr = ol; bml = om; bulk = ok; bmr = omr; bnr = onr;
                 }
+            }
+            if (NW > 1) {
+                // across the warps of the problem, same order
+                if ((threadIdx.x & 31) == 0) {
+                    int* b = s_best[threadIdx.x >> 5];
+                    b[0] = bval; b[1] = bupr; b[2] = blwr; b[3] = bml; b[4] = bulk; b[5] = bmr; b[6] = bnr;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0)
+                    for (int w = 1; w < NW; ++w) {
+                        const int* b = s_best[w];
+                        if (b[0] > bval || (b[0] == bval && b[0] > NG_NEVSEL && (b[5] < bmr || (b[5] == bmr && b[6] < bnr)))) {
+                            bval = b[0]; bupr = b[1]; blwr = b[2]; bml = b[3]; bulk = b[4]; bmr = b[5]; bnr = b[6];
+                        }
+                    }
             }
         }
         if (lane == 0) {
@@ -454,7 +496,7 @@ dp_xudh_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs,
             o.pad0 = o.pad1 = 0;
             results[ti] = o;
         }
-        __syncwarp();
+        sync_problem();
     }
 }
 
