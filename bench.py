@@ -661,6 +661,8 @@ def config5_sweep(args, prm, rank, local_rank, world):
         for m in (16, 32, 64, 128, 256, 512, 1024, 2048, 4096):
             if not (256 <= m * W <= 65536):
                 continue
+            if args.sweep_only and args.sweep_only != f"{W},{m}":
+                continue
             probs = []
             for k in range(distinct):
                 nin = k % 3 if (W >= 64 and m >= 32) else 0
@@ -908,6 +910,7 @@ def main():
                     help="2: the headline workload (default); 3 / 4: the protein and the long-intron mRNA "
                          "jobs at their stated scale; 5: band-width x query-length sweep")
     ap.add_argument("--sweep-tasks", type=int, default=102400, help="tasks per sweep point and rank")
+    ap.add_argument("--sweep-only", default="", help="W,m: run this point of the config-5 sweep alone (profiling)")
     ap.add_argument("--leg", default="", help=argparse.SUPPRESS)
     ap.add_argument("--leg-seed", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--leg-out", default="", help=argparse.SUPPRESS)

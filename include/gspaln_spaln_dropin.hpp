@@ -29,6 +29,7 @@
 
 #include <cstdio>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 
@@ -69,9 +70,11 @@ inline std::mutex& registry_mutex() { static std::mutex m; return m; }
 struct HookStats {
     enum { LSP, TRCBK_WIP, TRCBK_EXACT, HOM_WIP, HOM_EXACT, EXACT_NO_TABLES, EXACT_OVERFLOW, N };
     std::atomic<long long> n[2][N];
+    std::atomic<long long> setup_us[2];     // engine creation (CUDA context included), exact-ILD tables
     HookStats()
     {
         for (auto& row : n) for (auto& c : row) c = 0;
+        setup_us[0] = setup_us[1] = 0;
         if (getenv("GSPALN_DROPIN_STATS")) atexit(report);
     }
     static HookStats& get() { static HookStats s; return s; }
@@ -85,6 +88,8 @@ struct HookStats {
             for (int k = 0; k < N; ++k) fprintf(stderr, " %s=%lld", names[k], (long long) s.n[p][k]);
             fputc('\n', stderr);
         }
+        fprintf(stderr, "gspaln drop-in set-up: engines %.2f s, exact-ILD tables %.2f s\n",
+                1e-6 * (double) s.setup_us[0], 1e-6 * (double) s.setup_us[1]);
     }
 };
 inline bool counted(bool ok, int protein, int what)
@@ -111,8 +116,13 @@ inline SpalnEngine* engineS(const PwdB* pwd, const Seq* b)
     const bool spliced = b->inex.intr;
     SpalnEngine*& e = reg[std::make_pair(pwd, spliced)];
     if (!e) {
+        const auto t0 = std::chrono::steady_clock::now();
         e = new SpalnEngine(pwd, device_index(), spliced);
+        const auto t1 = std::chrono::steady_clock::now();
         if (spliced && sig53tab_of(b) && pwd->IntPen) e->enable_scalar(pwd, sig53tab_of(b), MAX_SEGMENT);
+        const auto t2 = std::chrono::steady_clock::now();
+        HookStats::get().setup_us[0] += std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+        HookStats::get().setup_us[1] += std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();
     }
     return e;
 }
@@ -124,12 +134,17 @@ inline SpalnEngineH* engineH(const PwdB* pwd, const Seq* b)
     const bool spliced = b->inex.intr;
     SpalnEngineH*& e = reg[std::make_pair(pwd, spliced)];
     if (!e) {
+        const auto t0 = std::chrono::steady_clock::now();
         e = new SpalnEngineH(pwd, device_index(), spliced);
+        const auto t1 = std::chrono::steady_clock::now();
         if (spliced && sig53tab_of(b) && pwd->IntPen) {
             unsigned char tabs[796];
             spj_tables(tabs);
             e->enable_scalar(pwd, sig53tab_of(b), tabs, MAX_SEGMENT);
         }
+        const auto t2 = std::chrono::steady_clock::now();
+        HookStats::get().setup_us[0] += std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+        HookStats::get().setup_us[1] += std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();
     }
     return e;
 }

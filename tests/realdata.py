@@ -74,7 +74,9 @@ class Workspace:
             raise RuntimeError(f"{binary} {' '.join(opts)} failed ({r.returncode}): {r.stderr[-400:].decode(errors='replace')}")
         if stats is not None:
             for ln in r.stderr.decode(errors="replace").splitlines():
-                if ln.startswith("gspaln drop-in ("):
+                if ln.startswith("gspaln drop-in set-up:"):
+                    stats["set-up"] = ln.split(":", 1)[1].strip()
+                elif ln.startswith("gspaln drop-in ("):
                     kind = ln[len("gspaln drop-in ("):].split(")")[0]
                     stats[kind] = {k: int(v) for k, v in (x.split("=") for x in ln.split(":", 1)[1].split())}
         return r.stdout

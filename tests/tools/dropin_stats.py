@@ -21,4 +21,6 @@ for binary in ("spaln", "spaln_gpu"):
     t0 = time.time()
     out = w.run(binary, opts, q, stats=st)
     print(binary, " ".join(opts), f"{time.time() - t0:.1f} s", len(out), "bytes", st, flush=True)
+    if st.get("set-up"):
+        print("   set-up:", st["set-up"], flush=True)
 w.close()
