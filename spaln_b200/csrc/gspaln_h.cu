@@ -645,6 +645,7 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
     std::vector<DevNgHTask> dt(n);
     std::vector<DevUdhHTask> du(udh ? n : 0);
     size_t cpos_elems = 0;
+    int n_wide = 0;
     std::vector<unsigned char> apool, bpool;
     std::vector<short> sgpool;
     std::vector<unsigned short> ipool;
@@ -662,10 +663,12 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
         d.lw = t.lw; d.up = t.up;
         d.a_exgl = t.a_exgl; d.a_exgr = t.a_exgr; d.b_exgl = t.b_exgl; d.b_exgr = t.b_exgr;
         d.skl_cap = std::max(0, t.skl_cap);
+        d.wide = t.a_right - t.a_left >= HNG_WIDE_ROWS; d.pad_ = 0;      // a CTA of warps per problem
+        n_wide += d.wide;
         const int width = t.up - t.lw + 7;
         const int64_t cells = gspaln_h_task_cells(&t);
         cells_total += cells;
-        d.rec_cap = (int) std::min<int64_t>(4 * cells + 4 * width + 64 + 33 * HNG_CHUNK, INT_MAX / 4);
+        d.rec_cap = (int) std::min<int64_t>(4 * cells + 4 * width + 64 + (32 * HNG_WIDE + 1) * HNG_CHUNK, INT_MAX / 4);
         // query residues a_left - 1 .. a_right, genome columns b_left - 4 .. b_right + 4 (zeros outside
         // the sequences, as the terminal residues of the reference's arrays)
         d.a_lo = t.a_left - 1; d.a_off = (long long) apool.size();
@@ -725,17 +728,23 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
     if (e == cudaSuccess) e = cudaMalloc((void**) &d_work, work_bytes + 16);
     if (e == cudaSuccess) e = cudaMalloc((void**) &d_skl, (skl_elems + 1) * sizeof(int2));
     if (e == cudaSuccess) e = cudaMalloc((void**) &d_res, (size_t) (n + 1) * sizeof(DevResult));
-    if (e == cudaSuccess) e = cudaMalloc((void**) &d_tick, sizeof(int));
-    if (e == cudaSuccess) e = cudaMemset(d_tick, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**) &d_tick, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(d_tick, 0, 2 * sizeof(int));
     if (e != cudaSuccess) { freeall(); cudaGetLastError(); return fail(ctx, GSPALN_ENOMEM, "scalar kernel buffers", e); }
     cudaEventRecord(ctx->ev[2], ctx->stream);
-    const int grid = std::max(1, std::min((n + HNG_WARPS - 1) / HNG_WARPS, 4 * ctx->sm_count));
-    if (udh)
-        dp_hxudh_kernel<<<grid, HNG_THREADS, 0, ctx->stream>>>(ctx->d_ngprm.p, d_tu, n, d_tick, d_a, d_b, d_sg, d_i,
-                                                             d_cip, d_work, d_cpos, d_ures);
-    else
-        dp_hxild_kernel<<<grid, HNG_THREADS, 0, ctx->stream>>>(ctx->d_ngprm.p, d_t, n, d_tick, d_a, d_b, d_sg, d_i,
-                                                             d_cip, d_work, d_skl, d_res);
+    // two classes by query length: one warp per problem (HNG_WARPS problems per CTA), or a CTA of
+    // HNG_WIDE warps per problem; every kernel walks the whole task list and takes its class
+    const int n_thin = n - n_wide;
+    const int grid = std::max(1, std::min((n_thin + HNG_WARPS - 1) / HNG_WARPS, 4 * ctx->sm_count));
+    const int grid_w = std::max(1, std::min(n_wide, 2 * ctx->sm_count));
+    int launches = 0;
+    if (udh) {
+        if (n_wide) { dp_hxudh_kernel<HNG_WIDE><<<grid_w, 32 * HNG_WIDE, 0, ctx->stream>>>(ctx->d_ngprm.p, d_tu, n, d_tick + 1, d_a, d_b, d_sg, d_i, d_cip, d_work, d_cpos, d_ures); ++launches; }
+        if (n_thin) { dp_hxudh_kernel<1><<<grid, HNG_THREADS, 0, ctx->stream>>>(ctx->d_ngprm.p, d_tu, n, d_tick, d_a, d_b, d_sg, d_i, d_cip, d_work, d_cpos, d_ures); ++launches; }
+    } else {
+        if (n_wide) { dp_hxild_kernel<HNG_WIDE><<<grid_w, 32 * HNG_WIDE, 0, ctx->stream>>>(ctx->d_ngprm.p, d_t, n, d_tick + 1, d_a, d_b, d_sg, d_i, d_cip, d_work, d_skl, d_res); ++launches; }
+        if (n_thin) { dp_hxild_kernel<1><<<grid, HNG_THREADS, 0, ctx->stream>>>(ctx->d_ngprm.p, d_t, n, d_tick, d_a, d_b, d_sg, d_i, d_cip, d_work, d_skl, d_res); ++launches; }
+    }
     cudaEventRecord(ctx->ev[3], ctx->stream);
     e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
@@ -749,7 +758,7 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
         freeall();
         if (e != cudaSuccess) return fail(ctx, GSPALN_ECUDA, "scalar Hirschberg kernel", e);
         memset(&ctx->tim, 0, sizeof(ctx->tim));
-        ctx->tim.kernel_ms = ums; ctx->tim.launches = 1; ctx->tim.cells = cells_total;
+        ctx->tim.kernel_ms = ums; ctx->tim.launches = launches; ctx->tim.cells = cells_total;
         for (int i = 0; i < n; ++i) {
             gspaln_result& o = results[i];
             o.score = hu[i].score; o.status = hu[i].status; o.n_skl = 0; o.reserved = 0;
@@ -768,7 +777,7 @@ static int h_ng_submit(gspaln_h_ctx* ctx, const gspaln_h_task* tasks, int n, gsp
     freeall();
     if (e != cudaSuccess) return fail(ctx, GSPALN_ECUDA, "scalar kernel", e);
     memset(&ctx->tim, 0, sizeof(ctx->tim));
-    ctx->tim.kernel_ms = ms; ctx->tim.launches = 1; ctx->tim.cells = cells_total;
+    ctx->tim.kernel_ms = ms; ctx->tim.launches = launches; ctx->tim.cells = cells_total;
     for (int i = 0; i < n; ++i) {
         gspaln_result& o = results[i];
         o.score = hres[i].score; o.status = hres[i].status; o.n_skl = hres[i].n_skl; o.reserved = 0;

@@ -61,6 +61,7 @@ struct DevNgHTask {
     long long sg_off;           // SGPT6 shorts (8 per column), int53: column b_lo first
     long long skl_off, work_off;    // corners (int2), workspace bytes
     long long cip_off;          // Cip_score words from coding position 3 a_left - 1 on; -1: none
+    int wide, pad_;             // 1: the problem runs on a CTA of HNG_WIDE warps
 };
 
 enum { F_SIG5, F_SIG3, F_SIGS, F_SIGT, F_SIGE, F_SIGI, F_PHS5, F_PHS3 };
@@ -157,27 +158,47 @@ struct HxList {
     }
 };
 
-__global__ void __launch_bounds__(HNG_THREADS)
+// NW = warps per problem: 1 (a CTA runs HNG_WARPS independent problems) or HNG_WIDE (queries of
+// HNG_WIDE_ROWS residues and more: one problem per CTA, the skewed wavefront 32 NW rows tall, the
+// per-step barrier the CTA's -- the lanes only ever meet through the band rows, so nothing else changes)
+constexpr int HNG_WIDE = 8;
+constexpr int HNG_WIDE_ROWS = 96;
+
+template <int NW>
+__global__ void __launch_bounds__(NW == 1 ? HNG_THREADS : 32 * NW)
 dp_hxild_kernel(const DevNgHParams* __restrict__ gP, const DevNgHTask* __restrict__ tasks, int ntasks, int* ticket,
                 const unsigned char* __restrict__ apool, const unsigned char* __restrict__ bpool,
                 const short* __restrict__ sgpool, const unsigned short* __restrict__ i53pool,
                 const int* __restrict__ cippool, unsigned char* workpool, int2* sklpool, DevResult* results)
 {
+    constexpr int NT = 32 * NW;
+    constexpr int NWARP = NW == 1 ? HNG_WARPS : NW;
     __shared__ DevNgHParams P;
-    __shared__ int warp_next[HNG_WARPS];
+    __shared__ int warp_next[NWARP];
+    __shared__ int s_ti, s_best[NWARP][4];
     if (threadIdx.x < sizeof(DevNgHParams) / 4)
         reinterpret_cast<int*>(&P)[threadIdx.x] = reinterpret_cast<const int*>(gP)[threadIdx.x];
     __syncthreads();
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x % NT;                  // lane of the problem's wavefront
+    const int wid = NW == 1 ? (threadIdx.x >> 5) : 0;   // problem slot of the CTA
+    auto sync_problem = [] { if (NW == 1) __syncwarp(); else __syncthreads(); };
     const HCell black = {HNG_NEVSEL, 0, 0, 0};
 
     for (;;) {
         int ti = 0;
-        if (lane == 0) ti = atomicAdd(ticket, 1);
-        ti = __shfl_sync(FULL, ti, 0);
+        if (NW == 1) {
+            if (lane == 0) ti = atomicAdd(ticket, 1);
+            ti = __shfl_sync(FULL, ti, 0);
+        } else {
+            __syncthreads();
+            if (threadIdx.x == 0) s_ti = atomicAdd(ticket, 1);
+            __syncthreads();
+            ti = s_ti;
+        }
         if (ti >= ntasks) break;
         const DevNgHTask t = tasks[ti];
+        if ((t.wide != 0) != (NW > 1)) continue;            // the other class runs it
         HngIn T;
         T.a = apool + t.a_off; T.b = bpool + t.b_off; T.sg = sgpool + 8 * t.sg_off; T.i53 = i53pool + t.sg_off;
         T.a_lo = t.a_lo; T.b_lo = t.b_lo; T.b_left = t.b_left; T.b_right = t.b_right;
@@ -198,8 +219,8 @@ dp_hxild_kernel(const DevNgHParams* __restrict__ gP, const DevNgHTask* __restric
         A.rec = reinterpret_cast<int*>(buf + 3 * (width + 8));
         A.cap = t.rec_cap; A.next = &warp_next[wid]; A.cur = A.end = 0; A.overflow = false;
         if (lane == 0) warp_next[wid] = HNG_CHUNK;      // record 0 is never a path node
-        for (int i = lane; i < 3 * (width + 8); i += 32) hx_st(buf + i, black);
-        __syncwarp();
+        for (int i = lane; i < 3 * (width + 8); i += NT) hx_st(buf + i, black);
+        sync_problem();
 
         // ---- start row and start column (initH_ng, src/fwd2h1.cc:143-222): serial, lane 0
         if (lane == 0) {
@@ -256,15 +277,15 @@ dp_hxild_kernel(const DevNgHParams* __restrict__ gP, const DevNgHTask* __restric
             }
         }
         __threadfence_block();
-        __syncwarp();
+        sync_problem();
 
         int best_val = HNG_NEVSEL, best_m = a_left, best_n = b_left, best_p = 0;    // LocalR (lane-local)
         const int m_first = a_exgl ? a_left + 1 : a_left;
-        for (int m0 = m_first; m0 <= a_right; m0 += 32) {
+        for (int m0 = m_first; m0 <= a_right; m0 += NT) {
             const int m = m0 + lane;
             const bool row = m <= a_right;
             const int n0 = max(3 * m + lw - 1, b_left), n9 = min(3 * m + up, b_right);
-            const int last_lane = min(31, a_right - m0);
+            const int last_lane = min(NT - 1, a_right - m0);
             const int s_begin = max(3 * m0 + lw - 1, b_left);
             const int s_end = min(3 * (m0 + last_lane) + up, b_right) + last_lane;
             // horizontal gap states by column phase (three-slot rings), donor lists by splice phase
@@ -429,10 +450,10 @@ dp_hxild_kernel(const DevNgHParams* __restrict__ gP, const DevNgHTask* __restric
                     e1[q] = st[1]; e2[q] = st[3];
                     if (++q == 3) q = 0;
                 }
-                __syncwarp();
+                sync_problem();
             }
             __threadfence_block();
-            __syncwarp();
+            sync_problem();
         }
 
         // ---- end point
@@ -443,6 +464,17 @@ dp_hxild_kernel(const DevNgHParams* __restrict__ gP, const DevNgHTask* __restric
                 const int ov = __shfl_xor_sync(FULL, bv, o), om = __shfl_xor_sync(FULL, bm, o);
                 const int on = __shfl_xor_sync(FULL, bn, o), op = __shfl_xor_sync(FULL, bp, o);
                 if (ov > bv || (ov == bv && ov > HNG_NEVSEL && (om < bm || (om == bm && on < bn)))) { bv = ov; bm = om; bn = on; bp = op; }
+            }
+            if (NW > 1) {
+                // across the warps of the problem, same order
+                const int w = threadIdx.x >> 5;
+                if ((threadIdx.x & 31) == 0) { s_best[w][0] = bv; s_best[w][1] = bm; s_best[w][2] = bn; s_best[w][3] = bp; }
+                __syncthreads();
+                if (threadIdx.x == 0)
+                    for (int k = 1; k < NW; ++k) {
+                        const int ov = s_best[k][0], om = s_best[k][1], on = s_best[k][2];
+                        if (ov > bv || (ov == bv && ov > HNG_NEVSEL && (om < bm || (om == bm && on < bn)))) { bv = ov; bm = om; bn = on; bp = s_best[k][3]; }
+                    }
             }
         }
         int ptr = 0, val = HNG_NEVSEL;
@@ -535,9 +567,9 @@ dp_hxild_kernel(const DevNgHParams* __restrict__ gP, const DevNgHTask* __restric
                 val = bv;
             }
         }
-        const bool overflow = __any_sync(FULL, A.overflow);
+        const bool overflow = NW == 1 ? __any_sync(FULL, A.overflow) != 0 : __syncthreads_or(A.overflow) != 0;
         __threadfence_block();
-        __syncwarp();
+        sync_problem();
 
         if (lane == 0) {
             // Vmf::traceback + the start-point adjustment of trcbkalignH_ng (src/fwd2h1.cc:2021-2037)
@@ -565,7 +597,7 @@ dp_hxild_kernel(const DevNgHParams* __restrict__ gP, const DevNgHTask* __restric
             res.n_skl = cnt; res.pad = 0;
             results[ti] = res;
         }
-        __syncwarp();
+        sync_problem();
     }
 }
 

@@ -67,25 +67,37 @@ struct DevUdhHTask {            // DevNgHTask + what the pass needs
     long long cpos_off;         // ints, (n_req + 1) x 10
 };
 
-__global__ void __launch_bounds__(HNG_THREADS)
+template <int NW>                       // warps per problem, as dp_hxild_kernel
+__global__ void __launch_bounds__(NW == 1 ? HNG_THREADS : 32 * NW)
 dp_hxudh_kernel(const DevNgHParams* __restrict__ gP, const DevUdhHTask* __restrict__ tasks, int ntasks, int* ticket,
                 const unsigned char* __restrict__ apool, const unsigned char* __restrict__ bpool,
                 const short* __restrict__ sgpool, const unsigned short* __restrict__ i53pool,
                 const int* __restrict__ cippool, unsigned char* workpool, int* cpospool, DevUdhOut* results)
 {
+    constexpr int NT = 32 * NW;
     __shared__ DevNgHParams P;
+    __shared__ int s_ti, s_rl[3], s_best[NW][7];
     if (threadIdx.x < sizeof(DevNgHParams) / 4)
         reinterpret_cast<int*>(&P)[threadIdx.x] = reinterpret_cast<const int*>(gP)[threadIdx.x];
     __syncthreads();
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x % NT;                  // lane of the problem's wavefront
+    auto sync_problem = [] { if (NW == 1) __syncwarp(); else __syncthreads(); };
 
     for (;;) {
         int ti = 0;
-        if (lane == 0) ti = atomicAdd(ticket, 1);
-        ti = __shfl_sync(FULL, ti, 0);
+        if (NW == 1) {
+            if (lane == 0) ti = atomicAdd(ticket, 1);
+            ti = __shfl_sync(FULL, ti, 0);
+        } else {
+            __syncthreads();
+            if (threadIdx.x == 0) s_ti = atomicAdd(ticket, 1);
+            __syncthreads();
+            ti = s_ti;
+        }
         if (ti >= ntasks) break;
         const DevNgHTask t = tasks[ti].g;
+        if ((t.wide != 0) != (NW > 1)) continue;            // the other class runs it
         const int n_req = tasks[ti].n_req;
         int* cpos = cpospool + tasks[ti].cpos_off;
         HngIn T;
@@ -114,16 +126,16 @@ dp_hxudh_kernel(const DevNgHParams* __restrict__ gP, const DevUdhHTask* __restri
 
         const int r_black = b_left - 3 * a_right;
         const HuCell black{HNG_NEVSEL, 0, r_black, r_black, 0, END_OF_ULK};
-        for (int i = lane; i < 3 * (width + 8); i += 32) hu_st(buf + i, black);
+        for (int i = lane; i < 3 * (width + 8); i += NT) hu_st(buf + i, black);
         {
             const long long u = (long long) noll * width;
-            for (long long i = lane; i < 4 * u * n_im; i += 32) {
+            for (long long i = lane; i < 4 * u * n_im; i += NT) {
                 const int which = (int) ((i / u) & 3);
                 I.base[i] = which < 2 ? END_OF_ULK : (which == 2 ? INT_MAX : INT_MIN);
             }
         }
-        for (int i = lane; i < 10 * (n_req + 1); i += 32) cpos[i] = END_OF_ULK;
-        __syncwarp();
+        for (int i = lane; i < 10 * (n_req + 1); i += NT) cpos[i] = END_OF_ULK;
+        sync_problem();
 
         // ---- start row and start column (hinitH_ng): serial, lane 0
         if (lane == 0) {
@@ -177,13 +189,13 @@ dp_hxudh_kernel(const DevNgHParams* __restrict__ gP, const DevUdhHTask* __restri
             }
         }
         __threadfence_block();
-        __syncwarp();
+        sync_problem();
 
-        int rl0 = INT_MAX, rl1 = INT_MAX, rl2 = INT_MAX;       // rlst[3], warp-uniform between passes
+        int rl0 = INT_MAX, rl1 = INT_MAX, rl2 = INT_MAX;       // rlst[3], uniform over the problem's lanes between passes
         int bval = HNG_NEVSEL, bupr = 0, blwr = 0, bml = a_left, bulk = 0, bmr = a_right, bnr = b_right;   // LocalR
         const int m_first = a_exgl ? a_left + 1 : a_left;
         for (int m0 = m_first; m0 <= a_right; ) {
-            int m9 = min(m0 + 31, a_right);
+            int m9 = min(m0 + NT - 1, a_right);
             int ia = (m0 - a_left + intvl - 1) / intvl - 1;
             if (ia < 0) ia = 0;
             const int mi_a = ia < n_im ? MI(ia) : INT_MAX;
@@ -384,17 +396,23 @@ dp_hxudh_kernel(const DevNgHParams* __restrict__ gP, const DevUdhHTask* __restri
                     e1[q] = st[1]; e2[q] = st[3];
                     q = qn;
                 }
-                __syncwarp();
+                sync_problem();
             }
-            {
+            if (NW == 1) {
                 const unsigned who = __ballot_sync(FULL, is_imd);
                 if (who) {
                     const int src = __ffs(who) - 1;
                     rl0 = __shfl_sync(FULL, rl[0], src); rl1 = __shfl_sync(FULL, rl[1], src); rl2 = __shfl_sync(FULL, rl[2], src);
                 }
+            } else {
+                if (threadIdx.x == 0) { s_rl[0] = rl0; s_rl[1] = rl1; s_rl[2] = rl2; }
+                __syncthreads();
+                if (is_imd) { s_rl[0] = rl[0]; s_rl[1] = rl[1]; s_rl[2] = rl[2]; }
+                __syncthreads();
+                rl0 = s_rl[0]; rl1 = s_rl[1]; rl2 = s_rl[2];
             }
             __threadfence_block();
-            __syncwarp();
+            sync_problem();
             m0 = m9 + 1;
         }
 
@@ -409,6 +427,20 @@ dp_hxudh_kernel(const DevNgHParams* __restrict__ gP, const DevUdhHTask* __restri
                 if (ov > bval || (ov == bval && ov > HNG_NEVSEL && (omr < bmr || (omr == bmr && onr < bnr)))) {
                     bval = ov; bupr = ou; blwr = ol; bml = om; bulk = ok; bmr = omr; bnr = onr;
                 }
+            }
+            if (NW > 1) {
+                if ((threadIdx.x & 31) == 0) {
+                    int* b = s_best[threadIdx.x >> 5];
+                    b[0] = bval; b[1] = bupr; b[2] = blwr; b[3] = bml; b[4] = bulk; b[5] = bmr; b[6] = bnr;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0)
+                    for (int w = 1; w < NW; ++w) {
+                        const int* b = s_best[w];
+                        if (b[0] > bval || (b[0] == bval && b[0] > HNG_NEVSEL && (b[5] < bmr || (b[5] == bmr && b[6] < bnr)))) {
+                            bval = b[0]; bupr = b[1]; blwr = b[2]; bml = b[3]; bulk = b[4]; bmr = b[5]; bnr = b[6];
+                        }
+                    }
             }
         }
         if (lane == 0) {
@@ -533,7 +565,7 @@ dp_hxudh_kernel(const DevNgHParams* __restrict__ gP, const DevUdhHTask* __restri
             o.pad0 = o.pad1 = 0;
             results[ti] = o;
         }
-        __syncwarp();
+        sync_problem();
     }
 }
 
