@@ -170,5 +170,94 @@ for fixture in ("prot_A2_global", "prot_A2_local") if ONLY in ("", "prot") else 
         report(f"{fixture} lspH_ng -V{vmf >> 10}K", bad, N)
     eng.close()
 
+EOU = 2 ** 31 - 1 - 2
+
+
+def sudh_equal(r, o):
+    """scalar Hirschberg pass: score; ranges and crossing records (with their diagonal bounds) if a path exists"""
+    if r.status or r.score != o["score"]:
+        return False
+    if r.score <= -(1 << 28):
+        return True
+    if list(r.ranges) != o["ranges"]:
+        return False
+    for ra, rb in zip(r.cpos[: len(o["cpos"])].tolist(), o["cpos"].tolist()):
+        ka = ra.index(EOU) if EOU in ra[:8] else 8
+        kb = rb.index(EOU) if EOU in rb[:8] else 8
+        if ra[:ka] != rb[:kb] or (ka > 0 and ra[8:] != rb[8:]):
+            return False
+    return True
+
+
+# ---- the reference's default mode -A0: scalar Hirschberg passes and the drivers with alg = 0
+for fixture in ("dna_A0_udh", "dna_A0_udh_local", "dna_A0_udh_dagp") if ONLY in ("", "a0", "dna_a0") else ():
+    prm, _ = golden_io.load(fixture)
+    rng = np.random.default_rng(SEED * 1000 + 29 + hash(fixture) % 997)
+    probs = [dna_problem(prm, rng, i) for i in range(N)]
+    P = [Problem.from_export(pb, pb["lw"], pb["up"]) for pb in probs]
+    eng = Engine(prm, device=0)
+    sel = [i for i, pb in enumerate(probs) if pb["a_right"] - pb["a_left"] >= 12]
+    PU = [Problem.from_export(probs[i], probs[i]["lw"], probs[i]["up"]) for i in sel]
+    want = []
+    for i, p in zip(sel, PU):
+        m = probs[i]["a_right"] - probs[i]["a_left"]
+        p.n_imd = int(rng.integers(1, max(2, min(9, m // 5))))
+        intvl = (m + p.n_imd) // (p.n_imd + 1)
+        nq = p.n_imd - 1 if intvl * p.n_imd == m else p.n_imd
+        want.append(O.hirschberg_ng(prm, probs[i], nq, intvl) if nq >= 1 else None)
+    bad = [i for i, r, o in zip(sel, eng.hirschbergS_ng(PU), want) if o is not None and not sudh_equal(r, o)]
+    report(f"{fixture} hirschbergS_ng", bad, len(sel))
+    for vmf in (1 << 17, 1 << 20, 1 << 25):
+        rl = eng.lspS_ng(P, max_vmf_space=vmf, sh=int(prm["sh"]), alg=0)
+        bad = []
+        for i, (pb, r) in enumerate(zip(probs, rl)):
+            o = O.lsp(prm, pb, cap=1 << 17, max_vmf_space=vmf)
+            if o["unsupported"]:
+                if r.status != 3:
+                    bad.append(i)
+            elif r.status or r.score != o["score"] or not np.array_equal(r.skl, o["skl"]):
+                bad.append(i)
+        report(f"{fixture} lspS_ng alg 0 -V{vmf >> 10}K", bad, N)
+    eng.close()
+
+for fixture in ("prot_A0_udh", "prot_A0_udh_local") if ONLY in ("", "a0", "prot_a0") else ():
+    prm, _ = golden_io.load_protein(fixture)
+    rng = np.random.default_rng(SEED * 1000 + 31 + hash(fixture) % 997)
+    probs = [prot_problem(prm, rng, i) for i in range(N)]
+    for pb in probs:
+        pb["int53"] = workload.synthetic_int53(workload.encode_dna(pb["genome"]))
+    P = [ProblemH.from_export(pb, pb["lw"], pb["up"]) for pb in probs]
+    eng = EngineH(prm, device=0)
+    rn = eng.forwardH_ng(P)
+    bad = []
+    for i, (pb, r) in enumerate(zip(probs, rn)):
+        o = O.trcbk_h_ng(prm, pb, cap=1 << 17)
+        if r.status or r.score != o["score"] or not np.array_equal(r.skl, o["skl"]):
+            bad.append(i)
+    report(f"{fixture} forwardH_ng", bad, N)
+    sel = [i for i, pb in enumerate(probs) if pb["a_right"] - pb["a_left"] >= 12]
+    PU = [ProblemH.from_export(probs[i], probs[i]["lw"], probs[i]["up"]) for i in sel]
+    want = []
+    for i, p in zip(sel, PU):
+        m = probs[i]["a_right"] - probs[i]["a_left"]
+        p.n_imd = int(rng.integers(1, max(2, min(9, m // 5))))
+        intvl = (m + p.n_imd) // (p.n_imd + 1)
+        nq = p.n_imd - 1 if intvl * p.n_imd == m else p.n_imd
+        want.append(O.hirschberg_h_ng(prm, probs[i], nq, intvl) if nq >= 1 else None)
+    bad = [i for i, r, o in zip(sel, eng.hirschbergH_ng(PU), want) if o is not None and not sudh_equal(r, o)]
+    report(f"{fixture} hirschbergH_ng", bad, len(sel))
+    for vmf in (1 << 17, 1 << 19, 1 << 25):
+        rl = eng.lspH_ng(P, max_vmf_space=vmf, sh=int(prm["sh"]), alg=0)
+        bad = []
+        for i, (pb, r) in enumerate(zip(probs, rl)):
+            o = O.lsp_h(prm, pb, cap=1 << 17, max_vmf_space=vmf)
+            if o["unsupported"]:
+                if r.status != 3:
+                    bad.append(i)
+            elif r.status or r.score != o["score"] or not np.array_equal(r.skl, o["skl"]):
+                bad.append(i)
+        report(f"{fixture} lspH_ng alg 0 -V{vmf >> 10}K", bad, N)
+    eng.close()
+
 print("TOTAL mismatches:", bad_total)
 sys.exit(1 if bad_total else 0)
