@@ -153,27 +153,31 @@ def gather_hit_records(hits: np.ndarray, corners: np.ndarray, dst: int = 0, devi
     cnts = torch.zeros(2 * world, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(cnts, cnt)
     cnts = cnts.cpu().numpy().reshape(world, 2)
-    max_h, max_c = max(int(cnts[:, 0].max()), 1), max(int(cnts[:, 1].max()), 1)
+    max_h, max_c = int(cnts[:, 0].max()), int(cnts[:, 1].max())
     hw = HIT_DTYPE.itemsize // 4
-    # one padded block per rank, received as the rows of ONE tensor and copied to the host once
-    hsrc = np.zeros(max_h * hw, np.int32)
-    hsrc[: len(hits) * hw] = hits.view(np.int32).reshape(-1)
-    csrc = np.zeros(max_c * 2, np.int32)
-    csrc[: len(corners) * 2] = corners.reshape(-1)
-    hbuf = torch.from_numpy(hsrc).to(dev)
-    cbuf = torch.from_numpy(csrc).to(dev)
-    hall = torch.empty((world, max_h * hw), dtype=torch.int32, device=dev) if rank == dst else None
-    call = torch.empty((world, max_c * 2), dtype=torch.int32, device=dev) if rank == dst else None
-    dist.gather(hbuf, list(hall.unbind(0)) if rank == dst else None, dst)
-    dist.gather(cbuf, list(call.unbind(0)) if rank == dst else None, dst)
+    hbuf = torch.zeros(max(max_h, 1) * hw, dtype=torch.int32, device=dev)
+    cbuf = torch.zeros(max(max_c, 1) * 2, dtype=torch.int32, device=dev)
+    if len(hits):
+        hbuf[: len(hits) * hw] = torch.from_numpy(hits.view(np.int32).reshape(-1))
+    if len(corners):
+        cbuf[: len(corners) * 2] = torch.from_numpy(corners.reshape(-1))
+    hall = [torch.empty_like(hbuf) for _ in range(world)] if rank == dst else None
+    call = [torch.empty_like(cbuf) for _ in range(world)] if rank == dst else None
+    dist.gather(hbuf, hall, dst)
+    dist.gather(cbuf, call, dst)
     if rank != dst:
         return None
-    H = hall.cpu().numpy().reshape(world, max_h, hw)
-    Cn = call.cpu().numpy().reshape(world, max_c, 2)
-    h = H[np.arange(max_h)[None, :] < cnts[:, :1]].view(HIT_DTYPE).reshape(-1)
-    c = Cn[np.arange(max_c)[None, :] < cnts[:, 1:2]]
-    base = np.concatenate([[0], np.cumsum(cnts[:, 1])[:-1]])
-    h["skl_off"] += np.repeat(base, cnts[:, 0]).astype(np.int32)
+    hs, cs = [], []
+    base = 0
+    for r in range(world):
+        nh, nc = int(cnts[r, 0]), int(cnts[r, 1])
+        h = hall[r][: nh * hw].cpu().numpy().view(HIT_DTYPE).copy()
+        h["skl_off"] += base
+        base += nc
+        hs.append(h)
+        cs.append(call[r][: nc * 2].cpu().numpy().reshape(-1, 2))
+    h = np.concatenate(hs) if hs else np.zeros(0, HIT_DTYPE)
+    c = np.concatenate(cs) if cs else np.zeros((0, 2), np.int32)
     order = np.argsort(h["Rid"], kind="stable")
     return h[order], c
 
