@@ -87,11 +87,14 @@ __device__ __forceinline__ int ux_val(const UxCell (&st)[5], int k)
     return v;
 }
 
+#ifndef GSPALN_XUDH_MINB
+#define GSPALN_XUDH_MINB 2               // CTAs of the wide class per SM the register budget is cut for
+#endif
 constexpr int XUDH_WIDE = 8;            // warps per problem of the wide class
 constexpr int XUDH_WIDE_ROWS = 128;     // queries with at least this many rows run in the wide class
 
 template <int NW>
-__global__ void __launch_bounds__(NW == 1 ? NG_THREADS : 32 * NW)
+__global__ void __launch_bounds__(NW == 1 ? NG_THREADS : 32 * NW, NW == 1 ? 1 : GSPALN_XUDH_MINB)
 dp_xudh_kernel(const DevParams* __restrict__ gP, const short* __restrict__ tabs, int n_pen,
                const DevTask* __restrict__ tasks, const int* __restrict__ order, int ntasks, int* ticket,
                const unsigned char* __restrict__ apool, const ColInfo* __restrict__ cpool,
