@@ -858,8 +858,16 @@ constexpr int ST_NEED_EXACT = 6;
 // for problems that can fill such a chain, 4 / 2 / 1 (8 / 4 / 2 slots) for problems whose band or
 // row count allows fewer strips in flight -- the host assigns the class (DevTask::pad0) so that a
 // thin or narrow problem still keeps all 32 lanes of its warp busy.
+// CTAs per SM the register budget of the packed kernels is cut for.  Measured on B200 (config 2):
+// NP = 8 at 2 / 3 / 4 CTAs per SM (204 / 168 / 128 registers, the last with spills): 472 / 515 / 319 GCUPS
+#ifndef GSPALN_PK8_MINB
+#define GSPALN_PK8_MINB 3
+#endif
+#ifndef GSPALN_PK4_MINB
+#define GSPALN_PK4_MINB 3
+#endif
 template <bool TRACE, bool LOCAL, bool SPJ, bool DAGP, int PK = 0, int NRT = 8>
-__global__ void __launch_bounds__(CTA_THREADS, PK == 8 ? 2 : 3)
+__global__ void __launch_bounds__(CTA_THREADS, PK == 8 ? GSPALN_PK8_MINB : (PK == 4 ? GSPALN_PK4_MINB : 3))
 dp_wip_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
               const DevTask* __restrict__ tasks,
               const int* __restrict__ order, int ntasks, int* ticket,

@@ -91,7 +91,10 @@ class PackedBatch:
     """Task descriptors marshalled once (the sequence / signal buffers stay host numpy
     arrays and are packed + copied to the device by every submit) plus a flat result area."""
 
-    def __init__(self, arr, keep, n):
+    def __init__(self, arr, keep, n, reuse=None):
+        """reuse: a PackedBatch of an earlier call whose result area (corner pool, result records) is
+        taken over if it is large enough -- what a caller that submits batch after batch does instead
+        of faulting in tens of MB of fresh pages per batch"""
         self.arr, self.keep, self.n = arr, keep, n
         if isinstance(arr, np.ndarray):     # descriptors built with array operations (pack_global)
             caps = arr["skl_cap"][:n].astype(np.int64)
@@ -100,8 +103,13 @@ class PackedBatch:
         else:
             caps = np.array([arr[i].skl_cap for i in range(n)], np.int64)
         self.off = np.concatenate([[0], np.cumsum(caps)])
-        self.skl = np.zeros((max(int(self.off[-1]), 1), 2), np.int32)
-        self.res = np.zeros(max(n, 1), _RESULT_DTYPE)
+        need = max(int(self.off[-1]), 1)
+        if reuse is not None and len(reuse.skl) >= need and len(reuse.res) >= max(n, 1):
+            self.skl, self.res = reuse.skl, reuse.res
+            self.res[:] = 0
+        else:
+            self.skl = np.zeros((need, 2), np.int32)
+            self.res = np.zeros(max(n, 1), _RESULT_DTYPE)
         self.res["skl"][:n] = self.skl.ctypes.data + 8 * self.off[:-1].astype(np.uint64)
         self.res["skl"][:n][caps == 0] = 0
 
@@ -241,7 +249,7 @@ class Engine:
         self._check(self.lib.gspaln_submit(self._h, batch.arr, batch.n, res), "gspaln_submit")
         return batch
 
-    def pack_global(self, g: dict, index, kind=capi.FORWARD_WIP, skl_cap=512, sh=100) -> PackedBatch:
+    def pack_global(self, g: dict, index, kind=capi.FORWARD_WIP, skl_cap=512, sh=100, reuse=None) -> PackedBatch:
         """Task descriptors of the problems `index` of a flat query set (the layout of
         workload.config2_global: concatenated query / genome codes and per-column tables plus a
         length table), filled with array operations: what a caller that keeps its sequences in
@@ -270,7 +278,7 @@ class Engine:
         t["up"] = np.minimum(up + sh, lb)
         t["lw"] = np.maximum(lw - sh, -la)
         t["skl_cap"] = skl_cap if kind in (capi.FORWARD_WIP, capi.FORWARD_NG) else 0
-        return PackedBatch(arr, g, n)
+        return PackedBatch(arr, g, n, reuse)
 
     def forwardS1_wip(self, problems):
         return self.submit(problems, capi.FORWARD_WIP)
