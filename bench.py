@@ -808,7 +808,9 @@ def shape_job(args, cfg, rank, local_rank, world, ncores):
         bad = int(np.count_nonzero(packed.status))
         return tm, got, bad, (t1 - t0, t2 - t1, t3 - t2)
 
-    run_once() if len(problems) <= 2000 else (eng.submit(problems[:64]) if cfg == 3 else eng.lspS_ng(problems[:64], **lsp_opts))
+    # warm-up: one whole untimed step, so that the grow-only pools (pinned staging of the whole batch,
+    # device pools) have their size before the clock starts -- as in the config-2 job
+    run_once()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
