@@ -250,6 +250,8 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
             int rc = TR::submit(ctx, batch.data(), (int) batch.size(), bres.data());
             if (rc != GSPALN_OK) return rc;
             t_submit += msec(t1, now());
+            if (dbg) fprintf(stderr, "gspaln lsp: level of %zu tasks (%zu Hirschberg passes): %.1f ms, kernels %.1f ms, %.3g cells\n",
+                             batch.size(), udh_items.size(), msec(t1, now()), ctx->tim.kernel_ms, (double) ctx->tim.cells);
             kernel_ms += ctx->tim.kernel_ms; h2d_ms += ctx->tim.h2d_ms; d2h_ms += ctx->tim.d2h_ms;
             launches += ctx->tim.launches; h2d_bytes += ctx->tim.h2d_bytes; d2h_bytes += ctx->tim.d2h_bytes;
             cells_total += ctx->tim.cells;
@@ -374,6 +376,8 @@ int lsp_driver(typename TR::Ctx* ctx, const typename TR::Task* tasks, int n,
             int rc = TR::submit(ctx, b2.data(), (int) b2.size(), r2.data());
             if (rc != GSPALN_OK) return rc;
             t_submit += msec(t3, now());
+            if (dbg) fprintf(stderr, "gspaln lsp: %zu block trace-backs: %.1f ms, kernels %.1f ms, %.3g cells\n",
+                             b2.size(), msec(t3, now()), ctx->tim.kernel_ms, (double) ctx->tim.cells);
             kernel_ms += ctx->tim.kernel_ms; h2d_ms += ctx->tim.h2d_ms; d2h_ms += ctx->tim.d2h_ms;
             launches += ctx->tim.launches; h2d_bytes += ctx->tim.h2d_bytes; d2h_bytes += ctx->tim.d2h_bytes;
             cells_total += ctx->tim.cells;
