@@ -82,6 +82,7 @@ struct gspaln_ctx {
     size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, skl_elems = 0;
     size_t udh_slab = 0, cpos_elems = 0;
     int grid_run_trace = 0, grid_run_score = 0, grid_run_udh = 0, grid_udh = 0;
+    int n_udh_t = 0, grid_run_udh_t = 0, grid_udh_t = 0;   // Hirschberg passes of the team class (a CTA per problem)
     std::vector<int64_t> cells;
     std::vector<int> skl_cap;
     gspaln_timing tim;
@@ -187,6 +188,14 @@ UdhKernelFn udh_kernel_fn(bool spj, bool local)
 {
     static const UdhKernelFn tab[4] = {dp_udh_kernel<false, false>, dp_udh_kernel<true, false>,
                                        dp_udh_kernel<false, true>, dp_udh_kernel<true, true>};
+    return tab[(local ? 2 : 0) | (spj ? 1 : 0)];
+}
+
+// the team class: one CTA per problem (queries of >= UDH_TEAM_ROWS rows)
+UdhKernelFn udh_team_kernel_fn(bool spj, bool local)
+{
+    static const UdhKernelFn tab[4] = {dp_udh_kernel<false, false, WARPS_PER_CTA>, dp_udh_kernel<true, false, WARPS_PER_CTA>,
+                                       dp_udh_kernel<false, true, WARPS_PER_CTA>, dp_udh_kernel<true, true, WARPS_PER_CTA>};
     return tab[(local ? 2 : 0) | (spj ? 1 : 0)];
 }
 
@@ -338,6 +347,10 @@ int gspaln_create(gspaln_ctx** out, const gspaln_params* prm, int device)
         cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_bytes);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ku, CTA_THREADS, ctx->smem_bytes);
         ctx->grid_udh = std::max(1, occ) * ctx->sm_count;
+        const void* kt = reinterpret_cast<const void*>(udh_team_kernel_fn(P.spj, P.local));
+        cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_bytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kt, CTA_THREADS, ctx->smem_bytes);
+        ctx->grid_udh_t = std::max(1, occ) * ctx->sm_count;
     }
     if (!dagp)
         for (int c = 0; c < 3; ++c) {
@@ -455,6 +468,26 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
     size_t a_bytes = 0, c_elems = 0, band_slab = 0, trace_slab = 0, skl_elems = 0;
     size_t udh_slab = 0, cpos_elems = 0;
     int n_trace = 0, n_score = 0, n_udh = 0, n_ng = 0, n_ngs = 0, n_xudh = 0, n_xudh_w = 0, n_ng_w = 0, n_ngs_w = 0;
+    int n_udh_t = 0;
+    // Hirschberg passes: the long queries (>= UDH_TEAM_ROWS rows) get a CTA (team of warps) each
+    // instead of one warp when the batch could not keep every warp of the device busy for as long as
+    // its largest problem would take on one warp -- with more than a warp's fair share of the batch's
+    // cells that problem would be the tail of the launch.  In a saturated batch one warp per problem
+    // is the faster form (no CTA barrier per step), and the two classes run one after the other, so
+    // it is all of the long queries or none.
+    // GSPALN_UDH_TEAM_ROWS=r puts every pass of >= r rows in the team class (tests, tuning).
+    static const int team_rows_env = getenv("GSPALN_UDH_TEAM_ROWS") ? atoi(getenv("GSPALN_UDH_TEAM_ROWS")) : 0;
+    const int udh_team_rows = team_rows_env > 0 ? team_rows_env : UDH_TEAM_ROWS;
+    int64_t udh_team_cells = 0;
+    if (team_rows_env <= 0) {
+        int64_t total = 0, largest = 0;
+        for (int i = 0; i < n; ++i)
+            if (tasks[i].kind == GSPALN_HIRSCHBERG_WIP) {
+                total += ctx->cells[i];
+                if (tasks[i].a_right - tasks[i].a_left >= udh_team_rows) largest = std::max(largest, ctx->cells[i]);
+            }
+        if (largest <= total / (int64_t) std::max(1, ctx->grid_udh * WARPS_PER_CTA)) udh_team_cells = INT64_MAX;
+    }
     size_t ng_width = 0, ng_rec = 0, ngs_width = 0, xudh_width = 0, xudh_links = 0;
     int n_trace_c[3] = {0, 0, 0}, n_score_c[3] = {0, 0, 0};
     size_t band_slab_c[3] = {0, 0, 0}, trace_slab_c[3] = {0, 0, 0};
@@ -522,7 +555,8 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             cpos_elems += (size_t) 10 * (t.n_imd + 1);
             udh_slab = std::max(udh_slab, align_up(4 * ((size_t) width + 2 * NELEM + 2) +
                                                    (size_t) t.n_imd * 4 * width + 8, 64));
-            ++n_udh;
+            if (mw >= udh_team_rows && ctx->cells[i] > udh_team_cells) { d.flags |= 32; ++n_udh_t; }   // a CTA per problem
+            else ++n_udh;
         } else if (cls == 8)
             ++n_score;
         else
@@ -564,6 +598,8 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
         const size_t budget = (size_t) (0.85 * (double) free_b);
         while (gt > 1 && (size_t) gt * WARPS_PER_CTA * (trace_slab + band_slab * 8) > budget) gt = gt * 3 / 4;
         int gu = n_udh ? ctas(ctx->grid_udh, n_udh) : 0;
+        const int gut = std::min(ctx->grid_udh_t, n_udh_t);
+        gu = std::max(gu, gut);                             // the two classes share the per-warp slabs
         const size_t warps = (size_t) std::max(std::max(gt, gs), gu) * WARPS_PER_CTA;
         // the narrower chain classes share the pools (the kernels run one after the other)
         size_t band_words = warps * band_slab * (ctx->prm.noll == 3 ? 2 : 1);
@@ -582,7 +618,8 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             cudaGetLastError();
             return fail(ctx, GSPALN_ENOMEM, "device UDH workspace allocation");
         }
-        ctx->grid_run_udh = gu;
+        ctx->grid_run_udh = n_udh ? ctas(ctx->grid_udh, n_udh) : 0;
+        ctx->grid_run_udh_t = gut;
         if (ctx->d_band.reserve(band_words + 32) != cudaSuccess ||
             ctx->d_trace.reserve(trace_bytes + 256) != cudaSuccess) {
             cudaGetLastError();
@@ -623,7 +660,7 @@ static int plan_batch(gspaln_ctx* ctx, const gspaln_task* tasks, int n)
             ctx->xudh_width = xudh_width;
         }
     }
-    ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score; ctx->n_udh = n_udh; ctx->n_ng = n_ng;
+    ctx->n = n; ctx->n_trace = n_trace; ctx->n_score = n_score; ctx->n_udh = n_udh; ctx->n_udh_t = n_udh_t; ctx->n_ng = n_ng;
     ctx->n_ngs = n_ngs; ctx->n_xudh = n_xudh; ctx->n_xudh_w = n_xudh_w; ctx->n_ng_w = n_ng_w; ctx->n_ngs_w = n_ngs_w;
     ctx->udh_slab = udh_slab; ctx->cpos_elems = cpos_elems;
     ctx->a_bytes = a_bytes; ctx->c_elems = c_elems; ctx->band_slab = band_slab;
@@ -768,6 +805,14 @@ static int launch_range(gspaln_ctx* ctx, int lo, int hi, int slot, int& launches
             ++launches;
         }
     }
+    if (ctx->n_udh_t) {
+        auto kt = udh_team_kernel_fn(spj, local);
+        kt<<<ctx->grid_run_udh_t, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
+            ctx->d_prm.p, ctx->d_pen.p, ctx->d_tasks.p, ctx->d_order.p + lo, cnt, tick + 3,
+            ctx->d_apool.p, ctx->d_cpool.p, ctx->d_band.p, (long long) ctx->band_slab,
+            ctx->d_udh.p, (long long) ctx->udh_slab, ctx->d_cpos.p, ctx->d_ures.p, ready);
+        ++launches;
+    }
     if (ctx->n_udh) {
         auto ku = udh_kernel_fn(spj, local);
         ku<<<ctx->grid_run_udh, CTA_THREADS, ctx->smem_bytes, ctx->stream>>>(
@@ -874,7 +919,7 @@ int gspaln_download(gspaln_ctx* ctx, gspaln_result* results)
     if (n) CK(cudaMemcpyAsync(ctx->h_res.p, ctx->d_res.p, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (ctx->skl_elems)
         CK(cudaMemcpyAsync(ctx->h_skl.p, ctx->d_skl.p, sizeof(int2) * ctx->skl_elems, cudaMemcpyDeviceToHost, ctx->stream));
-    if (ctx->n_udh || ctx->n_xudh || ctx->n_xudh_w) {
+    if (ctx->n_udh || ctx->n_udh_t || ctx->n_xudh || ctx->n_xudh_w) {
         CK(cudaMemcpyAsync(ctx->h_ures.p, ctx->d_ures.p, sizeof(DevUdhOut) * n, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_cpos.p, ctx->d_cpos.p, sizeof(int) * ctx->cpos_elems, cudaMemcpyDeviceToHost, ctx->stream));
     }

@@ -142,15 +142,23 @@ struct UdhTaskView {
     int n_imd, n_active, mm0;
 };
 
-template <bool SPJ, bool LOCAL>
+// NW = warps per problem.  NW == 1: every warp of the CTA runs its own problem, SPPU strips per
+// pass.  NW == WARPS_PER_CTA (the "team" class, queries of >= UDH_TEAM_ROWS rows): the CTA runs
+// one problem with NW * SPPU strips per pass on one systolic chain -- the strips of different
+// warps meet only through the band buffer, exactly as the strips of one warp do, so the only
+// change is that the per-step barrier is the CTA's; `tsm` is the team's scratch in shared memory.
+template <int NW>
+__device__ __forceinline__ void team_sync() { if (NW == 1) __syncwarp(); else __syncthreads(); }
+
+template <bool SPJ, bool LOCAL, int NW>
 __device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
                              const DevTask& t, const UdhTaskView& uv,
                              const unsigned char* __restrict__ aseq,
                              const ColInfo* __restrict__ cols, unsigned* band,
                              int ml0, int nstr, int& rlst_io,
-                             bool localL, bool localL_now, bool localR, int accscr, UdhBest& wbest)
+                             bool localL, bool localL_now, bool localR, int accscr, UdhBest& wbest, int* tsm)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = NW == 1 ? (threadIdx.x & 31) : (int) threadIdx.x;     // lane of the problem's chain
     const int sidx = lane / TPSU;
     const int sub = lane % TPSU;
     const int row0 = sub * NRU;
@@ -160,11 +168,23 @@ __device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
     const bool live = sidx < nstr && nsteps > 0;
     const int width = t.up - t.lw + 3;
 
-    const int n_start0 = __shfl_sync(0xffffffffu, g.n_start, 0);
+    int n_start0;
+    if (NW == 1) n_start0 = __shfl_sync(0xffffffffu, g.n_start, 0);
+    else {
+        if (lane == 0) tsm[0] = g.n_start;
+        __syncthreads();
+        n_start0 = tsm[0];
+    }
     const int off = (g.n_start - n_start0) + (NELEM - 1 + LAG) * sidx;
     int niter = live ? off + nsteps : 0;
 #pragma unroll
     for (int o = 16; o; o >>= 1) niter = max(niter, __shfl_xor_sync(0xffffffffu, niter, o));
+    if (NW > 1) {
+        if ((lane & 31) == 0) tsm[1 + (lane >> 5)] = niter;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < NW; ++w) niter = max(niter, tsm[1 + w]);
+    }
     if (niter == 0) return;
 
     // Which intermediate row (if any) lies in this strip?  mi_i = a_left + mm0 (i + 1).
@@ -369,7 +389,7 @@ __device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
         } else {
             prev_uh = NEV; prev_uc = 0; prev_ub = 0;
         }
-        __syncwarp();
+        team_sync<NW>();
     }
     if (LOCAL && localR) {
         // reference order: strips ascending, then step, then lane (first max)
@@ -386,6 +406,20 @@ __device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
             const bool take = ov > bv || (ov == bv && (ot < bst || (ot == bst && (os < bs || (os == bs && ok < bkk)))));
             if (take) { bv = ov; bs = os; bkk = ok; bst = ot; bm = om; bu = ou; }
         }
+        if (NW > 1) {
+            // the warps of the team, same order
+            int* b = tsm + 8 + 6 * (lane >> 5);
+            if ((lane & 31) == 0) { b[0] = bv; b[1] = bs; b[2] = bkk; b[3] = bst; b[4] = bm; b[5] = bu; }
+            __syncthreads();
+            bv = tsm[8]; bs = tsm[9]; bkk = tsm[10]; bst = tsm[11]; bm = tsm[12]; bu = tsm[13];
+#pragma unroll
+            for (int w = 1; w < NW; ++w) {
+                const int* c = tsm + 8 + 6 * w;
+                const int ov = c[0], os = c[1], ok = c[2], ot = c[3];
+                const bool take = ov > bv || (ov == bv && (ot < bst || (ot == bst && (os < bs || (os == bs && ok < bkk)))));
+                if (take) { bv = ov; bs = os; bkk = ok; bst = ot; bm = c[4]; bu = c[5]; }
+            }
+        }
         if (bv > INT_MIN && bv + accscr > wbest.val) {
             wbest.val = bv + accscr;
             wbest.ml = bm; wbest.ulk = bu;
@@ -399,7 +433,16 @@ __device__ void run_pass_udh(const DevParams& P, const SmemLayout& sm,
     int who = has_imd ? lane : -1;
 #pragma unroll
     for (int o = 16; o; o >>= 1) who = max(who, __shfl_xor_sync(0xffffffffu, who, o));
-    if (who >= 0) rlst_io = __shfl_sync(0xffffffffu, rlst, who);
+    if (NW == 1) {
+        if (who >= 0) rlst_io = __shfl_sync(0xffffffffu, rlst, who);
+    } else {
+        const int r = __shfl_sync(0xffffffffu, rlst, max(who, 0) & 31);
+        if ((lane & 31) == 0) { tsm[32 + 2 * (lane >> 5)] = who; tsm[33 + 2 * (lane >> 5)] = r; }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+            if (tsm[32 + 2 * w] >= 0) rlst_io = tsm[33 + 2 * w];     // ascending: the last one stays
+    }
 }
 
 struct DevUdhOut {                      // per problem
@@ -408,7 +451,9 @@ struct DevUdhOut {                      // per problem
     int pad0, pad1;
 };
 
-template <bool SPJ, bool LOCAL>
+constexpr int UDH_TEAM_ROWS = 512;      // queries with at least this many rows: a CTA (team of warps) per problem
+
+template <bool SPJ, bool LOCAL, int NW = 1>
 __global__ void __launch_bounds__(CTA_THREADS, 3)
 dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
               const DevTask* __restrict__ tasks, const int* __restrict__ order, int ntasks, int* ticket,
@@ -433,20 +478,33 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
     sm.mtx = sP.mtxT;
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
-    const long long wslot = (long long) blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    static_assert(NW == 1 || NW == WARPS_PER_CTA, "a team is the whole CTA");
+    constexpr int NT = 32 * NW;                             // lanes per problem
+    __shared__ int s_team[48];
+    int* tsm = s_team;
+    const int lane = NW == 1 ? (threadIdx.x & 31) : (int) threadIdx.x;
+    const long long wslot = (long long) blockIdx.x * WARPS_PER_CTA + (NW == 1 ? (threadIdx.x >> 5) : 0);
     unsigned* band = bandpool + wslot * band_slab;
     int* uslab = udhpool + wslot * udh_slab;
 
     for (;;) {
         int tk = 0;
-        if (lane == 0) tk = atomicAdd(ticket, 1);
-        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (NW == 1) {
+            if (lane == 0) tk = atomicAdd(ticket, 1);
+            tk = __shfl_sync(0xffffffffu, tk, 0);
+        } else {
+            __syncthreads();
+            if (lane == 0) tsm[44] = atomicAdd(ticket, 1);
+            __syncthreads();
+            tk = tsm[44];
+        }
         if (tk >= ntasks) break;
         const int ti = order[tk];
         const DevTask t = tasks[ti];
-        if (t.kind != 2) continue;
-        if (!wait_inputs(ready, tk)) {
+        if (t.kind != 2 || ((t.flags & 32) != 0) != (NW > 1)) continue;      // another kernel / class runs it
+        bool arrived = wait_inputs(ready, tk);
+        if (NW > 1) arrived = __syncthreads_and(arrived) != 0;
+        if (!arrived) {
             if (lane == 0) {
                 // inputs never arrived: no crossing records (the driver skips the post-work)
                 DevUdhOut r; memset(&r, 0, sizeof(r)); r.status = 4; r.score = INT_MIN / 16 * 7; results[ti] = r;
@@ -484,19 +542,19 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
         }
 
         // ---- fhinitS1: scores (src/fwd2s1_simd.cc:163-184) and links (205-238)
-        for (int i = lane; i < buf_size; i += 32) band[i] = pack16(NEV, NEV);
-        for (long long i = lane; i < (long long) n_imd * 4 * width; i += 32) uv.imd[i] = END_OF_ULK;
-        for (int i = lane; i <= n_imd; i += 32) { cpos[10 * i + 0] = END_OF_ULK; cpos[10 * i + 2] = END_OF_ULK; }
-        __syncwarp();
+        for (int i = lane; i < buf_size; i += NT) band[i] = pack16(NEV, NEV);
+        for (long long i = lane; i < (long long) n_imd * 4 * width; i += NT) uv.imd[i] = END_OF_ULK;
+        for (int i = lane; i <= n_imd; i += NT) { cpos[10 * i + 0] = END_OF_ULK; cpos[10 * i + 2] = END_OF_ULK; }
+        team_sync<NW>();
         {
             const int rl = t.b_left - t.a_left;
             const int ru = t.up + 2 * NELEM;
             int rr = t.b_right - t.a_left;
             if (t.up < rr) rr = t.up;
             if (b_exgl)
-                for (int r = t.lw + lane; r < rl; r += 32) band[r - t.lw + 1] = pack16(0, NEV);
+                for (int r = t.lw + lane; r < rl; r += NT) band[r - t.lw + 1] = pack16(0, NEV);
             if (a_exgl) {
-                for (int r = rl + lane; r <= rr; r += 32) band[r - t.lw + 1] = pack16(0, NEV);
+                for (int r = rl + lane; r <= rr; r += NT) band[r - t.lw + 1] = pack16(0, NEV);
             } else if (lane == 0) {
                 int r = rl;
                 int v = 0;
@@ -514,7 +572,7 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
             }
             // links: hc[r] = own diagonal along free ends, else the corner diagonal; fc = hc
             int2* bc = reinterpret_cast<int2*>(uv.bandc);
-            for (int i = lane; i < buf_size; i += 32) {
+            for (int i = lane; i < buf_size; i += NT) {
                 const int r = t.lw - 1 + i;
                 int v;
                 if (r < rl) v = b_exgl ? r : rl;
@@ -531,7 +589,7 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
             }
         }
         __threadfence_block();
-        __syncwarp();
+        team_sync<NW>();
 
         int accscr = 0;
         const int md = checkpoint(P.avmch, 0);
@@ -539,23 +597,37 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
         int rlst = INT_MAX;
         UdhBest wbest{NEV, END_OF_ULK, t.a_left, t.a_right, t.b_right};
         int ml0 = t.a_left;
+        // strips per pass: the chain's length, evened out over the passes the query needs
+        int sppu = SPPU * NW;
+        if (NW > 1) {
+            const int strips = (t.a_right - t.a_left + NELEM - 1) / NELEM;
+            const int passes = (strips + sppu - 1) / sppu;
+            sppu = (strips + passes - 1) / passes;
+        }
         while (ml0 < t.a_right) {
-            int nstr = min(SPPU, (t.a_right - ml0 + NELEM - 1) / NELEM);
+            int nstr = min(sppu, (t.a_right - ml0 + NELEM - 1) / NELEM);
             if (mc >= ml0 && mc < ml0 + nstr * NELEM && ((mc - ml0) % NELEM) == 0)
                 nstr = (mc - ml0) / NELEM + 1;
-            run_pass_udh<SPJ, LOCAL>(P, sm, t, uv, aseq, cols, band, ml0, nstr, rlst,
-                                     LocalL, LocalL && !accscr, LocalR, accscr, wbest);
+            run_pass_udh<SPJ, LOCAL, NW>(P, sm, t, uv, aseq, cols, band, ml0, nstr, rlst,
+                                         LocalL, LocalL && !accscr, LocalR, accscr, wbest, tsm);
             const int last_ml = ml0 + (nstr - 1) * NELEM;
             if (last_ml == mc) {
+                team_sync<NW>();
                 const int nmax = t.up - t.lw;
                 int cm = lo16(__ldcg(band + 1));
-                for (int i = lane; i < nmax; i += 32) cm = max(cm, lo16(__ldcg(band + 1 + i)));
+                for (int i = lane; i < nmax; i += NT) cm = max(cm, lo16(__ldcg(band + 1 + i)));
 #pragma unroll
                 for (int o = 16; o; o >>= 1) cm = max(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+                if (NW > 1) {
+                    if ((lane & 31) == 0) tsm[40 + (lane >> 5)] = cm;
+                    __syncthreads();
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) cm = max(cm, tsm[40 + w]);
+                }
                 const int d = checkpoint(P.avmch, cm);
                 if (d < md / 2) {
                     const int nn = width / NELEM * NELEM;
-                    for (int i = lane; i < width; i += 32) {
+                    for (int i = lane; i < width; i += NT) {
                         const unsigned w = __ldcg(band + i);
                         int h = lo16(w) - cm, f = hi16(w) - cm;
                         if (i < nn) { h = sat16(h); f = sat16(f); }
@@ -566,12 +638,12 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
                     mc += md;
                 } else
                     mc += d;
-                __syncwarp();
+                team_sync<NW>();
             }
             ml0 += nstr * NELEM;
         }
         __threadfence_block();
-        __syncwarp();
+        team_sync<NW>();
 
         // ---- fhlastS1 with links (src/fwd2s1_simd.cc:241-262) ...
         const int rr = t.b_right - t.a_right;
@@ -590,7 +662,7 @@ dp_udh_kernel(const DevParams* __restrict__ gP, const int2* __restrict__ gpen,
             }
             return n <= 0 ? from : bi;
         };
-        if (!LocalR) {
+        if (!LocalR && (NW == 1 || threadIdx.x < 32)) {     // (a team leaves the end point to its first warp)
             if (a_exgr) {
                 const int r = max(t.lw, t.b_left - t.a_right);
                 maxr = argmax(r, rr - r);
