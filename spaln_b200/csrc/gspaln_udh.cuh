@@ -15,6 +15,12 @@
 // with NRU = 4 rows per thread (4 threads per strip, 8 strips per pass) to keep
 // the doubled per-row state in registers.  The band buffer carries a second
 // word pair {H link, F link} per diagonal.
+//
+// Two classes: one warp per problem (a CTA runs four problems), and -- for long
+// queries in batches too small to keep every warp busy, where the largest
+// problem on one warp would be the whole launch -- a CTA per problem (NW = 4:
+// 32 strips per pass on one chain, the CTA barrier per step; see team_sync).
+// The host chooses per batch (gspaln.cu, plan_batch).
 #pragma once
 #include "gspaln_kernels.cuh"
 
